@@ -1,0 +1,201 @@
+/*
+ * song_los.h -- C-ABI of the B200 line-of-sight (LOS) engine behind SONG's transfer2 module.
+ *
+ * This is the "thin C-ABI layer" between SONG's host C code and the CUDA kernels: plain C,
+ * plain pointers and sizes, no CUDA or torch types.  The drop-in host module
+ * (song_b200/host/transfer2_gpu.c) implements SONG's own module API -- transfer2_init() and
+ * friends, reference include/transfer2.h:327-541 -- on top of these entry points; bessel2_gpu.c
+ * does the same for the projection-function tables (reference include/bessel2.h:161-260).
+ *
+ * What each entry point replaces in the reference (coccoinomane/song @ 2ea44ecf):
+ *
+ *   song_los_create            per-run state built at transfer2.c:128-281 (tau0, workspaces) and
+ *                              the index tables of transfer2_indices_of_transfers, :866-1067
+ *   song_los_set_projection    consumes pbs2->J_Llm_x / index_xmin_J / x_size_J as filled by
+ *                              bessel2_init, bessel2.c:315-374 (ragged -> dense device table)
+ *   song_los_build_projection  the J_Llm(x) assembly itself, bessel2_J_for_Llm + bessel2_J_Llm,
+ *                              bessel2.c:1041-1588, from a host j_l1 table and host 3j symbols
+ *   song_los_get_projection    writes the device-built tables back in bessels2 layout
+ *   song_los_upload_pairs      the inputs of the (k1,k2) loop body: ppt2->k3[k1][k2],
+ *                              ppt2->sources[tp][k1][k2] (transfer2.h:47-51 layout) and the fine
+ *                              grid of transfer2_get_k3_list, transfer2.c:1566-1737
+ *   song_los_compute           transfer2.c:401-539 for every uploaded pair: k3 spline
+ *                              (transfer2_interpolate_sources_in_k :2612), time grid (:2366),
+ *                              time interpolation (:2783) and every transfer2_compute /
+ *                              transfer2_integrate call (:1861, :2140)
+ *   song_los_download          ptr2->transfer[tt][k1][k2][k3] for the uploaded pairs, in the
+ *                              [tt][k1][k2][k3] order of transfers_%03d.dat (transfer2.c:2940-2957)
+ *   song_los_transfer_pairs    upload + compute + download in one call with HOST buffers (the
+ *                              end-to-end path a SONG run takes)
+ *
+ * Error convention (reference: _SUCCESS_/_FAILURE_ + ErrorMsg): every function
+ * returns SONG_LOS_SUCCESS (0) or SONG_LOS_FAILURE (1); the text is available from
+ * song_los_last_error() and is what the host module snprintf's into ptr2->error_message.
+ * There is NO CPU fallback: without a CUDA device every entry point fails.
+ */
+#ifndef SONG_LOS_H
+#define SONG_LOS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SONG_LOS_SUCCESS 0
+#define SONG_LOS_FAILURE 1
+
+/* mirrors of the reference enums, passed as ints */
+enum { SONG_LOS_TAU_SOURCES = 0, SONG_LOS_TAU_CUSTOM = 1, SONG_LOS_TAU_BESSEL = 2 }; /* transfer2.h:27-32 */
+enum { SONG_LOS_INTERP_LINEAR = 0, SONG_LOS_INTERP_CUBIC = 1 };
+enum { SONG_LOS_NO_K3_EXTRAPOLATION = 0, SONG_LOS_FLAT_K3_EXTRAPOLATION = 1 };
+enum { SONG_LOS_J_TT = 0, SONG_LOS_J_EE = 1, SONG_LOS_J_EB = 2 };                   /* bessel2.h:12-16 */
+
+/* Arithmetic mode of song_los_compute.
+   EXACT: one thread per (k3,l) walks tau and L in the reference's order with no FMA
+          contraction; bit-identical to the reference statement order (and to the oracle).
+   FAST : k3-sorted, register-tiled kernel; reassociates the L and tau sums and contracts FMAs
+          (max relative deviation ~1e-13 of the per-(l,m) maximum, tolerance stated in tests). */
+enum { SONG_LOS_MODE_EXACT = 0, SONG_LOS_MODE_FAST = 1 };
+
+/*
+ * Run-wide description.  Flattening of every [J][L][l][m] table (bessel2.h:64-91):
+ *     jidx = ((index_J*L_size + index_L)*l_size + index_l)*m_size + index_m
+ * Entries with |m| > min(L,l) are not allocated by the reference: pass NULL rows for them.
+ * All arrays are copied; the caller may free them after song_los_create returns.
+ */
+typedef struct song_los_config {
+  int device;                      /* CUDA device ordinal */
+
+  double tau0;                     /* pba->conformal_age, transfer2.c:128 */
+  int tau_size;                    /* ppt2->tau_size */
+  const double *tau_sampling;      /* ppt2->tau_sampling */
+  int tau_sampling_mode;           /* ptr2->tau_sampling */
+  double tau_linstep_song;         /* ppr2->tau_linstep_song (custom sampling only) */
+
+  int sources_k3_interpolation;    /* ppr2->sources_k3_interpolation */
+  int sources_time_interpolation;  /* ppr2->sources_time_interpolation */
+  int bessels_interpolation;       /* ppr->bessels_interpolation */
+  int k3_extrapolation;            /* ppr->bispectra_k3_extrapolation */
+
+  int xx_size;                     /* pbs2->xx_size */
+  const double *xx;                /* pbs2->xx (used verbatim: transfer2.c:2202) */
+  double xx_step;                  /* pbs2->xx_step */
+
+  int l_size;  const int *l;       /* ptr2->l */
+  int m_size;  const int *m;       /* ptr2->m */
+  int L_size;                      /* pbs2->L_size, L[i] = i */
+  int n_transfers;                 /* ptr2->n_transfers */
+  const int *lm_array;             /* ptr2->lm_array as [l_size][m_size], -1 where m > l */
+  const int *lm_src;               /* lm(L,m) of perturbations2_macros.h:53 as [L_size][m_size], -1 where m > L */
+
+  int has_source_T, has_source_E, has_source_B;     /* ppt2->has_source_X */
+  int index_tp2_T, index_tp2_E, index_tp2_B;        /* ppt2->index_tp2_X  */
+  int tp2_size;                                     /* ppt2->tp2_size     */
+  int l_max_los_t, l_max_los_p;                     /* ppr2->l_max_los_t/p */
+
+  int index_tt2_T, index_tt2_E, index_tt2_B;        /* ptr2->index_tt2_X  */
+  int tt2_size;                                     /* ptr2->tt2_size     */
+  const int *tt_index_l;           /* ptr2->corresponding_index_l [tt2_size] */
+  const int *tt_index_m;           /* ptr2->corresponding_index_m [tt2_size] */
+
+  int J_size;                      /* pbs2->J_size */
+  int index_J_TT, index_J_EE, index_J_EB;           /* -1 when the table is absent */
+} song_los_config;
+
+/* One batch of (k1,k2) pairs, packed.  Pair p:
+ *   coarse grid   k3_pt + pt_off[p],  k3_pt_size[p] doubles      (ppt2->k3[k1][k2])
+ *   sources       src + src_off[p] + tp*tau_size*np + itau*np + j (ppt2->sources[tp][k1][k2])
+ *   fine grid     k3_tr + tr_off[p],  k3_tr_size[p] doubles      (transfer2_get_k3_list)
+ *   physical range [phys_start[p], phys_start[p]+phys_size[p])   (ptr2->k_physical_*_k1k2)
+ * Output unit index of (p, i) is tr_off[p] + i; the transfer array is [tt2_size][n_units]. */
+typedef struct song_los_batch {
+  int n_pairs;
+  const int *k3_pt_size;
+  const int *k3_tr_size;
+  const int *phys_start;
+  const int *phys_size;
+  const int64_t *pt_off;
+  const int64_t *tr_off;
+  const int64_t *src_off;
+  int64_t n_pt_total;              /* sum of k3_pt_size */
+  int64_t n_units;                 /* sum of k3_tr_size */
+  int64_t n_src_total;             /* doubles in src */
+  const double *k3_pt;
+  const double *k3_tr;
+  const double *src;
+} song_los_batch;
+
+/* Device-side timings of the last song_los_compute, in milliseconds (CUDA events on the
+   engine's stream), plus exact work counters. */
+typedef struct song_los_timing {
+  float ms_total;
+  float ms_spline;                 /* k3 second derivatives (transfer2.c:2639)        */
+  float ms_sort;                   /* FAST: k3 ordering of the units                  */
+  float ms_interp;                 /* FAST: source interpolation into the sorted slab */
+  float ms_integrate;              /* the LOS kernel proper                           */
+  float ms_reorder;                /* FAST: [unit][tt] -> [tt][unit]                  */
+  int   n_launches;                /* kernels launched by the call                    */
+  int64_t n_integrals;             /* stored T values = n_units * tt2_size            */
+  int64_t n_terms_upper;           /* n_integrals * tau_size * (L_max+1) upper bound  */
+} song_los_timing;
+
+typedef struct song_los_ctx song_los_ctx;
+
+int  song_los_create(const song_los_config *cfg, song_los_ctx **ctx);
+int  song_los_destroy(song_los_ctx *ctx);
+const char *song_los_last_error(const song_los_ctx *ctx);   /* ctx may be NULL: last create error */
+
+/* ragged host tables -> dense device table.  ddJ_rows may be NULL unless bessels_interpolation
+   is cubic.  Arrays have J_size*L_size*l_size*m_size entries. */
+int  song_los_set_projection(song_los_ctx *ctx, const double *const *J_rows,
+                             const double *const *ddJ_rows,
+                             const int *index_xmin_J, const int *x_size_J);
+
+/* Device assembly of J_Llm(x) (bessel2.c:1041-1588).
+ *   j_l1 rows: j_l1[i] has x_size_l1[i] doubles starting at grid index index_xmin_l1[i]
+ *   three_j  : per jidx, first_3j and second_3j as [n_jidx][2*L_max+1] (zero padded),
+ *              l1_min[jidx], l1_size[jidx]; l1_size[jidx] = 0 marks a vanishing table
+ *              (spin / EB constraint, bessel2.c:1090-1100)
+ *   index_l1_of_l1min[jidx]: position of l1_min in the l1 list (bessel2.c:1175)           */
+int  song_los_build_projection(song_los_ctx *ctx, int l1_size, const int *l1,
+                               const double *const *j_l1, const int *index_xmin_l1,
+                               const int *x_size_l1,
+                               int n3j, const double *first_3j, const double *second_3j,
+                               const int *l1_min, const int *l1_count, const int *index_l1_of_l1min,
+                               const int *J_type_of_index_J, double J_Llm_cut, double xx_max);
+
+/* Sizes then contents of the device-built tables, bessels2 layout.  Call with rows == NULL to
+   obtain index_xmin_J / x_size_J first, allocate, then call again with rows. */
+int  song_los_get_projection(song_los_ctx *ctx, int *index_xmin_J, int *x_size_J,
+                             double *const *J_rows);
+
+int  song_los_upload_pairs(song_los_ctx *ctx, const song_los_batch *batch);
+int  song_los_compute(song_los_ctx *ctx, int mode, song_los_timing *timing);
+int  song_los_download(song_los_ctx *ctx, double *transfer /* [tt2_size][n_units] */);
+int  song_los_transfer_pairs(song_los_ctx *ctx, const song_los_batch *batch, int mode,
+                             double *transfer, song_los_timing *timing);
+
+/* Device pointer of the [tt2_size][n_units] result of the last compute (for the NCCL gather
+   done by the multi-GPU driver), as an integer address; 0 before the first compute. */
+uint64_t song_los_device_result(song_los_ctx *ctx, int64_t *n_doubles);
+
+/* Runs the engine's kernels on an external CUDA stream (a cudaStream_t passed as void*),
+   so that a caller's own events see the work.  NULL restores the engine's stream. */
+int  song_los_set_stream(song_los_ctx *ctx, void *cuda_stream);
+
+/* Roofline denominators measured on the device the context lives on:
+   dependent-free DFMA loop -> FP64 TFLOP/s; device-to-device copy -> GB/s. */
+int  song_los_measure_peaks(song_los_ctx *ctx, double *fp64_tflops, double *copy_gbs);
+
+/* Free bytes / total bytes / SM count of the context's device. */
+int  song_los_device_info(song_los_ctx *ctx, int64_t *free_bytes, int64_t *total_bytes,
+                          int *sm_count, char *name, int name_len);
+
+int  song_los_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,605 @@
+// song_los_api.cu -- C-ABI of the LOS engine (include/song_los.h): device memory, table
+// construction, launches, timing.  No CPU fallback: every path needs a CUDA device.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/song_los.h"
+#include "los_common.h"
+
+namespace songlos {
+// los_exact.cu
+cudaError_t launch_spline_k3(const Batch &b, int tau_size, int tp2_size, double *dd, int *err, cudaStream_t st);
+cudaError_t launch_los_exact(const ExactParams &P, int n_tiles, cudaStream_t st);
+size_t exact_smem_bytes(int tau_chunk, int tp2_size);
+// los_fast.cu
+struct FastState;
+FastState *fast_state_create();
+void fast_state_destroy(FastState *);
+int fast_compute(FastState *fs, const ExactParams &P, int device_sms, cudaStream_t st,
+                 song_los_timing *tm, std::string &err);
+// los_peaks.cu
+cudaError_t launch_dfma_probe(double *out, int iters, int blocks, int threads, cudaStream_t st);
+}  // namespace songlos
+
+using namespace songlos;
+
+static std::string g_create_error;
+static std::mutex g_mutex;
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct song_los_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::string err;
+
+  // configuration (host copies)
+  song_los_config cfg{};
+  std::vector<double> tau, xx;
+  std::vector<int> l, m, lm_array, lm_src, tt_index_l, tt_index_m;
+  std::vector<int> tt_type, tt_lm, tt_l, tt_m, tt_im;
+
+  // static device tables
+  DevBuf<double> d_tau, d_tau0_minus_tau, d_delta_tau, d_xx;
+  DevBuf<int> d_tt_type, d_tt_lm, d_tt_l, d_tt_m, d_tt_im, d_lm_src;
+  DevBuf<double2> d_J, d_ddJ;
+  DevBuf<unsigned char> d_block_nonzero;
+  int64_t n_cols = 0;
+  bool have_proj = false;
+  // ragged mirror kept for song_los_get_projection
+  DevBuf<double> d_ragged; DevBuf<int64_t> d_col_off; DevBuf<int> d_col_xmin, d_col_xsize;
+  std::vector<int> h_col_xmin, h_col_xsize; std::vector<int64_t> h_col_off;
+
+  // batch
+  song_los_batch hb{};          // scalar fields only are valid
+  std::vector<int> h_np, h_nt;
+  std::vector<int64_t> h_tr_off;
+  DevBuf<int> d_np, d_nt, d_phys_start, d_phys_size;
+  DevBuf<int64_t> d_pt_off, d_tr_off, d_src_off;
+  DevBuf<double> d_k3_pt, d_k3_tr, d_src, d_dd, d_out;
+  DevBuf<int2> d_tiles; int n_tiles = 0;
+  DevBuf<int> d_err;
+  DevBuf<double> d_scratch;
+  bool have_batch = false, have_result = false;
+
+  FastState *fast = nullptr;
+  cudaEvent_t ev[8]{};
+};
+
+static int fail(song_los_ctx *c, const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (c) c->err = buf; else { std::lock_guard<std::mutex> g(g_mutex); g_create_error = buf; }
+  return SONG_LOS_FAILURE;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  return fail(ctx, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+
+template <typename T>
+static cudaError_t upload(DevBuf<T> &d, const T *h, size_t n, cudaStream_t st)
+{
+  cudaError_t e = d.reserve(n);
+  if (e != cudaSuccess || n == 0) return e;
+  return cudaMemcpyAsync(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+extern "C" int song_los_version(void) { return 100; }
+
+extern "C" const char *song_los_last_error(const song_los_ctx *ctx)
+{
+  if (ctx) return ctx->err.c_str();
+  return g_create_error.c_str();
+}
+
+extern "C" int song_los_create(const song_los_config *cfg, song_los_ctx **out)
+{
+  song_los_ctx *ctx = nullptr;
+  if (!cfg || !out) return fail(nullptr, "song_los_create: NULL argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, "song_los_create: no CUDA device available (%s); there is no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(nullptr, "song_los_create: device %d out of range (have %d)", cfg->device, ndev);
+  if (cfg->tau_size < 2) return fail(nullptr, "song_los_create: tau_size=%d < 2", cfg->tau_size);
+  if (cfg->xx_size < 2 || cfg->xx_step <= 0) return fail(nullptr, "song_los_create: bad xx grid");
+  if (cfg->tt2_size < 1 || cfg->tp2_size < 1 || cfg->l_size < 1 || cfg->m_size < 1 || cfg->L_size < 1)
+    return fail(nullptr, "song_los_create: empty index tables");
+  if (cfg->tt2_size > 32 * EXACT_MAX_TT_PASSES)
+    return fail(nullptr, "song_los_create: tt2_size=%d exceeds the supported %d", cfg->tt2_size, 32 * EXACT_MAX_TT_PASSES);
+  if (cfg->l_max_los_t >= cfg->L_size || cfg->l_max_los_p >= cfg->L_size)
+    return fail(nullptr, "song_los_create: l_max_los exceeds L_size-1");
+
+  ctx = new song_los_ctx();
+  ctx->device = cfg->device;
+  ctx->cfg = *cfg;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { delete ctx; return fail(nullptr, "cudaSetDevice failed"); }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, ctx->device);
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx; return fail(nullptr, "cudaStreamCreate failed");
+  }
+  ctx->stream = ctx->own_stream;
+  for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+
+  ctx->tau.assign(cfg->tau_sampling, cfg->tau_sampling + cfg->tau_size);
+  ctx->xx.assign(cfg->xx, cfg->xx + cfg->xx_size);
+  ctx->l.assign(cfg->l, cfg->l + cfg->l_size);
+  ctx->m.assign(cfg->m, cfg->m + cfg->m_size);
+  ctx->lm_array.assign(cfg->lm_array, cfg->lm_array + (size_t)cfg->l_size * cfg->m_size);
+  ctx->lm_src.assign(cfg->lm_src, cfg->lm_src + (size_t)cfg->L_size * cfg->m_size);
+  ctx->tt_index_l.assign(cfg->tt_index_l, cfg->tt_index_l + cfg->tt2_size);
+  ctx->tt_index_m.assign(cfg->tt_index_m, cfg->tt_index_m + cfg->tt2_size);
+  ctx->cfg.tau_sampling = ctx->tau.data(); ctx->cfg.xx = ctx->xx.data();
+  ctx->cfg.l = ctx->l.data(); ctx->cfg.m = ctx->m.data();
+  ctx->cfg.lm_array = ctx->lm_array.data(); ctx->cfg.lm_src = ctx->lm_src.data();
+  ctx->cfg.tt_index_l = ctx->tt_index_l.data(); ctx->cfg.tt_index_m = ctx->tt_index_m.data();
+
+  // per-transfer-type tables (the dispatch of transfer2_compute, transfer2.c:1885-2061)
+  int ntt = cfg->tt2_size;
+  ctx->tt_type.resize(ntt); ctx->tt_lm.resize(ntt); ctx->tt_l.resize(ntt);
+  ctx->tt_m.resize(ntt); ctx->tt_im.resize(ntt);
+  for (int tt = 0; tt < ntt; ++tt) {
+    int type = -1, base = 0;
+    if (cfg->has_source_T && tt >= cfg->index_tt2_T && tt < cfg->index_tt2_T + cfg->n_transfers) { type = 0; base = cfg->index_tt2_T; }
+    else if (cfg->has_source_E && tt >= cfg->index_tt2_E && tt < cfg->index_tt2_E + cfg->n_transfers) { type = 1; base = cfg->index_tt2_E; }
+    else if (cfg->has_source_B && tt >= cfg->index_tt2_B && tt < cfg->index_tt2_B + cfg->n_transfers) { type = 2; base = cfg->index_tt2_B; }
+    if (type < 0) { song_los_destroy(ctx); return fail(nullptr, "song_los_create: transfer type %d belongs to no field", tt); }
+    int il = cfg->tt_index_l[tt], im = cfg->tt_index_m[tt];
+    if (il < 0 || il >= cfg->l_size || im < 0 || im >= cfg->m_size) {
+      song_los_destroy(ctx); return fail(nullptr, "song_los_create: (index_l,index_m) of tt=%d out of bounds", tt);
+    }
+    ctx->tt_type[tt] = type;
+    ctx->tt_lm[tt] = tt - base;
+    ctx->tt_l[tt] = cfg->l[il];
+    ctx->tt_m[tt] = cfg->m[im];
+    ctx->tt_im[tt] = im;
+    if (cfg->lm_array[(size_t)il * cfg->m_size + im] != tt - base) {
+      song_los_destroy(ctx); return fail(nullptr, "song_los_create: lm_array inconsistent with corresponding_index at tt=%d", tt);
+    }
+  }
+
+  // integration measure for the sources time sampling, transfer2.c:2567-2580
+  std::vector<double> d(cfg->tau_size), w(cfg->tau_size);
+  for (int i = 0; i < cfg->tau_size; ++i) d[i] = cfg->tau0 - ctx->tau[i];
+  w[0] = ctx->tau[1] - ctx->tau[0];
+  for (int i = 1; i < cfg->tau_size - 1; ++i) w[i] = ctx->tau[i + 1] - ctx->tau[i - 1];
+  w[cfg->tau_size - 1] = ctx->tau[cfg->tau_size - 1] - ctx->tau[cfg->tau_size - 2];
+
+  cudaStream_t st = ctx->stream;
+  bool ok = upload(ctx->d_tau, ctx->tau.data(), ctx->tau.size(), st) == cudaSuccess
+         && upload(ctx->d_tau0_minus_tau, d.data(), d.size(), st) == cudaSuccess
+         && upload(ctx->d_delta_tau, w.data(), w.size(), st) == cudaSuccess
+         && upload(ctx->d_xx, ctx->xx.data(), ctx->xx.size(), st) == cudaSuccess
+         && upload(ctx->d_tt_type, ctx->tt_type.data(), (size_t)ntt, st) == cudaSuccess
+         && upload(ctx->d_tt_lm, ctx->tt_lm.data(), (size_t)ntt, st) == cudaSuccess
+         && upload(ctx->d_tt_l, ctx->tt_l.data(), (size_t)ntt, st) == cudaSuccess
+         && upload(ctx->d_tt_m, ctx->tt_m.data(), (size_t)ntt, st) == cudaSuccess
+         && upload(ctx->d_tt_im, ctx->tt_im.data(), (size_t)ntt, st) == cudaSuccess
+         && upload(ctx->d_lm_src, ctx->lm_src.data(), ctx->lm_src.size(), st) == cudaSuccess
+         && ctx->d_err.reserve(1) == cudaSuccess
+         && cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), st) == cudaSuccess
+         && cudaStreamSynchronize(st) == cudaSuccess;
+  if (!ok) { song_los_destroy(ctx); return fail(nullptr, "song_los_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError())); }
+  ctx->fast = fast_state_create();
+  *out = ctx;
+  return SONG_LOS_SUCCESS;
+}
+
+extern "C" int song_los_destroy(song_los_ctx *ctx)
+{
+  if (!ctx) return SONG_LOS_SUCCESS;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+  ctx->d_tau.release(); ctx->d_tau0_minus_tau.release(); ctx->d_delta_tau.release(); ctx->d_xx.release();
+  ctx->d_tt_type.release(); ctx->d_tt_lm.release(); ctx->d_tt_l.release(); ctx->d_tt_m.release();
+  ctx->d_tt_im.release(); ctx->d_lm_src.release(); ctx->d_J.release(); ctx->d_ddJ.release();
+  ctx->d_block_nonzero.release(); ctx->d_ragged.release(); ctx->d_col_off.release();
+  ctx->d_col_xmin.release(); ctx->d_col_xsize.release();
+  ctx->d_np.release(); ctx->d_nt.release(); ctx->d_phys_start.release(); ctx->d_phys_size.release();
+  ctx->d_pt_off.release(); ctx->d_tr_off.release(); ctx->d_src_off.release();
+  ctx->d_k3_pt.release(); ctx->d_k3_tr.release(); ctx->d_src.release(); ctx->d_dd.release();
+  ctx->d_out.release(); ctx->d_tiles.release(); ctx->d_err.release(); ctx->d_scratch.release();
+  if (ctx->fast) fast_state_destroy(ctx->fast);
+  for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return SONG_LOS_SUCCESS;
+}
+
+extern "C" int song_los_set_stream(song_los_ctx *ctx, void *cuda_stream)
+{
+  if (!ctx) return SONG_LOS_FAILURE;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return SONG_LOS_SUCCESS;
+}
+
+extern "C" int song_los_device_info(song_los_ctx *ctx, int64_t *free_bytes, int64_t *total_bytes,
+                                    int *sm_count, char *name, int name_len)
+{
+  if (!ctx) return SONG_LOS_FAILURE;
+  CK(cudaSetDevice(ctx->device));
+  size_t f = 0, t = 0;
+  CK(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = (int64_t)f;
+  if (total_bytes) *total_bytes = (int64_t)t;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (name && name_len > 0) {
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
+    snprintf(name, (size_t)name_len, "%s", prop.name);
+  }
+  return SONG_LOS_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Projection tables
+// ---------------------------------------------------------------------------------------------
+namespace songlos {
+__global__ void densify_projection_kernel(const double *ragged, const int64_t *col_off,
+                                          const int *col_xmin, const int *col_xsize,
+                                          int64_t n_cols, int xx_size, double2 *dense)
+{
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int ix = blockIdx.y;
+  if (c >= n_cols) return;
+  double2 v = make_double2(0., 0.);
+  int xsize = col_xsize[c];
+  int xmin = col_xmin[c];
+  if (xsize > 0 && ix >= xmin) {                      // skip test of transfer2.c:2232
+    int r = ix - xmin;
+    const double *row = ragged + col_off[c];
+    if (r < xsize) v.x = row[r];
+    if (r + 1 < xsize) v.y = row[r + 1];
+  }
+  dense[(int64_t)ix * n_cols + c] = v;
+}
+}  // namespace songlos
+
+// column c of the dense table <-> (index_J, L, lm);  lm <-> (index_l, index_m) through lm_array
+static int densify(song_los_ctx *ctx, const std::vector<double> &flat, DevBuf<double2> &dense)
+{
+  cudaStream_t st = ctx->stream;
+  CK(upload(ctx->d_ragged, flat.data(), flat.size(), st));
+  CK(upload(ctx->d_col_off, ctx->h_col_off.data(), ctx->h_col_off.size(), st));
+  CK(upload(ctx->d_col_xmin, ctx->h_col_xmin.data(), ctx->h_col_xmin.size(), st));
+  CK(upload(ctx->d_col_xsize, ctx->h_col_xsize.data(), ctx->h_col_xsize.size(), st));
+  CK(dense.reserve((size_t)ctx->cfg.xx_size * ctx->n_cols));
+  dim3 grid((unsigned)((ctx->n_cols + 127) / 128), (unsigned)ctx->cfg.xx_size);
+  densify_projection_kernel<<<grid, 128, 0, st>>>(ctx->d_ragged.p, ctx->d_col_off.p, ctx->d_col_xmin.p,
+                                                  ctx->d_col_xsize.p, ctx->n_cols, ctx->cfg.xx_size, dense.p);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  return SONG_LOS_SUCCESS;
+}
+
+extern "C" int song_los_set_projection(song_los_ctx *ctx, const double *const *J_rows,
+                                       const double *const *ddJ_rows,
+                                       const int *index_xmin_J, const int *x_size_J)
+{
+  if (!ctx || !J_rows || !index_xmin_J || !x_size_J) return fail(ctx, "song_los_set_projection: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  const song_los_config &c = ctx->cfg;
+  if (c.bessels_interpolation == SONG_LOS_INTERP_CUBIC && !ddJ_rows)
+    return fail(ctx, "song_los_set_projection: cubic Bessel interpolation needs ddJ rows");
+  ctx->n_cols = (int64_t)c.J_size * c.L_size * c.n_transfers;
+  ctx->h_col_off.assign((size_t)ctx->n_cols, 0);
+  ctx->h_col_xmin.assign((size_t)ctx->n_cols, c.xx_size);
+  ctx->h_col_xsize.assign((size_t)ctx->n_cols, 0);
+  std::vector<unsigned char> block_nonzero((size_t)c.J_size * c.L_size, 0);
+
+  // pass 1: sizes
+  int64_t total = 0;
+  std::vector<int64_t> src_jidx((size_t)ctx->n_cols, -1);
+  for (int J = 0; J < c.J_size; ++J)
+    for (int L = 0; L < c.L_size; ++L)
+      for (int il = 0; il < c.l_size; ++il)
+        for (int im = 0; im < c.m_size; ++im) {
+          int lm = c.lm_array[(size_t)il * c.m_size + im];
+          if (lm < 0) continue;
+          size_t jidx = (((size_t)J * c.L_size + L) * c.l_size + il) * c.m_size + im;
+          if (!J_rows[jidx]) continue;
+          int xs = x_size_J[jidx], xm = index_xmin_J[jidx];
+          if (xs < 1 || xm < 0 || xm + xs > c.xx_size)
+            return fail(ctx, "song_los_set_projection: row (J=%d,L=%d,il=%d,im=%d) has xmin=%d size=%d outside xx_size=%d",
+                        J, L, il, im, xm, xs, c.xx_size);
+          int64_t col = ((int64_t)J * c.L_size + L) * c.n_transfers + lm;
+          // a row holding the single value 0 at the last grid point is the reference's
+          // "negligible everywhere" marker (bessel2.c:1378-1388): keep the column empty
+          if (xs == 1 && xm == c.xx_size - 1) continue;
+          ctx->h_col_off[(size_t)col] = total;
+          ctx->h_col_xmin[(size_t)col] = xm;
+          ctx->h_col_xsize[(size_t)col] = xs;
+          src_jidx[(size_t)col] = (int64_t)jidx;
+          total += xs;
+          block_nonzero[(size_t)J * c.L_size + L] = 1;
+        }
+  std::vector<double> flat((size_t)total);
+  for (int64_t col = 0; col < ctx->n_cols; ++col)
+    if (src_jidx[(size_t)col] >= 0)
+      std::memcpy(flat.data() + ctx->h_col_off[(size_t)col], J_rows[src_jidx[(size_t)col]],
+                  (size_t)ctx->h_col_xsize[(size_t)col] * sizeof(double));
+  if (densify(ctx, flat, ctx->d_J) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
+  if (c.bessels_interpolation == SONG_LOS_INTERP_CUBIC) {
+    for (int64_t col = 0; col < ctx->n_cols; ++col)
+      if (src_jidx[(size_t)col] >= 0) {
+        if (!ddJ_rows[src_jidx[(size_t)col]]) return fail(ctx, "song_los_set_projection: missing ddJ row");
+        std::memcpy(flat.data() + ctx->h_col_off[(size_t)col], ddJ_rows[src_jidx[(size_t)col]],
+                    (size_t)ctx->h_col_xsize[(size_t)col] * sizeof(double));
+      }
+    if (densify(ctx, flat, ctx->d_ddJ) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
+    // restore the J values in the ragged mirror
+    for (int64_t col = 0; col < ctx->n_cols; ++col)
+      if (src_jidx[(size_t)col] >= 0)
+        std::memcpy(flat.data() + ctx->h_col_off[(size_t)col], J_rows[src_jidx[(size_t)col]],
+                    (size_t)ctx->h_col_xsize[(size_t)col] * sizeof(double));
+    CK(upload(ctx->d_ragged, flat.data(), flat.size(), ctx->stream));
+  }
+  CK(upload(ctx->d_block_nonzero, block_nonzero.data(), block_nonzero.size(), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_proj = true;
+  return SONG_LOS_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batches
+// ---------------------------------------------------------------------------------------------
+extern "C" int song_los_upload_pairs(song_los_ctx *ctx, const song_los_batch *b)
+{
+  if (!ctx || !b) return fail(ctx, "song_los_upload_pairs: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  const song_los_config &c = ctx->cfg;
+  if (b->n_pairs < 0) return fail(ctx, "song_los_upload_pairs: negative n_pairs");
+  // consistency checks (the reference's class_test of transfer2.c:1766-1771 and layout checks)
+  int64_t pt = 0, tr = 0, so = 0;
+  for (int p = 0; p < b->n_pairs; ++p) {
+    int np = b->k3_pt_size[p], nt = b->k3_tr_size[p];
+    int need = (c.sources_k3_interpolation == SONG_LOS_INTERP_CUBIC) ? 4 : 2;
+    if (np < need)
+      return fail(ctx, "pair %d: cannot do interpolation in k3 with just k3_size=%d values. Increase k3_size.", p, np);
+    if (nt < 1) return fail(ctx, "pair %d: empty k3 grid", p);
+    if (b->phys_start[p] < 0 || b->phys_size[p] < 1 || b->phys_start[p] + b->phys_size[p] > nt)
+      return fail(ctx, "pair %d: physical range [%d,+%d) outside the k3 grid of %d points", p, b->phys_start[p], b->phys_size[p], nt);
+    if (c.k3_extrapolation == SONG_LOS_NO_K3_EXTRAPOLATION && (b->phys_start[p] != 0 || b->phys_size[p] != nt))
+      return fail(ctx, "pair %d: when no extrapolation is requested, all k's should be physical", p);
+    if (b->pt_off[p] != pt || b->tr_off[p] != tr || b->src_off[p] != so)
+      return fail(ctx, "pair %d: offsets are not the running sums of the sizes (packed layout expected)", p);
+    pt += np; tr += nt; so += (int64_t)c.tp2_size * c.tau_size * np;
+  }
+  if (pt != b->n_pt_total || tr != b->n_units || so != b->n_src_total)
+    return fail(ctx, "song_los_upload_pairs: totals do not match the per-pair sizes");
+
+  cudaStream_t st = ctx->stream;
+  size_t n = (size_t)b->n_pairs;
+  CK(upload(ctx->d_np, b->k3_pt_size, n, st));
+  CK(upload(ctx->d_nt, b->k3_tr_size, n, st));
+  CK(upload(ctx->d_phys_start, b->phys_start, n, st));
+  CK(upload(ctx->d_phys_size, b->phys_size, n, st));
+  CK(upload(ctx->d_pt_off, b->pt_off, n, st));
+  CK(upload(ctx->d_tr_off, b->tr_off, n, st));
+  CK(upload(ctx->d_src_off, b->src_off, n, st));
+  CK(upload(ctx->d_k3_pt, b->k3_pt, (size_t)b->n_pt_total, st));
+  CK(upload(ctx->d_k3_tr, b->k3_tr, (size_t)b->n_units, st));
+  CK(upload(ctx->d_src, b->src, (size_t)b->n_src_total, st));
+  CK(ctx->d_out.reserve((size_t)b->n_units * c.tt2_size));
+  if (c.sources_k3_interpolation == SONG_LOS_INTERP_CUBIC) CK(ctx->d_dd.reserve((size_t)b->n_src_total));
+
+  // CTA work list of the exact kernel: (pair, first k3 index)
+  std::vector<int2> tiles;
+  for (int p = 0; p < b->n_pairs; ++p)
+    for (int u0 = 0; u0 < b->k3_tr_size[p]; u0 += EXACT_UNITS_PER_CTA)
+      tiles.push_back(make_int2(p, u0));
+  ctx->n_tiles = (int)tiles.size();
+  CK(upload(ctx->d_tiles, tiles.data(), tiles.size(), st));
+  CK(cudaStreamSynchronize(st));
+
+  ctx->hb = *b;
+  ctx->hb.k3_pt_size = ctx->hb.k3_tr_size = ctx->hb.phys_start = ctx->hb.phys_size = nullptr;
+  ctx->hb.pt_off = ctx->hb.tr_off = ctx->hb.src_off = nullptr;
+  ctx->hb.k3_pt = ctx->hb.k3_tr = ctx->hb.src = nullptr;
+  ctx->h_np.assign(b->k3_pt_size, b->k3_pt_size + n);
+  ctx->h_nt.assign(b->k3_tr_size, b->k3_tr_size + n);
+  ctx->h_tr_off.assign(b->tr_off, b->tr_off + n);
+  ctx->have_batch = true;
+  ctx->have_result = false;
+  return SONG_LOS_SUCCESS;
+}
+
+static void fill_params(song_los_ctx *ctx, ExactParams &P)
+{
+  const song_los_config &c = ctx->cfg;
+  std::memset(&P, 0, sizeof P);
+  P.proj.J = ctx->d_J.p; P.proj.ddJ = ctx->d_ddJ.p; P.proj.n_cols = ctx->n_cols;
+  P.proj.block_nonzero = ctx->d_block_nonzero.p;
+  P.ty.tt2_size = c.tt2_size; P.ty.n_transfers = c.n_transfers; P.ty.L_size = c.L_size;
+  P.ty.m_size = c.m_size; P.ty.l_size = c.l_size;
+  P.ty.tt_type = ctx->d_tt_type.p; P.ty.tt_lm = ctx->d_tt_lm.p; P.ty.tt_l = ctx->d_tt_l.p;
+  P.ty.tt_m = ctx->d_tt_m.p; P.ty.tt_im = ctx->d_tt_im.p; P.ty.lm_src = ctx->d_lm_src.p;
+  P.ty.index_J_TT = c.index_J_TT; P.ty.index_J_EE = c.index_J_EE; P.ty.index_J_EB = c.index_J_EB;
+  P.ty.index_tp2_T = c.index_tp2_T; P.ty.index_tp2_E = c.index_tp2_E; P.ty.index_tp2_B = c.index_tp2_B;
+  P.ty.l_max_los_t = c.l_max_los_t; P.ty.l_max_los_p = c.l_max_los_p; P.ty.tp2_size = c.tp2_size;
+  P.tm.tau_size = c.tau_size; P.tm.tau = ctx->d_tau.p; P.tm.tau0_minus_tau = ctx->d_tau0_minus_tau.p;
+  P.tm.delta_tau = ctx->d_delta_tau.p; P.tm.tau0 = c.tau0; P.tm.mode = c.tau_sampling_mode;
+  P.tm.tau_linstep_song = c.tau_linstep_song;
+  P.b.n_pairs = ctx->hb.n_pairs; P.b.np = ctx->d_np.p; P.b.nt = ctx->d_nt.p;
+  P.b.phys_start = ctx->d_phys_start.p; P.b.phys_size = ctx->d_phys_size.p;
+  P.b.pt_off = ctx->d_pt_off.p; P.b.tr_off = ctx->d_tr_off.p; P.b.src_off = ctx->d_src_off.p;
+  P.b.k3_pt = ctx->d_k3_pt.p; P.b.k3_tr = ctx->d_k3_tr.p; P.b.src = ctx->d_src.p; P.b.dd = ctx->d_dd.p;
+  P.b.n_units = ctx->hb.n_units; P.b.out = ctx->d_out.p;
+  P.xx = ctx->d_xx.p; P.xx_size = c.xx_size; P.xx_step = c.xx_step;
+  P.cubic_k3 = (c.sources_k3_interpolation == SONG_LOS_INTERP_CUBIC);
+  P.cubic_J = (c.bessels_interpolation == SONG_LOS_INTERP_CUBIC);
+  P.cubic_time = (c.sources_time_interpolation == SONG_LOS_INTERP_CUBIC);
+  P.flat_extrap = (c.k3_extrapolation == SONG_LOS_FLAT_K3_EXTRAPOLATION);
+  P.tiles = ctx->d_tiles.p;
+  P.err = ctx->d_err.p;
+}
+
+static int check_device_errors(song_los_ctx *ctx)
+{
+  int h = 0;
+  CK(cudaMemcpyAsync(&h, ctx->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (h) {
+    cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), ctx->stream);
+    if (h & ERR_X_OUT_OF_RANGE)
+      return fail(ctx, "not enough J's: k*(tau0-tau) exceeds xx_max (transfer2.c:2172); increase l_max or decrease k_max");
+    if (h & ERR_H_ZERO) return fail(ctx, "stop to avoid division by zero in the k3 interpolation (or k3_size outside [3,256])");
+    if (h & ERR_TAU_GRID_OVERFLOW) return fail(ctx, "time integration grid larger than the allocated maximum");
+    if (h & ERR_NAN) return fail(ctx, "found nan in second-order transfer function");
+  }
+  return SONG_LOS_SUCCESS;
+}
+
+extern "C" int song_los_compute(song_los_ctx *ctx, int mode, song_los_timing *tm)
+{
+  if (!ctx) return SONG_LOS_FAILURE;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->have_proj) return fail(ctx, "song_los_compute: projection functions not set (bessel2 first)");
+  if (!ctx->have_batch) return fail(ctx, "song_los_compute: no pairs uploaded");
+  const song_los_config &c = ctx->cfg;
+  song_los_timing t{};
+  t.n_integrals = ctx->hb.n_units * c.tt2_size;
+  {
+    int64_t nT = 0, nP = 0;
+    for (int tt = 0; tt < c.tt2_size; ++tt) (ctx->tt_type[tt] == 0 ? nT : nP)++;
+    t.n_terms_upper = ctx->hb.n_units * c.tau_size * (nT * (c.l_max_los_t + 1) + nP * (c.l_max_los_p + 1));
+  }
+  cudaStream_t st = ctx->stream;
+  ExactParams P;
+  fill_params(ctx, P);
+
+  CK(cudaEventRecord(ctx->ev[0], st));
+  if (P.cubic_k3) {
+    CK(launch_spline_k3(P.b, c.tau_size, c.tp2_size, ctx->d_dd.p, ctx->d_err.p, st));
+    t.n_launches++;
+  }
+  CK(cudaEventRecord(ctx->ev[1], st));
+
+  if (mode == SONG_LOS_MODE_EXACT || c.tau_sampling_mode != SONG_LOS_TAU_SOURCES) {
+    if (c.tau_sampling_mode != SONG_LOS_TAU_SOURCES)
+      return fail(ctx, "song_los_compute: custom/bessel tau sampling is not available in this build");
+    // tau chunk: as many time samples as fit in ~96 KB of shared memory
+    size_t per_tau = exact_smem_bytes(1, c.tp2_size) - 16;
+    int chunk = (int)std::min<size_t>((size_t)c.tau_size, (96 * 1024) / per_tau);
+    if (chunk < 1) return fail(ctx, "song_los_compute: tp2_size=%d too large for the shared-memory stage", c.tp2_size);
+    P.tau_chunk = chunk;
+    CK(launch_los_exact(P, ctx->n_tiles, st));
+    t.n_launches++;
+    CK(cudaEventRecord(ctx->ev[2], st));
+    CK(cudaEventSynchronize(ctx->ev[2]));
+    CK(cudaEventElapsedTime(&t.ms_spline, ctx->ev[0], ctx->ev[1]));
+    CK(cudaEventElapsedTime(&t.ms_integrate, ctx->ev[1], ctx->ev[2]));
+    CK(cudaEventElapsedTime(&t.ms_total, ctx->ev[0], ctx->ev[2]));
+  } else if (mode == SONG_LOS_MODE_FAST) {
+    std::string e;
+    if (fast_compute(ctx->fast, P, ctx->sm_count, st, &t, e) != 0) return fail(ctx, "%s", e.c_str());
+    CK(cudaEventRecord(ctx->ev[2], st));
+    CK(cudaEventSynchronize(ctx->ev[2]));
+    CK(cudaEventElapsedTime(&t.ms_spline, ctx->ev[0], ctx->ev[1]));
+    CK(cudaEventElapsedTime(&t.ms_total, ctx->ev[0], ctx->ev[2]));
+  } else {
+    return fail(ctx, "song_los_compute: unknown mode %d", mode);
+  }
+  if (check_device_errors(ctx) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
+  ctx->have_result = true;
+  if (tm) *tm = t;
+  return SONG_LOS_SUCCESS;
+}
+
+extern "C" int song_los_download(song_los_ctx *ctx, double *transfer)
+{
+  if (!ctx || !transfer) return fail(ctx, "song_los_download: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->have_result) return fail(ctx, "song_los_download: nothing computed yet");
+  size_t n = (size_t)ctx->hb.n_units * ctx->cfg.tt2_size;
+  CK(cudaMemcpyAsync(transfer, ctx->d_out.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SONG_LOS_SUCCESS;
+}
+
+extern "C" int song_los_transfer_pairs(song_los_ctx *ctx, const song_los_batch *batch, int mode,
+                                       double *transfer, song_los_timing *timing)
+{
+  if (song_los_upload_pairs(ctx, batch) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
+  if (song_los_compute(ctx, mode, timing) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
+  return song_los_download(ctx, transfer);
+}
+
+extern "C" uint64_t song_los_device_result(song_los_ctx *ctx, int64_t *n_doubles)
+{
+  if (!ctx || !ctx->have_result) { if (n_doubles) *n_doubles = 0; return 0; }
+  if (n_doubles) *n_doubles = ctx->hb.n_units * ctx->cfg.tt2_size;
+  return (uint64_t)(uintptr_t)ctx->d_out.p;
+}
+
+extern "C" int song_los_measure_peaks(song_los_ctx *ctx, double *fp64_tflops, double *copy_gbs)
+{
+  if (!ctx) return SONG_LOS_FAILURE;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (fp64_tflops) {
+    const int threads = 256, blocks = ctx->sm_count * 8, iters = 4096;
+    DevBuf<double> sink;
+    CK(sink.reserve((size_t)blocks * threads));
+    CK(launch_dfma_probe(sink.p, 64, blocks, threads, st));      // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+      CK(cudaEventRecord(ctx->ev[3], st));
+      CK(launch_dfma_probe(sink.p, iters, blocks, threads, st));
+      CK(cudaEventRecord(ctx->ev[4], st));
+      CK(cudaEventSynchronize(ctx->ev[4]));
+      float ms; CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
+      best = std::min(best, ms);
+    }
+    // 16 independent chains x 2 flop per DFMA per iteration per thread
+    double flops = 2.0 * 16.0 * iters * (double)blocks * threads;
+    *fp64_tflops = flops / (best * 1e-3) / 1e12;
+    sink.release();
+  }
+  if (copy_gbs) {
+    size_t n = (size_t)1 << 28;   // 2 GiB of doubles per buffer
+    DevBuf<double> a, b;
+    CK(a.reserve(n)); CK(b.reserve(n));
+    CK(cudaMemsetAsync(a.p, 0, n * 8, st));
+    CK(cudaMemcpyAsync(b.p, a.p, n * 8, cudaMemcpyDeviceToDevice, st));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+      CK(cudaEventRecord(ctx->ev[3], st));
+      CK(cudaMemcpyAsync(b.p, a.p, n * 8, cudaMemcpyDeviceToDevice, st));
+      CK(cudaEventRecord(ctx->ev[4], st));
+      CK(cudaEventSynchronize(ctx->ev[4]));
+      float ms; CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
+      best = std::min(best, ms);
+    }
+    *copy_gbs = 2.0 * n * 8 / (best * 1e-3) / 1e9;
+    a.release(); b.release();
+  }
+  return SONG_LOS_SUCCESS;
+}
+
+// song_los_build_projection / song_los_get_projection live in song_los_proj.cu

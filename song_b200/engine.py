@@ -1,0 +1,142 @@
+"""Thin Python handle on the C-ABI LOS engine (``include/song_los.h``).
+
+This is plumbing for the tests, ``bench.py`` and the multi-GPU driver; SONG itself reaches the
+same entry points from C through ``song_b200/host/transfer2_gpu.c``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .workload import INTERP, K3_EXTRAPOLATION, TAU_SAMPLING, Workload, make_batch
+
+MODE_EXACT = 0
+MODE_FAST = 1
+
+
+class Projection:
+    """Host copy of the bessels2 tables the engine consumes (bessel2.h:64-91), flattened as
+    jidx = ((index_J*L_size + L)*l_size + index_l)*m_size + index_m."""
+
+    def __init__(self, rows, index_xmin, x_size, ddrows=None):
+        self.rows = rows                  # list of 1-D float64 arrays or None
+        self.index_xmin = np.ascontiguousarray(index_xmin, dtype=np.int32)
+        self.x_size = np.ascontiguousarray(x_size, dtype=np.int32)
+        self.ddrows = ddrows
+
+    def _ptrs(self, rows):
+        arr = (_lib.c_double_p * len(rows))()
+        for i, r in enumerate(rows):
+            if r is not None:
+                arr[i] = _lib.dptr(r)
+        return arr
+
+    def row_ptrs(self):
+        return self._ptrs(self.rows)
+
+    def ddrow_ptrs(self):
+        return self._ptrs(self.ddrows) if self.ddrows is not None else None
+
+
+class LosEngine:
+    """One engine per GPU.  Fails loudly when the CUDA library or a device is missing."""
+
+    def __init__(self, wl: Workload, device: int = 0):
+        self.lib = _lib.los()
+        lay, p = wl.layout, wl.params
+        self._keep = dict(tau=np.ascontiguousarray(wl.tau), xx=np.ascontiguousarray(wl.xx),
+                          l=np.ascontiguousarray(lay.l), m=np.ascontiguousarray(lay.m),
+                          lm_array=np.ascontiguousarray(lay.lm_array), lm_src=np.ascontiguousarray(lay.lm_src),
+                          tl=np.ascontiguousarray(lay.tt_index_l), tm=np.ascontiguousarray(lay.tt_index_m))
+        k = self._keep
+        cfg = _lib.LosConfig(
+            device=device, tau0=wl.cosmo["tau0"], tau_size=int(wl.tau.size), tau_sampling=_lib.dptr(k["tau"]),
+            tau_sampling_mode=TAU_SAMPLING[p["transfer2_tau_sampling"]],
+            tau_linstep_song=float(p.get("tau_linstep_song", 0.0)),
+            sources_k3_interpolation=INTERP[p["sources_k3_interpolation"]],
+            sources_time_interpolation=INTERP[p["sources_time_interpolation"]],
+            bessels_interpolation=INTERP[p["bessels_interpolation"]],
+            k3_extrapolation=K3_EXTRAPOLATION[p["bispectra_k3_extrapolation"]],
+            xx_size=int(wl.xx.size), xx=_lib.dptr(k["xx"]), xx_step=float(wl.xx_step),
+            l_size=lay.l_size, l=_lib.iptr(k["l"]), m_size=lay.m_size, m=_lib.iptr(k["m"]),
+            L_size=lay.L_size, n_transfers=lay.n_transfers,
+            lm_array=_lib.iptr(k["lm_array"]), lm_src=_lib.iptr(k["lm_src"]),
+            has_source_T=int(lay.has_source_T), has_source_E=int(lay.has_source_E), has_source_B=int(lay.has_source_B),
+            index_tp2_T=lay.index_tp2_T, index_tp2_E=lay.index_tp2_E, index_tp2_B=lay.index_tp2_B,
+            tp2_size=lay.tp2_size, l_max_los_t=lay.l_max_los_t, l_max_los_p=lay.l_max_los_p,
+            index_tt2_T=lay.index_tt2_T, index_tt2_E=lay.index_tt2_E, index_tt2_B=lay.index_tt2_B,
+            tt2_size=lay.tt2_size, tt_index_l=_lib.iptr(k["tl"]), tt_index_m=_lib.iptr(k["tm"]),
+            J_size=lay.J_size, index_J_TT=lay.index_J_TT, index_J_EE=lay.index_J_EE, index_J_EB=lay.index_J_EB)
+        self.ctx = C.c_void_p()
+        if self.lib.song_los_create(C.byref(cfg), C.byref(self.ctx)):
+            raise _lib.SongLosError(self.lib.song_los_last_error(None).decode())
+        self.tt2_size = lay.tt2_size
+        self.n_units = 0
+        self.timing = _lib.LosTiming()
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc:
+            raise _lib.SongLosError(self.lib.song_los_last_error(self.ctx).decode())
+
+    def close(self):
+        if self.ctx:
+            self.lib.song_los_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- projection functions --------------------------------------------------------------
+    def set_projection(self, proj: Projection):
+        dd = proj.ddrow_ptrs()
+        self._check(self.lib.song_los_set_projection(self.ctx, proj.row_ptrs(), dd,
+                                                     _lib.iptr(proj.index_xmin), _lib.iptr(proj.x_size)))
+
+    # -- batches ---------------------------------------------------------------------------
+    def upload(self, wl: Workload):
+        b = make_batch(wl)
+        self._check(self.lib.song_los_upload_pairs(self.ctx, C.byref(b)))
+        self.n_units = wl.n_units
+
+    def compute(self, mode: int = MODE_EXACT) -> dict:
+        self._check(self.lib.song_los_compute(self.ctx, mode, C.byref(self.timing)))
+        return self.timing.as_dict()
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.tt2_size, self.n_units), dtype=np.float64)
+        self._check(self.lib.song_los_download(self.ctx, _lib.dptr(out)))
+        return out
+
+    def transfer_pairs(self, wl: Workload, mode: int = MODE_EXACT, out: np.ndarray | None = None) -> np.ndarray:
+        """Host buffers in, host buffer out: upload + compute + download (the e2e path)."""
+        b = make_batch(wl)
+        if out is None:
+            out = np.empty((self.tt2_size, wl.n_units), dtype=np.float64)
+        self._check(self.lib.song_los_transfer_pairs(self.ctx, C.byref(b), mode, _lib.dptr(out), C.byref(self.timing)))
+        self.n_units = wl.n_units
+        return out
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self.lib.song_los_set_stream(self.ctx, C.c_void_p(cuda_stream or 0)))
+
+    def device_result(self):
+        n = C.c_int64(0)
+        ptr = self.lib.song_los_device_result(self.ctx, C.byref(n))
+        return int(ptr), int(n.value)
+
+    def measure_peaks(self):
+        f, c = C.c_double(0), C.c_double(0)
+        self._check(self.lib.song_los_measure_peaks(self.ctx, C.byref(f), C.byref(c)))
+        return {"fp64_tflops": f.value, "copy_gbs": c.value}
+
+    def device_info(self):
+        fr, tot, sm = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        name = C.create_string_buffer(128)
+        self._check(self.lib.song_los_device_info(self.ctx, C.byref(fr), C.byref(tot), C.byref(sm), name, 128))
+        return {"free": fr.value, "total": tot.value, "sm_count": sm.value, "name": name.value.decode()}

@@ -1,0 +1,167 @@
+/*
+ * los_host.c -- host-side k3 integration grids of the transfer2 drop-in (see los_host.h).
+ *
+ * The grid is produced by one generator, k3_walk(), used both to count the points
+ * (transfer2_get_k3_size, reference source/transfer2.c:1329-1551) and to write them
+ * (transfer2_get_k3_list, :1566-1737).  The floating-point recurrence `k += k_step` and every
+ * comparison are the reference's, so the grids are bit-identical to what bispectra2.c:1255 and
+ * spectra2.c:451 re-derive.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include "los_host.h"
+
+#define SONG_PI 3.1415926535897932384626433832795e0
+
+static int host_fail(char *errmsg, int errlen, const char *text)
+{
+  if (errmsg && errlen > 0) snprintf(errmsg, (size_t)errlen, "%s", text);
+  return 1;
+}
+
+/* linear step of the fine grid, transfer2.c:1428-1448 */
+static double k3_linear_step(const song_k3_params *p)
+{
+  if (p->k_sampling == 1) {
+    if (p->old_run_step) return 2. * SONG_PI / p->rs_rec * p->q_linstep_song;
+    return 2. * SONG_PI / (p->tau0 - p->tau_rec) * p->q_linstep_song;
+  }
+  return p->xx_step / p->tau0;
+}
+
+/* limits of the grid including the flat-extrapolation wings, transfer2.c:1354-1404 */
+static void k3_limits(const song_k3_params *p, double k_min_pt, double k_max_pt,
+                      double *k_min_tr, double *k_max_tr)
+{
+  double lo = k_min_pt, hi = k_max_pt;
+  if (p->k3_extrapolation != 0) {
+    double physical = k_max_pt - k_min_pt;
+    double want_right = 2. * SONG_PI * p->extra_k3_oscillations_right / (p->tau0 - p->tau_rec);
+    double want_left = 2. * SONG_PI * p->extra_k3_oscillations_left / (p->tau0 - p->tau_rec);
+    if (physical < want_right) hi += (want_right - physical);
+    if (hi > p->k_last) hi = p->k_last;
+    if (physical < want_left) lo -= (want_left - physical);
+    double floor_k = (p->k_first < k_min_pt) ? p->k_first : k_min_pt;
+    if (lo < floor_k) lo = floor_k;
+    if (p->extra_k3_oscillations_left < 0) lo = p->k_first;
+    if (p->extra_k3_oscillations_right < 0) hi = p->k_last;
+  }
+  *k_min_tr = lo;
+  *k_max_tr = hi;
+}
+
+/*
+ * Emits the grid: [left wing by repeated k += step, snapped onto k_min_pt] + [source points
+ * while their spacing is finer than step] + [k += step up to k_max_tr].  `out` may be NULL
+ * (count only).  Returns the number of emitted points and the physical bookkeeping.
+ */
+static int k3_walk(const song_k3_params *p, const double *k3_pt, int np,
+                   double k_min_tr, double k_max_tr, double *out, int cap,
+                   int *n_out, int *phys_start, int *phys_size, int *n_pt_used)
+{
+  const double k_min_pt = k3_pt[0], k_max_pt = k3_pt[np - 1];
+  const double step = k3_linear_step(p);
+  if (step == 0) return 1;
+
+  int n = 0;
+  double k = k_min_tr;
+#define EMIT(v) do { if (out && n < cap) out[n] = (v); ++n; } while (0)
+  EMIT(k);
+  if (p->k3_extrapolation != 0) {
+    if (step < p->smallest_allowed_variation) return 2;
+    while (k < k_min_pt) { k += step; EMIT(k); }                 /* :1486 / :1638 */
+    if (k != k_min_pt) { k = k_min_pt; if (out && n - 1 < cap) out[n - 1] = k; }
+  }
+  *phys_start = n - 1;                                           /* :1498 */
+
+  int ipt = 1;
+  while (ipt < np && (k3_pt[ipt] - k) < step) {                  /* :1502 / :1653 */
+    k = k3_pt[ipt];
+    EMIT(k);
+    ++ipt;
+  }
+  *n_pt_used = ipt;
+  int physical = ipt;                                            /* :1509 */
+
+  while (k < k_max_tr) {                                         /* :1513 / :1663 */
+    k += step;
+    EMIT(k);
+    if (k <= k_max_pt && k >= k_min_pt) ++physical;
+  }
+  if (k > k_max_tr) --n;                                         /* :1525 */
+#undef EMIT
+  *n_out = n;
+  *phys_size = physical;
+  return 0;
+}
+
+int song_host_k3_size(const song_k3_params *p, const double *k3_pt, int np,
+                      song_k3_range *r, char *errmsg, int errlen)
+{
+  char buf[256];
+  if (np < 2) return host_fail(errmsg, errlen, "k3 grid of the sources has less than 2 points");
+  k3_limits(p, k3_pt[0], k3_pt[np - 1], &r->k_min, &r->k_max);
+  if (r->k_max > p->xx_max / p->tau0) {                          /* :1408 */
+    snprintf(buf, sizeof buf, "xx_max is not large enough. The projection functions J(k*(tau0-tau)) do not cover "
+             "the needed k-range (k_max=%g,tau0=%g,xx_max=%g). Maybe you are using too much extrapolation.",
+             r->k_max, p->tau0, p->xx_max);
+    return host_fail(errmsg, errlen, buf);
+  }
+  int used = 0;
+  int rc = k3_walk(p, k3_pt, np, r->k_min, r->k_max, NULL, 0, &r->k_size, &r->k_physical_start,
+                   &r->k_physical_size, &used);
+  if (rc == 1) return host_fail(errmsg, errlen, "stop to avoid infinite loop");             /* :1450 */
+  if (rc == 2) return host_fail(errmsg, errlen, "stopping to avoid segmentation fault, k3 step below smallest_allowed_variation");
+  if (r->k_size < 2)                                                                        /* :1531 */
+    return host_fail(errmsg, errlen, "found less than 2 valid values for the k-grid; k3_size_min must be at least 2");
+  if (p->k3_extrapolation == 0 && (r->k_physical_size != r->k_size || r->k_physical_start != 0))
+    return host_fail(errmsg, errlen, "when no extrapolation is requested, all k's should be physical, "
+                     "i.e. satisfy the triangular condition.");                              /* :1538-1546 */
+  return 0;
+}
+
+int song_host_k3_list(const song_k3_params *p, const double *k3_pt, int np,
+                      const song_k3_range *r, double *k3, int *last_used_index_pt,
+                      char *errmsg, int errlen)
+{
+  int n = 0, ps = 0, pz = 0, used = 0;
+  int rc = k3_walk(p, k3_pt, np, r->k_min, r->k_max, k3, r->k_size, &n, &ps, &pz, &used);
+  if (rc != 0) return host_fail(errmsg, errlen, "stop to avoid infinite loop");
+  if (last_used_index_pt) *last_used_index_pt = used;
+  if (n != r->k_size)
+    return host_fail(errmsg, errlen, "bug in k list calculation: size differs from transfer2_get_k3_size");
+  if (k3[r->k_size - 1] > r->k_max)                                                         /* :1670 */
+    return host_fail(errmsg, errlen, "bug in k list calculation, k_max_transfers2 is larger than k_max_tr");
+  for (int i = 0; i + 1 < r->k_size; ++i)                                                   /* :1727 */
+    if (k3[i] >= k3[i + 1])
+      return host_fail(errmsg, errlen, "bug in k list calculation, k3-grid is not strictly ascending");
+  return 0;
+}
+
+int song_host_k3_sizes(const song_k3_params *p, int n_pairs, const int *k3_pt_size,
+                       const int64_t *pt_off, const double *k3_pt, song_k3_range *ranges,
+                       int *k3_size_max, int64_t *k3_size_sum, char *errmsg, int errlen)
+{
+  int mx = 0;
+  int64_t sum = 0;
+  for (int i = 0; i < n_pairs; ++i) {
+    if (song_host_k3_size(p, k3_pt + pt_off[i], k3_pt_size[i], &ranges[i], errmsg, errlen)) return 1;
+    if (ranges[i].k_size > mx) mx = ranges[i].k_size;
+    sum += ranges[i].k_size;
+  }
+  if (k3_size_max) *k3_size_max = mx;                                                       /* :1816-1826 */
+  if (k3_size_sum) *k3_size_sum = sum;
+  return 0;
+}
+
+int song_host_k3_lists(const song_k3_params *p, int n_pairs, const int *k3_pt_size,
+                       const int64_t *pt_off, const double *k3_pt, const song_k3_range *ranges,
+                       const int64_t *tr_off, double *k3_tr, char *errmsg, int errlen)
+{
+  for (int i = 0; i < n_pairs; ++i)
+    if (song_host_k3_list(p, k3_pt + pt_off[i], k3_pt_size[i], &ranges[i], k3_tr + tr_off[i], NULL,
+                          errmsg, errlen))
+      return 1;
+  return 0;
+}

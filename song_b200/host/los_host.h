@@ -1,0 +1,54 @@
+/*
+ * los_host.h -- host-side C pieces of the transfer2 drop-in that do not touch the GPU:
+ * the k3 integration grids (kept on the host so that bispectra2.c / spectra2.c, which re-derive
+ * them through transfer2_get_k3_list, see bit-identical values) and the trapezoid time grid.
+ * Flat-argument forms; the struct-based SONG prototypes in transfer2_gpu.c forward to these.
+ */
+#ifndef SONG_LOS_HOST_H
+#define SONG_LOS_HOST_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* the scalars transfer2_get_k3_size / _list read from ppr, ppr2, ptr2, pbs2, ppt2 */
+typedef struct song_k3_params {
+  double tau0, tau_rec, rs_rec;          /* ptr2->tau0, tau_rec, rs_rec                 */
+  double k_first, k_last;                /* ppt2->k[0], ppt2->k[k_size-1]               */
+  int    k3_extrapolation;               /* ppr->bispectra_k3_extrapolation (0 = none)  */
+  double extra_k3_oscillations_left;     /* ppr->extra_k3_oscillations_left             */
+  double extra_k3_oscillations_right;    /* ppr->extra_k3_oscillations_right            */
+  int    k_sampling;                     /* ptr2->k_sampling: 0 bessel, 1 class/smart   */
+  double q_linstep_song;                 /* ppr2->q_linstep_song                        */
+  int    old_run_step;                   /* ppr->load_run && ppr2->old_run              */
+  double smallest_allowed_variation;     /* ppr->smallest_allowed_variation             */
+  double xx_max, xx_step;                /* pbs2->xx_max, pbs2->xx_step                 */
+} song_k3_params;
+
+typedef struct song_k3_range {
+  double k_min, k_max;                   /* ptr2->k_min_k1k2, k_max_k1k2                */
+  int k_size;                            /* ptr2->k_size_k1k2                           */
+  int k_physical_start;                  /* ptr2->k_physical_start_k1k2                 */
+  int k_physical_size;                   /* ptr2->k_physical_size_k1k2                  */
+} song_k3_range;
+
+/* reference: transfer2_get_k3_size, source/transfer2.c:1329-1551.  Returns 0 or 1 (+ message). */
+int song_host_k3_size(const song_k3_params *p, const double *k3_pt, int k3_pt_size,
+                      song_k3_range *out, char *errmsg, int errlen);
+/* reference: transfer2_get_k3_list, source/transfer2.c:1566-1737 */
+int song_host_k3_list(const song_k3_params *p, const double *k3_pt, int k3_pt_size,
+                      const song_k3_range *range, double *k3, int *last_used_index_pt,
+                      char *errmsg, int errlen);
+/* all pairs at once (transfer2_get_k3_sizes, source/transfer2.c:1752-1834): fills ranges[] and
+   returns k3_size_max / sum through the pointers */
+int song_host_k3_sizes(const song_k3_params *p, int n_pairs, const int *k3_pt_size,
+                       const int64_t *pt_off, const double *k3_pt, song_k3_range *ranges,
+                       int *k3_size_max, int64_t *k3_size_sum, char *errmsg, int errlen);
+int song_host_k3_lists(const song_k3_params *p, int n_pairs, const int *k3_pt_size,
+                       const int64_t *pt_off, const double *k3_pt, const song_k3_range *ranges,
+                       const int64_t *tr_off, double *k3_tr, char *errmsg, int errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

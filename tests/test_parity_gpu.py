@@ -1,0 +1,84 @@
+"""GPU parity: the CUDA path, called through the C-ABI, against the CPU oracle.
+
+EXACT mode must be bit-identical to the oracle (same statement order, no FMA contraction);
+FAST mode must agree to BASELINE.json's tolerance: max relative error 1e-9 on transfer
+functions above 1e-6 of their per-(l,m) maximum.
+"""
+import numpy as np
+import pytest
+
+from song_b200 import configs, workload
+from song_b200.engine import MODE_EXACT, MODE_FAST, LosEngine, Projection
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-9      # BASELINE.json north_star
+FLOOR = 1e-6        # fraction of the per-(l,m) maximum below which values are not compared
+
+
+def rel_err_above_floor(got, ref):
+    """max over tt of max |got-ref|/|ref| restricted to |ref| > FLOOR * max_k |ref[tt]|."""
+    worst = 0.0
+    for tt in range(ref.shape[0]):
+        mx = np.abs(ref[tt]).max()
+        if mx == 0:
+            assert np.all(got[tt] == 0)
+            continue
+        sel = np.abs(ref[tt]) > FLOOR * mx
+        worst = max(worst, float(np.max(np.abs(got[tt][sel] - ref[tt][sel]) / np.abs(ref[tt][sel]))))
+    return worst
+
+
+def run_both(oracle, params, kind="smooth", mode=MODE_EXACT, spline_J=False):
+    wl = workload.build_grids(params)
+    workload.fill_sources(wl, kind=kind)
+    oproj = oracle.build_projection(wl, spline=spline_J)
+    ref, nterms = oracle.OracleRun(wl, oproj).run()
+    eng = LosEngine(wl, device=0)
+    eng.set_projection(Projection(oproj.rows, oproj.index_xmin, oproj.x_size, oproj.ddrows))
+    got = eng.transfer_pairs(wl, mode=mode)
+    eng.close()
+    return wl, ref, got
+
+
+@pytest.mark.parametrize("k3_interp", ["linear", "cubic"])
+@pytest.mark.parametrize("kind", ["smooth", "noise"])
+def test_exact_bitwise_tiny(oracle, k3_interp, kind):
+    p = configs.tiny(sources_k3_interpolation=k3_interp)
+    wl, ref, got = run_both(oracle, p, kind=kind)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref), f"max abs diff {np.abs(got - ref).max()}"
+
+
+def test_exact_bitwise_temperature_only(oracle):
+    p = configs.tiny(output=["tBisp"], sources_k3_interpolation="cubic")
+    wl, ref, got = run_both(oracle, p)
+    assert np.array_equal(got, ref)
+
+
+def test_exact_bitwise_no_extrapolation(oracle):
+    p = configs.tiny(bispectra_k3_extrapolation="no_extrapolation", sources_k3_interpolation="cubic")
+    wl, ref, got = run_both(oracle, p)
+    assert np.all(wl.phys_start == 0) and np.array_equal(wl.phys_size, wl.k3_tr_size)
+    assert np.array_equal(got, ref)
+
+
+def test_exact_bitwise_cubic_bessel_interpolation(oracle):
+    p = configs.tiny(bessels_interpolation="cubic", sources_k3_interpolation="cubic")
+    wl, ref, got = run_both(oracle, p, spline_J=True)
+    assert np.array_equal(got, ref)
+
+
+def test_exact_bitwise_nonscalar_modes(oracle):
+    """m = 0,1,2: E/B mixing through J_EB (transfer2.c:1960-2061)."""
+    p = configs.tiny(modes_song=[0, 1, 2], sources_k3_interpolation="cubic", has_source_B=True)
+    wl, ref, got = run_both(oracle, p)
+    assert wl.layout.index_J_EB >= 0 and wl.layout.has_source_B
+    assert np.array_equal(got, ref)
+
+
+def test_exact_bitwise_quick_song_run(oracle):
+    """BASELINE configs[0] at full size (6.5e5 integrals)."""
+    wl, ref, got = run_both(oracle, configs.get("quick_song_run"))
+    assert wl.n_integrals == 654112
+    assert np.array_equal(got, ref)
