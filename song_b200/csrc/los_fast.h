@@ -1,0 +1,30 @@
+// los_fast.h -- interface between the C-ABI layer and the FAST (DMMA) path (internal).
+#pragma once
+#include <string>
+#include <vector>
+#include "../../include/song_los.h"
+#include "los_common.h"
+
+namespace songlos {
+
+// host copies of the index tables the FAST layout is derived from
+struct FastHostLayout {
+  int has_T, has_E, has_B;
+  int index_tt2_T, index_tt2_E, index_tt2_B;
+  int index_tp2_T, index_tp2_E, index_tp2_B;
+  int index_J_TT, index_J_EE, index_J_EB;
+  int l_max_los_t, l_max_los_p;
+  int l_size, m_size, L_size, n_transfers, xx_size;
+  const int *l, *m, *lm_array, *lm_src;
+  const unsigned char *block_nonzero;   // [J_size*L_size]
+  int64_t n_src_total;
+};
+
+struct FastState;
+FastState *fast_state_create();
+void fast_state_destroy(FastState *);
+void fast_invalidate_table(FastState *);
+int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, const int *h_unit_pair,
+                 int device_sms, cudaStream_t st, song_los_timing *tm, std::string &err);
+
+}  // namespace songlos

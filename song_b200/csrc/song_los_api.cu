@@ -12,18 +12,13 @@
 
 #include "../../include/song_los.h"
 #include "los_common.h"
+#include "los_fast.h"
 
 namespace songlos {
 // los_exact.cu
 cudaError_t launch_spline_k3(const Batch &b, int tau_size, int tp2_size, double *dd, int *err, cudaStream_t st);
 cudaError_t launch_los_exact(const ExactParams &P, int n_tiles, cudaStream_t st);
 size_t exact_smem_bytes(int tau_chunk, int tp2_size);
-// los_fast.cu
-struct FastState;
-FastState *fast_state_create();
-void fast_state_destroy(FastState *);
-int fast_compute(FastState *fs, const ExactParams &P, int device_sms, cudaStream_t st,
-                 song_los_timing *tm, std::string &err);
 // los_peaks.cu
 cudaError_t launch_dfma_probe(double *out, int iters, int blocks, int threads, cudaStream_t st);
 }  // namespace songlos
@@ -73,8 +68,9 @@ struct song_los_ctx {
 
   // batch
   song_los_batch hb{};          // scalar fields only are valid
-  std::vector<int> h_np, h_nt;
+  std::vector<int> h_np, h_nt, h_unit_pair;
   std::vector<int64_t> h_tr_off;
+  std::vector<unsigned char> h_block_nonzero;
   DevBuf<int> d_np, d_nt, d_phys_start, d_phys_size;
   DevBuf<int64_t> d_pt_off, d_tr_off, d_src_off;
   DevBuf<double> d_k3_pt, d_k3_tr, d_src, d_dd, d_out;
@@ -361,6 +357,8 @@ extern "C" int song_los_set_projection(song_los_ctx *ctx, const double *const *J
   }
   CK(upload(ctx->d_block_nonzero, block_nonzero.data(), block_nonzero.size(), ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->h_block_nonzero = block_nonzero;
+  fast_invalidate_table(ctx->fast);
   ctx->have_proj = true;
   return SONG_LOS_SUCCESS;
 }
@@ -424,6 +422,9 @@ extern "C" int song_los_upload_pairs(song_los_ctx *ctx, const song_los_batch *b)
   ctx->h_np.assign(b->k3_pt_size, b->k3_pt_size + n);
   ctx->h_nt.assign(b->k3_tr_size, b->k3_tr_size + n);
   ctx->h_tr_off.assign(b->tr_off, b->tr_off + n);
+  ctx->h_unit_pair.resize((size_t)b->n_units);
+  for (int p = 0; p < b->n_pairs; ++p)
+    std::fill(ctx->h_unit_pair.begin() + b->tr_off[p], ctx->h_unit_pair.begin() + b->tr_off[p] + b->k3_tr_size[p], p);
   ctx->have_batch = true;
   ctx->have_result = false;
   return SONG_LOS_SUCCESS;
@@ -494,7 +495,8 @@ extern "C" int song_los_compute(song_los_ctx *ctx, int mode, song_los_timing *tm
   fill_params(ctx, P);
 
   CK(cudaEventRecord(ctx->ev[0], st));
-  if (P.cubic_k3) {
+  const bool exact_path = (mode == SONG_LOS_MODE_EXACT || c.tau_sampling_mode != SONG_LOS_TAU_SOURCES);
+  if (P.cubic_k3 && exact_path) {
     CK(launch_spline_k3(P.b, c.tau_size, c.tp2_size, ctx->d_dd.p, ctx->d_err.p, st));
     t.n_launches++;
   }
@@ -517,11 +519,17 @@ extern "C" int song_los_compute(song_los_ctx *ctx, int mode, song_los_timing *tm
     CK(cudaEventElapsedTime(&t.ms_total, ctx->ev[0], ctx->ev[2]));
   } else if (mode == SONG_LOS_MODE_FAST) {
     std::string e;
-    if (fast_compute(ctx->fast, P, ctx->sm_count, st, &t, e) != 0) return fail(ctx, "%s", e.c_str());
-    CK(cudaEventRecord(ctx->ev[2], st));
-    CK(cudaEventSynchronize(ctx->ev[2]));
-    CK(cudaEventElapsedTime(&t.ms_spline, ctx->ev[0], ctx->ev[1]));
-    CK(cudaEventElapsedTime(&t.ms_total, ctx->ev[0], ctx->ev[2]));
+    FastHostLayout h{};
+    h.has_T = c.has_source_T; h.has_E = c.has_source_E; h.has_B = c.has_source_B;
+    h.index_tt2_T = c.index_tt2_T; h.index_tt2_E = c.index_tt2_E; h.index_tt2_B = c.index_tt2_B;
+    h.index_tp2_T = c.index_tp2_T; h.index_tp2_E = c.index_tp2_E; h.index_tp2_B = c.index_tp2_B;
+    h.index_J_TT = c.index_J_TT; h.index_J_EE = c.index_J_EE; h.index_J_EB = c.index_J_EB;
+    h.l_max_los_t = c.l_max_los_t; h.l_max_los_p = c.l_max_los_p;
+    h.l_size = c.l_size; h.m_size = c.m_size; h.L_size = c.L_size; h.n_transfers = c.n_transfers;
+    h.xx_size = c.xx_size; h.l = c.l; h.m = c.m; h.lm_array = c.lm_array; h.lm_src = c.lm_src;
+    h.block_nonzero = ctx->h_block_nonzero.data(); h.n_src_total = ctx->hb.n_src_total;
+    if (fast_compute(ctx->fast, h, P, ctx->h_unit_pair.data(), ctx->sm_count, st, &t, e) != 0)
+      return fail(ctx, "%s", e.c_str());
   } else {
     return fail(ctx, "song_los_compute: unknown mode %d", mode);
   }

@@ -82,3 +82,55 @@ def test_exact_bitwise_quick_song_run(oracle):
     wl, ref, got = run_both(oracle, configs.get("quick_song_run"))
     assert wl.n_integrals == 654112
     assert np.array_equal(got, ref)
+
+
+# ----------------------------------------------------------------------------------------------
+# FAST mode (k3-sorted DMMA kernel): BASELINE.json tolerance
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k3_interp", ["linear", "cubic"])
+@pytest.mark.parametrize("kind", ["smooth", "noise"])
+def test_fast_tolerance_tiny(oracle, k3_interp, kind):
+    p = configs.tiny(sources_k3_interpolation=k3_interp)
+    wl, ref, got = run_both(oracle, p, kind=kind, mode=MODE_FAST)
+    err = rel_err_above_floor(got, ref)
+    assert err < REL_TOL, err
+
+
+def test_fast_tolerance_temperature_only(oracle):
+    p = configs.tiny(output=["tBisp"], sources_k3_interpolation="cubic")
+    wl, ref, got = run_both(oracle, p, mode=MODE_FAST)
+    assert rel_err_above_floor(got, ref) < REL_TOL
+
+
+def test_fast_tolerance_no_extrapolation(oracle):
+    p = configs.tiny(bispectra_k3_extrapolation="no_extrapolation", sources_k3_interpolation="cubic")
+    wl, ref, got = run_both(oracle, p, mode=MODE_FAST)
+    assert rel_err_above_floor(got, ref) < REL_TOL
+
+
+def test_fast_tolerance_nonscalar_modes(oracle):
+    p = configs.tiny(modes_song=[0, 1, 2], sources_k3_interpolation="cubic", has_source_B=True)
+    wl, ref, got = run_both(oracle, p, mode=MODE_FAST)
+    assert rel_err_above_floor(got, ref) < REL_TOL
+
+
+def test_fast_tolerance_quick_song_run(oracle):
+    wl, ref, got = run_both(oracle, configs.get("quick_song_run"), mode=MODE_FAST)
+    assert rel_err_above_floor(got, ref) < REL_TOL
+
+
+def test_fast_many_columns_layouts(oracle):
+    """Column counts that exercise the (WM,WN) = (4,2) and (2,4) warp grids and partial sub-blocks."""
+    for lmax, linstep in ((300, 4), (700, 4)):
+        p = configs.tiny(l_max_scalars=lmax, l_linstep=linstep, l_logstep=1.05, sources_k3_interpolation="cubic",
+                         k_max_tau0_over_l_max_song=0.25)
+        wl, ref, got = run_both(oracle, p, mode=MODE_FAST)
+        assert wl.layout.l_size > 64
+        assert rel_err_above_floor(got, ref) < REL_TOL
+
+
+def test_fast_rejects_cubic_bessel_interpolation(oracle):
+    p = configs.tiny(bessels_interpolation="cubic")
+    from song_b200._lib import SongLosError
+    with pytest.raises(SongLosError, match="linear Bessel interpolation"):
+        run_both(oracle, p, mode=MODE_FAST, spline_J=True)
