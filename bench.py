@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- LOS transfer integrals per second of the transfer2 stage on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: under torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (song_los_compute: k3 spline, k3 sort, DMMA LOS kernel) over
+one batch of synthetic input.  At N=1 the workload is BASELINE.json configs[1]
+(ini/intrinsic.ini + pre/sn_t_10percent_lmax2000.pre, temperature only: 8.6e7 integrals).  With N
+ranks every rank processes its own (k1,k2) shard of the same size (independent sources, no
+data-path collective): weak scaling, value = all ranks' integrals / max-over-ranks time.
+
+`value`  : inputs resident in HBM when the timed region starts.
+`e2e`    : the same metric through the C-ABI call with HOST (pinned) buffers: every step copies the
+           sources and grids host->device and the transfer functions device->host.
+`--impl reference` : the CPU restatement of the reference's transfer2 loops (oracle/, OpenMP on all
+           host threads) on a bounded sample of the same workload.  The reference itself cannot be
+           built here (its CLASS fork is an empty submodule), so kind = "port".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+METRIC = "2nd-order LOS transfer integrals/sec (k1,k2,k3,l,m)"
+UNIT = "integrals/s"
+DEFAULT_WORKLOAD = "sn_t_10percent_lmax2000"
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# work counters
+# ----------------------------------------------------------------------------------------------
+def count_terms(wl, xmin, xsize) -> int:
+    """Exact number of (tau, L) terms that pass the reference's skip tests (transfer2.c:2217,2232),
+    summed over every stored integral: sum over (k3, tau) of #{(tt, L): index_x >= index_xmin_J}."""
+    lay = wl.layout
+    nx = wl.xx.size
+    hist = np.zeros(nx + 1, dtype=np.int64)
+    for tt in range(lay.tt2_size):
+        il, im = int(lay.tt_index_l[tt]), int(lay.tt_index_m[tt])
+        segs = []
+        if lay.has_source_T and lay.index_tt2_T <= tt < lay.index_tt2_T + lay.n_transfers:
+            segs.append((lay.index_J_TT, lay.l_max_los_t))
+        elif lay.has_source_E and lay.index_tt2_E <= tt < lay.index_tt2_E + lay.n_transfers:
+            segs.append((lay.index_J_EE, lay.l_max_los_p))
+            if lay.m[im] != 0:
+                segs.append((lay.index_J_EB, lay.l_max_los_p))
+        else:
+            segs.append((lay.index_J_EE, lay.l_max_los_p)); segs.append((lay.index_J_EB, lay.l_max_los_p))
+        for J, lmax in segs:
+            for L in range(lmax + 1):
+                if lay.m[im] > min(L, int(lay.l[il])):
+                    continue
+                jidx = ((J * lay.L_size + L) * lay.l_size + il) * lay.m_size + im
+                if xsize[jidx] <= 0:
+                    continue
+                hist[int(xmin[jidx])] += 1
+    cnt = np.cumsum(hist)            # cnt[ix] = number of (tt,L) with xmin <= ix
+    d = wl.cosmo["tau0"] - wl.tau
+    total = 0
+    step = 200_000
+    for s in range(0, wl.k3_tr.size, step):
+        x = wl.k3_tr[s:s + step, None] * d[None, :]
+        ix = (x / wl.xx_step).astype(np.int64)
+        total += int(cnt[np.minimum(ix, nx)].sum())
+    return total
+
+
+def pinned_copy(wl):
+    """The workload with its large host arrays in pinned memory (torch allocator)."""
+    import copy
+    import torch
+    out = copy.copy(wl)
+    keep = []
+    for name in ("src", "k3_pt", "k3_tr"):
+        t = torch.from_numpy(getattr(wl, name)).pin_memory()
+        keep.append(t)
+        setattr(out, name, t.numpy())
+    out._pinned = keep
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference arm: CPU restatement of transfer2 (oracle/) on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_sample(name: str, target_seconds: float, max_pairs=None):
+    """(sub-workload, projection) sized for about `target_seconds` of oracle time per pass."""
+    import oracle_lib as O
+    from song_b200 import configs, workload
+    p = configs.get(name)
+    grids = workload.build_grids(p, max_pairs=max_pairs)
+    # calibrate on a thin slice, then size the sample
+    probe_idx = np.unique(np.linspace(0, grids.n_pairs - 1, 24).astype(int))
+    probe = workload.fill_sources(grids.select(probe_idx))
+    proj = O.build_projection(grids)
+    run = O.OracleRun(probe, proj)
+    t = time.perf_counter(); run.run(); dt = time.perf_counter() - t
+    rate = probe.n_integrals / max(dt, 1e-6)
+    want = rate * target_seconds
+    stride = max(1, int(round(grids.n_integrals / max(want, 1.0))))
+    idx = np.arange(0, grids.n_pairs, stride)
+    sub = workload.fill_sources(grids.select(idx))
+    return grids, sub, proj, stride
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    import oracle_lib as O
+    from song_b200 import workload
+    grids, sub, proj, stride = cpu_sample(args.workload, args.cpu_seconds)
+    run = O.OracleRun(sub, proj)
+    for _ in range(args.warmup):
+        run.run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run.run()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = sub.n_integrals / dt
+    cores = O.lib().oracle_num_threads()
+    sample = (f"every {stride}-th (k1,k2) pair of {args.workload} in the reference loop order: {sub.n_pairs} of "
+              f"{grids.n_pairs} pairs, {sub.n_integrals} of {grids.n_integrals} integrals per step")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload.describe(grids), workload=args.workload,
+                       note="CPU restatement of reference transfer2 (reference not buildable here: class.git is an empty submodule)"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--max-pairs", type=int, default=None, help="debug: truncate the pair list")
+    ap.add_argument("--cpu-seconds", type=float, default=6.0, help="CPU time per oracle pass of the baselines")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from song_b200 import configs, workload
+    from song_b200.bessel2 import Bessel2
+    from song_b200.engine import MODE_EXACT, MODE_FAST, LosEngine
+
+    args.warmup = max(args.warmup, 3)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    mode = MODE_FAST if args.mode == "fast" else MODE_EXACT
+
+    # ---- inputs: every rank owns a shard of the same shape with its own sources (weak scaling) ----
+    p = configs.get(args.workload)
+    wl = workload.build_grids(p, max_pairs=args.max_pairs)
+    workload.fill_sources(wl, seed=20261017 + 7919 * rank)
+    eng = LosEngine(wl, device=local_rank)
+    b2 = Bessel2(wl).init(eng)                      # bessel2_init: host j_l1 + 3j, device J_Llm assembly
+    peaks = eng.measure_peaks()
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    wl_pin = pinned_copy(wl)
+    out_pin = torch.empty((wl.layout.tt2_size, wl.n_units), dtype=torch.float64).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: inputs resident in HBM ----
+    eng.upload(wl_pin)
+    for _ in range(args.warmup):
+        eng.compute(mode)
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern = {"ms_integrate": 0.0, "ms_spline": 0.0, "ms_sort": 0.0, "ms_interp": 0.0, "ms_total": 0.0}
+    launches = 0
+    barrier()
+    sampler.start()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        tm = eng.compute(mode)
+        for k in kern:
+            kern[k] += tm[k]
+        launches += tm["n_launches"]
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    for k in kern:
+        kern[k] /= args.steps
+    n_int_rank = wl.n_integrals
+    n_int_total = n_int_rank * world
+    value = n_int_total / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI call, H2D + D2H inside the timed region ----
+    out_np = out_pin.numpy()
+    eng.transfer_pairs(wl_pin, mode=mode, out=out_np)          # warm
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_host0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        eng.transfer_pairs(wl_pin, mode=mode, out=out_np)
+    e1.record(stream)
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t_host0) * 1e3) / args.steps)
+    h2d = int(wl.src.nbytes + wl.k3_pt.nbytes + wl.k3_tr.nbytes + 7 * 8 * wl.n_pairs)
+    d2h = int(out_np.nbytes)
+    e2e_value = n_int_total / (e2e_ms * 1e-3)
+    checksum = float(np.abs(out_np).sum())
+
+    # ---- multi-GPU: the one collective of the path, the gather of the per-GPU transfer arrays ----
+    gather_ms = None
+    if world > 1:
+        res = torch.empty(wl.layout.tt2_size * wl.n_units, dtype=torch.float64, device="cuda")
+        eng.copy_result_to(res.data_ptr(), res.numel())
+        bufs = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        dist.gather(res, bufs, dst=0)
+        g1.record()
+        barrier()
+        gather_ms = max_over_ranks(g0.elapsed_time(g1))
+
+    # ---- roofline of the dominant kernel (the DMMA LOS kernel) ----
+    rows, xmin, xsize = None, None, None
+    lay = wl.layout
+    n_j = lay.J_size * lay.L_size * lay.l_size * lay.m_size
+    xmin = np.zeros(n_j, dtype=np.int32); xsize = np.zeros(n_j, dtype=np.int32)
+    from song_b200 import _lib
+    _lib.los().song_los_get_projection(eng.ctx, _lib.iptr(xmin), _lib.iptr(xsize), None)
+    n_terms = count_terms(wl, xmin, xsize)
+    flops = 5.0 * n_terms + 2.0 * n_int_rank * wl.tau.size          # F = 5 N_terms + 2 N_int n_tau
+    t_kernel = kern["ms_integrate"] * 1e-3
+    achieved = flops / t_kernel / 1e12
+    peak = max(peaks["dmma_tflops"], peaks["dfma_tflops"])
+    alg_bytes = 8.0 * (n_int_rank + wl.src.size + wl.k3_pt.size + wl.k3_tr.size)
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "traffic_bytes.json")
+    if os.path.exists(tfile):
+        try:
+            traffic = json.load(open(tfile)).get(args.workload, {}).get("los_fast_kernel")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "tensor", "kernel": "los_fast_kernel (FP64 tensor core, DMMA m8n8k4)" if mode == MODE_FAST else "los_exact_kernel",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+        "peak_source": "measured in this run with song_los_measure_peaks (DMMA m8n8k4 loop; MEASURED_PEAKS.json has no FP64 entry)",
+        "algorithmic_flops_per_launch": flops, "n_terms": n_terms, "kernel_ms": kern["ms_integrate"],
+        "kernel_share_of_step": kern["ms_integrate"] / max(kern["ms_total"], 1e-9),
+        "dfma_peak_tflops": peaks["dfma_tflops"], "dmma_peak_tflops": peaks["dmma_tflops"],
+        "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / (kern["ms_total"] * 1e-3) / 1e9,
+                "peak_gbs": peaks["copy_gbs"], "frac": alg_bytes / (kern["ms_total"] * 1e-3) / 1e9 / peaks["copy_gbs"]},
+        "step_breakdown_ms": kern,
+    }
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle_lib as O
+        grids, sub, proj, stride = cpu_sample(args.workload, args.cpu_seconds, max_pairs=args.max_pairs)
+        run = O.OracleRun(sub, proj)
+        t0 = time.perf_counter(); ref, _ = run.run(); dt = time.perf_counter() - t0
+        cpu = {"value": sub.n_integrals / dt, "unit": UNIT, "cores": O.lib().oracle_num_threads(), "kind": "port",
+               "sample": f"every {stride}-th (k1,k2) pair, {sub.n_pairs} of {grids.n_pairs} pairs, "
+                         f"{sub.n_integrals} integrals, one pass of {dt:.1f} s; CPU restatement of reference transfer2 "
+                         f"(gcc -O3 -fopenmp, reference loop structure; reference not buildable here)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": dict(workload.describe(wl), workload=args.workload, mode=args.mode,
+                           per_gpu_integrals=n_int_rank, parallelism=f"(k1,k2)-pair shards x{world}, no data-path collective",
+                           l2_policy="inputs larger than L2: each step streams ~%.1f GB (sources, transposed sources, "
+                                     "projection table, output) against 126 MB of L2" %
+                                     ((3 * wl.src.nbytes + out_np.nbytes) / 1e9),
+                           tau_sampling="synthetic, geometric 230->330 then linear ->700 Mpc"),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "checksum_abs_sum": checksum},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        if gather_ms is not None:
+            line["nccl_gather_ms"] = gather_ms
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -181,13 +181,17 @@ int  song_los_transfer_pairs(song_los_ctx *ctx, const song_los_batch *batch, int
    done by the multi-GPU driver), as an integer address; 0 before the first compute. */
 uint64_t song_los_device_result(song_los_ctx *ctx, int64_t *n_doubles);
 
+/* Copies the result of the last compute into caller-owned DEVICE memory (device-to-device, on the
+   engine's stream, synchronised before returning): the hand-off to an NCCL gather. */
+int  song_los_copy_result(song_los_ctx *ctx, uint64_t device_dst, int64_t n_doubles);
+
 /* Runs the engine's kernels on an external CUDA stream (a cudaStream_t passed as void*),
    so that a caller's own events see the work.  NULL restores the engine's stream. */
 int  song_los_set_stream(song_los_ctx *ctx, void *cuda_stream);
 
-/* Roofline denominators measured on the device the context lives on:
-   dependent-free DFMA loop -> FP64 TFLOP/s; device-to-device copy -> GB/s. */
-int  song_los_measure_peaks(song_los_ctx *ctx, double *fp64_tflops, double *copy_gbs);
+/* Roofline denominators measured on the device the context lives on: dependency-free DFMA loop
+   and DMMA (m8n8k4) loop -> FP64 TFLOP/s; device-to-device copy -> GB/s (read+write bytes). */
+int  song_los_measure_peaks(song_los_ctx *ctx, double *dfma_tflops, double *dmma_tflops, double *copy_gbs);
 
 /* Free bytes / total bytes / SM count of the context's device. */
 int  song_los_device_info(song_los_ctx *ctx, int64_t *free_bytes, int64_t *total_bytes,

@@ -118,15 +118,28 @@ class K3Range(C.Structure):
     ]
 
 
+class Bessel2Host(C.Structure):
+    """struct song_bessel2_host (song_b200/host/bessel2_host.h)."""
+    _fields_ = [
+        ("l1_size", C.c_int), ("l1", c_int_p), ("index_l1", c_int_p), ("index_l1_len", C.c_int),
+        ("j_l1", C.POINTER(c_double_p)), ("index_xmin_l1", c_int_p), ("x_size_l1", c_int_p), ("x_min_l1", c_double_p),
+        ("n_jidx", C.c_int), ("ndim", C.c_int),
+        ("first_3j", c_double_p), ("second_3j", c_double_p),
+        ("l1_min", c_int_p), ("l1_count", c_int_p), ("index_l1_of_l1min", c_int_p),
+        ("count_allocated_Js", C.c_long),
+    ]
+
+
 #: every symbol include/song_los.h declares (checked by tests/test_abi.py without a GPU)
 LOS_SYMBOLS = [
     "song_los_create", "song_los_destroy", "song_los_last_error", "song_los_set_projection",
     "song_los_build_projection", "song_los_get_projection", "song_los_upload_pairs",
     "song_los_compute", "song_los_download", "song_los_transfer_pairs",
-    "song_los_device_result", "song_los_set_stream", "song_los_measure_peaks",
+    "song_los_device_result", "song_los_copy_result", "song_los_set_stream", "song_los_measure_peaks",
     "song_los_device_info", "song_los_version",
 ]
-HOST_SYMBOLS = ["song_host_k3_size", "song_host_k3_list", "song_host_k3_sizes", "song_host_k3_lists"]
+HOST_SYMBOLS = ["song_host_k3_size", "song_host_k3_list", "song_host_k3_sizes", "song_host_k3_lists",
+                "song_host_bessel2_prepare", "song_host_bessel2_free", "song_host_bessel2_upload"]
 
 _los = None
 _host = None
@@ -158,7 +171,8 @@ def los():
         lib.song_los_device_result.argtypes = [vp, c_int64_p]
         lib.song_los_device_result.restype = C.c_uint64
         lib.song_los_set_stream.argtypes = [vp, vp]
-        lib.song_los_measure_peaks.argtypes = [vp, c_double_p, c_double_p]
+        lib.song_los_measure_peaks.argtypes = [vp, c_double_p, c_double_p, c_double_p]
+        lib.song_los_copy_result.argtypes = [vp, C.c_uint64, C.c_int64]
         lib.song_los_device_info.argtypes = [vp, c_int64_p, c_int64_p, c_int_p, C.c_char_p, C.c_int]
         lib.song_los_version.argtypes = []
         _los = lib
@@ -179,6 +193,15 @@ def host():
                                            C.POINTER(K3Range), c_int_p, c_int64_p, C.c_char_p, C.c_int]
         lib.song_host_k3_lists.argtypes = [C.POINTER(K3Params), C.c_int, c_int_p, c_int64_p, c_double_p,
                                            C.POINTER(K3Range), c_int64_p, c_double_p, C.c_char_p, C.c_int]
+        lib.song_host_bessel2_prepare.argtypes = [c_int_p, C.c_int, c_int_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_double,
+                                                  C.c_int, c_int_p, C.c_double, C.c_double, C.c_double,
+                                                  C.POINTER(C.POINTER(Bessel2Host)), C.c_char_p, C.c_int]
+        lib.song_host_bessel2_free.argtypes = [C.POINTER(Bessel2Host)]
+        lib.song_host_bessel2_upload.argtypes = [C.c_void_p, C.POINTER(Bessel2Host), c_int_p, C.c_double, C.c_double,
+                                                 C.c_char_p, C.c_int]
+        lib.compat_drc3jj.argtypes = [C.c_double] * 4 + [c_double_p, c_double_p, c_double_p, C.c_int]
+        lib.compat_bessel_j.argtypes = [C.c_int, C.c_double]
+        lib.compat_bessel_j.restype = C.c_double
         _host = lib
     return _host
 

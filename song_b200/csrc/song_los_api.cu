@@ -13,6 +13,7 @@
 #include "../../include/song_los.h"
 #include "los_common.h"
 #include "los_fast.h"
+#include "song_los_ctx.h"
 
 namespace songlos {
 // los_exact.cu
@@ -21,6 +22,7 @@ cudaError_t launch_los_exact(const ExactParams &P, int n_tiles, cudaStream_t st)
 size_t exact_smem_bytes(int tau_chunk, int tp2_size);
 // los_peaks.cu
 cudaError_t launch_dfma_probe(double *out, int iters, int blocks, int threads, cudaStream_t st);
+cudaError_t launch_dmma_probe(double *out, int iters, int blocks, int threads, cudaStream_t st);
 }  // namespace songlos
 
 using namespace songlos;
@@ -28,62 +30,7 @@ using namespace songlos;
 static std::string g_create_error;
 static std::mutex g_mutex;
 
-template <typename T>
-struct DevBuf {
-  T *p = nullptr;
-  size_t cap = 0;  // elements
-  cudaError_t reserve(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
-    if (e == cudaSuccess) cap = n;
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct song_los_ctx {
-  int device = 0;
-  int sm_count = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  std::string err;
-
-  // configuration (host copies)
-  song_los_config cfg{};
-  std::vector<double> tau, xx;
-  std::vector<int> l, m, lm_array, lm_src, tt_index_l, tt_index_m;
-  std::vector<int> tt_type, tt_lm, tt_l, tt_m, tt_im;
-
-  // static device tables
-  DevBuf<double> d_tau, d_tau0_minus_tau, d_delta_tau, d_xx;
-  DevBuf<int> d_tt_type, d_tt_lm, d_tt_l, d_tt_m, d_tt_im, d_lm_src;
-  DevBuf<double2> d_J, d_ddJ;
-  DevBuf<unsigned char> d_block_nonzero;
-  int64_t n_cols = 0;
-  bool have_proj = false;
-  // ragged mirror kept for song_los_get_projection
-  DevBuf<double> d_ragged; DevBuf<int64_t> d_col_off; DevBuf<int> d_col_xmin, d_col_xsize;
-  std::vector<int> h_col_xmin, h_col_xsize; std::vector<int64_t> h_col_off;
-
-  // batch
-  song_los_batch hb{};          // scalar fields only are valid
-  std::vector<int> h_np, h_nt, h_unit_pair;
-  std::vector<int64_t> h_tr_off;
-  std::vector<unsigned char> h_block_nonzero;
-  DevBuf<int> d_np, d_nt, d_phys_start, d_phys_size;
-  DevBuf<int64_t> d_pt_off, d_tr_off, d_src_off;
-  DevBuf<double> d_k3_pt, d_k3_tr, d_src, d_dd, d_out;
-  DevBuf<int2> d_tiles; int n_tiles = 0;
-  DevBuf<int> d_err;
-  DevBuf<double> d_scratch;
-  bool have_batch = false, have_result = false;
-
-  FastState *fast = nullptr;
-  cudaEvent_t ev[8]{};
-};
-
-static int fail(song_los_ctx *c, const char *fmt, ...)
+int ctx_fail(song_los_ctx *c, const char *fmt, ...)
 {
   char buf[1024];
   va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
@@ -91,7 +38,7 @@ static int fail(song_los_ctx *c, const char *fmt, ...)
   return SONG_LOS_FAILURE;
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
-  return fail(ctx, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+  return ctx_fail(ctx, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
 
 template <typename T>
 static cudaError_t upload(DevBuf<T> &d, const T *h, size_t n, cudaStream_t st)
@@ -112,33 +59,33 @@ extern "C" const char *song_los_last_error(const song_los_ctx *ctx)
 extern "C" int song_los_create(const song_los_config *cfg, song_los_ctx **out)
 {
   song_los_ctx *ctx = nullptr;
-  if (!cfg || !out) return fail(nullptr, "song_los_create: NULL argument");
+  if (!cfg || !out) return ctx_fail(nullptr, "song_los_create: NULL argument");
   *out = nullptr;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
-    return fail(nullptr, "song_los_create: no CUDA device available (%s); there is no CPU fallback",
+    return ctx_fail(nullptr, "song_los_create: no CUDA device available (%s); there is no CPU fallback",
                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
   if (cfg->device < 0 || cfg->device >= ndev)
-    return fail(nullptr, "song_los_create: device %d out of range (have %d)", cfg->device, ndev);
-  if (cfg->tau_size < 2) return fail(nullptr, "song_los_create: tau_size=%d < 2", cfg->tau_size);
-  if (cfg->xx_size < 2 || cfg->xx_step <= 0) return fail(nullptr, "song_los_create: bad xx grid");
+    return ctx_fail(nullptr, "song_los_create: device %d out of range (have %d)", cfg->device, ndev);
+  if (cfg->tau_size < 2) return ctx_fail(nullptr, "song_los_create: tau_size=%d < 2", cfg->tau_size);
+  if (cfg->xx_size < 2 || cfg->xx_step <= 0) return ctx_fail(nullptr, "song_los_create: bad xx grid");
   if (cfg->tt2_size < 1 || cfg->tp2_size < 1 || cfg->l_size < 1 || cfg->m_size < 1 || cfg->L_size < 1)
-    return fail(nullptr, "song_los_create: empty index tables");
+    return ctx_fail(nullptr, "song_los_create: empty index tables");
   if (cfg->tt2_size > 32 * EXACT_MAX_TT_PASSES)
-    return fail(nullptr, "song_los_create: tt2_size=%d exceeds the supported %d", cfg->tt2_size, 32 * EXACT_MAX_TT_PASSES);
+    return ctx_fail(nullptr, "song_los_create: tt2_size=%d exceeds the supported %d", cfg->tt2_size, 32 * EXACT_MAX_TT_PASSES);
   if (cfg->l_max_los_t >= cfg->L_size || cfg->l_max_los_p >= cfg->L_size)
-    return fail(nullptr, "song_los_create: l_max_los exceeds L_size-1");
+    return ctx_fail(nullptr, "song_los_create: l_max_los exceeds L_size-1");
 
   ctx = new song_los_ctx();
   ctx->device = cfg->device;
   ctx->cfg = *cfg;
-  if (cudaSetDevice(ctx->device) != cudaSuccess) { delete ctx; return fail(nullptr, "cudaSetDevice failed"); }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { delete ctx; return ctx_fail(nullptr, "cudaSetDevice failed"); }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, ctx->device);
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
-    delete ctx; return fail(nullptr, "cudaStreamCreate failed");
+    delete ctx; return ctx_fail(nullptr, "cudaStreamCreate failed");
   }
   ctx->stream = ctx->own_stream;
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
@@ -165,10 +112,10 @@ extern "C" int song_los_create(const song_los_config *cfg, song_los_ctx **out)
     if (cfg->has_source_T && tt >= cfg->index_tt2_T && tt < cfg->index_tt2_T + cfg->n_transfers) { type = 0; base = cfg->index_tt2_T; }
     else if (cfg->has_source_E && tt >= cfg->index_tt2_E && tt < cfg->index_tt2_E + cfg->n_transfers) { type = 1; base = cfg->index_tt2_E; }
     else if (cfg->has_source_B && tt >= cfg->index_tt2_B && tt < cfg->index_tt2_B + cfg->n_transfers) { type = 2; base = cfg->index_tt2_B; }
-    if (type < 0) { song_los_destroy(ctx); return fail(nullptr, "song_los_create: transfer type %d belongs to no field", tt); }
+    if (type < 0) { song_los_destroy(ctx); return ctx_fail(nullptr, "song_los_create: transfer type %d belongs to no field", tt); }
     int il = cfg->tt_index_l[tt], im = cfg->tt_index_m[tt];
     if (il < 0 || il >= cfg->l_size || im < 0 || im >= cfg->m_size) {
-      song_los_destroy(ctx); return fail(nullptr, "song_los_create: (index_l,index_m) of tt=%d out of bounds", tt);
+      song_los_destroy(ctx); return ctx_fail(nullptr, "song_los_create: (index_l,index_m) of tt=%d out of bounds", tt);
     }
     ctx->tt_type[tt] = type;
     ctx->tt_lm[tt] = tt - base;
@@ -176,7 +123,7 @@ extern "C" int song_los_create(const song_los_config *cfg, song_los_ctx **out)
     ctx->tt_m[tt] = cfg->m[im];
     ctx->tt_im[tt] = im;
     if (cfg->lm_array[(size_t)il * cfg->m_size + im] != tt - base) {
-      song_los_destroy(ctx); return fail(nullptr, "song_los_create: lm_array inconsistent with corresponding_index at tt=%d", tt);
+      song_los_destroy(ctx); return ctx_fail(nullptr, "song_los_create: lm_array inconsistent with corresponding_index at tt=%d", tt);
     }
   }
 
@@ -201,7 +148,7 @@ extern "C" int song_los_create(const song_los_config *cfg, song_los_ctx **out)
          && ctx->d_err.reserve(1) == cudaSuccess
          && cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), st) == cudaSuccess
          && cudaStreamSynchronize(st) == cudaSuccess;
-  if (!ok) { song_los_destroy(ctx); return fail(nullptr, "song_los_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError())); }
+  if (!ok) { song_los_destroy(ctx); return ctx_fail(nullptr, "song_los_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError())); }
   ctx->fast = fast_state_create();
   *out = ctx;
   return SONG_LOS_SUCCESS;
@@ -222,6 +169,7 @@ extern "C" int song_los_destroy(song_los_ctx *ctx)
   ctx->d_k3_pt.release(); ctx->d_k3_tr.release(); ctx->d_src.release(); ctx->d_dd.release();
   ctx->d_out.release(); ctx->d_tiles.release(); ctx->d_err.release(); ctx->d_scratch.release();
   if (ctx->fast) fast_state_destroy(ctx->fast);
+  if (ctx->d_proj_rows) cudaFree(ctx->d_proj_rows);
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -297,11 +245,11 @@ extern "C" int song_los_set_projection(song_los_ctx *ctx, const double *const *J
                                        const double *const *ddJ_rows,
                                        const int *index_xmin_J, const int *x_size_J)
 {
-  if (!ctx || !J_rows || !index_xmin_J || !x_size_J) return fail(ctx, "song_los_set_projection: NULL argument");
+  if (!ctx || !J_rows || !index_xmin_J || !x_size_J) return ctx_fail(ctx, "song_los_set_projection: NULL argument");
   CK(cudaSetDevice(ctx->device));
   const song_los_config &c = ctx->cfg;
   if (c.bessels_interpolation == SONG_LOS_INTERP_CUBIC && !ddJ_rows)
-    return fail(ctx, "song_los_set_projection: cubic Bessel interpolation needs ddJ rows");
+    return ctx_fail(ctx, "song_los_set_projection: cubic Bessel interpolation needs ddJ rows");
   ctx->n_cols = (int64_t)c.J_size * c.L_size * c.n_transfers;
   ctx->h_col_off.assign((size_t)ctx->n_cols, 0);
   ctx->h_col_xmin.assign((size_t)ctx->n_cols, c.xx_size);
@@ -321,7 +269,7 @@ extern "C" int song_los_set_projection(song_los_ctx *ctx, const double *const *J
           if (!J_rows[jidx]) continue;
           int xs = x_size_J[jidx], xm = index_xmin_J[jidx];
           if (xs < 1 || xm < 0 || xm + xs > c.xx_size)
-            return fail(ctx, "song_los_set_projection: row (J=%d,L=%d,il=%d,im=%d) has xmin=%d size=%d outside xx_size=%d",
+            return ctx_fail(ctx, "song_los_set_projection: row (J=%d,L=%d,il=%d,im=%d) has xmin=%d size=%d outside xx_size=%d",
                         J, L, il, im, xm, xs, c.xx_size);
           int64_t col = ((int64_t)J * c.L_size + L) * c.n_transfers + lm;
           // a row holding the single value 0 at the last grid point is the reference's
@@ -343,7 +291,7 @@ extern "C" int song_los_set_projection(song_los_ctx *ctx, const double *const *J
   if (c.bessels_interpolation == SONG_LOS_INTERP_CUBIC) {
     for (int64_t col = 0; col < ctx->n_cols; ++col)
       if (src_jidx[(size_t)col] >= 0) {
-        if (!ddJ_rows[src_jidx[(size_t)col]]) return fail(ctx, "song_los_set_projection: missing ddJ row");
+        if (!ddJ_rows[src_jidx[(size_t)col]]) return ctx_fail(ctx, "song_los_set_projection: missing ddJ row");
         std::memcpy(flat.data() + ctx->h_col_off[(size_t)col], ddJ_rows[src_jidx[(size_t)col]],
                     (size_t)ctx->h_col_xsize[(size_t)col] * sizeof(double));
       }
@@ -368,28 +316,28 @@ extern "C" int song_los_set_projection(song_los_ctx *ctx, const double *const *J
 // ---------------------------------------------------------------------------------------------
 extern "C" int song_los_upload_pairs(song_los_ctx *ctx, const song_los_batch *b)
 {
-  if (!ctx || !b) return fail(ctx, "song_los_upload_pairs: NULL argument");
+  if (!ctx || !b) return ctx_fail(ctx, "song_los_upload_pairs: NULL argument");
   CK(cudaSetDevice(ctx->device));
   const song_los_config &c = ctx->cfg;
-  if (b->n_pairs < 0) return fail(ctx, "song_los_upload_pairs: negative n_pairs");
+  if (b->n_pairs < 0) return ctx_fail(ctx, "song_los_upload_pairs: negative n_pairs");
   // consistency checks (the reference's class_test of transfer2.c:1766-1771 and layout checks)
   int64_t pt = 0, tr = 0, so = 0;
   for (int p = 0; p < b->n_pairs; ++p) {
     int np = b->k3_pt_size[p], nt = b->k3_tr_size[p];
     int need = (c.sources_k3_interpolation == SONG_LOS_INTERP_CUBIC) ? 4 : 2;
     if (np < need)
-      return fail(ctx, "pair %d: cannot do interpolation in k3 with just k3_size=%d values. Increase k3_size.", p, np);
-    if (nt < 1) return fail(ctx, "pair %d: empty k3 grid", p);
+      return ctx_fail(ctx, "pair %d: cannot do interpolation in k3 with just k3_size=%d values. Increase k3_size.", p, np);
+    if (nt < 1) return ctx_fail(ctx, "pair %d: empty k3 grid", p);
     if (b->phys_start[p] < 0 || b->phys_size[p] < 1 || b->phys_start[p] + b->phys_size[p] > nt)
-      return fail(ctx, "pair %d: physical range [%d,+%d) outside the k3 grid of %d points", p, b->phys_start[p], b->phys_size[p], nt);
+      return ctx_fail(ctx, "pair %d: physical range [%d,+%d) outside the k3 grid of %d points", p, b->phys_start[p], b->phys_size[p], nt);
     if (c.k3_extrapolation == SONG_LOS_NO_K3_EXTRAPOLATION && (b->phys_start[p] != 0 || b->phys_size[p] != nt))
-      return fail(ctx, "pair %d: when no extrapolation is requested, all k's should be physical", p);
+      return ctx_fail(ctx, "pair %d: when no extrapolation is requested, all k's should be physical", p);
     if (b->pt_off[p] != pt || b->tr_off[p] != tr || b->src_off[p] != so)
-      return fail(ctx, "pair %d: offsets are not the running sums of the sizes (packed layout expected)", p);
+      return ctx_fail(ctx, "pair %d: offsets are not the running sums of the sizes (packed layout expected)", p);
     pt += np; tr += nt; so += (int64_t)c.tp2_size * c.tau_size * np;
   }
   if (pt != b->n_pt_total || tr != b->n_units || so != b->n_src_total)
-    return fail(ctx, "song_los_upload_pairs: totals do not match the per-pair sizes");
+    return ctx_fail(ctx, "song_los_upload_pairs: totals do not match the per-pair sizes");
 
   cudaStream_t st = ctx->stream;
   size_t n = (size_t)b->n_pairs;
@@ -468,10 +416,10 @@ static int check_device_errors(song_los_ctx *ctx)
   if (h) {
     cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), ctx->stream);
     if (h & ERR_X_OUT_OF_RANGE)
-      return fail(ctx, "not enough J's: k*(tau0-tau) exceeds xx_max (transfer2.c:2172); increase l_max or decrease k_max");
-    if (h & ERR_H_ZERO) return fail(ctx, "stop to avoid division by zero in the k3 interpolation (or k3_size outside [3,256])");
-    if (h & ERR_TAU_GRID_OVERFLOW) return fail(ctx, "time integration grid larger than the allocated maximum");
-    if (h & ERR_NAN) return fail(ctx, "found nan in second-order transfer function");
+      return ctx_fail(ctx, "not enough J's: k*(tau0-tau) exceeds xx_max (transfer2.c:2172); increase l_max or decrease k_max");
+    if (h & ERR_H_ZERO) return ctx_fail(ctx, "stop to avoid division by zero in the k3 interpolation (or k3_size outside [3,256])");
+    if (h & ERR_TAU_GRID_OVERFLOW) return ctx_fail(ctx, "time integration grid larger than the allocated maximum");
+    if (h & ERR_NAN) return ctx_fail(ctx, "found nan in second-order transfer function");
   }
   return SONG_LOS_SUCCESS;
 }
@@ -480,8 +428,8 @@ extern "C" int song_los_compute(song_los_ctx *ctx, int mode, song_los_timing *tm
 {
   if (!ctx) return SONG_LOS_FAILURE;
   CK(cudaSetDevice(ctx->device));
-  if (!ctx->have_proj) return fail(ctx, "song_los_compute: projection functions not set (bessel2 first)");
-  if (!ctx->have_batch) return fail(ctx, "song_los_compute: no pairs uploaded");
+  if (!ctx->have_proj) return ctx_fail(ctx, "song_los_compute: projection functions not set (bessel2 first)");
+  if (!ctx->have_batch) return ctx_fail(ctx, "song_los_compute: no pairs uploaded");
   const song_los_config &c = ctx->cfg;
   song_los_timing t{};
   t.n_integrals = ctx->hb.n_units * c.tt2_size;
@@ -504,11 +452,11 @@ extern "C" int song_los_compute(song_los_ctx *ctx, int mode, song_los_timing *tm
 
   if (mode == SONG_LOS_MODE_EXACT || c.tau_sampling_mode != SONG_LOS_TAU_SOURCES) {
     if (c.tau_sampling_mode != SONG_LOS_TAU_SOURCES)
-      return fail(ctx, "song_los_compute: custom/bessel tau sampling is not available in this build");
+      return ctx_fail(ctx, "song_los_compute: custom/bessel tau sampling is not available in this build");
     // tau chunk: as many time samples as fit in ~96 KB of shared memory
     size_t per_tau = exact_smem_bytes(1, c.tp2_size) - 16;
     int chunk = (int)std::min<size_t>((size_t)c.tau_size, (96 * 1024) / per_tau);
-    if (chunk < 1) return fail(ctx, "song_los_compute: tp2_size=%d too large for the shared-memory stage", c.tp2_size);
+    if (chunk < 1) return ctx_fail(ctx, "song_los_compute: tp2_size=%d too large for the shared-memory stage", c.tp2_size);
     P.tau_chunk = chunk;
     CK(launch_los_exact(P, ctx->n_tiles, st));
     t.n_launches++;
@@ -529,9 +477,9 @@ extern "C" int song_los_compute(song_los_ctx *ctx, int mode, song_los_timing *tm
     h.xx_size = c.xx_size; h.l = c.l; h.m = c.m; h.lm_array = c.lm_array; h.lm_src = c.lm_src;
     h.block_nonzero = ctx->h_block_nonzero.data(); h.n_src_total = ctx->hb.n_src_total;
     if (fast_compute(ctx->fast, h, P, ctx->h_unit_pair.data(), ctx->sm_count, st, &t, e) != 0)
-      return fail(ctx, "%s", e.c_str());
+      return ctx_fail(ctx, "%s", e.c_str());
   } else {
-    return fail(ctx, "song_los_compute: unknown mode %d", mode);
+    return ctx_fail(ctx, "song_los_compute: unknown mode %d", mode);
   }
   if (check_device_errors(ctx) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
   ctx->have_result = true;
@@ -541,9 +489,9 @@ extern "C" int song_los_compute(song_los_ctx *ctx, int mode, song_los_timing *tm
 
 extern "C" int song_los_download(song_los_ctx *ctx, double *transfer)
 {
-  if (!ctx || !transfer) return fail(ctx, "song_los_download: NULL argument");
+  if (!ctx || !transfer) return ctx_fail(ctx, "song_los_download: NULL argument");
   CK(cudaSetDevice(ctx->device));
-  if (!ctx->have_result) return fail(ctx, "song_los_download: nothing computed yet");
+  if (!ctx->have_result) return ctx_fail(ctx, "song_los_download: nothing computed yet");
   size_t n = (size_t)ctx->hb.n_units * ctx->cfg.tt2_size;
   CK(cudaMemcpyAsync(transfer, ctx->d_out.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -565,28 +513,44 @@ extern "C" uint64_t song_los_device_result(song_los_ctx *ctx, int64_t *n_doubles
   return (uint64_t)(uintptr_t)ctx->d_out.p;
 }
 
-extern "C" int song_los_measure_peaks(song_los_ctx *ctx, double *fp64_tflops, double *copy_gbs)
+extern "C" int song_los_copy_result(song_los_ctx *ctx, uint64_t device_dst, int64_t n_doubles)
+{
+  if (!ctx || !device_dst) return ctx_fail(ctx, "song_los_copy_result: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->have_result) return ctx_fail(ctx, "song_los_copy_result: nothing computed yet");
+  int64_t n = ctx->hb.n_units * ctx->cfg.tt2_size;
+  if (n_doubles != n) return ctx_fail(ctx, "song_los_copy_result: expected %lld doubles, got %lld", (long long)n, (long long)n_doubles);
+  CK(cudaMemcpyAsync((void *)(uintptr_t)device_dst, ctx->d_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SONG_LOS_SUCCESS;
+}
+
+extern "C" int song_los_measure_peaks(song_los_ctx *ctx, double *dfma_tflops, double *dmma_tflops, double *copy_gbs)
 {
   if (!ctx) return SONG_LOS_FAILURE;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  if (fp64_tflops) {
+  for (int which = 0; which < 2; ++which) {
+    double *dst = which ? dmma_tflops : dfma_tflops;
+    if (!dst) continue;
     const int threads = 256, blocks = ctx->sm_count * 8, iters = 4096;
     DevBuf<double> sink;
     CK(sink.reserve((size_t)blocks * threads));
-    CK(launch_dfma_probe(sink.p, 64, blocks, threads, st));      // warm-up
+    auto launch = [&](int it) { return which ? launch_dmma_probe(sink.p, it, blocks, threads, st) : launch_dfma_probe(sink.p, it, blocks, threads, st); };
+    CK(launch(64));      // warm-up
     float best = 1e30f;
     for (int rep = 0; rep < 5; ++rep) {
       CK(cudaEventRecord(ctx->ev[3], st));
-      CK(launch_dfma_probe(sink.p, iters, blocks, threads, st));
+      CK(launch(iters));
       CK(cudaEventRecord(ctx->ev[4], st));
       CK(cudaEventSynchronize(ctx->ev[4]));
       float ms; CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
       best = std::min(best, ms);
     }
-    // 16 independent chains x 2 flop per DFMA per iteration per thread
-    double flops = 2.0 * 16.0 * iters * (double)blocks * threads;
-    *fp64_tflops = flops / (best * 1e-3) / 1e12;
+    // DFMA: 16 chains x 2 flop per thread-iteration; DMMA: 8 MMAs x 512 flop per warp-iteration
+    double flops = which ? 2.0 * 256 * 8 * iters * (double)blocks * (threads / 32)
+                         : 2.0 * 16.0 * iters * (double)blocks * threads;
+    *dst = flops / (best * 1e-3) / 1e12;
     sink.release();
   }
   if (copy_gbs) {
@@ -610,4 +574,3 @@ extern "C" int song_los_measure_peaks(song_los_ctx *ctx, double *fp64_tflops, do
   return SONG_LOS_SUCCESS;
 }
 
-// song_los_build_projection / song_los_get_projection live in song_los_proj.cu

@@ -130,10 +130,14 @@ class LosEngine:
         ptr = self.lib.song_los_device_result(self.ctx, C.byref(n))
         return int(ptr), int(n.value)
 
-    def measure_peaks(self):
-        f, c = C.c_double(0), C.c_double(0)
-        self._check(self.lib.song_los_measure_peaks(self.ctx, C.byref(f), C.byref(c)))
-        return {"fp64_tflops": f.value, "copy_gbs": c.value}
+    def copy_result_to(self, device_ptr: int, n_doubles: int):
+        """Device-to-device copy of the last result into caller-owned device memory (e.g. a torch tensor)."""
+        self._check(self.lib.song_los_copy_result(self.ctx, C.c_uint64(device_ptr), C.c_int64(n_doubles)))
+
+    def measure_peaks(self, copy: bool = True):
+        f, t, c = C.c_double(0), C.c_double(0), C.c_double(0)
+        self._check(self.lib.song_los_measure_peaks(self.ctx, C.byref(f), C.byref(t), C.byref(c) if copy else None))
+        return {"dfma_tflops": f.value, "dmma_tflops": t.value, "copy_gbs": c.value}
 
     def device_info(self):
         fr, tot, sm = C.c_int64(0), C.c_int64(0), C.c_int(0)

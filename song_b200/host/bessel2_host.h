@@ -1,0 +1,38 @@
+/*
+ * bessel2_host.h -- host half of the bessel2 drop-in: everything bessel2_init (reference
+ * source/bessel2.c:75-468) computes on the host before the J_Llm assembly, which runs on the GPU
+ * through song_los_build_projection.
+ */
+#ifndef SONG_BESSEL2_HOST_H
+#define SONG_BESSEL2_HOST_H
+#include "../../include/song_los.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* the j_l1 members of struct bessels2 (include/bessel2.h:96-106) plus the 3j symbols of every
+   (J,L,l,m) table, flattened with jidx = ((J*L_size + L)*l_size + il)*m_size + im */
+typedef struct song_bessel2_host {
+  int l1_size; int *l1; int *index_l1; int index_l1_len;
+  double **j_l1; int *index_xmin_l1; int *x_size_l1; double *x_min_l1;
+  int n_jidx, ndim;
+  double *first_3j, *second_3j;            /* [n_jidx][ndim] */
+  int *l1_min, *l1_count, *index_l1_of_l1min;
+  long count_allocated_Js;
+} song_bessel2_host;
+
+/* bessel2_get_l1_list (:832-943), bessel2_j_for_l1 (:1669-1815) for every l1, and the drc3jj
+   calls of bessel2_J_for_Llm (:1131,:1154).  J_types[index_J] is SONG_LOS_J_TT/EE/EB. */
+int song_host_bessel2_prepare(const int *l, int l_size, const int *m, int m_size, int L_max,
+                              const double *xx, int xx_size, double xx_max,
+                              int J_size, const int *J_types,
+                              double j_l1_cut, double bessel_tol_x_min, double smallest_allowed_variation,
+                              song_bessel2_host **out, char *errmsg, int errlen);
+void song_host_bessel2_free(song_bessel2_host *t);
+/* hands the tables to the engine: J_Llm(x) is assembled on the device */
+int song_host_bessel2_upload(song_los_ctx *ctx, const song_bessel2_host *t, const int *J_types,
+                             double J_Llm_cut, double xx_max, char *errmsg, int errlen);
+#ifdef __cplusplus
+}
+#endif
+#endif
