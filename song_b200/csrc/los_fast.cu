@@ -20,6 +20,7 @@
 //                 straight from the dense table (L1/L2 resident), accumulators in registers
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "../../include/song_los.h"
@@ -43,6 +44,7 @@ struct FastBlock {
   int64_t jq_off;                   // offset of the block inside a table row (doubles)
   int col_off;                      // offset into col_tt / col_l
   int term_off;                     // offset into term_tp / term_sign
+  int log2_lanes;                   // producer lanes per (unit,tau): 2^log2_lanes >= 2*nkc
 };
 
 struct UnitPrep {
@@ -63,7 +65,7 @@ struct FastParams {
   const UnitPrep *units; int64_t n_units;
   const double *CS, *CD, *E;        // transposed sources, second derivatives, edge rows
   int64_t rowlen;                   // tau_size * tp2_size
-  int tau_size, tp2_size, tau_chunk, cubic_k3;
+  int tau_size, tp2_size, tau_chunk, cubic_k3, nkc_max;
   const double *tau0_minus_tau, *delta_tau, *xx;
   double xx_step; int xx_size;
   double *out; int64_t out_stride;  // [tt][n_units]
@@ -369,6 +371,213 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) los_fast_kernel(const __grid_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised variant: 8 consumer warps issue DMMAs, 4 producer warps stage the A operands
+// of the NEXT tau chunk into the other half of a double buffer.  Hand-off through named barriers
+// (FULL/EMPTY per buffer), so the tensor pipe never waits on the L2 latency of the staging loads.
+// ---------------------------------------------------------------------------------------------
+constexpr int WS_CONSUMERS = 256, WS_PRODUCERS = 128, WS_THREADS = WS_CONSUMERS + WS_PRODUCERS;
+constexpr int BAR_FULL0 = 1, BAR_EMPTY0 = 3, BAR_PROD = 5;
+constexpr int WS_UNR = 4;
+
+__device__ __forceinline__ void bar_sync_named(int id, int count)
+{
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_named(int id, int count)
+{
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <int WM, int WN>
+__global__ void __launch_bounds__(WS_THREADS, 1) los_fast_ws_kernel(const __grid_constant__ FastParams P)
+{
+  constexpr int MT = 16 * WM;
+  constexpr int LOG_MT = (MT == 128) ? 7 : (MT == 64 ? 6 : 5);
+  constexpr int AROW = MT * 4 + AS_PAD;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int TC = P.tau_chunk;
+  const int nkc_max = P.nkc_max;
+  UnitPrep *su = reinterpret_cast<UnitPrep *>(smem_raw);
+  double2 *coef = reinterpret_cast<double2 *>(su + MT);                 // [2][TC][MT]
+  int *ixs = reinterpret_cast<int *>(coef + (size_t)2 * TC * MT);       // [2][TC][MT]
+  double *As = reinterpret_cast<double *>(ixs + (size_t)2 * TC * MT);   // [2][TC][nkc_max][AROW]
+  const size_t as_buf = (size_t)TC * nkc_max * AROW;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t s0 = (int64_t)blockIdx.x * MT;
+  const int64_t nleft = P.n_units - s0;
+  const int nvalid = nleft < (int64_t)MT ? (int)nleft : MT;
+
+  for (int n = tid; n < MT; n += WS_THREADS) {
+    UnitPrep up;
+    if (n < nvalid) up = P.units[s0 + n];
+    else { up = P.units[s0 + nvalid - 1]; up.u = -1; }
+    su[n] = up;
+  }
+  __syncthreads();
+
+  if (warp >= WS_CONSUMERS / 32) {
+    // =========================== producers ===========================
+    const int ptid = tid - WS_CONSUMERS, pw = warp - WS_CONSUMERS / 32;
+    int item = 0;
+    for (int ib = 0; ib < P.n_blocks; ++ib) {
+      const FastBlock B = P.blk[ib];
+      const int nsb = B.ncols8 >> 3;
+      const int nt2 = B.nkc * 2;
+      const int lg = B.log2_lanes;               // lanes per (unit,tau): 2^lg >= nt2
+      const int gpw = 32 >> lg;                  // (unit,tau) groups per warp
+      const int sub = lane >> lg, e = lane & ((1 << lg) - 1);
+      const bool e_real = e < B.nterms, e_slot = e < nt2;
+      const int tp = e_real ? P.term_tp[B.term_off + e] : 0;
+      const double sgn = e_real ? P.term_sign[B.term_off + e] : 0.;
+      for (int sb0 = 0; sb0 < nsb; sb0 += FAST_RC * WN) {
+        for (int c0 = 0; c0 < P.tau_size; c0 += TC, ++item) {
+          const int tc = min(TC, P.tau_size - c0);
+          const int buf = item & 1;
+          if (item >= 2) bar_sync_named(BAR_EMPTY0 + buf, WS_THREADS);
+          double2 *cf = coef + (size_t)buf * TC * MT;
+          int *ixb = ixs + (size_t)buf * TC * MT;
+          double *Ab = As + (size_t)buf * as_buf;
+          // ---- stage 1: row index and quadrature x lerp weights per (tau, unit) ----
+          for (int idx = ptid; idx < tc * MT; idx += WS_PRODUCERS) {
+            int t = idx >> LOG_MT, n = idx & (MT - 1);
+            double x = su[n].k * P.tau0_minus_tau[c0 + t];                 // transfer2.c:2195
+            int index_x = (int)(x / P.xx_step);                            // transfer2.c:2199
+            if (index_x < 0 || index_x + 1 >= P.xx_size) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); index_x = 0; }
+            double a_J = (P.xx[index_x + 1] - x) / P.xx_step;              // transfer2.c:2202
+            double w = P.delta_tau[c0 + t];
+            cf[idx] = make_double2(w * a_J, w * (1 - a_J));
+            ixb[idx] = index_x;
+          }
+          bar_sync_named(BAR_PROD, WS_PRODUCERS);
+          // ---- stage 2: A operands, WS_UNR (unit,tau) pairs per lane group in flight ----
+          const int ntot = tc * MT;
+          const int stride = WS_PRODUCERS / 32 * gpw;
+          for (int r0 = pw * gpw + sub; r0 < ntot; r0 += stride * WS_UNR) {
+            double y0[WS_UNR], y1[WS_UNR], d0[WS_UNR], d1[WS_UNR];
+#pragma unroll
+            for (int u = 0; u < WS_UNR; ++u) {
+              const int r = r0 + u * stride;
+              y0[u] = y1[u] = d0[u] = d1[u] = 0.;
+              if (r < ntot && e_real) {
+                const int n = r & (MT - 1), t = r >> LOG_MT;
+                if (n < nvalid) {
+                  const UnitPrep &up = su[n];
+                  const int64_t col = (int64_t)(c0 + t) * P.tp2_size + tp;
+                  if (up.wing) y0[u] = __ldg(P.E + up.off + col);
+                  else {
+                    y0[u] = __ldg(P.CS + up.off + col);
+                    y1[u] = __ldg(P.CS + up.off + P.rowlen + col);
+                    if (P.cubic_k3) { d0[u] = __ldg(P.CD + up.off + col); d1[u] = __ldg(P.CD + up.off + P.rowlen + col); }
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < WS_UNR; ++u) {
+              const int r = r0 + u * stride;
+              if (r < ntot && e_slot) {
+                const int n = r & (MT - 1), t = r >> LOG_MT;
+                const UnitPrep &up = su[n];
+                double v = up.wing ? y0[u] : (up.a * y0[u] + up.b * y1[u] + (up.a3 * d0[u] + up.b3 * d1[u]) * up.h6);
+                v *= sgn;
+                const double2 c2 = cf[r];
+                double *dst = Ab + ((size_t)t * B.nkc + (e >> 1)) * AROW + n * 4 + 2 * (e & 1);
+                *reinterpret_cast<double2 *>(dst) = make_double2(c2.x * v, c2.y * v);
+              }
+            }
+          }
+          bar_arrive_named(BAR_FULL0 + buf, WS_THREADS);
+        }
+      }
+    }
+    return;
+  }
+
+  // =========================== consumers ===========================
+  const int warp_m = warp / WN, warp_n = warp % WN;
+  const int g0 = warp_m * 2, g1 = g0 + 1;
+  const int um = lane >> 2;
+  int item = 0;
+  for (int ib = 0; ib < P.n_blocks; ++ib) {
+    const FastBlock B = P.blk[ib];
+    const int nsb = B.ncols8 >> 3;
+    for (int sb0 = 0; sb0 < nsb; sb0 += FAST_RC * WN) {
+      int nbp = 0;
+      for (int j = 0; j < FAST_RC; ++j) nbp += (sb0 + warp_n + j * WN < nsb) ? 1 : 0;
+      double acc0[FAST_RC][2], acc1[FAST_RC][2];
+#pragma unroll
+      for (int j = 0; j < FAST_RC; ++j) { acc0[j][0] = acc0[j][1] = 0.; acc1[j][0] = acc1[j][1] = 0.; }
+
+      for (int c0 = 0; c0 < P.tau_size; c0 += TC, ++item) {
+        const int tc = min(TC, P.tau_size - c0);
+        const int buf = item & 1;
+        const int *ixb = ixs + (size_t)buf * TC * MT;
+        const double *Ab = As + (size_t)buf * as_buf;
+        bar_sync_named(BAR_FULL0 + buf, WS_THREADS);
+        if (nbp > 0) {
+          for (int t = 0; t < tc; ++t) {
+            const int ix0 = ixb[t * MT + g0 * 8 + um];
+            const int ix1 = ixb[t * MT + g1 * 8 + um];
+            const int lo = __reduce_min_sync(0xffffffffu, min(ix0, ix1));
+            const int hi = __reduce_max_sync(0xffffffffu, max(ix0, ix1));
+            const double *arow = Ab + (size_t)t * B.nkc * AROW + lane;
+            for (int v = lo; v <= hi; ++v) {
+              const bool m0 = (ix0 == v), m1 = (ix1 == v);
+              const bool any0 = __any_sync(0xffffffffu, m0), any1 = __any_sync(0xffffffffu, m1);
+              if (!any0 && !any1) continue;
+              const double *brow = P.Jq + (int64_t)v * P.jq_row + B.jq_off + lane + (int64_t)(sb0 + warp_n) * 32;
+              for (int kc = 0; kc < B.nkc; ++kc) {
+                const double *bp = brow + (int64_t)kc * B.ncols8 * 4;
+                double bf[FAST_RC];
+#pragma unroll
+                for (int j = 0; j < FAST_RC; ++j)
+                  bf[j] = (j < nbp) ? __ldg(bp + (int64_t)j * WN * 32) : 0.;
+                if (any0) {
+                  double a0 = arow[(size_t)kc * AROW + g0 * 32];
+                  if (!m0) a0 = 0.;
+#pragma unroll
+                  for (int j = 0; j < FAST_RC; ++j)
+                    if (j < nbp) dmma884(acc0[j][0], acc0[j][1], a0, bf[j]);
+                }
+                if (any1) {
+                  double a1 = arow[(size_t)kc * AROW + g1 * 32];
+                  if (!m1) a1 = 0.;
+#pragma unroll
+                  for (int j = 0; j < FAST_RC; ++j)
+                    if (j < nbp) dmma884(acc1[j][0], acc1[j][1], a1, bf[j]);
+                }
+              }
+            }
+          }
+        }
+        bar_arrive_named(BAR_EMPTY0 + buf, WS_THREADS);
+      }
+
+      const int cpair = 2 * (lane & 3);
+#pragma unroll
+      for (int j = 0; j < FAST_RC; ++j) {
+        if (j >= nbp) continue;
+        int cbase = (sb0 + warp_n + j * WN) * 8 + cpair;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          int c = cbase + h;
+          if (c >= B.ncols) continue;
+          int tt = P.col_tt[B.col_off + c];
+          double lfac = 2. * P.col_l[B.col_off + c] + 1;
+          int u0 = su[g0 * 8 + um].u, u1 = su[g1 * 8 + um].u;
+          double t0 = acc0[j][h] * 0.5; t0 /= 4.; t0 /= lfac; t0 /= 2.;
+          double t1 = acc1[j][h] * 0.5; t1 /= 4.; t1 /= lfac; t1 /= 2.;
+          if (u0 >= 0) { if (t0 != t0) atomicOr(P.err, ERR_NAN); P.out[(int64_t)tt * P.out_stride + u0] = t0; }
+          if (u1 >= 0) { if (t1 != t1) atomicOr(P.err, ERR_NAN); P.out[(int64_t)tt * P.out_stride + u1] = t1; }
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -472,6 +681,9 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
         term_tp.push_back(0); term_sign.push_back(0.); term_col0.push_back(0); B.nterms = 1;
       }
       B.nkc = (B.nterms + 1) / 2;
+      B.log2_lanes = 0;
+      while ((1 << B.log2_lanes) < 2 * B.nkc) ++B.log2_lanes;
+      if (B.log2_lanes > 5) { err = "too many K terms for one warp of producers"; return 1; }
       B.ncols8 = (B.ncols + 7) / 8 * 8;
       B.jq_off = jq_off;
       jq_off += (int64_t)B.nkc * B.ncols8 * 4;
@@ -594,18 +806,44 @@ int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
   FP.out = b.out; FP.out_stride = U; FP.err = P.err;
 
   const int MT = 16 * fs->wm;
-  // tau chunk: largest TC with <= ~100 KB of shared memory (two CTAs per SM)
-  int TC = 1;
-  while (TC < P.tm.tau_size && fast_smem_bytes(MT, TC + 1, nkc_max) <= 100 * 1024) ++TC;
-  FP.tau_chunk = TC;
-  size_t smem = fast_smem_bytes(MT, TC, nkc_max);
-  if (smem > 220 * 1024) { err = "FAST kernel: shared-memory stage does not fit"; return 1; }
+  FP.nkc_max = nkc_max;
   int64_t n_tiles = (U + MT - 1) / MT;
-  if (n_tiles > 0) {
-    if (fs->wm == 8) FCK((launch_fast<8, 1>(FP, n_tiles, smem, st)));
-    else if (fs->wm == 4) FCK((launch_fast<4, 2>(FP, n_tiles, smem, st)));
-    else FCK((launch_fast<2, 4>(FP, n_tiles, smem, st)));
-    tm->n_launches++;
+  static const int variant = []() { const char *v = getenv("SONG_LOS_FAST_VARIANT"); return v ? atoi(v) : 1; }();
+  if (variant == 1) {
+    // warp-specialised: one CTA per SM, double-buffered operands, as many tau samples per chunk as fit
+    auto ws_smem = [&](int TC) {
+      return (size_t)MT * sizeof(UnitPrep) + (size_t)2 * TC * MT * (sizeof(double2) + sizeof(int))
+           + (size_t)2 * TC * nkc_max * (MT * 4 + AS_PAD) * sizeof(double);
+    };
+    int TC = 1;
+    while (TC < P.tm.tau_size && TC < 8 && ws_smem(TC + 1) <= 200 * 1024) ++TC;
+    FP.tau_chunk = TC;
+    size_t smem = ws_smem(TC);
+    if (smem > 225 * 1024) { err = "FAST kernel: shared-memory stage does not fit"; return 1; }
+    if (n_tiles > 0) {
+      cudaError_t e;
+      if (fs->wm == 8) { e = cudaFuncSetAttribute(los_fast_ws_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                         if (e == cudaSuccess) { los_fast_ws_kernel<8, 1><<<(unsigned)n_tiles, WS_THREADS, smem, st>>>(FP); e = cudaGetLastError(); } }
+      else if (fs->wm == 4) { e = cudaFuncSetAttribute(los_fast_ws_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                         if (e == cudaSuccess) { los_fast_ws_kernel<4, 2><<<(unsigned)n_tiles, WS_THREADS, smem, st>>>(FP); e = cudaGetLastError(); } }
+      else { e = cudaFuncSetAttribute(los_fast_ws_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                         if (e == cudaSuccess) { los_fast_ws_kernel<2, 4><<<(unsigned)n_tiles, WS_THREADS, smem, st>>>(FP); e = cudaGetLastError(); } }
+      FCK(e);
+      tm->n_launches++;
+    }
+  } else {
+    // single-role variant (kept for A/B measurements): two CTAs per SM overlap staging and MMA
+    int TC = 1;
+    while (TC < P.tm.tau_size && fast_smem_bytes(MT, TC + 1, nkc_max) <= 100 * 1024) ++TC;
+    FP.tau_chunk = TC;
+    size_t smem = fast_smem_bytes(MT, TC, nkc_max);
+    if (smem > 220 * 1024) { err = "FAST kernel: shared-memory stage does not fit"; return 1; }
+    if (n_tiles > 0) {
+      if (fs->wm == 8) FCK((launch_fast<8, 1>(FP, n_tiles, smem, st)));
+      else if (fs->wm == 4) FCK((launch_fast<4, 2>(FP, n_tiles, smem, st)));
+      else FCK((launch_fast<2, 4>(FP, n_tiles, smem, st)));
+      tm->n_launches++;
+    }
   }
   FCK(cudaEventRecord(fs->ev[4], st));
   FCK(cudaEventSynchronize(fs->ev[4]));
