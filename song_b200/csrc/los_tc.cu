@@ -13,7 +13,8 @@
 // which is the 8x8x4 FP64 MMA (the only FP64 tensor instruction of sm_100a; tcgen05 has no f64 kind).
 //
 // Pipeline of one song_los_compute(FAST):
-//   spline_csd    k3 second derivatives, written transposed and interleaved CSD[pair][j][tau][tp]{y,dd}
+//   spline_csd    k3 second derivatives, written per interval: CSD[pair][j][tau][tp] = {y_j, dd_j, y_j+1, dd_j+1}
+//                 (one 256-bit load per (unit, tau, source type) in the kernel)
 //   edge_rows     interpolated sources at the first/last physical k3 (flat-extrapolation wings)
 //   sort          cub radix sort of (k3, unit)
 //   prep_units    per sorted unit: bracket, spline weights, source row pointer
@@ -59,7 +60,7 @@ struct TcPass {                           // one column pass of a block = one ac
 struct TcUnit {
   double k;                               // k3 (argument of the projection functions)
   double a, b, a3h, b3h;                  // spline weights: a, b, (a^3-a) h^2/6, (b^3-b) h^2/6
-  const double2 *base;                    // {y, dd} of row j at (tau=0, tp=0); wing units: edge row
+  const double4 *base;                    // interval j of the pair at (tau=0, tp=0); wing units: edge row
   int u;                                  // original unit index (output position), -1 = padding
   int pad;
 };
@@ -117,6 +118,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ double4 ldg256(const double4 *p)
+{
+  double4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
 }
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
@@ -195,13 +202,14 @@ __global__ void tc_nact_cummax_kernel(int *nact, int xx_size, int n_blocks)
 }
 
 // ---------------------------------------------------------------------------------------------
-// spline_csd: one thread per (pair, tau, tp) column; writes CSD[pair][j][tau][tp] = {y, dd}
+// spline_csd: one thread per (pair, tau, tp) column; writes, for every k3 interval j of the pair,
+// CSD[pair][j][tau][tp] = {y_j, dd_j, y_j+1, dd_j+1}   (pair p starts at entry src_off[p] - p*rowlen)
 // (same algorithm as array_spline_table_columns, _SPLINE_EST_DERIV_; transfer2.c:2639)
 // ---------------------------------------------------------------------------------------------
 constexpr int TC_SPLINE_MAX_NP = 256;
 
 __global__ void __launch_bounds__(128) tc_spline_csd_kernel(Batch b, int tau_size, int tp2_size, int cubic,
-                                                            double2 *CSD, int *err)
+                                                            double4 *CSD, int *err)
 {
   int64_t rowlen = (int64_t)tp2_size * tau_size;
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,9 +220,9 @@ __global__ void __launch_bounds__(128) tc_spline_csd_kernel(Batch b, int tau_siz
   int n = b.np[p];
   const double *x = b.k3_pt + b.pt_off[p];
   const double *y = b.src + b.src_off[p] + ((int64_t)tp * tau_size + tau) * n;
-  double2 *cs = CSD + b.src_off[p] + col;
+  double4 *cs = CSD + (b.src_off[p] - (int64_t)p * rowlen) + col;
   if (!cubic) {
-    for (int i = 0; i < n; ++i) cs[(int64_t)i * rowlen] = make_double2(y[i], 0.);
+    for (int i = 0; i + 1 < n; ++i) cs[(int64_t)i * rowlen] = make_double4(y[i], 0., y[i + 1], 0.);
     return;
   }
   if (n > TC_SPLINE_MAX_NP || n < 3) { atomicOr(err, ERR_H_ZERO); return; }
@@ -234,11 +242,11 @@ __global__ void __launch_bounds__(128) tc_spline_csd_kernel(Batch b, int tau_siz
                     - (x[n - 2] - x[n - 1]) * (x[n - 2] - x[n - 1]) * (y[n - 3] - y[n - 1]))
                    / ((x[n - 3] - x[n - 1]) * (x[n - 2] - x[n - 1]) * (x[n - 3] - x[n - 2]));
   double un = (3. / (x[n - 1] - x[n - 2])) * (dy_last - (y[n - 1] - y[n - 2]) / (x[n - 1] - x[n - 2]));
-  double next = (un - 0.5 * u[n - 2]) / (0.5 * dd[n - 2] + 1.0);
-  cs[(int64_t)(n - 1) * rowlen] = make_double2(y[n - 1], next);
+  double next = (un - 0.5 * u[n - 2]) / (0.5 * dd[n - 2] + 1.0);     // dd of point i+1
   for (int i = n - 2; i >= 0; --i) {
-    next = dd[i] * next + u[i];
-    cs[(int64_t)i * rowlen] = make_double2(y[i], next);
+    double cur = dd[i] * next + u[i];                                  // dd of point i
+    cs[(int64_t)i * rowlen] = make_double4(y[i], cur, y[i + 1], next);
+    next = cur;
   }
 }
 
@@ -255,9 +263,9 @@ __device__ __forceinline__ void tc_bracket(const double *kp, int np, double ke, 
   a = 1 - b;
 }
 
-// edge rows: E[pair][side][col] = {S(k3 edge), 0}; side 0 = first physical k3, 1 = last
-// (flat extrapolation, transfer2.c:2743-2757).  Wing units read them with weights a=1, b=0.
-__global__ void tc_edge_rows_kernel(Batch b, int64_t rowlen, const double2 *CSD, double2 *E, int *err)
+// edge rows: E[pair][side][col] = {S(k3 edge), 0, 0, 0}; side 0 = first physical k3, 1 = last
+// (flat extrapolation, transfer2.c:2743-2757).  Wing units read them with weights a=1, b=a3h=b3h=0.
+__global__ void tc_edge_rows_kernel(Batch b, int64_t rowlen, const double4 *CSD, double4 *E, int *err)
 {
   int p = blockIdx.y;
   int side = blockIdx.z;
@@ -269,10 +277,10 @@ __global__ void tc_edge_rows_kernel(Batch b, int64_t rowlen, const double2 *CSD,
   tc_bracket(kp, b.np[p], ke, j, a, bb, h);
   if (h == 0) { if (threadIdx.x == 0) atomicOr(err, ERR_H_ZERO); return; }
   double a3h = (a * a * a - a) * (h * h / 6.0), b3h = (bb * bb * bb - bb) * (h * h / 6.0);
-  const double2 *r0 = CSD + b.src_off[p] + (int64_t)j * rowlen;
+  const double4 *r0 = CSD + (b.src_off[p] - (int64_t)p * rowlen) + (int64_t)j * rowlen;
   for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < rowlen; col += (int64_t)gridDim.x * blockDim.x) {
-    double2 s0 = r0[col], s1 = r0[rowlen + col];
-    E[((int64_t)p * 2 + side) * rowlen + col] = make_double2(a * s0.x + bb * s1.x + a3h * s0.y + b3h * s1.y, 0.);
+    double4 s4 = r0[col];
+    E[((int64_t)p * 2 + side) * rowlen + col] = make_double4(a * s4.x + bb * s4.z + a3h * s4.y + b3h * s4.w, 0., 0., 0.);
   }
 }
 
@@ -284,7 +292,7 @@ __global__ void tc_iota_kernel(int *p, int64_t n)
 
 // prep_units: everything a sorted unit needs, once per unit
 __global__ void tc_prep_units_kernel(Batch b, const int *perm, const int *unit_pair, int64_t rowlen,
-                                     int flat_extrap, const double2 *CSD, const double2 *E, TcUnit *out, int *err)
+                                     int flat_extrap, const double4 *CSD, const double4 *E, TcUnit *out, int *err)
 {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= b.n_units) return;
@@ -307,7 +315,7 @@ __global__ void tc_prep_units_kernel(Batch b, const int *perm, const int *unit_p
     if (h == 0) atomicOr(err, ERR_H_ZERO);
     double h6 = h * h / 6.0;
     up.a = a; up.b = bb; up.a3h = (a * a * a - a) * h6; up.b3h = (bb * bb * bb - bb) * h6;
-    up.base = CSD + b.src_off[p] + (int64_t)j * rowlen;
+    up.base = CSD + (b.src_off[p] - (int64_t)p * rowlen) + (int64_t)j * rowlen;
   }
   out[s] = up;
 }
@@ -334,46 +342,93 @@ __device__ __forceinline__ TcStagePtrs tc_stage(unsigned char *stage0, int s, co
   return r;
 }
 
-// one pass over the kc's of a chunk for one table row: A fragments masked to the units of that row
-template <int NW, bool B_IN_SMEM>
-__device__ __forceinline__ void tc_mma_row(double (&acc0)[NW][2], double (&acc1)[NW][2],
-                                           const double *a0p, const double *a1p, int arow,
-                                           bool m0, bool m1, bool any0, bool any1,
-                                           const double *bp, int kcs, int b_sb_stride, int nactw)
+// ---- consumer inner loops -------------------------------------------------------------------
+// One table row against the staged A operands of a chunk.  NACT (active sub-blocks of this warp) is
+// a template parameter so that the body is straight-line code: per kc 1-2 A fragments and NACT B
+// fragments (LDS.64, 256 contiguous bytes per warp) feed 1-2 x NACT DMMAs; the fragments of kc+1 are
+// loaded into the other register set before the DMMAs of kc are issued (ping-pong, no moves).
+
+// both 8-unit groups of the warp have units on this row
+template <int NACT, int NW>
+__device__ __forceinline__ void tc_mma_both(double (&acc0)[NW][2], double (&acc1)[NW][2],
+                                            const double *a0p, const double *a1p, int arow, bool m0, bool m1,
+                                            const double *bp, int kcs, int b_sb_stride)
 {
-  // bp -> fragment (first owned sub-block, kc 0) + lane; owned sub-block j at bp + j*b_sb_stride
-  double a0 = any0 ? a0p[0] : 0., a1 = any1 ? a1p[0] : 0.;
-  double bf[NW];
-#pragma unroll
-  for (int j = 0; j < NW; ++j)
-    bf[j] = (j < nactw) ? (B_IN_SMEM ? bp[(size_t)j * b_sb_stride] : __ldg(bp + (size_t)j * b_sb_stride)) : 0.;
+  double pa0, pa1, pb[NACT], qa0, qa1, qb[NACT];
+#define TC_LOAD(A0, A1, BF, KC) do { \
+    A0 = a0p[(size_t)(KC) * arow]; A1 = a1p[(size_t)(KC) * arow]; \
+    _Pragma("unroll") for (int j = 0; j < NACT; ++j) BF[j] = bp[(size_t)j * b_sb_stride + (KC) * 32]; } while (0)
+#define TC_MMA(A0, A1, BF) do { \
+    const double x0 = m0 ? A0 : 0., x1 = m1 ? A1 : 0.; \
+    _Pragma("unroll") for (int j = 0; j < NACT; ++j) dmma884(acc0[j][0], acc0[j][1], x0, BF[j]); \
+    _Pragma("unroll") for (int j = 0; j < NACT; ++j) dmma884(acc1[j][0], acc1[j][1], x1, BF[j]); } while (0)
+  TC_LOAD(pa0, pa1, pb, 0);
+  int kc = 0;
+  for (; kc + 2 <= kcs; kc += 2) {
+    TC_LOAD(qa0, qa1, qb, kc + 1);
+    TC_MMA(pa0, pa1, pb);
+    if (kc + 2 < kcs) TC_LOAD(pa0, pa1, pb, kc + 2);
+    TC_MMA(qa0, qa1, qb);
+  }
+  if (kc < kcs) TC_MMA(pa0, pa1, pb);
+#undef TC_LOAD
+#undef TC_MMA
+}
+
+// only one of the two groups has units on this row
+template <int NACT, int NW>
+__device__ __forceinline__ void tc_mma_one(double (&acc)[NW][2], const double *ap, int arow, bool m,
+                                           const double *bp, int kcs, int b_sb_stride)
+{
+  double pa, pb[NACT], qa, qb[NACT];
+#define TC_LOAD(A0, BF, KC) do { \
+    A0 = ap[(size_t)(KC) * arow]; \
+    _Pragma("unroll") for (int j = 0; j < NACT; ++j) BF[j] = bp[(size_t)j * b_sb_stride + (KC) * 32]; } while (0)
+#define TC_MMA(A0, BF) do { \
+    const double x = m ? A0 : 0.; \
+    _Pragma("unroll") for (int j = 0; j < NACT; ++j) dmma884(acc[j][0], acc[j][1], x, BF[j]); } while (0)
+  TC_LOAD(pa, pb, 0);
+  int kc = 0;
+  for (; kc + 2 <= kcs; kc += 2) {
+    TC_LOAD(qa, qb, kc + 1);
+    TC_MMA(pa, pb);
+    if (kc + 2 < kcs) TC_LOAD(pa, pb, kc + 2);
+    TC_MMA(qa, qb);
+  }
+  if (kc < kcs) TC_MMA(pa, pb);
+#undef TC_LOAD
+#undef TC_MMA
+}
+
+template <int NACT, int NW>
+__device__ __forceinline__ void tc_mma_row_smem(double (&acc0)[NW][2], double (&acc1)[NW][2],
+                                                const double *a0p, const double *a1p, int arow,
+                                                bool m0, bool m1, bool any0, bool any1,
+                                                const double *bp, int kcs, int b_sb_stride)
+{
+  if (any0 && any1) tc_mma_both<NACT, NW>(acc0, acc1, a0p, a1p, arow, m0, m1, bp, kcs, b_sb_stride);
+  else if (any0) tc_mma_one<NACT, NW>(acc0, a0p, arow, m0, bp, kcs, b_sb_stride);
+  else tc_mma_one<NACT, NW>(acc1, a1p, arow, m1, bp, kcs, b_sb_stride);
+}
+
+// rows outside the staged window (sparse k3 regions): B fragments straight from the table in global
+// memory; generic in the number of active sub-blocks (rare path, kept small)
+template <int NW>
+__device__ __forceinline__ void tc_mma_row_global(double (&acc0)[NW][2], double (&acc1)[NW][2],
+                                               const double *a0p, const double *a1p, int arow,
+                                               bool m0, bool m1, const double *bp, int kcs, int b_sb_stride, int nactw)
+{
   for (int kc = 0; kc < kcs; ++kc) {
-    double na0 = 0., na1 = 0., nbf[NW];
-    const bool more = (kc + 1 < kcs);
-    if (more) {
-      if (any0) na0 = a0p[(size_t)(kc + 1) * arow];
-      if (any1) na1 = a1p[(size_t)(kc + 1) * arow];
+    double a0 = a0p[(size_t)kc * arow], a1 = a1p[(size_t)kc * arow];
+    if (!m0) a0 = 0.;
+    if (!m1) a1 = 0.;
 #pragma unroll
-      for (int j = 0; j < NW; ++j)
-        nbf[j] = (j < nactw) ? (B_IN_SMEM ? bp[(size_t)j * b_sb_stride + (kc + 1) * 32]
-                                          : __ldg(bp + (size_t)j * b_sb_stride + (kc + 1) * 32)) : 0.;
-    }
-    const double x0 = m0 ? a0 : 0., x1 = m1 ? a1 : 0.;
-    if (any0) {
-#pragma unroll
-      for (int j = 0; j < NW; ++j)
-        if (j < nactw) dmma884(acc0[j][0], acc0[j][1], x0, bf[j]);
-    }
-    if (any1) {
-#pragma unroll
-      for (int j = 0; j < NW; ++j)
-        if (j < nactw) dmma884(acc1[j][0], acc1[j][1], x1, bf[j]);
-    }
-    if (more) {
-      a0 = na0; a1 = na1;
-#pragma unroll
-      for (int j = 0; j < NW; ++j) bf[j] = nbf[j];
-    }
+    for (int j = 0; j < NW; ++j)
+      if (j < nactw) {
+        const double bf = __ldg(bp + (size_t)j * b_sb_stride + kc * 32);
+        dmma884(acc0[j][0], acc0[j][1], a0, bf);
+        dmma884(acc1[j][0], acc1[j][1], a1, bf);
+      }
   }
 }
 
@@ -408,8 +463,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
 
   if (warp >= TC_CONSUMERS / 32) {
     // =========================== producers ===========================
+    // thread <-> (unit n, share `sub` of the kc's of a chunk); stage sequence: pass, chunk q, tau
     const int ptid = tid - TC_CONSUMERS;
     const int n = ptid % MT, sub = ptid / MT;
+    constexpr int NKC_T = (TC_KCS_MAX + TPU - 1) / TPU;          // kc's per thread per stage
     const TcUnit up = P.units[s0 + (n < nvalid ? n : nvalid - 1)];   // tail: replicate, never stored
     const double k_first = P.units[s0].k, k_last = P.units[s0 + nvalid - 1].k;
     int it = 0;
@@ -417,33 +474,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
       const TcPass ps = P.pass[ip];
       const TcBlock B = P.blk[ps.blk];
       const int *nact_b = P.nact + (int64_t)ps.blk * P.xx_size;
-      for (int t = 0; t < P.tau_size; ++t) {
-        const double d = P.tau0_minus_tau[t], w = P.delta_tau[t];
-        // row index and quadrature x lerp weights of this thread's unit (transfer2.c:2195-2202)
-        const double x = up.k * d;
-        int ix = (int)(x * P.inv_xx_step);
-        if (ix < 0 || ix + 1 >= P.xx_size) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); ix = 0; }
-        const double a_J = (__ldg(P.xx + ix + 1) - x) * P.inv_xx_step;
-        const double c0 = w * a_J, c1 = w - c0;
-        const double2 *src_t = up.base + (int64_t)t * P.tp2_size;
-        for (int q = 0; q < ps.nq; ++q, ++it) {
+      for (int q = 0; q < ps.nq; ++q) {
+        const int kc0 = q * ps.kcs;
+        const int kcs_q = min(ps.kcs, B.nkc - kc0);
+        // source types and signs of this thread's terms, hoisted out of the tau loop; slots past
+        // the last term read term 0 with weight 0 (unconditional loads, no predication)
+        int tpo[NKC_T * 2];
+        unsigned real_mask = 0, neg_mask = 0;                    // bit per slot: term exists / enters with sign -1
+        int nmine = 0;
+#pragma unroll
+        for (int i = 0; i < NKC_T; ++i) {
+          const int kcq = sub + i * TPU;
+          if (kcq < kcs_q) nmine = i + 1;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int e = 2 * (kc0 + kcq) + h;
+            const bool real = (kcq < kcs_q) && (e < B.nterms);
+            tpo[2 * i + h] = real ? P.term_tp[B.term_off + e] : P.term_tp[B.term_off];
+            if (real) { real_mask |= 1u << (2 * i + h); if (P.term_sign[B.term_off + e] < 0.) neg_mask |= 1u << (2 * i + h); }
+          }
+        }
+        const uint32_t bytes_per_sb = (uint32_t)kcs_q * 256u;
+        const int64_t q_off = ps.jq_off + (int64_t)ps.nsb * kc0 * 32;
+        for (int t = 0; t < P.tau_size; ++t, ++it) {
           const int s = it % NS;
           const uint32_t full = smem_u32(&bars[s]), empty = smem_u32(&bars[8 + s]);
-          if (it >= NS) mbar_wait(empty, ((it / NS) - 1) & 1);
           const TcStagePtrs st = tc_stage<MT>(stage0, s, P);
-          const int kc0 = q * ps.kcs;
-          const int kcs_q = min(ps.kcs, B.nkc - kc0);
+          const double d = __ldg(P.tau0_minus_tau + t), w = __ldg(P.delta_tau + t);
+          // ---- source loads first: {y_j, dd_j, y_j+1, dd_j+1} of every term of this thread ----
+          const double4 *src_t = up.base + (int64_t)t * P.tp2_size;
+          double4 y[NKC_T * 2];
+#pragma unroll
+          for (int i = 0; i < NKC_T; ++i)
+            if (i < nmine) { y[2 * i] = ldg256(src_t + tpo[2 * i]); y[2 * i + 1] = ldg256(src_t + tpo[2 * i + 1]); }
+          // ---- row index and quadrature x lerp weights of this unit (transfer2.c:2195-2202) ----
+          const double x = up.k * d;
+          int ix = (int)(x * P.inv_xx_step);
+          if (ix < 0 || ix + 1 >= P.xx_size) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); ix = 0; }
+          const double a_J = (__ldg(P.xx + ix + 1) - x) * P.inv_xx_step;
+          const double c0 = w * a_J, c1 = w - c0;
+          int row_lo = 0, row_hi = 0, nact = 0;
           if (ptid == 0) {
             // table rows of the tile at this tau: units are k3-sorted, so rows are [row(first), row(last)]
-            int row_lo = (int)(k_first * d * P.inv_xx_step), row_hi = (int)(k_last * d * P.inv_xx_step);
+            row_lo = (int)(k_first * d * P.inv_xx_step); row_hi = (int)(k_last * d * P.inv_xx_step);
             row_lo = max(0, min(row_lo, P.xx_size - 2)); row_hi = max(row_lo, min(row_hi, P.xx_size - 2));
+            nact = max(0, min(__ldg(nact_b + row_hi) - ps.sb0, ps.nsb));
+          }
+          if (it >= NS) mbar_wait(empty, ((it / NS) - 1) & 1);
+          if (ptid == 0) {
             const int nrows = min(row_hi - row_lo + 1, P.rmax);
-            const int nact = max(0, min(__ldg(nact_b + row_hi) - ps.sb0, ps.nsb));
-            const uint32_t bytes_row = (uint32_t)nact * kcs_q * 256u;
+            const uint32_t bytes_row = (uint32_t)nact * bytes_per_sb;
             st.meta[0] = row_lo; st.meta[1] = nrows; st.meta[2] = nact; st.meta[3] = row_hi;
             if (bytes_row > 0) {
               mbar_arrive_expect_tx(full, bytes_row * nrows);
-              const double *src = P.Jq + (int64_t)row_lo * P.jq_row + ps.jq_off + (int64_t)ps.nsb * kc0 * 32;
+              const double *src = P.Jq + (int64_t)row_lo * P.jq_row + q_off;
               for (int r = 0; r < nrows; ++r)
                 bulk_g2s(smem_u32(st.B) + r * P.b_row_bytes, src + (int64_t)r * P.jq_row, bytes_row, full);
             } else {
@@ -451,36 +535,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
             }
           }
           if (sub == 0) st.ixs[n] = ix;
-          // A operands of this unit: v = S(k3, tau, term) by the k3 spline (transfer2.c:2697-2705),
-          // stored as {c0 v, c1 v} per term, two terms per kc
-          constexpr int NKC_T = (TC_KCS_MAX + TPU - 1) / TPU;       // kc's per thread per stage
-          double2 y0[NKC_T * 2], y1[NKC_T * 2];
+          // ---- A operands: v = S(k3, tau, term) by the k3 spline (transfer2.c:2697-2705), stored
+          //      as {c0 v, c1 v} per term, two terms per kc ----
 #pragma unroll
           for (int i = 0; i < NKC_T; ++i) {
-            const int kcq = sub + i * TPU;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int e = 2 * (kc0 + kcq) + h;
-              y0[2 * i + h] = y1[2 * i + h] = make_double2(0., 0.);
-              if (kcq < kcs_q && e < B.nterms) {
-                const int tp = P.term_tp[B.term_off + e];
-                y0[2 * i + h] = __ldg(src_t + tp);
-                y1[2 * i + h] = __ldg(src_t + P.rowlen + tp);
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < NKC_T; ++i) {
-            const int kcq = sub + i * TPU;
-            if (kcq < kcs_q) {
+            if (i < nmine) {
               double v[2];
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                const int e = 2 * (kc0 + kcq) + h;
-                v[h] = up.a * y0[2 * i + h].x + up.b * y1[2 * i + h].x + up.a3h * y0[2 * i + h].y + up.b3h * y1[2 * i + h].y;
-                if (e < B.nterms) v[h] *= P.term_sign[B.term_off + e];
+                const double4 yy = y[2 * i + h];
+                double val = up.a * yy.x + up.b * yy.z + up.a3h * yy.y + up.b3h * yy.w;
+                if (neg_mask >> (2 * i + h) & 1u) val = -val;
+                v[h] = (real_mask >> (2 * i + h) & 1u) ? val : 0.;
               }
-              double *dst = st.A + (size_t)kcq * AROW + n * 4;
+              double *dst = st.A + (size_t)(sub + i * TPU) * AROW + n * 4;
               reinterpret_cast<double2 *>(dst)[0] = make_double2(c0 * v[0], c1 * v[0]);
               reinterpret_cast<double2 *>(dst)[1] = make_double2(c0 * v[1], c1 * v[1]);
             }
@@ -504,12 +572,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
 #pragma unroll
     for (int j = 0; j < NW; ++j) { acc0[j][0] = acc0[j][1] = 0.; acc1[j][0] = acc1[j][1] = 0.; }
 
-    for (int t = 0; t < P.tau_size; ++t) {
-      for (int q = 0; q < ps.nq; ++q, ++it) {
+    for (int q = 0; q < ps.nq; ++q) {
+      const int kc0 = q * ps.kcs;
+      const int kcs_q = min(ps.kcs, B.nkc - kc0);
+      for (int t = 0; t < P.tau_size; ++t, ++it) {
         const int s = it % NS;
         const TcStagePtrs st = tc_stage<MT>(stage0, s, P);
-        const int kc0 = q * ps.kcs;
-        const int kcs_q = min(ps.kcs, B.nkc - kc0);
         mbar_wait(smem_u32(&bars[s]), (it / NS) & 1);
         const int row_lo = st.meta[0], nrows = st.meta[1], nact = st.meta[2];
         // owned sub-blocks: warp_n, warp_n + WN, ... ; active ones form a prefix of that list
@@ -527,11 +595,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
             const int rb = v - row_lo;
             if (rb < nrows) {
               const double *bp = st.B + (size_t)rb * (P.b_row_bytes / 8) + (size_t)warp_n * kcs_q * 32 + lane;
-              tc_mma_row<NW, true>(acc0, acc1, a0p, a1p, AROW, m0, m1, any0, any1, bp, kcs_q, b_sb_stride, nactw);
+#define TC_CASE(N) case N: if constexpr (N <= NW) tc_mma_row_smem<N, NW>(acc0, acc1, a0p, a1p, AROW, m0, m1, any0, any1, bp, kcs_q, b_sb_stride); break;
+              switch (nactw) {
+                TC_CASE(1) TC_CASE(2) TC_CASE(3) TC_CASE(4) TC_CASE(5) TC_CASE(6) TC_CASE(7) TC_CASE(8) TC_CASE(9) TC_CASE(10)
+              }
+#undef TC_CASE
             } else {
               const double *bp = P.Jq + (int64_t)v * P.jq_row + ps.jq_off + (int64_t)ps.nsb * kc0 * 32
                                + (size_t)warp_n * kcs_q * 32 + lane;
-              tc_mma_row<NW, false>(acc0, acc1, a0p, a1p, AROW, m0, m1, any0, any1, bp, kcs_q, b_sb_stride, nactw);
+              tc_mma_row_global<NW>(acc0, acc1, a0p, a1p, AROW, m0, m1, bp, kcs_q, b_sb_stride, nactw);
             }
             const int n0 = (ix0 > v) ? ix0 : 0x7fffffff, n1 = (ix1 > v) ? ix1 : 0x7fffffff;
             v = __reduce_min_sync(0xffffffffu, min(n0, n1));
@@ -592,7 +664,7 @@ struct FastState {
   int wm = 8, wn = 1, nw = 8;
   int kcs_max = 1, nsb_pass_max = 1;
   Buf<double> Jq, keys_out;
-  Buf<double2> CSD, E;
+  Buf<double4> CSD, E;
   Buf<int> col_tt, col_l, col_lm, term_col0, nact, perm_in, perm, unit_pair;
   Buf<TcUnit> units;
   Buf<unsigned char> cub_tmp;
@@ -776,7 +848,7 @@ int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
   // ---- phase 0: transposed {y, dd} sources, edge rows ----
   FCK(cudaEventRecord(fs->ev[0], st));
   const int64_t n_src = h.n_src_total;
-  FCK(fs->CSD.reserve((size_t)n_src + (size_t)rowlen));          // + one row: wing/last-row reads of row j+1
+  FCK(fs->CSD.reserve((size_t)n_src));                           // (np - 1) intervals per pair: n_src is an upper bound
   {
     int64_t cols = rowlen * b.n_pairs;
     if (cols > 0) {
@@ -786,8 +858,7 @@ int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
       tm->n_launches++;
     }
   }
-  FCK(fs->E.reserve((size_t)(b.n_pairs * 2 + 1) * rowlen));      // + one zero row behind the last edge row:
-  FCK(cudaMemsetAsync(fs->E.p + (size_t)b.n_pairs * 2 * rowlen, 0, (size_t)rowlen * sizeof(double2), st));  // read with weight 0
+  FCK(fs->E.reserve((size_t)b.n_pairs * 2 * rowlen));
   if (P.flat_extrap && b.n_pairs > 0) {
     dim3 grid((unsigned)std::min<int64_t>((rowlen + 255) / 256, 64), (unsigned)b.n_pairs, 2);
     tc_edge_rows_kernel<<<grid, 256, 0, st>>>(b, rowlen, fs->CSD.p, fs->E.p, P.err);
