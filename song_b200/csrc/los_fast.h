@@ -18,6 +18,7 @@ struct FastHostLayout {
   const int *l, *m, *lm_array, *lm_src;
   const unsigned char *block_nonzero;   // [J_size*L_size]
   int64_t n_src_total;
+  int tau_size;
 };
 
 struct FastState;

@@ -1,5 +1,5 @@
-// los_tc.cu -- FAST mode: k3-sorted FP64 tensor-core (DMMA m8n8k4) line-of-sight kernel with a
-// TMA-bulk / mbarrier operand pipeline.
+// los_tc.cu -- FAST mode: k3-sorted FP64 tensor-core (DMMA m8n8k4) line-of-sight kernel fed by a
+// TMA / mbarrier operand pipeline.
 //
 // The sum being evaluated (reference transfer2_integrate, source/transfer2.c:2140-2341, and the
 // field dispatch of transfer2_compute, :1861-2116):
@@ -13,18 +13,25 @@
 // which is the 8x8x4 FP64 MMA (the only FP64 tensor instruction of sm_100a; tcgen05 has no f64 kind).
 //
 // Pipeline of one song_los_compute(FAST):
-//   spline_csd    k3 second derivatives, written per interval: CSD[pair][j][tau][tp] = {y_j, dd_j, y_j+1, dd_j+1}
-//                 (one 256-bit load per (unit, tau, source type) in the kernel)
-//   edge_rows     interpolated sources at the first/last physical k3 (flat-extrapolation wings)
+//   spline_csd    k3 second derivatives of every (pair, tau, source type) column (transfer2.c:2639),
+//                 written transposed: CSD[pair][j][tau][tp] = {y, dd}
 //   sort          cub radix sort of (k3, unit)
-//   prep_units    per sorted unit: bracket, spline weights, source row pointer
-//   los_tc        per CTA one tile of MT sorted units.  4 producer warps: one thread issues
-//                 cp.async.bulk (TMA 1-D) copies of the needed table rows into a shared-memory ring,
-//                 all of them evaluate the k3 spline and the quadrature/lerp weights and write the A
-//                 operands into the same ring stage; 8 consumer warps wait on the stage's mbarrier,
-//                 read conflict-free 256-byte fragments and issue DMMAs into register accumulators.
-//                 Columns whose J is still below the reference's cut at this row (x << l) are skipped.
+//   prep_units    per unit: bracket j, spline weights (transfer2.c:2683-2691), sorted position; flat
+//                 extrapolation = weights of the first/last physical k3 (transfer2.c:2743-2757)
+//   interp_units  one CTA per (k1,k2) pair walks the pair's units in k3 order, so that the two CSD rows
+//                 of an interval are read once for all the units inside it, and writes the interpolated
+//                 sources in the order the tensor-core kernel consumes them:
+//                 S[group][sorted unit][tau][slot]   (group = K chunk of a column block, slot = term)
+//   los_tc        per CTA one tile of MT sorted units.  One producer warp: a single thread issues, per
+//                 tau, ONE cp.async.bulk.tensor (TMA, 3-D box {slots, 1 tau, MT units}) for the sources
+//                 and one cp.async.bulk per needed table row into a shared-memory ring; its lanes
+//                 compute row index and quadrature x lerp weights of every unit.  Eight consumer warps
+//                 wait on the stage's mbarrier, read conflict-free 256-byte fragments and issue DMMAs
+//                 into register accumulators.  Columns whose J is still below the reference's cut at
+//                 this row (x << l) are skipped.
 #include <cub/cub.cuh>
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <algorithm>
 #include <cstdlib>
 #include <string>
@@ -39,11 +46,12 @@ namespace songlos {
 // device structures
 // ---------------------------------------------------------------------------------------------
 constexpr int TC_MAX_BLOCKS = 12;
+constexpr int TC_MAX_GROUPS = 12;         // (block, K chunk): one source slab and one tensor map each
 constexpr int TC_MAX_PASSES = 24;
 constexpr int TC_MAX_TERMS = 64;          // K terms of one block (2 per kc)
 constexpr int TC_KCS_MAX = 6;             // kc's (pairs of terms) per pipeline stage
-constexpr int TC_CONSUMERS = 256, TC_PRODUCERS = 128, TC_THREADS = TC_CONSUMERS + TC_PRODUCERS;
-constexpr int TC_APAD = 4;                // doubles of padding per A row
+constexpr int TC_CONSUMERS = 256, TC_PRODUCERS = 32, TC_THREADS = TC_CONSUMERS + TC_PRODUCERS;
+constexpr int TC_MAX_STAGES = 8;
 
 struct TcBlock {
   int ncols, nsb;                         // real columns, 8-column sub-blocks
@@ -51,42 +59,40 @@ struct TcBlock {
   int col_off, term_off;                  // offsets into col_* / term_* tables
 };
 
+struct TcGroup {                          // K chunk q of a block: kc in [kc0, kc0 + kcs)
+  int blk, kc0, kcs;
+  int tpp;                                // doubles per (unit, tau) row of the slab: 2*kcs padded to 4
+  int64_t s_off;                          // offset of the slab inside the S buffer (doubles)
+};
+
 struct TcPass {                           // one column pass of a block = one accumulator lifetime
   int blk, sb0, nsb;                      // block, first sub-block, sub-blocks in the pass
-  int nq, kcs;                            // K chunks and kc's per chunk (last chunk may be shorter)
+  int g0, nq;                             // first group and number of K chunks of the block
   int64_t jq_off;                         // offset of the pass inside a table row (doubles)
 };
 
-struct TcUnit {
-  double k;                               // k3 (argument of the projection functions)
-  double a, b, a3h, b3h;                  // spline weights: a, b, (a^3-a) h^2/6, (b^3-b) h^2/6
-  const double4 *base;                    // interval j of the pair at (tau=0, tp=0); wing units: edge row
-  int u;                                  // original unit index (output position), -1 = padding
-  int pad;
-};
-
 struct TcParams {
-  int n_blocks, n_pass;
+  CUtensorMap tmap[TC_MAX_GROUPS];        // S[group]: dims {tpp, tau, units}, box {tpp, 1, MT}
+  int n_blocks, n_groups, n_pass;
   TcBlock blk[TC_MAX_BLOCKS];
+  TcGroup grp[TC_MAX_GROUPS];
   TcPass pass[TC_MAX_PASSES];
-  int term_tp[TC_MAX_TERMS * 2];          // per term: source type index          (indexed term_off + e)
-  double term_sign[TC_MAX_TERMS * 2];     // per term: +1 / -1 (B-mode mixing)
   const int *col_tt, *col_l;              // per column: transfer type index, multipole l
   const double *Jq; int64_t jq_row;       // tensor-core table and its row length (doubles)
   const int *nact;                        // [n_blocks][xx_size] active sub-block prefix per row
-  const TcUnit *units; int64_t n_units;
-  int64_t rowlen;                         // tau_size * tp2_size
-  int tau_size, tp2_size;
+  const double *k_sorted; const int *perm; int64_t n_units;   // sorted k3 and original unit index
+  int tau_size;
   const double *tau0_minus_tau, *delta_tau, *xx;
   double inv_xx_step; int xx_size;
   int n_stages, rmax;                     // ring depth, table rows per stage
   int hdr_bytes, a_bytes, b_row_bytes, stage_bytes;  // shared-memory geometry of one stage
   double *out; int64_t out_stride;        // [tt][n_units]
   int *err;
+  int dbg;                                // timing experiments only (results invalid): 4 = no MMAs
 };
 
 // ---------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D bulk copy (TMA)
+// PTX helpers: mbarrier, bulk copies (TMA), FP64 MMA
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -114,16 +120,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
       "TC_DONE:\n"
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
+// 1-D bulk copy global -> shared, completion on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ double4 ldg256(const double4 *p)
+// 3-D tensor (TMA descriptor) box copy global -> shared
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
 {
-  double4 v;
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
-  return v;
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
@@ -140,7 +147,7 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 // contiguous piece, i.e. one bulk copy.
 // ---------------------------------------------------------------------------------------------
 __global__ void tc_build_table_kernel(const double2 *J, int64_t n_cols_dense, int64_t jq_row, TcPass ps, TcBlock blk,
-                                      const int *term_col0, const int *col_lm, double *Jq)
+                                      int kcs, const int *term_col0, const int *col_lm, double *Jq)
 {
   // one thread per (kc, column of the pass), grid.y = ix
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,10 +168,10 @@ __global__ void tc_build_table_kernel(const double2 *J, int64_t n_cols_dense, in
       }
     }
   }
-  int q = kc / ps.kcs, kcq = kc - q * ps.kcs;
-  int kcs_q = min(ps.kcs, blk.nkc - q * ps.kcs);
+  int q = kc / kcs, kcq = kc - q * kcs;
+  int kcs_q = min(kcs, blk.nkc - q * kcs);
   int sb = cp >> 3, c8 = cp & 7;
-  double *dst = Jq + (int64_t)ix * jq_row + ps.jq_off + (int64_t)ps.nsb * (q * ps.kcs) * 32
+  double *dst = Jq + (int64_t)ix * jq_row + ps.jq_off + (int64_t)ps.nsb * (q * kcs) * 32
               + ((int64_t)sb * kcs_q + kcq) * 32 + c8 * 4;
   reinterpret_cast<double2 *>(dst)[0] = make_double2(v[0], v[1]);
   reinterpret_cast<double2 *>(dst)[1] = make_double2(v[2], v[3]);
@@ -202,14 +209,13 @@ __global__ void tc_nact_cummax_kernel(int *nact, int xx_size, int n_blocks)
 }
 
 // ---------------------------------------------------------------------------------------------
-// spline_csd: one thread per (pair, tau, tp) column; writes, for every k3 interval j of the pair,
-// CSD[pair][j][tau][tp] = {y_j, dd_j, y_j+1, dd_j+1}   (pair p starts at entry src_off[p] - p*rowlen)
+// spline_csd: one thread per (pair, tau, tp) column; writes CSD[pair][j][tau][tp] = {y, dd}
 // (same algorithm as array_spline_table_columns, _SPLINE_EST_DERIV_; transfer2.c:2639)
 // ---------------------------------------------------------------------------------------------
 constexpr int TC_SPLINE_MAX_NP = 256;
 
 __global__ void __launch_bounds__(128) tc_spline_csd_kernel(Batch b, int tau_size, int tp2_size, int cubic,
-                                                            double4 *CSD, int *err)
+                                                            double2 *CSD, int *err)
 {
   int64_t rowlen = (int64_t)tp2_size * tau_size;
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -220,9 +226,9 @@ __global__ void __launch_bounds__(128) tc_spline_csd_kernel(Batch b, int tau_siz
   int n = b.np[p];
   const double *x = b.k3_pt + b.pt_off[p];
   const double *y = b.src + b.src_off[p] + ((int64_t)tp * tau_size + tau) * n;
-  double4 *cs = CSD + (b.src_off[p] - (int64_t)p * rowlen) + col;
+  double2 *cs = CSD + b.src_off[p] + col;
   if (!cubic) {
-    for (int i = 0; i + 1 < n; ++i) cs[(int64_t)i * rowlen] = make_double4(y[i], 0., y[i + 1], 0.);
+    for (int i = 0; i < n; ++i) cs[(int64_t)i * rowlen] = make_double2(y[i], 0.);
     return;
   }
   if (n > TC_SPLINE_MAX_NP || n < 3) { atomicOr(err, ERR_H_ZERO); return; }
@@ -242,45 +248,11 @@ __global__ void __launch_bounds__(128) tc_spline_csd_kernel(Batch b, int tau_siz
                     - (x[n - 2] - x[n - 1]) * (x[n - 2] - x[n - 1]) * (y[n - 3] - y[n - 1]))
                    / ((x[n - 3] - x[n - 1]) * (x[n - 2] - x[n - 1]) * (x[n - 3] - x[n - 2]));
   double un = (3. / (x[n - 1] - x[n - 2])) * (dy_last - (y[n - 1] - y[n - 2]) / (x[n - 1] - x[n - 2]));
-  double next = (un - 0.5 * u[n - 2]) / (0.5 * dd[n - 2] + 1.0);     // dd of point i+1
+  double next = (un - 0.5 * u[n - 2]) / (0.5 * dd[n - 2] + 1.0);
+  cs[(int64_t)(n - 1) * rowlen] = make_double2(y[n - 1], next);
   for (int i = n - 2; i >= 0; --i) {
-    double cur = dd[i] * next + u[i];                                  // dd of point i
-    cs[(int64_t)i * rowlen] = make_double4(y[i], cur, y[i + 1], next);
-    next = cur;
-  }
-}
-
-// bracket and weights of one interpolation point (transfer2.c:2683-2691)
-__device__ __forceinline__ void tc_bracket(const double *kp, int np, double ke, int &j, double &a, double &b, double &h)
-{
-  // j = number of interior coarse points kp[i], 1 <= i <= np-2, strictly below ke
-  int lo = 1, hi = np - 1;
-  while (lo < hi) { int mid = (lo + hi) >> 1; if (kp[mid] < ke) lo = mid + 1; else hi = mid; }
-  j = lo - 1;
-  if (j > np - 2) j = np - 2;
-  h = kp[j + 1] - kp[j];
-  b = (ke - kp[j]) / h;
-  a = 1 - b;
-}
-
-// edge rows: E[pair][side][col] = {S(k3 edge), 0, 0, 0}; side 0 = first physical k3, 1 = last
-// (flat extrapolation, transfer2.c:2743-2757).  Wing units read them with weights a=1, b=a3h=b3h=0.
-__global__ void tc_edge_rows_kernel(Batch b, int64_t rowlen, const double4 *CSD, double4 *E, int *err)
-{
-  int p = blockIdx.y;
-  int side = blockIdx.z;
-  const double *kp = b.k3_pt + b.pt_off[p];
-  const double *kt = b.k3_tr + b.tr_off[p];
-  int first = b.phys_start[p], last = first + b.phys_size[p] - 1;
-  double ke = kt[side ? last : first];
-  int j; double a, bb, h;
-  tc_bracket(kp, b.np[p], ke, j, a, bb, h);
-  if (h == 0) { if (threadIdx.x == 0) atomicOr(err, ERR_H_ZERO); return; }
-  double a3h = (a * a * a - a) * (h * h / 6.0), b3h = (bb * bb * bb - bb) * (h * h / 6.0);
-  const double4 *r0 = CSD + (b.src_off[p] - (int64_t)p * rowlen) + (int64_t)j * rowlen;
-  for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < rowlen; col += (int64_t)gridDim.x * blockDim.x) {
-    double4 s4 = r0[col];
-    E[((int64_t)p * 2 + side) * rowlen + col] = make_double4(a * s4.x + bb * s4.z + a3h * s4.y + b3h * s4.w, 0., 0., 0.);
+    next = dd[i] * next + u[i];
+    cs[(int64_t)i * rowlen] = make_double2(y[i], next);
   }
 }
 
@@ -290,44 +262,99 @@ __global__ void tc_iota_kernel(int *p, int64_t n)
   if (i < n) p[i] = (int)i;
 }
 
-// prep_units: everything a sorted unit needs, once per unit
-__global__ void tc_prep_units_kernel(Batch b, const int *perm, const int *unit_pair, int64_t rowlen,
-                                     int flat_extrap, const double4 *CSD, const double4 *E, TcUnit *out, int *err)
+// prep_units: per unit in ORIGINAL order (pair-major, k3 ascending inside a pair): the k3 bracket and
+// spline weights of transfer2.c:2683-2691 and the position of the unit in the k3-sorted sequence.
+// Flat extrapolation (transfer2.c:2743-2757): wing units take the weights of the first / last
+// physical k3 of their pair.
+struct TcUnitW { double a, b, a3h, b3h; };          // a, b, (a^3-a) h^2/6, (b^3-b) h^2/6
+
+__global__ void tc_prep_units_kernel(Batch b, const int *perm, const int *unit_pair, int flat_extrap,
+                                     TcUnitW *uw, int2 *ujp, int *err)
 {
-  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // sorted position
   if (s >= b.n_units) return;
   int u = perm[s];
   int p = unit_pair[u];
   int i = u - (int)b.tr_off[p];
   const double *kp = b.k3_pt + b.pt_off[p];
   const double *kt = b.k3_tr + b.tr_off[p];
+  int np = b.np[p];
   int first = b.phys_start[p], last = first + b.phys_size[p] - 1;
-  TcUnit up;
-  up.k = kt[i];
-  up.u = u;
-  up.pad = 0;
-  if (flat_extrap && (i < first || i > last)) {
-    up.a = 1.; up.b = 0.; up.a3h = 0.; up.b3h = 0.;
-    up.base = E + ((int64_t)p * 2 + (i > last ? 1 : 0)) * rowlen;
-  } else {
-    int j; double a, bb, h;
-    tc_bracket(kp, b.np[p], kt[i], j, a, bb, h);
-    if (h == 0) atomicOr(err, ERR_H_ZERO);
-    double h6 = h * h / 6.0;
-    up.a = a; up.b = bb; up.a3h = (a * a * a - a) * h6; up.b3h = (bb * bb * bb - bb) * h6;
-    up.base = CSD + (b.src_off[p] - (int64_t)p * rowlen) + (int64_t)j * rowlen;
+  int ie = i;
+  if (flat_extrap) ie = max(first, min(last, i));
+  double ke = kt[ie];
+  // j = number of interior coarse points kp[i], 1 <= i <= np-2, strictly below ke (strict <, :2683)
+  int lo = 1, hi = np - 1;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (kp[mid] < ke) lo = mid + 1; else hi = mid; }
+  int j = min(lo - 1, np - 2);
+  double h = kp[j + 1] - kp[j];
+  if (h == 0) atomicOr(err, ERR_H_ZERO);
+  double bb = (ke - kp[j]) / h, a = 1 - bb, h6 = h * h / 6.0;
+  TcUnitW w; w.a = a; w.b = bb; w.a3h = (a * a * a - a) * h6; w.b3h = (bb * bb * bb - bb) * h6;
+  uw[u] = w;
+  ujp[u] = make_int2(j, (int)s);
+}
+
+// interp_units: CTA = (pair, chunk of 256 columns); thread = one column (group, tau, slot) of the
+// S slabs.  Walks the units of the pair in k3 order: the bracket j only moves forward, so the CSD rows
+// of an interval are (re)loaded once per interval; each unit costs 4 FMAs and one coalesced store
+// (consecutive threads = consecutive doubles of S[group][sorted unit][tau][slot]).
+constexpr int TC_SLOTS = 2 * TC_KCS_MAX + 4;
+struct TcInterp {
+  int n_groups;
+  int grp_tpp[TC_MAX_GROUPS];             // slots per (unit, tau) row of the group
+  int64_t grp_s_off[TC_MAX_GROUPS];       // slab offsets
+  int64_t grp_col0[TC_MAX_GROUPS + 1];    // first column index of each group: cumulative tau_size*tpp
+  const int *slot_tp;                     // per (group, slot): source type, -1 = padding   [n_groups][TC_SLOTS]
+  const double *slot_sign;
+};
+
+__global__ void __launch_bounds__(256) tc_interp_units_kernel(Batch b, TcInterp I, int tau_size, int tp2_size,
+                                                              const double2 *CSD, const TcUnitW *uw, const int2 *ujp, double *S)
+{
+  const int p = blockIdx.x;
+  const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= I.grp_col0[I.n_groups]) return;
+  int g = 0;
+  while (c >= I.grp_col0[g + 1]) ++g;
+  const int tpp = I.grp_tpp[g];
+  const int64_t cg = c - I.grp_col0[g];
+  const int tau = (int)(cg / tpp), slot = (int)(cg % tpp);
+  const int tp = I.slot_tp[g * TC_SLOTS + slot];
+  const double sign = I.slot_sign[g * TC_SLOTS + slot];
+  const int nt = b.nt[p];
+  const int64_t u0 = b.tr_off[p];
+  double *Sg = S + I.grp_s_off[g] + (int64_t)tau * tpp + slot;
+  const int64_t unit_stride = (int64_t)tau_size * tpp;
+  if (tp < 0) {                                              // padding slot: zeros (whole sectors get written)
+    for (int i = 0; i < nt; ++i) Sg[(int64_t)ujp[u0 + i].y * unit_stride] = 0.;
+    return;
   }
-  out[s] = up;
+  const int64_t rowlen = (int64_t)tau_size * tp2_size;
+  const double2 *cs = CSD + b.src_off[p] + (int64_t)tau * tp2_size + tp;
+  int jc = -1;
+  double2 s0 = make_double2(0., 0.), s1 = s0;
+  for (int i = 0; i < nt; ++i) {
+    const int2 jp = ujp[u0 + i];
+    const TcUnitW w = uw[u0 + i];
+    if (jp.x != jc) {
+      jc = jp.x;
+      s0 = cs[(int64_t)jc * rowlen]; s1 = cs[(int64_t)(jc + 1) * rowlen];
+    }
+    // transfer2.c:2697 (linear: dd = 0) / :2703-2705 (cubic)
+    const double v = w.a * s0.x + w.b * s1.x + w.a3h * s0.y + w.b3h * s1.y;
+    Sg[(int64_t)jp.y * unit_stride] = sign * v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // the DMMA kernel
 // ---------------------------------------------------------------------------------------------
-// shared memory:  [bars: full[NS], empty[NS]] [unit ids: MT ints] [stage 0] [stage 1] ...
-// stage:          header {meta int4 {row_lo, nrows, nact, row_hi}, ixs[MT]} | A[KCS][AROW] | B[rmax][b_row]
-//                 (each part padded to 128 bytes: bulk-copy destinations must be 16-byte aligned)
+// shared memory:  [bars: full[8], empty[8]] [unit ids: MT ints] [k3: MT doubles] [tau tables] [stages...]
+// stage:          header {meta int4 {row_lo, nrows, nact, row_hi}, ixs[MT], cc[MT] double2 {c0, c1}}
+//                 | S[MT][tpp] (TMA box) | B[rmax][b_row]     (each part padded to 128 bytes)
 struct TcStagePtrs {
-  int *meta; int *ixs; double *A; double *B;
+  int *meta; int *ixs; double2 *cc; double *S; double *B;
 };
 
 template <int MT>
@@ -337,29 +364,31 @@ __device__ __forceinline__ TcStagePtrs tc_stage(unsigned char *stage0, int s, co
   TcStagePtrs r;
   r.meta = reinterpret_cast<int *>(base);
   r.ixs = reinterpret_cast<int *>(base + 16);
-  r.A = reinterpret_cast<double *>(base + P.hdr_bytes);
+  r.cc = reinterpret_cast<double2 *>(base + 16 + MT * 4);
+  r.S = reinterpret_cast<double *>(base + P.hdr_bytes);
   r.B = reinterpret_cast<double *>(base + P.hdr_bytes + P.a_bytes);
   return r;
 }
 
 // ---- consumer inner loops -------------------------------------------------------------------
-// One table row against the staged A operands of a chunk.  NACT (active sub-blocks of this warp) is
-// a template parameter so that the body is straight-line code: per kc 1-2 A fragments and NACT B
-// fragments (LDS.64, 256 contiguous bytes per warp) feed 1-2 x NACT DMMAs; the fragments of kc+1 are
-// loaded into the other register set before the DMMAs of kc are issued (ping-pong, no moves).
+// One table row against the staged sources of a chunk.  NACT (active sub-blocks of this warp) is a
+// template parameter so that the body is straight-line code: per kc 1-2 A fragments (source value x
+// per-unit weight, zero weight for units on another row) and NACT B fragments (LDS.64, 256 contiguous
+// bytes per warp) feed 1-2 x NACT DMMAs; the fragments of kc+1 are loaded into the other register
+// set before the DMMAs of kc are issued (ping-pong, no moves).
 
 // both 8-unit groups of the warp have units on this row
 template <int NACT, int NW>
 __device__ __forceinline__ void tc_mma_both(double (&acc0)[NW][2], double (&acc1)[NW][2],
-                                            const double *a0p, const double *a1p, int arow, bool m0, bool m1,
+                                            const double *a0p, const double *a1p, double w0, double w1,
                                             const double *bp, int kcs, int b_sb_stride)
 {
   double pa0, pa1, pb[NACT], qa0, qa1, qb[NACT];
 #define TC_LOAD(A0, A1, BF, KC) do { \
-    A0 = a0p[(size_t)(KC) * arow]; A1 = a1p[(size_t)(KC) * arow]; \
+    A0 = a0p[2 * (KC)]; A1 = a1p[2 * (KC)]; \
     _Pragma("unroll") for (int j = 0; j < NACT; ++j) BF[j] = bp[(size_t)j * b_sb_stride + (KC) * 32]; } while (0)
 #define TC_MMA(A0, A1, BF) do { \
-    const double x0 = m0 ? A0 : 0., x1 = m1 ? A1 : 0.; \
+    const double x0 = w0 * A0, x1 = w1 * A1; \
     _Pragma("unroll") for (int j = 0; j < NACT; ++j) dmma884(acc0[j][0], acc0[j][1], x0, BF[j]); \
     _Pragma("unroll") for (int j = 0; j < NACT; ++j) dmma884(acc1[j][0], acc1[j][1], x1, BF[j]); } while (0)
   TC_LOAD(pa0, pa1, pb, 0);
@@ -377,15 +406,15 @@ __device__ __forceinline__ void tc_mma_both(double (&acc0)[NW][2], double (&acc1
 
 // only one of the two groups has units on this row
 template <int NACT, int NW>
-__device__ __forceinline__ void tc_mma_one(double (&acc)[NW][2], const double *ap, int arow, bool m,
+__device__ __forceinline__ void tc_mma_one(double (&acc)[NW][2], const double *ap, double w,
                                            const double *bp, int kcs, int b_sb_stride)
 {
   double pa, pb[NACT], qa, qb[NACT];
 #define TC_LOAD(A0, BF, KC) do { \
-    A0 = ap[(size_t)(KC) * arow]; \
+    A0 = ap[2 * (KC)]; \
     _Pragma("unroll") for (int j = 0; j < NACT; ++j) BF[j] = bp[(size_t)j * b_sb_stride + (KC) * 32]; } while (0)
 #define TC_MMA(A0, BF) do { \
-    const double x = m ? A0 : 0.; \
+    const double x = w * A0; \
     _Pragma("unroll") for (int j = 0; j < NACT; ++j) dmma884(acc[j][0], acc[j][1], x, BF[j]); } while (0)
   TC_LOAD(pa, pb, 0);
   int kc = 0;
@@ -402,26 +431,23 @@ __device__ __forceinline__ void tc_mma_one(double (&acc)[NW][2], const double *a
 
 template <int NACT, int NW>
 __device__ __forceinline__ void tc_mma_row_smem(double (&acc0)[NW][2], double (&acc1)[NW][2],
-                                                const double *a0p, const double *a1p, int arow,
-                                                bool m0, bool m1, bool any0, bool any1,
-                                                const double *bp, int kcs, int b_sb_stride)
+                                                const double *a0p, const double *a1p, double w0, double w1,
+                                                bool any0, bool any1, const double *bp, int kcs, int b_sb_stride)
 {
-  if (any0 && any1) tc_mma_both<NACT, NW>(acc0, acc1, a0p, a1p, arow, m0, m1, bp, kcs, b_sb_stride);
-  else if (any0) tc_mma_one<NACT, NW>(acc0, a0p, arow, m0, bp, kcs, b_sb_stride);
-  else tc_mma_one<NACT, NW>(acc1, a1p, arow, m1, bp, kcs, b_sb_stride);
+  if (any0 && any1) tc_mma_both<NACT, NW>(acc0, acc1, a0p, a1p, w0, w1, bp, kcs, b_sb_stride);
+  else if (any0) tc_mma_one<NACT, NW>(acc0, a0p, w0, bp, kcs, b_sb_stride);
+  else tc_mma_one<NACT, NW>(acc1, a1p, w1, bp, kcs, b_sb_stride);
 }
 
 // rows outside the staged window (sparse k3 regions): B fragments straight from the table in global
 // memory; generic in the number of active sub-blocks (rare path, kept small)
 template <int NW>
 __device__ __forceinline__ void tc_mma_row_global(double (&acc0)[NW][2], double (&acc1)[NW][2],
-                                               const double *a0p, const double *a1p, int arow,
-                                               bool m0, bool m1, const double *bp, int kcs, int b_sb_stride, int nactw)
+                                                  const double *a0p, const double *a1p, double w0, double w1,
+                                                  const double *bp, int kcs, int b_sb_stride, int nactw)
 {
   for (int kc = 0; kc < kcs; ++kc) {
-    double a0 = a0p[(size_t)kc * arow], a1 = a1p[(size_t)kc * arow];
-    if (!m0) a0 = 0.;
-    if (!m1) a1 = 0.;
+    const double a0 = w0 * a0p[2 * kc], a1 = w1 * a1p[2 * kc];
 #pragma unroll
     for (int j = 0; j < NW; ++j)
       if (j < nactw) {
@@ -436,15 +462,17 @@ template <int WM, int WN, int NW>
 __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_constant__ TcParams P)
 {
   constexpr int MT = 16 * WM;                    // units per CTA
-  constexpr int AROW = MT * 4 + TC_APAD;         // doubles per kc row of A operands
-  constexpr int TPU = TC_PRODUCERS / MT;         // producer threads per unit (1, 2 or 4)
+  constexpr int UPL = MT / 32;                   // units per producer lane
   static_assert(WM * WN == TC_CONSUMERS / 32, "8 consumer warps");
-  static_assert(TPU >= 1 && TPU * MT == TC_PRODUCERS, "producer mapping");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int NS = P.n_stages;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);            // full[NS], empty[NS]
-  int *unit_id = reinterpret_cast<int *>(smem_raw + 16 * 8);           // up to 8 stages of barriers
-  unsigned char *stage0 = smem_raw + 128 + MT * 4;                     // 128-byte aligned for MT % 32 == 0
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);             // full[8], empty[8]
+  int *unit_id = reinterpret_cast<int *>(smem_raw + 128);
+  double *unit_k = reinterpret_cast<double *>(smem_raw + 128 + MT * 4);
+  double *tau_d = unit_k + MT;                                          // tau0 - tau       [tau_pad]
+  const int tau_pad = (P.tau_size + 15) & ~15;
+  double *tau_w = tau_d + tau_pad;                                      // trapezoid weight [tau_pad]
+  unsigned char *stage0 = smem_raw + 128 + MT * 12 + (size_t)tau_pad * 16;   // 128-byte aligned (MT % 32 == 0)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t s0 = (int64_t)blockIdx.x * MT;
@@ -453,110 +481,92 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(smem_u32(&bars[s]), TC_PRODUCERS + 1);          // producers' A writes + the copy issuer
+      mbar_init(smem_u32(&bars[s]), TC_PRODUCERS + 1);          // producer lanes + the copy issuer's expect_tx
       mbar_init(smem_u32(&bars[8 + s]), TC_CONSUMERS / 32);     // one arrival per consumer warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  for (int n = tid; n < MT; n += TC_THREADS) unit_id[n] = (n < nvalid) ? P.units[s0 + n].u : -1;
+  for (int n = tid; n < MT; n += TC_THREADS) {
+    const int64_t sidx = s0 + (n < nvalid ? n : nvalid - 1);        // tail: replicate the last unit, never stored
+    unit_id[n] = (n < nvalid) ? P.perm[sidx] : -1;
+    unit_k[n] = P.k_sorted[sidx];
+  }
+  for (int t = tid; t < P.tau_size; t += TC_THREADS) { tau_d[t] = P.tau0_minus_tau[t]; tau_w[t] = P.delta_tau[t]; }
   __syncthreads();
 
-  if (warp >= TC_CONSUMERS / 32) {
-    // =========================== producers ===========================
-    // thread <-> (unit n, share `sub` of the kc's of a chunk); stage sequence: pass, chunk q, tau
-    const int ptid = tid - TC_CONSUMERS;
-    const int n = ptid % MT, sub = ptid / MT;
-    constexpr int NKC_T = (TC_KCS_MAX + TPU - 1) / TPU;          // kc's per thread per stage
-    const TcUnit up = P.units[s0 + (n < nvalid ? n : nvalid - 1)];   // tail: replicate, never stored
-    const double k_first = P.units[s0].k, k_last = P.units[s0 + nvalid - 1].k;
+  if (warp == TC_CONSUMERS / 32) {
+    // =========================== producer warp ===========================
+    // lane <-> units lane, lane+32, ...; stage sequence: pass, K chunk, tau
+    double kk[UPL];
+#pragma unroll
+    for (int i = 0; i < UPL; ++i) kk[i] = unit_k[lane + 32 * i];
+    const double k_first = unit_k[0], k_last = unit_k[MT - 1];
+    int n_stage_total = 0;
+    for (int ip = 0; ip < P.n_pass; ++ip) n_stage_total += P.pass[ip].nq * P.tau_size;
+    // row index and xx[ix+1] of the NEXT stage are fetched one stage ahead (the table read is the
+    // only long-latency step of the lane's work)
+    int ix_n[UPL]; double xxn_n[UPL], x_n[UPL];
+#define TC_PREFETCH(T) do { \
+      const double d_ = tau_d[T]; \
+      _Pragma("unroll") for (int i = 0; i < UPL; ++i) { \
+        const double x_ = kk[i] * d_;                                 /* transfer2.c:2195 */ \
+        int ix_ = (int)(x_ * P.inv_xx_step);                          /* transfer2.c:2199 */ \
+        if (ix_ < 0 || ix_ + 1 >= P.xx_size) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); ix_ = 0; } \
+        x_n[i] = x_; ix_n[i] = ix_; xxn_n[i] = __ldg(P.xx + ix_ + 1); } } while (0)
+    TC_PREFETCH(0);
     int it = 0;
     for (int ip = 0; ip < P.n_pass; ++ip) {
       const TcPass ps = P.pass[ip];
-      const TcBlock B = P.blk[ps.blk];
       const int *nact_b = P.nact + (int64_t)ps.blk * P.xx_size;
       for (int q = 0; q < ps.nq; ++q) {
-        const int kc0 = q * ps.kcs;
-        const int kcs_q = min(ps.kcs, B.nkc - kc0);
-        // source types and signs of this thread's terms, hoisted out of the tau loop; slots past
-        // the last term read term 0 with weight 0 (unconditional loads, no predication)
-        int tpo[NKC_T * 2];
-        unsigned real_mask = 0, neg_mask = 0;                    // bit per slot: term exists / enters with sign -1
-        int nmine = 0;
-#pragma unroll
-        for (int i = 0; i < NKC_T; ++i) {
-          const int kcq = sub + i * TPU;
-          if (kcq < kcs_q) nmine = i + 1;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int e = 2 * (kc0 + kcq) + h;
-            const bool real = (kcq < kcs_q) && (e < B.nterms);
-            tpo[2 * i + h] = real ? P.term_tp[B.term_off + e] : P.term_tp[B.term_off];
-            if (real) { real_mask |= 1u << (2 * i + h); if (P.term_sign[B.term_off + e] < 0.) neg_mask |= 1u << (2 * i + h); }
-          }
-        }
-        const uint32_t bytes_per_sb = (uint32_t)kcs_q * 256u;
-        const int64_t q_off = ps.jq_off + (int64_t)ps.nsb * kc0 * 32;
+        const TcGroup G = P.grp[ps.g0 + q];
+        const uint32_t bytes_per_sb = (uint32_t)G.kcs * 256u;
+        const uint32_t s_bytes = (uint32_t)MT * G.tpp * 8u;
+        const int64_t q_off = ps.jq_off + (int64_t)ps.nsb * G.kc0 * 32;
+        const CUtensorMap *tmap = &P.tmap[ps.g0 + q];
         for (int t = 0; t < P.tau_size; ++t, ++it) {
           const int s = it % NS;
           const uint32_t full = smem_u32(&bars[s]), empty = smem_u32(&bars[8 + s]);
           const TcStagePtrs st = tc_stage<MT>(stage0, s, P);
-          const double d = __ldg(P.tau0_minus_tau + t), w = __ldg(P.delta_tau + t);
-          // ---- source loads first: {y_j, dd_j, y_j+1, dd_j+1} of every term of this thread ----
-          const double4 *src_t = up.base + (int64_t)t * P.tp2_size;
-          double4 y[NKC_T * 2];
+          const double d = tau_d[t], w = tau_w[t];
+          int ix[UPL]; double c0[UPL], c1[UPL];
 #pragma unroll
-          for (int i = 0; i < NKC_T; ++i)
-            if (i < nmine) { y[2 * i] = ldg256(src_t + tpo[2 * i]); y[2 * i + 1] = ldg256(src_t + tpo[2 * i + 1]); }
-          // ---- row index and quadrature x lerp weights of this unit (transfer2.c:2195-2202) ----
-          const double x = up.k * d;
-          int ix = (int)(x * P.inv_xx_step);
-          if (ix < 0 || ix + 1 >= P.xx_size) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); ix = 0; }
-          const double a_J = (__ldg(P.xx + ix + 1) - x) * P.inv_xx_step;
-          const double c0 = w * a_J, c1 = w - c0;
+          for (int i = 0; i < UPL; ++i) {
+            ix[i] = ix_n[i];
+            const double a_J = (xxn_n[i] - x_n[i]) * P.inv_xx_step;        // transfer2.c:2202
+            c0[i] = w * a_J; c1[i] = w - c0[i];                            // weights of J[ix], J[ix+1]
+          }
           int row_lo = 0, row_hi = 0, nact = 0;
-          if (ptid == 0) {
+          if (lane == 0) {
             // table rows of the tile at this tau: units are k3-sorted, so rows are [row(first), row(last)]
             row_lo = (int)(k_first * d * P.inv_xx_step); row_hi = (int)(k_last * d * P.inv_xx_step);
             row_lo = max(0, min(row_lo, P.xx_size - 2)); row_hi = max(row_lo, min(row_hi, P.xx_size - 2));
             nact = max(0, min(__ldg(nact_b + row_hi) - ps.sb0, ps.nsb));
           }
+          if (it + 1 < n_stage_total) { const int tn = (t + 1 < P.tau_size) ? t + 1 : 0; TC_PREFETCH(tn); }
           if (it >= NS) mbar_wait(empty, ((it / NS) - 1) & 1);
-          if (ptid == 0) {
+          if (lane == 0) {
             const int nrows = min(row_hi - row_lo + 1, P.rmax);
             const uint32_t bytes_row = (uint32_t)nact * bytes_per_sb;
             st.meta[0] = row_lo; st.meta[1] = nrows; st.meta[2] = nact; st.meta[3] = row_hi;
-            if (bytes_row > 0) {
-              mbar_arrive_expect_tx(full, bytes_row * nrows);
-              const double *src = P.Jq + (int64_t)row_lo * P.jq_row + q_off;
+            mbar_arrive_expect_tx(full, s_bytes + bytes_row * nrows);
+            tma_load_3d(smem_u32(st.S), tmap, 0, t, (int)s0, full);
+            const double *src = P.Jq + (int64_t)row_lo * P.jq_row + q_off;
+            if (bytes_row > 0)
               for (int r = 0; r < nrows; ++r)
                 bulk_g2s(smem_u32(st.B) + r * P.b_row_bytes, src + (int64_t)r * P.jq_row, bytes_row, full);
-            } else {
-              mbar_arrive(full);
-            }
           }
-          if (sub == 0) st.ixs[n] = ix;
-          // ---- A operands: v = S(k3, tau, term) by the k3 spline (transfer2.c:2697-2705), stored
-          //      as {c0 v, c1 v} per term, two terms per kc ----
 #pragma unroll
-          for (int i = 0; i < NKC_T; ++i) {
-            if (i < nmine) {
-              double v[2];
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const double4 yy = y[2 * i + h];
-                double val = up.a * yy.x + up.b * yy.z + up.a3h * yy.y + up.b3h * yy.w;
-                if (neg_mask >> (2 * i + h) & 1u) val = -val;
-                v[h] = (real_mask >> (2 * i + h) & 1u) ? val : 0.;
-              }
-              double *dst = st.A + (size_t)(sub + i * TPU) * AROW + n * 4;
-              reinterpret_cast<double2 *>(dst)[0] = make_double2(c0 * v[0], c1 * v[0]);
-              reinterpret_cast<double2 *>(dst)[1] = make_double2(c0 * v[1], c1 * v[1]);
-            }
+          for (int i = 0; i < UPL; ++i) {
+            st.ixs[lane + 32 * i] = ix[i];
+            st.cc[lane + 32 * i] = make_double2(c0[i], c1[i]);
           }
           mbar_arrive(full);
         }
       }
     }
+#undef TC_PREFETCH
     return;
   }
 
@@ -564,6 +574,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
   const int warp_m = warp / WN, warp_n = (warp + warp_m) % WN;      // rotate column groups over the SM sub-partitions
   const int g0 = warp_m * 2, g1 = g0 + 1;      // the two 8-unit groups of this warp
   const int um = lane >> 2;                    // unit inside a group held by this lane (A and C rows)
+  const int ksel = lane & 1, tsel = (lane & 3) >> 1;   // weight {c0,c1} and term of the kc held by this lane
   int it = 0;
   for (int ip = 0; ip < P.n_pass; ++ip) {
     const TcPass ps = P.pass[ip];
@@ -573,8 +584,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
     for (int j = 0; j < NW; ++j) { acc0[j][0] = acc0[j][1] = 0.; acc1[j][0] = acc1[j][1] = 0.; }
 
     for (int q = 0; q < ps.nq; ++q) {
-      const int kc0 = q * ps.kcs;
-      const int kcs_q = min(ps.kcs, B.nkc - kc0);
+      const TcGroup G = P.grp[ps.g0 + q];
+      const int kcs_q = G.kcs;
+      const int b_sb_stride = WN * kcs_q * 32;
       for (int t = 0; t < P.tau_size; ++t, ++it) {
         const int s = it % NS;
         const TcStagePtrs st = tc_stage<MT>(stage0, s, P);
@@ -582,28 +594,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
         const int row_lo = st.meta[0], nrows = st.meta[1], nact = st.meta[2];
         // owned sub-blocks: warp_n, warp_n + WN, ... ; active ones form a prefix of that list
         const int nactw = (nact > warp_n) ? min(NW, (nact - warp_n + WN - 1) / WN) : 0;
-        if (nactw > 0) {
+        if (nactw > 0 && !(P.dbg & 4)) {
           const int ix0 = st.ixs[g0 * 8 + um];
           const int ix1 = st.ixs[g1 * 8 + um];
-          const double *a0p = st.A + g0 * 32 + lane;
-          const double *a1p = st.A + g1 * 32 + lane;
-          const int b_sb_stride = WN * kcs_q * 32;
+          const double2 cc0 = st.cc[g0 * 8 + um], cc1 = st.cc[g1 * 8 + um];
+          const double cw0 = ksel ? cc0.y : cc0.x, cw1 = ksel ? cc1.y : cc1.x;
+          // A fragment of kc: S[unit][2 kc + tsel] x weight
+          const double *a0p = st.S + (size_t)(g0 * 8 + um) * G.tpp + tsel;
+          const double *a1p = st.S + (size_t)(g1 * 8 + um) * G.tpp + tsel;
           int v = __reduce_min_sync(0xffffffffu, min(ix0, ix1));
           while (v != 0x7fffffff) {
             const bool m0 = (ix0 == v), m1 = (ix1 == v);
             const bool any0 = __any_sync(0xffffffffu, m0), any1 = __any_sync(0xffffffffu, m1);
+            const double w0 = m0 ? cw0 : 0., w1 = m1 ? cw1 : 0.;
             const int rb = v - row_lo;
             if (rb < nrows) {
               const double *bp = st.B + (size_t)rb * (P.b_row_bytes / 8) + (size_t)warp_n * kcs_q * 32 + lane;
-#define TC_CASE(N) case N: if constexpr (N <= NW) tc_mma_row_smem<N, NW>(acc0, acc1, a0p, a1p, AROW, m0, m1, any0, any1, bp, kcs_q, b_sb_stride); break;
+#define TC_CASE(N) case N: if constexpr (N <= NW) tc_mma_row_smem<N, NW>(acc0, acc1, a0p, a1p, w0, w1, any0, any1, bp, kcs_q, b_sb_stride); break;
               switch (nactw) {
                 TC_CASE(1) TC_CASE(2) TC_CASE(3) TC_CASE(4) TC_CASE(5) TC_CASE(6) TC_CASE(7) TC_CASE(8) TC_CASE(9) TC_CASE(10)
               }
 #undef TC_CASE
             } else {
-              const double *bp = P.Jq + (int64_t)v * P.jq_row + ps.jq_off + (int64_t)ps.nsb * kc0 * 32
+              const double *bp = P.Jq + (int64_t)v * P.jq_row + ps.jq_off + (int64_t)ps.nsb * G.kc0 * 32
                                + (size_t)warp_n * kcs_q * 32 + lane;
-              tc_mma_row_global<NW>(acc0, acc1, a0p, a1p, AROW, m0, m1, bp, kcs_q, b_sb_stride, nactw);
+              tc_mma_row_global<NW>(acc0, acc1, a0p, a1p, w0, w1, bp, kcs_q, b_sb_stride, nactw);
             }
             const int n0 = (ix0 > v) ? ix0 : 0x7fffffff, n1 = (ix1 > v) ? ix1 : 0x7fffffff;
             v = __reduce_min_sync(0xffffffffu, min(n0, n1));
@@ -656,19 +671,22 @@ struct Buf {
 
 struct FastState {
   bool table_ready = false;
-  int n_blocks = 0, n_pass = 0;
+  int n_blocks = 0, n_groups = 0, n_pass = 0;
   TcBlock blk[TC_MAX_BLOCKS];
+  TcGroup grp[TC_MAX_GROUPS];
   TcPass pass[TC_MAX_PASSES];
-  std::vector<int> term_tp; std::vector<double> term_sign;
   int64_t jq_row = 0;
+  int64_t s_doubles_per_unit = 0;        // sum over groups of tau_size * tpp
   int wm = 8, wn = 1, nw = 8;
-  int kcs_max = 1, nsb_pass_max = 1;
-  Buf<double> Jq, keys_out;
-  Buf<double4> CSD, E;
-  Buf<int> col_tt, col_l, col_lm, term_col0, nact, perm_in, perm, unit_pair;
-  Buf<TcUnit> units;
+  int kcs_max = 1, nsb_pass_max = 1, tpp_max = 4;
+  Buf<double> Jq, keys_out, S, slot_sign;
+  Buf<double2> CSD;
+  Buf<int> col_tt, col_l, col_lm, term_col0, nact, perm_in, perm, unit_pair, slot_tp;
+  Buf<TcUnitW> uw; Buf<int2> ujp;
   Buf<unsigned char> cub_tmp;
-  TcParams tp{};                 // kernel parameter block (about 2 KB: kept off the stack)
+  TcParams tp{};                 // kernel parameter block (about 3 KB: kept off the stack)
+  TcInterp interp{};
+  PFN_cuTensorMapEncodeTiled encode = nullptr;
   cudaEvent_t ev[6]{};
   bool ev_ready = false;
 };
@@ -678,9 +696,10 @@ FastState *fast_state_create() { return new FastState(); }
 void fast_state_destroy(FastState *f)
 {
   if (!f) return;
-  f->Jq.release(); f->keys_out.release(); f->CSD.release(); f->E.release();
+  f->Jq.release(); f->keys_out.release(); f->S.release(); f->slot_sign.release(); f->CSD.release();
   f->col_tt.release(); f->col_l.release(); f->col_lm.release(); f->term_col0.release(); f->nact.release();
-  f->perm_in.release(); f->perm.release(); f->unit_pair.release(); f->units.release(); f->cub_tmp.release();
+  f->perm_in.release(); f->perm.release(); f->unit_pair.release(); f->slot_tp.release();
+  f->uw.release(); f->ujp.release(); f->cub_tmp.release();
   if (f->ev_ready) for (auto &e : f->ev) cudaEventDestroy(e);
   delete f;
 }
@@ -695,10 +714,10 @@ void fast_invalidate_table(FastState *f) { if (f) f->table_ready = false; }
 static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParams &P, cudaStream_t st,
                         std::string &err)
 {
-  std::vector<int> col_tt, col_l, col_lm, term_col0;
-  fs->term_tp.clear(); fs->term_sign.clear();
+  std::vector<int> col_tt, col_l, col_lm, term_col0, term_tp;
+  std::vector<double> term_sign;
   fs->n_blocks = 0;
-  int max_sb = 0, max_kc = 0;
+  int max_sb = 0;
   for (int type = 0; type < 3; ++type) {
     bool on = (type == 0 && h.has_T) || (type == 1 && h.has_E) || (type == 2 && h.has_B);
     if (!on) continue;
@@ -709,7 +728,7 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
       if (fs->n_blocks >= TC_MAX_BLOCKS) { err = "too many (field,m) blocks for the FAST kernel"; return 1; }
       TcBlock B{};
       B.col_off = (int)col_tt.size();
-      B.term_off = (int)fs->term_tp.size();
+      B.term_off = (int)term_tp.size();
       for (int il = 0; il < h.l_size; ++il) {
         int lm = h.lm_array[(size_t)il * h.m_size + im];
         if (lm < 0) continue;
@@ -731,24 +750,22 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
           int ls = h.lm_src[(size_t)L * h.m_size + im];
           if (ls < 0) continue;                                   // |m| > L
           if (!h.block_nonzero[(size_t)sg.J * h.L_size + L]) continue;   // spin constraint: empty (J,L)
-          fs->term_tp.push_back(sg.tp + ls);
-          fs->term_sign.push_back(sg.sign);
+          term_tp.push_back(sg.tp + ls);
+          term_sign.push_back(sg.sign);
           term_col0.push_back((sg.J * h.L_size + L) * h.n_transfers);
         }
       }
-      B.nterms = (int)fs->term_tp.size() - B.term_off;
+      B.nterms = (int)term_tp.size() - B.term_off;
       if (B.nterms > TC_MAX_TERMS) { err = "too many K terms for the FAST kernel"; return 1; }
       if (B.nterms == 0) {                      // nothing contributes: outputs are exactly zero
-        fs->term_tp.push_back(0); fs->term_sign.push_back(0.); term_col0.push_back(0); B.nterms = 1;
+        term_tp.push_back(0); term_sign.push_back(0.); term_col0.push_back(0); B.nterms = 1;
       }
       B.nkc = (B.nterms + 1) / 2;
       B.nsb = (B.ncols + 7) / 8;
       max_sb = std::max(max_sb, B.nsb);
-      max_kc = std::max(max_kc, B.nkc);
       fs->blk[fs->n_blocks++] = B;
     }
   }
-  if ((int)fs->term_tp.size() > TC_MAX_TERMS * 2) { err = "too many K terms in total for the FAST kernel"; return 1; }
 
   // warp grid (WM x WN consumer warps, NW sub-blocks per warp): widest tile of units that still
   // covers the columns of a block in one pass
@@ -768,29 +785,50 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
   int kcs_cap = TC_KCS_MAX;
   if (const char *v = getenv("SONG_LOS_TC_KCS")) kcs_cap = std::max(1, std::min(TC_KCS_MAX, atoi(v)));
 
-  // passes and the row layout
-  fs->n_pass = 0;
-  int64_t off = 0;
-  fs->kcs_max = 1; fs->nsb_pass_max = 1;
+  // K chunks (groups) of every block, column passes, and the row layout of the table
+  fs->n_groups = 0; fs->n_pass = 0;
+  int64_t off = 0, s_per_unit = 0;
+  fs->kcs_max = 1; fs->nsb_pass_max = 1; fs->tpp_max = 4;
+  std::vector<int> slot_tp((size_t)TC_MAX_GROUPS * TC_SLOTS, -1);
+  std::vector<double> slot_sign((size_t)TC_MAX_GROUPS * TC_SLOTS, 0.);
+  std::vector<int> blk_kcs(fs->n_blocks);
   for (int ib = 0; ib < fs->n_blocks; ++ib) {
     const TcBlock &B = fs->blk[ib];
+    int nq = (B.nkc + kcs_cap - 1) / kcs_cap;
+    int kcs = (B.nkc + nq - 1) / nq;
+    nq = (B.nkc + kcs - 1) / kcs;
+    blk_kcs[ib] = kcs;
+    const int g_first = fs->n_groups;
+    for (int q = 0; q < nq; ++q) {
+      if (fs->n_groups >= TC_MAX_GROUPS) { err = "too many K chunks for the FAST kernel"; return 1; }
+      TcGroup G{};
+      G.blk = ib; G.kc0 = q * kcs; G.kcs = std::min(kcs, B.nkc - G.kc0);
+      G.tpp = (2 * G.kcs + 3) / 4 * 4;           // 32-byte multiples: whole sectors per (unit, tau)
+      for (int sl = 0; sl < 2 * G.kcs; ++sl) {
+        int e = 2 * G.kc0 + sl;
+        if (e < B.nterms) { slot_tp[(size_t)fs->n_groups * TC_SLOTS + sl] = term_tp[B.term_off + e];
+                            slot_sign[(size_t)fs->n_groups * TC_SLOTS + sl] = term_sign[B.term_off + e]; }
+      }
+      s_per_unit += (int64_t)h.tau_size * G.tpp;
+      fs->kcs_max = std::max(fs->kcs_max, G.kcs);
+      fs->tpp_max = std::max(fs->tpp_max, G.tpp);
+      fs->grp[fs->n_groups++] = G;
+    }
     int npass_b = (B.nsb + sb_per_pass - 1) / sb_per_pass;
     int per = (B.nsb + npass_b - 1) / npass_b;                // balanced passes
     for (int sb0 = 0; sb0 < B.nsb; sb0 += per) {
       if (fs->n_pass >= TC_MAX_PASSES) { err = "too many column passes for the FAST kernel"; return 1; }
       TcPass ps{};
       ps.blk = ib; ps.sb0 = sb0; ps.nsb = std::min(per, B.nsb - sb0);
-      ps.nq = (B.nkc + kcs_cap - 1) / kcs_cap;
-      ps.kcs = (B.nkc + ps.nq - 1) / ps.nq;
+      ps.g0 = g_first; ps.nq = nq;
       ps.jq_off = off;
       off += (int64_t)ps.nsb * B.nkc * 32;
-      fs->kcs_max = std::max(fs->kcs_max, ps.kcs);
       fs->nsb_pass_max = std::max(fs->nsb_pass_max, ps.nsb);
       fs->pass[fs->n_pass++] = ps;
     }
   }
   fs->jq_row = off;
-  (void)max_kc;
+  fs->s_doubles_per_unit = s_per_unit;
 
   auto up = [&](auto &buf, const auto &vec) -> cudaError_t {
     cudaError_t e = buf.reserve(vec.size());
@@ -798,15 +836,15 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
     return cudaMemcpyAsync(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice, st);
   };
   FCK(up(fs->col_tt, col_tt)); FCK(up(fs->col_l, col_l)); FCK(up(fs->col_lm, col_lm));
-  FCK(up(fs->term_col0, term_col0));
+  FCK(up(fs->term_col0, term_col0)); FCK(up(fs->slot_tp, slot_tp)); FCK(up(fs->slot_sign, slot_sign));
   FCK(fs->Jq.reserve((size_t)h.xx_size * fs->jq_row));
   for (int ip = 0; ip < fs->n_pass; ++ip) {
     const TcPass &ps = fs->pass[ip];
     const TcBlock &B = fs->blk[ps.blk];
     int64_t n = (int64_t)B.nkc * ps.nsb * 8;
     dim3 grid((unsigned)((n + 127) / 128), (unsigned)h.xx_size);
-    tc_build_table_kernel<<<grid, 128, 0, st>>>(P.proj.J, P.proj.n_cols, fs->jq_row, ps, B, fs->term_col0.p,
-                                                fs->col_lm.p, fs->Jq.p);
+    tc_build_table_kernel<<<grid, 128, 0, st>>>(P.proj.J, P.proj.n_cols, fs->jq_row, ps, B, blk_kcs[ps.blk],
+                                                fs->term_col0.p, fs->col_lm.p, fs->Jq.p);
     FCK(cudaGetLastError());
   }
   FCK(fs->nact.reserve((size_t)fs->n_blocks * h.xx_size));
@@ -819,6 +857,14 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
   tc_nact_cummax_kernel<<<1, 32, 0, st>>>(fs->nact.p, h.xx_size, fs->n_blocks);
   FCK(cudaGetLastError());
   FCK(cudaStreamSynchronize(st));
+
+  if (!fs->encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FCK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { err = "cuTensorMapEncodeTiled is not available in this driver"; return 1; }
+    fs->encode = (PFN_cuTensorMapEncodeTiled)fn;
+  }
   fs->table_ready = true;
   return 0;
 }
@@ -841,29 +887,22 @@ int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
   if (!fs->table_ready && build_layout(fs, h, P, st, err)) return 1;
   const Batch &b = P.b;
   const int64_t U = b.n_units;
-  const int64_t rowlen = (int64_t)P.tm.tau_size * P.ty.tp2_size;
+  const int tau_size = P.tm.tau_size, tp2 = P.ty.tp2_size;
+  const int64_t rowlen = (int64_t)tau_size * tp2;
   if (U >= (int64_t)1 << 31) { err = "more than 2^31 k3 units in one batch"; return 1; }
-  if (b.n_pairs > 65535) { err = "more than 65535 pairs in one batch"; return 1; }
+  const int MT = 16 * fs->wm;
+  const int64_t n_tiles = (U + MT - 1) / MT;
 
-  // ---- phase 0: transposed {y, dd} sources, edge rows ----
+  // ---- phase 0: transposed {y, dd} sources ----
   FCK(cudaEventRecord(fs->ev[0], st));
-  const int64_t n_src = h.n_src_total;
-  FCK(fs->CSD.reserve((size_t)n_src));                           // (np - 1) intervals per pair: n_src is an upper bound
+  FCK(fs->CSD.reserve((size_t)h.n_src_total));
   {
     int64_t cols = rowlen * b.n_pairs;
     if (cols > 0) {
-      tc_spline_csd_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(b, P.tm.tau_size, P.ty.tp2_size,
-                                                                          P.cubic_k3, fs->CSD.p, P.err);
+      tc_spline_csd_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(b, tau_size, tp2, P.cubic_k3, fs->CSD.p, P.err);
       FCK(cudaGetLastError());
       tm->n_launches++;
     }
-  }
-  FCK(fs->E.reserve((size_t)b.n_pairs * 2 * rowlen));
-  if (P.flat_extrap && b.n_pairs > 0) {
-    dim3 grid((unsigned)std::min<int64_t>((rowlen + 255) / 256, 64), (unsigned)b.n_pairs, 2);
-    tc_edge_rows_kernel<<<grid, 256, 0, st>>>(b, rowlen, fs->CSD.p, fs->E.p, P.err);
-    FCK(cudaGetLastError());
-    tm->n_launches++;
   }
   FCK(cudaEventRecord(fs->ev[1], st));
 
@@ -883,50 +922,83 @@ int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
     tm->n_launches += 4;
   }
   FCK(cudaEventRecord(fs->ev[2], st));
-  FCK(fs->units.reserve((size_t)U));
+
+  // ---- phase 2: interpolated sources in consumption order ----
+  FCK(fs->uw.reserve((size_t)U)); FCK(fs->ujp.reserve((size_t)U));
+  FCK(fs->S.reserve((size_t)U * fs->s_doubles_per_unit));
+  TcInterp &I = fs->interp;
+  I = TcInterp{};
+  I.n_groups = fs->n_groups;
+  {
+    int64_t s_off = 0, col0 = 0;
+    for (int g = 0; g < fs->n_groups; ++g) {
+      fs->grp[g].s_off = s_off;
+      I.grp_tpp[g] = fs->grp[g].tpp; I.grp_s_off[g] = s_off; I.grp_col0[g] = col0;
+      s_off += U * (int64_t)tau_size * fs->grp[g].tpp;
+      col0 += (int64_t)tau_size * fs->grp[g].tpp;
+    }
+    I.grp_col0[fs->n_groups] = col0;
+  }
+  I.slot_tp = fs->slot_tp.p; I.slot_sign = fs->slot_sign.p;
   if (U > 0) {
-    tc_prep_units_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(b, fs->perm.p, fs->unit_pair.p, rowlen,
-                                                                     P.flat_extrap, fs->CSD.p, fs->E.p, fs->units.p, P.err);
+    tc_prep_units_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(b, fs->perm.p, fs->unit_pair.p, P.flat_extrap,
+                                                                     fs->uw.p, fs->ujp.p, P.err);
     FCK(cudaGetLastError());
-    tm->n_launches++;
+    const int64_t ncol = I.grp_col0[fs->n_groups];
+    dim3 grid((unsigned)b.n_pairs, (unsigned)((ncol + 255) / 256));
+    if (grid.y > 65535) { err = "too many source columns for the interpolation kernel"; return 1; }
+    tc_interp_units_kernel<<<grid, 256, 0, st>>>(b, I, tau_size, tp2, fs->CSD.p, fs->uw.p, fs->ujp.p, fs->S.p);
+    FCK(cudaGetLastError());
+    tm->n_launches += 2;
   }
   FCK(cudaEventRecord(fs->ev[3], st));
 
-  // ---- phase 2: the DMMA kernel ----
+  // ---- phase 3: the DMMA kernel ----
   TcParams &TP = fs->tp;
   TP = TcParams{};
-  TP.n_blocks = fs->n_blocks; TP.n_pass = fs->n_pass;
+  TP.n_blocks = fs->n_blocks; TP.n_groups = fs->n_groups; TP.n_pass = fs->n_pass;
   for (int i = 0; i < fs->n_blocks; ++i) TP.blk[i] = fs->blk[i];
+  for (int i = 0; i < fs->n_groups; ++i) TP.grp[i] = fs->grp[i];
   for (int i = 0; i < fs->n_pass; ++i) TP.pass[i] = fs->pass[i];
-  for (size_t i = 0; i < fs->term_tp.size(); ++i) { TP.term_tp[i] = fs->term_tp[i]; TP.term_sign[i] = fs->term_sign[i]; }
   TP.col_tt = fs->col_tt.p; TP.col_l = fs->col_l.p;
   TP.Jq = fs->Jq.p; TP.jq_row = fs->jq_row; TP.nact = fs->nact.p;
-  TP.units = fs->units.p; TP.n_units = U;
-  TP.rowlen = rowlen; TP.tau_size = P.tm.tau_size; TP.tp2_size = P.ty.tp2_size;
+  TP.k_sorted = fs->keys_out.p; TP.perm = fs->perm.p; TP.n_units = U;
+  TP.tau_size = tau_size;
   TP.tau0_minus_tau = P.tm.tau0_minus_tau; TP.delta_tau = P.tm.delta_tau; TP.xx = P.xx;
   TP.inv_xx_step = 1.0 / P.xx_step; TP.xx_size = P.xx_size;
   TP.out = b.out; TP.out_stride = U; TP.err = P.err;
+  if (const char *v = getenv("SONG_LOS_TC_DBG")) TP.dbg = atoi(v);
+  if (U > 0) {
+    for (int g = 0; g < fs->n_groups; ++g) {
+      const TcGroup &G = fs->grp[g];
+      cuuint64_t gdim[3] = {(cuuint64_t)G.tpp, (cuuint64_t)tau_size, (cuuint64_t)U};
+      cuuint64_t gstr[2] = {(cuuint64_t)G.tpp * 8, (cuuint64_t)G.tpp * 8 * (cuuint64_t)tau_size};
+      cuuint32_t box[3] = {(cuuint32_t)G.tpp, 1u, (cuuint32_t)MT};
+      cuuint32_t estr[3] = {1u, 1u, 1u};
+      CUresult r = fs->encode(&TP.tmap[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, fs->S.p + G.s_off, gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r); return 1; }
+    }
+  }
 
-  const int MT = 16 * fs->wm;
-  const int arow = MT * 4 + TC_APAD;
   auto r128 = [](size_t x) { return (x + 127) / 128 * 128; };
-  TP.hdr_bytes = (int)r128(16 + (size_t)MT * 4);
-  TP.a_bytes = (int)r128((size_t)fs->kcs_max * arow * 8);
+  TP.hdr_bytes = (int)r128(16 + (size_t)MT * 4 + (size_t)MT * 16);
+  TP.a_bytes = (int)r128((size_t)MT * fs->tpp_max * 8);
   TP.b_row_bytes = fs->nsb_pass_max * fs->kcs_max * 256;
   int rmax = (MT >= 128) ? 4 : (MT >= 64 ? 3 : 2);
   if (const char *v = getenv("SONG_LOS_TC_RMAX")) rmax = std::max(1, std::min(8, atoi(v)));
-  const size_t fixed = 128 + (size_t)MT * 4;
+  const size_t fixed = 128 + (size_t)MT * 12 + (size_t)((tau_size + 15) & ~15) * 16;
   const size_t budget = 224 * 1024;
   auto stage_bytes = [&](int r) { return (size_t)TP.hdr_bytes + TP.a_bytes + (size_t)r * TP.b_row_bytes; };
   while (rmax > 1 && (budget - fixed) / stage_bytes(rmax) < 3) --rmax;
-  int ns = (int)std::min<size_t>(8, (budget - fixed) / stage_bytes(rmax));
+  int ns = (int)std::min<size_t>(TC_MAX_STAGES, (budget - fixed) / stage_bytes(rmax));
   if (const char *v = getenv("SONG_LOS_TC_STAGES")) ns = std::max(2, std::min(ns, atoi(v)));
   if (ns < 2) { err = "FAST kernel: shared-memory stage does not fit"; return 1; }
   TP.rmax = rmax; TP.n_stages = ns;
   TP.stage_bytes = (int)stage_bytes(rmax);
   const size_t smem = fixed + (size_t)ns * TP.stage_bytes;
 
-  const int64_t n_tiles = (U + MT - 1) / MT;
   if (n_tiles > 0) {
     cudaError_t e = cudaErrorInvalidValue;
     const int key = fs->wm * 100 + fs->nw;
