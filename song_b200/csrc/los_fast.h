@@ -19,6 +19,7 @@ struct FastHostLayout {
   const unsigned char *block_nonzero;   // [J_size*L_size]
   int64_t n_src_total;
   int tau_size;
+  int64_t n_pt_total;                   // coarse k3 points of the batch
 };
 
 struct FastState;

@@ -269,7 +269,7 @@ __global__ void tc_iota_kernel(int *p, int64_t n)
 struct TcUnitW { double a, b, a3h, b3h; };          // a, b, (a^3-a) h^2/6, (b^3-b) h^2/6
 
 __global__ void tc_prep_units_kernel(Batch b, const int *perm, const int *unit_pair, int flat_extrap,
-                                     TcUnitW *uw, int2 *ujp, int *err)
+                                     TcUnitW *uw, int2 *ujp, int *jcount, int *err)
 {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // sorted position
   if (s >= b.n_units) return;
@@ -293,57 +293,73 @@ __global__ void tc_prep_units_kernel(Batch b, const int *perm, const int *unit_p
   TcUnitW w; w.a = a; w.b = bb; w.a3h = (a * a * a - a) * h6; w.b3h = (bb * bb * bb - bb) * h6;
   uw[u] = w;
   ujp[u] = make_int2(j, (int)s);
+  atomicAdd(&jcount[b.pt_off[p] + j], 1);
 }
 
-// interp_units: CTA = (pair, chunk of 256 columns); thread = one column (group, tau, slot) of the
-// S slabs.  Walks the units of the pair in k3 order: the bracket j only moves forward, so the CSD rows
-// of an interval are (re)loaded once per interval; each unit costs 4 FMAs and one coalesced store
-// (consecutive threads = consecutive doubles of S[group][sorted unit][tau][slot]).
+// interp_units: CTA = (pair, chunk of TAUC tau samples).  The CTA walks the k3 intervals of the pair;
+// per interval it stages the one new CSD row in shared memory (each row is read once per CTA) and its
+// warps take the units inside the interval round-robin.  A warp evaluates the spline of its unit for
+// every (group, tau, slot) column of the chunk -- 4 FMAs each -- and writes them as one contiguous
+// run per group of S[group][sorted unit][tau][slot]: full 256-byte stores, sequential per unit.
 constexpr int TC_SLOTS = 2 * TC_KCS_MAX + 4;
+constexpr int TC_INTERP_THREADS = 256;
 struct TcInterp {
   int n_groups;
+  int tauc;                               // tau samples per CTA
   int grp_tpp[TC_MAX_GROUPS];             // slots per (unit, tau) row of the group
   int64_t grp_s_off[TC_MAX_GROUPS];       // slab offsets
-  int64_t grp_col0[TC_MAX_GROUPS + 1];    // first column index of each group: cumulative tau_size*tpp
   const int *slot_tp;                     // per (group, slot): source type, -1 = padding   [n_groups][TC_SLOTS]
   const double *slot_sign;
+  const int *jcount;                      // units per (pair, interval): indexed pt_off[p] + j
 };
 
-__global__ void __launch_bounds__(256) tc_interp_units_kernel(Batch b, TcInterp I, int tau_size, int tp2_size,
+__global__ void __launch_bounds__(TC_INTERP_THREADS) tc_interp_units_kernel(Batch b, TcInterp I, int tau_size, int tp2_size,
                                                               const double2 *CSD, const TcUnitW *uw, const int2 *ujp, double *S)
 {
+  extern __shared__ __align__(16) unsigned char interp_smem[];
   const int p = blockIdx.x;
-  const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-  if (c >= I.grp_col0[I.n_groups]) return;
-  int g = 0;
-  while (c >= I.grp_col0[g + 1]) ++g;
-  const int tpp = I.grp_tpp[g];
-  const int64_t cg = c - I.grp_col0[g];
-  const int tau = (int)(cg / tpp), slot = (int)(cg % tpp);
-  const int tp = I.slot_tp[g * TC_SLOTS + slot];
-  const double sign = I.slot_sign[g * TC_SLOTS + slot];
-  const int nt = b.nt[p];
+  const int tau0 = blockIdx.y * I.tauc;
+  const int ntau = min(I.tauc, tau_size - tau0);
+  const int chunk = ntau * tp2_size;                                  // double2 entries of a row chunk
+  double2 *rows = reinterpret_cast<double2 *>(interp_smem);           // [2][tauc * tp2]
+  int *s_tp = reinterpret_cast<int *>(rows + 2 * (size_t)I.tauc * tp2_size);   // [n_groups][TC_SLOTS]
+  double *s_sign = reinterpret_cast<double *>(s_tp + TC_MAX_GROUPS * TC_SLOTS);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = TC_INTERP_THREADS / 32;
+  for (int i = tid; i < I.n_groups * TC_SLOTS; i += TC_INTERP_THREADS) { s_tp[i] = I.slot_tp[i]; s_sign[i] = I.slot_sign[i]; }
+  const int np = b.np[p];
   const int64_t u0 = b.tr_off[p];
-  double *Sg = S + I.grp_s_off[g] + (int64_t)tau * tpp + slot;
-  const int64_t unit_stride = (int64_t)tau_size * tpp;
-  if (tp < 0) {                                              // padding slot: zeros (whole sectors get written)
-    for (int i = 0; i < nt; ++i) Sg[(int64_t)ujp[u0 + i].y * unit_stride] = 0.;
-    return;
-  }
   const int64_t rowlen = (int64_t)tau_size * tp2_size;
-  const double2 *cs = CSD + b.src_off[p] + (int64_t)tau * tp2_size + tp;
-  int jc = -1;
-  double2 s0 = make_double2(0., 0.), s1 = s0;
-  for (int i = 0; i < nt; ++i) {
-    const int2 jp = ujp[u0 + i];
-    const TcUnitW w = uw[u0 + i];
-    if (jp.x != jc) {
-      jc = jp.x;
-      s0 = cs[(int64_t)jc * rowlen]; s1 = cs[(int64_t)(jc + 1) * rowlen];
+  const double2 *cs = CSD + b.src_off[p] + (int64_t)tau0 * tp2_size;
+  const int *jcount = I.jcount + b.pt_off[p];
+  for (int c = tid; c < chunk; c += TC_INTERP_THREADS) rows[c] = cs[c];      // row 0
+  int start = 0;
+  for (int j = 0; j + 1 < np; ++j) {
+    double2 *r0 = rows + (size_t)(j & 1) * I.tauc * tp2_size, *r1 = rows + (size_t)((j + 1) & 1) * I.tauc * tp2_size;
+    for (int c = tid; c < chunk; c += TC_INTERP_THREADS) r1[c] = cs[(int64_t)(j + 1) * rowlen + c];
+    __syncthreads();
+    const int cnt = jcount[j];
+    for (int i = start + warp; i < start + cnt; i += nwarps) {
+      const TcUnitW w = uw[u0 + i];
+      const int64_t pos = ujp[u0 + i].y;
+      for (int g = 0; g < I.n_groups; ++g) {
+        const int tpp = I.grp_tpp[g];
+        double *dst = S + I.grp_s_off[g] + (pos * tau_size + tau0) * tpp;
+        const int ncol = ntau * tpp;
+        for (int c = lane; c < ncol; c += 32) {
+          const int tl = c / tpp, slot = c - tl * tpp;
+          const int tp = s_tp[g * TC_SLOTS + slot];
+          double v = 0.;
+          if (tp >= 0) {
+            const double2 a0 = r0[tl * tp2_size + tp], a1 = r1[tl * tp2_size + tp];
+            // transfer2.c:2697 (linear: dd = 0) / :2703-2705 (cubic)
+            v = s_sign[g * TC_SLOTS + slot] * (w.a * a0.x + w.b * a1.x + w.a3h * a0.y + w.b3h * a1.y);
+          }
+          dst[c] = v;
+        }
+      }
     }
-    // transfer2.c:2697 (linear: dd = 0) / :2703-2705 (cubic)
-    const double v = w.a * s0.x + w.b * s1.x + w.a3h * s0.y + w.b3h * s1.y;
-    Sg[(int64_t)jp.y * unit_stride] = sign * v;
+    start += cnt;
+    __syncthreads();
   }
 }
 
@@ -681,7 +697,7 @@ struct FastState {
   int kcs_max = 1, nsb_pass_max = 1, tpp_max = 4;
   Buf<double> Jq, keys_out, S, slot_sign;
   Buf<double2> CSD;
-  Buf<int> col_tt, col_l, col_lm, term_col0, nact, perm_in, perm, unit_pair, slot_tp;
+  Buf<int> col_tt, col_l, col_lm, term_col0, nact, perm_in, perm, unit_pair, slot_tp, jcount;
   Buf<TcUnitW> uw; Buf<int2> ujp;
   Buf<unsigned char> cub_tmp;
   TcParams tp{};                 // kernel parameter block (about 3 KB: kept off the stack)
@@ -699,7 +715,7 @@ void fast_state_destroy(FastState *f)
   f->Jq.release(); f->keys_out.release(); f->S.release(); f->slot_sign.release(); f->CSD.release();
   f->col_tt.release(); f->col_l.release(); f->col_lm.release(); f->term_col0.release(); f->nact.release();
   f->perm_in.release(); f->perm.release(); f->unit_pair.release(); f->slot_tp.release();
-  f->uw.release(); f->ujp.release(); f->cub_tmp.release();
+  f->uw.release(); f->ujp.release(); f->cub_tmp.release(); f->jcount.release();
   if (f->ev_ready) for (auto &e : f->ev) cudaEventDestroy(e);
   delete f;
 }
@@ -930,24 +946,27 @@ int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
   I = TcInterp{};
   I.n_groups = fs->n_groups;
   {
-    int64_t s_off = 0, col0 = 0;
+    int64_t s_off = 0;
     for (int g = 0; g < fs->n_groups; ++g) {
       fs->grp[g].s_off = s_off;
-      I.grp_tpp[g] = fs->grp[g].tpp; I.grp_s_off[g] = s_off; I.grp_col0[g] = col0;
+      I.grp_tpp[g] = fs->grp[g].tpp; I.grp_s_off[g] = s_off;
       s_off += U * (int64_t)tau_size * fs->grp[g].tpp;
-      col0 += (int64_t)tau_size * fs->grp[g].tpp;
     }
-    I.grp_col0[fs->n_groups] = col0;
   }
   I.slot_tp = fs->slot_tp.p; I.slot_sign = fs->slot_sign.p;
+  FCK(fs->jcount.reserve((size_t)h.n_pt_total));
+  I.jcount = fs->jcount.p;
+  // tau samples per CTA: two staged rows of tauc*tp2 {y, dd} entries within ~64 KB
+  I.tauc = std::max(1, std::min(tau_size, (int)((64 * 1024) / (2 * 16 * (size_t)tp2))));
   if (U > 0) {
+    FCK(cudaMemsetAsync(fs->jcount.p, 0, (size_t)h.n_pt_total * sizeof(int), st));
     tc_prep_units_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(b, fs->perm.p, fs->unit_pair.p, P.flat_extrap,
-                                                                     fs->uw.p, fs->ujp.p, P.err);
+                                                                     fs->uw.p, fs->ujp.p, fs->jcount.p, P.err);
     FCK(cudaGetLastError());
-    const int64_t ncol = I.grp_col0[fs->n_groups];
-    dim3 grid((unsigned)b.n_pairs, (unsigned)((ncol + 255) / 256));
-    if (grid.y > 65535) { err = "too many source columns for the interpolation kernel"; return 1; }
-    tc_interp_units_kernel<<<grid, 256, 0, st>>>(b, I, tau_size, tp2, fs->CSD.p, fs->uw.p, fs->ujp.p, fs->S.p);
+    dim3 grid((unsigned)b.n_pairs, (unsigned)((tau_size + I.tauc - 1) / I.tauc));
+    const size_t ismem = (size_t)2 * I.tauc * tp2 * 16 + (size_t)TC_MAX_GROUPS * TC_SLOTS * 12;
+    FCK(cudaFuncSetAttribute(tc_interp_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
+    tc_interp_units_kernel<<<grid, TC_INTERP_THREADS, ismem, st>>>(b, I, tau_size, tp2, fs->CSD.p, fs->uw.p, fs->ujp.p, fs->S.p);
     FCK(cudaGetLastError());
     tm->n_launches += 2;
   }

@@ -476,7 +476,7 @@ extern "C" int song_los_compute(song_los_ctx *ctx, int mode, song_los_timing *tm
     h.l_size = c.l_size; h.m_size = c.m_size; h.L_size = c.L_size; h.n_transfers = c.n_transfers;
     h.xx_size = c.xx_size; h.l = c.l; h.m = c.m; h.lm_array = c.lm_array; h.lm_src = c.lm_src;
     h.block_nonzero = ctx->h_block_nonzero.data(); h.n_src_total = ctx->hb.n_src_total;
-    h.tau_size = c.tau_size;
+    h.tau_size = c.tau_size; h.n_pt_total = ctx->hb.n_pt_total;
     if (fast_compute(ctx->fast, h, P, ctx->h_unit_pair.data(), ctx->sm_count, st, &t, e) != 0)
       return ctx_fail(ctx, "%s", e.c_str());
   } else {
