@@ -77,10 +77,11 @@ struct TcParams {
   TcBlock blk[TC_MAX_BLOCKS];
   TcGroup grp[TC_MAX_GROUPS];
   TcPass pass[TC_MAX_PASSES];
-  const int *col_tt, *col_l;              // per column: transfer type index, multipole l
+  const int *col_tt; const double *col_scale;   // per column: transfer type index, 1 / (16 (2l+1))
   const double *Jq; int64_t jq_row;       // tensor-core table and its row length (doubles)
   const int *nact;                        // [n_blocks][xx_size] active sub-block prefix per row
   const double *k_sorted; const int *perm; int64_t n_units;   // sorted k3 and original unit index
+  int sm_count;
   int tau_size;
   const double *tau0_minus_tau, *delta_tau, *xx;
   double inv_xx_step; int xx_size;
@@ -477,23 +478,20 @@ __device__ __forceinline__ void tc_mma_row_global(double (&acc0)[NW][2], double 
 template <int WM, int WN, int NW>
 __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_constant__ TcParams P)
 {
-  constexpr int MT = 16 * WM;                    // units per CTA
+  constexpr int MT = 16 * WM;                    // units per tile
   constexpr int UPL = MT / 32;                   // units per producer lane
   static_assert(WM * WN == TC_CONSUMERS / 32, "8 consumer warps");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int NS = P.n_stages;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);             // full[8], empty[8]
-  int *unit_id = reinterpret_cast<int *>(smem_raw + 128);
-  double *unit_k = reinterpret_cast<double *>(smem_raw + 128 + MT * 4);
-  double *tau_d = unit_k + MT;                                          // tau0 - tau       [tau_pad]
+  int *unit_id = reinterpret_cast<int *>(smem_raw + 128);               // [2][MT]: tiles alternate buffers
+  double *tau_d = reinterpret_cast<double *>(smem_raw + 128 + MT * 8); // tau0 - tau       [tau_pad]
   const int tau_pad = (P.tau_size + 15) & ~15;
   double *tau_w = tau_d + tau_pad;                                      // trapezoid weight [tau_pad]
-  unsigned char *stage0 = smem_raw + 128 + MT * 12 + (size_t)tau_pad * 16;   // 128-byte aligned (MT % 32 == 0)
+  unsigned char *stage0 = smem_raw + 128 + MT * 8 + (size_t)tau_pad * 16;   // 128-byte aligned (MT % 32 == 0)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t s0 = (int64_t)blockIdx.x * MT;
-  const int64_t nleft = P.n_units - s0;
-  const int nvalid = nleft < (int64_t)MT ? (int)nleft : MT;
+  const int64_t n_tiles = (P.n_units + MT - 1) / MT;
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -503,86 +501,97 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  for (int n = tid; n < MT; n += TC_THREADS) {
-    const int64_t sidx = s0 + (n < nvalid ? n : nvalid - 1);        // tail: replicate the last unit, never stored
-    unit_id[n] = (n < nvalid) ? P.perm[sidx] : -1;
-    unit_k[n] = P.k_sorted[sidx];
-  }
   for (int t = tid; t < P.tau_size; t += TC_THREADS) { tau_d[t] = P.tau0_minus_tau[t]; tau_w[t] = P.delta_tau[t]; }
   __syncthreads();
 
+  // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (the k3-sorted sequence is sampled
+  // with a stride, so every CTA sees the same mix of cheap low-k and expensive high-k tiles).  The
+  // ring of stages runs across tile boundaries: the producer warp is already filling the stages of
+  // the next tile while the consumers drain and store the current one.
+  int s = 0; uint32_t ph = 0;                   // ring slot and its phase parity, advanced per stage
+#define TC_ADVANCE() do { if (++s == NS) { s = 0; ph ^= 1u; } } while (0)
+
   if (warp == TC_CONSUMERS / 32) {
     // =========================== producer warp ===========================
-    // lane <-> units lane, lane+32, ...; stage sequence: pass, K chunk, tau
-    double kk[UPL];
+    // lane <-> units lane, lane+32, ...; stage sequence per tile: pass, K chunk, tau
+    bool first_round = true;                    // the first NS stages need no empty-slot wait
+    int tbuf = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tbuf ^= 1) {
+      const int64_t s0 = tile * MT;
+      const int64_t nleft = P.n_units - s0;
+      const int nvalid = nleft < (int64_t)MT ? (int)nleft : MT;
+      double kk[UPL];
 #pragma unroll
-    for (int i = 0; i < UPL; ++i) kk[i] = unit_k[lane + 32 * i];
-    const double k_first = unit_k[0], k_last = unit_k[MT - 1];
-    int n_stage_total = 0;
-    for (int ip = 0; ip < P.n_pass; ++ip) n_stage_total += P.pass[ip].nq * P.tau_size;
-    // row index and xx[ix+1] of the NEXT stage are fetched one stage ahead (the table read is the
-    // only long-latency step of the lane's work)
-    int ix_n[UPL]; double xxn_n[UPL], x_n[UPL];
+      for (int i = 0; i < UPL; ++i) {
+        const int n = lane + 32 * i;
+        const int64_t sidx = s0 + (n < nvalid ? n : nvalid - 1);      // tail: replicate the last unit, never stored
+        kk[i] = __ldg(P.k_sorted + sidx);
+        unit_id[tbuf * MT + n] = (n < nvalid) ? __ldg(P.perm + sidx) : -1;
+      }
+      const double k_first = __ldg(P.k_sorted + s0), k_last = __ldg(P.k_sorted + s0 + nvalid - 1);
+      // row index and xx[ix+1] of the NEXT stage are fetched one stage ahead (the table read is the
+      // only long-latency step of the lane's work)
+      int ix_n[UPL]; double xxn_n[UPL], x_n[UPL];
 #define TC_PREFETCH(T) do { \
-      const double d_ = tau_d[T]; \
-      _Pragma("unroll") for (int i = 0; i < UPL; ++i) { \
-        const double x_ = kk[i] * d_;                                 /* transfer2.c:2195 */ \
-        int ix_ = (int)(x_ * P.inv_xx_step);                          /* transfer2.c:2199 */ \
-        if (ix_ < 0 || ix_ + 1 >= P.xx_size) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); ix_ = 0; } \
-        x_n[i] = x_; ix_n[i] = ix_; xxn_n[i] = __ldg(P.xx + ix_ + 1); } } while (0)
-    TC_PREFETCH(0);
-    int it = 0;
-    for (int ip = 0; ip < P.n_pass; ++ip) {
-      const TcPass ps = P.pass[ip];
-      const int *nact_b = P.nact + (int64_t)ps.blk * P.xx_size;
-      for (int q = 0; q < ps.nq; ++q) {
-        const TcGroup G = P.grp[ps.g0 + q];
-        const uint32_t bytes_per_sb = (uint32_t)G.kcs * 256u;
-        const uint32_t s_bytes = (uint32_t)MT * G.tpp * 8u;
-        const int64_t q_off = ps.jq_off + (int64_t)ps.nsb * G.kc0 * 32;
-        const CUtensorMap *tmap = &P.tmap[ps.g0 + q];
-        for (int t = 0; t < P.tau_size; ++t, ++it) {
-          const int s = it % NS;
-          const uint32_t full = smem_u32(&bars[s]), empty = smem_u32(&bars[8 + s]);
-          const TcStagePtrs st = tc_stage<MT>(stage0, s, P);
-          const double d = tau_d[t], w = tau_w[t];
-          int ix[UPL]; double c0[UPL], c1[UPL];
+        const double d_ = tau_d[T]; \
+        _Pragma("unroll") for (int i = 0; i < UPL; ++i) { \
+          const double x_ = kk[i] * d_;                                 /* transfer2.c:2195 */ \
+          int ix_ = (int)(x_ * P.inv_xx_step);                          /* transfer2.c:2199 */ \
+          if (ix_ < 0 || ix_ + 1 >= P.xx_size) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); ix_ = 0; } \
+          x_n[i] = x_; ix_n[i] = ix_; xxn_n[i] = __ldg(P.xx + ix_ + 1); } } while (0)
+      TC_PREFETCH(0);
+      for (int ip = 0; ip < P.n_pass; ++ip) {
+        const TcPass ps = P.pass[ip];
+        const int *nact_b = P.nact + (int64_t)ps.blk * P.xx_size;
+        for (int q = 0; q < ps.nq; ++q) {
+          const TcGroup G = P.grp[ps.g0 + q];
+          const uint32_t bytes_per_sb = (uint32_t)G.kcs * 256u;
+          const uint32_t s_bytes = (uint32_t)MT * G.tpp * 8u;
+          const int64_t q_off = ps.jq_off + (int64_t)ps.nsb * G.kc0 * 32;
+          const CUtensorMap *tmap = &P.tmap[ps.g0 + q];
+          for (int t = 0; t < P.tau_size; ++t) {
+            const uint32_t full = smem_u32(&bars[s]), empty = smem_u32(&bars[8 + s]);
+            const TcStagePtrs st = tc_stage<MT>(stage0, s, P);
+            const double d = tau_d[t], w = tau_w[t];
+            int ix[UPL]; double c0[UPL], c1[UPL];
 #pragma unroll
-          for (int i = 0; i < UPL; ++i) {
-            ix[i] = ix_n[i];
-            const double a_J = (xxn_n[i] - x_n[i]) * P.inv_xx_step;        // transfer2.c:2202
-            c0[i] = w * a_J; c1[i] = w - c0[i];                            // weights of J[ix], J[ix+1]
-          }
-          int row_lo = 0, row_hi = 0, nact = 0;
-          if (lane == 0) {
-            // table rows of the tile at this tau: units are k3-sorted, so rows are [row(first), row(last)]
-            row_lo = (int)(k_first * d * P.inv_xx_step); row_hi = (int)(k_last * d * P.inv_xx_step);
-            row_lo = max(0, min(row_lo, P.xx_size - 2)); row_hi = max(row_lo, min(row_hi, P.xx_size - 2));
-            nact = max(0, min(__ldg(nact_b + row_hi) - ps.sb0, ps.nsb));
-          }
-          if (it + 1 < n_stage_total) { const int tn = (t + 1 < P.tau_size) ? t + 1 : 0; TC_PREFETCH(tn); }
-          if (it >= NS) mbar_wait(empty, ((it / NS) - 1) & 1);
-          if (lane == 0) {
-            const int nrows = min(row_hi - row_lo + 1, P.rmax);
-            const uint32_t bytes_row = (uint32_t)nact * bytes_per_sb;
-            st.meta[0] = row_lo; st.meta[1] = nrows; st.meta[2] = nact; st.meta[3] = row_hi;
-            mbar_arrive_expect_tx(full, s_bytes + bytes_row * nrows);
-            tma_load_3d(smem_u32(st.S), tmap, 0, t, (int)s0, full);
-            const double *src = P.Jq + (int64_t)row_lo * P.jq_row + q_off;
-            if (bytes_row > 0)
-              for (int r = 0; r < nrows; ++r)
-                bulk_g2s(smem_u32(st.B) + r * P.b_row_bytes, src + (int64_t)r * P.jq_row, bytes_row, full);
-          }
+            for (int i = 0; i < UPL; ++i) {
+              ix[i] = ix_n[i];
+              const double a_J = (xxn_n[i] - x_n[i]) * P.inv_xx_step;        // transfer2.c:2202
+              c0[i] = w * a_J; c1[i] = w - c0[i];                            // weights of J[ix], J[ix+1]
+            }
+            int row_lo = 0, row_hi = 0, nact = 0;
+            if (lane == 0) {
+              // table rows of the tile at this tau: units are k3-sorted, so rows are [row(first), row(last)]
+              row_lo = (int)(k_first * d * P.inv_xx_step); row_hi = (int)(k_last * d * P.inv_xx_step);
+              row_lo = max(0, min(row_lo, P.xx_size - 2)); row_hi = max(row_lo, min(row_hi, P.xx_size - 2));
+              nact = max(0, min(__ldg(nact_b + row_hi) - ps.sb0, ps.nsb));
+            }
+            { const int tn = (t + 1 < P.tau_size) ? t + 1 : 0; TC_PREFETCH(tn); }   // next stage of this tile
+            if (!first_round) mbar_wait(empty, ph ^ 1u);
+            if (lane == 0) {
+              const int nrows = min(row_hi - row_lo + 1, P.rmax);
+              const uint32_t bytes_row = (uint32_t)nact * bytes_per_sb;
+              st.meta[0] = row_lo; st.meta[1] = nrows; st.meta[2] = nact; st.meta[3] = row_hi;
+              mbar_arrive_expect_tx(full, s_bytes + bytes_row * nrows);
+              tma_load_3d(smem_u32(st.S), tmap, 0, t, (int)s0, full);
+              const double *src = P.Jq + (int64_t)row_lo * P.jq_row + q_off;
+              if (bytes_row > 0)
+                for (int r = 0; r < nrows; ++r)
+                  bulk_g2s(smem_u32(st.B) + r * P.b_row_bytes, src + (int64_t)r * P.jq_row, bytes_row, full);
+            }
 #pragma unroll
-          for (int i = 0; i < UPL; ++i) {
-            st.ixs[lane + 32 * i] = ix[i];
-            st.cc[lane + 32 * i] = make_double2(c0[i], c1[i]);
+            for (int i = 0; i < UPL; ++i) {
+              st.ixs[lane + 32 * i] = ix[i];
+              st.cc[lane + 32 * i] = make_double2(c0[i], c1[i]);
+            }
+            mbar_arrive(full);
+            if (++s == NS) { s = 0; ph ^= 1u; first_round = false; }
           }
-          mbar_arrive(full);
         }
       }
-    }
 #undef TC_PREFETCH
+    }
     return;
   }
 
@@ -591,81 +600,85 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
   const int g0 = warp_m * 2, g1 = g0 + 1;      // the two 8-unit groups of this warp
   const int um = lane >> 2;                    // unit inside a group held by this lane (A and C rows)
   const int ksel = lane & 1, tsel = (lane & 3) >> 1;   // weight {c0,c1} and term of the kc held by this lane
-  int it = 0;
-  for (int ip = 0; ip < P.n_pass; ++ip) {
-    const TcPass ps = P.pass[ip];
-    const TcBlock B = P.blk[ps.blk];
-    double acc0[NW][2], acc1[NW][2];
+  int tbuf = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tbuf ^= 1) {
+    for (int ip = 0; ip < P.n_pass; ++ip) {
+      const TcPass ps = P.pass[ip];
+      const TcBlock B = P.blk[ps.blk];
+      double acc0[NW][2], acc1[NW][2];
 #pragma unroll
-    for (int j = 0; j < NW; ++j) { acc0[j][0] = acc0[j][1] = 0.; acc1[j][0] = acc1[j][1] = 0.; }
+      for (int j = 0; j < NW; ++j) { acc0[j][0] = acc0[j][1] = 0.; acc1[j][0] = acc1[j][1] = 0.; }
 
-    for (int q = 0; q < ps.nq; ++q) {
-      const TcGroup G = P.grp[ps.g0 + q];
-      const int kcs_q = G.kcs;
-      const int b_sb_stride = WN * kcs_q * 32;
-      for (int t = 0; t < P.tau_size; ++t, ++it) {
-        const int s = it % NS;
-        const TcStagePtrs st = tc_stage<MT>(stage0, s, P);
-        mbar_wait(smem_u32(&bars[s]), (it / NS) & 1);
-        const int row_lo = st.meta[0], nrows = st.meta[1], nact = st.meta[2];
-        // owned sub-blocks: warp_n, warp_n + WN, ... ; active ones form a prefix of that list
-        const int nactw = (nact > warp_n) ? min(NW, (nact - warp_n + WN - 1) / WN) : 0;
-        if (nactw > 0 && !(P.dbg & 4)) {
-          const int ix0 = st.ixs[g0 * 8 + um];
-          const int ix1 = st.ixs[g1 * 8 + um];
-          const double2 cc0 = st.cc[g0 * 8 + um], cc1 = st.cc[g1 * 8 + um];
-          const double cw0 = ksel ? cc0.y : cc0.x, cw1 = ksel ? cc1.y : cc1.x;
-          // A fragment of kc: S[unit][2 kc + tsel] x weight
-          const double *a0p = st.S + (size_t)(g0 * 8 + um) * G.tpp + tsel;
-          const double *a1p = st.S + (size_t)(g1 * 8 + um) * G.tpp + tsel;
-          int v = __reduce_min_sync(0xffffffffu, min(ix0, ix1));
-          while (v != 0x7fffffff) {
-            const bool m0 = (ix0 == v), m1 = (ix1 == v);
-            const bool any0 = __any_sync(0xffffffffu, m0), any1 = __any_sync(0xffffffffu, m1);
-            const double w0 = m0 ? cw0 : 0., w1 = m1 ? cw1 : 0.;
-            const int rb = v - row_lo;
-            if (rb < nrows) {
-              const double *bp = st.B + (size_t)rb * (P.b_row_bytes / 8) + (size_t)warp_n * kcs_q * 32 + lane;
+      for (int q = 0; q < ps.nq; ++q) {
+        const TcGroup G = P.grp[ps.g0 + q];
+        const int kcs_q = G.kcs;
+        const int b_sb_stride = WN * kcs_q * 32;
+        const int a_off0 = (g0 * 8 + um) * G.tpp + tsel, a_off1 = (g1 * 8 + um) * G.tpp + tsel;
+        for (int t = 0; t < P.tau_size; ++t) {
+          const TcStagePtrs st = tc_stage<MT>(stage0, s, P);
+          mbar_wait(smem_u32(&bars[s]), ph);
+          const int row_lo = st.meta[0], nrows = st.meta[1], nact = st.meta[2];
+          // owned sub-blocks: warp_n, warp_n + WN, ... ; active ones form a prefix of that list
+          const int nactw = (nact > warp_n) ? min(NW, (nact - warp_n + WN - 1) / WN) : 0;
+          if (nactw > 0 && !(P.dbg & 4)) {
+            const int ix0 = st.ixs[g0 * 8 + um];
+            const int ix1 = st.ixs[g1 * 8 + um];
+            const double2 cc0 = st.cc[g0 * 8 + um], cc1 = st.cc[g1 * 8 + um];
+            const double cw0 = ksel ? cc0.y : cc0.x, cw1 = ksel ? cc1.y : cc1.x;
+            // A fragment of kc: S[unit][2 kc + tsel] x weight
+            const double *a0p = st.S + a_off0;
+            const double *a1p = st.S + a_off1;
+            int v = __reduce_min_sync(0xffffffffu, min(ix0, ix1));
+            while (v != 0x7fffffff) {
+              const bool m0 = (ix0 == v), m1 = (ix1 == v);
+              const bool any0 = __any_sync(0xffffffffu, m0), any1 = __any_sync(0xffffffffu, m1);
+              const double w0 = m0 ? cw0 : 0., w1 = m1 ? cw1 : 0.;
+              const int rb = v - row_lo;
+              if (rb < nrows) {
+                const double *bp = st.B + (size_t)rb * (P.b_row_bytes / 8) + (size_t)warp_n * kcs_q * 32 + lane;
 #define TC_CASE(N) case N: if constexpr (N <= NW) tc_mma_row_smem<N, NW>(acc0, acc1, a0p, a1p, w0, w1, any0, any1, bp, kcs_q, b_sb_stride); break;
-              switch (nactw) {
-                TC_CASE(1) TC_CASE(2) TC_CASE(3) TC_CASE(4) TC_CASE(5) TC_CASE(6) TC_CASE(7) TC_CASE(8) TC_CASE(9) TC_CASE(10)
-              }
+                switch (nactw) {
+                  TC_CASE(1) TC_CASE(2) TC_CASE(3) TC_CASE(4) TC_CASE(5) TC_CASE(6) TC_CASE(7) TC_CASE(8) TC_CASE(9) TC_CASE(10)
+                }
 #undef TC_CASE
-            } else {
-              const double *bp = P.Jq + (int64_t)v * P.jq_row + ps.jq_off + (int64_t)ps.nsb * G.kc0 * 32
-                               + (size_t)warp_n * kcs_q * 32 + lane;
-              tc_mma_row_global<NW>(acc0, acc1, a0p, a1p, w0, w1, bp, kcs_q, b_sb_stride, nactw);
+              } else {
+                const double *bp = P.Jq + (int64_t)v * P.jq_row + ps.jq_off + (int64_t)ps.nsb * G.kc0 * 32
+                                 + (size_t)warp_n * kcs_q * 32 + lane;
+                tc_mma_row_global<NW>(acc0, acc1, a0p, a1p, w0, w1, bp, kcs_q, b_sb_stride, nactw);
+              }
+              const int n0 = (ix0 > v) ? ix0 : 0x7fffffff, n1 = (ix1 > v) ? ix1 : 0x7fffffff;
+              v = __reduce_min_sync(0xffffffffu, min(n0, n1));
             }
-            const int n0 = (ix0 > v) ? ix0 : 0x7fffffff, n1 = (ix1 > v) ? ix1 : 0x7fffffff;
-            v = __reduce_min_sync(0xffffffffu, min(n0, n1));
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars[8 + s]));
+          TC_ADVANCE();
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars[8 + s]));
       }
-    }
 
-    // ---- epilogue: 1/2 of the trapezoid and the divisions of transfer2.c:2092-2098 ----
-    const int cpair = 2 * (lane & 3);
-    const int u0 = unit_id[g0 * 8 + um], u1 = unit_id[g1 * 8 + um];
+      // ---- epilogue: the 1/2 of the trapezoid and the divisions by 4, (2l+1), 2 of
+      //      transfer2.c:2092-2098 as one multiplication by 1 / (16 (2l+1)) ----
+      const int cpair = 2 * (lane & 3);
+      const int u0 = unit_id[tbuf * MT + g0 * 8 + um], u1 = unit_id[tbuf * MT + g1 * 8 + um];
 #pragma unroll
-    for (int j = 0; j < NW; ++j) {
-      const int sb = warp_n + j * WN;
-      if (sb >= ps.nsb) continue;
-      const int cbase = (ps.sb0 + sb) * 8 + cpair;
+      for (int j = 0; j < NW; ++j) {
+        const int sb = warp_n + j * WN;
+        if (sb >= ps.nsb) continue;
+        const int cbase = (ps.sb0 + sb) * 8 + cpair;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = cbase + h;
-        if (c >= B.ncols) continue;
-        const int tt = P.col_tt[B.col_off + c];
-        const double lfac = 2. * P.col_l[B.col_off + c] + 1;
-        double t0 = acc0[j][h] * 0.5; t0 /= 4.; t0 /= lfac; t0 /= 2.;
-        double t1 = acc1[j][h] * 0.5; t1 /= 4.; t1 /= lfac; t1 /= 2.;
-        if (u0 >= 0) { if (t0 != t0) atomicOr(P.err, ERR_NAN); P.out[(int64_t)tt * P.out_stride + u0] = t0; }
-        if (u1 >= 0) { if (t1 != t1) atomicOr(P.err, ERR_NAN); P.out[(int64_t)tt * P.out_stride + u1] = t1; }
+        for (int h = 0; h < 2; ++h) {
+          const int c = cbase + h;
+          if (c >= B.ncols) continue;
+          const int tt = P.col_tt[B.col_off + c];
+          const double scale = P.col_scale[B.col_off + c];
+          const double t0 = acc0[j][h] * scale, t1 = acc1[j][h] * scale;
+          if (u0 >= 0) { if (t0 != t0) atomicOr(P.err, ERR_NAN); P.out[(int64_t)tt * P.out_stride + u0] = t0; }
+          if (u1 >= 0) { if (t1 != t1) atomicOr(P.err, ERR_NAN); P.out[(int64_t)tt * P.out_stride + u1] = t1; }
+        }
       }
     }
   }
+#undef TC_ADVANCE
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -695,7 +708,7 @@ struct FastState {
   int64_t s_doubles_per_unit = 0;        // sum over groups of tau_size * tpp
   int wm = 8, wn = 1, nw = 8;
   int kcs_max = 1, nsb_pass_max = 1, tpp_max = 4;
-  Buf<double> Jq, keys_out, S, slot_sign;
+  Buf<double> Jq, keys_out, S, slot_sign, col_scale;
   Buf<double2> CSD;
   Buf<int> col_tt, col_l, col_lm, term_col0, nact, perm_in, perm, unit_pair, slot_tp, jcount;
   Buf<TcUnitW> uw; Buf<int2> ujp;
@@ -712,7 +725,7 @@ FastState *fast_state_create() { return new FastState(); }
 void fast_state_destroy(FastState *f)
 {
   if (!f) return;
-  f->Jq.release(); f->keys_out.release(); f->S.release(); f->slot_sign.release(); f->CSD.release();
+  f->Jq.release(); f->keys_out.release(); f->S.release(); f->slot_sign.release(); f->col_scale.release(); f->CSD.release();
   f->col_tt.release(); f->col_l.release(); f->col_lm.release(); f->term_col0.release(); f->nact.release();
   f->perm_in.release(); f->perm.release(); f->unit_pair.release(); f->slot_tp.release();
   f->uw.release(); f->ujp.release(); f->cub_tmp.release(); f->jcount.release();
@@ -851,7 +864,9 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
     if (e != cudaSuccess) return e;
     return cudaMemcpyAsync(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice, st);
   };
-  FCK(up(fs->col_tt, col_tt)); FCK(up(fs->col_l, col_l)); FCK(up(fs->col_lm, col_lm));
+  std::vector<double> col_scale(col_l.size());
+  for (size_t i = 0; i < col_l.size(); ++i) col_scale[i] = 1.0 / (16.0 * (2.0 * col_l[i] + 1.0));
+  FCK(up(fs->col_tt, col_tt)); FCK(up(fs->col_l, col_l)); FCK(up(fs->col_lm, col_lm)); FCK(up(fs->col_scale, col_scale));
   FCK(up(fs->term_col0, term_col0)); FCK(up(fs->slot_tp, slot_tp)); FCK(up(fs->slot_sign, slot_sign));
   FCK(fs->Jq.reserve((size_t)h.xx_size * fs->jq_row));
   for (int ip = 0; ip < fs->n_pass; ++ip) {
@@ -886,18 +901,17 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
 }
 
 template <int WM, int WN, int NW>
-static cudaError_t launch_tc(const TcParams &TP, int64_t n_tiles, size_t smem, cudaStream_t st)
+static cudaError_t launch_tc(const TcParams &TP, int64_t n_ctas, size_t smem, cudaStream_t st)
 {
   cudaError_t e = cudaFuncSetAttribute(los_tc_kernel<WM, WN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  los_tc_kernel<WM, WN, NW><<<(unsigned)n_tiles, TC_THREADS, smem, st>>>(TP);
+  los_tc_kernel<WM, WN, NW><<<(unsigned)n_ctas, TC_THREADS, smem, st>>>(TP);
   return cudaGetLastError();
 }
 
 int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, const int *h_unit_pair,
                  int device_sms, cudaStream_t st, song_los_timing *tm, std::string &err)
 {
-  (void)device_sms;
   if (P.cubic_J) { err = "FAST mode supports linear Bessel interpolation only; use SONG_LOS_MODE_EXACT"; return 1; }
   if (!fs->ev_ready) { for (auto &e : fs->ev) FCK(cudaEventCreate(&e)); fs->ev_ready = true; }
   if (!fs->table_ready && build_layout(fs, h, P, st, err)) return 1;
@@ -979,7 +993,7 @@ int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
   for (int i = 0; i < fs->n_blocks; ++i) TP.blk[i] = fs->blk[i];
   for (int i = 0; i < fs->n_groups; ++i) TP.grp[i] = fs->grp[i];
   for (int i = 0; i < fs->n_pass; ++i) TP.pass[i] = fs->pass[i];
-  TP.col_tt = fs->col_tt.p; TP.col_l = fs->col_l.p;
+  TP.col_tt = fs->col_tt.p; TP.col_scale = fs->col_scale.p;
   TP.Jq = fs->Jq.p; TP.jq_row = fs->jq_row; TP.nact = fs->nact.p;
   TP.k_sorted = fs->keys_out.p; TP.perm = fs->perm.p; TP.n_units = U;
   TP.tau_size = tau_size;
@@ -1007,7 +1021,7 @@ int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
   TP.b_row_bytes = fs->nsb_pass_max * fs->kcs_max * 256;
   int rmax = (MT >= 128) ? 4 : (MT >= 64 ? 3 : 2);
   if (const char *v = getenv("SONG_LOS_TC_RMAX")) rmax = std::max(1, std::min(8, atoi(v)));
-  const size_t fixed = 128 + (size_t)MT * 12 + (size_t)((tau_size + 15) & ~15) * 16;
+  const size_t fixed = 128 + (size_t)MT * 8 + (size_t)((tau_size + 15) & ~15) * 16;
   const size_t budget = 224 * 1024;
   auto stage_bytes = [&](int r) { return (size_t)TP.hdr_bytes + TP.a_bytes + (size_t)r * TP.b_row_bytes; };
   while (rmax > 1 && (budget - fixed) / stage_bytes(rmax) < 3) --rmax;
@@ -1021,13 +1035,14 @@ int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
   if (n_tiles > 0) {
     cudaError_t e = cudaErrorInvalidValue;
     const int key = fs->wm * 100 + fs->nw;
+    const int64_t n_ctas = std::min<int64_t>(n_tiles, std::max(1, device_sms));     // persistent: one CTA per SM
     switch (key) {
-      case 808:  e = launch_tc<8, 1, 8>(TP, n_tiles, smem, st); break;
-      case 810:  e = launch_tc<8, 1, 10>(TP, n_tiles, smem, st); break;
-      case 408:  e = launch_tc<4, 2, 8>(TP, n_tiles, smem, st); break;
-      case 410:  e = launch_tc<4, 2, 10>(TP, n_tiles, smem, st); break;
-      case 208:  e = launch_tc<2, 4, 8>(TP, n_tiles, smem, st); break;
-      case 210:  e = launch_tc<2, 4, 10>(TP, n_tiles, smem, st); break;
+      case 808:  e = launch_tc<8, 1, 8>(TP, n_ctas, smem, st); break;
+      case 810:  e = launch_tc<8, 1, 10>(TP, n_ctas, smem, st); break;
+      case 408:  e = launch_tc<4, 2, 8>(TP, n_ctas, smem, st); break;
+      case 410:  e = launch_tc<4, 2, 10>(TP, n_ctas, smem, st); break;
+      case 208:  e = launch_tc<2, 4, 8>(TP, n_ctas, smem, st); break;
+      case 210:  e = launch_tc<2, 4, 10>(TP, n_ctas, smem, st); break;
     }
     FCK(e);
     tm->n_launches++;
