@@ -4,7 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: under torch.distributed.run)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-A "step" is one pass of the hot path (song_los_compute: k3 spline, k3 sort, DMMA LOS kernel) over
+A "step" is one pass of the hot path (song_los_compute: k3 spline, k3 sort, source interpolation,
+DMMA LOS kernel) over
 one batch of synthetic input.  At N=1 the workload is BASELINE.json configs[1]
 (ini/intrinsic.ini + pre/sn_t_10percent_lmax2000.pre, temperature only: 8.6e7 integrals).  With N
 ranks every rank processes its own (k1,k2) shard of the same size (independent sources, no
@@ -337,11 +338,11 @@ def main():
     tfile = os.path.join(ROOT, "profiles", "traffic_bytes.json")
     if os.path.exists(tfile):
         try:
-            traffic = json.load(open(tfile)).get(args.workload, {}).get("los_fast_kernel")
+            traffic = json.load(open(tfile)).get(args.workload, {}).get("los_tc_kernel")
         except Exception:
             traffic = None
     roofline = {
-        "bound": "tensor", "kernel": "los_fast_kernel (FP64 tensor core, DMMA m8n8k4)" if mode == MODE_FAST else "los_exact_kernel",
+        "bound": "tensor", "kernel": "los_tc_kernel (FP64 tensor core, DMMA m8n8k4, TMA-fed)" if mode == MODE_FAST else "los_exact_kernel",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": "measured in this run with song_los_measure_peaks (DMMA m8n8k4 loop; MEASURED_PEAKS.json has no FP64 entry)",
         "algorithmic_flops_per_launch": flops, "n_terms": n_terms, "kernel_ms": kern["ms_integrate"],
