@@ -1,0 +1,684 @@
+/*
+ * transfer2_gpu.c -- drop-in replacement of SONG's source/transfer2.c: same exported symbols and struct
+ * semantics (reference include/transfer2.h:327-541), with the (k1,k2) loop body -- k3 interpolation of the
+ * sources, time grid, and every transfer2_compute / transfer2_integrate call (reference
+ * source/transfer2.c:401-539) -- running on B200 GPUs through the C-ABI of include/song_los.h.
+ *
+ * Compiled against SONG's OWN headers (-I<song>/include -I<song>/class.git/include); the stand-ins under
+ * song_b200/host/compat/ are used only when the CLASS fork is absent, as in this repository's tests.
+ *
+ * What stays on the host, bit-identical to the reference: the index tables (transfer2.c:866-1285), the k3
+ * integration grids (transfer2.c:1329-1737, through los_host.c, because bispectra2.c:1255 and spectra2.c:451
+ * re-derive them), memory management of ptr2->transfer (transfer2.c:636-691, 2976-3104) and the disk format
+ * (transfer2.c:705-763, 2929-2963: raw doubles, [k1][k2][k3] per transfer type).
+ *
+ * Batching: the reference handles one (k1,k2) pair at a time; here consecutive k1 levels are packed into one GPU
+ * batch (SONG_LOS_BATCH_UNITS k3 values, default 2e6) because the tensor-core kernel wants many k3 values per
+ * table row.  Side effects keep the reference's per-k1 order: sources of a k1 level are loaded before and freed
+ * after use (transfer2.c:332-344, 553), transfers are stored and freed per k1 (transfer2.c:559-567).
+ * With several visible GPUs and nothing to write to disk, batches are distributed over one host thread per GPU
+ * (static longest-processing-time schedule on the number of k3 values); the results land directly in
+ * ptr2->transfer, which is the "gather to the host".
+ *
+ * Environment: SONG_LOS_MODE=fast|exact (default fast; cubic Bessel interpolation forces exact),
+ * SONG_LOS_DEVICES=<n> (default: all visible), SONG_LOS_BATCH_UNITS=<n>.
+ */
+#include "transfer2.h"
+#include "song_los.h"
+#include "los_host.h"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------------ */
+/*  small helpers                                                                                    */
+/* ------------------------------------------------------------------------------------------------ */
+static void k3_params_of(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2,
+                         struct bessels2 *pbs2, struct transfers2 *ptr2, song_k3_params *kp)
+{
+  kp->tau0 = ptr2->tau0; kp->tau_rec = ptr2->tau_rec; kp->rs_rec = ptr2->rs_rec;
+  kp->k_first = ppt2->k[0]; kp->k_last = ppt2->k[ppt2->k_size - 1];
+  kp->k3_extrapolation = (ppr->bispectra_k3_extrapolation != no_k3_extrapolation);
+  kp->extra_k3_oscillations_left = ppr->extra_k3_oscillations_left;
+  kp->extra_k3_oscillations_right = ppr->extra_k3_oscillations_right;
+  kp->k_sampling = (ptr2->k_sampling == class_transfer2_k3_sampling) ? 1 : 0;
+  kp->q_linstep_song = ppr2->q_linstep_song;
+  kp->old_run_step = (ppr->load_run == _TRUE_) && (ppr2->old_run == _TRUE_);
+  kp->smallest_allowed_variation = ppr->smallest_allowed_variation;
+  kp->xx_max = pbs2->xx_max; kp->xx_step = pbs2->xx_step;
+}
+
+static int env_int(const char *name, int fallback)
+{
+  const char *v = getenv(name);
+  return (v && *v) ? atoi(v) : fallback;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/*  index tables (reference: transfer2.c:866-1285)                                                   */
+/* ------------------------------------------------------------------------------------------------ */
+int transfer2_get_l_list(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2,
+                         struct bessels *pbs, struct bessels2 *pbs2, struct transfers2 *ptr2)
+{
+  /* the multipoles are those of the Bessel module (transfer2.c:1081-1103) */
+  ptr2->l_size = pbs->l_size;
+  class_alloc(ptr2->l, ptr2->l_size * sizeof(int), ptr2->error_message);
+  for (int index_l = 0; index_l < ptr2->l_size; ++index_l) ptr2->l[index_l] = pbs->l[index_l];
+  return _SUCCESS_;
+}
+
+int transfer2_get_lm_lists(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2,
+                           struct bessels *pbs, struct bessels2 *pbs2, struct transfers2 *ptr2)
+{
+  /* (l,m) -> offset inside a field block (transfer2.c:1133-1166) */
+  class_alloc(ptr2->lm_array, ptr2->l_size * sizeof(int *), ptr2->error_message);
+  for (int index_l = 0; index_l < ptr2->l_size; ++index_l) {
+    int l = ptr2->l[index_l];
+    class_calloc(ptr2->lm_array[index_l], ppr2->index_m_max[l] + 1, sizeof(int), ptr2->error_message);
+    for (int index_m = 0; index_m <= ppr2->index_m_max[l]; ++index_m)
+      ptr2->lm_array[index_l][index_m] =
+          multipole2offset_indexl_indexm(l, ptr2->m[index_m], ptr2->l, ptr2->l_size, ptr2->m, ptr2->m_size);
+  }
+  /* transfer type -> (field, index_l, index_m) and labels (transfer2.c:1180-1282) */
+  class_alloc(ptr2->corresponding_index_l, ptr2->tt2_size * sizeof(int), ptr2->error_message);
+  class_alloc(ptr2->corresponding_index_m, ptr2->tt2_size * sizeof(int), ptr2->error_message);
+  class_alloc(ptr2->index_tt2_monopole, ptr2->tt2_size * sizeof(int), ptr2->error_message);
+  class_alloc(ptr2->index_pt2_monopole, ptr2->tt2_size * sizeof(int), ptr2->error_message);
+  for (int index_tt = 0; index_tt < ptr2->tt2_size; ++index_tt) {
+    int index_l = -1, index_m = -1;
+    const char *field = NULL;
+    if (ppt2->has_source_T == _TRUE_ && index_tt >= ptr2->index_tt2_T && index_tt < ptr2->index_tt2_T + ptr2->n_transfers) {
+      ptr2->index_pt2_monopole[index_tt] = ppt2->index_tp2_T; ptr2->index_tt2_monopole[index_tt] = ptr2->index_tt2_T; field = "T";
+    }
+    else if (ppt2->has_source_E == _TRUE_ && index_tt >= ptr2->index_tt2_E && index_tt < ptr2->index_tt2_E + ptr2->n_transfers) {
+      ptr2->index_pt2_monopole[index_tt] = ppt2->index_tp2_E; ptr2->index_tt2_monopole[index_tt] = ptr2->index_tt2_E; field = "E";
+    }
+    else if (ppt2->has_source_B == _TRUE_ && index_tt >= ptr2->index_tt2_B && index_tt < ptr2->index_tt2_B + ptr2->n_transfers) {
+      ptr2->index_pt2_monopole[index_tt] = ppt2->index_tp2_B; ptr2->index_tt2_monopole[index_tt] = ptr2->index_tt2_B; field = "B";
+    }
+    if (field != NULL) {
+      offset2multipole_indexl_indexm(index_tt - ptr2->index_tt2_monopole[index_tt], ptr2->l, ptr2->l_size,
+                                     ptr2->m, ptr2->m_size, &index_l, &index_m);
+      if (index_l >= 0 && index_m >= 0 && index_l < ptr2->l_size && index_m < ptr2->m_size)
+        sprintf(ptr2->tt2_labels[index_tt], "%s_%d_%d", field, ptr2->l[index_l], ptr2->m[index_m]);
+    }
+    class_test((index_l >= ptr2->l_size) || (index_m >= ptr2->m_size) || (index_l < 0) || (index_m < 0),
+               ptr2->error_message,
+               "index_tt=%d: result (index_l,index_m)=(%d,%d) is out of bounds index_l=[%d,%d], index_m=[%d,%d]\n",
+               index_tt, index_l, index_m, 0, ptr2->l_size - 1, 0, ptr2->m_size - 1);
+    ptr2->corresponding_index_l[index_tt] = index_l;
+    ptr2->corresponding_index_m[index_tt] = index_m;
+  }
+  return _SUCCESS_;
+}
+
+/* fine k3 grid of one pair: size (transfer2.c:1329-1551) and values (transfer2.c:1566-1737) */
+int transfer2_get_k3_size(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2,
+                          struct bessels *pbs, struct bessels2 *pbs2, struct transfers2 *ptr2,
+                          int index_k1, int index_k2)
+{
+  song_k3_params kp; song_k3_range r;
+  k3_params_of(ppr, ppr2, ppt2, pbs2, ptr2, &kp);
+  class_test(song_host_k3_size(&kp, ppt2->k3[index_k1][index_k2], ppt2->k3_size[index_k1][index_k2], &r,
+                               ptr2->error_message, _ERRORMSGSIZE_) != 0,
+             ptr2->error_message, "k3 grid of (index_k1,index_k2)=(%d,%d): %.1000s", index_k1, index_k2, ptr2->error_message);
+  ptr2->k_min_k1k2[index_k1][index_k2] = r.k_min;
+  ptr2->k_max_k1k2[index_k1][index_k2] = r.k_max;
+  ptr2->k_size_k1k2[index_k1][index_k2] = r.k_size;
+  ptr2->k_physical_start_k1k2[index_k1][index_k2] = r.k_physical_start;
+  ptr2->k_physical_size_k1k2[index_k1][index_k2] = r.k_physical_size;
+  return _SUCCESS_;
+}
+
+int transfer2_get_k3_list(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2,
+                          struct bessels *pbs, struct bessels2 *pbs2, struct transfers2 *ptr2,
+                          int index_k1, int index_k2, double *k3, int *last_used_index_pt)
+{
+  song_k3_params kp; song_k3_range r;
+  k3_params_of(ppr, ppr2, ppt2, pbs2, ptr2, &kp);
+  r.k_min = ptr2->k_min_k1k2[index_k1][index_k2];
+  r.k_max = ptr2->k_max_k1k2[index_k1][index_k2];
+  r.k_size = ptr2->k_size_k1k2[index_k1][index_k2];
+  r.k_physical_start = ptr2->k_physical_start_k1k2[index_k1][index_k2];
+  r.k_physical_size = ptr2->k_physical_size_k1k2[index_k1][index_k2];
+  int last = 0;
+  class_test(song_host_k3_list(&kp, ppt2->k3[index_k1][index_k2], ppt2->k3_size[index_k1][index_k2], &r, k3, &last,
+                               ptr2->error_message, _ERRORMSGSIZE_) != 0,
+             ptr2->error_message, "k3 list of (index_k1,index_k2)=(%d,%d): %.1000s", index_k1, index_k2, ptr2->error_message);
+  if (last_used_index_pt != NULL) *last_used_index_pt = last;
+  return _SUCCESS_;
+}
+
+int transfer2_get_k3_sizes(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2,
+                           struct bessels *pbs, struct bessels2 *pbs2, struct transfers *ptr, struct transfers2 *ptr2)
+{
+  /* transfer2.c:1752-1834 */
+  int k1_size = ppt2->k_size;
+  class_alloc(ptr2->k_size_k1k2, k1_size * sizeof(int *), ptr2->error_message);
+  class_alloc(ptr2->k_physical_start_k1k2, k1_size * sizeof(int *), ptr2->error_message);
+  class_alloc(ptr2->k_physical_size_k1k2, k1_size * sizeof(int *), ptr2->error_message);
+  class_alloc(ptr2->k_min_k1k2, k1_size * sizeof(double *), ptr2->error_message);
+  class_alloc(ptr2->k_max_k1k2, k1_size * sizeof(double *), ptr2->error_message);
+  ptr2->k3_size_max = 0;
+  for (int index_k1 = 0; index_k1 < k1_size; ++index_k1) {
+    int k2_size = index_k1 + 1;
+    class_alloc(ptr2->k_size_k1k2[index_k1], k2_size * sizeof(int), ptr2->error_message);
+    class_alloc(ptr2->k_physical_start_k1k2[index_k1], k2_size * sizeof(int), ptr2->error_message);
+    class_alloc(ptr2->k_physical_size_k1k2[index_k1], k2_size * sizeof(int), ptr2->error_message);
+    class_alloc(ptr2->k_min_k1k2[index_k1], k2_size * sizeof(double), ptr2->error_message);
+    class_alloc(ptr2->k_max_k1k2[index_k1], k2_size * sizeof(double), ptr2->error_message);
+    for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) {
+      /* cubic interpolation needs at least 4 source points (transfer2.c:1766-1771) */
+      class_test((ppr2->sources_k3_interpolation == cubic_interpolation) && (ppt2->k3_size[index_k1][index_k2] < 4),
+                 ptr2->error_message,
+                 "index_k1=%d, index_k2=%d: cannot do cubic interpolation in k3 with just k3_size=%d values. Increase k3_size.",
+                 index_k1, index_k2, ppt2->k3_size[index_k1][index_k2]);
+      class_call(transfer2_get_k3_size(ppr, ppr2, ppt2, pbs, pbs2, ptr2, index_k1, index_k2),
+                 ptr2->error_message, ptr2->error_message);
+      ptr2->k3_size_max = MAX(ptr2->k3_size_max, ptr2->k_size_k1k2[index_k1][index_k2]);
+    }
+  }
+  return _SUCCESS_;
+}
+
+int transfer2_indices_of_transfers(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2,
+                                   struct bessels *pbs, struct bessels2 *pbs2, struct transfers *ptr, struct transfers2 *ptr2)
+{
+  class_call(transfer2_get_l_list(ppr, ppr2, ppt2, pbs, pbs2, ptr2), ptr2->error_message, ptr2->error_message);
+  ptr2->m_size = ppr2->m_size;
+  class_alloc(ptr2->m, ptr2->m_size * sizeof(int), ptr2->error_message);
+  for (int index_m = 0; index_m < ptr2->m_size; ++index_m) ptr2->m[index_m] = ppr2->m[index_m];
+
+  ptr2->n_transfers = size_indexl_indexm(ptr2->l, ptr2->l_size, ppr2->m, ppr2->m_size);
+  ptr2->n_nonzero_transfers_E = ptr2->n_transfers;                     /* transfer2.c:903-915 (debug only) */
+  if (ppr2->compute_m[0]) ptr2->n_nonzero_transfers_E -= 2;
+  if (ppr2->compute_m[1]) ptr2->n_nonzero_transfers_E -= 1;
+  ptr2->n_nonzero_transfers_B = ptr2->n_transfers;
+  if (ppr2->compute_m[0]) ptr2->n_nonzero_transfers_B -= ptr2->l_size;
+  if (ppr2->compute_m[1]) ptr2->n_nonzero_transfers_B -= 1;
+
+  int index_tt = 0;                                                   /* T block, then E, then B (:917-940) */
+  if (ppt2->has_source_T) { ptr2->index_tt2_T = index_tt; index_tt += ptr2->n_transfers; }
+  if (ppt2->has_source_E) { ptr2->index_tt2_E = index_tt; index_tt += ptr2->n_transfers; }
+  if (ppt2->has_source_B) { ptr2->index_tt2_B = index_tt; index_tt += ptr2->n_transfers; }
+  ptr2->tt2_size = index_tt;
+  class_calloc(ptr2->tt2_labels, ptr2->tt2_size * _MAX_LENGTH_LABEL_, sizeof(char), ptr2->error_message);
+  if (ptr2->transfer2_verbose > 1)
+    printf(" -> will compute tt2_size=%d transfer functions (%d per field)\n", ptr2->tt2_size, ptr2->n_transfers);
+
+  class_call(transfer2_get_lm_lists(ppr, ppr2, ppt2, pbs, pbs2, ptr2), ptr2->error_message, ptr2->error_message);
+  class_call(transfer2_get_k3_sizes(ppr, ppr2, ppt2, pbs, pbs2, ptr, ptr2), ptr2->error_message, ptr2->error_message);
+
+  ptr2->count_memorised_transfers = 0;
+  ptr2->count_allocated_transfers = 0;
+  class_alloc(ptr2->transfer, ptr2->tt2_size * sizeof(double ***), ptr2->error_message);
+  for (int itt = 0; itt < ptr2->tt2_size; ++itt)
+    class_alloc(ptr2->transfer[itt], ppt2->k_size * sizeof(double **), ptr2->error_message);
+  class_calloc(ptr2->has_allocated_transfers, ppt2->k_size, sizeof(short), ptr2->error_message);
+
+  if ((ppr2->store_transfers_to_disk == _TRUE_) || (ppr2->load_transfers_from_disk == _TRUE_)) {   /* :1043-1062 */
+    class_alloc(ptr2->transfers_files, ptr2->tt2_size * sizeof(FILE *), ptr2->error_message);
+    class_alloc(ptr2->transfers_paths, ptr2->tt2_size * sizeof(char *), ptr2->error_message);
+    for (int itt = 0; itt < ptr2->tt2_size; ++itt) {
+      class_alloc(ptr2->transfers_paths[itt], _FILENAMESIZE_ * sizeof(char), ptr2->error_message);
+      snprintf(ptr2->transfers_paths[itt], _FILENAMESIZE_, "%s/transfers_%03d.dat", ptr2->transfers_dir, itt);
+      if (ppr2->store_transfers_to_disk == _TRUE_)
+        class_open(ptr2->transfers_files[itt], ptr2->transfers_paths[itt], "wb", ptr2->error_message);
+    }
+  }
+  return _SUCCESS_;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/*  memory management and disk format of ptr2->transfer                                              */
+/* ------------------------------------------------------------------------------------------------ */
+int transfer2_allocate_k1_level(struct perturbs2 *ppt2, struct transfers2 *ptr2, int index_k1)
+{
+  class_test(ptr2->has_allocated_transfers[index_k1] == _TRUE_, ptr2->error_message,
+             "the index_k1=%d level of ptr2->transfers is already allocated, stop to prevent error", index_k1);
+  long int count = 0;
+  for (int index_tt = 0; index_tt < ptr2->tt2_size; ++index_tt) {
+    class_alloc(ptr2->transfer[index_tt][index_k1], (index_k1 + 1) * sizeof(double *), ptr2->error_message);
+    for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) {
+      class_alloc(ptr2->transfer[index_tt][index_k1][index_k2],
+                  ptr2->k_size_k1k2[index_k1][index_k2] * sizeof(double), ptr2->error_message);
+      count += ptr2->k_size_k1k2[index_k1][index_k2];
+    }
+  }
+  #pragma omp atomic
+  ptr2->count_allocated_transfers += count;
+  ptr2->has_allocated_transfers[index_k1] = _TRUE_;
+  return _SUCCESS_;
+}
+
+int transfer2_free_k1_level(struct perturbs2 *ppt2, struct transfers2 *ptr2, int index_k1)
+{
+  class_test(ptr2->has_allocated_transfers[index_k1] == _FALSE_, ptr2->error_message,
+             "the index_k1=%d level of ptr2->transfers is already free, stop to prevent error", index_k1);
+  for (int index_tt = 0; index_tt < ptr2->tt2_size; ++index_tt) {
+    for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) free(ptr2->transfer[index_tt][index_k1][index_k2]);
+    free(ptr2->transfer[index_tt][index_k1]);
+  }
+  ptr2->has_allocated_transfers[index_k1] = _FALSE_;
+  return _SUCCESS_;
+}
+
+int transfer2_allocate_type_level(struct perturbs2 *ppt2, struct transfers2 *ptr2, int index_tt)
+{
+  int k1_size = ppt2->k_size;
+  class_alloc(ptr2->transfer[index_tt], k1_size * sizeof(double **), ptr2->error_message);
+  for (int index_k1 = 0; index_k1 < k1_size; ++index_k1) {
+    class_alloc(ptr2->transfer[index_tt][index_k1], (index_k1 + 1) * sizeof(double *), ptr2->error_message);
+    for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) {
+      class_alloc(ptr2->transfer[index_tt][index_k1][index_k2],
+                  ptr2->k_size_k1k2[index_k1][index_k2] * sizeof(double), ptr2->error_message);
+      #pragma omp atomic
+      ptr2->count_allocated_transfers += ptr2->k_size_k1k2[index_k1][index_k2];
+    }
+  }
+  return _SUCCESS_;
+}
+
+int transfer2_free_type_level(struct perturbs2 *ppt2, struct transfers2 *ptr2, int index_tt)
+{
+  for (int index_k1 = 0; index_k1 < ppt2->k_size; ++index_k1) {
+    for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) free(ptr2->transfer[index_tt][index_k1][index_k2]);
+    free(ptr2->transfer[index_tt][index_k1]);
+  }
+  free(ptr2->transfer[index_tt]);
+  return _SUCCESS_;
+}
+
+int transfer2_store_transfers_to_disk(struct perturbs2 *ppt2, struct transfers2 *ptr2, int index_k1)
+{
+  /* one file per transfer type, appended per k1 in [k2][k3] order (transfer2.c:2940-2957) */
+  for (int index_tt = 0; index_tt < ptr2->tt2_size; ++index_tt)
+    for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) {
+      size_t n = (size_t)ptr2->k_size_k1k2[index_k1][index_k2];
+      class_test(fwrite(ptr2->transfer[index_tt][index_k1][index_k2], sizeof(double), n, ptr2->transfers_files[index_tt]) != n,
+                 ptr2->error_message, "could not write to '%s'", ptr2->transfers_paths[index_tt]);
+    }
+  return _SUCCESS_;
+}
+
+int transfer2_load_transfers_from_disk(struct perturbs2 *ppt2, struct transfers2 *ptr2, int index_tt)
+{
+  class_call(transfer2_allocate_type_level(ppt2, ptr2, index_tt), ptr2->error_message, ptr2->error_message);
+  class_open(ptr2->transfers_files[index_tt], ptr2->transfers_paths[index_tt], "rb", ptr2->error_message);
+  for (int index_k1 = 0; index_k1 < ppt2->k_size; ++index_k1)
+    for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) {
+      int n_to_read = ptr2->k_size_k1k2[index_k1][index_k2];
+      int n_read = (int)fread(ptr2->transfer[index_tt][index_k1][index_k2], sizeof(double), n_to_read,
+                              ptr2->transfers_files[index_tt]);
+      class_test(n_read != n_to_read, ptr2->error_message,
+                 "Could not read in '%s' file, read %d entries but expected %d (index_tt=%d,index_k1=%d,index_k2=%d)",
+                 ptr2->transfers_paths[index_tt], n_read, n_to_read, index_tt, index_k1, index_k2);
+      #pragma omp atomic
+      ptr2->count_memorised_transfers += n_to_read;
+    }
+  fclose(ptr2->transfers_files[index_tt]);
+  return _SUCCESS_;
+}
+
+int transfer2_free(struct precision2 *ppr2, struct perturbs2 *ppt2, struct transfers2 *ptr2)
+{
+  if (ptr2->has_cls == _TRUE_) {
+    free(ptr2->tt2_labels);
+    if ((ppr2->store_transfers_to_disk == _FALSE_) && (ppr2->load_transfers_from_disk == _FALSE_)) {
+      for (int index_k1 = 0; index_k1 < ppt2->k_size; ++index_k1)
+        if (ptr2->has_allocated_transfers[index_k1] == _TRUE_)
+          class_call(transfer2_free_k1_level(ppt2, ptr2, index_k1), ptr2->error_message, ptr2->error_message);
+      for (int index_tt = 0; index_tt < ptr2->tt2_size; ++index_tt) free(ptr2->transfer[index_tt]);
+    }
+    free(ptr2->transfer);
+    free(ptr2->has_allocated_transfers);
+    for (int index_k1 = 0; index_k1 < ppt2->k_size; ++index_k1) {
+      free(ptr2->k_size_k1k2[index_k1]); free(ptr2->k_physical_start_k1k2[index_k1]);
+      free(ptr2->k_physical_size_k1k2[index_k1]); free(ptr2->k_min_k1k2[index_k1]); free(ptr2->k_max_k1k2[index_k1]);
+    }
+    free(ptr2->k_size_k1k2); free(ptr2->k_physical_start_k1k2); free(ptr2->k_physical_size_k1k2);
+    free(ptr2->k_min_k1k2); free(ptr2->k_max_k1k2);
+    free(ptr2->l); free(ptr2->m);
+    free(ptr2->corresponding_index_l); free(ptr2->corresponding_index_m);
+    free(ptr2->index_tt2_monopole); free(ptr2->index_pt2_monopole);
+    for (int index_l = 0; index_l < ptr2->l_size; ++index_l) free(ptr2->lm_array[index_l]);
+    free(ptr2->lm_array);
+    if ((ppr2->store_transfers_to_disk == _TRUE_) || (ppr2->load_transfers_from_disk == _TRUE_)) {
+      for (int index_tt = 0; index_tt < ptr2->tt2_size; ++index_tt) free(ptr2->transfers_paths[index_tt]);
+      free(ptr2->transfers_files); free(ptr2->transfers_paths);
+    }
+  }
+  return _SUCCESS_;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/*  the per-element functions of the reference run inside the GPU kernels                            */
+/* ------------------------------------------------------------------------------------------------ */
+#define ON_DEVICE(name) class_stop(ptr2->error_message, \
+  "%s is evaluated inside the CUDA kernels of this build (include/song_los.h); it is not available as a host call", name)
+
+int transfer2_interpolate_sources_in_k(struct precision *ppr, struct precision2 *ppr2, struct perturbs *ppt,
+      struct perturbs2 *ppt2, struct bessels *pbs, struct bessels2 *pbs2, struct transfers2 *ptr2, int index_k1,
+      int index_k2, int index_tp, double *k_grid, double *splines, double *interpolated_sources)
+{ ON_DEVICE("transfer2_interpolate_sources_in_k"); }
+int transfer2_get_time_grid(struct precision *ppr, struct precision2 *ppr2, struct perturbs *ppt, struct perturbs2 *ppt2,
+      struct bessels *pbs, struct bessels2 *pbs2, struct transfers2 *ptr2, int index_k1, int index_k2, int index_k,
+      struct transfer2_workspace *pw)
+{ ON_DEVICE("transfer2_get_time_grid"); }
+int transfer2_interpolate_sources_in_time(struct precision *ppr, struct precision2 *ppr2, struct perturbs *ppt,
+      struct perturbs2 *ppt2, struct bessels *pbs, struct bessels2 *pbs2, struct transfers2 *ptr2, int index_tp2,
+      double *interpolated_sources_in_k, double *sources_time_spline, double *interpolated_sources_in_time,
+      struct transfer2_workspace *pw)
+{ ON_DEVICE("transfer2_interpolate_sources_in_time"); }
+int transfer2_compute(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2, struct bessels *pbs,
+      struct bessels2 *pbs2, struct transfers2 *ptr2, int index_k1, int index_k2, int index_k, int index_l, int index_m,
+      int index_tt, double **interpolated_sources_in_time, struct transfer2_workspace *pw)
+{ ON_DEVICE("transfer2_compute"); }
+int transfer2_integrate(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2, struct bessels *pbs,
+      struct bessels2 *pbs2, struct transfers2 *ptr2, int index_k1, int index_k2, int index_k, int index_l, int index_m,
+      double **interpolated_sources_in_time, int index_J, int index_source_monopole, struct transfer2_workspace *pw,
+      double *integral)
+{ ON_DEVICE("transfer2_integrate"); }
+
+/* ------------------------------------------------------------------------------------------------ */
+/*  engine set-up from the SONG structures                                                           */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  song_los_ctx *ctx;
+  int device;
+} los_device;
+
+static int create_engine(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2, struct bessels2 *pbs2,
+                         struct transfers2 *ptr2, int device, song_los_ctx **out)
+{
+  song_los_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.device = device;
+  cfg.tau0 = ptr2->tau0;
+  cfg.tau_size = ppt2->tau_size; cfg.tau_sampling = ppt2->tau_sampling;
+  cfg.tau_sampling_mode = (ptr2->tau_sampling == sources_tau_sampling) ? SONG_LOS_TAU_SOURCES
+                        : (ptr2->tau_sampling == bessel_tau_sampling) ? SONG_LOS_TAU_BESSEL : SONG_LOS_TAU_CUSTOM;
+  cfg.tau_linstep_song = ppr2->tau_linstep_song;
+  cfg.sources_k3_interpolation = (ppr2->sources_k3_interpolation == cubic_interpolation) ? SONG_LOS_INTERP_CUBIC : SONG_LOS_INTERP_LINEAR;
+  cfg.sources_time_interpolation = (ppr2->sources_time_interpolation == cubic_interpolation) ? SONG_LOS_INTERP_CUBIC : SONG_LOS_INTERP_LINEAR;
+  cfg.bessels_interpolation = (ppr->bessels_interpolation == cubic_interpolation) ? SONG_LOS_INTERP_CUBIC : SONG_LOS_INTERP_LINEAR;
+  cfg.k3_extrapolation = (ppr->bispectra_k3_extrapolation == no_k3_extrapolation) ? SONG_LOS_NO_K3_EXTRAPOLATION : SONG_LOS_FLAT_K3_EXTRAPOLATION;
+  cfg.xx_size = pbs2->xx_size; cfg.xx = pbs2->xx; cfg.xx_step = pbs2->xx_step;
+  cfg.l_size = ptr2->l_size; cfg.l = ptr2->l;
+  cfg.m_size = ptr2->m_size; cfg.m = ptr2->m;
+  cfg.L_size = pbs2->L_size;
+  cfg.n_transfers = ptr2->n_transfers;
+
+  /* lm_array as [l_size][m_size] and lm(L,m) of the sources as [L_size][m_size], -1 where not defined */
+  int *lm_array, *lm_src;
+  class_alloc(lm_array, (size_t)ptr2->l_size * ptr2->m_size * sizeof(int), ptr2->error_message);
+  class_alloc(lm_src, (size_t)pbs2->L_size * ptr2->m_size * sizeof(int), ptr2->error_message);
+  for (int index_l = 0; index_l < ptr2->l_size; ++index_l)
+    for (int index_m = 0; index_m < ptr2->m_size; ++index_m)
+      lm_array[index_l * ptr2->m_size + index_m] =
+          (index_m <= ppr2->index_m_max[ptr2->l[index_l]]) ? ptr2->lm_array[index_l][index_m] : -1;
+  for (int L = 0; L < pbs2->L_size; ++L)
+    for (int index_m = 0; index_m < ptr2->m_size; ++index_m)
+      lm_src[L * ptr2->m_size + index_m] = (ptr2->m[index_m] <= L) ? ppt2->lm_array[L][index_m] : -1;   /* lm(L,m), perturbations2_macros.h:53 */
+  cfg.lm_array = lm_array; cfg.lm_src = lm_src;
+
+  cfg.has_source_T = ppt2->has_source_T; cfg.has_source_E = ppt2->has_source_E; cfg.has_source_B = ppt2->has_source_B;
+  cfg.index_tp2_T = ppt2->index_tp2_T; cfg.index_tp2_E = ppt2->index_tp2_E; cfg.index_tp2_B = ppt2->index_tp2_B;
+  cfg.tp2_size = ppt2->tp2_size;
+  cfg.l_max_los_t = ppr2->l_max_los_t; cfg.l_max_los_p = ppr2->l_max_los_p;
+  cfg.index_tt2_T = ptr2->index_tt2_T; cfg.index_tt2_E = ptr2->index_tt2_E; cfg.index_tt2_B = ptr2->index_tt2_B;
+  cfg.tt2_size = ptr2->tt2_size;
+  cfg.tt_index_l = ptr2->corresponding_index_l; cfg.tt_index_m = ptr2->corresponding_index_m;
+  cfg.J_size = pbs2->J_size;
+  cfg.index_J_TT = pbs2->has_J_TT ? pbs2->index_J_TT : -1;
+  cfg.index_J_EE = pbs2->has_J_EE ? pbs2->index_J_EE : -1;
+  cfg.index_J_EB = pbs2->has_J_EB ? pbs2->index_J_EB : -1;
+
+  int rc = song_los_create(&cfg, out);
+  free(lm_array); free(lm_src);
+  class_test(rc != SONG_LOS_SUCCESS, ptr2->error_message, "%.1500s", song_los_last_error(NULL));
+
+  /* projection functions of bessel2_init: ragged [J][L][l][m] rows -> flat list (bessel2.h:64-91) */
+  size_t n_j = (size_t)pbs2->J_size * pbs2->L_size * ptr2->l_size * ptr2->m_size;
+  const double **rows, **ddrows; int *xmin, *xsize;
+  class_calloc(rows, n_j, sizeof(double *), ptr2->error_message);
+  class_calloc(ddrows, n_j, sizeof(double *), ptr2->error_message);
+  class_calloc(xmin, n_j, sizeof(int), ptr2->error_message);
+  class_calloc(xsize, n_j, sizeof(int), ptr2->error_message);
+  int cubic_J = (ppr->bessels_interpolation == cubic_interpolation);
+  for (int J = 0; J < pbs2->J_size; ++J)
+    for (int L = 0; L < pbs2->L_size; ++L)
+      for (int index_l = 0; index_l < ptr2->l_size; ++index_l)
+        for (int index_m = 0; index_m < ptr2->m_size; ++index_m) {
+          if (ptr2->m[index_m] > MIN(pbs2->L[L], ptr2->l[index_l])) continue;       /* not allocated by bessel2_init */
+          size_t q = (((size_t)J * pbs2->L_size + L) * ptr2->l_size + index_l) * ptr2->m_size + index_m;
+          rows[q] = pbs2->J_Llm_x[J][L][index_l][index_m];
+          if (cubic_J) ddrows[q] = pbs2->ddJ_Llm_x[J][L][index_l][index_m];
+          xmin[q] = pbs2->index_xmin_J[J][L][index_l][index_m];
+          xsize[q] = pbs2->x_size_J[J][L][index_l][index_m];
+        }
+  rc = song_los_set_projection(*out, rows, cubic_J ? ddrows : NULL, xmin, xsize);
+  free(rows); free(ddrows); free(xmin); free(xsize);
+  if (rc != SONG_LOS_SUCCESS) {
+    snprintf(ptr2->error_message, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(*out));
+    song_los_destroy(*out); *out = NULL;
+    return _FAILURE_;
+  }
+  return _SUCCESS_;
+}
+
+/* one GPU batch = the k1 levels [k1_first, k1_last] */
+typedef struct { int k1_first, k1_last; long n_units; int device; } los_k1_batch;
+
+static int run_batch(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2, struct bessels *pbs,
+                     struct bessels2 *pbs2, struct transfers2 *ptr2, song_los_ctx *ctx, int mode, const los_k1_batch *kb,
+                     char *errmsg)
+{
+  const int tp2 = ppt2->tp2_size, ntau = ppt2->tau_size;
+  int n_pairs = 0;
+  int64_t n_pt = 0, n_units = 0, n_src = 0;
+  for (int k1 = kb->k1_first; k1 <= kb->k1_last; ++k1)
+    for (int k2 = 0; k2 <= k1; ++k2) {
+      ++n_pairs; n_pt += ppt2->k3_size[k1][k2]; n_units += ptr2->k_size_k1k2[k1][k2];
+      n_src += (int64_t)tp2 * ntau * ppt2->k3_size[k1][k2];
+    }
+  int *np = malloc(sizeof(int) * n_pairs), *nt = malloc(sizeof(int) * n_pairs);
+  int *ps = malloc(sizeof(int) * n_pairs), *pz = malloc(sizeof(int) * n_pairs);
+  int64_t *pt_off = malloc(sizeof(int64_t) * n_pairs), *tr_off = malloc(sizeof(int64_t) * n_pairs), *src_off = malloc(sizeof(int64_t) * n_pairs);
+  double *k3_pt = malloc(sizeof(double) * (size_t)n_pt), *k3_tr = malloc(sizeof(double) * (size_t)n_units);
+  double *src = malloc(sizeof(double) * (size_t)n_src), *out = malloc(sizeof(double) * (size_t)n_units * ptr2->tt2_size);
+  int failed = 0;
+  if (!np || !nt || !ps || !pz || !pt_off || !tr_off || !src_off || !k3_pt || !k3_tr || !src || !out) {
+    snprintf(errmsg, _ERRORMSGSIZE_, "could not allocate the staging buffers of a GPU batch (%ld k3 values)", (long)n_units);
+    failed = 1;
+  }
+  int p = 0;
+  int64_t o_pt = 0, o_tr = 0, o_src = 0;
+  for (int k1 = kb->k1_first; !failed && k1 <= kb->k1_last; ++k1)
+    for (int k2 = 0; !failed && k2 <= k1; ++k2, ++p) {
+      np[p] = ppt2->k3_size[k1][k2]; nt[p] = ptr2->k_size_k1k2[k1][k2];
+      ps[p] = ptr2->k_physical_start_k1k2[k1][k2]; pz[p] = ptr2->k_physical_size_k1k2[k1][k2];
+      pt_off[p] = o_pt; tr_off[p] = o_tr; src_off[p] = o_src;
+      memcpy(k3_pt + o_pt, ppt2->k3[k1][k2], sizeof(double) * np[p]);
+      if (transfer2_get_k3_list(ppr, ppr2, ppt2, pbs, pbs2, ptr2, k1, k2, k3_tr + o_tr, NULL) == _FAILURE_) {
+        snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); failed = 1; break;
+      }
+      /* ppt2->sources[tp][k1][k2][tau*k3_size + k3] (transfer2.h:47-51) -> packed [pair][tp][tau][k3] */
+      for (int tp = 0; tp < tp2; ++tp)
+        memcpy(src + o_src + (int64_t)tp * ntau * np[p], ppt2->sources[tp][k1][k2], sizeof(double) * (size_t)ntau * np[p]);
+      o_pt += np[p]; o_tr += nt[p]; o_src += (int64_t)tp2 * ntau * np[p];
+    }
+  if (!failed) {
+    song_los_batch b;
+    memset(&b, 0, sizeof b);
+    b.n_pairs = n_pairs; b.k3_pt_size = np; b.k3_tr_size = nt; b.phys_start = ps; b.phys_size = pz;
+    b.pt_off = pt_off; b.tr_off = tr_off; b.src_off = src_off;
+    b.n_pt_total = n_pt; b.n_units = n_units; b.n_src_total = n_src;
+    b.k3_pt = k3_pt; b.k3_tr = k3_tr; b.src = src;
+    if (song_los_transfer_pairs(ctx, &b, mode, out, NULL) != SONG_LOS_SUCCESS) {
+      snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(ctx)); failed = 1;
+    }
+  }
+  if (!failed) {
+    /* out is [tt2_size][n_units]: scatter the rows into ptr2->transfer[tt][k1][k2][k3] (transfer2.c:2107) */
+    p = 0;
+    long stored = 0;
+    for (int k1 = kb->k1_first; k1 <= kb->k1_last; ++k1)
+      for (int k2 = 0; k2 <= k1; ++k2, ++p)
+        for (int tt = 0; tt < ptr2->tt2_size; ++tt) {
+          memcpy(ptr2->transfer[tt][k1][k2], out + (int64_t)tt * n_units + tr_off[p], sizeof(double) * nt[p]);
+          stored += nt[p];
+        }
+    #pragma omp atomic
+    ptr2->count_memorised_transfers += stored;                                    /* transfer2.c:2110-2111 */
+  }
+  free(np); free(nt); free(ps); free(pz); free(pt_off); free(tr_off); free(src_off);
+  free(k3_pt); free(k3_tr); free(src); free(out);
+  return failed ? _FAILURE_ : _SUCCESS_;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/*  transfer2_init (reference: transfer2.c:79-621)                                                   */
+/* ------------------------------------------------------------------------------------------------ */
+int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct background *pba, struct thermo *pth,
+                   struct perturbs *ppt, struct perturbs2 *ppt2, struct bessels *pbs, struct bessels2 *pbs2,
+                   struct transfers *ptr, struct transfers2 *ptr2)
+{
+  if (!ppt2->has_perturbations2 ||
+      (!ppt2->has_cmb_spectra && !ppt2->has_cmb_bispectra && !ptr2->stop_at_transfers2)) {   /* :99-110 */
+    ptr2->has_cls = _FALSE_;
+    if (ptr2->transfer2_verbose > 0) printf("Second-order transfer module skipped.\n");
+    return _SUCCESS_;
+  }
+  ptr2->has_cls = _TRUE_;
+  if (ptr2->transfer2_verbose > 0) printf("Computing second-order transfer functions (B200 line-of-sight engine)\n");
+  if ((ppt2->k_size < 4) && (ptr2->stop_at_transfers2 == _FALSE_))
+    printf("# WARNING: cannot do cubic interpolation in k1 with less than 4 values. "
+           "Increase k_size, or do not trust results for 1st-order transfer functions.\n");
+
+  ptr2->tau0 = pba->conformal_age;                                                            /* :128-130 */
+  ptr2->tau_rec = pth->tau_rec;
+  ptr2->rs_rec = pth->rs_rec;
+
+  class_call(transfer2_indices_of_transfers(ppr, ppr2, ppt2, pbs, pbs2, ptr, ptr2), ptr2->error_message, ptr2->error_message);
+
+  if (ppr2->load_transfers_from_disk == _TRUE_) {                                             /* :151-157 */
+    if (ptr2->transfer2_verbose > 0) printf(" -> leaving transfer2 module; transfer functions will be read from disk\n");
+    return _SUCCESS_;
+  }
+
+  /* arithmetic mode */
+  int mode = SONG_LOS_MODE_FAST;
+  const char *mode_env = getenv("SONG_LOS_MODE");
+  if ((mode_env && strcmp(mode_env, "exact") == 0) || (ppr->bessels_interpolation == cubic_interpolation))
+    mode = SONG_LOS_MODE_EXACT;
+
+  /* k1 batches */
+  const long batch_units = (long)env_int("SONG_LOS_BATCH_UNITS", 2000000);
+  los_k1_batch *batches;
+  class_alloc(batches, ppt2->k_size * sizeof(los_k1_batch), ptr2->error_message);
+  int n_batches = 0;
+  for (int k1 = 0; k1 < ppt2->k_size;) {
+    los_k1_batch kb = {k1, k1, 0, 0};
+    for (; k1 < ppt2->k_size; ++k1) {
+      long level = 0;
+      for (int k2 = 0; k2 <= k1; ++k2) level += ptr2->k_size_k1k2[k1][k2];
+      if (kb.n_units > 0 && kb.n_units + level > batch_units) break;
+      kb.n_units += level; kb.k1_last = k1;
+    }
+    batches[n_batches++] = kb;
+  }
+
+  /* devices: one host thread per GPU when nothing has to be written in k1 order */
+  const int sources_on_disk = (ppr2->load_sources_from_disk == _TRUE_) || (ppr2->store_sources_to_disk == _TRUE_);
+  const int ordered = sources_on_disk || (ppr2->store_transfers_to_disk == _TRUE_);
+  int n_dev = env_int("SONG_LOS_DEVICES", 0);
+  if (n_dev <= 0) {
+    /* probe: engines are created on devices 0,1,... until creation fails */
+    n_dev = 64;
+  }
+  if (ordered) n_dev = 1;
+  if (n_dev > n_batches) n_dev = n_batches > 0 ? n_batches : 1;
+  los_device *dev;
+  class_calloc(dev, n_dev, sizeof(los_device), ptr2->error_message);
+  int n_created = 0;
+  for (int d = 0; d < n_dev; ++d) {
+    if (create_engine(ppr, ppr2, ppt2, pbs2, ptr2, d, &dev[d].ctx) == _FAILURE_) {
+      if (d == 0) { free(dev); free(batches); return _FAILURE_; }   /* no usable GPU: there is no CPU fallback */
+      break;
+    }
+    dev[d].device = d; ++n_created;
+  }
+  n_dev = n_created;
+  if (ptr2->transfer2_verbose > 0)
+    printf(" -> %d k1 batches on %d GPU(s), %s arithmetic\n", n_batches, n_dev, mode == SONG_LOS_MODE_FAST ? "tensor-core" : "reference-order");
+
+  /* static longest-processing-time schedule: batches by decreasing size to the least loaded device */
+  {
+    long *load = calloc(n_dev, sizeof(long));
+    int *order = malloc(n_batches * sizeof(int));
+    for (int i = 0; i < n_batches; ++i) order[i] = i;
+    for (int i = 1; i < n_batches; ++i)
+      for (int j = i; j > 0 && batches[order[j]].n_units > batches[order[j - 1]].n_units; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+    for (int i = 0; i < n_batches; ++i) {
+      int best = 0;
+      for (int d = 1; d < n_dev; ++d) if (load[d] < load[best]) best = d;
+      batches[order[i]].device = best; load[best] += batches[order[i]].n_units;
+    }
+    free(load); free(order);
+  }
+
+  int abort_flag = _FALSE_;
+  ErrorMsg first_error = "";
+  #pragma omp parallel for num_threads(n_dev) schedule(static, 1) if (n_dev > 1)
+  for (int d = 0; d < n_dev; ++d) {
+    ErrorMsg local = "";
+    for (int ib = 0; ib < n_batches; ++ib) {
+      if (batches[ib].device != d) continue;
+      if (abort_flag == _TRUE_) break;
+      const los_k1_batch *kb = &batches[ib];
+      int ok = _TRUE_;
+      for (int k1 = kb->k1_first; ok && k1 <= kb->k1_last; ++k1) {
+        if (ptr2->transfer2_verbose > 1)
+          printf("     * computing transfer functions today for index_k1=%d of %d, k1=%g\n", k1, ppt2->k_size, ppt2->k[k1]);
+        if (transfer2_allocate_k1_level(ppt2, ptr2, k1) == _FAILURE_) { snprintf(local, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); ok = _FALSE_; break; }
+        if (sources_on_disk) {                                                                 /* :332-344 */
+          if (perturb2_allocate_k1_level(ppt2, k1) == _FAILURE_ || perturb2_load_sources_from_disk(ppt2, k1) == _FAILURE_) {
+            snprintf(local, _ERRORMSGSIZE_, "%.1500s", ppt2->error_message); ok = _FALSE_; break;
+          }
+        }
+      }
+      if (ok && run_batch(ppr, ppr2, ppt2, pbs, pbs2, ptr2, dev[d].ctx, mode, kb, local) == _FAILURE_) ok = _FALSE_;
+      for (int k1 = kb->k1_first; ok && k1 <= kb->k1_last; ++k1) {
+        if (perturb2_free_k1_level(ppt2, k1) == _FAILURE_) { snprintf(local, _ERRORMSGSIZE_, "%.1500s", ppt2->error_message); ok = _FALSE_; break; }   /* :553 */
+        if (ppr2->store_transfers_to_disk == _TRUE_) {                                         /* :559-567 */
+          if (transfer2_store_transfers_to_disk(ppt2, ptr2, k1) == _FAILURE_ || transfer2_free_k1_level(ppt2, ptr2, k1) == _FAILURE_) {
+            snprintf(local, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); ok = _FALSE_; break;
+          }
+        }
+      }
+      if (!ok) {
+        #pragma omp critical
+        { if (abort_flag == _FALSE_) { abort_flag = _TRUE_; snprintf(first_error, _ERRORMSGSIZE_, "%s", local); } }
+        break;
+      }
+    }
+  }
+  for (int d = 0; d < n_dev; ++d) song_los_destroy(dev[d].ctx);
+  free(dev); free(batches);
+  class_test(abort_flag == _TRUE_, ptr2->error_message, "%.1900s", first_error);
+
+  if (ppr2->store_transfers_to_disk == _TRUE_)                                                 /* :598-600 */
+    for (int index_tt = 0; index_tt < ptr2->tt2_size; ++index_tt) fclose(ptr2->transfers_files[index_tt]);
+  if (ptr2->transfer2_verbose > 1)
+    printf(" -> filled ptr2->transfer with %ld values (%g MB)\n", ptr2->count_memorised_transfers, ptr2->count_memorised_transfers / 1e6 * 8);
+  class_test(ptr2->count_allocated_transfers != ptr2->count_memorised_transfers, ptr2->error_message,        /* :607-610 */
+             "there is a mismatch between allocated (%ld) and used (%ld) space!", ptr2->count_allocated_transfers, ptr2->count_memorised_transfers);
+
+  if (ptr2->stop_at_transfers2 == _TRUE_) {                                                    /* :613-618 */
+    ppt->has_cls = _FALSE_; ppt->has_cmb_bispectra = _FALSE_;
+    ppt2->has_cmb_spectra = _FALSE_; ppt2->has_cmb_bispectra = _FALSE_;
+  }
+  return _SUCCESS_;
+}

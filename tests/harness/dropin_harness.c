@@ -1,0 +1,206 @@
+/*
+ * dropin_harness.c -- TEST HARNESS for the transfer2 drop-in (song_b200/host/transfer2_gpu.c).
+ *
+ * Plays the part of SONG's main/song.c and of the modules that run before transfer2 (input2, perturbations2,
+ * bessel2): it fills the SONG structures -- declared by SONG's own headers, include/transfer2.h & co. -- from the
+ * flat arrays of a synthetic workload, calls transfer2_init() exactly as main/song.c:106 does, and returns
+ * ptr2->transfer flattened in transfers_%03d.dat order.  Modelled on test/print_transfers2.c:147-185.
+ * perturb2_allocate/load/free_k1_level stand in for source/perturbations2.c:457-660 (out of scope).
+ */
+#include "transfer2.h"
+
+typedef struct harness_input {
+  double tau0, tau_rec, rs_rec;
+  int k_size; const double *k;
+  int tau_size; const double *tau_sampling;
+  int l_size; const int *l;
+  int m_size; const int *m;
+  int L_max, l_max_los_t, l_max_los_p;
+  int has_T, has_E, has_B;
+  int cubic_k3, cubic_bessel, k3_extrapolation;
+  double extra_left, extra_right, q_linstep_song, smallest_allowed_variation;
+  int xx_size; const double *xx; double xx_step, xx_max;
+  int J_size, index_J_TT, index_J_EE, index_J_EB;
+  const double *const *J_rows; const double *const *ddJ_rows; const int *index_xmin_J; const int *x_size_J;   /* flat jidx */
+  /* pairs in the reference loop order (k1 major, k2 <= k1) */
+  const int *k3_pt_size; const long long *pt_off; const double *k3_pt;
+  const long long *src_off; const double *src;           /* packed [pair][tp][tau][k3] */
+  int store_to_disk, load_from_disk; const char *transfers_dir;
+  int verbose;
+} harness_input;
+
+int perturb2_allocate_k1_level(struct perturbs2 *ppt2, int index_k1)
+{
+  snprintf(ppt2->error_message, _ERRORMSGSIZE_, "harness: sources are kept in memory, nothing to allocate for index_k1=%d", index_k1);
+  return _FAILURE_;
+}
+int perturb2_load_sources_from_disk(struct perturbs2 *ppt2, int index_k1)
+{
+  snprintf(ppt2->error_message, _ERRORMSGSIZE_, "harness: no sources on disk (index_k1=%d)", index_k1);
+  return _FAILURE_;
+}
+int perturb2_free_k1_level(struct perturbs2 *ppt2, int index_k1)
+{
+  /* as source/perturbations2.c:609-660: the k1 level of every source type is released */
+  for (int tp = 0; tp < ppt2->tp2_size; ++tp) {
+    for (int k2 = 0; k2 <= index_k1; ++k2) { free(ppt2->sources[tp][index_k1][k2]); ppt2->sources[tp][index_k1][k2] = NULL; }
+    free(ppt2->sources[tp][index_k1]); ppt2->sources[tp][index_k1] = NULL;
+  }
+  ppt2->has_allocated_sources[index_k1] = _FALSE_;
+  return _SUCCESS_;
+}
+
+static int n_sources(int l_max, const int *m, int m_size)
+{
+  int n = 0;
+  for (int L = 0; L <= l_max; ++L) for (int im = 0; im < m_size; ++im) if (m[im] <= L) ++n;
+  return n;
+}
+
+/* returns 0 on success; `out` receives, per transfer type, the [k1][k2][k3] values; sizes via out_sizes[3] =
+   {tt2_size, total k3 values per type, count_memorised_transfers} */
+int harness_transfer2(const harness_input *in, double *out, long long out_capacity, long long *out_sizes, int *labels_ok,
+                      char *errmsg, int errlen)
+{
+  static struct precision pr; static struct precision2 pr2; static struct background ba; static struct thermo th;
+  static struct perturbs pt; static struct perturbs2 pt2; static struct bessels bs; static struct bessels2 bs2;
+  static struct transfers tr; static struct transfers2 tr2;
+  memset(&pr, 0, sizeof pr); memset(&pr2, 0, sizeof pr2); memset(&ba, 0, sizeof ba); memset(&th, 0, sizeof th);
+  memset(&pt, 0, sizeof pt); memset(&pt2, 0, sizeof pt2); memset(&bs, 0, sizeof bs); memset(&bs2, 0, sizeof bs2);
+  memset(&tr, 0, sizeof tr); memset(&tr2, 0, sizeof tr2);
+  int rc = 1;
+
+  /* ---- input2 / precision ---- */
+  pr.bispectra_k3_extrapolation = in->k3_extrapolation ? flat_k3_extrapolation : no_k3_extrapolation;
+  pr.extra_k3_oscillations_left = in->extra_left; pr.extra_k3_oscillations_right = in->extra_right;
+  pr.smallest_allowed_variation = in->smallest_allowed_variation;
+  pr.bessels_interpolation = in->cubic_bessel ? cubic_interpolation : linear_interpolation;
+  pr2.m_size = in->m_size;
+  for (int im = 0; im < in->m_size; ++im) pr2.m[im] = in->m[im];
+  pr2.m_max_song = in->m[in->m_size - 1];
+  for (int M = 0; M < _MAX_NUM_AZIMUTHAL_; ++M) { pr2.compute_m[M] = _FALSE_; pr2.index_m[M] = -1; }
+  for (int im = 0; im < in->m_size; ++im) { pr2.compute_m[in->m[im]] = _TRUE_; pr2.index_m[in->m[im]] = im; }
+  int l_top = in->l[in->l_size - 1];
+  if (l_top < in->L_max) l_top = in->L_max;
+  pr2.index_m_max = malloc(sizeof(int) * (l_top + 1));
+  for (int l = 0; l <= l_top; ++l) { int idx = -1; for (int im = 0; im < in->m_size; ++im) if (in->m[im] <= l) idx = im; pr2.index_m_max[l] = idx; }
+  pr2.l_max_los_t = in->l_max_los_t; pr2.l_max_los_p = in->l_max_los_p;
+  pr2.q_linstep_song = in->q_linstep_song;
+  pr2.sources_k3_interpolation = in->cubic_k3 ? cubic_interpolation : linear_interpolation;
+  pr2.sources_time_interpolation = linear_interpolation;
+  pr2.store_transfers_to_disk = in->store_to_disk; pr2.load_transfers_from_disk = in->load_from_disk;
+
+  /* ---- background / thermodynamics ---- */
+  ba.conformal_age = in->tau0; th.tau_rec = in->tau_rec; th.rs_rec = in->rs_rec;
+
+  /* ---- perturbations2: samplings and sources ---- */
+  pt2.has_perturbations2 = _TRUE_; pt2.has_cmb_bispectra = _TRUE_;
+  pt2.k_size = in->k_size; pt2.k = (double *)in->k;
+  pt2.tau_size = in->tau_size; pt2.tau_sampling = (double *)in->tau_sampling;
+  pt2.has_source_T = in->has_T; pt2.has_source_E = in->has_E; pt2.has_source_B = in->has_B;
+  int nT = n_sources(in->l_max_los_t, in->m, in->m_size), nP = n_sources(in->l_max_los_p, in->m, in->m_size), tp = 0;
+  if (in->has_T) { pt2.index_tp2_T = tp; tp += nT; }
+  if (in->has_E) { pt2.index_tp2_E = tp; tp += nP; }
+  if (in->has_B) { pt2.index_tp2_B = tp; tp += nP; }
+  pt2.tp2_size = tp;
+  pt2.lm_array = malloc(sizeof(int *) * (in->L_max + 1));
+  for (int L = 0; L <= in->L_max; ++L) {
+    pt2.lm_array[L] = malloc(sizeof(int) * in->m_size);
+    for (int im = 0; im < in->m_size; ++im)
+      pt2.lm_array[L][im] = (in->m[im] <= L) ? multipole2offset_l_indexm(L, in->m[im], (int *)in->m, in->m_size) : -1;
+  }
+  pt2.k3 = malloc(sizeof(double **) * in->k_size);
+  pt2.k3_size = malloc(sizeof(int *) * in->k_size);
+  pt2.sources = malloc(sizeof(double ***) * pt2.tp2_size);
+  pt2.has_allocated_sources = calloc(in->k_size, sizeof(short));
+  for (int t = 0; t < pt2.tp2_size; ++t) pt2.sources[t] = malloc(sizeof(double **) * in->k_size);
+  int p = 0;
+  for (int k1 = 0; k1 < in->k_size; ++k1) {
+    pt2.k3[k1] = malloc(sizeof(double *) * (k1 + 1));
+    pt2.k3_size[k1] = malloc(sizeof(int) * (k1 + 1));
+    for (int t = 0; t < pt2.tp2_size; ++t) pt2.sources[t][k1] = malloc(sizeof(double *) * (k1 + 1));
+    for (int k2 = 0; k2 <= k1; ++k2, ++p) {
+      int np = in->k3_pt_size[p];
+      pt2.k3_size[k1][k2] = np;
+      pt2.k3[k1][k2] = (double *)(in->k3_pt + in->pt_off[p]);
+      for (int t = 0; t < pt2.tp2_size; ++t) {
+        size_t n = (size_t)in->tau_size * np;
+        pt2.sources[t][k1][k2] = malloc(sizeof(double) * n);
+        memcpy(pt2.sources[t][k1][k2], in->src + in->src_off[p] + (long long)t * n, sizeof(double) * n);
+      }
+    }
+    pt2.has_allocated_sources[k1] = _TRUE_;
+  }
+
+  /* ---- bessel / bessel2 ---- */
+  bs.l_size = in->l_size; bs.l = (int *)in->l; bs.l_max = in->l[in->l_size - 1];
+  bs2.L_max = in->L_max; bs2.L_size = in->L_max + 1;
+  bs2.L = malloc(sizeof(int) * bs2.L_size);
+  for (int L = 0; L < bs2.L_size; ++L) bs2.L[L] = L;
+  bs2.m_size = in->m_size; bs2.m = (int *)in->m;
+  bs2.xx = (double *)in->xx; bs2.xx_size = in->xx_size; bs2.xx_step = in->xx_step; bs2.xx_max = in->xx_max;
+  bs2.J_size = in->J_size;
+  bs2.has_J_TT = in->index_J_TT >= 0; bs2.has_J_EE = in->index_J_EE >= 0; bs2.has_J_EB = in->index_J_EB >= 0;
+  bs2.index_J_TT = in->index_J_TT; bs2.index_J_EE = in->index_J_EE; bs2.index_J_EB = in->index_J_EB;
+  bs2.J_Llm_x = malloc(sizeof(double ****) * in->J_size);
+  bs2.ddJ_Llm_x = malloc(sizeof(double ****) * in->J_size);
+  bs2.index_xmin_J = malloc(sizeof(int ***) * in->J_size);
+  bs2.x_size_J = malloc(sizeof(int ***) * in->J_size);
+  for (int J = 0; J < in->J_size; ++J) {
+    bs2.J_Llm_x[J] = malloc(sizeof(double ***) * bs2.L_size); bs2.ddJ_Llm_x[J] = malloc(sizeof(double ***) * bs2.L_size);
+    bs2.index_xmin_J[J] = malloc(sizeof(int **) * bs2.L_size); bs2.x_size_J[J] = malloc(sizeof(int **) * bs2.L_size);
+    for (int L = 0; L < bs2.L_size; ++L) {
+      bs2.J_Llm_x[J][L] = malloc(sizeof(double **) * in->l_size); bs2.ddJ_Llm_x[J][L] = malloc(sizeof(double **) * in->l_size);
+      bs2.index_xmin_J[J][L] = malloc(sizeof(int *) * in->l_size); bs2.x_size_J[J][L] = malloc(sizeof(int *) * in->l_size);
+      for (int il = 0; il < in->l_size; ++il) {
+        bs2.J_Llm_x[J][L][il] = calloc(in->m_size, sizeof(double *)); bs2.ddJ_Llm_x[J][L][il] = calloc(in->m_size, sizeof(double *));
+        bs2.index_xmin_J[J][L][il] = calloc(in->m_size, sizeof(int)); bs2.x_size_J[J][L][il] = calloc(in->m_size, sizeof(int));
+        for (int im = 0; im < in->m_size; ++im) {
+          size_t q = (((size_t)J * bs2.L_size + L) * in->l_size + il) * in->m_size + im;
+          bs2.J_Llm_x[J][L][il][im] = (double *)in->J_rows[q];
+          if (in->ddJ_rows) bs2.ddJ_Llm_x[J][L][il][im] = (double *)in->ddJ_rows[q];
+          bs2.index_xmin_J[J][L][il][im] = in->index_xmin_J[q];
+          bs2.x_size_J[J][L][il][im] = in->x_size_J[q];
+        }
+      }
+    }
+  }
+
+  /* ---- transfer2 (fields written by input2.c:1450-1522,1647) ---- */
+  tr2.k_sampling = class_transfer2_k3_sampling;
+  tr2.tau_sampling = sources_tau_sampling;
+  tr2.transfer2_verbose = in->verbose;
+  if (in->transfers_dir) snprintf(tr2.transfers_dir, _FILENAMESIZE_, "%s", in->transfers_dir);
+
+  if (transfer2_init(&pr, &pr2, &ba, &th, &pt, &pt2, &bs, &bs2, &tr, &tr2) == _FAILURE_) {       /* main/song.c:106 */
+    snprintf(errmsg, errlen, "%s", tr2.error_message);
+    return 1;
+  }
+
+  /* ---- read the result the way bispectra2.c:1213,1298 does ---- */
+  long long per_type = 0;
+  for (int k1 = 0; k1 < in->k_size; ++k1) for (int k2 = 0; k2 <= k1; ++k2) per_type += tr2.k_size_k1k2[k1][k2];
+  out_sizes[0] = tr2.tt2_size; out_sizes[1] = per_type; out_sizes[2] = tr2.count_memorised_transfers;
+  *labels_ok = 1;
+  if (out_capacity < per_type * tr2.tt2_size) { snprintf(errmsg, errlen, "output buffer too small"); return 1; }
+  for (int tt = 0; tt < tr2.tt2_size; ++tt) {
+    char expect[_MAX_LENGTH_LABEL_];
+    const char *f = (in->has_T && tt >= tr2.index_tt2_T && tt < tr2.index_tt2_T + tr2.n_transfers) ? "T"
+                  : (in->has_E && tt >= tr2.index_tt2_E && tt < tr2.index_tt2_E + tr2.n_transfers) ? "E" : "B";
+    snprintf(expect, sizeof expect, "%s_%d_%d", f, tr2.l[tr2.corresponding_index_l[tt]], tr2.m[tr2.corresponding_index_m[tt]]);
+    if (strcmp(expect, tr2.tt2_labels[tt]) != 0) *labels_ok = 0;
+    if (in->store_to_disk || in->load_from_disk) {
+      if (transfer2_load_transfers_from_disk(&pt2, &tr2, tt) == _FAILURE_) { snprintf(errmsg, errlen, "%s", tr2.error_message); return 1; }
+    }
+    long long o = 0;
+    for (int k1 = 0; k1 < in->k_size; ++k1)
+      for (int k2 = 0; k2 <= k1; ++k2) {
+        memcpy(out + tt * per_type + o, tr2.transfer[tt][k1][k2], sizeof(double) * tr2.k_size_k1k2[k1][k2]);
+        o += tr2.k_size_k1k2[k1][k2];
+      }
+    if (in->store_to_disk || in->load_from_disk) transfer2_free_type_level(&pt2, &tr2, tt);
+  }
+  rc = 0;
+  if (transfer2_free(&pr2, &pt2, &tr2) == _FAILURE_) { snprintf(errmsg, errlen, "%s", tr2.error_message); rc = 1; }
+  return rc;
+}
