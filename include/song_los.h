@@ -27,6 +27,12 @@
  *                              [tt][k1][k2][k3] order of transfers_%03d.dat (transfer2.c:2940-2957)
  *   song_los_transfer_pairs    upload + compute + download in one call with HOST buffers (the
  *                              end-to-end path a SONG run takes)
+ *   song_los_submit / _wait    the same, asynchronous and double-buffered: the k1 loop of
+ *                              transfer2_init (transfer2.c:315-570) as a pipeline in which the copy of
+ *                              batch n+1 to the device and of batch n-1 to the host overlap the
+ *                              kernels of batch n (the k1 levels are independent, transfer2.c:549-551)
+ *   song_los_host_alloc/_free  page-locked staging memory for ppt2->sources / ptr2->transfer slabs
+ *   song_los_max_batch_units   how many k3 values of consecutive k1 levels fit in one batch
  *
  * Error convention (reference: _SUCCESS_/_FAILURE_ + ErrorMsg): every function
  * returns SONG_LOS_SUCCESS (0) or SONG_LOS_FAILURE (1); the text is available from
@@ -45,6 +51,7 @@ extern "C" {
 
 #define SONG_LOS_SUCCESS 0
 #define SONG_LOS_FAILURE 1
+#define SONG_LOS_MAX_IN_FLIGHT 3
 
 /* mirrors of the reference enums, passed as ints */
 enum { SONG_LOS_TAU_SOURCES = 0, SONG_LOS_TAU_CUSTOM = 1, SONG_LOS_TAU_BESSEL = 2 }; /* transfer2.h:27-32 */
@@ -139,6 +146,8 @@ typedef struct song_los_timing {
   int   n_launches;                /* kernels launched by the call                    */
   int64_t n_integrals;             /* stored T values = n_units * tt2_size            */
   int64_t n_terms_upper;           /* n_integrals * tau_size * (L_max+1) upper bound  */
+  float ms_h2d;                    /* host->device copy of the batch (copy stream)    */
+  float ms_d2h;                    /* device->host copy of the result (song_los_wait) */
 } song_los_timing;
 
 typedef struct song_los_ctx song_los_ctx;
@@ -176,6 +185,26 @@ int  song_los_compute(song_los_ctx *ctx, int mode, song_los_timing *timing);
 int  song_los_download(song_los_ctx *ctx, double *transfer /* [tt2_size][n_units] */);
 int  song_los_transfer_pairs(song_los_ctx *ctx, const song_los_batch *batch, int mode,
                              double *transfer, song_los_timing *timing);
+
+/* Asynchronous pipeline.  song_los_submit validates the batch, enqueues its host->device copy, its
+ * kernels and the device->host copy of the result into `transfer` on three CUDA streams and returns.
+ * At most SONG_LOS_MAX_IN_FLIGHT (3) batches may be in flight -- one being copied in, one in the kernels, one
+ * being copied out; song_los_wait blocks until the OLDEST one is complete (result
+ * in `transfer`, device error flags converted to the error convention) and reports its timing.
+ * The batch arrays and `transfer` must stay valid until the matching song_los_wait returns; use
+ * song_los_host_alloc memory for k3_pt / k3_tr / src / transfer so that the copies overlap.
+ * The synchronous calls above refuse to run while submissions are in flight. */
+int  song_los_submit(song_los_ctx *ctx, const song_los_batch *batch, int mode, double *transfer);
+int  song_los_wait(song_los_ctx *ctx, song_los_timing *timing);
+
+/* Page-locked host memory (cudaHostAlloc, portable across devices). */
+int  song_los_host_alloc(void **ptr, size_t bytes);
+int  song_los_host_free(void *ptr);
+
+/* Upper bound on the k3 values of one batch such that three batches in flight and the intermediates of
+ * one compute fit in the free device memory.  src_doubles_per_unit = (source doubles of the run) /
+ * (k3 values of the run), i.e. tp2_size * tau_size * <k3_pt> / <k3_tr>.  Needs the projection tables. */
+int  song_los_max_batch_units(song_los_ctx *ctx, int mode, double src_doubles_per_unit, int64_t *units);
 
 /* Device pointer of the [tt2_size][n_units] result of the last compute (for the NCCL gather
    done by the multi-GPU driver), as an integer address; 0 before the first compute. */

@@ -88,6 +88,8 @@ class LosTiming(C.Structure):
         ("n_launches", C.c_int),
         ("n_integrals", C.c_int64),
         ("n_terms_upper", C.c_int64),
+        ("ms_h2d", C.c_float),
+        ("ms_d2h", C.c_float),
     ]
 
     def as_dict(self):
@@ -137,6 +139,7 @@ LOS_SYMBOLS = [
     "song_los_compute", "song_los_download", "song_los_transfer_pairs",
     "song_los_device_result", "song_los_copy_result", "song_los_set_stream", "song_los_measure_peaks",
     "song_los_device_info", "song_los_version",
+    "song_los_submit", "song_los_wait", "song_los_host_alloc", "song_los_host_free", "song_los_max_batch_units",
 ]
 HOST_SYMBOLS = ["song_host_k3_size", "song_host_k3_list", "song_host_k3_sizes", "song_host_k3_lists",
                 "song_host_bessel2_prepare", "song_host_bessel2_free", "song_host_bessel2_upload"]
@@ -175,6 +178,11 @@ def los():
         lib.song_los_copy_result.argtypes = [vp, C.c_uint64, C.c_int64]
         lib.song_los_device_info.argtypes = [vp, c_int64_p, c_int64_p, c_int_p, C.c_char_p, C.c_int]
         lib.song_los_version.argtypes = []
+        lib.song_los_submit.argtypes = [vp, C.POINTER(LosBatch), C.c_int, c_double_p]
+        lib.song_los_wait.argtypes = [vp, C.POINTER(LosTiming)]
+        lib.song_los_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+        lib.song_los_host_free.argtypes = [vp]
+        lib.song_los_max_batch_units.argtypes = [vp, C.c_int, C.c_double, c_int64_p]
         _los = lib
     return _los
 

@@ -257,6 +257,14 @@ __global__ void __launch_bounds__(128) tc_spline_csd_kernel(Batch b, int tau_siz
   }
 }
 
+// unit -> pair map: one CTA per pair writes its run of the pair-major unit sequence
+__global__ void tc_unit_pair_kernel(Batch b, int *unit_pair)
+{
+  const int p = blockIdx.x;
+  int *dst = unit_pair + b.tr_off[p];
+  for (int i = threadIdx.x; i < b.nt[p]; i += blockDim.x) dst[i] = p;
+}
+
 __global__ void tc_iota_kernel(int *p, int64_t n)
 {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -537,7 +545,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
         _Pragma("unroll") for (int i = 0; i < UPL; ++i) { \
           const double x_ = kk[i] * d_;                                 /* transfer2.c:2195 */ \
           int ix_ = (int)(x_ * P.inv_xx_step);                          /* transfer2.c:2199 */ \
-          if (ix_ < 0 || ix_ + 1 >= P.xx_size) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); ix_ = 0; } \
+          if (ix_ < 0 || ix_ + 1 >= P.xx_size) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); ix_ = max(0, min(ix_, P.xx_size - 2)); } \
           x_n[i] = x_; ix_n[i] = ix_; xxn_n[i] = __ldg(P.xx + ix_ + 1); } } while (0)
       TC_PREFETCH(0);
       for (int ip = 0; ip < P.n_pass; ++ip) {
@@ -716,8 +724,6 @@ struct FastState {
   TcParams tp{};                 // kernel parameter block (about 3 KB: kept off the stack)
   TcInterp interp{};
   PFN_cuTensorMapEncodeTiled encode = nullptr;
-  cudaEvent_t ev[6]{};
-  bool ev_ready = false;
 };
 
 FastState *fast_state_create() { return new FastState(); }
@@ -729,7 +735,6 @@ void fast_state_destroy(FastState *f)
   f->col_tt.release(); f->col_l.release(); f->col_lm.release(); f->term_col0.release(); f->nact.release();
   f->perm_in.release(); f->perm.release(); f->unit_pair.release(); f->slot_tp.release();
   f->uw.release(); f->ujp.release(); f->cub_tmp.release(); f->jcount.release();
-  if (f->ev_ready) for (auto &e : f->ev) cudaEventDestroy(e);
   delete f;
 }
 
@@ -909,12 +914,26 @@ static cudaError_t launch_tc(const TcParams &TP, int64_t n_ctas, size_t smem, cu
   return cudaGetLastError();
 }
 
-int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, const int *h_unit_pair,
-                 int device_sms, cudaStream_t st, song_los_timing *tm, std::string &err)
+int fast_prepare(FastState *fs, const FastHostLayout &h, const ExactParams &P, cudaStream_t st, std::string &err)
 {
   if (P.cubic_J) { err = "FAST mode supports linear Bessel interpolation only; use SONG_LOS_MODE_EXACT"; return 1; }
-  if (!fs->ev_ready) { for (auto &e : fs->ev) FCK(cudaEventCreate(&e)); fs->ev_ready = true; }
   if (!fs->table_ready && build_layout(fs, h, P, st, err)) return 1;
+  return 0;
+}
+
+// device bytes the FAST path needs per k3 unit beyond the batch inputs and the result: the source
+// slab S plus the per-unit sort / weight arrays
+int64_t fast_bytes_per_unit(const FastState *fs)
+{
+  return fs->s_doubles_per_unit * 8 + 8 /*keys*/ + 3 * 4 /*perm_in, perm, unit_pair*/ + (int64_t)sizeof(TcUnitW) + 8 /*ujp*/ + 16 /*cub*/;
+}
+
+// Enqueues the whole FAST pipeline on `st` and returns without waiting; ev[0..4] (caller-owned) are
+// recorded at the phase boundaries and read later by fast_collect.
+int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, int device_sms, cudaStream_t st,
+                 cudaEvent_t *ev, int *n_launches, std::string &err)
+{
+  if (fast_prepare(fs, h, P, st, err)) return 1;
   const Batch &b = P.b;
   const int64_t U = b.n_units;
   const int tau_size = P.tm.tau_size, tp2 = P.ty.tp2_size;
@@ -924,23 +943,24 @@ int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
   const int64_t n_tiles = (U + MT - 1) / MT;
 
   // ---- phase 0: transposed {y, dd} sources ----
-  FCK(cudaEventRecord(fs->ev[0], st));
+  FCK(cudaEventRecord(ev[0], st));
   FCK(fs->CSD.reserve((size_t)h.n_src_total));
   {
     int64_t cols = rowlen * b.n_pairs;
     if (cols > 0) {
       tc_spline_csd_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(b, tau_size, tp2, P.cubic_k3, fs->CSD.p, P.err);
       FCK(cudaGetLastError());
-      tm->n_launches++;
+      ++*n_launches;
     }
   }
-  FCK(cudaEventRecord(fs->ev[1], st));
+  FCK(cudaEventRecord(ev[1], st));
 
   // ---- phase 1: global k3 order ----
   FCK(fs->perm_in.reserve((size_t)U)); FCK(fs->perm.reserve((size_t)U)); FCK(fs->keys_out.reserve((size_t)U));
   FCK(fs->unit_pair.reserve((size_t)U));
-  FCK(cudaMemcpyAsync(fs->unit_pair.p, h_unit_pair, (size_t)U * sizeof(int), cudaMemcpyHostToDevice, st));
   if (U > 0) {
+    tc_unit_pair_kernel<<<(unsigned)b.n_pairs, 128, 0, st>>>(b, fs->unit_pair.p);
+    FCK(cudaGetLastError());
     tc_iota_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(fs->perm_in.p, U);
     FCK(cudaGetLastError());
     size_t tmp_bytes = 0;
@@ -949,9 +969,9 @@ int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
     FCK(fs->cub_tmp.reserve(tmp_bytes));
     FCK(cub::DeviceRadixSort::SortPairs(fs->cub_tmp.p, tmp_bytes, b.k3_tr, fs->keys_out.p, fs->perm_in.p, fs->perm.p,
                                         (int)U, 0, 64, st));
-    tm->n_launches += 4;
+    *n_launches += 5;
   }
-  FCK(cudaEventRecord(fs->ev[2], st));
+  FCK(cudaEventRecord(ev[2], st));
 
   // ---- phase 2: interpolated sources in consumption order ----
   FCK(fs->uw.reserve((size_t)U)); FCK(fs->ujp.reserve((size_t)U));
@@ -982,9 +1002,9 @@ int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
     FCK(cudaFuncSetAttribute(tc_interp_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
     tc_interp_units_kernel<<<grid, TC_INTERP_THREADS, ismem, st>>>(b, I, tau_size, tp2, fs->CSD.p, fs->uw.p, fs->ujp.p, fs->S.p);
     FCK(cudaGetLastError());
-    tm->n_launches += 2;
+    *n_launches += 2;
   }
-  FCK(cudaEventRecord(fs->ev[3], st));
+  FCK(cudaEventRecord(ev[3], st));
 
   // ---- phase 3: the DMMA kernel ----
   TcParams &TP = fs->tp;
@@ -1045,16 +1065,21 @@ int fast_compute(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
       case 210:  e = launch_tc<2, 4, 10>(TP, n_ctas, smem, st); break;
     }
     FCK(e);
-    tm->n_launches++;
+    ++*n_launches;
   }
-  FCK(cudaEventRecord(fs->ev[4], st));
-  FCK(cudaEventSynchronize(fs->ev[4]));
+  FCK(cudaEventRecord(ev[4], st));
+  return 0;
+}
+
+int fast_collect(cudaEvent_t *ev, song_los_timing *tm, std::string &err)
+{
+  FCK(cudaEventSynchronize(ev[4]));
   float ms;
-  FCK(cudaEventElapsedTime(&ms, fs->ev[0], fs->ev[1])); tm->ms_spline = ms;
-  FCK(cudaEventElapsedTime(&ms, fs->ev[1], fs->ev[2])); tm->ms_sort = ms;
-  FCK(cudaEventElapsedTime(&ms, fs->ev[2], fs->ev[3])); tm->ms_interp = ms;
-  FCK(cudaEventElapsedTime(&ms, fs->ev[3], fs->ev[4])); tm->ms_integrate = ms;
-  FCK(cudaEventElapsedTime(&ms, fs->ev[0], fs->ev[4])); tm->ms_total = ms;
+  FCK(cudaEventElapsedTime(&ms, ev[0], ev[1])); tm->ms_spline = ms;
+  FCK(cudaEventElapsedTime(&ms, ev[1], ev[2])); tm->ms_sort = ms;
+  FCK(cudaEventElapsedTime(&ms, ev[2], ev[3])); tm->ms_interp = ms;
+  FCK(cudaEventElapsedTime(&ms, ev[3], ev[4])); tm->ms_integrate = ms;
+  FCK(cudaEventElapsedTime(&ms, ev[0], ev[4])); tm->ms_total = ms;
   return 0;
 }
 

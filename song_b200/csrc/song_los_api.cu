@@ -89,6 +89,17 @@ extern "C" int song_los_create(const song_los_config *cfg, song_los_ctx **out)
   }
   ctx->stream = ctx->own_stream;
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+  bool slots_ok = cudaStreamCreateWithFlags(&ctx->st_h2d, cudaStreamNonBlocking) == cudaSuccess
+               && cudaStreamCreateWithFlags(&ctx->st_d2h, cudaStreamNonBlocking) == cudaSuccess;
+  for (auto &S : ctx->slot) {
+    slots_ok = slots_ok && cudaEventCreate(&S.ev_h2d) == cudaSuccess && cudaEventCreate(&S.ev_compute) == cudaSuccess
+            && cudaEventCreate(&S.ev_d2h) == cudaSuccess && cudaEventCreate(&S.ev_h2d_start) == cudaSuccess
+            && cudaEventCreate(&S.ev_d2h_start) == cudaSuccess
+            && cudaHostAlloc((void **)&S.h_err, sizeof(int), cudaHostAllocDefault) == cudaSuccess;
+    for (auto &e : S.ev_t) slots_ok = slots_ok && cudaEventCreate(&e) == cudaSuccess;
+    if (S.h_err) *S.h_err = 0;
+  }
+  if (!slots_ok) { song_los_destroy(ctx); return ctx_fail(nullptr, "song_los_create: stream/event creation failed"); }
 
   ctx->tau.assign(cfg->tau_sampling, cfg->tau_sampling + cfg->tau_size);
   ctx->xx.assign(cfg->xx, cfg->xx + cfg->xx_size);
@@ -164,10 +175,17 @@ extern "C" int song_los_destroy(song_los_ctx *ctx)
   ctx->d_tt_im.release(); ctx->d_lm_src.release(); ctx->d_J.release(); ctx->d_ddJ.release();
   ctx->d_block_nonzero.release(); ctx->d_ragged.release(); ctx->d_col_off.release();
   ctx->d_col_xmin.release(); ctx->d_col_xsize.release();
-  ctx->d_np.release(); ctx->d_nt.release(); ctx->d_phys_start.release(); ctx->d_phys_size.release();
-  ctx->d_pt_off.release(); ctx->d_tr_off.release(); ctx->d_src_off.release();
-  ctx->d_k3_pt.release(); ctx->d_k3_tr.release(); ctx->d_src.release(); ctx->d_dd.release();
-  ctx->d_out.release(); ctx->d_tiles.release(); ctx->d_err.release(); ctx->d_scratch.release();
+  cudaDeviceSynchronize();
+  for (auto &S : ctx->slot) {
+    S.d_meta.release(); S.d_k3_pt.release(); S.d_k3_tr.release(); S.d_src.release(); S.d_out.release(); S.d_tiles.release();
+    if (S.h_meta) cudaFreeHost(S.h_meta);
+    if (S.h_err) cudaFreeHost(S.h_err);
+    for (cudaEvent_t e : {S.ev_h2d, S.ev_compute, S.ev_d2h, S.ev_h2d_start, S.ev_d2h_start}) if (e) cudaEventDestroy(e);
+    for (auto &e : S.ev_t) if (e) cudaEventDestroy(e);
+  }
+  if (ctx->st_h2d) cudaStreamDestroy(ctx->st_h2d);
+  if (ctx->st_d2h) cudaStreamDestroy(ctx->st_d2h);
+  ctx->d_dd.release(); ctx->d_err.release(); ctx->d_scratch.release();
   if (ctx->fast) fast_state_destroy(ctx->fast);
   if (ctx->d_proj_rows) cudaFree(ctx->d_proj_rows);
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -312,19 +330,30 @@ extern "C" int song_los_set_projection(song_los_ctx *ctx, const double *const *J
 }
 
 // ---------------------------------------------------------------------------------------------
-// Batches
+// Batches.  Every batch lives in one of three slots (inputs + result on the device, pinned staging of
+// the per-pair arrays on the host).  Three streams: host->device copies, kernels, device->host copies.
+// A slot is reused only after song_los_wait has seen its device->host copy finish, so no cross-slot
+// event waits are needed beyond  h2d -> compute -> d2h  inside a slot.
 // ---------------------------------------------------------------------------------------------
-extern "C" int song_los_upload_pairs(song_los_ctx *ctx, const song_los_batch *b)
+namespace songlos {
+// CTA work list of the exact kernel, (pair, first k3 index), built on the device
+__global__ void fill_tiles_kernel(const int *nt, const int *tile_off, int n_pairs, int2 *tiles)
 {
-  if (!ctx || !b) return ctx_fail(ctx, "song_los_upload_pairs: NULL argument");
-  CK(cudaSetDevice(ctx->device));
+  const int p = blockIdx.x;
+  const int n = (nt[p] + EXACT_UNITS_PER_CTA - 1) / EXACT_UNITS_PER_CTA;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) tiles[tile_off[p] + i] = make_int2(p, i * EXACT_UNITS_PER_CTA);
+}
+}  // namespace songlos
+
+static int validate_batch(song_los_ctx *ctx, const song_los_batch *b)
+{
   const song_los_config &c = ctx->cfg;
   if (b->n_pairs < 0) return ctx_fail(ctx, "song_los_upload_pairs: negative n_pairs");
   // consistency checks (the reference's class_test of transfer2.c:1766-1771 and layout checks)
   int64_t pt = 0, tr = 0, so = 0;
+  const int need = (c.sources_k3_interpolation == SONG_LOS_INTERP_CUBIC) ? 4 : 2;
   for (int p = 0; p < b->n_pairs; ++p) {
     int np = b->k3_pt_size[p], nt = b->k3_tr_size[p];
-    int need = (c.sources_k3_interpolation == SONG_LOS_INTERP_CUBIC) ? 4 : 2;
     if (np < need)
       return ctx_fail(ctx, "pair %d: cannot do interpolation in k3 with just k3_size=%d values. Increase k3_size.", p, np);
     if (nt < 1) return ctx_fail(ctx, "pair %d: empty k3 grid", p);
@@ -338,47 +367,75 @@ extern "C" int song_los_upload_pairs(song_los_ctx *ctx, const song_los_batch *b)
   }
   if (pt != b->n_pt_total || tr != b->n_units || so != b->n_src_total)
     return ctx_fail(ctx, "song_los_upload_pairs: totals do not match the per-pair sizes");
-
-  cudaStream_t st = ctx->stream;
-  size_t n = (size_t)b->n_pairs;
-  CK(upload(ctx->d_np, b->k3_pt_size, n, st));
-  CK(upload(ctx->d_nt, b->k3_tr_size, n, st));
-  CK(upload(ctx->d_phys_start, b->phys_start, n, st));
-  CK(upload(ctx->d_phys_size, b->phys_size, n, st));
-  CK(upload(ctx->d_pt_off, b->pt_off, n, st));
-  CK(upload(ctx->d_tr_off, b->tr_off, n, st));
-  CK(upload(ctx->d_src_off, b->src_off, n, st));
-  CK(upload(ctx->d_k3_pt, b->k3_pt, (size_t)b->n_pt_total, st));
-  CK(upload(ctx->d_k3_tr, b->k3_tr, (size_t)b->n_units, st));
-  CK(upload(ctx->d_src, b->src, (size_t)b->n_src_total, st));
-  CK(ctx->d_out.reserve((size_t)b->n_units * c.tt2_size));
-  if (c.sources_k3_interpolation == SONG_LOS_INTERP_CUBIC) CK(ctx->d_dd.reserve((size_t)b->n_src_total));
-
-  // CTA work list of the exact kernel: (pair, first k3 index)
-  std::vector<int2> tiles;
-  for (int p = 0; p < b->n_pairs; ++p)
-    for (int u0 = 0; u0 < b->k3_tr_size[p]; u0 += EXACT_UNITS_PER_CTA)
-      tiles.push_back(make_int2(p, u0));
-  ctx->n_tiles = (int)tiles.size();
-  CK(upload(ctx->d_tiles, tiles.data(), tiles.size(), st));
-  CK(cudaStreamSynchronize(st));
-
-  ctx->hb = *b;
-  ctx->hb.k3_pt_size = ctx->hb.k3_tr_size = ctx->hb.phys_start = ctx->hb.phys_size = nullptr;
-  ctx->hb.pt_off = ctx->hb.tr_off = ctx->hb.src_off = nullptr;
-  ctx->hb.k3_pt = ctx->hb.k3_tr = ctx->hb.src = nullptr;
-  ctx->h_np.assign(b->k3_pt_size, b->k3_pt_size + n);
-  ctx->h_nt.assign(b->k3_tr_size, b->k3_tr_size + n);
-  ctx->h_tr_off.assign(b->tr_off, b->tr_off + n);
-  ctx->h_unit_pair.resize((size_t)b->n_units);
-  for (int p = 0; p < b->n_pairs; ++p)
-    std::fill(ctx->h_unit_pair.begin() + b->tr_off[p], ctx->h_unit_pair.begin() + b->tr_off[p] + b->k3_tr_size[p], p);
-  ctx->have_batch = true;
-  ctx->have_result = false;
+  if (b->n_units >= ((int64_t)1 << 31)) return ctx_fail(ctx, "song_los_upload_pairs: more than 2^31 k3 values in one batch");
   return SONG_LOS_SUCCESS;
 }
 
-static void fill_params(song_los_ctx *ctx, ExactParams &P)
+// host->device copies of one batch into slot S, enqueued on the copy stream; records S.ev_h2d
+static int enqueue_upload(song_los_ctx *ctx, song_los_ctx::Slot &S, const song_los_batch *b)
+{
+  const song_los_config &c = ctx->cfg;
+  if (validate_batch(ctx, b) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
+  const size_t n = (size_t)b->n_pairs;
+  // packed per-pair arrays: 3 x int64 then 5 x int, one pinned staging buffer, one copy
+  const size_t meta_bytes = n * (3 * sizeof(int64_t) + 5 * sizeof(int));
+  if (meta_bytes > S.h_meta_cap) {
+    if (S.h_meta) cudaFreeHost(S.h_meta);
+    S.h_meta = nullptr; S.h_meta_cap = 0;
+    CK(cudaHostAlloc((void **)&S.h_meta, std::max<size_t>(meta_bytes, 64), cudaHostAllocDefault));
+    S.h_meta_cap = std::max<size_t>(meta_bytes, 64);
+  }
+  CK(S.d_meta.reserve(std::max<size_t>(meta_bytes, 64)));
+  int64_t *h64 = reinterpret_cast<int64_t *>(S.h_meta);
+  int *h32 = reinterpret_cast<int *>(S.h_meta + n * 3 * sizeof(int64_t));
+  std::memcpy(h64, b->pt_off, n * 8); std::memcpy(h64 + n, b->tr_off, n * 8); std::memcpy(h64 + 2 * n, b->src_off, n * 8);
+  std::memcpy(h32, b->k3_pt_size, n * 4); std::memcpy(h32 + n, b->k3_tr_size, n * 4);
+  std::memcpy(h32 + 2 * n, b->phys_start, n * 4); std::memcpy(h32 + 3 * n, b->phys_size, n * 4);
+  int64_t n_tiles = 0;
+  for (size_t p = 0; p < n; ++p) {
+    h32[4 * n + p] = (int)n_tiles;
+    n_tiles += (b->k3_tr_size[p] + EXACT_UNITS_PER_CTA - 1) / EXACT_UNITS_PER_CTA;
+  }
+  if (n_tiles >= ((int64_t)1 << 31)) return ctx_fail(ctx, "song_los_upload_pairs: too many k3 tiles in one batch");
+  S.n_tiles = (int)n_tiles; S.tiles_ready = false;
+  int64_t *d64 = reinterpret_cast<int64_t *>(S.d_meta.p);
+  int *d32 = reinterpret_cast<int *>(S.d_meta.p + n * 3 * sizeof(int64_t));
+  S.d_pt_off = d64; S.d_tr_off = d64 + n; S.d_src_off = d64 + 2 * n;
+  S.d_np = d32; S.d_nt = d32 + n; S.d_phys_start = d32 + 2 * n; S.d_phys_size = d32 + 3 * n; S.d_tile_off = d32 + 4 * n;
+
+  CK(S.d_k3_pt.reserve((size_t)b->n_pt_total));
+  CK(S.d_k3_tr.reserve((size_t)b->n_units));
+  CK(S.d_src.reserve((size_t)b->n_src_total));
+  CK(S.d_out.reserve((size_t)b->n_units * c.tt2_size));
+  cudaStream_t st = ctx->st_h2d;
+  CK(cudaEventRecord(S.ev_h2d_start, st));
+  if (meta_bytes) CK(cudaMemcpyAsync(S.d_meta.p, S.h_meta, meta_bytes, cudaMemcpyHostToDevice, st));
+  if (b->n_pt_total) CK(cudaMemcpyAsync(S.d_k3_pt.p, b->k3_pt, (size_t)b->n_pt_total * 8, cudaMemcpyHostToDevice, st));
+  if (b->n_units) CK(cudaMemcpyAsync(S.d_k3_tr.p, b->k3_tr, (size_t)b->n_units * 8, cudaMemcpyHostToDevice, st));
+  if (b->n_src_total) CK(cudaMemcpyAsync(S.d_src.p, b->src, (size_t)b->n_src_total * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(S.ev_h2d, st));
+
+  S.hb = *b;
+  S.hb.k3_pt_size = S.hb.k3_tr_size = S.hb.phys_start = S.hb.phys_size = nullptr;
+  S.hb.pt_off = S.hb.tr_off = S.hb.src_off = nullptr;
+  S.hb.k3_pt = S.hb.k3_tr = S.hb.src = nullptr;
+  S.have_batch = true;
+  S.have_result = false;
+  return SONG_LOS_SUCCESS;
+}
+
+extern "C" int song_los_upload_pairs(song_los_ctx *ctx, const song_los_batch *b)
+{
+  if (!ctx || !b) return ctx_fail(ctx, "song_los_upload_pairs: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->n_in_flight) return ctx_fail(ctx, "song_los_upload_pairs: %d submitted batches are still in flight; call song_los_wait first", ctx->n_in_flight);
+  song_los_ctx::Slot &S = ctx->slot[ctx->cur];
+  if (enqueue_upload(ctx, S, b) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
+  CK(cudaEventSynchronize(S.ev_h2d));
+  return SONG_LOS_SUCCESS;
+}
+
+static void fill_params(song_los_ctx *ctx, const song_los_ctx::Slot &S, ExactParams &P)
 {
   const song_los_config &c = ctx->cfg;
   std::memset(&P, 0, sizeof P);
@@ -394,33 +451,132 @@ static void fill_params(song_los_ctx *ctx, ExactParams &P)
   P.tm.tau_size = c.tau_size; P.tm.tau = ctx->d_tau.p; P.tm.tau0_minus_tau = ctx->d_tau0_minus_tau.p;
   P.tm.delta_tau = ctx->d_delta_tau.p; P.tm.tau0 = c.tau0; P.tm.mode = c.tau_sampling_mode;
   P.tm.tau_linstep_song = c.tau_linstep_song;
-  P.b.n_pairs = ctx->hb.n_pairs; P.b.np = ctx->d_np.p; P.b.nt = ctx->d_nt.p;
-  P.b.phys_start = ctx->d_phys_start.p; P.b.phys_size = ctx->d_phys_size.p;
-  P.b.pt_off = ctx->d_pt_off.p; P.b.tr_off = ctx->d_tr_off.p; P.b.src_off = ctx->d_src_off.p;
-  P.b.k3_pt = ctx->d_k3_pt.p; P.b.k3_tr = ctx->d_k3_tr.p; P.b.src = ctx->d_src.p; P.b.dd = ctx->d_dd.p;
-  P.b.n_units = ctx->hb.n_units; P.b.out = ctx->d_out.p;
+  P.b.n_pairs = S.hb.n_pairs; P.b.np = S.d_np; P.b.nt = S.d_nt;
+  P.b.phys_start = S.d_phys_start; P.b.phys_size = S.d_phys_size;
+  P.b.pt_off = S.d_pt_off; P.b.tr_off = S.d_tr_off; P.b.src_off = S.d_src_off;
+  P.b.k3_pt = S.d_k3_pt.p; P.b.k3_tr = S.d_k3_tr.p; P.b.src = S.d_src.p; P.b.dd = ctx->d_dd.p;
+  P.b.n_units = S.hb.n_units; P.b.out = S.d_out.p;
   P.xx = ctx->d_xx.p; P.xx_size = c.xx_size; P.xx_step = c.xx_step;
   P.cubic_k3 = (c.sources_k3_interpolation == SONG_LOS_INTERP_CUBIC);
   P.cubic_J = (c.bessels_interpolation == SONG_LOS_INTERP_CUBIC);
   P.cubic_time = (c.sources_time_interpolation == SONG_LOS_INTERP_CUBIC);
   P.flat_extrap = (c.k3_extrapolation == SONG_LOS_FLAT_K3_EXTRAPOLATION);
-  P.tiles = ctx->d_tiles.p;
+  P.tiles = S.d_tiles.p;
   P.err = ctx->d_err.p;
 }
 
-static int check_device_errors(song_los_ctx *ctx)
+static void fill_fast_layout(song_los_ctx *ctx, const song_los_ctx::Slot &S, FastHostLayout &h)
 {
-  int h = 0;
-  CK(cudaMemcpyAsync(&h, ctx->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (h) {
-    cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), ctx->stream);
-    if (h & ERR_X_OUT_OF_RANGE)
-      return ctx_fail(ctx, "not enough J's: k*(tau0-tau) exceeds xx_max (transfer2.c:2172); increase l_max or decrease k_max");
-    if (h & ERR_H_ZERO) return ctx_fail(ctx, "stop to avoid division by zero in the k3 interpolation (or k3_size outside [3,256])");
-    if (h & ERR_TAU_GRID_OVERFLOW) return ctx_fail(ctx, "time integration grid larger than the allocated maximum");
-    if (h & ERR_NAN) return ctx_fail(ctx, "found nan in second-order transfer function");
+  const song_los_config &c = ctx->cfg;
+  h = FastHostLayout{};
+  h.has_T = c.has_source_T; h.has_E = c.has_source_E; h.has_B = c.has_source_B;
+  h.index_tt2_T = c.index_tt2_T; h.index_tt2_E = c.index_tt2_E; h.index_tt2_B = c.index_tt2_B;
+  h.index_tp2_T = c.index_tp2_T; h.index_tp2_E = c.index_tp2_E; h.index_tp2_B = c.index_tp2_B;
+  h.index_J_TT = c.index_J_TT; h.index_J_EE = c.index_J_EE; h.index_J_EB = c.index_J_EB;
+  h.l_max_los_t = c.l_max_los_t; h.l_max_los_p = c.l_max_los_p;
+  h.l_size = c.l_size; h.m_size = c.m_size; h.L_size = c.L_size; h.n_transfers = c.n_transfers;
+  h.xx_size = c.xx_size; h.l = c.l; h.m = c.m; h.lm_array = c.lm_array; h.lm_src = c.lm_src;
+  h.block_nonzero = ctx->h_block_nonzero.data(); h.n_src_total = S.hb.n_src_total;
+  h.tau_size = c.tau_size; h.n_pt_total = S.hb.n_pt_total;
+}
+
+static int report_device_errors(song_los_ctx *ctx, int h)
+{
+  if (h & ERR_X_OUT_OF_RANGE)
+    return ctx_fail(ctx, "not enough J's: k*(tau0-tau) exceeds xx_max (transfer2.c:2172); increase l_max or decrease k_max");
+  if (h & ERR_H_ZERO) return ctx_fail(ctx, "stop to avoid division by zero in the k3 interpolation (or k3_size outside [3,256])");
+  if (h & ERR_TAU_GRID_OVERFLOW) return ctx_fail(ctx, "time integration grid larger than the allocated maximum");
+  if (h & ERR_NAN) return ctx_fail(ctx, "found nan in second-order transfer function");
+  return SONG_LOS_SUCCESS;
+}
+
+// kernels of one batch on the compute stream, after the slot's upload; records S.ev_compute.  No host wait.
+static int enqueue_compute(song_los_ctx *ctx, song_los_ctx::Slot &S, int mode)
+{
+  if (!ctx->have_proj) return ctx_fail(ctx, "song_los_compute: projection functions not set (bessel2 first)");
+  if (!S.have_batch) return ctx_fail(ctx, "song_los_compute: no pairs uploaded");
+  const song_los_config &c = ctx->cfg;
+  if (mode != SONG_LOS_MODE_EXACT && mode != SONG_LOS_MODE_FAST) return ctx_fail(ctx, "song_los_compute: unknown mode %d", mode);
+  if (c.tau_sampling_mode != SONG_LOS_TAU_SOURCES)
+    return ctx_fail(ctx, "song_los_compute: custom/bessel tau sampling is not available in this build");
+  song_los_timing &t = S.t;
+  t = song_los_timing{};
+  t.n_integrals = S.hb.n_units * c.tt2_size;
+  {
+    int64_t nT = 0, nP = 0;
+    for (int tt = 0; tt < c.tt2_size; ++tt) (ctx->tt_type[tt] == 0 ? nT : nP)++;
+    t.n_terms_upper = S.hb.n_units * c.tau_size * (nT * (c.l_max_los_t + 1) + nP * (c.l_max_los_p + 1));
   }
+  cudaStream_t st = ctx->stream;
+  CK(cudaStreamWaitEvent(st, S.ev_h2d, 0));
+  if (mode == SONG_LOS_MODE_EXACT && c.sources_k3_interpolation == SONG_LOS_INTERP_CUBIC)
+    CK(ctx->d_dd.reserve((size_t)S.hb.n_src_total));
+  ExactParams P;
+  fill_params(ctx, S, P);
+  S.fast_timed = false;
+  if (mode == SONG_LOS_MODE_EXACT) {
+    CK(cudaEventRecord(S.ev_t[0], st));
+    if (!S.tiles_ready && S.n_tiles > 0) {
+      CK(S.d_tiles.reserve((size_t)S.n_tiles));
+      P.tiles = S.d_tiles.p;
+      fill_tiles_kernel<<<(unsigned)S.hb.n_pairs, 64, 0, st>>>(S.d_nt, S.d_tile_off, S.hb.n_pairs, S.d_tiles.p);
+      CK(cudaGetLastError());
+      S.tiles_ready = true; t.n_launches++;
+    }
+    if (P.cubic_k3) {
+      CK(launch_spline_k3(P.b, c.tau_size, c.tp2_size, ctx->d_dd.p, ctx->d_err.p, st));
+      t.n_launches++;
+    }
+    CK(cudaEventRecord(S.ev_t[1], st));
+    // tau chunk: as many time samples as fit in ~96 KB of shared memory
+    size_t per_tau = exact_smem_bytes(1, c.tp2_size) - 16;
+    int chunk = (int)std::min<size_t>((size_t)c.tau_size, (96 * 1024) / per_tau);
+    if (chunk < 1) return ctx_fail(ctx, "song_los_compute: tp2_size=%d too large for the shared-memory stage", c.tp2_size);
+    P.tau_chunk = chunk;
+    CK(launch_los_exact(P, S.n_tiles, st));
+    t.n_launches++;
+    CK(cudaEventRecord(S.ev_t[2], st));
+  } else {
+    std::string e;
+    FastHostLayout h;
+    fill_fast_layout(ctx, S, h);
+    if (fast_enqueue(ctx->fast, h, P, ctx->sm_count, st, S.ev_t, &t.n_launches, e) != 0)
+      return ctx_fail(ctx, "%s", e.c_str());
+    S.fast_timed = true;
+  }
+  // error flags of this batch: copied to the slot's pinned word, then cleared for the next batch
+  CK(cudaMemcpyAsync(S.h_err, ctx->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), st));
+  CK(cudaEventRecord(S.ev_compute, st));
+  return SONG_LOS_SUCCESS;
+}
+
+// waits for the slot's kernels, fills the timing and converts device error flags
+static int finish_compute(song_los_ctx *ctx, song_los_ctx::Slot &S)
+{
+  CK(cudaEventSynchronize(S.ev_compute));
+  song_los_timing &t = S.t;
+  if (S.fast_timed) {
+    std::string e;
+    if (fast_collect(S.ev_t, &t, e) != 0) return ctx_fail(ctx, "%s", e.c_str());
+  } else {
+    CK(cudaEventElapsedTime(&t.ms_spline, S.ev_t[0], S.ev_t[1]));
+    CK(cudaEventElapsedTime(&t.ms_integrate, S.ev_t[1], S.ev_t[2]));
+    CK(cudaEventElapsedTime(&t.ms_total, S.ev_t[0], S.ev_t[2]));
+  }
+  CK(cudaEventElapsedTime(&t.ms_h2d, S.ev_h2d_start, S.ev_h2d));
+  if (*S.h_err) return report_device_errors(ctx, *S.h_err);
+  S.have_result = true;
+  return SONG_LOS_SUCCESS;
+}
+
+static int enqueue_download(song_los_ctx *ctx, song_los_ctx::Slot &S, double *transfer)
+{
+  size_t n = (size_t)S.hb.n_units * ctx->cfg.tt2_size;
+  CK(cudaStreamWaitEvent(ctx->st_d2h, S.ev_compute, 0));
+  CK(cudaEventRecord(S.ev_d2h_start, ctx->st_d2h));
+  if (n) CK(cudaMemcpyAsync(transfer, S.d_out.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->st_d2h));
+  CK(cudaEventRecord(S.ev_d2h, ctx->st_d2h));
   return SONG_LOS_SUCCESS;
 }
 
@@ -428,63 +584,11 @@ extern "C" int song_los_compute(song_los_ctx *ctx, int mode, song_los_timing *tm
 {
   if (!ctx) return SONG_LOS_FAILURE;
   CK(cudaSetDevice(ctx->device));
-  if (!ctx->have_proj) return ctx_fail(ctx, "song_los_compute: projection functions not set (bessel2 first)");
-  if (!ctx->have_batch) return ctx_fail(ctx, "song_los_compute: no pairs uploaded");
-  const song_los_config &c = ctx->cfg;
-  song_los_timing t{};
-  t.n_integrals = ctx->hb.n_units * c.tt2_size;
-  {
-    int64_t nT = 0, nP = 0;
-    for (int tt = 0; tt < c.tt2_size; ++tt) (ctx->tt_type[tt] == 0 ? nT : nP)++;
-    t.n_terms_upper = ctx->hb.n_units * c.tau_size * (nT * (c.l_max_los_t + 1) + nP * (c.l_max_los_p + 1));
-  }
-  cudaStream_t st = ctx->stream;
-  ExactParams P;
-  fill_params(ctx, P);
-
-  CK(cudaEventRecord(ctx->ev[0], st));
-  const bool exact_path = (mode == SONG_LOS_MODE_EXACT || c.tau_sampling_mode != SONG_LOS_TAU_SOURCES);
-  if (P.cubic_k3 && exact_path) {
-    CK(launch_spline_k3(P.b, c.tau_size, c.tp2_size, ctx->d_dd.p, ctx->d_err.p, st));
-    t.n_launches++;
-  }
-  CK(cudaEventRecord(ctx->ev[1], st));
-
-  if (mode == SONG_LOS_MODE_EXACT || c.tau_sampling_mode != SONG_LOS_TAU_SOURCES) {
-    if (c.tau_sampling_mode != SONG_LOS_TAU_SOURCES)
-      return ctx_fail(ctx, "song_los_compute: custom/bessel tau sampling is not available in this build");
-    // tau chunk: as many time samples as fit in ~96 KB of shared memory
-    size_t per_tau = exact_smem_bytes(1, c.tp2_size) - 16;
-    int chunk = (int)std::min<size_t>((size_t)c.tau_size, (96 * 1024) / per_tau);
-    if (chunk < 1) return ctx_fail(ctx, "song_los_compute: tp2_size=%d too large for the shared-memory stage", c.tp2_size);
-    P.tau_chunk = chunk;
-    CK(launch_los_exact(P, ctx->n_tiles, st));
-    t.n_launches++;
-    CK(cudaEventRecord(ctx->ev[2], st));
-    CK(cudaEventSynchronize(ctx->ev[2]));
-    CK(cudaEventElapsedTime(&t.ms_spline, ctx->ev[0], ctx->ev[1]));
-    CK(cudaEventElapsedTime(&t.ms_integrate, ctx->ev[1], ctx->ev[2]));
-    CK(cudaEventElapsedTime(&t.ms_total, ctx->ev[0], ctx->ev[2]));
-  } else if (mode == SONG_LOS_MODE_FAST) {
-    std::string e;
-    FastHostLayout h{};
-    h.has_T = c.has_source_T; h.has_E = c.has_source_E; h.has_B = c.has_source_B;
-    h.index_tt2_T = c.index_tt2_T; h.index_tt2_E = c.index_tt2_E; h.index_tt2_B = c.index_tt2_B;
-    h.index_tp2_T = c.index_tp2_T; h.index_tp2_E = c.index_tp2_E; h.index_tp2_B = c.index_tp2_B;
-    h.index_J_TT = c.index_J_TT; h.index_J_EE = c.index_J_EE; h.index_J_EB = c.index_J_EB;
-    h.l_max_los_t = c.l_max_los_t; h.l_max_los_p = c.l_max_los_p;
-    h.l_size = c.l_size; h.m_size = c.m_size; h.L_size = c.L_size; h.n_transfers = c.n_transfers;
-    h.xx_size = c.xx_size; h.l = c.l; h.m = c.m; h.lm_array = c.lm_array; h.lm_src = c.lm_src;
-    h.block_nonzero = ctx->h_block_nonzero.data(); h.n_src_total = ctx->hb.n_src_total;
-    h.tau_size = c.tau_size; h.n_pt_total = ctx->hb.n_pt_total;
-    if (fast_compute(ctx->fast, h, P, ctx->h_unit_pair.data(), ctx->sm_count, st, &t, e) != 0)
-      return ctx_fail(ctx, "%s", e.c_str());
-  } else {
-    return ctx_fail(ctx, "song_los_compute: unknown mode %d", mode);
-  }
-  if (check_device_errors(ctx) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
-  ctx->have_result = true;
-  if (tm) *tm = t;
+  if (ctx->n_in_flight) return ctx_fail(ctx, "song_los_compute: %d submitted batches are still in flight; call song_los_wait first", ctx->n_in_flight);
+  song_los_ctx::Slot &S = ctx->slot[ctx->cur];
+  if (enqueue_compute(ctx, S, mode) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
+  if (finish_compute(ctx, S) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
+  if (tm) *tm = S.t;
   return SONG_LOS_SUCCESS;
 }
 
@@ -492,36 +596,123 @@ extern "C" int song_los_download(song_los_ctx *ctx, double *transfer)
 {
   if (!ctx || !transfer) return ctx_fail(ctx, "song_los_download: NULL argument");
   CK(cudaSetDevice(ctx->device));
-  if (!ctx->have_result) return ctx_fail(ctx, "song_los_download: nothing computed yet");
-  size_t n = (size_t)ctx->hb.n_units * ctx->cfg.tt2_size;
-  CK(cudaMemcpyAsync(transfer, ctx->d_out.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  song_los_ctx::Slot &S = ctx->slot[ctx->cur];
+  if (!S.have_result) return ctx_fail(ctx, "song_los_download: nothing computed yet");
+  if (enqueue_download(ctx, S, transfer) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
+  CK(cudaEventSynchronize(S.ev_d2h));
+  return SONG_LOS_SUCCESS;
+}
+
+// Asynchronous path: enqueue upload, kernels and download of one batch and return.  Up to three batches
+// may be in flight; they complete in submission order through song_los_wait.
+extern "C" int song_los_submit(song_los_ctx *ctx, const song_los_batch *batch, int mode, double *transfer)
+{
+  if (!ctx || !batch || !transfer) return ctx_fail(ctx, "song_los_submit: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->n_in_flight >= song_los_ctx::N_SLOTS)
+    return ctx_fail(ctx, "song_los_submit: %d batches already in flight; call song_los_wait first", ctx->n_in_flight);
+  const int is = (ctx->n_in_flight == 0) ? ctx->cur : (ctx->cur + 1) % song_los_ctx::N_SLOTS;
+  song_los_ctx::Slot &S = ctx->slot[is];
+  if (enqueue_upload(ctx, S, batch) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
+  if (enqueue_compute(ctx, S, mode) != SONG_LOS_SUCCESS) { cudaDeviceSynchronize(); return SONG_LOS_FAILURE; }
+  if (enqueue_download(ctx, S, transfer) != SONG_LOS_SUCCESS) { cudaDeviceSynchronize(); return SONG_LOS_FAILURE; }
+  S.in_flight = true;
+  if (ctx->n_in_flight == 0) ctx->oldest = is;
+  ctx->n_in_flight++;
+  ctx->cur = is;
+  return SONG_LOS_SUCCESS;
+}
+
+extern "C" int song_los_wait(song_los_ctx *ctx, song_los_timing *tm)
+{
+  if (!ctx) return SONG_LOS_FAILURE;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->n_in_flight == 0) return ctx_fail(ctx, "song_los_wait: nothing submitted");
+  song_los_ctx::Slot &S = ctx->slot[ctx->oldest];
+  S.in_flight = false;
+  ctx->n_in_flight--;
+  ctx->oldest = (ctx->oldest + 1) % song_los_ctx::N_SLOTS;
+  if (finish_compute(ctx, S) != SONG_LOS_SUCCESS) { cudaDeviceSynchronize(); return SONG_LOS_FAILURE; }
+  CK(cudaEventSynchronize(S.ev_d2h));
+  CK(cudaEventElapsedTime(&S.t.ms_d2h, S.ev_d2h_start, S.ev_d2h));
+  if (tm) *tm = S.t;
   return SONG_LOS_SUCCESS;
 }
 
 extern "C" int song_los_transfer_pairs(song_los_ctx *ctx, const song_los_batch *batch, int mode,
                                        double *transfer, song_los_timing *timing)
 {
-  if (song_los_upload_pairs(ctx, batch) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
-  if (song_los_compute(ctx, mode, timing) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
-  return song_los_download(ctx, transfer);
+  if (ctx && ctx->n_in_flight) return ctx_fail(ctx, "song_los_transfer_pairs: submitted batches are still in flight; call song_los_wait first");
+  if (song_los_submit(ctx, batch, mode, transfer) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
+  return song_los_wait(ctx, timing);
+}
+
+// Pinned host memory for the batch inputs and the result: copies from/to it run asynchronously at
+// full PCIe rate, pageable memory works too but serialises the copies with the host.
+extern "C" int song_los_host_alloc(void **ptr, size_t bytes)
+{
+  if (!ptr) return SONG_LOS_FAILURE;
+  *ptr = nullptr;
+  cudaError_t e = cudaHostAlloc(ptr, std::max<size_t>(bytes, 1), cudaHostAllocPortable);
+  if (e != cudaSuccess) { ctx_fail(nullptr, "song_los_host_alloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e)); *ptr = nullptr; return SONG_LOS_FAILURE; }
+  return SONG_LOS_SUCCESS;
+}
+
+extern "C" int song_los_host_free(void *ptr)
+{
+  if (ptr && cudaFreeHost(ptr) != cudaSuccess) return SONG_LOS_FAILURE;
+  return SONG_LOS_SUCCESS;
+}
+
+// Largest number of k3 values one batch may hold so that three batches in flight plus the intermediates
+// of one compute fit in the free device memory (with a 10% margin).  per-unit bytes: result rows and
+// fine grid of two slots + FAST intermediates; sources are accounted with the caller's ratio.
+extern "C" int song_los_max_batch_units(song_los_ctx *ctx, int mode, double src_doubles_per_unit, int64_t *units)
+{
+  if (!ctx || !units) return ctx_fail(ctx, "song_los_max_batch_units: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->have_proj) return ctx_fail(ctx, "song_los_max_batch_units: projection functions not set");
+  const song_los_config &c = ctx->cfg;
+  size_t fr = 0, tot = 0;
+  CK(cudaMemGetInfo(&fr, &tot));
+  // memory already held by the batch buffers is reusable
+  size_t held = 0;
+  for (auto &S : ctx->slot) held += (S.d_k3_pt.cap + S.d_k3_tr.cap + S.d_src.cap + S.d_out.cap) * 8 + S.d_tiles.cap * 8;
+  held += ctx->d_dd.cap * 8;
+  double per_unit = (double)song_los_ctx::N_SLOTS * (8.0 * c.tt2_size + 8.0 + 8.0 * src_doubles_per_unit);
+  if (mode == SONG_LOS_MODE_FAST) {
+    std::string e;
+    song_los_ctx::Slot dummy;
+    ExactParams P; fill_params(ctx, dummy, P);
+    FastHostLayout h; fill_fast_layout(ctx, dummy, h);
+    if (fast_prepare(ctx->fast, h, P, ctx->stream, e) != 0) return ctx_fail(ctx, "%s", e.c_str());
+    size_t fr2 = 0; CK(cudaMemGetInfo(&fr2, &tot)); fr = fr2;
+    per_unit += (double)fast_bytes_per_unit(ctx->fast) + 16.0 * src_doubles_per_unit;   // S, sort arrays, {y,dd} sources
+  } else {
+    per_unit += 8.0 * src_doubles_per_unit + 8.0 / EXACT_UNITS_PER_CTA;                 // dd, tiles
+  }
+  double budget = 0.90 * ((double)fr + (double)held);
+  int64_t u = (int64_t)(budget / per_unit);
+  *units = std::max<int64_t>(1, std::min<int64_t>(u, ((int64_t)1 << 31) - 1));
+  return SONG_LOS_SUCCESS;
 }
 
 extern "C" uint64_t song_los_device_result(song_los_ctx *ctx, int64_t *n_doubles)
 {
-  if (!ctx || !ctx->have_result) { if (n_doubles) *n_doubles = 0; return 0; }
-  if (n_doubles) *n_doubles = ctx->hb.n_units * ctx->cfg.tt2_size;
-  return (uint64_t)(uintptr_t)ctx->d_out.p;
+  if (!ctx || !ctx->slot[ctx->cur].have_result) { if (n_doubles) *n_doubles = 0; return 0; }
+  if (n_doubles) *n_doubles = ctx->slot[ctx->cur].hb.n_units * ctx->cfg.tt2_size;
+  return (uint64_t)(uintptr_t)ctx->slot[ctx->cur].d_out.p;
 }
 
 extern "C" int song_los_copy_result(song_los_ctx *ctx, uint64_t device_dst, int64_t n_doubles)
 {
   if (!ctx || !device_dst) return ctx_fail(ctx, "song_los_copy_result: NULL argument");
   CK(cudaSetDevice(ctx->device));
-  if (!ctx->have_result) return ctx_fail(ctx, "song_los_copy_result: nothing computed yet");
-  int64_t n = ctx->hb.n_units * ctx->cfg.tt2_size;
+  song_los_ctx::Slot &S = ctx->slot[ctx->cur];
+  if (!S.have_result) return ctx_fail(ctx, "song_los_copy_result: nothing computed yet");
+  int64_t n = S.hb.n_units * ctx->cfg.tt2_size;
   if (n_doubles != n) return ctx_fail(ctx, "song_los_copy_result: expected %lld doubles, got %lld", (long long)n, (long long)n_doubles);
-  CK(cudaMemcpyAsync((void *)(uintptr_t)device_dst, ctx->d_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync((void *)(uintptr_t)device_dst, S.d_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return SONG_LOS_SUCCESS;
 }

@@ -46,18 +46,31 @@ struct song_los_ctx {
   DevBuf<double> d_ragged; DevBuf<int64_t> d_col_off; DevBuf<int> d_col_xmin, d_col_xsize;
   std::vector<int> h_col_xmin, h_col_xsize; std::vector<int64_t> h_col_off;
 
-  // batch
-  song_los_batch hb{};          // scalar fields only are valid
-  std::vector<int> h_np, h_nt, h_unit_pair;
-  std::vector<int64_t> h_tr_off;
+  // batches: three slots, so that the host->device copy of one batch and the device->host copy of
+  // another overlap the kernels of a third stage (song_los_submit / song_los_wait)
+  struct Slot {
+    song_los_batch hb{};          // scalar fields only are valid
+    unsigned char *h_meta = nullptr; size_t h_meta_cap = 0;     // pinned staging of the per-pair arrays
+    DevBuf<unsigned char> d_meta;                               // packed per-pair arrays on the device
+    int *d_np = nullptr, *d_nt = nullptr, *d_phys_start = nullptr, *d_phys_size = nullptr, *d_tile_off = nullptr;
+    int64_t *d_pt_off = nullptr, *d_tr_off = nullptr, *d_src_off = nullptr;
+    DevBuf<double> d_k3_pt, d_k3_tr, d_src, d_out;
+    DevBuf<int2> d_tiles; int n_tiles = 0; bool tiles_ready = false;
+    cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr, ev_h2d_start = nullptr, ev_d2h_start = nullptr;
+    cudaEvent_t ev_t[6]{};        // phase boundaries of this slot's compute
+    int *h_err = nullptr;         // pinned copy of the device error flags after this slot's compute
+    bool have_batch = false, have_result = false, in_flight = false, fast_timed = false, with_d2h = false;
+    song_los_timing t{};
+  };
+  static constexpr int N_SLOTS = 3;
+  Slot slot[N_SLOTS];
+  int cur = 0;                    // slot of the synchronous upload/compute/download calls and of the last submit
+  int n_in_flight = 0, oldest = 0;
+  cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
   std::vector<unsigned char> h_block_nonzero;
-  DevBuf<int> d_np, d_nt, d_phys_start, d_phys_size;
-  DevBuf<int64_t> d_pt_off, d_tr_off, d_src_off;
-  DevBuf<double> d_k3_pt, d_k3_tr, d_src, d_dd, d_out;
-  DevBuf<int2> d_tiles; int n_tiles = 0;
+  DevBuf<double> d_dd;
   DevBuf<int> d_err;
   DevBuf<double> d_scratch;
-  bool have_batch = false, have_result = false;
 
   songlos::FastState *fast = nullptr;
   // device-built projection functions (song_los_build_projection)

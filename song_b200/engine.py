@@ -40,6 +40,28 @@ class Projection:
         return self._ptrs(self.ddrows) if self.ddrows is not None else None
 
 
+class PinnedArray:
+    """A numpy view of page-locked host memory from song_los_host_alloc (freed with the object)."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.lib = _lib.los()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = C.c_void_p()
+        if self.lib.song_los_host_alloc(C.byref(self.ptr), n):
+            raise _lib.SongLosError(self.lib.song_los_last_error(None).decode())
+        buf = (C.c_char * max(n, 1)).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.array = None
+                self.lib.song_los_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
 class LosEngine:
     """One engine per GPU.  Fails loudly when the CUDA library or a device is missing."""
 
@@ -121,6 +143,29 @@ class LosEngine:
         self._check(self.lib.song_los_transfer_pairs(self.ctx, C.byref(b), mode, _lib.dptr(out), C.byref(self.timing)))
         self.n_units = wl.n_units
         return out
+
+    # -- asynchronous pipeline (song_los_submit / song_los_wait) ------------------------------
+    def submit(self, wl: Workload, mode: int, out: np.ndarray):
+        """Enqueue upload + kernels + download of `wl`; `wl`'s arrays and `out` must stay alive (and
+        should be pinned, see :class:`PinnedArray`) until the matching :meth:`wait` returns."""
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == self.tt2_size * wl.n_units
+        b = make_batch(wl)
+        self._inflight = getattr(self, "_inflight", [])
+        self._inflight.append((b, wl, out))
+        self._check(self.lib.song_los_submit(self.ctx, C.byref(b), mode, _lib.dptr(out)))
+        self.n_units = wl.n_units
+
+    def wait(self) -> dict:
+        """Block until the oldest submitted batch is complete; returns its timing."""
+        self._check(self.lib.song_los_wait(self.ctx, C.byref(self.timing)))
+        if getattr(self, "_inflight", None):
+            self._inflight.pop(0)
+        return self.timing.as_dict()
+
+    def max_batch_units(self, mode: int, src_doubles_per_unit: float) -> int:
+        n = C.c_int64(0)
+        self._check(self.lib.song_los_max_batch_units(self.ctx, mode, float(src_doubles_per_unit), C.byref(n)))
+        return int(n.value)
 
     def set_stream(self, cuda_stream: int | None):
         self._check(self.lib.song_los_set_stream(self.ctx, C.c_void_p(cuda_stream or 0)))

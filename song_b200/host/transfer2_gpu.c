@@ -13,8 +13,10 @@
  * (transfer2.c:705-763, 2929-2963: raw doubles, [k1][k2][k3] per transfer type).
  *
  * Batching: the reference handles one (k1,k2) pair at a time; here consecutive k1 levels are packed into one GPU
- * batch (SONG_LOS_BATCH_UNITS k3 values, default 2e6) because the tensor-core kernel wants many k3 values per
- * table row.  Side effects keep the reference's per-k1 order: sources of a k1 level are loaded before and freed
+ * batch (SONG_LOS_BATCH_UNITS k3 values; default: about three batches per GPU, at least 4e5 k3 values, at most
+ * what song_los_max_batch_units says fits in device memory) because the tensor-core kernel wants many k3 values
+ * per table row.  Batches of a GPU run as a three-deep pipeline (song_los_submit / song_los_wait) through page-locked
+ * staging, so that the copies of neighbouring batches overlap the kernels.  Side effects keep the reference's per-k1 order: sources of a k1 level are loaded before and freed
  * after use (transfer2.c:332-344, 553), transfers are stored and freed per k1 (transfer2.c:559-567).
  * With several visible GPUs and nothing to write to disk, batches are distributed over one host thread per GPU
  * (static longest-processing-time schedule on the number of k3 values); the results land directly in
@@ -471,71 +473,116 @@ static int create_engine(struct precision *ppr, struct precision2 *ppr2, struct 
 /* one GPU batch = the k1 levels [k1_first, k1_last] */
 typedef struct { int k1_first, k1_last; long n_units; int device; } los_k1_batch;
 
-static int run_batch(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2, struct bessels *pbs,
-                     struct bessels2 *pbs2, struct transfers2 *ptr2, song_los_ctx *ctx, int mode, const los_k1_batch *kb,
-                     char *errmsg)
+/* Page-locked staging of one batch in flight (song_los_host_alloc): the packed inputs the C-ABI reads
+   and the [tt2_size][n_units] result it writes.  SONG_LOS_MAX_IN_FLIGHT of these per GPU, used in turn. */
+typedef struct {
+  int *np, *nt, *ps, *pz; int64_t *pt_off, *tr_off, *src_off;
+  double *k3_pt, *k3_tr, *src, *out;
+  int n_pairs; int64_t n_pt, n_units, n_src;
+  const los_k1_batch *kb;          /* NULL when the staging is free */
+} los_staging;
+
+static void staging_free(los_staging *s)
 {
-  const int tp2 = ppt2->tp2_size, ntau = ppt2->tau_size;
-  int n_pairs = 0;
-  int64_t n_pt = 0, n_units = 0, n_src = 0;
+  song_los_host_free(s->np); song_los_host_free(s->nt); song_los_host_free(s->ps); song_los_host_free(s->pz);
+  song_los_host_free(s->pt_off); song_los_host_free(s->tr_off); song_los_host_free(s->src_off);
+  song_los_host_free(s->k3_pt); song_los_host_free(s->k3_tr); song_los_host_free(s->src); song_los_host_free(s->out);
+  memset(s, 0, sizeof *s);
+}
+
+/* capacity of the largest batch of a device */
+static int staging_alloc(los_staging *s, int max_pairs, int64_t max_pt, int64_t max_units, int64_t max_src, int tt2_size)
+{
+  memset(s, 0, sizeof *s);
+  int rc = 0;
+  rc |= song_los_host_alloc((void **)&s->np, sizeof(int) * (size_t)max_pairs);
+  rc |= song_los_host_alloc((void **)&s->nt, sizeof(int) * (size_t)max_pairs);
+  rc |= song_los_host_alloc((void **)&s->ps, sizeof(int) * (size_t)max_pairs);
+  rc |= song_los_host_alloc((void **)&s->pz, sizeof(int) * (size_t)max_pairs);
+  rc |= song_los_host_alloc((void **)&s->pt_off, sizeof(int64_t) * (size_t)max_pairs);
+  rc |= song_los_host_alloc((void **)&s->tr_off, sizeof(int64_t) * (size_t)max_pairs);
+  rc |= song_los_host_alloc((void **)&s->src_off, sizeof(int64_t) * (size_t)max_pairs);
+  rc |= song_los_host_alloc((void **)&s->k3_pt, sizeof(double) * (size_t)max_pt);
+  rc |= song_los_host_alloc((void **)&s->k3_tr, sizeof(double) * (size_t)max_units);
+  rc |= song_los_host_alloc((void **)&s->src, sizeof(double) * (size_t)max_src);
+  rc |= song_los_host_alloc((void **)&s->out, sizeof(double) * (size_t)max_units * tt2_size);
+  if (rc != SONG_LOS_SUCCESS) { staging_free(s); return _FAILURE_; }
+  return _SUCCESS_;
+}
+
+static void batch_sizes(struct perturbs2 *ppt2, struct transfers2 *ptr2, const los_k1_batch *kb,
+                        int *n_pairs, int64_t *n_pt, int64_t *n_units, int64_t *n_src)
+{
+  *n_pairs = 0; *n_pt = 0; *n_units = 0; *n_src = 0;
   for (int k1 = kb->k1_first; k1 <= kb->k1_last; ++k1)
     for (int k2 = 0; k2 <= k1; ++k2) {
-      ++n_pairs; n_pt += ppt2->k3_size[k1][k2]; n_units += ptr2->k_size_k1k2[k1][k2];
-      n_src += (int64_t)tp2 * ntau * ppt2->k3_size[k1][k2];
+      ++*n_pairs; *n_pt += ppt2->k3_size[k1][k2]; *n_units += ptr2->k_size_k1k2[k1][k2];
+      *n_src += (int64_t)ppt2->tp2_size * ppt2->tau_size * ppt2->k3_size[k1][k2];
     }
-  int *np = malloc(sizeof(int) * n_pairs), *nt = malloc(sizeof(int) * n_pairs);
-  int *ps = malloc(sizeof(int) * n_pairs), *pz = malloc(sizeof(int) * n_pairs);
-  int64_t *pt_off = malloc(sizeof(int64_t) * n_pairs), *tr_off = malloc(sizeof(int64_t) * n_pairs), *src_off = malloc(sizeof(int64_t) * n_pairs);
-  double *k3_pt = malloc(sizeof(double) * (size_t)n_pt), *k3_tr = malloc(sizeof(double) * (size_t)n_units);
-  double *src = malloc(sizeof(double) * (size_t)n_src), *out = malloc(sizeof(double) * (size_t)n_units * ptr2->tt2_size);
-  int failed = 0;
-  if (!np || !nt || !ps || !pz || !pt_off || !tr_off || !src_off || !k3_pt || !k3_tr || !src || !out) {
-    snprintf(errmsg, _ERRORMSGSIZE_, "could not allocate the staging buffers of a GPU batch (%ld k3 values)", (long)n_units);
-    failed = 1;
-  }
+}
+
+/* packs the k1 levels of `kb` into the staging and enqueues the batch on the GPU (song_los_submit) */
+static int submit_batch(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2, struct bessels *pbs,
+                        struct bessels2 *pbs2, struct transfers2 *ptr2, song_los_ctx *ctx, int mode, const los_k1_batch *kb,
+                        los_staging *s, char *errmsg)
+{
+  const int tp2 = ppt2->tp2_size, ntau = ppt2->tau_size;
+  batch_sizes(ppt2, ptr2, kb, &s->n_pairs, &s->n_pt, &s->n_units, &s->n_src);
   int p = 0;
   int64_t o_pt = 0, o_tr = 0, o_src = 0;
-  for (int k1 = kb->k1_first; !failed && k1 <= kb->k1_last; ++k1)
-    for (int k2 = 0; !failed && k2 <= k1; ++k2, ++p) {
-      np[p] = ppt2->k3_size[k1][k2]; nt[p] = ptr2->k_size_k1k2[k1][k2];
-      ps[p] = ptr2->k_physical_start_k1k2[k1][k2]; pz[p] = ptr2->k_physical_size_k1k2[k1][k2];
-      pt_off[p] = o_pt; tr_off[p] = o_tr; src_off[p] = o_src;
-      memcpy(k3_pt + o_pt, ppt2->k3[k1][k2], sizeof(double) * np[p]);
-      if (transfer2_get_k3_list(ppr, ppr2, ppt2, pbs, pbs2, ptr2, k1, k2, k3_tr + o_tr, NULL) == _FAILURE_) {
-        snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); failed = 1; break;
+  for (int k1 = kb->k1_first; k1 <= kb->k1_last; ++k1)
+    for (int k2 = 0; k2 <= k1; ++k2, ++p) {
+      s->np[p] = ppt2->k3_size[k1][k2]; s->nt[p] = ptr2->k_size_k1k2[k1][k2];
+      s->ps[p] = ptr2->k_physical_start_k1k2[k1][k2]; s->pz[p] = ptr2->k_physical_size_k1k2[k1][k2];
+      s->pt_off[p] = o_pt; s->tr_off[p] = o_tr; s->src_off[p] = o_src;
+      memcpy(s->k3_pt + o_pt, ppt2->k3[k1][k2], sizeof(double) * s->np[p]);
+      if (transfer2_get_k3_list(ppr, ppr2, ppt2, pbs, pbs2, ptr2, k1, k2, s->k3_tr + o_tr, NULL) == _FAILURE_) {
+        snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); return _FAILURE_;
       }
       /* ppt2->sources[tp][k1][k2][tau*k3_size + k3] (transfer2.h:47-51) -> packed [pair][tp][tau][k3] */
       for (int tp = 0; tp < tp2; ++tp)
-        memcpy(src + o_src + (int64_t)tp * ntau * np[p], ppt2->sources[tp][k1][k2], sizeof(double) * (size_t)ntau * np[p]);
-      o_pt += np[p]; o_tr += nt[p]; o_src += (int64_t)tp2 * ntau * np[p];
+        memcpy(s->src + o_src + (int64_t)tp * ntau * s->np[p], ppt2->sources[tp][k1][k2], sizeof(double) * (size_t)ntau * s->np[p]);
+      o_pt += s->np[p]; o_tr += s->nt[p]; o_src += (int64_t)tp2 * ntau * s->np[p];
     }
-  if (!failed) {
-    song_los_batch b;
-    memset(&b, 0, sizeof b);
-    b.n_pairs = n_pairs; b.k3_pt_size = np; b.k3_tr_size = nt; b.phys_start = ps; b.phys_size = pz;
-    b.pt_off = pt_off; b.tr_off = tr_off; b.src_off = src_off;
-    b.n_pt_total = n_pt; b.n_units = n_units; b.n_src_total = n_src;
-    b.k3_pt = k3_pt; b.k3_tr = k3_tr; b.src = src;
-    if (song_los_transfer_pairs(ctx, &b, mode, out, NULL) != SONG_LOS_SUCCESS) {
-      snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(ctx)); failed = 1;
-    }
+  song_los_batch b;
+  memset(&b, 0, sizeof b);
+  b.n_pairs = s->n_pairs; b.k3_pt_size = s->np; b.k3_tr_size = s->nt; b.phys_start = s->ps; b.phys_size = s->pz;
+  b.pt_off = s->pt_off; b.tr_off = s->tr_off; b.src_off = s->src_off;
+  b.n_pt_total = s->n_pt; b.n_units = s->n_units; b.n_src_total = s->n_src;
+  b.k3_pt = s->k3_pt; b.k3_tr = s->k3_tr; b.src = s->src;
+  if (song_los_submit(ctx, &b, mode, s->out) != SONG_LOS_SUCCESS) {
+    snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(ctx)); return _FAILURE_;
   }
-  if (!failed) {
-    /* out is [tt2_size][n_units]: scatter the rows into ptr2->transfer[tt][k1][k2][k3] (transfer2.c:2107) */
-    p = 0;
-    long stored = 0;
+  s->kb = kb;
+  return _SUCCESS_;
+}
+
+/* waits for the oldest batch in flight and scatters its result into ptr2->transfer[tt][k1][k2][k3]
+   (transfer2.c:2107), then applies the per-k1 side effects of transfer2.c:559-567 */
+static int finish_batch(struct precision2 *ppr2, struct perturbs2 *ppt2, struct transfers2 *ptr2, song_los_ctx *ctx,
+                        los_staging *s, char *errmsg)
+{
+  const los_k1_batch *kb = s->kb;
+  s->kb = NULL;
+  if (song_los_wait(ctx, NULL) != SONG_LOS_SUCCESS) {
+    snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(ctx)); return _FAILURE_;
+  }
+  int p = 0;
+  long stored = 0;
+  for (int k1 = kb->k1_first; k1 <= kb->k1_last; ++k1)
+    for (int k2 = 0; k2 <= k1; ++k2, ++p)
+      for (int tt = 0; tt < ptr2->tt2_size; ++tt) {
+        memcpy(ptr2->transfer[tt][k1][k2], s->out + (int64_t)tt * s->n_units + s->tr_off[p], sizeof(double) * s->nt[p]);
+        stored += s->nt[p];
+      }
+  #pragma omp atomic
+  ptr2->count_memorised_transfers += stored;                                    /* transfer2.c:2110-2111 */
+  if (ppr2->store_transfers_to_disk == _TRUE_)                                  /* :559-567, in k1 order */
     for (int k1 = kb->k1_first; k1 <= kb->k1_last; ++k1)
-      for (int k2 = 0; k2 <= k1; ++k2, ++p)
-        for (int tt = 0; tt < ptr2->tt2_size; ++tt) {
-          memcpy(ptr2->transfer[tt][k1][k2], out + (int64_t)tt * n_units + tr_off[p], sizeof(double) * nt[p]);
-          stored += nt[p];
-        }
-    #pragma omp atomic
-    ptr2->count_memorised_transfers += stored;                                    /* transfer2.c:2110-2111 */
-  }
-  free(np); free(nt); free(ps); free(pz); free(pt_off); free(tr_off); free(src_off);
-  free(k3_pt); free(k3_tr); free(src); free(out);
-  return failed ? _FAILURE_ : _SUCCESS_;
+      if (transfer2_store_transfers_to_disk(ppt2, ptr2, k1) == _FAILURE_ || transfer2_free_k1_level(ppt2, ptr2, k1) == _FAILURE_) {
+        snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); return _FAILURE_;
+      }
+  return _SUCCESS_;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -574,8 +621,35 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   if ((mode_env && strcmp(mode_env, "exact") == 0) || (ppr->bessels_interpolation == cubic_interpolation))
     mode = SONG_LOS_MODE_EXACT;
 
-  /* k1 batches */
-  const long batch_units = (long)env_int("SONG_LOS_BATCH_UNITS", 2000000);
+  /* devices: one host thread per GPU when nothing has to be written in k1 order */
+  const int sources_on_disk = (ppr2->load_sources_from_disk == _TRUE_) || (ppr2->store_sources_to_disk == _TRUE_);
+  const int ordered = sources_on_disk || (ppr2->store_transfers_to_disk == _TRUE_);
+  int n_dev = env_int("SONG_LOS_DEVICES", 0);
+  if (n_dev <= 0) n_dev = 64;          /* probe: engines are created on devices 0,1,... until creation fails */
+  if (ordered) n_dev = 1;
+  los_device *dev;
+  class_calloc(dev, n_dev, sizeof(los_device), ptr2->error_message);
+  if (create_engine(ppr, ppr2, ppt2, pbs2, ptr2, 0, &dev[0].ctx) == _FAILURE_) { free(dev); return _FAILURE_; }   /* no usable GPU: there is no CPU fallback */
+
+  /* k1 batches: consecutive k1 levels up to `batch_units` k3 values.  Large batches make the tensor-core kernel
+     efficient (many k3 per table row); several batches per GPU let the copies overlap the kernels; the upper
+     bound is what fits in device memory twice (two batches in flight). */
+  long total_units = 0, total_pt = 0;
+  for (int k1 = 0; k1 < ppt2->k_size; ++k1)
+    for (int k2 = 0; k2 <= k1; ++k2) { total_units += ptr2->k_size_k1k2[k1][k2]; total_pt += ppt2->k3_size[k1][k2]; }
+  int64_t cap_units = 0;
+  if (song_los_max_batch_units(dev[0].ctx, mode, (double)ppt2->tp2_size * ppt2->tau_size * (double)total_pt / (double)(total_units > 0 ? total_units : 1),
+                               &cap_units) != SONG_LOS_SUCCESS) {
+    snprintf(ptr2->error_message, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(dev[0].ctx));
+    song_los_destroy(dev[0].ctx); free(dev); return _FAILURE_;
+  }
+  long batch_units = (long)env_int("SONG_LOS_BATCH_UNITS", 0);
+  if (batch_units <= 0) {
+    int n_dev_guess = ordered ? 1 : env_int("SONG_LOS_DEVICES", 1);
+    batch_units = total_units / (3 * (n_dev_guess > 0 ? n_dev_guess : 1));       /* about three batches per GPU ... */
+    if (batch_units < 400000) batch_units = 400000;                              /* ... but not below 4e5 k3 values */
+  }
+  if (batch_units > (long)cap_units) batch_units = (long)cap_units;
   los_k1_batch *batches;
   class_alloc(batches, ppt2->k_size * sizeof(los_k1_batch), ptr2->error_message);
   int n_batches = 0;
@@ -590,29 +664,16 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
     batches[n_batches++] = kb;
   }
 
-  /* devices: one host thread per GPU when nothing has to be written in k1 order */
-  const int sources_on_disk = (ppr2->load_sources_from_disk == _TRUE_) || (ppr2->store_sources_to_disk == _TRUE_);
-  const int ordered = sources_on_disk || (ppr2->store_transfers_to_disk == _TRUE_);
-  int n_dev = env_int("SONG_LOS_DEVICES", 0);
-  if (n_dev <= 0) {
-    /* probe: engines are created on devices 0,1,... until creation fails */
-    n_dev = 64;
-  }
-  if (ordered) n_dev = 1;
   if (n_dev > n_batches) n_dev = n_batches > 0 ? n_batches : 1;
-  los_device *dev;
-  class_calloc(dev, n_dev, sizeof(los_device), ptr2->error_message);
-  int n_created = 0;
-  for (int d = 0; d < n_dev; ++d) {
-    if (create_engine(ppr, ppr2, ppt2, pbs2, ptr2, d, &dev[d].ctx) == _FAILURE_) {
-      if (d == 0) { free(dev); free(batches); return _FAILURE_; }   /* no usable GPU: there is no CPU fallback */
-      break;
-    }
+  int n_created = 1;
+  for (int d = 1; d < n_dev; ++d) {
+    if (create_engine(ppr, ppr2, ppt2, pbs2, ptr2, d, &dev[d].ctx) == _FAILURE_) break;
     dev[d].device = d; ++n_created;
   }
   n_dev = n_created;
   if (ptr2->transfer2_verbose > 0)
-    printf(" -> %d k1 batches on %d GPU(s), %s arithmetic\n", n_batches, n_dev, mode == SONG_LOS_MODE_FAST ? "tensor-core" : "reference-order");
+    printf(" -> %d k1 batches (up to %ld k3 values each) on %d GPU(s), %s arithmetic\n", n_batches, batch_units, n_dev,
+           mode == SONG_LOS_MODE_FAST ? "tensor-core" : "reference-order");
 
   /* static longest-processing-time schedule: batches by decreasing size to the least loaded device */
   {
@@ -629,16 +690,40 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
     free(load); free(order);
   }
 
+  /* Per GPU: a pipeline of up to SONG_LOS_MAX_IN_FLIGHT batches (in k1 order).  While the kernels of batch n run, the host
+     packs batch n+1 into the other staging and submits it (its host->device copy overlaps), and the result of
+     batch n-1 travels back and is scattered into ptr2->transfer. */
   int abort_flag = _FALSE_;
   ErrorMsg first_error = "";
   #pragma omp parallel for num_threads(n_dev) schedule(static, 1) if (n_dev > 1)
   for (int d = 0; d < n_dev; ++d) {
     ErrorMsg local = "";
+    int ok = _TRUE_;
+    /* staging sized for the largest batch of this device */
+    int max_pairs = 1; int64_t max_pt = 1, max_units = 1, max_src = 1;
     for (int ib = 0; ib < n_batches; ++ib) {
+      if (batches[ib].device != d) continue;
+      int np_; int64_t a, b, c;
+      batch_sizes(ppt2, ptr2, &batches[ib], &np_, &a, &b, &c);
+      if (np_ > max_pairs) max_pairs = np_;
+      if (a > max_pt) max_pt = a;
+      if (b > max_units) max_units = b;
+      if (c > max_src) max_src = c;
+    }
+    enum { DEPTH = SONG_LOS_MAX_IN_FLIGHT };
+    los_staging stg[DEPTH];
+    memset(stg, 0, sizeof stg);
+    for (int i = 0; i < DEPTH && ok; ++i)
+      if (staging_alloc(&stg[i], max_pairs, max_pt, max_units, max_src, ptr2->tt2_size) == _FAILURE_) {
+        snprintf(local, _ERRORMSGSIZE_, "could not allocate the page-locked staging of a GPU batch (%ld k3 values): %.1000s",
+                 (long)max_units, song_los_last_error(NULL));
+        ok = _FALSE_;
+      }
+    int cur = 0, in_flight = 0;
+    for (int ib = 0; ok && ib < n_batches; ++ib) {
       if (batches[ib].device != d) continue;
       if (abort_flag == _TRUE_) break;
       const los_k1_batch *kb = &batches[ib];
-      int ok = _TRUE_;
       for (int k1 = kb->k1_first; ok && k1 <= kb->k1_last; ++k1) {
         if (ptr2->transfer2_verbose > 1)
           printf("     * computing transfer functions today for index_k1=%d of %d, k1=%g\n", k1, ppt2->k_size, ppt2->k[k1]);
@@ -649,20 +734,28 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
           }
         }
       }
-      if (ok && run_batch(ppr, ppr2, ppt2, pbs, pbs2, ptr2, dev[d].ctx, mode, kb, local) == _FAILURE_) ok = _FALSE_;
-      for (int k1 = kb->k1_first; ok && k1 <= kb->k1_last; ++k1) {
-        if (perturb2_free_k1_level(ppt2, k1) == _FAILURE_) { snprintf(local, _ERRORMSGSIZE_, "%.1500s", ppt2->error_message); ok = _FALSE_; break; }   /* :553 */
-        if (ppr2->store_transfers_to_disk == _TRUE_) {                                         /* :559-567 */
-          if (transfer2_store_transfers_to_disk(ppt2, ptr2, k1) == _FAILURE_ || transfer2_free_k1_level(ppt2, ptr2, k1) == _FAILURE_) {
-            snprintf(local, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); ok = _FALSE_; break;
-          }
-        }
+      /* the staging about to be reused must have been drained: at most DEPTH batches are in flight */
+      if (ok && stg[cur].kb != NULL) {
+        if (finish_batch(ppr2, ppt2, ptr2, dev[d].ctx, &stg[cur], local) == _FAILURE_) ok = _FALSE_;
+        --in_flight;
       }
-      if (!ok) {
-        #pragma omp critical
-        { if (abort_flag == _FALSE_) { abort_flag = _TRUE_; snprintf(first_error, _ERRORMSGSIZE_, "%s", local); } }
-        break;
-      }
+      if (ok && submit_batch(ppr, ppr2, ppt2, pbs, pbs2, ptr2, dev[d].ctx, mode, kb, &stg[cur], local) == _FAILURE_) ok = _FALSE_;
+      if (ok) { ++in_flight; cur = (cur + 1) % DEPTH; }
+      /* the sources of these k1 levels now live in the staging: free them as the reference does (:553) */
+      for (int k1 = kb->k1_first; ok && k1 <= kb->k1_last; ++k1)
+        if (perturb2_free_k1_level(ppt2, k1) == _FAILURE_) { snprintf(local, _ERRORMSGSIZE_, "%.1500s", ppt2->error_message); ok = _FALSE_; break; }
+    }
+    /* drain in submission order: stg[cur] holds the older batch */
+    for (int i = 0; i < DEPTH; ++i) {
+      los_staging *s = &stg[(cur + i) % DEPTH];
+      if (s->kb == NULL) continue;
+      if (ok) { if (finish_batch(ppr2, ppt2, ptr2, dev[d].ctx, s, local) == _FAILURE_) ok = _FALSE_; }
+      else { song_los_wait(dev[d].ctx, NULL); s->kb = NULL; }
+    }
+    for (int i = 0; i < DEPTH; ++i) staging_free(&stg[i]);
+    if (!ok) {
+      #pragma omp critical
+      { if (abort_flag == _FALSE_) { abort_flag = _TRUE_; snprintf(first_error, _ERRORMSGSIZE_, "%s", local); } }
     }
   }
   for (int d = 0; d < n_dev; ++d) song_los_destroy(dev[d].ctx);

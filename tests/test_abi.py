@@ -38,7 +38,7 @@ def test_host_library_exports_every_declared_symbol():
 def test_struct_sizes_match_the_header_layout():
     # natural alignment of the C structs, computed independently of ctypes
     assert C.sizeof(_lib.K3Range) == 8 + 8 + 4 + 4 + 4 + 4
-    assert C.sizeof(_lib.LosTiming) == 6 * 4 + 4 + 4 + 8 + 8
+    assert C.sizeof(_lib.LosTiming) == 6 * 4 + 4 + 4 + 8 + 8 + 4 + 4
     assert C.sizeof(_lib.LosBatch) == 8 + 7 * 8 + 3 * 8 + 3 * 8
 
 
