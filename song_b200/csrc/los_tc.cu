@@ -50,7 +50,7 @@ constexpr int TC_MAX_GROUPS = 12;         // (block, K chunk): one source slab a
 constexpr int TC_MAX_PASSES = 24;
 constexpr int TC_MAX_TERMS = 64;          // K terms of one block (2 per kc)
 constexpr int TC_KCS_MAX = 6;             // kc's (pairs of terms) per pipeline stage
-constexpr int TC_CONSUMERS = 256, TC_PRODUCERS = 32, TC_THREADS = TC_CONSUMERS + TC_PRODUCERS;
+// WM x WN consumer warps and NP producer warps are template parameters of the kernel
 constexpr int TC_MAX_STAGES = 8;
 
 struct TcBlock {
@@ -61,7 +61,7 @@ struct TcBlock {
 
 struct TcGroup {                          // K chunk q of a block: kc in [kc0, kc0 + kcs)
   int blk, kc0, kcs;
-  int tpp;                                // doubles per (unit, tau) row of the slab: 2*kcs padded to 4
+  int tpp;                                // doubles per (unit, tau) row of the slab: 2*kcs
   int64_t s_off;                          // offset of the slab inside the S buffer (doubles)
 };
 
@@ -85,11 +85,13 @@ struct TcParams {
   int tau_size;
   const double *tau0_minus_tau, *delta_tau, *xx;
   double inv_xx_step; int xx_size;
+  double xx_step; int xx_uniform;         // xx[i] == i * xx_step BIT FOR BIT (xx_step = the grid's own delta): no table read for a_J
+  int n_cols_total, cols_pad;             // columns of all blocks; padded to 32 (shared-memory copies)
   int n_stages, rmax;                     // ring depth, table rows per stage
   int hdr_bytes, a_bytes, b_row_bytes, stage_bytes;  // shared-memory geometry of one stage
   double *out; int64_t out_stride;        // [tt][n_units]
   int *err;
-  int dbg;                                // timing experiments only (results invalid): 4 = no MMAs
+  int dbg;                                // timing experiments only (results invalid): 4 = no MMAs, 8 = no source copies, 16 = no table copies
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -403,11 +405,25 @@ __device__ __forceinline__ TcStagePtrs tc_stage(unsigned char *stage0, int s, co
 // set before the DMMAs of kc are issued (ping-pong, no moves).
 
 // both 8-unit groups of the warp have units on this row
-template <int NACT, int NW>
+template <int NACT, int NW, bool PP>
 __device__ __forceinline__ void tc_mma_both(double (&acc0)[NW][2], double (&acc1)[NW][2],
                                             const double *a0p, const double *a1p, double w0, double w1,
                                             const double *bp, int kcs, int b_sb_stride)
 {
+  if constexpr (!PP) {
+    // single-buffered: with three or four warps per SM sub-partition the other warps cover the LDS latency
+    for (int kc = 0; kc < kcs; ++kc) {
+      const double x0 = w0 * a0p[2 * kc], x1 = w1 * a1p[2 * kc];
+      double bf[NACT];
+#pragma unroll
+      for (int j = 0; j < NACT; ++j) bf[j] = bp[(size_t)j * b_sb_stride + kc * 32];
+#pragma unroll
+      for (int j = 0; j < NACT; ++j) dmma884(acc0[j][0], acc0[j][1], x0, bf[j]);
+#pragma unroll
+      for (int j = 0; j < NACT; ++j) dmma884(acc1[j][0], acc1[j][1], x1, bf[j]);
+    }
+    return;
+  }
   double pa0, pa1, pb[NACT], qa0, qa1, qb[NACT];
 #define TC_LOAD(A0, A1, BF, KC) do { \
     A0 = a0p[2 * (KC)]; A1 = a1p[2 * (KC)]; \
@@ -430,10 +446,21 @@ __device__ __forceinline__ void tc_mma_both(double (&acc0)[NW][2], double (&acc1
 }
 
 // only one of the two groups has units on this row
-template <int NACT, int NW>
+template <int NACT, int NW, bool PP>
 __device__ __forceinline__ void tc_mma_one(double (&acc)[NW][2], const double *ap, double w,
                                            const double *bp, int kcs, int b_sb_stride)
 {
+  if constexpr (!PP) {
+    for (int kc = 0; kc < kcs; ++kc) {
+      const double x = w * ap[2 * kc];
+      double bf[NACT];
+#pragma unroll
+      for (int j = 0; j < NACT; ++j) bf[j] = bp[(size_t)j * b_sb_stride + kc * 32];
+#pragma unroll
+      for (int j = 0; j < NACT; ++j) dmma884(acc[j][0], acc[j][1], x, bf[j]);
+    }
+    return;
+  }
   double pa, pb[NACT], qa, qb[NACT];
 #define TC_LOAD(A0, BF, KC) do { \
     A0 = ap[2 * (KC)]; \
@@ -454,14 +481,14 @@ __device__ __forceinline__ void tc_mma_one(double (&acc)[NW][2], const double *a
 #undef TC_MMA
 }
 
-template <int NACT, int NW>
+template <int NACT, int NW, bool PP>
 __device__ __forceinline__ void tc_mma_row_smem(double (&acc0)[NW][2], double (&acc1)[NW][2],
                                                 const double *a0p, const double *a1p, double w0, double w1,
                                                 bool any0, bool any1, const double *bp, int kcs, int b_sb_stride)
 {
-  if (any0 && any1) tc_mma_both<NACT, NW>(acc0, acc1, a0p, a1p, w0, w1, bp, kcs, b_sb_stride);
-  else if (any0) tc_mma_one<NACT, NW>(acc0, a0p, w0, bp, kcs, b_sb_stride);
-  else tc_mma_one<NACT, NW>(acc1, a1p, w1, bp, kcs, b_sb_stride);
+  if (any0 && any1) tc_mma_both<NACT, NW, PP>(acc0, acc1, a0p, a1p, w0, w1, bp, kcs, b_sb_stride);
+  else if (any0) tc_mma_one<NACT, NW, PP>(acc0, a0p, w0, bp, kcs, b_sb_stride);
+  else tc_mma_one<NACT, NW, PP>(acc1, a1p, w1, bp, kcs, b_sb_stride);
 }
 
 // rows outside the staged window (sparse k3 regions): B fragments straight from the table in global
@@ -483,12 +510,50 @@ __device__ __forceinline__ void tc_mma_row_global(double (&acc0)[NW][2], double 
   }
 }
 
-template <int WM, int WN, int NW>
-__global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_constant__ TcParams P)
+// All table rows of one stage for one consumer warp.  The units of a tile are k3-sorted, so the row
+// index ix is non-decreasing with the unit: the rows of the warp's 16 units are [lo0, hi1] with group 0
+// covering [lo0, hi0] and group 1 [lo1, hi1] (all four read as shared-memory broadcasts, warp-uniform).
+// Dense k3 regions (a handful of rows per warp) step through the rows without any warp reduction or
+// vote; sparse regions (rows far apart) find the next occupied row with a reduction.
+constexpr int TC_DENSE_SPAN = 3;
+
+template <int NACT, int NW, bool PP>
+__device__ __forceinline__ void tc_stage_rows(double (&acc0)[NW][2], double (&acc1)[NW][2],
+                                              const double *a0p, const double *a1p, int ix0, int ix1, double cw0, double cw1,
+                                              int lo0, int hi0, int lo1, int hi1, int row_lo, int nrows,
+                                              const double *bs, int b_row_doubles, const double *bg, int64_t jq_row,
+                                              int kcs, int b_sb_stride)
+{
+  if (hi1 - lo0 <= TC_DENSE_SPAN) {
+    for (int v = lo0; v <= hi1; ++v) {
+      const bool any0 = (v <= hi0), any1 = (v >= lo1);
+      if (!any0 && !any1) continue;
+      const double w0 = (ix0 == v) ? cw0 : 0., w1 = (ix1 == v) ? cw1 : 0.;
+      const int rb = v - row_lo;
+      if (rb < nrows) tc_mma_row_smem<NACT, NW, PP>(acc0, acc1, a0p, a1p, w0, w1, any0, any1, bs + (size_t)rb * b_row_doubles, kcs, b_sb_stride);
+      else tc_mma_row_global<NW>(acc0, acc1, a0p, a1p, w0, w1, bg + (int64_t)v * jq_row, kcs, b_sb_stride, NACT);
+    }
+  } else {
+    int v = lo0;
+    while (v != 0x7fffffff) {
+      const bool m0 = (ix0 == v), m1 = (ix1 == v);
+      const double w0 = m0 ? cw0 : 0., w1 = m1 ? cw1 : 0.;
+      const int rb = v - row_lo;
+      if (rb < nrows) tc_mma_row_smem<NACT, NW, PP>(acc0, acc1, a0p, a1p, w0, w1, v <= hi0, v >= lo1, bs + (size_t)rb * b_row_doubles, kcs, b_sb_stride);
+      else tc_mma_row_global<NW>(acc0, acc1, a0p, a1p, w0, w1, bg + (int64_t)v * jq_row, kcs, b_sb_stride, NACT);
+      const int n0 = (ix0 > v) ? ix0 : 0x7fffffff, n1 = (ix1 > v) ? ix1 : 0x7fffffff;
+      v = __reduce_min_sync(0xffffffffu, min(n0, n1));
+    }
+  }
+}
+
+template <int WM, int WN, int NW, int NP>
+__global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __grid_constant__ TcParams P)
 {
   constexpr int MT = 16 * WM;                    // units per tile
-  constexpr int UPL = MT / 32;                   // units per producer lane
-  static_assert(WM * WN == TC_CONSUMERS / 32, "8 consumer warps");
+  constexpr int UPL = MT / (32 * NP);            // units per producer lane
+  constexpr int TC_CONSUMERS = WM * WN * 32, TC_THREADS = TC_CONSUMERS + NP * 32;
+  static_assert(MT % (32 * NP) == 0, "producer lanes own MT/(32 NP) units each");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int NS = P.n_stages;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);             // full[8], empty[8]
@@ -496,20 +561,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
   double *tau_d = reinterpret_cast<double *>(smem_raw + 128 + MT * 8); // tau0 - tau       [tau_pad]
   const int tau_pad = (P.tau_size + 15) & ~15;
   double *tau_w = tau_d + tau_pad;                                      // trapezoid weight [tau_pad]
-  unsigned char *stage0 = smem_raw + 128 + MT * 8 + (size_t)tau_pad * 16;   // 128-byte aligned (MT % 32 == 0)
+  int4 *prow = reinterpret_cast<int4 *>(tau_w + tau_pad);               // producer: {row_lo, nrows, nact, row_hi} per tau
+  double *col_scale_s = reinterpret_cast<double *>(prow + tau_pad);     // epilogue: 1/(16(2l+1)) per column [cols_pad]
+  int *col_tt_s = reinterpret_cast<int *>(col_scale_s + P.cols_pad);    //           transfer type per column [cols_pad]
+  unsigned char *stage0 = smem_raw + 128 + MT * 8 + (size_t)tau_pad * 32 + (size_t)P.cols_pad * 12;   // 128-byte aligned
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_tiles = (P.n_units + MT - 1) / MT;
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(smem_u32(&bars[s]), TC_PRODUCERS + 1);          // producer lanes + the copy issuer's expect_tx
+      mbar_init(smem_u32(&bars[s]), NP + 1);                    // one arrival per producer warp + the copy issuer's expect_tx
       mbar_init(smem_u32(&bars[8 + s]), TC_CONSUMERS / 32);     // one arrival per consumer warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   for (int t = tid; t < P.tau_size; t += TC_THREADS) { tau_d[t] = P.tau0_minus_tau[t]; tau_w[t] = P.delta_tau[t]; }
+  for (int c = tid; c < P.n_cols_total; c += TC_THREADS) { col_scale_s[c] = P.col_scale[c]; col_tt_s[c] = P.col_tt[c]; }
   __syncthreads();
 
   // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (the k3-sorted sequence is sampled
@@ -519,9 +588,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
   int s = 0; uint32_t ph = 0;                   // ring slot and its phase parity, advanced per stage
 #define TC_ADVANCE() do { if (++s == NS) { s = 0; ph ^= 1u; } } while (0)
 
-  if (warp == TC_CONSUMERS / 32) {
-    // =========================== producer warp ===========================
-    // lane <-> units lane, lane+32, ...; stage sequence per tile: pass, K chunk, tau
+  if (warp >= TC_CONSUMERS / 32) {
+    // =========================== producer warps ===========================
+    // NP warps share the per-unit header work of a stage (row index and quadrature x lerp weights of every
+    // unit: lane <-> units pw*32 + lane + 32*NP*i); lane 0 of the first one also issues the copies.  With the
+    // uniform xx grid of bessel2_get_xx_list nothing here waits on global memory: per unit and stage
+    //   x = k3 (tau0-tau),  ix = (int)(x/dx),  a_J = (xx[ix+1] - x)/dx,  c0 = w a_J,  c1 = w - c0
+    // (transfer2.c:2195-2202, xx[ix+1] recomputed as (ix+1) delta).  Stage sequence per tile: pass, K chunk, tau.
+    const int pw = warp - TC_CONSUMERS / 32;
     bool first_round = true;                    // the first NS stages need no empty-slot wait
     int tbuf = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tbuf ^= 1) {
@@ -531,26 +605,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
       double kk[UPL];
 #pragma unroll
       for (int i = 0; i < UPL; ++i) {
-        const int n = lane + 32 * i;
+        const int n = pw * 32 + lane + 32 * NP * i;
         const int64_t sidx = s0 + (n < nvalid ? n : nvalid - 1);      // tail: replicate the last unit, never stored
         kk[i] = __ldg(P.k_sorted + sidx);
         unit_id[tbuf * MT + n] = (n < nvalid) ? __ldg(P.perm + sidx) : -1;
       }
-      const double k_first = __ldg(P.k_sorted + s0), k_last = __ldg(P.k_sorted + s0 + nvalid - 1);
-      // row index and xx[ix+1] of the NEXT stage are fetched one stage ahead (the table read is the
-      // only long-latency step of the lane's work)
-      int ix_n[UPL]; double xxn_n[UPL], x_n[UPL];
-#define TC_PREFETCH(T) do { \
-        const double d_ = tau_d[T]; \
-        _Pragma("unroll") for (int i = 0; i < UPL; ++i) { \
-          const double x_ = kk[i] * d_;                                 /* transfer2.c:2195 */ \
-          int ix_ = (int)(x_ * P.inv_xx_step);                          /* transfer2.c:2199 */ \
-          if (ix_ < 0 || ix_ + 1 >= P.xx_size) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); ix_ = max(0, min(ix_, P.xx_size - 2)); } \
-          x_n[i] = x_; ix_n[i] = ix_; xxn_n[i] = __ldg(P.xx + ix_ + 1); } } while (0)
-      TC_PREFETCH(0);
+      double k_first = 0., k_last = 0.;
+      if (pw == 0) { k_first = __ldg(P.k_sorted + s0); k_last = __ldg(P.k_sorted + s0 + nvalid - 1); }
       for (int ip = 0; ip < P.n_pass; ++ip) {
         const TcPass ps = P.pass[ip];
-        const int *nact_b = P.nact + (int64_t)ps.blk * P.xx_size;
+        if (pw == 0) {
+          // Table rows of the tile at every tau (units are k3-sorted: rows span [row(first), row(last)]) and the
+          // active column prefix of this pass there: one parallel round of global reads per (tile, pass), so that
+          // no table read sits on the per-stage critical path of the copy issuer.
+          const int *nact_b = P.nact + (int64_t)ps.blk * P.xx_size;
+          __syncwarp();
+          for (int t = lane; t < P.tau_size; t += 32) {
+            const double d = tau_d[t];
+            int row_lo = (int)(k_first * d * P.inv_xx_step), row_hi = (int)(k_last * d * P.inv_xx_step);
+            row_lo = max(0, min(row_lo, P.xx_size - 2)); row_hi = max(row_lo, min(row_hi, P.xx_size - 2));
+            const int nact = max(0, min(__ldg(nact_b + row_hi) - ps.sb0, ps.nsb));
+            prow[t] = make_int4(row_lo, min(row_hi - row_lo + 1, P.rmax), nact, row_hi);
+          }
+          __syncwarp();
+        }
         for (int q = 0; q < ps.nq; ++q) {
           const TcGroup G = P.grp[ps.g0 + q];
           const uint32_t bytes_per_sb = (uint32_t)G.kcs * 256u;
@@ -564,41 +642,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
             int ix[UPL]; double c0[UPL], c1[UPL];
 #pragma unroll
             for (int i = 0; i < UPL; ++i) {
-              ix[i] = ix_n[i];
-              const double a_J = (xxn_n[i] - x_n[i]) * P.inv_xx_step;        // transfer2.c:2202
-              c0[i] = w * a_J; c1[i] = w - c0[i];                            // weights of J[ix], J[ix+1]
+              const double x = kk[i] * d;                                     // transfer2.c:2195
+              int ixi = (int)(x * P.inv_xx_step);                             // transfer2.c:2199
+              const bool bad = (ixi < 0 || ixi + 1 >= P.xx_size);
+              if (bad) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); ixi = max(0, min(ixi, P.xx_size - 2)); }
+              // xx[ix+1]: the grid of bessel2_get_xx_list is i * delta bit for bit (checked on the host), else read it
+              const double xxn = P.xx_uniform ? (double)(ixi + 1) * P.xx_step : __ldg(P.xx + ixi + 1);
+              double a_J = (xxn - x) * P.inv_xx_step;                         // transfer2.c:2202
+              if (bad) a_J = 0.;
+              ix[i] = ixi;
+              c0[i] = w * a_J; c1[i] = w - c0[i];                             // weights of J[ix], J[ix+1]
             }
-            int row_lo = 0, row_hi = 0, nact = 0;
-            if (lane == 0) {
-              // table rows of the tile at this tau: units are k3-sorted, so rows are [row(first), row(last)]
-              row_lo = (int)(k_first * d * P.inv_xx_step); row_hi = (int)(k_last * d * P.inv_xx_step);
-              row_lo = max(0, min(row_lo, P.xx_size - 2)); row_hi = max(row_lo, min(row_hi, P.xx_size - 2));
-              nact = max(0, min(__ldg(nact_b + row_hi) - ps.sb0, ps.nsb));
-            }
-            { const int tn = (t + 1 < P.tau_size) ? t + 1 : 0; TC_PREFETCH(tn); }   // next stage of this tile
             if (!first_round) mbar_wait(empty, ph ^ 1u);
-            if (lane == 0) {
-              const int nrows = min(row_hi - row_lo + 1, P.rmax);
-              const uint32_t bytes_row = (uint32_t)nact * bytes_per_sb;
-              st.meta[0] = row_lo; st.meta[1] = nrows; st.meta[2] = nact; st.meta[3] = row_hi;
-              mbar_arrive_expect_tx(full, s_bytes + bytes_row * nrows);
-              tma_load_3d(smem_u32(st.S), tmap, 0, t, (int)s0, full);
-              const double *src = P.Jq + (int64_t)row_lo * P.jq_row + q_off;
-              if (bytes_row > 0)
+            if (pw == 0 && lane == 0) {
+              const int4 pr = prow[t];
+              const int nrows = pr.y;
+              const uint32_t bytes_row = (uint32_t)pr.z * bytes_per_sb;
+              *reinterpret_cast<int4 *>(st.meta) = pr;
+              mbar_arrive_expect_tx(full, ((P.dbg & 8) ? 0u : s_bytes) + ((P.dbg & 16) ? 0u : bytes_row * nrows));
+              if (!(P.dbg & 8)) tma_load_3d(smem_u32(st.S), tmap, 0, t, (int)s0, full);
+              const double *src = P.Jq + (int64_t)pr.x * P.jq_row + q_off;
+              if (bytes_row > 0 && !(P.dbg & 16))
                 for (int r = 0; r < nrows; ++r)
                   bulk_g2s(smem_u32(st.B) + r * P.b_row_bytes, src + (int64_t)r * P.jq_row, bytes_row, full);
             }
 #pragma unroll
             for (int i = 0; i < UPL; ++i) {
-              st.ixs[lane + 32 * i] = ix[i];
-              st.cc[lane + 32 * i] = make_double2(c0[i], c1[i]);
+              const int n = pw * 32 + lane + 32 * NP * i;
+              st.ixs[n] = ix[i];
+              st.cc[n] = make_double2(c0[i], c1[i]);
             }
-            mbar_arrive(full);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full);
             if (++s == NS) { s = 0; ph ^= 1u; first_round = false; }
           }
         }
       }
-#undef TC_PREFETCH
     }
     return;
   }
@@ -625,38 +704,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
         for (int t = 0; t < P.tau_size; ++t) {
           const TcStagePtrs st = tc_stage<MT>(stage0, s, P);
           mbar_wait(smem_u32(&bars[s]), ph);
-          const int row_lo = st.meta[0], nrows = st.meta[1], nact = st.meta[2];
+          const int4 meta = *reinterpret_cast<const int4 *>(st.meta);      // {row_lo, nrows, nact, row_hi}
+          const int nact = meta.z;
           // owned sub-blocks: warp_n, warp_n + WN, ... ; active ones form a prefix of that list
           const int nactw = (nact > warp_n) ? min(NW, (nact - warp_n + WN - 1) / WN) : 0;
           if (nactw > 0 && !(P.dbg & 4)) {
-            const int ix0 = st.ixs[g0 * 8 + um];
-            const int ix1 = st.ixs[g1 * 8 + um];
+            const int ix0 = st.ixs[g0 * 8 + um], ix1 = st.ixs[g1 * 8 + um];
+            const int lo0 = st.ixs[g0 * 8], hi0 = st.ixs[g0 * 8 + 7], lo1 = st.ixs[g1 * 8], hi1 = st.ixs[g1 * 8 + 7];
             const double2 cc0 = st.cc[g0 * 8 + um], cc1 = st.cc[g1 * 8 + um];
             const double cw0 = ksel ? cc0.y : cc0.x, cw1 = ksel ? cc1.y : cc1.x;
             // A fragment of kc: S[unit][2 kc + tsel] x weight
             const double *a0p = st.S + a_off0;
             const double *a1p = st.S + a_off1;
-            int v = __reduce_min_sync(0xffffffffu, min(ix0, ix1));
-            while (v != 0x7fffffff) {
-              const bool m0 = (ix0 == v), m1 = (ix1 == v);
-              const bool any0 = __any_sync(0xffffffffu, m0), any1 = __any_sync(0xffffffffu, m1);
-              const double w0 = m0 ? cw0 : 0., w1 = m1 ? cw1 : 0.;
-              const int rb = v - row_lo;
-              if (rb < nrows) {
-                const double *bp = st.B + (size_t)rb * (P.b_row_bytes / 8) + (size_t)warp_n * kcs_q * 32 + lane;
-#define TC_CASE(N) case N: if constexpr (N <= NW) tc_mma_row_smem<N, NW>(acc0, acc1, a0p, a1p, w0, w1, any0, any1, bp, kcs_q, b_sb_stride); break;
-                switch (nactw) {
-                  TC_CASE(1) TC_CASE(2) TC_CASE(3) TC_CASE(4) TC_CASE(5) TC_CASE(6) TC_CASE(7) TC_CASE(8) TC_CASE(9) TC_CASE(10)
-                }
-#undef TC_CASE
-              } else {
-                const double *bp = P.Jq + (int64_t)v * P.jq_row + ps.jq_off + (int64_t)ps.nsb * G.kc0 * 32
-                                 + (size_t)warp_n * kcs_q * 32 + lane;
-                tc_mma_row_global<NW>(acc0, acc1, a0p, a1p, w0, w1, bp, kcs_q, b_sb_stride, nactw);
-              }
-              const int n0 = (ix0 > v) ? ix0 : 0x7fffffff, n1 = (ix1 > v) ? ix1 : 0x7fffffff;
-              v = __reduce_min_sync(0xffffffffu, min(n0, n1));
+            const double *bs = st.B + (size_t)warp_n * kcs_q * 32 + lane;
+            const double *bg = P.Jq + ps.jq_off + (int64_t)ps.nsb * G.kc0 * 32 + (size_t)warp_n * kcs_q * 32 + lane;
+#define TC_CASE(N) case N: if constexpr (N <= NW) tc_stage_rows<N, NW, (WM * WN <= 8)>(acc0, acc1, a0p, a1p, ix0, ix1, cw0, cw1, lo0, hi0, lo1, hi1, \
+                                       meta.x, meta.y, bs, P.b_row_bytes / 8, bg, P.jq_row, kcs_q, b_sb_stride); break;
+            switch (nactw) {
+              TC_CASE(1) TC_CASE(2) TC_CASE(3) TC_CASE(4) TC_CASE(5) TC_CASE(6) TC_CASE(7) TC_CASE(8) TC_CASE(9) TC_CASE(10)
             }
+#undef TC_CASE
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars[8 + s]));
@@ -677,8 +744,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) los_tc_kernel(const __grid_cons
         for (int h = 0; h < 2; ++h) {
           const int c = cbase + h;
           if (c >= B.ncols) continue;
-          const int tt = P.col_tt[B.col_off + c];
-          const double scale = P.col_scale[B.col_off + c];
+          const int tt = col_tt_s[B.col_off + c];
+          const double scale = col_scale_s[B.col_off + c];
           const double t0 = acc0[j][h] * scale, t1 = acc1[j][h] * scale;
           if (u0 >= 0) { if (t0 != t0) atomicOr(P.err, ERR_NAN); P.out[(int64_t)tt * P.out_stride + u0] = t0; }
           if (u1 >= 0) { if (t1 != t1) atomicOr(P.err, ERR_NAN); P.out[(int64_t)tt * P.out_stride + u1] = t1; }
@@ -715,7 +782,7 @@ struct FastState {
   int64_t jq_row = 0;
   int64_t s_doubles_per_unit = 0;        // sum over groups of tau_size * tpp
   int wm = 8, wn = 1, nw = 8;
-  int kcs_max = 1, nsb_pass_max = 1, tpp_max = 4;
+  int kcs_max = 1, nsb_pass_max = 1, tpp_max = 4, n_cols_total = 0;
   Buf<double> Jq, keys_out, S, slot_sign, col_scale;
   Buf<double2> CSD;
   Buf<int> col_tt, col_l, col_lm, term_col0, nact, perm_in, perm, unit_pair, slot_tp, jcount;
@@ -803,7 +870,7 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
 
   // warp grid (WM x WN consumer warps, NW sub-blocks per warp): widest tile of units that still
   // covers the columns of a block in one pass
-  if (max_sb <= 8) { fs->wm = 8; fs->wn = 1; fs->nw = 8; }
+  if (max_sb <= 8) { fs->wm = 12; fs->wn = 1; fs->nw = 8; }     // three consumer warps per SM sub-partition
   else if (max_sb <= 10) { fs->wm = 8; fs->wn = 1; fs->nw = 10; }
   else if (max_sb <= 16) { fs->wm = 4; fs->wn = 2; fs->nw = 8; }
   else if (max_sb <= 20) { fs->wm = 4; fs->wn = 2; fs->nw = 10; }
@@ -811,7 +878,7 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
   else { fs->wm = 2; fs->wn = 4; fs->nw = 10; }
   if (const char *v = getenv("SONG_LOS_TC_SHAPE")) {          // A/B measurements: "wm,wn,nw"
     int a, b, c;
-    if (sscanf(v, "%d,%d,%d", &a, &b, &c) == 3 && a * b == 8 && (c == 8 || c == 10) && (a == 8 || a == 4 || a == 2)) {
+    if (sscanf(v, "%d,%d,%d", &a, &b, &c) == 3) {
       fs->wm = a; fs->wn = b; fs->nw = c;
     }
   }
@@ -837,7 +904,7 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
       if (fs->n_groups >= TC_MAX_GROUPS) { err = "too many K chunks for the FAST kernel"; return 1; }
       TcGroup G{};
       G.blk = ib; G.kc0 = q * kcs; G.kcs = std::min(kcs, B.nkc - G.kc0);
-      G.tpp = (2 * G.kcs + 3) / 4 * 4;           // 32-byte multiples: whole sectors per (unit, tau)
+      G.tpp = 2 * G.kcs;                         // 16-byte multiples (TMA stride rule); odd kcs: conflict-free A-fragment reads
       for (int sl = 0; sl < 2 * G.kcs; ++sl) {
         int e = 2 * G.kc0 + sl;
         if (e < B.nterms) { slot_tp[(size_t)fs->n_groups * TC_SLOTS + sl] = term_tp[B.term_off + e];
@@ -869,6 +936,7 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
     if (e != cudaSuccess) return e;
     return cudaMemcpyAsync(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice, st);
   };
+  fs->n_cols_total = (int)col_tt.size();
   std::vector<double> col_scale(col_l.size());
   for (size_t i = 0; i < col_l.size(); ++i) col_scale[i] = 1.0 / (16.0 * (2.0 * col_l[i] + 1.0));
   FCK(up(fs->col_tt, col_tt)); FCK(up(fs->col_l, col_l)); FCK(up(fs->col_lm, col_lm)); FCK(up(fs->col_scale, col_scale));
@@ -905,12 +973,12 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
   return 0;
 }
 
-template <int WM, int WN, int NW>
+template <int WM, int WN, int NW, int NP>
 static cudaError_t launch_tc(const TcParams &TP, int64_t n_ctas, size_t smem, cudaStream_t st)
 {
-  cudaError_t e = cudaFuncSetAttribute(los_tc_kernel<WM, WN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(los_tc_kernel<WM, WN, NW, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  los_tc_kernel<WM, WN, NW><<<(unsigned)n_ctas, TC_THREADS, smem, st>>>(TP);
+  los_tc_kernel<WM, WN, NW, NP><<<(unsigned)n_ctas, (WM * WN + NP) * 32, smem, st>>>(TP);
   return cudaGetLastError();
 }
 
@@ -1019,6 +1087,8 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
   TP.tau_size = tau_size;
   TP.tau0_minus_tau = P.tm.tau0_minus_tau; TP.delta_tau = P.tm.delta_tau; TP.xx = P.xx;
   TP.inv_xx_step = 1.0 / P.xx_step; TP.xx_size = P.xx_size;
+  TP.xx_step = h.xx_delta; TP.xx_uniform = h.xx_uniform;
+  if (getenv("SONG_LOS_TC_XX_TABLE")) TP.xx_uniform = 0;
   TP.out = b.out; TP.out_stride = U; TP.err = P.err;
   if (const char *v = getenv("SONG_LOS_TC_DBG")) TP.dbg = atoi(v);
   if (U > 0) {
@@ -1041,7 +1111,8 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
   TP.b_row_bytes = fs->nsb_pass_max * fs->kcs_max * 256;
   int rmax = (MT >= 128) ? 4 : (MT >= 64 ? 3 : 2);
   if (const char *v = getenv("SONG_LOS_TC_RMAX")) rmax = std::max(1, std::min(8, atoi(v)));
-  const size_t fixed = 128 + (size_t)MT * 8 + (size_t)((tau_size + 15) & ~15) * 16;
+  TP.n_cols_total = fs->n_cols_total; TP.cols_pad = (fs->n_cols_total + 31) & ~31;
+  const size_t fixed = 128 + (size_t)MT * 8 + (size_t)((tau_size + 15) & ~15) * 32 + (size_t)TP.cols_pad * 12;
   const size_t budget = 224 * 1024;
   auto stage_bytes = [&](int r) { return (size_t)TP.hdr_bytes + TP.a_bytes + (size_t)r * TP.b_row_bytes; };
   while (rmax > 1 && (budget - fixed) / stage_bytes(rmax) < 3) --rmax;
@@ -1054,15 +1125,20 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
 
   if (n_tiles > 0) {
     cudaError_t e = cudaErrorInvalidValue;
-    const int key = fs->wm * 100 + fs->nw;
+    const int key = fs->wm * 10000 + fs->wn * 100 + fs->nw;
     const int64_t n_ctas = std::min<int64_t>(n_tiles, std::max(1, device_sms));     // persistent: one CTA per SM
+    const int np1 = getenv("SONG_LOS_TC_NP1") != nullptr;     // A/B: a single producer warp
     switch (key) {
-      case 808:  e = launch_tc<8, 1, 8>(TP, n_ctas, smem, st); break;
-      case 810:  e = launch_tc<8, 1, 10>(TP, n_ctas, smem, st); break;
-      case 408:  e = launch_tc<4, 2, 8>(TP, n_ctas, smem, st); break;
-      case 410:  e = launch_tc<4, 2, 10>(TP, n_ctas, smem, st); break;
-      case 208:  e = launch_tc<2, 4, 8>(TP, n_ctas, smem, st); break;
-      case 210:  e = launch_tc<2, 4, 10>(TP, n_ctas, smem, st); break;
+      case 80108:  e = np1 ? launch_tc<8, 1, 8, 1>(TP, n_ctas, smem, st) : launch_tc<8, 1, 8, 4>(TP, n_ctas, smem, st); break;
+      case 80110:  e = launch_tc<8, 1, 10, 4>(TP, n_ctas, smem, st); break;
+      case 40208:  e = launch_tc<4, 2, 8, 2>(TP, n_ctas, smem, st); break;
+      case 40210:  e = launch_tc<4, 2, 10, 2>(TP, n_ctas, smem, st); break;
+      case 20408:  e = launch_tc<2, 4, 8, 1>(TP, n_ctas, smem, st); break;
+      case 20410:  e = launch_tc<2, 4, 10, 1>(TP, n_ctas, smem, st); break;
+      // three consumer warps per SM sub-partition
+      case 120107: e = launch_tc<12, 1, 7, 3>(TP, n_ctas, smem, st); break;
+      case 120108: e = np1 ? launch_tc<12, 1, 8, 3>(TP, n_ctas, smem, st) : launch_tc<12, 1, 8, 1>(TP, n_ctas, smem, st); break;
+      default: err = "FAST kernel: no instantiation for the requested warp grid"; return 1;
     }
     FCK(e);
     ++*n_launches;

@@ -103,6 +103,18 @@ extern "C" int song_los_create(const song_los_config *cfg, song_los_ctx **out)
 
   ctx->tau.assign(cfg->tau_sampling, cfg->tau_sampling + cfg->tau_size);
   ctx->xx.assign(cfg->xx, cfg->xx + cfg->xx_size);
+  // bessel2.c:976-981 builds xx with lin_space(0, xx_max, xx_size): xx[i] = i * delta.  If one of the candidate deltas
+  // reproduces the whole grid BIT FOR BIT the FAST kernel recomputes xx[ix+1] instead of reading it (transfer2.c:2202).
+  ctx->xx_uniform = 0;
+  {
+    const int n = cfg->xx_size;
+    const double cand[3] = {cfg->xx_step, ctx->xx[1] - ctx->xx[0], (ctx->xx[n - 1] - ctx->xx[0]) / (n - 1)};
+    for (double delta : cand) {
+      bool same = (ctx->xx[0] == 0.);
+      for (int i = 0; same && i < n; ++i) same = (ctx->xx[i] == (double)i * delta);
+      if (same) { ctx->xx_uniform = 1; ctx->xx_delta = delta; break; }
+    }
+  }
   ctx->l.assign(cfg->l, cfg->l + cfg->l_size);
   ctx->m.assign(cfg->m, cfg->m + cfg->m_size);
   ctx->lm_array.assign(cfg->lm_array, cfg->lm_array + (size_t)cfg->l_size * cfg->m_size);
@@ -478,6 +490,7 @@ static void fill_fast_layout(song_los_ctx *ctx, const song_los_ctx::Slot &S, Fas
   h.xx_size = c.xx_size; h.l = c.l; h.m = c.m; h.lm_array = c.lm_array; h.lm_src = c.lm_src;
   h.block_nonzero = ctx->h_block_nonzero.data(); h.n_src_total = S.hb.n_src_total;
   h.tau_size = c.tau_size; h.n_pt_total = S.hb.n_pt_total;
+  h.xx_uniform = ctx->xx_uniform; h.xx_delta = ctx->xx_delta;
 }
 
 static int report_device_errors(song_los_ctx *ctx, int h)

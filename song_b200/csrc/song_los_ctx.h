@@ -32,6 +32,7 @@ struct song_los_ctx {
   // configuration (host copies)
   song_los_config cfg{};
   std::vector<double> tau, xx;
+  int xx_uniform = 0; double xx_delta = 0.;   // xx[i] == i*xx_delta bit for bit
   std::vector<int> l, m, lm_array, lm_src, tt_index_l, tt_index_m;
   std::vector<int> tt_type, tt_lm, tt_l, tt_m, tt_im;
 
