@@ -33,6 +33,7 @@
  *                              kernels of batch n (the k1 levels are independent, transfer2.c:549-551)
  *   song_los_host_alloc/_free  page-locked staging memory for ppt2->sources / ptr2->transfer slabs
  *   song_los_max_batch_units   how many k3 values of consecutive k1 levels fit in one batch
+ *   song_los_reserve           device buffers for the largest batch, allocated before the k1 loop starts
  *
  * Error convention (reference: _SUCCESS_/_FAILURE_ + ErrorMsg): every function
  * returns SONG_LOS_SUCCESS (0) or SONG_LOS_FAILURE (1); the text is available from
@@ -205,6 +206,11 @@ int  song_los_host_free(void *ptr);
  * one compute fit in the free device memory.  src_doubles_per_unit = (source doubles of the run) /
  * (k3 values of the run), i.e. tp2_size * tau_size * <k3_pt> / <k3_tr>.  Needs the projection tables. */
 int  song_los_max_batch_units(song_los_ctx *ctx, int mode, double src_doubles_per_unit, int64_t *units);
+
+/* Pre-allocates all device buffers for batches of up to the given sizes (pairs, k3 values, coarse k3
+ * points, source doubles).  Optional, but without it a batch larger than every earlier one makes the
+ * engine grow its buffers, and cudaMalloc/cudaFree stall the pipeline. */
+int  song_los_reserve(song_los_ctx *ctx, int mode, int max_pairs, int64_t max_units, int64_t max_pt, int64_t max_src);
 
 /* Device pointer of the [tt2_size][n_units] result of the last compute (for the NCCL gather
    done by the multi-GPU driver), as an integer address; 0 before the first compute. */

@@ -139,7 +139,7 @@ LOS_SYMBOLS = [
     "song_los_compute", "song_los_download", "song_los_transfer_pairs",
     "song_los_device_result", "song_los_copy_result", "song_los_set_stream", "song_los_measure_peaks",
     "song_los_device_info", "song_los_version",
-    "song_los_submit", "song_los_wait", "song_los_host_alloc", "song_los_host_free", "song_los_max_batch_units",
+    "song_los_submit", "song_los_wait", "song_los_host_alloc", "song_los_host_free", "song_los_max_batch_units", "song_los_reserve",
 ]
 HOST_SYMBOLS = ["song_host_k3_size", "song_host_k3_list", "song_host_k3_sizes", "song_host_k3_lists",
                 "song_host_bessel2_prepare", "song_host_bessel2_free", "song_host_bessel2_upload"]
@@ -183,6 +183,7 @@ def los():
         lib.song_los_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
         lib.song_los_host_free.argtypes = [vp]
         lib.song_los_max_batch_units.argtypes = [vp, C.c_int, C.c_double, c_int64_p]
+        lib.song_los_reserve.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64]
         _los = lib
     return _los
 

@@ -29,6 +29,7 @@ void fast_state_destroy(FastState *);
 void fast_invalidate_table(FastState *);
 int fast_prepare(FastState *fs, const FastHostLayout &h, const ExactParams &P, cudaStream_t st, std::string &err);
 int64_t fast_bytes_per_unit(const FastState *fs);
+int fast_reserve(FastState *fs, int64_t n_units, int64_t n_src, int64_t n_pt, std::string &err);
 int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, int device_sms, cudaStream_t st,
                  cudaEvent_t *ev /* [5] */, int *n_launches, std::string &err);
 int fast_collect(cudaEvent_t *ev, song_los_timing *tm, std::string &err);

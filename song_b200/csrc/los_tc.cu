@@ -612,6 +612,19 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
       }
       double k_first = 0., k_last = 0.;
       if (pw == 0) { k_first = __ldg(P.k_sorted + s0); k_last = __ldg(P.k_sorted + s0 + nvalid - 1); }
+      // x, row index and xx[ix+1] of the NEXT stage are prepared one stage ahead: when the xx grid is not
+      // i * delta bit for bit, xx[ix+1] is a table read whose latency then overlaps the wait for a free slot
+      int ix_n[UPL]; double xxn_n[UPL], x_n[UPL]; bool bad_n[UPL];
+#define TC_PREFETCH(T) do { \
+        const double d_ = tau_d[T]; \
+        _Pragma("unroll") for (int i = 0; i < UPL; ++i) { \
+          const double x_ = kk[i] * d_;                                 /* transfer2.c:2195 */ \
+          int ix_ = (int)(x_ * P.inv_xx_step);                          /* transfer2.c:2199 */ \
+          bad_n[i] = (ix_ < 0 || ix_ + 1 >= P.xx_size); \
+          if (bad_n[i]) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); ix_ = max(0, min(ix_, P.xx_size - 2)); } \
+          x_n[i] = x_; ix_n[i] = ix_; \
+          xxn_n[i] = P.xx_uniform ? (double)(ix_ + 1) * P.xx_step : __ldg(P.xx + ix_ + 1); } } while (0)
+      TC_PREFETCH(0);
       for (int ip = 0; ip < P.n_pass; ++ip) {
         const TcPass ps = P.pass[ip];
         if (pw == 0) {
@@ -638,21 +651,15 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
           for (int t = 0; t < P.tau_size; ++t) {
             const uint32_t full = smem_u32(&bars[s]), empty = smem_u32(&bars[8 + s]);
             const TcStagePtrs st = tc_stage<MT>(stage0, s, P);
-            const double d = tau_d[t], w = tau_w[t];
+            const double w = tau_w[t];
             int ix[UPL]; double c0[UPL], c1[UPL];
 #pragma unroll
             for (int i = 0; i < UPL; ++i) {
-              const double x = kk[i] * d;                                     // transfer2.c:2195
-              int ixi = (int)(x * P.inv_xx_step);                             // transfer2.c:2199
-              const bool bad = (ixi < 0 || ixi + 1 >= P.xx_size);
-              if (bad) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); ixi = max(0, min(ixi, P.xx_size - 2)); }
-              // xx[ix+1]: the grid of bessel2_get_xx_list is i * delta bit for bit (checked on the host), else read it
-              const double xxn = P.xx_uniform ? (double)(ixi + 1) * P.xx_step : __ldg(P.xx + ixi + 1);
-              double a_J = (xxn - x) * P.inv_xx_step;                         // transfer2.c:2202
-              if (bad) a_J = 0.;
-              ix[i] = ixi;
+              ix[i] = ix_n[i];
+              const double a_J = bad_n[i] ? 0. : (xxn_n[i] - x_n[i]) * P.inv_xx_step;     // transfer2.c:2202
               c0[i] = w * a_J; c1[i] = w - c0[i];                             // weights of J[ix], J[ix+1]
             }
+            { const int tn = (t + 1 < P.tau_size) ? t + 1 : 0; TC_PREFETCH(tn); }   // header inputs of the next stage
             if (!first_round) mbar_wait(empty, ph ^ 1u);
             if (pw == 0 && lane == 0) {
               const int4 pr = prow[t];
@@ -678,6 +685,7 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
           }
         }
       }
+#undef TC_PREFETCH
     }
     return;
   }
@@ -996,6 +1004,24 @@ int64_t fast_bytes_per_unit(const FastState *fs)
   return fs->s_doubles_per_unit * 8 + 8 /*keys*/ + 3 * 4 /*perm_in, perm, unit_pair*/ + (int64_t)sizeof(TcUnitW) + 8 /*ujp*/ + 16 /*cub*/;
 }
 
+// Allocates every intermediate of the FAST path for batches of up to U k3 values / n_src source doubles /
+// n_pt coarse k3 points, so that no (device-synchronising) allocation happens between pipelined batches.
+int fast_reserve(FastState *fs, int64_t U, int64_t n_src, int64_t n_pt, std::string &err)
+{
+  if (!fs->table_ready) { err = "fast_reserve: layout not built"; return 1; }
+  FCK(fs->CSD.reserve((size_t)n_src));
+  FCK(fs->perm_in.reserve((size_t)U)); FCK(fs->perm.reserve((size_t)U)); FCK(fs->keys_out.reserve((size_t)U));
+  FCK(fs->unit_pair.reserve((size_t)U));
+  size_t tmp_bytes = 0;
+  FCK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const double *)nullptr, fs->keys_out.p, fs->perm_in.p, fs->perm.p,
+                                      (int)U, 0, 64, (cudaStream_t)0));
+  FCK(fs->cub_tmp.reserve(tmp_bytes));
+  FCK(fs->uw.reserve((size_t)U)); FCK(fs->ujp.reserve((size_t)U));
+  FCK(fs->S.reserve((size_t)U * fs->s_doubles_per_unit));
+  FCK(fs->jcount.reserve((size_t)n_pt));
+  return 0;
+}
+
 // Enqueues the whole FAST pipeline on `st` and returns without waiting; ev[0..4] (caller-owned) are
 // recorded at the phase boundaries and read later by fast_collect.
 int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, int device_sms, cudaStream_t st,
@@ -1138,6 +1164,11 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
       // three consumer warps per SM sub-partition
       case 120107: e = launch_tc<12, 1, 7, 3>(TP, n_ctas, smem, st); break;
       case 120108: e = np1 ? launch_tc<12, 1, 8, 3>(TP, n_ctas, smem, st) : launch_tc<12, 1, 8, 1>(TP, n_ctas, smem, st); break;
+      case 60205:  e = launch_tc<6, 2, 5, 1>(TP, n_ctas, smem, st); break;
+      case 60208:  e = launch_tc<6, 2, 8, 1>(TP, n_ctas, smem, st); break;
+      case 40307:  e = launch_tc<4, 3, 7, 1>(TP, n_ctas, smem, st); break;
+      case 40308:  e = launch_tc<4, 3, 8, 1>(TP, n_ctas, smem, st); break;
+      case 80205:  e = launch_tc<8, 2, 5, 2>(TP, n_ctas, smem, st); break;
       default: err = "FAST kernel: no instantiation for the requested warp grid"; return 1;
     }
     FCK(e);

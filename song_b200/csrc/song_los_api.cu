@@ -404,7 +404,9 @@ static int enqueue_upload(song_los_ctx *ctx, song_los_ctx::Slot &S, const song_l
   std::memcpy(h32, b->k3_pt_size, n * 4); std::memcpy(h32 + n, b->k3_tr_size, n * 4);
   std::memcpy(h32 + 2 * n, b->phys_start, n * 4); std::memcpy(h32 + 3 * n, b->phys_size, n * 4);
   int64_t n_tiles = 0;
+  S.max_np = 0;
   for (size_t p = 0; p < n; ++p) {
+    S.max_np = std::max(S.max_np, b->k3_pt_size[p]);
     h32[4 * n + p] = (int)n_tiles;
     n_tiles += (b->k3_tr_size[p] + EXACT_UNITS_PER_CTA - 1) / EXACT_UNITS_PER_CTA;
   }
@@ -674,6 +676,42 @@ extern "C" int song_los_host_alloc(void **ptr, size_t bytes)
 extern "C" int song_los_host_free(void *ptr)
 {
   if (ptr && cudaFreeHost(ptr) != cudaSuccess) return SONG_LOS_FAILURE;
+  return SONG_LOS_SUCCESS;
+}
+
+// Pre-allocates the device buffers of all slots and the intermediates of one compute for batches of up to
+// the given sizes: cudaMalloc/cudaFree synchronise the whole device, so growing a buffer between pipelined
+// batches would serialise the copies of one batch with the kernels of another.
+extern "C" int song_los_reserve(song_los_ctx *ctx, int mode, int max_pairs, int64_t max_units, int64_t max_pt, int64_t max_src)
+{
+  if (!ctx) return SONG_LOS_FAILURE;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->n_in_flight) return ctx_fail(ctx, "song_los_reserve: submitted batches are still in flight");
+  const song_los_config &c = ctx->cfg;
+  for (auto &S : ctx->slot) {
+    const size_t meta_bytes = std::max<size_t>((size_t)max_pairs * (3 * sizeof(int64_t) + 5 * sizeof(int)), 64);
+    if (meta_bytes > S.h_meta_cap) {
+      if (S.h_meta) cudaFreeHost(S.h_meta);
+      S.h_meta = nullptr; S.h_meta_cap = 0;
+      CK(cudaHostAlloc((void **)&S.h_meta, meta_bytes, cudaHostAllocDefault));
+      S.h_meta_cap = meta_bytes;
+    }
+    CK(S.d_meta.reserve(meta_bytes));
+    CK(S.d_k3_pt.reserve((size_t)max_pt)); CK(S.d_k3_tr.reserve((size_t)max_units));
+    CK(S.d_src.reserve((size_t)max_src)); CK(S.d_out.reserve((size_t)max_units * c.tt2_size));
+  }
+  if (mode == SONG_LOS_MODE_FAST) {
+    if (!ctx->have_proj) return ctx_fail(ctx, "song_los_reserve: projection functions not set");
+    std::string e;
+    song_los_ctx::Slot dummy;
+    ExactParams P; fill_params(ctx, dummy, P);
+    FastHostLayout h; fill_fast_layout(ctx, dummy, h);
+    if (fast_prepare(ctx->fast, h, P, ctx->stream, e) != 0) return ctx_fail(ctx, "%s", e.c_str());
+    if (fast_reserve(ctx->fast, max_units, max_src, max_pt, e) != 0) return ctx_fail(ctx, "song_los_reserve: %s", e.c_str());
+  } else {
+    if (c.sources_k3_interpolation == SONG_LOS_INTERP_CUBIC) CK(ctx->d_dd.reserve((size_t)max_src));
+    for (auto &S : ctx->slot) CK(S.d_tiles.reserve((size_t)(max_units / EXACT_UNITS_PER_CTA + max_pairs + 1)));
+  }
   return SONG_LOS_SUCCESS;
 }
 

@@ -57,6 +57,7 @@ struct song_los_ctx {
     int64_t *d_pt_off = nullptr, *d_tr_off = nullptr, *d_src_off = nullptr;
     DevBuf<double> d_k3_pt, d_k3_tr, d_src, d_out;
     DevBuf<int2> d_tiles; int n_tiles = 0; bool tiles_ready = false;
+    int max_np = 0;               // largest coarse k3 grid of the batch
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr, ev_h2d_start = nullptr, ev_d2h_start = nullptr;
     cudaEvent_t ev_t[6]{};        // phase boundaries of this slot's compute
     int *h_err = nullptr;         // pinned copy of the device error flags after this slot's compute

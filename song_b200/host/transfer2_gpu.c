@@ -13,8 +13,8 @@
  * (transfer2.c:705-763, 2929-2963: raw doubles, [k1][k2][k3] per transfer type).
  *
  * Batching: the reference handles one (k1,k2) pair at a time; here consecutive k1 levels are packed into one GPU
- * batch (SONG_LOS_BATCH_UNITS k3 values; default: about three batches per GPU, at least 4e5 k3 values, at most
- * what song_los_max_batch_units says fits in device memory) because the tensor-core kernel wants many k3 values
+ * batch (SONG_LOS_BATCH_UNITS k3 values; default: an even share of the run per GPU, at most what
+ * song_los_max_batch_units says fits in device memory) because the tensor-core kernel wants many k3 values
  * per table row.  Batches of a GPU run as a three-deep pipeline (song_los_submit / song_los_wait) through page-locked
  * staging, so that the copies of neighbouring batches overlap the kernels.  Side effects keep the reference's per-k1 order: sources of a k1 level are loaded before and freed
  * after use (transfer2.c:332-344, 553), transfers are stored and freed per k1 (transfer2.c:559-567).
@@ -645,9 +645,11 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   }
   long batch_units = (long)env_int("SONG_LOS_BATCH_UNITS", 0);
   if (batch_units <= 0) {
+    /* as large as device memory allows (the kernel's efficiency grows with the number of k3 values per table
+       row), but not larger than an even share of the run per GPU */
     int n_dev_guess = ordered ? 1 : env_int("SONG_LOS_DEVICES", 1);
-    batch_units = total_units / (3 * (n_dev_guess > 0 ? n_dev_guess : 1));       /* about three batches per GPU ... */
-    if (batch_units < 400000) batch_units = 400000;                              /* ... but not below 4e5 k3 values */
+    if (n_dev_guess < 1) n_dev_guess = 1;
+    batch_units = (total_units + n_dev_guess - 1) / n_dev_guess;
   }
   if (batch_units > (long)cap_units) batch_units = (long)cap_units;
   los_k1_batch *batches;
@@ -719,6 +721,10 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
                  (long)max_units, song_los_last_error(NULL));
         ok = _FALSE_;
       }
+    /* device buffers for the largest batch: no allocation (= device-wide synchronisation) inside the pipeline */
+    if (ok && song_los_reserve(dev[d].ctx, mode, max_pairs, max_units, max_pt, max_src) != SONG_LOS_SUCCESS) {
+      snprintf(local, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(dev[d].ctx)); ok = _FALSE_;
+    }
     int cur = 0, in_flight = 0;
     for (int ib = 0; ok && ib < n_batches; ++ib) {
       if (batches[ib].device != d) continue;

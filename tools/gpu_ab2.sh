@@ -1,11 +1,9 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-run() { echo "=== $*"; env "$@" timeout 600 python tools/time_configs.py --mode fast --reps 2 --oracle-pairs 6 ${CONFIGS:-sn_t_10percent_lmax2000} 2>&1 | grep -E "FAST|Error|error" | tail -2 | cut -c1-130; }
-for shape in 8,1,8 12,1,8 12,1,7; do
-run SONG_LOS_TC_SHAPE=$shape
-run SONG_LOS_TC_SHAPE=$shape SONG_LOS_TC_DBG=4
-run SONG_LOS_TC_SHAPE=$shape SONG_LOS_TC_DBG=28
-done
-run SONG_LOS_TC_SHAPE=8,1,8 SONG_LOS_TC_NP1=1
-run SONG_LOS_TC_SHAPE=12,1,8 SONG_LOS_TC_NP1=1
+run3() { echo "=== $*"; env "$@" timeout 900 python tools/run_config.py sn_pol_5percent_lmax3000 --pair-stride 5 --oracle-pairs 2 > gpurun_out/r3.out 2> gpurun_out/r3.err; tail -2 gpurun_out/r3.err | cut -c1-300; python -c "
+import json
+d=json.load(open('gpurun_out/r3.out')); print('RESULT', d['gpu_ms']['ms_integrate'], d['gpu_ms']['ms_total'], d['parity']['max_rel_err_above_1e-6_of_max'])"; }
+run3 SONG_LOS_TC_SHAPE=2,4,8
+run3 SONG_LOS_TC_SHAPE=4,3,7
+run3 SONG_LOS_TC_SHAPE=4,3,8
+run3 SONG_LOS_TC_SHAPE=4,2,10
