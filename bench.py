@@ -173,6 +173,9 @@ def cpu_sample(name: str, target_seconds: float, max_pairs=None):
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
+    # torch.distributed.run exports OMP_NUM_THREADS=1 when it is unset; the CPU arm uses every host thread
+    if "LOCAL_RANK" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import oracle_lib as O
     from song_b200 import workload
     grids, sub, proj, stride = cpu_sample(args.workload, args.cpu_seconds)

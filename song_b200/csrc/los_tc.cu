@@ -317,6 +317,7 @@ constexpr int TC_INTERP_THREADS = 256;
 struct TcInterp {
   int n_groups;
   int tauc;                               // tau samples per CTA
+  int col_stride;                         // tauc * (largest tpp): row length of the column map
   int grp_tpp[TC_MAX_GROUPS];             // slots per (unit, tau) row of the group
   int64_t grp_s_off[TC_MAX_GROUPS];       // slab offsets
   const int *slot_tp;                     // per (group, slot): source type, -1 = padding   [n_groups][TC_SLOTS]
@@ -335,8 +336,19 @@ __global__ void __launch_bounds__(TC_INTERP_THREADS) tc_interp_units_kernel(Batc
   double2 *rows = reinterpret_cast<double2 *>(interp_smem);           // [2][tauc * tp2]
   int *s_tp = reinterpret_cast<int *>(rows + 2 * (size_t)I.tauc * tp2_size);   // [n_groups][TC_SLOTS]
   double *s_sign = reinterpret_cast<double *>(s_tp + TC_MAX_GROUPS * TC_SLOTS);
+  // per (group, column of the chunk): index of the staged {y, dd} entry (tau_local * tp2 + tp) and the slot,
+  // packed as idx | slot << 24; -1 for padding slots.  Replaces a division per element in the inner loop.
+  int *s_col = reinterpret_cast<int *>(s_sign + TC_MAX_GROUPS * TC_SLOTS);   // [n_groups][tauc * tpp_max]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = TC_INTERP_THREADS / 32;
   for (int i = tid; i < I.n_groups * TC_SLOTS; i += TC_INTERP_THREADS) { s_tp[i] = I.slot_tp[i]; s_sign[i] = I.slot_sign[i]; }
+  for (int g = 0; g < I.n_groups; ++g) {
+    const int tpp = I.grp_tpp[g];
+    for (int c = tid; c < ntau * tpp; c += TC_INTERP_THREADS) {
+      const int tl = c / tpp, slot = c - tl * tpp;
+      const int tp = I.slot_tp[g * TC_SLOTS + slot];
+      s_col[g * I.col_stride + c] = (tp >= 0) ? ((tl * tp2_size + tp) | (slot << 24)) : -1;
+    }
+  }
   const int np = b.np[p];
   const int64_t u0 = b.tr_off[p];
   const int64_t rowlen = (int64_t)tau_size * tp2_size;
@@ -356,14 +368,16 @@ __global__ void __launch_bounds__(TC_INTERP_THREADS) tc_interp_units_kernel(Batc
         const int tpp = I.grp_tpp[g];
         double *dst = S + I.grp_s_off[g] + (pos * tau_size + tau0) * tpp;
         const int ncol = ntau * tpp;
+        const int *colmap = s_col + g * I.col_stride;
+        const double *sgn = s_sign + g * TC_SLOTS;
         for (int c = lane; c < ncol; c += 32) {
-          const int tl = c / tpp, slot = c - tl * tpp;
-          const int tp = s_tp[g * TC_SLOTS + slot];
+          const int m = colmap[c];
           double v = 0.;
-          if (tp >= 0) {
-            const double2 a0 = r0[tl * tp2_size + tp], a1 = r1[tl * tp2_size + tp];
+          if (m >= 0) {
+            const int e = m & 0xffffff;
+            const double2 a0 = r0[e], a1 = r1[e];
             // transfer2.c:2697 (linear: dd = 0) / :2703-2705 (cubic)
-            v = s_sign[g * TC_SLOTS + slot] * (w.a * a0.x + w.b * a1.x + w.a3h * a0.y + w.b3h * a1.y);
+            v = sgn[m >> 24] * (w.a * a0.x + w.b * a1.x + w.a3h * a0.y + w.b3h * a1.y);
           }
           dst[c] = v;
         }
@@ -878,10 +892,13 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
 
   // warp grid (WM x WN consumer warps, NW sub-blocks per warp): widest tile of units that still
   // covers the columns of a block in one pass
+  // (measured on B200: sn_t_10percent 7.0 ms with (12,1,8) vs 7.3 ms with (8,1,8); sn_pol_10percent 16.1 ms with
+  //  (6,2,5) vs 16.7 ms with (8,1,10); sn_pol_5percent_lmax3000 357 ms with (4,3,7) vs 367 ms with (2,4,8))
   if (max_sb <= 8) { fs->wm = 12; fs->wn = 1; fs->nw = 8; }     // three consumer warps per SM sub-partition
-  else if (max_sb <= 10) { fs->wm = 8; fs->wn = 1; fs->nw = 10; }
+  else if (max_sb <= 10) { fs->wm = 6; fs->wn = 2; fs->nw = 5; }
   else if (max_sb <= 16) { fs->wm = 4; fs->wn = 2; fs->nw = 8; }
   else if (max_sb <= 20) { fs->wm = 4; fs->wn = 2; fs->nw = 10; }
+  else if (max_sb <= 21) { fs->wm = 4; fs->wn = 3; fs->nw = 7; }
   else if (max_sb <= 32) { fs->wm = 2; fs->wn = 4; fs->nw = 8; }
   else { fs->wm = 2; fs->wn = 4; fs->nw = 10; }
   if (const char *v = getenv("SONG_LOS_TC_SHAPE")) {          // A/B measurements: "wm,wn,nw"
@@ -1092,7 +1109,8 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
                                                                      fs->uw.p, fs->ujp.p, fs->jcount.p, P.err);
     FCK(cudaGetLastError());
     dim3 grid((unsigned)b.n_pairs, (unsigned)((tau_size + I.tauc - 1) / I.tauc));
-    const size_t ismem = (size_t)2 * I.tauc * tp2 * 16 + (size_t)TC_MAX_GROUPS * TC_SLOTS * 12;
+    I.col_stride = I.tauc * fs->tpp_max;
+    const size_t ismem = (size_t)2 * I.tauc * tp2 * 16 + (size_t)TC_MAX_GROUPS * TC_SLOTS * 12 + (size_t)fs->n_groups * I.col_stride * 4;
     FCK(cudaFuncSetAttribute(tc_interp_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
     tc_interp_units_kernel<<<grid, TC_INTERP_THREADS, ismem, st>>>(b, I, tau_size, tp2, fs->CSD.p, fs->uw.p, fs->ujp.p, fs->S.p);
     FCK(cudaGetLastError());
