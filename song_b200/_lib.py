@@ -142,7 +142,8 @@ LOS_SYMBOLS = [
     "song_los_submit", "song_los_wait", "song_los_host_alloc", "song_los_host_free", "song_los_max_batch_units", "song_los_reserve",
 ]
 HOST_SYMBOLS = ["song_host_k3_size", "song_host_k3_list", "song_host_k3_sizes", "song_host_k3_lists",
-                "song_host_bessel2_prepare", "song_host_bessel2_free", "song_host_bessel2_upload"]
+                "song_host_bessel2_prepare", "song_host_bessel2_free", "song_host_bessel2_upload",
+                "song_host_lpt_schedule"]
 
 _los = None
 _host = None
@@ -208,6 +209,7 @@ def host():
         lib.song_host_bessel2_free.argtypes = [C.POINTER(Bessel2Host)]
         lib.song_host_bessel2_upload.argtypes = [C.c_void_p, C.POINTER(Bessel2Host), c_int_p, C.c_double, C.c_double,
                                                  C.c_char_p, C.c_int]
+        lib.song_host_lpt_schedule.argtypes = [c_int64_p, C.c_int, C.c_int, c_int_p, c_int64_p]
         lib.compat_drc3jj.argtypes = [C.c_double] * 4 + [c_double_p, c_double_p, c_double_p, C.c_int]
         lib.compat_bessel_j.argtypes = [C.c_int, C.c_double]
         lib.compat_bessel_j.restype = C.c_double

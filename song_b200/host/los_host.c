@@ -9,6 +9,7 @@
  */
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "los_host.h"
 
@@ -163,5 +164,45 @@ int song_host_k3_lists(const song_k3_params *p, int n_pairs, const int *k3_pt_si
     if (song_host_k3_list(p, k3_pt + pt_off[i], k3_pt_size[i], &ranges[i], k3_tr + tr_off[i], NULL,
                           errmsg, errlen))
       return 1;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/*  multi-GPU partition of the (k1,k2) work: static LPT                               */
+/* ------------------------------------------------------------------------------------------------ */
+int song_host_lpt_schedule(const int64_t *cost, int n, int n_dev, int *device, int64_t *load)
+{
+  if (!cost || !device || n < 0 || n_dev < 1) return 1;
+  int64_t *l = (int64_t *)calloc((size_t)n_dev, sizeof(int64_t));
+  int *order = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  if (!l || !order) { free(l); free(order); return 1; }
+  for (int i = 0; i < n; ++i) order[i] = i;
+  /* stable insertion sort by decreasing cost (n = number of k1 batches, small) -- for long pair lists a
+     merge sort keeps the same order */
+  if (n <= 2048) {
+    for (int i = 1; i < n; ++i)
+      for (int j = i; j > 0 && cost[order[j]] > cost[order[j - 1]]; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+  } else {
+    int *tmp = (int *)malloc(sizeof(int) * (size_t)n);
+    if (!tmp) { free(l); free(order); return 1; }
+    for (int w = 1; w < n; w *= 2) {
+      for (int lo = 0; lo < n; lo += 2 * w) {
+        int mid = lo + w < n ? lo + w : n, hi = lo + 2 * w < n ? lo + 2 * w : n;
+        int a = lo, b = mid, o = lo;
+        while (a < mid && b < hi) tmp[o++] = (cost[order[b]] > cost[order[a]]) ? order[b++] : order[a++];
+        while (a < mid) tmp[o++] = order[a++];
+        while (b < hi) tmp[o++] = order[b++];
+      }
+      int *sw = order; order = tmp; tmp = sw;
+    }
+    free(tmp);
+  }
+  for (int i = 0; i < n; ++i) {
+    int best = 0;
+    for (int d = 1; d < n_dev; ++d) if (l[d] < l[best]) best = d;
+    device[order[i]] = best; l[best] += cost[order[i]];
+  }
+  if (load) for (int d = 0; d < n_dev; ++d) load[d] = l[d];
+  free(l); free(order);
   return 0;
 }

@@ -48,6 +48,13 @@ int song_host_k3_lists(const song_k3_params *p, int n_pairs, const int *k3_pt_si
                        const int64_t *pt_off, const double *k3_pt, const song_k3_range *ranges,
                        const int64_t *tr_off, double *k3_tr, char *errmsg, int errlen);
 
+/* Static longest-processing-time schedule of `n` work items (k1 batches, or (k1,k2) pairs) over `n_dev`
+   GPUs: items by decreasing cost (ties: lower index first), each to the least loaded device (ties: lower
+   device).  cost[i] = k3 values of item i x tt2_size x tau_size x (L_max+1) up to a common factor
+   (SURVEY.md 8e).  Writes device[i] and, when load != NULL, the per-device totals.  Returns 0, or 1 on
+   bad arguments. */
+int song_host_lpt_schedule(const int64_t *cost, int n, int n_dev, int *device, int64_t *load);
+
 #ifdef __cplusplus
 }
 #endif

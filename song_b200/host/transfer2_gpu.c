@@ -679,17 +679,12 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
 
   /* static longest-processing-time schedule: batches by decreasing size to the least loaded device */
   {
-    long *load = calloc(n_dev, sizeof(long));
-    int *order = malloc(n_batches * sizeof(int));
-    for (int i = 0; i < n_batches; ++i) order[i] = i;
-    for (int i = 1; i < n_batches; ++i)
-      for (int j = i; j > 0 && batches[order[j]].n_units > batches[order[j - 1]].n_units; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
-    for (int i = 0; i < n_batches; ++i) {
-      int best = 0;
-      for (int d = 1; d < n_dev; ++d) if (load[d] < load[best]) best = d;
-      batches[order[i]].device = best; load[best] += batches[order[i]].n_units;
-    }
-    free(load); free(order);
+    int64_t *cost = malloc(sizeof(int64_t) * (n_batches > 0 ? n_batches : 1));
+    int *where = malloc(sizeof(int) * (n_batches > 0 ? n_batches : 1));
+    for (int i = 0; i < n_batches; ++i) cost[i] = batches[i].n_units;
+    song_host_lpt_schedule(cost, n_batches, n_dev, where, NULL);
+    for (int i = 0; i < n_batches; ++i) batches[i].device = where[i];
+    free(cost); free(where);
   }
 
   /* Per GPU: a pipeline of up to SONG_LOS_MAX_IN_FLIGHT batches (in k1 order).  While the kernels of batch n run, the host

@@ -1,0 +1,68 @@
+"""Multi-GPU partition of the (k1,k2) work and the gather of the per-GPU transfer arrays.
+
+The (k1,k2) pairs are independent (reference source/transfer2.c:549-551): every rank computes the
+pairs the static longest-processing-time schedule gives it (`song_host_lpt_schedule`, the same C
+function the drop-in module uses for its k1 batches) and the results are gathered on rank 0 in the
+reference's [tt][k1][k2][k3] order.  The gather is the only collective of the path
+(``torch.distributed``: NCCL between GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def lpt_schedule(cost, n_ranks: int):
+    """device[i] of every work item and the per-rank loads (C: song_host_lpt_schedule)."""
+    cost = np.ascontiguousarray(cost, dtype=np.int64)
+    dev = np.zeros(cost.size, dtype=np.int32)
+    load = np.zeros(n_ranks, dtype=np.int64)
+    if _lib.host().song_host_lpt_schedule(_lib.lptr(cost), int(cost.size), int(n_ranks), _lib.iptr(dev), _lib.lptr(load)):
+        raise _lib.SongLosError("song_host_lpt_schedule: bad arguments")
+    return dev, load
+
+
+def pair_cost(wl) -> np.ndarray:
+    """Cost model of SURVEY.md 8e per (k1,k2) pair: k3 values x tt2_size x tau_size x (L_max+1)."""
+    lay = wl.layout
+    return wl.k3_tr_size.astype(np.int64) * lay.tt2_size * int(wl.tau.size) * lay.L_size
+
+
+def shard_pairs(wl, rank: int, world: int) -> np.ndarray:
+    """Indices (ascending, i.e. reference loop order) of the pairs rank `rank` owns."""
+    dev, _ = lpt_schedule(pair_cost(wl), world)
+    return np.nonzero(dev == rank)[0]
+
+
+def gather_transfers(local: np.ndarray, wl, owned: np.ndarray, rank: int, world: int, dist=None, device="cpu"):
+    """Gather the [tt2_size][units of the owned pairs] arrays of all ranks on rank 0 and assemble
+    ptr2->transfer as [tt2_size][n_units] in the reference pair order.  Returns None on other ranks."""
+    import torch
+    tt2 = wl.layout.tt2_size
+    if world == 1:
+        full = np.empty((tt2, wl.n_units))
+        _scatter_into(full, local, wl, owned)
+        return full
+    sizes = [int(wl.k3_tr_size[shard_pairs(wl, r, world)].sum()) * tt2 for r in range(world)]   # known to every rank
+    n_max = max(sizes)
+    buf = torch.zeros(n_max, dtype=torch.float64, device=device)                 # ragged -> padded (no gatherv)
+    buf[:local.size] = torch.from_numpy(np.ascontiguousarray(local).reshape(-1)).to(device)
+    bufs = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, bufs, dst=0)
+    if rank != 0:
+        return None
+    full = np.empty((tt2, wl.n_units))
+    for r in range(world):
+        own_r = shard_pairs(wl, r, world)
+        part = bufs[r][:sizes[r]].cpu().numpy().reshape(tt2, -1)
+        _scatter_into(full, part, wl, own_r)
+    return full
+
+
+def _scatter_into(full, part, wl, owned):
+    o = 0
+    for ip in owned:
+        n = int(wl.k3_tr_size[ip]); a = int(wl.tr_off[ip])
+        full[:, a:a + n] = part[:, o:o + n]
+        o += n
