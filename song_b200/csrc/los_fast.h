@@ -30,8 +30,9 @@ void fast_invalidate_table(FastState *);
 int fast_prepare(FastState *fs, const FastHostLayout &h, const ExactParams &P, cudaStream_t st, std::string &err);
 int64_t fast_bytes_per_unit(const FastState *fs);
 int fast_reserve(FastState *fs, int64_t n_units, int64_t n_src, int64_t n_pt, std::string &err);
+constexpr int FAST_MAX_EVENTS = 32;     // 5 phase boundaries + 2 per (column block, K chunk) launch
 int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, int device_sms, cudaStream_t st,
-                 cudaEvent_t *ev /* [5] */, int *n_launches, std::string &err);
-int fast_collect(cudaEvent_t *ev, song_los_timing *tm, std::string &err);
+                 cudaEvent_t *ev /* [FAST_MAX_EVENTS] */, int *n_launches, int *n_chunks, std::string &err);
+int fast_collect(cudaEvent_t *ev, int n_chunks, song_los_timing *tm, std::string &err);
 
 }  // namespace songlos

@@ -91,6 +91,9 @@ struct TcParams {
   int hdr_bytes, a_bytes, b_row_bytes, stage_bytes;  // shared-memory geometry of one stage
   double *out; int64_t out_stride;        // [tt][n_units]
   int *err;
+  int pass_begin, pass_end;               // passes of this launch (one column block)
+  int q_fixed;                            // K chunk of this launch (-1: all chunks of the block)
+  int acc_in, acc_final;                  // accumulators start from the partial sums in `out` / are scaled and final
   int dbg;                                // timing experiments only (results invalid): 4 = no MMAs, 8 = no source copies, 16 = no table copies
 };
 
@@ -639,7 +642,7 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
           x_n[i] = x_; ix_n[i] = ix_; \
           xxn_n[i] = P.xx_uniform ? (double)(ix_ + 1) * P.xx_step : __ldg(P.xx + ix_ + 1); } } while (0)
       TC_PREFETCH(0);
-      for (int ip = 0; ip < P.n_pass; ++ip) {
+      for (int ip = P.pass_begin; ip < P.pass_end; ++ip) {
         const TcPass ps = P.pass[ip];
         if (pw == 0) {
           // Table rows of the tile at every tau (units are k3-sorted: rows span [row(first), row(last)]) and the
@@ -656,7 +659,7 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
           }
           __syncwarp();
         }
-        for (int q = 0; q < ps.nq; ++q) {
+        for (int q = (P.q_fixed >= 0 ? P.q_fixed : 0); q < (P.q_fixed >= 0 ? P.q_fixed + 1 : ps.nq); ++q) {
           const TcGroup G = P.grp[ps.g0 + q];
           const uint32_t bytes_per_sb = (uint32_t)G.kcs * 256u;
           const uint32_t s_bytes = (uint32_t)MT * G.tpp * 8u;
@@ -711,14 +714,34 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
   const int ksel = lane & 1, tsel = (lane & 3) >> 1;   // weight {c0,c1} and term of the kc held by this lane
   int tbuf = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tbuf ^= 1) {
-    for (int ip = 0; ip < P.n_pass; ++ip) {
+    for (int ip = P.pass_begin; ip < P.pass_end; ++ip) {
       const TcPass ps = P.pass[ip];
       const TcBlock B = P.blk[ps.blk];
       double acc0[NW][2], acc1[NW][2];
 #pragma unroll
       for (int j = 0; j < NW; ++j) { acc0[j][0] = acc0[j][1] = 0.; acc1[j][0] = acc1[j][1] = 0.; }
+      if (P.acc_in) {
+        // later K chunk of the block: continue from the unscaled partial sums the previous launch left in `out`
+        // (the producer has filled unit_id[tbuf] before the first stage of the tile can complete: wait for it)
+        mbar_wait(smem_u32(&bars[s]), ph);
+        const int cpair = 2 * (lane & 3);
+        const int u0 = unit_id[tbuf * MT + g0 * 8 + um], u1 = unit_id[tbuf * MT + g1 * 8 + um];
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+          const int sb = warp_n + j * WN;
+          if (sb >= ps.nsb) continue;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = (ps.sb0 + sb) * 8 + cpair + h;
+            if (c >= B.ncols) continue;
+            const int tt = col_tt_s[B.col_off + c];
+            if (u0 >= 0) acc0[j][h] = P.out[(int64_t)tt * P.out_stride + u0];
+            if (u1 >= 0) acc1[j][h] = P.out[(int64_t)tt * P.out_stride + u1];
+          }
+        }
+      }
 
-      for (int q = 0; q < ps.nq; ++q) {
+      for (int q = (P.q_fixed >= 0 ? P.q_fixed : 0); q < (P.q_fixed >= 0 ? P.q_fixed + 1 : ps.nq); ++q) {
         const TcGroup G = P.grp[ps.g0 + q];
         const int kcs_q = G.kcs;
         const int b_sb_stride = WN * kcs_q * 32;
@@ -768,7 +791,7 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
           if (c >= B.ncols) continue;
           const int tt = col_tt_s[B.col_off + c];
           const double scale = col_scale_s[B.col_off + c];
-          const double t0 = acc0[j][h] * scale, t1 = acc1[j][h] * scale;
+          const double t0 = P.acc_final ? acc0[j][h] * scale : acc0[j][h], t1 = P.acc_final ? acc1[j][h] * scale : acc1[j][h];
           if (u0 >= 0) { if (t0 != t0) atomicOr(P.err, ERR_NAN); P.out[(int64_t)tt * P.out_stride + u0] = t0; }
           if (u1 >= 0) { if (t1 != t1) atomicOr(P.err, ERR_NAN); P.out[(int64_t)tt * P.out_stride + u1] = t1; }
         }
@@ -804,7 +827,7 @@ struct FastState {
   int64_t jq_row = 0;
   int64_t s_doubles_per_unit = 0;        // sum over groups of tau_size * tpp
   int wm = 8, wn = 1, nw = 8;
-  int kcs_max = 1, nsb_pass_max = 1, tpp_max = 4, n_cols_total = 0;
+  int kcs_max = 1, nsb_pass_max = 1, tpp_max = 4, n_cols_total = 0, tau_size = 0;
   Buf<double> Jq, keys_out, S, slot_sign, col_scale;
   Buf<double2> CSD;
   Buf<int> col_tt, col_l, col_lm, term_col0, nact, perm_in, perm, unit_pair, slot_tp, jcount;
@@ -954,6 +977,7 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
     }
   }
   fs->jq_row = off;
+  fs->tau_size = h.tau_size;
   fs->s_doubles_per_unit = s_per_unit;
 
   auto up = [&](auto &buf, const auto &vec) -> cudaError_t {
@@ -1018,7 +1042,7 @@ int fast_prepare(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
 // slab S plus the per-unit sort / weight arrays
 int64_t fast_bytes_per_unit(const FastState *fs)
 {
-  return fs->s_doubles_per_unit * 8 + 8 /*keys*/ + 3 * 4 /*perm_in, perm, unit_pair*/ + (int64_t)sizeof(TcUnitW) + 8 /*ujp*/ + 16 /*cub*/;
+  return (int64_t)fs->tau_size * fs->tpp_max * 8 + 8 /*keys*/ + 3 * 4 /*perm_in, perm, unit_pair*/ + (int64_t)sizeof(TcUnitW) + 8 /*ujp*/ + 16 /*cub*/;
 }
 
 // Allocates every intermediate of the FAST path for batches of up to U k3 values / n_src source doubles /
@@ -1034,7 +1058,7 @@ int fast_reserve(FastState *fs, int64_t U, int64_t n_src, int64_t n_pt, std::str
                                       (int)U, 0, 64, (cudaStream_t)0));
   FCK(fs->cub_tmp.reserve(tmp_bytes));
   FCK(fs->uw.reserve((size_t)U)); FCK(fs->ujp.reserve((size_t)U));
-  FCK(fs->S.reserve((size_t)U * fs->s_doubles_per_unit));
+  FCK(fs->S.reserve((size_t)U * fs->tau_size * fs->tpp_max));
   FCK(fs->jcount.reserve((size_t)n_pt));
   return 0;
 }
@@ -1042,7 +1066,7 @@ int fast_reserve(FastState *fs, int64_t U, int64_t n_src, int64_t n_pt, std::str
 // Enqueues the whole FAST pipeline on `st` and returns without waiting; ev[0..4] (caller-owned) are
 // recorded at the phase boundaries and read later by fast_collect.
 int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, int device_sms, cudaStream_t st,
-                 cudaEvent_t *ev, int *n_launches, std::string &err)
+                 cudaEvent_t *ev, int *n_launches, int *n_chunks_out, std::string &err)
 {
   if (fast_prepare(fs, h, P, st, err)) return 1;
   const Batch &b = P.b;
@@ -1084,46 +1108,28 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
   }
   FCK(cudaEventRecord(ev[2], st));
 
-  // ---- phase 2: interpolated sources in consumption order ----
+  // ---- phase 2: per-unit k3 brackets and spline weights ----
   FCK(fs->uw.reserve((size_t)U)); FCK(fs->ujp.reserve((size_t)U));
-  FCK(fs->S.reserve((size_t)U * fs->s_doubles_per_unit));
-  TcInterp &I = fs->interp;
-  I = TcInterp{};
-  I.n_groups = fs->n_groups;
-  {
-    int64_t s_off = 0;
-    for (int g = 0; g < fs->n_groups; ++g) {
-      fs->grp[g].s_off = s_off;
-      I.grp_tpp[g] = fs->grp[g].tpp; I.grp_s_off[g] = s_off;
-      s_off += U * (int64_t)tau_size * fs->grp[g].tpp;
-    }
-  }
-  I.slot_tp = fs->slot_tp.p; I.slot_sign = fs->slot_sign.p;
+  FCK(fs->S.reserve((size_t)U * tau_size * fs->tpp_max));
   FCK(fs->jcount.reserve((size_t)h.n_pt_total));
-  I.jcount = fs->jcount.p;
-  // tau samples per CTA: two staged rows of tauc*tp2 {y, dd} entries within ~64 KB
-  I.tauc = std::max(1, std::min(tau_size, (int)((64 * 1024) / (2 * 16 * (size_t)tp2))));
   if (U > 0) {
     FCK(cudaMemsetAsync(fs->jcount.p, 0, (size_t)h.n_pt_total * sizeof(int), st));
     tc_prep_units_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(b, fs->perm.p, fs->unit_pair.p, P.flat_extrap,
                                                                      fs->uw.p, fs->ujp.p, fs->jcount.p, P.err);
     FCK(cudaGetLastError());
-    dim3 grid((unsigned)b.n_pairs, (unsigned)((tau_size + I.tauc - 1) / I.tauc));
-    I.col_stride = I.tauc * fs->tpp_max;
-    const size_t ismem = (size_t)2 * I.tauc * tp2 * 16 + (size_t)TC_MAX_GROUPS * TC_SLOTS * 12 + (size_t)fs->n_groups * I.col_stride * 4;
-    FCK(cudaFuncSetAttribute(tc_interp_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
-    tc_interp_units_kernel<<<grid, TC_INTERP_THREADS, ismem, st>>>(b, I, tau_size, tp2, fs->CSD.p, fs->uw.p, fs->ujp.p, fs->S.p);
-    FCK(cudaGetLastError());
-    *n_launches += 2;
+    ++*n_launches;
   }
   FCK(cudaEventRecord(ev[3], st));
 
-  // ---- phase 3: the DMMA kernel ----
+  // ---- phase 3: per (column block, K chunk): interpolated sources of the chunk, then the DMMA kernel ----
+  // One source slab S (the largest chunk's size) is reused by every chunk: the slab is what limits the number of
+  // k3 values per batch, and the kernel's efficiency grows with that number (more k3 values per table row).
+  // Later chunks of a block start from the unscaled partial sums the previous launch left in `out`.
   TcParams &TP = fs->tp;
   TP = TcParams{};
   TP.n_blocks = fs->n_blocks; TP.n_groups = fs->n_groups; TP.n_pass = fs->n_pass;
   for (int i = 0; i < fs->n_blocks; ++i) TP.blk[i] = fs->blk[i];
-  for (int i = 0; i < fs->n_groups; ++i) TP.grp[i] = fs->grp[i];
+  for (int i = 0; i < fs->n_groups; ++i) { TP.grp[i] = fs->grp[i]; TP.grp[i].s_off = 0; }
   for (int i = 0; i < fs->n_pass; ++i) TP.pass[i] = fs->pass[i];
   TP.col_tt = fs->col_tt.p; TP.col_scale = fs->col_scale.p;
   TP.Jq = fs->Jq.p; TP.jq_row = fs->jq_row; TP.nact = fs->nact.p;
@@ -1135,19 +1141,6 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
   if (getenv("SONG_LOS_TC_XX_TABLE")) TP.xx_uniform = 0;
   TP.out = b.out; TP.out_stride = U; TP.err = P.err;
   if (const char *v = getenv("SONG_LOS_TC_DBG")) TP.dbg = atoi(v);
-  if (U > 0) {
-    for (int g = 0; g < fs->n_groups; ++g) {
-      const TcGroup &G = fs->grp[g];
-      cuuint64_t gdim[3] = {(cuuint64_t)G.tpp, (cuuint64_t)tau_size, (cuuint64_t)U};
-      cuuint64_t gstr[2] = {(cuuint64_t)G.tpp * 8, (cuuint64_t)G.tpp * 8 * (cuuint64_t)tau_size};
-      cuuint32_t box[3] = {(cuuint32_t)G.tpp, 1u, (cuuint32_t)MT};
-      cuuint32_t estr[3] = {1u, 1u, 1u};
-      CUresult r = fs->encode(&TP.tmap[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, fs->S.p + G.s_off, gdim, gstr, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r); return 1; }
-    }
-  }
 
   auto r128 = [](size_t x) { return (x + 127) / 128 * 128; };
   TP.hdr_bytes = (int)r128(16 + (size_t)MT * 4 + (size_t)MT * 16);
@@ -1167,43 +1160,89 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
   TP.stage_bytes = (int)stage_bytes(rmax);
   const size_t smem = fixed + (size_t)ns * TP.stage_bytes;
 
-  if (n_tiles > 0) {
-    cudaError_t e = cudaErrorInvalidValue;
-    const int key = fs->wm * 10000 + fs->wn * 100 + fs->nw;
-    const int64_t n_ctas = std::min<int64_t>(n_tiles, std::max(1, device_sms));     // persistent: one CTA per SM
-    const int np1 = getenv("SONG_LOS_TC_NP1") != nullptr;     // A/B: a single producer warp
-    switch (key) {
-      case 80108:  e = np1 ? launch_tc<8, 1, 8, 1>(TP, n_ctas, smem, st) : launch_tc<8, 1, 8, 4>(TP, n_ctas, smem, st); break;
-      case 80110:  e = launch_tc<8, 1, 10, 4>(TP, n_ctas, smem, st); break;
-      case 40208:  e = launch_tc<4, 2, 8, 2>(TP, n_ctas, smem, st); break;
-      case 40210:  e = launch_tc<4, 2, 10, 2>(TP, n_ctas, smem, st); break;
-      case 20408:  e = launch_tc<2, 4, 8, 1>(TP, n_ctas, smem, st); break;
-      case 20410:  e = launch_tc<2, 4, 10, 1>(TP, n_ctas, smem, st); break;
-      // three consumer warps per SM sub-partition
-      case 120107: e = launch_tc<12, 1, 7, 3>(TP, n_ctas, smem, st); break;
-      case 120108: e = np1 ? launch_tc<12, 1, 8, 3>(TP, n_ctas, smem, st) : launch_tc<12, 1, 8, 1>(TP, n_ctas, smem, st); break;
-      case 60205:  e = launch_tc<6, 2, 5, 1>(TP, n_ctas, smem, st); break;
-      case 60208:  e = launch_tc<6, 2, 8, 1>(TP, n_ctas, smem, st); break;
-      case 40307:  e = launch_tc<4, 3, 7, 1>(TP, n_ctas, smem, st); break;
-      case 40308:  e = launch_tc<4, 3, 8, 1>(TP, n_ctas, smem, st); break;
-      case 80205:  e = launch_tc<8, 2, 5, 2>(TP, n_ctas, smem, st); break;
-      default: err = "FAST kernel: no instantiation for the requested warp grid"; return 1;
+  TcInterp &I = fs->interp;
+  // tau samples per CTA: two staged rows of tauc*tp2 {y, dd} entries within ~64 KB
+  const int tauc = std::max(1, std::min(tau_size, (int)((64 * 1024) / (2 * 16 * (size_t)tp2))));
+  int n_chunks = 0;
+  for (int ib = 0; ib < fs->n_blocks && U > 0; ++ib) {
+    int pb = fs->n_pass, pe = 0;
+    for (int ip = 0; ip < fs->n_pass; ++ip) if (fs->pass[ip].blk == ib) { pb = std::min(pb, ip); pe = std::max(pe, ip + 1); }
+    if (pb >= pe) continue;
+    const int g_first = fs->pass[pb].g0, nq = fs->pass[pb].nq;
+    for (int q = 0; q < nq; ++q, ++n_chunks) {
+      const int g = g_first + q;
+      const TcGroup &G = fs->grp[g];
+      if (5 + 2 * n_chunks + 1 >= FAST_MAX_EVENTS) { err = "FAST path: too many K chunks for the timing events"; return 1; }
+      FCK(cudaEventRecord(ev[5 + 2 * n_chunks], st));
+      // interpolated, sign-folded sources of this chunk: S[sorted unit][tau][slot]
+      I = TcInterp{};
+      I.n_groups = 1; I.tauc = tauc;
+      I.grp_tpp[0] = G.tpp; I.grp_s_off[0] = 0;
+      I.slot_tp = fs->slot_tp.p + (size_t)g * TC_SLOTS; I.slot_sign = fs->slot_sign.p + (size_t)g * TC_SLOTS;
+      I.jcount = fs->jcount.p;
+      I.col_stride = I.tauc * G.tpp;
+      dim3 grid((unsigned)b.n_pairs, (unsigned)((tau_size + I.tauc - 1) / I.tauc));
+      const size_t ismem = (size_t)2 * I.tauc * tp2 * 16 + (size_t)TC_MAX_GROUPS * TC_SLOTS * 12 + (size_t)I.col_stride * 4;
+      FCK(cudaFuncSetAttribute(tc_interp_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
+      tc_interp_units_kernel<<<grid, TC_INTERP_THREADS, ismem, st>>>(b, I, tau_size, tp2, fs->CSD.p, fs->uw.p, fs->ujp.p, fs->S.p);
+      FCK(cudaGetLastError());
+      ++*n_launches;
+      FCK(cudaEventRecord(ev[6 + 2 * n_chunks], st));
+
+      {
+        cuuint64_t gdim[3] = {(cuuint64_t)G.tpp, (cuuint64_t)tau_size, (cuuint64_t)U};
+        cuuint64_t gstr[2] = {(cuuint64_t)G.tpp * 8, (cuuint64_t)G.tpp * 8 * (cuuint64_t)tau_size};
+        cuuint32_t box[3] = {(cuuint32_t)G.tpp, 1u, (cuuint32_t)MT};
+        cuuint32_t estr[3] = {1u, 1u, 1u};
+        CUresult r = fs->encode(&TP.tmap[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, fs->S.p, gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r); return 1; }
+      }
+      TP.pass_begin = pb; TP.pass_end = pe; TP.q_fixed = q;
+      TP.acc_in = (q > 0); TP.acc_final = (q == nq - 1);
+      cudaError_t e = cudaErrorInvalidValue;
+      const int key = fs->wm * 10000 + fs->wn * 100 + fs->nw;
+      const int64_t n_ctas = std::min<int64_t>(n_tiles, std::max(1, device_sms));     // persistent: one CTA per SM
+      const int np1 = getenv("SONG_LOS_TC_NP1") != nullptr;     // A/B: a single producer warp
+      switch (key) {
+        case 80108:  e = np1 ? launch_tc<8, 1, 8, 1>(TP, n_ctas, smem, st) : launch_tc<8, 1, 8, 4>(TP, n_ctas, smem, st); break;
+        case 80110:  e = launch_tc<8, 1, 10, 4>(TP, n_ctas, smem, st); break;
+        case 40208:  e = launch_tc<4, 2, 8, 2>(TP, n_ctas, smem, st); break;
+        case 40210:  e = launch_tc<4, 2, 10, 2>(TP, n_ctas, smem, st); break;
+        case 20408:  e = launch_tc<2, 4, 8, 1>(TP, n_ctas, smem, st); break;
+        case 20410:  e = launch_tc<2, 4, 10, 1>(TP, n_ctas, smem, st); break;
+        // three consumer warps per SM sub-partition
+        case 120107: e = launch_tc<12, 1, 7, 3>(TP, n_ctas, smem, st); break;
+        case 120108: e = np1 ? launch_tc<12, 1, 8, 3>(TP, n_ctas, smem, st) : launch_tc<12, 1, 8, 1>(TP, n_ctas, smem, st); break;
+        case 60205:  e = launch_tc<6, 2, 5, 1>(TP, n_ctas, smem, st); break;
+        case 60208:  e = launch_tc<6, 2, 8, 1>(TP, n_ctas, smem, st); break;
+        case 40307:  e = launch_tc<4, 3, 7, 1>(TP, n_ctas, smem, st); break;
+        case 40308:  e = launch_tc<4, 3, 8, 1>(TP, n_ctas, smem, st); break;
+        case 80205:  e = launch_tc<8, 2, 5, 2>(TP, n_ctas, smem, st); break;
+        default: err = "FAST kernel: no instantiation for the requested warp grid"; return 1;
+      }
+      FCK(e);
+      ++*n_launches;
     }
-    FCK(e);
-    ++*n_launches;
   }
   FCK(cudaEventRecord(ev[4], st));
+  *n_chunks_out = n_chunks;
   return 0;
 }
 
-int fast_collect(cudaEvent_t *ev, song_los_timing *tm, std::string &err)
+int fast_collect(cudaEvent_t *ev, int n_chunks, song_los_timing *tm, std::string &err)
 {
   FCK(cudaEventSynchronize(ev[4]));
   float ms;
   FCK(cudaEventElapsedTime(&ms, ev[0], ev[1])); tm->ms_spline = ms;
   FCK(cudaEventElapsedTime(&ms, ev[1], ev[2])); tm->ms_sort = ms;
-  FCK(cudaEventElapsedTime(&ms, ev[2], ev[3])); tm->ms_interp = ms;
-  FCK(cudaEventElapsedTime(&ms, ev[3], ev[4])); tm->ms_integrate = ms;
+  FCK(cudaEventElapsedTime(&ms, ev[2], ev[3])); tm->ms_interp = ms;            // prep_units
+  tm->ms_integrate = 0.f;
+  for (int i = 0; i < n_chunks; ++i) {
+    FCK(cudaEventElapsedTime(&ms, ev[5 + 2 * i], ev[6 + 2 * i])); tm->ms_interp += ms;
+    FCK(cudaEventElapsedTime(&ms, ev[6 + 2 * i], i + 1 < n_chunks ? ev[5 + 2 * (i + 1)] : ev[4])); tm->ms_integrate += ms;
+  }
   FCK(cudaEventElapsedTime(&ms, ev[0], ev[4])); tm->ms_total = ms;
   return 0;
 }

@@ -555,7 +555,7 @@ static int enqueue_compute(song_los_ctx *ctx, song_los_ctx::Slot &S, int mode)
     std::string e;
     FastHostLayout h;
     fill_fast_layout(ctx, S, h);
-    if (fast_enqueue(ctx->fast, h, P, ctx->sm_count, st, S.ev_t, &t.n_launches, e) != 0)
+    if (fast_enqueue(ctx->fast, h, P, ctx->sm_count, st, S.ev_t, &t.n_launches, &S.n_chunks, e) != 0)
       return ctx_fail(ctx, "%s", e.c_str());
     S.fast_timed = true;
   }
@@ -573,7 +573,7 @@ static int finish_compute(song_los_ctx *ctx, song_los_ctx::Slot &S)
   song_los_timing &t = S.t;
   if (S.fast_timed) {
     std::string e;
-    if (fast_collect(S.ev_t, &t, e) != 0) return ctx_fail(ctx, "%s", e.c_str());
+    if (fast_collect(S.ev_t, S.n_chunks, &t, e) != 0) return ctx_fail(ctx, "%s", e.c_str());
   } else {
     CK(cudaEventElapsedTime(&t.ms_spline, S.ev_t[0], S.ev_t[1]));
     CK(cudaEventElapsedTime(&t.ms_integrate, S.ev_t[1], S.ev_t[2]));

@@ -59,7 +59,8 @@ struct song_los_ctx {
     DevBuf<int2> d_tiles; int n_tiles = 0; bool tiles_ready = false;
     int max_np = 0;               // largest coarse k3 grid of the batch
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr, ev_h2d_start = nullptr, ev_d2h_start = nullptr;
-    cudaEvent_t ev_t[6]{};        // phase boundaries of this slot's compute
+    cudaEvent_t ev_t[songlos::FAST_MAX_EVENTS]{};   // phase boundaries of this slot's compute
+    int n_chunks = 0;             // (column block, K chunk) launches of the last FAST compute
     int *h_err = nullptr;         // pinned copy of the device error flags after this slot's compute
     bool have_batch = false, have_result = false, in_flight = false, fast_timed = false, with_d2h = false;
     song_los_timing t{};

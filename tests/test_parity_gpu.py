@@ -129,6 +129,16 @@ def test_fast_many_columns_layouts(oracle):
         assert rel_err_above_floor(got, ref) < REL_TOL
 
 
+def test_fast_several_k_chunks(oracle):
+    """l_max_los = 14: 15 (T) and 13 (E) terms -> two K chunks per column block, i.e. two kernel launches per block,
+    the second one continuing from the partial sums of the first (the path the 5 % BASELINE workloads take)."""
+    p = configs.tiny(l_max_los_t=14, l_max_los_p=14, sources_k3_interpolation="cubic")
+    for kind in ("smooth", "noise"):
+        wl, ref, got = run_both(oracle, p, kind=kind, mode=MODE_FAST)
+        assert wl.layout.L_size == 15
+        assert rel_err_above_floor(got, ref) < REL_TOL
+
+
 def test_fast_rejects_cubic_bessel_interpolation(oracle):
     p = configs.tiny(bessels_interpolation="cubic")
     from song_b200._lib import SongLosError
