@@ -71,28 +71,39 @@ kern = {"ms_total": 0.0, "ms_integrate": 0.0, "ms_interp": 0.0, "ms_spline": 0.0
 launches = 0
 worst = 0.0
 exact_equal = True
+checked = []
+tt_max = np.zeros(lay.tt2_size)
 t_gen = 0.0
 t_wall0 = time.time()
 t_gpu_wall = 0.0
 
 
 def finish():
-    global launches, worst, exact_equal
+    global launches, worst, exact_equal, tt_max
     sub, out, lo = inflight.pop(0)
     tm = eng.wait()
     for k in kern:
         kern[k] += tm[k]
     launches += tm["n_launches"]
+    tt_max = np.maximum(tt_max, np.abs(out).max(axis=1))       # per-(l,m) maximum over every (k1,k2,k3) of the run
     for ip in sorted(check):
         if lo <= ip < lo + sub.n_pairs:
             one = sub.select(np.array([ip - lo]))
             ref, _ = O.OracleRun(one, proj).run()
-            a = int(sub.tr_off[ip - lo]); got = out[:, a:a + int(sub.k3_tr_size[ip - lo])]
-            scale = np.abs(ref).max(axis=1, keepdims=True)
-            sel = np.abs(ref) > 1e-6 * np.maximum(scale, 1e-300)
-            if sel.any():
-                worst = max(worst, float(np.max(np.abs(got - ref)[sel] / np.abs(ref)[sel])))
+            a = int(sub.tr_off[ip - lo]); got = out[:, a:a + int(sub.k3_tr_size[ip - lo])].copy()
+            checked.append((got, ref))
             exact_equal = exact_equal and bool(np.array_equal(got, ref))
+
+
+def parity(scale_of):
+    """max |got-ref|/|ref| over the checked pairs, restricted to |ref| > 1e-6 x scale."""
+    w = 0.0
+    for got, ref in checked:
+        scale = scale_of(ref)
+        sel = np.abs(ref) > 1e-6 * np.maximum(scale, 1e-300)
+        if sel.any():
+            w = max(w, float(np.max(np.abs(got - ref)[sel] / np.abs(ref)[sel])))
+    return w
 
 
 for ib, (lo, hi) in enumerate(bounds):
@@ -116,6 +127,9 @@ for ib, (lo, hi) in enumerate(bounds):
 while inflight:
     finish()
 wall = time.time() - t_wall0
+# BASELINE.json criterion: floor = 1e-6 of the per-(l,m) maximum over the whole run; the per-pair floor is stricter
+worst = parity(lambda ref: tt_max[:, None])
+worst_pair_floor = parity(lambda ref: np.abs(ref).max(axis=1, keepdims=True))
 
 n_int = grids.n_integrals
 line = {
@@ -124,7 +138,8 @@ line = {
     "gpu_ms": kern, "gpu_launches": launches,
     "integrals_per_s_kernels": n_int / (kern["ms_total"] * 1e-3),
     "wall_s_including_source_generation": wall, "source_generation_s": t_gen,
-    "parity": {"pairs_checked": len(check), "max_rel_err_above_1e-6_of_max": worst, "bitwise_equal": exact_equal,
+    "parity": {"pairs_checked": len(check), "max_rel_err_above_1e-6_of_max": worst,
+               "max_rel_err_with_per_pair_floor": worst_pair_floor, "bitwise_equal": exact_equal,
                "tolerance": 1e-9 if mode == MODE_FAST else 0.0},
 }
 print(json.dumps(line), flush=True)
