@@ -64,7 +64,9 @@ enum { SONG_LOS_J_TT = 0, SONG_LOS_J_EE = 1, SONG_LOS_J_EB = 2 };               
    EXACT: one thread per (k3,l) walks tau and L in the reference's order with no FMA
           contraction; bit-identical to the reference statement order (and to the oracle).
    FAST : k3-sorted, register-tiled kernel; reassociates the L and tau sums and contracts FMAs
-          (max relative deviation ~1e-13 of the per-(l,m) maximum, tolerance stated in tests). */
+          (max relative deviation ~1e-13 of the per-(l,m) maximum, tolerance stated in tests).
+          Requires the sources time sampling and linear Bessel interpolation; custom / bessel
+          time sampling (k-dependent grids) is computed by the EXACT kernels in either mode. */
 enum { SONG_LOS_MODE_EXACT = 0, SONG_LOS_MODE_FAST = 1 };
 
 /*

@@ -19,6 +19,8 @@ namespace songlos {
 // los_exact.cu
 cudaError_t launch_spline_k3(const Batch &b, int tau_size, int tp2_size, double *dd, int *err, cudaStream_t st);
 cudaError_t launch_los_exact(const ExactParams &P, int n_tiles, cudaStream_t st);
+cudaError_t launch_los_exact_resample(const ExactParams &P, int n_tiles, int n_ctas, cudaStream_t st);
+int64_t exact_resample_scratch_doubles(int tau_size, int tp2_size, int tau_grid_max);
 size_t exact_smem_bytes(int tau_chunk, int tp2_size);
 // los_peaks.cu
 cudaError_t launch_dfma_probe(double *out, int iters, int blocks, int threads, cudaStream_t st);
@@ -429,6 +431,9 @@ static int enqueue_upload(song_los_ctx *ctx, song_los_ctx::Slot &S, const song_l
   if (b->n_src_total) CK(cudaMemcpyAsync(S.d_src.p, b->src, (size_t)b->n_src_total * 8, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(S.ev_h2d, st));
 
+  S.k3_max = 0.;
+  if (c.tau_sampling_mode != SONG_LOS_TAU_SOURCES)
+    for (int64_t i = 0; i < b->n_units; ++i) S.k3_max = std::max(S.k3_max, b->k3_tr[i]);
   S.hb = *b;
   S.hb.k3_pt_size = S.hb.k3_tr_size = S.hb.phys_start = S.hb.phys_size = nullptr;
   S.hb.pt_off = S.hb.tr_off = S.hb.src_off = nullptr;
@@ -512,8 +517,7 @@ static int enqueue_compute(song_los_ctx *ctx, song_los_ctx::Slot &S, int mode)
   if (!S.have_batch) return ctx_fail(ctx, "song_los_compute: no pairs uploaded");
   const song_los_config &c = ctx->cfg;
   if (mode != SONG_LOS_MODE_EXACT && mode != SONG_LOS_MODE_FAST) return ctx_fail(ctx, "song_los_compute: unknown mode %d", mode);
-  if (c.tau_sampling_mode != SONG_LOS_TAU_SOURCES)
-    return ctx_fail(ctx, "song_los_compute: custom/bessel tau sampling is not available in this build");
+  if (c.tau_sampling_mode != SONG_LOS_TAU_SOURCES) mode = SONG_LOS_MODE_EXACT;     // k-dependent time grids: exact kernels only
   song_los_timing &t = S.t;
   t = song_los_timing{};
   t.n_integrals = S.hb.n_units * c.tt2_size;
@@ -548,7 +552,26 @@ static int enqueue_compute(song_los_ctx *ctx, song_los_ctx::Slot &S, int mode)
     int chunk = (int)std::min<size_t>((size_t)c.tau_size, (96 * 1024) / per_tau);
     if (chunk < 1) return ctx_fail(ctx, "song_los_compute: tp2_size=%d too large for the shared-memory stage", c.tp2_size);
     P.tau_chunk = chunk;
-    CK(launch_los_exact(P, S.n_tiles, st));
+    if (c.tau_sampling_mode == SONG_LOS_TAU_SOURCES) {
+      CK(launch_los_exact(P, S.n_tiles, st));
+    } else {
+      // upper bound on the points of a time grid, transfer2.c:185-203
+      int gmax;
+      if (c.tau_sampling_mode == SONG_LOS_TAU_CUSTOM) {
+        if (!(c.tau_linstep_song > 0) || !(S.k3_max > 0)) return ctx_fail(ctx, "stopping to prevent segmentation fault (tau_step_max == 0)");
+        double tau_step_min = 2 * 3.1415926535897932384626433832795 / S.k3_max * c.tau_linstep_song;
+        gmax = c.tau_size + (int)std::ceil(ctx->tau[c.tau_size - 1] / tau_step_min) + 1;
+      } else {
+        gmax = c.tau_size + c.xx_size;
+      }
+      P.tau_grid_max = gmax;
+      P.tau_chunk = (int)std::min<size_t>((size_t)gmax, (96 * 1024) / (per_tau + 8));
+      const int n_ctas = std::min(S.n_tiles, ctx->sm_count * 2);
+      P.scratch_stride = exact_resample_scratch_doubles(c.tau_size, c.tp2_size, gmax);
+      CK(ctx->d_scratch.reserve((size_t)n_ctas * P.scratch_stride));
+      P.scratch = ctx->d_scratch.p;
+      CK(launch_los_exact_resample(P, S.n_tiles, n_ctas, st));
+    }
     t.n_launches++;
     CK(cudaEventRecord(S.ev_t[2], st));
   } else {

@@ -58,6 +58,7 @@ struct song_los_ctx {
     DevBuf<double> d_k3_pt, d_k3_tr, d_src, d_out;
     DevBuf<int2> d_tiles; int n_tiles = 0; bool tiles_ready = false;
     int max_np = 0;               // largest coarse k3 grid of the batch
+    double k3_max = 0.;           // largest k3 of the batch (custom/bessel time sampling: grid size bound)
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr, ev_h2d_start = nullptr, ev_d2h_start = nullptr;
     cudaEvent_t ev_t[songlos::FAST_MAX_EVENTS]{};   // phase boundaries of this slot's compute
     int n_chunks = 0;             // (column block, K chunk) launches of the last FAST compute

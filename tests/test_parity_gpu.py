@@ -84,6 +84,25 @@ def test_exact_bitwise_quick_song_run(oracle):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("time_interp", ["linear", "cubic"])
+@pytest.mark.parametrize("sampling", ["custom", "bessel"])
+def test_exact_bitwise_k_dependent_time_grids(oracle, sampling, time_interp):
+    """transfer2_tau_sampling = custom / bessel: transfer2_get_time_grid inserts points so that no step exceeds
+    2 pi/k tau_linstep_song (transfer2.c:2422) or xx_step/k (:2432); the sources are resampled in time, linearly or
+    with a cubic spline (transfer2.c:2816-2880).  Both arithmetic modes route to the exact kernels."""
+    p = configs.tiny(transfer2_tau_sampling=sampling, sources_time_interpolation=time_interp,
+                     sources_k3_interpolation="cubic", tau_linstep_song=0.6)
+    for mode in (MODE_EXACT, MODE_FAST):
+        wl, ref, got = run_both(oracle, p, mode=mode)
+        assert np.array_equal(got, ref), f"max abs diff {np.abs(got - ref).max()}"
+    # the grids really are k dependent: more integration points than source times for the largest k3
+    import ctypes as C
+    s = oracle.OracleRun(wl, oracle.build_projection(wl)).setup
+    kmax = float(wl.k3_tr.max())
+    nmax = oracle.lib().oracle_time_grid_size_max(C.byref(s), kmax)
+    assert nmax > wl.tau.size
+
+
 # ----------------------------------------------------------------------------------------------
 # FAST mode (k3-sorted DMMA kernel): BASELINE.json tolerance
 # ----------------------------------------------------------------------------------------------
