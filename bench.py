@@ -57,7 +57,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -285,7 +285,6 @@ def main():
         launches += tm["n_launches"]
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
     for k in kern:
         kern[k] /= args.steps
@@ -327,6 +326,7 @@ def main():
         tm = eng.wait(); copy_ms["h2d"] += tm["ms_h2d"]; copy_ms["d2h"] += tm["ms_d2h"]
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t_host0) * 1e3 / args.steps)
+    clocks = sampler.stop()          # sampled over both timed regions (value and e2e), 50 ms period
     if world > 1:
         dist.barrier()
     h2d = int(wl.src.nbytes + wl.k3_pt.nbytes + wl.k3_tr.nbytes + (3 * 8 + 5 * 4) * wl.n_pairs)

@@ -126,6 +126,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
       "TC_DONE:\n"
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      " selp.u32 %0, 1, 0, p;\n"
+      "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 // 1-D bulk copy global -> shared, completion on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
@@ -746,18 +758,45 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
         const int kcs_q = G.kcs;
         const int b_sb_stride = WN * kcs_q * 32;
         const int a_off0 = (g0 * 8 + um) * G.tpp + tsel, a_off1 = (g1 * 8 + um) * G.tpp + tsel;
+        // The header of the NEXT stage (row window, row indices and weights of this lane's units) is fetched
+        // before the MMAs of the current one whenever that stage has already landed, so that its barrier
+        // test and shared-memory latencies are covered by the DMMA stream.
+        // (register budget: only the (12,1,7) grid has room for the second header without spilling in the MMA loop;
+        //  measured 7.05 -> 6.84 ms there, slower elsewhere)
+        constexpr bool PREFETCH_HDR = (WM == 12 && WN == 1 && NW == 7);
+        bool have_next = false;
+        int4 n_meta = make_int4(0, 0, 0, 0);
+        int n_ix0 = 0, n_ix1 = 0, n_lo0 = 0, n_hi0 = 0, n_lo1 = 0, n_hi1 = 0;
+        double n_cw0 = 0., n_cw1 = 0.;
+#define TC_LOAD_HDR(ST, META, IX0, IX1, LO0, HI0, LO1, HI1, CW0, CW1) do { \
+          META = *reinterpret_cast<const int4 *>((ST).meta);      /* {row_lo, nrows, nact, row_hi} */ \
+          IX0 = (ST).ixs[g0 * 8 + um]; IX1 = (ST).ixs[g1 * 8 + um]; \
+          LO0 = (ST).ixs[g0 * 8]; HI0 = (ST).ixs[g0 * 8 + 7]; LO1 = (ST).ixs[g1 * 8]; HI1 = (ST).ixs[g1 * 8 + 7]; \
+          const double2 cc0_ = (ST).cc[g0 * 8 + um], cc1_ = (ST).cc[g1 * 8 + um]; \
+          CW0 = ksel ? cc0_.y : cc0_.x; CW1 = ksel ? cc1_.y : cc1_.x; } while (0)
         for (int t = 0; t < P.tau_size; ++t) {
           const TcStagePtrs st = tc_stage<MT>(stage0, s, P);
-          mbar_wait(smem_u32(&bars[s]), ph);
-          const int4 meta = *reinterpret_cast<const int4 *>(st.meta);      // {row_lo, nrows, nact, row_hi}
+          int4 meta; int ix0, ix1, lo0, hi0, lo1, hi1; double cw0, cw1;
+          if (have_next) {
+            meta = n_meta; ix0 = n_ix0; ix1 = n_ix1; lo0 = n_lo0; hi0 = n_hi0; lo1 = n_lo1; hi1 = n_hi1; cw0 = n_cw0; cw1 = n_cw1;
+          } else {
+            mbar_wait(smem_u32(&bars[s]), ph);
+            TC_LOAD_HDR(st, meta, ix0, ix1, lo0, hi0, lo1, hi1, cw0, cw1);
+          }
+          have_next = false;
+          if (PREFETCH_HDR && t + 1 < P.tau_size && !(P.dbg & 32)) {
+            const int s1 = (s + 1 == NS) ? 0 : s + 1;
+            const uint32_t ph1 = (s + 1 == NS) ? (ph ^ 1u) : ph;
+            if (__all_sync(0xffffffffu, mbar_test(smem_u32(&bars[s1]), ph1))) {
+              const TcStagePtrs st1 = tc_stage<MT>(stage0, s1, P);
+              TC_LOAD_HDR(st1, n_meta, n_ix0, n_ix1, n_lo0, n_hi0, n_lo1, n_hi1, n_cw0, n_cw1);
+              have_next = true;
+            }
+          }
           const int nact = meta.z;
           // owned sub-blocks: warp_n, warp_n + WN, ... ; active ones form a prefix of that list
           const int nactw = (nact > warp_n) ? min(NW, (nact - warp_n + WN - 1) / WN) : 0;
           if (nactw > 0 && !(P.dbg & 4)) {
-            const int ix0 = st.ixs[g0 * 8 + um], ix1 = st.ixs[g1 * 8 + um];
-            const int lo0 = st.ixs[g0 * 8], hi0 = st.ixs[g0 * 8 + 7], lo1 = st.ixs[g1 * 8], hi1 = st.ixs[g1 * 8 + 7];
-            const double2 cc0 = st.cc[g0 * 8 + um], cc1 = st.cc[g1 * 8 + um];
-            const double cw0 = ksel ? cc0.y : cc0.x, cw1 = ksel ? cc1.y : cc1.x;
             // A fragment of kc: S[unit][2 kc + tsel] x weight
             const double *a0p = st.S + a_off0;
             const double *a1p = st.S + a_off1;
@@ -774,6 +813,7 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
           if (lane == 0) mbar_arrive(smem_u32(&bars[8 + s]));
           TC_ADVANCE();
         }
+#undef TC_LOAD_HDR
       }
 
       // ---- epilogue: the 1/2 of the trapezoid and the divisions by 4, (2l+1), 2 of
@@ -917,7 +957,8 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
   // covers the columns of a block in one pass
   // (measured on B200: sn_t_10percent 7.0 ms with (12,1,8) vs 7.3 ms with (8,1,8); sn_pol_10percent 16.1 ms with
   //  (6,2,5) vs 16.7 ms with (8,1,10); sn_pol_5percent_lmax3000 357 ms with (4,3,7) vs 367 ms with (2,4,8))
-  if (max_sb <= 8) { fs->wm = 12; fs->wn = 1; fs->nw = 8; }     // three consumer warps per SM sub-partition
+  if (max_sb <= 7) { fs->wm = 12; fs->wn = 1; fs->nw = 7; }     // three consumer warps per SM sub-partition
+  else if (max_sb <= 8) { fs->wm = 12; fs->wn = 1; fs->nw = 8; }
   else if (max_sb <= 10) { fs->wm = 6; fs->wn = 2; fs->nw = 5; }
   else if (max_sb <= 16) { fs->wm = 4; fs->wn = 2; fs->nw = 8; }
   else if (max_sb <= 20) { fs->wm = 4; fs->wn = 2; fs->nw = 10; }
@@ -1213,7 +1254,7 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
         case 20408:  e = launch_tc<2, 4, 8, 1>(TP, n_ctas, smem, st); break;
         case 20410:  e = launch_tc<2, 4, 10, 1>(TP, n_ctas, smem, st); break;
         // three consumer warps per SM sub-partition
-        case 120107: e = launch_tc<12, 1, 7, 3>(TP, n_ctas, smem, st); break;
+        case 120107: e = np1 ? launch_tc<12, 1, 7, 1>(TP, n_ctas, smem, st) : launch_tc<12, 1, 7, 3>(TP, n_ctas, smem, st); break;
         case 120108: e = np1 ? launch_tc<12, 1, 8, 3>(TP, n_ctas, smem, st) : launch_tc<12, 1, 8, 1>(TP, n_ctas, smem, st); break;
         case 60205:  e = launch_tc<6, 2, 5, 1>(TP, n_ctas, smem, st); break;
         case 60208:  e = launch_tc<6, 2, 8, 1>(TP, n_ctas, smem, st); break;
