@@ -14,7 +14,8 @@
  *   song_los_set_projection    consumes pbs2->J_Llm_x / index_xmin_J / x_size_J as filled by
  *                              bessel2_init, bessel2.c:315-374 (ragged -> dense device table)
  *   song_los_build_projection  the J_Llm(x) assembly itself, bessel2_J_for_Llm + bessel2_J_Llm,
- *                              bessel2.c:1041-1588, from a host j_l1 table and host 3j symbols
+ *                              bessel2.c:1041-1588, from a host j_l1 table and host 3j symbols, and for
+ *                              cubic Bessel interpolation their second derivatives, bessel2.c:395-435
  *   song_los_get_projection    writes the device-built tables back in bessels2 layout
  *   song_los_upload_pairs      the inputs of the (k1,k2) loop body: ppt2->k3[k1][k2],
  *                              ppt2->sources[tp][k1][k2] (transfer2.h:47-51 layout) and the fine
@@ -182,6 +183,9 @@ int  song_los_build_projection(song_los_ctx *ctx, int l1_size, const int *l1,
    obtain index_xmin_J / x_size_J first, allocate, then call again with rows. */
 int  song_los_get_projection(song_los_ctx *ctx, int *index_xmin_J, int *x_size_J,
                              double *const *J_rows);
+/* pbs2->ddJ_Llm_x of the device-built tables (cubic Bessel interpolation only; bessel2.c:395-435),
+   rows sized and offset like J_rows. */
+int  song_los_get_projection_dd(song_los_ctx *ctx, double *const *ddJ_rows);
 
 int  song_los_upload_pairs(song_los_ctx *ctx, const song_los_batch *batch);
 int  song_los_compute(song_los_ctx *ctx, int mode, song_los_timing *timing);

@@ -139,7 +139,7 @@ LOS_SYMBOLS = [
     "song_los_compute", "song_los_download", "song_los_transfer_pairs",
     "song_los_device_result", "song_los_copy_result", "song_los_set_stream", "song_los_measure_peaks",
     "song_los_device_info", "song_los_version",
-    "song_los_submit", "song_los_wait", "song_los_host_alloc", "song_los_host_free", "song_los_max_batch_units", "song_los_reserve",
+    "song_los_submit", "song_los_wait", "song_los_host_alloc", "song_los_host_free", "song_los_max_batch_units", "song_los_reserve", "song_los_get_projection_dd",
 ]
 HOST_SYMBOLS = ["song_host_k3_size", "song_host_k3_list", "song_host_k3_sizes", "song_host_k3_lists",
                 "song_host_bessel2_prepare", "song_host_bessel2_free", "song_host_bessel2_upload",
@@ -168,6 +168,7 @@ def los():
             vp, C.c_int, c_int_p, C.POINTER(c_double_p), c_int_p, c_int_p,
             C.c_int, c_double_p, c_double_p, c_int_p, c_int_p, c_int_p, c_int_p, C.c_double, C.c_double]
         lib.song_los_get_projection.argtypes = [vp, c_int_p, c_int_p, C.POINTER(c_double_p)]
+        lib.song_los_get_projection_dd.argtypes = [vp, C.POINTER(c_double_p)]
         lib.song_los_upload_pairs.argtypes = [vp, C.POINTER(LosBatch)]
         lib.song_los_compute.argtypes = [vp, C.c_int, C.POINTER(LosTiming)]
         lib.song_los_download.argtypes = [vp, c_double_p]

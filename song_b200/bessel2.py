@@ -108,6 +108,18 @@ class Bessel2:
             raise _lib.SongLosError(lib.song_los_last_error(engine.ctx).decode())
         return rows, xmin, xsize
 
+    def dd_tables(self, engine, xsize):
+        """pbs2->ddJ_Llm_x (cubic Bessel interpolation, bessel2.c:395-435) read back from the device."""
+        lib = _lib.los()
+        rows = [np.zeros(int(s)) if s > 0 else None for s in xsize]
+        ptrs = (_lib.c_double_p * len(rows))()
+        for i, r in enumerate(rows):
+            if r is not None:
+                ptrs[i] = _lib.dptr(r)
+        if lib.song_los_get_projection_dd(engine.ctx, ptrs):
+            raise _lib.SongLosError(lib.song_los_last_error(engine.ctx).decode())
+        return rows
+
 
 def build_projection_direct(engine, wl, l1, j_l1_rows, index_xmin_l1, first_3j, second_3j, l1_min, l1_count,
                             index_l1_of_l1min, J_types):

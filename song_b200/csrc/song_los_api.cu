@@ -202,6 +202,7 @@ extern "C" int song_los_destroy(song_los_ctx *ctx)
   ctx->d_dd.release(); ctx->d_err.release(); ctx->d_scratch.release();
   if (ctx->fast) fast_state_destroy(ctx->fast);
   if (ctx->d_proj_rows) cudaFree(ctx->d_proj_rows);
+  if (ctx->d_proj_ddrows) cudaFree(ctx->d_proj_ddrows);
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;

@@ -78,7 +78,7 @@ struct song_los_ctx {
 
   songlos::FastState *fast = nullptr;
   // device-built projection functions (song_los_build_projection)
-  double *d_proj_rows = nullptr; int proj_rows_n = 0;
+  double *d_proj_rows = nullptr, *d_proj_ddrows = nullptr; int proj_rows_n = 0;
   std::vector<int> h_jidx_xmin, h_jidx_xsize;
   cudaEvent_t ev[8]{};
 };

@@ -8,6 +8,9 @@
 //   proj_rows_kernel    J_Llm(xx[ix]) for every ix and every (J,L,l,m)        (bessel2.c:1400-1423)
 //   proj_xmin_kernel    first grid index where |J| >= J_Llm_cut, by the reference's bisection on
 //                       grid indices                                          (bessel2.c:1202-1342)
+//   proj_dd_kernel      second derivatives of every J_Llm row for the cubic interpolation of
+//                       transfer2.c:2262-2271 (bessel2.c:395-435: array_spline_table_one_column,
+//                       _SPLINE_EST_DERIV_ for l = 2, _SPLINE_NATURAL_ otherwise)
 //   proj_dense_kernel   masked {J[ix], J[ix+1]} table used by the LOS kernels (transfer2.c:2232)
 #include <cuda_runtime.h>
 #include <cstring>
@@ -85,6 +88,47 @@ __global__ void proj_xmin_kernel(ProjBuild B, const double *rows, const double *
   x_size[q] = B.xx_size - xmin;                             // bessel2.c:1357
 }
 
+// one thread per (J,L,l,m) row: the tridiagonal sweep is sequential in x (up to xx_size points)
+__global__ void proj_dd_kernel(ProjBuild B, const double *rows, const double *xx, const int *index_xmin, const int *x_size,
+                               const int *l_of, double *ddrows, double *work)
+{
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= B.n_jidx || B.col_of[q] < 0) return;
+  const int xmin = index_xmin[q];
+  const int n = (xmin == B.xx_size - 1) ? 1 : x_size[q];    // all-negligible marker: a single zero (bessel2.c:1378-1388)
+  if (n < 3) return;                                       // ddrows is zero-initialised
+  const double *x = xx + xmin;
+  const double *y = rows + (size_t)q * B.xx_size + xmin;
+  double *dd = ddrows + (size_t)q * B.xx_size + xmin;
+  double *u = work + (size_t)q * B.xx_size;
+  const bool est = (l_of[q] == 2);                         // bessel2.c:414
+  if (!est) { dd[0] = 0.0; u[0] = 0.0; }
+  else {
+    double dy_first = ((x[2] - x[0]) * (x[2] - x[0]) * (y[1] - y[0]) - (x[1] - x[0]) * (x[1] - x[0]) * (y[2] - y[0]))
+                      / ((x[2] - x[0]) * (x[1] - x[0]) * (x[2] - x[1]));
+    dd[0] = -0.5;
+    u[0] = (3. / (x[1] - x[0])) * ((y[1] - y[0]) / (x[1] - x[0]) - dy_first);
+  }
+  for (int i = 1; i < n - 1; ++i) {
+    double sig = (x[i] - x[i - 1]) / (x[i + 1] - x[i - 1]);
+    double p = sig * dd[i - 1] + 2.0;
+    dd[i] = (sig - 1.0) / p;
+    double ui = (y[i + 1] - y[i]) / (x[i + 1] - x[i]) - (y[i] - y[i - 1]) / (x[i] - x[i - 1]);
+    u[i] = (6.0 * ui / (x[i + 1] - x[i - 1]) - sig * u[i - 1]) / p;
+  }
+  double qn, un;
+  if (!est) { qn = 0.0; un = 0.0; }
+  else {
+    double dy_last = ((x[n - 3] - x[n - 1]) * (x[n - 3] - x[n - 1]) * (y[n - 2] - y[n - 1])
+                      - (x[n - 2] - x[n - 1]) * (x[n - 2] - x[n - 1]) * (y[n - 3] - y[n - 1]))
+                     / ((x[n - 3] - x[n - 1]) * (x[n - 2] - x[n - 1]) * (x[n - 3] - x[n - 2]));
+    qn = 0.5;
+    un = (3. / (x[n - 1] - x[n - 2])) * (dy_last - (y[n - 1] - y[n - 2]) / (x[n - 1] - x[n - 2]));
+  }
+  dd[n - 1] = (un - qn * u[n - 2]) / (qn * dd[n - 2] + 1.0);
+  for (int i = n - 2; i >= 0; --i) dd[i] = dd[i] * dd[i + 1] + u[i];
+}
+
 __global__ void proj_dense_kernel(ProjBuild B, const double *rows, const int *index_xmin,
                                   int64_t n_cols, double2 *dense)
 {
@@ -124,9 +168,7 @@ extern "C" int song_los_build_projection(song_los_ctx *ctx, int l1_size, const i
   const song_los_config &c = ctx->cfg;
   const int n_jidx = c.J_size * c.L_size * c.l_size * c.m_size;
   if (n3j != n_jidx) return ctx_fail(ctx, "song_los_build_projection: expected %d 3j blocks, got %d", n_jidx, n3j);
-  if (c.bessels_interpolation == SONG_LOS_INTERP_CUBIC)
-    return ctx_fail(ctx, "song_los_build_projection: cubic Bessel interpolation needs the splined tables; "
-                         "build them on the host and use song_los_set_projection");
+  const bool cubic_J = (c.bessels_interpolation == SONG_LOS_INTERP_CUBIC);
   const int ndim = 2 * (c.L_size - 1) + 1;
   const int xs = c.xx_size;
   cudaStream_t st = ctx->stream;
@@ -213,6 +255,24 @@ extern "C" int song_los_build_projection(song_los_ctx *ctx, int l1_size, const i
                                                         d_xmin, d_xsize, ctx->d_err.p);
   proj_dense_kernel<<<grid, 128, 0, st>>>(B, d_rows, d_xmin, ctx->n_cols, ctx->d_J.p);
   e = cudaGetLastError();
+  double *d_ddrows = nullptr, *d_work = nullptr;
+  if (e == cudaSuccess && cubic_J) {
+    // second derivatives of every row (bessel2.c:395-435), then the same masked dense layout as J
+    e = cudaMalloc(&d_ddrows, (size_t)n_jidx * xs * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_work, (size_t)n_jidx * xs * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_ddrows, 0, (size_t)n_jidx * xs * sizeof(double), st);
+    if (e == cudaSuccess) e = ctx->d_ddJ.reserve((size_t)xs * ctx->n_cols);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_ddJ.p, 0, (size_t)xs * ctx->n_cols * sizeof(double2), st);
+    if (e == cudaSuccess) {
+      proj_dd_kernel<<<(n_jidx + 63) / 64, 64, 0, st>>>(B, d_rows, ctx->d_xx.p, d_xmin, d_xsize, d_l, d_ddrows, d_work);
+      proj_dense_kernel<<<grid, 128, 0, st>>>(B, d_ddrows, d_xmin, ctx->n_cols, ctx->d_ddJ.p);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_work);
+    if (e != cudaSuccess) cudaFree(d_ddrows);
+    else { if (ctx->d_proj_ddrows) cudaFree(ctx->d_proj_ddrows); ctx->d_proj_ddrows = d_ddrows; }
+  }
   // host mirrors: index tables + ragged rows for song_los_get_projection
   ctx->h_jidx_xmin.resize((size_t)n_jidx); ctx->h_jidx_xsize.resize((size_t)n_jidx);
   if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_jidx_xmin.data(), d_xmin, (size_t)n_jidx * sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -243,6 +303,30 @@ extern "C" int song_los_build_projection(song_los_ctx *ctx, int l1_size, const i
     if (col_of[(size_t)q] < 0) { ctx->h_jidx_xmin[(size_t)q] = xs - 1; ctx->h_jidx_xsize[(size_t)q] = 0; }
   fast_invalidate_table(ctx->fast);
   ctx->have_proj = true;
+  return SONG_LOS_SUCCESS;
+}
+
+static int get_rows(song_los_ctx *ctx, const double *d_rows, double *const *out_rows);
+
+extern "C" int song_los_get_projection_dd(song_los_ctx *ctx, double *const *ddJ_rows)
+{
+  if (!ctx || !ddJ_rows) return ctx_fail(ctx, "song_los_get_projection_dd: NULL argument");
+  PCK(cudaSetDevice(ctx->device));
+  if (!ctx->d_proj_ddrows) return ctx_fail(ctx, "song_los_get_projection_dd: no device-built second derivatives (bessels_interpolation is not cubic)");
+  return get_rows(ctx, ctx->d_proj_ddrows, ddJ_rows);
+}
+
+static int get_rows(song_los_ctx *ctx, const double *d_rows, double *const *out_rows)
+{
+  const int n = ctx->proj_rows_n, xs = ctx->cfg.xx_size;
+  for (int q = 0; q < n; ++q) {
+    int sz = ctx->h_jidx_xsize[(size_t)q], xm = ctx->h_jidx_xmin[(size_t)q];
+    if (sz <= 0 || !out_rows[q]) continue;
+    if (xm == xs - 1) { out_rows[q][0] = 0.; continue; }       // bessel2.c:1378-1388
+    PCK(cudaMemcpyAsync(out_rows[q], d_rows + (size_t)q * xs + xm, (size_t)sz * sizeof(double),
+                        cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  PCK(cudaStreamSynchronize(ctx->stream));
   return SONG_LOS_SUCCESS;
 }
 

@@ -67,6 +67,34 @@ def test_device_tables_bitwise_from_the_same_inputs(oracle, params):
     eng.close()
 
 
+def test_device_second_derivatives_bitwise_and_cubic_los(oracle):
+    """bessels_interpolation = cubic: ddJ_Llm_x built on the device (bessel2.c:395-435: EST_DERIV for l = 2, NATURAL
+    otherwise) is bit-identical to the oracle's, and the LOS integral with the device-built {J, ddJ} tables
+    (transfer2.c:2262-2271) is bit-identical to the oracle run on the oracle's tables."""
+    from song_b200.engine import MODE_EXACT
+    wl = workload.build_grids(configs.tiny(bessels_interpolation="cubic", sources_k3_interpolation="cubic"))
+    workload.fill_sources(wl)
+    oproj = oracle.build_projection(wl, with_jl1=True, spline=True)
+    b2 = Bessel2(wl)
+    f1, f2, l1_min, cnt, idx = oracle_3j_blocks(oracle, wl, b2.J_types, oproj.jl1)
+    eng = LosEngine(wl, 0)
+    build_projection_direct(eng, wl, oproj.jl1["l1"], oproj.jl1["j_l1"], oproj.jl1["index_xmin_l1"], f1, f2,
+                            l1_min, cnt, idx, b2.J_types)
+    rows, xmin, xsize = b2.tables(eng)
+    dd = b2.dd_tables(eng, xsize)
+    checked = 0
+    for q, ref in enumerate(oproj.ddrows):
+        if ref is None:
+            continue
+        assert np.array_equal(dd[q], ref), (q, np.abs(dd[q] - ref).max())
+        checked += int(np.any(ref != 0))
+    assert checked > 0
+    ref_T, _ = oracle.OracleRun(wl, oproj).run()
+    got = eng.transfer_pairs(wl, mode=MODE_EXACT)
+    assert np.array_equal(got, ref_T)
+    eng.close()
+
+
 def test_product_bessel2_matches_oracle_tables(oracle):
     """Bessel2.init (host compat j_l / 3j + device assembly) against the oracle's own generators:
     different algorithms for the inputs, so agreement is to rounding, not bitwise."""
