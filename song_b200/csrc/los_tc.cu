@@ -1203,7 +1203,8 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
 
   TcInterp &I = fs->interp;
   // tau samples per CTA: two staged rows of tauc*tp2 {y, dd} entries within ~64 KB
-  const int tauc = std::max(1, std::min(tau_size, (int)((64 * 1024) / (2 * 16 * (size_t)tp2))));
+  int tauc = std::max(1, std::min(tau_size, (int)((64 * 1024) / (2 * 16 * (size_t)tp2))));
+  if (const char *v = getenv("SONG_LOS_TC_TAUC")) tauc = std::max(1, std::min(tauc, atoi(v)));
   int n_chunks = 0;
   for (int ib = 0; ib < fs->n_blocks && U > 0; ++ib) {
     int pb = fs->n_pass, pe = 0;

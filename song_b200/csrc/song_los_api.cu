@@ -499,6 +499,7 @@ static void fill_fast_layout(song_los_ctx *ctx, const song_los_ctx::Slot &S, Fas
   h.block_nonzero = ctx->h_block_nonzero.data(); h.n_src_total = S.hb.n_src_total;
   h.tau_size = c.tau_size; h.n_pt_total = S.hb.n_pt_total;
   h.xx_uniform = ctx->xx_uniform; h.xx_delta = ctx->xx_delta;
+  h.max_np = S.max_np;
 }
 
 static int report_device_errors(song_los_ctx *ctx, int h)
