@@ -40,6 +40,7 @@ class HarnessInput(C.Structure):
         ("src_off", lp), ("src", dp),
         ("store_to_disk", C.c_int), ("load_from_disk", C.c_int), ("transfers_dir", C.c_char_p),
         ("verbose", C.c_int),
+        ("tau_sampling_mode", C.c_int), ("cubic_time", C.c_int), ("tau_linstep_song", C.c_double),
     ]
 
 
@@ -92,7 +93,9 @@ def run_transfer2(wl, proj, store_dir: str | None = None, verbose: int = 0):
         k3_pt_size=_lib.iptr(wl.k3_pt_size), pt_off=keep["pt_off"].ctypes.data_as(lp), k3_pt=_lib.dptr(wl.k3_pt),
         src_off=keep["src_off"].ctypes.data_as(lp), src=_lib.dptr(wl.src),
         store_to_disk=int(store_dir is not None), load_from_disk=0,
-        transfers_dir=(store_dir.encode() if store_dir else None), verbose=verbose)
+        transfers_dir=(store_dir.encode() if store_dir else None), verbose=verbose,
+        tau_sampling_mode={"sources": 0, "custom": 1, "smart": 1, "bessel": 2}[p["transfer2_tau_sampling"]],
+        cubic_time=int(p["sources_time_interpolation"] == "cubic"), tau_linstep_song=float(p.get("tau_linstep_song", 0.0)))
     out = np.zeros((lay.tt2_size, wl.n_units), dtype=np.float64)
     sizes = (C.c_longlong * 3)()
     labels_ok = C.c_int(0)

@@ -27,6 +27,8 @@ typedef struct harness_input {
   const long long *src_off; const double *src;           /* packed [pair][tp][tau][k3] */
   int store_to_disk, load_from_disk; const char *transfers_dir;
   int verbose;
+  int tau_sampling_mode;           /* 0 sources, 1 custom, 2 bessel (ptr2->tau_sampling, input2.c:1480-1500) */
+  int cubic_time; double tau_linstep_song;
 } harness_input;
 
 int perturb2_allocate_k1_level(struct perturbs2 *ppt2, int index_k1)
@@ -87,7 +89,8 @@ int harness_transfer2(const harness_input *in, double *out, long long out_capaci
   pr2.l_max_los_t = in->l_max_los_t; pr2.l_max_los_p = in->l_max_los_p;
   pr2.q_linstep_song = in->q_linstep_song;
   pr2.sources_k3_interpolation = in->cubic_k3 ? cubic_interpolation : linear_interpolation;
-  pr2.sources_time_interpolation = linear_interpolation;
+  pr2.sources_time_interpolation = in->cubic_time ? cubic_interpolation : linear_interpolation;
+  pr2.tau_linstep_song = in->tau_linstep_song;
   pr2.store_transfers_to_disk = in->store_to_disk; pr2.load_transfers_from_disk = in->load_from_disk;
 
   /* ---- background / thermodynamics ---- */
@@ -168,7 +171,7 @@ int harness_transfer2(const harness_input *in, double *out, long long out_capaci
 
   /* ---- transfer2 (fields written by input2.c:1450-1522,1647) ---- */
   tr2.k_sampling = class_transfer2_k3_sampling;
-  tr2.tau_sampling = sources_tau_sampling;
+  tr2.tau_sampling = in->tau_sampling_mode == 1 ? custom_tau_sampling : in->tau_sampling_mode == 2 ? bessel_tau_sampling : sources_tau_sampling;
   tr2.transfer2_verbose = in->verbose;
   if (in->transfers_dir) snprintf(tr2.transfers_dir, _FILENAMESIZE_, "%s", in->transfers_dir);
 

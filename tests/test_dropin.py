@@ -74,6 +74,36 @@ def test_transfer2_init_small_batches_and_polarisation(oracle, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_transfer2_init_multi_gpu_schedule_and_pipeline(oracle, monkeypatch, mode):
+    """Many small k1 batches spread over up to 8 GPUs (one host thread and one three-deep submit/wait pipeline per GPU,
+    static LPT schedule).  On a single-GPU box the module finds one device and runs the same pipeline there; the result
+    must not depend on the number of devices."""
+    wl = _tiny(sources_k3_interpolation="cubic")
+    proj = oracle.build_projection(wl)
+    ref, _ = oracle.OracleRun(wl, proj).run()
+    monkeypatch.setenv("SONG_LOS_BATCH_UNITS", "150")
+    monkeypatch.setenv("SONG_LOS_DEVICES", "8")
+    monkeypatch.setenv("SONG_LOS_MODE", mode)
+    got, count, labels_ok = dropin_lib.run_transfer2(wl, Projection(proj.rows, proj.index_xmin, proj.x_size))
+    assert count == wl.n_integrals and labels_ok
+    if mode == "exact":
+        assert np.array_equal(got, ref)
+    else:
+        assert _rel_err(got, ref) < 1e-9
+
+
+@pytest.mark.gpu
+def test_transfer2_custom_time_sampling(oracle, monkeypatch):
+    """ptr2->tau_sampling = custom_tau_sampling through the drop-in (k-dependent time grids, cubic time interpolation)."""
+    wl = _tiny(transfer2_tau_sampling="custom", sources_time_interpolation="cubic", sources_k3_interpolation="cubic")
+    proj = oracle.build_projection(wl)
+    ref, _ = oracle.OracleRun(wl, proj).run()
+    got, count, _ = dropin_lib.run_transfer2(wl, Projection(proj.rows, proj.index_xmin, proj.x_size))
+    assert np.array_equal(got, ref) and count == wl.n_integrals
+
+
+@pytest.mark.gpu
 def test_transfer2_store_and_load_from_disk(oracle, tmp_path, monkeypatch):
     """store_transfers_to_disk: one transfers_%03d.dat per type in [k1][k2][k3] order, read back with
     transfer2_load_transfers_from_disk (the path bispectra2.c:1213 takes)."""
