@@ -993,7 +993,9 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
       if (fs->n_groups >= TC_MAX_GROUPS) { err = "too many K chunks for the FAST kernel"; return 1; }
       TcGroup G{};
       G.blk = ib; G.kc0 = q * kcs; G.kcs = std::min(kcs, B.nkc - G.kc0);
-      G.tpp = 2 * G.kcs;                         // 16-byte multiples (TMA stride rule); odd kcs: conflict-free A-fragment reads
+      // row of 2*kcs doubles (16-byte multiples: TMA stride rule).  Odd kcs: conflict-free A-fragment reads; even kcs has
+      // 2- to 4-way conflicts there, but padding the rows by a pair cost more in slab traffic than it gained (measured)
+      G.tpp = 2 * G.kcs;
       for (int sl = 0; sl < 2 * G.kcs; ++sl) {
         int e = 2 * G.kc0 + sl;
         if (e < B.nterms) { slot_tp[(size_t)fs->n_groups * TC_SLOTS + sl] = term_tp[B.term_off + e];
