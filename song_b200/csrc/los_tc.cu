@@ -441,15 +441,28 @@ __device__ __forceinline__ void tc_mma_both(double (&acc0)[NW][2], double (&acc1
 {
   if constexpr (!PP) {
     // single-buffered: with three or four warps per SM sub-partition the other warps cover the LDS latency
+    // B fragments in two halves when a warp owns many sub-blocks: fewer live registers (NW = 10 at 128 registers)
+    constexpr int H0 = (NACT > 8) ? (NACT + 1) / 2 : NACT;
     for (int kc = 0; kc < kcs; ++kc) {
       const double x0 = w0 * a0p[2 * kc], x1 = w1 * a1p[2 * kc];
-      double bf[NACT];
+      {
+        double bf[H0];
 #pragma unroll
-      for (int j = 0; j < NACT; ++j) bf[j] = bp[(size_t)j * b_sb_stride + kc * 32];
+        for (int j = 0; j < H0; ++j) bf[j] = bp[(size_t)j * b_sb_stride + kc * 32];
 #pragma unroll
-      for (int j = 0; j < NACT; ++j) dmma884(acc0[j][0], acc0[j][1], x0, bf[j]);
+        for (int j = 0; j < H0; ++j) dmma884(acc0[j][0], acc0[j][1], x0, bf[j]);
 #pragma unroll
-      for (int j = 0; j < NACT; ++j) dmma884(acc1[j][0], acc1[j][1], x1, bf[j]);
+        for (int j = 0; j < H0; ++j) dmma884(acc1[j][0], acc1[j][1], x1, bf[j]);
+      }
+      if constexpr (H0 < NACT) {
+        double bf[NACT - H0];
+#pragma unroll
+        for (int j = H0; j < NACT; ++j) bf[j - H0] = bp[(size_t)j * b_sb_stride + kc * 32];
+#pragma unroll
+        for (int j = H0; j < NACT; ++j) dmma884(acc0[j][0], acc0[j][1], x0, bf[j - H0]);
+#pragma unroll
+        for (int j = H0; j < NACT; ++j) dmma884(acc1[j][0], acc1[j][1], x1, bf[j - H0]);
+      }
     }
     return;
   }
@@ -955,11 +968,11 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
 
   // warp grid (WM x WN consumer warps, NW sub-blocks per warp): widest tile of units that still
   // covers the columns of a block in one pass
-  // (measured on B200: sn_t_10percent 7.0 ms with (12,1,8) vs 7.3 ms with (8,1,8); sn_pol_10percent 16.1 ms with
-  //  (6,2,5) vs 16.7 ms with (8,1,10); sn_pol_5percent_lmax3000 357 ms with (4,3,7) vs 367 ms with (2,4,8))
+  // (measured on B200: sn_t_10percent 7.0 ms with (12,1,8) vs 7.3 ms with (8,1,8); sn_pol_10percent 14.8 ms with
+  //  (12,1,10) vs 16.0 ms with (6,2,5) and 16.6 ms with (8,1,10); sn_pol_5percent_lmax3000 357 ms with (4,3,7) vs 367 ms with (2,4,8))
   if (max_sb <= 7) { fs->wm = 12; fs->wn = 1; fs->nw = 7; }     // three consumer warps per SM sub-partition
   else if (max_sb <= 8) { fs->wm = 12; fs->wn = 1; fs->nw = 8; }
-  else if (max_sb <= 10) { fs->wm = 6; fs->wn = 2; fs->nw = 5; }
+  else if (max_sb <= 10) { fs->wm = 12; fs->wn = 1; fs->nw = 10; }
   else if (max_sb <= 16) { fs->wm = 4; fs->wn = 2; fs->nw = 8; }
   else if (max_sb <= 20) { fs->wm = 4; fs->wn = 2; fs->nw = 10; }
   else if (max_sb <= 21) { fs->wm = 4; fs->wn = 3; fs->nw = 7; }
@@ -1259,6 +1272,7 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
         // three consumer warps per SM sub-partition
         case 120107: e = np1 ? launch_tc<12, 1, 7, 1>(TP, n_ctas, smem, st) : launch_tc<12, 1, 7, 3>(TP, n_ctas, smem, st); break;
         case 120108: e = np1 ? launch_tc<12, 1, 8, 3>(TP, n_ctas, smem, st) : launch_tc<12, 1, 8, 1>(TP, n_ctas, smem, st); break;
+        case 120110: e = launch_tc<12, 1, 10, 1>(TP, n_ctas, smem, st); break;
         case 60205:  e = launch_tc<6, 2, 5, 1>(TP, n_ctas, smem, st); break;
         case 60208:  e = launch_tc<6, 2, 8, 1>(TP, n_ctas, smem, st); break;
         case 40307:  e = launch_tc<4, 3, 7, 1>(TP, n_ctas, smem, st); break;
