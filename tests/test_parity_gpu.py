@@ -138,8 +138,12 @@ def test_fast_tolerance_quick_song_run(oracle):
     assert rel_err_above_floor(got, ref) < REL_TOL
 
 
-def test_fast_many_columns_layouts(oracle):
-    """Column counts that exercise the (WM,WN) = (4,2) and (2,4) warp grids and partial sub-blocks."""
+@pytest.mark.parametrize("shape", [None, "12,1,7", "12,1,10"])
+def test_fast_many_columns_layouts(oracle, monkeypatch, shape):
+    """Column counts that exercise the (WM,WN) = (4,2) and (2,4) warp grids and partial sub-blocks; with a forced
+    (12,1,x) grid the wide blocks are covered in several column passes (the choice made for large batches)."""
+    if shape:
+        monkeypatch.setenv("SONG_LOS_TC_SHAPE", shape)
     for lmax, linstep in ((300, 4), (700, 4)):
         p = configs.tiny(l_max_scalars=lmax, l_linstep=linstep, l_logstep=1.05, sources_k3_interpolation="cubic",
                          k_max_tau0_over_l_max_song=0.25)
