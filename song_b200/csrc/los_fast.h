@@ -21,7 +21,6 @@ struct FastHostLayout {
   int tau_size;
   int64_t n_pt_total;                   // coarse k3 points of the batch
   int max_np;                           // longest coarse k3 grid of the batch
-  int units_per_row;                    // k3 values of the batch / xx_size (0: unknown, assume a large batch)
   int xx_uniform; double xx_delta;      // xx[i] == i*xx_delta bit for bit (bessel2_get_xx_list's lin_space from 0)
 };
 

@@ -880,7 +880,6 @@ struct FastState {
   int64_t jq_row = 0;
   int64_t s_doubles_per_unit = 0;        // sum over groups of tau_size * tpp
   int wm = 8, wn = 1, nw = 8;
-  bool dense_class = true;               // the warp grid was chosen for >= 60 k3 values per table row
   int kcs_max = 1, nsb_pass_max = 1, tpp_max = 4, n_cols_total = 0, tau_size = 0;
   Buf<double> Jq, keys_out, S, slot_sign, col_scale;
   Buf<double2> CSD;
@@ -970,15 +969,13 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
   // warp grid (WM x WN consumer warps, NW sub-blocks per warp): widest tile of units that still
   // covers the columns of a block in one pass
   // (measured on B200: sn_t_10percent 7.0 ms with (12,1,8) vs 7.3 ms with (8,1,8); sn_pol_10percent 14.8 ms with
-  //  (12,1,10) vs 16.0 ms with (6,2,5) and 16.6 ms with (8,1,10); sn_pol_5percent_lmax3000 357 ms with (4,3,7) vs 367 ms with (2,4,8))
-  //  sn_pol_5percent_lmax3000 at 85 k3 values per table row: 616 ms with (12,1,7) in three column passes vs 648 ms with
-  //  (4,3,7); at 34 per row a 192-unit tile spans 6-7 rows and the narrow tiles win: 352 ms (4,3,7) vs 402 ms)
-  const bool dense = (h.units_per_row == 0 || h.units_per_row >= 60);
-  fs->dense_class = dense;
+  //  (12,1,10) vs 16.0 ms with (6,2,5) and 16.6 ms with (8,1,10);
+  //  sn_pol_5percent_lmax3000 357 ms with (4,3,7) vs 367 ms with (2,4,8) on a 1.5 M k3 sample; 192-unit tiles in three
+  //  column passes, (12,1,7), won on a uniformly sampled 3.7 M k3 batch (616 vs 648 ms) but lost on the full run, whose
+  //  batches are consecutive k1 levels (1448 vs 1387 ms): not adopted)
   if (max_sb <= 7) { fs->wm = 12; fs->wn = 1; fs->nw = 7; }     // three consumer warps per SM sub-partition
   else if (max_sb <= 8) { fs->wm = 12; fs->wn = 1; fs->nw = 8; }
   else if (max_sb <= 10) { fs->wm = 12; fs->wn = 1; fs->nw = 10; }
-  else if (dense) { fs->wm = 12; fs->wn = 1; fs->nw = 7; }      // several column passes of <= 7 sub-blocks
   else if (max_sb <= 16) { fs->wm = 4; fs->wn = 2; fs->nw = 8; }
   else if (max_sb <= 20) { fs->wm = 4; fs->wn = 2; fs->nw = 10; }
   else if (max_sb <= 21) { fs->wm = 4; fs->wn = 3; fs->nw = 7; }
@@ -1096,9 +1093,6 @@ static cudaError_t launch_tc(const TcParams &TP, int64_t n_ctas, size_t smem, cu
 int fast_prepare(FastState *fs, const FastHostLayout &h, const ExactParams &P, cudaStream_t st, std::string &err)
 {
   if (P.cubic_J) { err = "FAST mode supports linear Bessel interpolation only; use SONG_LOS_MODE_EXACT"; return 1; }
-  // the warp grid (and with it the column passes and the table layout) depends on how many k3 values share a table
-  // row: rebuild when a batch falls in the other density class (batches of one run are of similar size, so this is rare)
-  if (fs->table_ready && h.units_per_row > 0 && ((h.units_per_row >= 60) != fs->dense_class)) fs->table_ready = false;
   if (!fs->table_ready && build_layout(fs, h, P, st, err)) return 1;
   return 0;
 }
@@ -1133,9 +1127,7 @@ int fast_reserve(FastState *fs, int64_t U, int64_t n_src, int64_t n_pt, std::str
 int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, int device_sms, cudaStream_t st,
                  cudaEvent_t *ev, int *n_launches, int *n_chunks_out, std::string &err)
 {
-  FastHostLayout hb = h;
-  hb.units_per_row = (int)std::max<int64_t>(1, P.b.n_units / std::max(1, P.xx_size));
-  if (fast_prepare(fs, hb, P, st, err)) return 1;
+  if (fast_prepare(fs, h, P, st, err)) return 1;
   const Batch &b = P.b;
   const int64_t U = b.n_units;
   const int tau_size = P.tm.tau_size, tp2 = P.ty.tp2_size;
