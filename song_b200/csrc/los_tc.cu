@@ -274,6 +274,79 @@ __global__ void __launch_bounds__(128) tc_spline_csd_kernel(Batch b, int tau_siz
   }
 }
 
+// The part of the tridiagonal elimination that depends on the k3 grid only is the same for the tp2 x tau_size columns
+// of a pair: one thread per pair computes it once (reciprocal spacings, sig, 1/pp, the dd coefficients and the weights
+// of the end-derivative estimates); the column kernel below is then free of divisions.
+struct TcSplineCoef { double rh, r6, sig, rpp, ddc; };     // per coarse k3 point, indexed pt_off[p] + i
+struct TcSplineEnds { double fa, fb, la, lb, rbot; };      // per pair
+
+__global__ void tc_spline_coef_kernel(Batch b, TcSplineCoef *coef, TcSplineEnds *ends, int *err)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= b.n_pairs) return;
+  const int n = b.np[p];
+  const double *x = b.k3_pt + b.pt_off[p];
+  TcSplineCoef *c = coef + b.pt_off[p];
+  if (n > TC_SPLINE_MAX_NP || n < 3) { atomicOr(err, ERR_H_ZERO); return; }
+  double ddp = -0.5;
+  c[0].ddc = ddp; c[0].sig = 0.; c[0].rpp = 0.; c[0].r6 = 0.;
+  for (int i = 0; i + 1 < n; ++i) c[i].rh = 1.0 / (x[i + 1] - x[i]);
+  c[n - 1].rh = 0.;
+  for (int i = 1; i + 1 < n; ++i) {
+    const double sig = (x[i] - x[i - 1]) / (x[i + 1] - x[i - 1]);
+    const double pp = sig * ddp + 2.0;
+    ddp = (sig - 1.0) / pp;
+    c[i].sig = sig; c[i].rpp = 1.0 / pp; c[i].ddc = ddp; c[i].r6 = 6.0 / (x[i + 1] - x[i - 1]);
+  }
+  TcSplineEnds e;
+  const double a = x[2] - x[0], cc = x[1] - x[0], g = x[2] - x[1];
+  e.fa = a * a / (a * cc * g); e.fb = cc * cc / (a * cc * g);
+  const double al = x[n - 3] - x[n - 1], cl = x[n - 2] - x[n - 1], gl = x[n - 3] - x[n - 2];
+  e.la = al * al / (al * cl * gl); e.lb = cl * cl / (al * cl * gl);
+  e.rbot = 1.0 / (0.5 * c[n - 2].ddc + 1.0);
+  ends[p] = e;
+}
+
+__global__ void __launch_bounds__(128) tc_spline_csd_coef_kernel(Batch b, int tau_size, int tp2_size, const TcSplineCoef *coef,
+                                                                 const TcSplineEnds *ends, double2 *CSD)
+{
+  int64_t rowlen = (int64_t)tp2_size * tau_size;
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= rowlen * b.n_pairs) return;
+  int p = (int)(c / rowlen);
+  int64_t col = c - (int64_t)p * rowlen;           // col = tau*tp2 + tp   (tp fastest)
+  int tau = (int)(col / tp2_size), tp = (int)(col % tp2_size);
+  int n = b.np[p];
+  if (n > TC_SPLINE_MAX_NP || n < 3) return;       // flagged by the coefficient kernel
+  const double *y = b.src + b.src_off[p] + ((int64_t)tp * tau_size + tau) * n;
+  const TcSplineCoef *k = coef + b.pt_off[p];
+  const TcSplineEnds e = ends[p];
+  double2 *cs = CSD + b.src_off[p] + col;
+  double u[TC_SPLINE_MAX_NP];
+  double ylo = y[0], ymid = y[1];
+  const double dy_first = e.fa * (ymid - ylo) - e.fb * (y[2] - ylo);
+  double up = (3. * k[0].rh) * ((ymid - ylo) * k[0].rh - dy_first);
+  u[0] = up;
+  double rh_prev = k[0].rh;
+  for (int i = 1; i + 1 < n; ++i) {
+    const TcSplineCoef ki = k[i];
+    const double yhi = y[i + 1];
+    const double ui = (yhi - ymid) * ki.rh - (ymid - ylo) * rh_prev;
+    up = (ki.r6 * ui - ki.sig * up) * ki.rpp;
+    u[i] = up;
+    ylo = ymid; ymid = yhi; rh_prev = ki.rh;
+  }
+  // here ylo = y[n-2], ymid = y[n-1]
+  const double dy_last = e.la * (ylo - ymid) - e.lb * (y[n - 3] - ymid);
+  const double un = (3. * k[n - 2].rh) * (dy_last - (ymid - ylo) * k[n - 2].rh);
+  double next = (un - 0.5 * u[n - 2]) * e.rbot;
+  cs[(int64_t)(n - 1) * rowlen] = make_double2(ymid, next);
+  for (int i = n - 2; i >= 0; --i) {
+    next = k[i].ddc * next + u[i];
+    cs[(int64_t)i * rowlen] = make_double2(y[i], next);
+  }
+}
+
 // unit -> pair map: one CTA per pair writes its run of the pair-major unit sequence
 __global__ void tc_unit_pair_kernel(Batch b, int *unit_pair)
 {
@@ -885,6 +958,7 @@ struct FastState {
   Buf<double2> CSD;
   Buf<int> col_tt, col_l, col_lm, term_col0, nact, perm_in, perm, unit_pair, slot_tp, jcount;
   Buf<TcUnitW> uw; Buf<int2> ujp;
+  Buf<TcSplineCoef> spl_coef; Buf<TcSplineEnds> spl_ends;
   Buf<unsigned char> cub_tmp;
   TcParams tp{};                 // kernel parameter block (about 3 KB: kept off the stack)
   TcInterp interp{};
@@ -899,7 +973,7 @@ void fast_state_destroy(FastState *f)
   f->Jq.release(); f->keys_out.release(); f->S.release(); f->slot_sign.release(); f->col_scale.release(); f->CSD.release();
   f->col_tt.release(); f->col_l.release(); f->col_lm.release(); f->term_col0.release(); f->nact.release();
   f->perm_in.release(); f->perm.release(); f->unit_pair.release(); f->slot_tp.release();
-  f->uw.release(); f->ujp.release(); f->cub_tmp.release(); f->jcount.release();
+  f->uw.release(); f->ujp.release(); f->cub_tmp.release(); f->jcount.release(); f->spl_coef.release(); f->spl_ends.release();
   delete f;
 }
 
@@ -1119,6 +1193,7 @@ int fast_reserve(FastState *fs, int64_t U, int64_t n_src, int64_t n_pt, std::str
   FCK(fs->uw.reserve((size_t)U)); FCK(fs->ujp.reserve((size_t)U));
   FCK(fs->S.reserve((size_t)U * fs->tau_size * fs->tpp_max));
   FCK(fs->jcount.reserve((size_t)n_pt));
+  FCK(fs->spl_coef.reserve((size_t)n_pt)); FCK(fs->spl_ends.reserve((size_t)n_pt));    // n_pairs <= n_pt / 2
   return 0;
 }
 
@@ -1141,7 +1216,14 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
   FCK(fs->CSD.reserve((size_t)h.n_src_total));
   {
     int64_t cols = rowlen * b.n_pairs;
-    if (cols > 0) {
+    if (cols > 0 && P.cubic_k3 && !getenv("SONG_LOS_TC_OLD_SPLINE")) {
+      FCK(fs->spl_coef.reserve((size_t)h.n_pt_total)); FCK(fs->spl_ends.reserve((size_t)b.n_pairs));
+      tc_spline_coef_kernel<<<(unsigned)((b.n_pairs + 63) / 64), 64, 0, st>>>(b, fs->spl_coef.p, fs->spl_ends.p, P.err);
+      FCK(cudaGetLastError());
+      tc_spline_csd_coef_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(b, tau_size, tp2, fs->spl_coef.p, fs->spl_ends.p, fs->CSD.p);
+      FCK(cudaGetLastError());
+      *n_launches += 2;
+    } else if (cols > 0) {
       tc_spline_csd_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(b, tau_size, tp2, P.cubic_k3, fs->CSD.p, P.err);
       FCK(cudaGetLastError());
       ++*n_launches;
