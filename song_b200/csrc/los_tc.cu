@@ -1245,7 +1245,7 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
     FCK(fs->cub_tmp.reserve(tmp_bytes));
     FCK(cub::DeviceRadixSort::SortPairs(fs->cub_tmp.p, tmp_bytes, b.k3_tr, fs->keys_out.p, fs->perm_in.p, fs->perm.p,
                                         (int)U, 0, 64, st));
-    *n_launches += 5;
+    *n_launches += 2 + 10;                 // unit_pair, iota + cub (histogram, scan, 8 onesweep passes over 64-bit keys)
   }
   FCK(cudaEventRecord(ev[2], st));
 
