@@ -282,6 +282,11 @@ def main():
     workload.fill_sources(wl, seed=20261017 + 7919 * rank)
     eng = LosEngine(wl, device=local_rank)
     b2 = Bessel2(wl).init(eng)                      # bessel2_init: host j_l1 + 3j, device J_Llm assembly
+    cap = eng.max_batch_units(mode, wl.src.size / max(wl.n_units, 1))
+    if wl.n_units > cap:
+        raise SystemExit(f"bench.py: {args.workload} has {wl.n_units} k3 values, one resident batch holds {cap} on this GPU; "
+                         f"bench.py times configs[1]-sized workloads in one batch -- use tools/run_config.py {args.workload} "
+                         "for the batched end-to-end run of the larger BASELINE workloads")
     peaks = eng.measure_peaks()
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
