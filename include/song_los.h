@@ -213,10 +213,11 @@ int  song_los_host_free(void *ptr);
  * (k3 values of the run), i.e. tp2_size * tau_size * <k3_pt> / <k3_tr>.  Needs the projection tables. */
 int  song_los_max_batch_units(song_los_ctx *ctx, int mode, double src_doubles_per_unit, int64_t *units);
 
-/* Pre-allocates all device buffers for batches of up to the given sizes (pairs, k3 values, coarse k3
- * points, source doubles).  Optional, but without it a batch larger than every earlier one makes the
+/* Pre-allocates all device buffers for a pipeline of `n_in_flight` (1..SONG_LOS_MAX_IN_FLIGHT) batches of up to the
+ * given sizes (pairs, k3 values, coarse k3 points, source doubles).  Optional, but without it a batch larger than every earlier one makes the
  * engine grow its buffers, and cudaMalloc/cudaFree stall the pipeline. */
-int  song_los_reserve(song_los_ctx *ctx, int mode, int max_pairs, int64_t max_units, int64_t max_pt, int64_t max_src);
+int  song_los_reserve(song_los_ctx *ctx, int mode, int n_in_flight, int max_pairs, int64_t max_units, int64_t max_pt,
+                      int64_t max_src);
 
 /* Device pointer of the [tt2_size][n_units] result of the last compute (for the NCCL gather
    done by the multi-GPU driver), as an integer address; 0 before the first compute. */

@@ -185,7 +185,7 @@ def los():
         lib.song_los_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
         lib.song_los_host_free.argtypes = [vp]
         lib.song_los_max_batch_units.argtypes = [vp, C.c_int, C.c_double, c_int64_p]
-        lib.song_los_reserve.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64]
+        lib.song_los_reserve.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64]
         _los = lib
     return _los
 

@@ -707,13 +707,17 @@ extern "C" int song_los_host_free(void *ptr)
 // Pre-allocates the device buffers of all slots and the intermediates of one compute for batches of up to
 // the given sizes: cudaMalloc/cudaFree synchronise the whole device, so growing a buffer between pipelined
 // batches would serialise the copies of one batch with the kernels of another.
-extern "C" int song_los_reserve(song_los_ctx *ctx, int mode, int max_pairs, int64_t max_units, int64_t max_pt, int64_t max_src)
+extern "C" int song_los_reserve(song_los_ctx *ctx, int mode, int n_in_flight, int max_pairs, int64_t max_units, int64_t max_pt, int64_t max_src)
 {
   if (!ctx) return SONG_LOS_FAILURE;
   CK(cudaSetDevice(ctx->device));
   if (ctx->n_in_flight) return ctx_fail(ctx, "song_los_reserve: submitted batches are still in flight");
   const song_los_config &c = ctx->cfg;
-  for (auto &S : ctx->slot) {
+  // one batch at a time stays in the current slot; any deeper pipeline cycles through all of them
+  const int n_slots = (n_in_flight <= 1) ? 1 : (int)song_los_ctx::N_SLOTS;
+  for (int is = 0; is < n_slots; ++is) {
+    // the slots a pipeline of this depth cycles through start at the current one
+    song_los_ctx::Slot &S = ctx->slot[(ctx->cur + is) % song_los_ctx::N_SLOTS];
     const size_t meta_bytes = std::max<size_t>((size_t)max_pairs * (3 * sizeof(int64_t) + 5 * sizeof(int)), 64);
     if (meta_bytes > S.h_meta_cap) {
       if (S.h_meta) cudaFreeHost(S.h_meta);

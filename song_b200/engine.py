@@ -167,8 +167,8 @@ class LosEngine:
         self._check(self.lib.song_los_max_batch_units(self.ctx, mode, float(src_doubles_per_unit), C.byref(n)))
         return int(n.value)
 
-    def reserve(self, mode: int, max_pairs: int, max_units: int, max_pt: int, max_src: int):
-        self._check(self.lib.song_los_reserve(self.ctx, mode, int(max_pairs), int(max_units), int(max_pt), int(max_src)))
+    def reserve(self, mode: int, max_pairs: int, max_units: int, max_pt: int, max_src: int, n_in_flight: int = 3):
+        self._check(self.lib.song_los_reserve(self.ctx, mode, int(n_in_flight), int(max_pairs), int(max_units), int(max_pt), int(max_src)))
 
     def set_stream(self, cuda_stream: int | None):
         self._check(self.lib.song_los_set_stream(self.ctx, C.c_void_p(cuda_stream or 0)))

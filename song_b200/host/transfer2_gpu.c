@@ -480,32 +480,43 @@ typedef struct {
   double *k3_pt, *k3_tr, *src, *out;
   int n_pairs; int64_t n_pt, n_units, n_src;
   const los_k1_batch *kb;          /* NULL when the staging is free */
+  int pinned;                      /* page-locked (song_los_host_alloc) or plain malloc */
 } los_staging;
+
+static int stg_alloc(los_staging *s, void **ptr, size_t bytes)
+{
+  if (s->pinned) return song_los_host_alloc(ptr, bytes);
+  *ptr = malloc(bytes > 0 ? bytes : 1);
+  return *ptr ? SONG_LOS_SUCCESS : SONG_LOS_FAILURE;
+}
+static void stg_free(los_staging *s, void *ptr) { if (s->pinned) song_los_host_free(ptr); else free(ptr); }
 
 static void staging_free(los_staging *s)
 {
-  song_los_host_free(s->np); song_los_host_free(s->nt); song_los_host_free(s->ps); song_los_host_free(s->pz);
-  song_los_host_free(s->pt_off); song_los_host_free(s->tr_off); song_los_host_free(s->src_off);
-  song_los_host_free(s->k3_pt); song_los_host_free(s->k3_tr); song_los_host_free(s->src); song_los_host_free(s->out);
+  stg_free(s, s->np); stg_free(s, s->nt); stg_free(s, s->ps); stg_free(s, s->pz);
+  stg_free(s, s->pt_off); stg_free(s, s->tr_off); stg_free(s, s->src_off);
+  stg_free(s, s->k3_pt); stg_free(s, s->k3_tr); stg_free(s, s->src); stg_free(s, s->out);
   memset(s, 0, sizeof *s);
 }
 
-/* capacity of the largest batch of a device */
-static int staging_alloc(los_staging *s, int max_pairs, int64_t max_pt, int64_t max_units, int64_t max_src, int tt2_size)
+/* capacity of the largest batch of a device.  Page-locking costs about half a second per GB: it pays only when
+   copies have something to overlap with, i.e. when the device runs more than one batch. */
+static int staging_alloc(los_staging *s, int pinned, int max_pairs, int64_t max_pt, int64_t max_units, int64_t max_src, int tt2_size)
 {
   memset(s, 0, sizeof *s);
+  s->pinned = pinned;
   int rc = 0;
-  rc |= song_los_host_alloc((void **)&s->np, sizeof(int) * (size_t)max_pairs);
-  rc |= song_los_host_alloc((void **)&s->nt, sizeof(int) * (size_t)max_pairs);
-  rc |= song_los_host_alloc((void **)&s->ps, sizeof(int) * (size_t)max_pairs);
-  rc |= song_los_host_alloc((void **)&s->pz, sizeof(int) * (size_t)max_pairs);
-  rc |= song_los_host_alloc((void **)&s->pt_off, sizeof(int64_t) * (size_t)max_pairs);
-  rc |= song_los_host_alloc((void **)&s->tr_off, sizeof(int64_t) * (size_t)max_pairs);
-  rc |= song_los_host_alloc((void **)&s->src_off, sizeof(int64_t) * (size_t)max_pairs);
-  rc |= song_los_host_alloc((void **)&s->k3_pt, sizeof(double) * (size_t)max_pt);
-  rc |= song_los_host_alloc((void **)&s->k3_tr, sizeof(double) * (size_t)max_units);
-  rc |= song_los_host_alloc((void **)&s->src, sizeof(double) * (size_t)max_src);
-  rc |= song_los_host_alloc((void **)&s->out, sizeof(double) * (size_t)max_units * tt2_size);
+  rc |= stg_alloc(s, (void **)&s->np, sizeof(int) * (size_t)max_pairs);
+  rc |= stg_alloc(s, (void **)&s->nt, sizeof(int) * (size_t)max_pairs);
+  rc |= stg_alloc(s, (void **)&s->ps, sizeof(int) * (size_t)max_pairs);
+  rc |= stg_alloc(s, (void **)&s->pz, sizeof(int) * (size_t)max_pairs);
+  rc |= stg_alloc(s, (void **)&s->pt_off, sizeof(int64_t) * (size_t)max_pairs);
+  rc |= stg_alloc(s, (void **)&s->tr_off, sizeof(int64_t) * (size_t)max_pairs);
+  rc |= stg_alloc(s, (void **)&s->src_off, sizeof(int64_t) * (size_t)max_pairs);
+  rc |= stg_alloc(s, (void **)&s->k3_pt, sizeof(double) * (size_t)max_pt);
+  rc |= stg_alloc(s, (void **)&s->k3_tr, sizeof(double) * (size_t)max_units);
+  rc |= stg_alloc(s, (void **)&s->src, sizeof(double) * (size_t)max_src);
+  rc |= stg_alloc(s, (void **)&s->out, sizeof(double) * (size_t)max_units * tt2_size);
   if (rc != SONG_LOS_SUCCESS) { staging_free(s); return _FAILURE_; }
   return _SUCCESS_;
 }
@@ -524,10 +535,11 @@ static void batch_sizes(struct perturbs2 *ppt2, struct transfers2 *ptr2, const l
 /* packs the k1 levels of `kb` into the staging and enqueues the batch on the GPU (song_los_submit) */
 static int submit_batch(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2, struct bessels *pbs,
                         struct bessels2 *pbs2, struct transfers2 *ptr2, song_los_ctx *ctx, int mode, const los_k1_batch *kb,
-                        los_staging *s, char *errmsg)
+                        los_staging *s, int host_threads, char *errmsg)
 {
   const int tp2 = ppt2->tp2_size, ntau = ppt2->tau_size;
   batch_sizes(ppt2, ptr2, kb, &s->n_pairs, &s->n_pt, &s->n_units, &s->n_src);
+  /* sizes and offsets first (serial), then every pair is packed independently by the host threads of this GPU */
   int p = 0;
   int64_t o_pt = 0, o_tr = 0, o_src = 0;
   for (int k1 = kb->k1_first; k1 <= kb->k1_last; ++k1)
@@ -535,15 +547,26 @@ static int submit_batch(struct precision *ppr, struct precision2 *ppr2, struct p
       s->np[p] = ppt2->k3_size[k1][k2]; s->nt[p] = ptr2->k_size_k1k2[k1][k2];
       s->ps[p] = ptr2->k_physical_start_k1k2[k1][k2]; s->pz[p] = ptr2->k_physical_size_k1k2[k1][k2];
       s->pt_off[p] = o_pt; s->tr_off[p] = o_tr; s->src_off[p] = o_src;
-      memcpy(s->k3_pt + o_pt, ppt2->k3[k1][k2], sizeof(double) * s->np[p]);
-      if (transfer2_get_k3_list(ppr, ppr2, ppt2, pbs, pbs2, ptr2, k1, k2, s->k3_tr + o_tr, NULL) == _FAILURE_) {
-        snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); return _FAILURE_;
-      }
-      /* ppt2->sources[tp][k1][k2][tau*k3_size + k3] (transfer2.h:47-51) -> packed [pair][tp][tau][k3] */
-      for (int tp = 0; tp < tp2; ++tp)
-        memcpy(s->src + o_src + (int64_t)tp * ntau * s->np[p], ppt2->sources[tp][k1][k2], sizeof(double) * (size_t)ntau * s->np[p]);
       o_pt += s->np[p]; o_tr += s->nt[p]; o_src += (int64_t)tp2 * ntau * s->np[p];
     }
+  int failed = 0;
+  #pragma omp parallel for schedule(dynamic, 8) num_threads(host_threads) if (host_threads > 1)
+  for (int q = 0; q < s->n_pairs; ++q) {
+    /* pair q of the batch -> (k1,k2): k1 levels are consecutive, level k1 holds k1+1 pairs */
+    int k1 = kb->k1_first, r = q;
+    while (r > k1) { r -= k1 + 1; ++k1; }
+    const int k2 = r;
+    memcpy(s->k3_pt + s->pt_off[q], ppt2->k3[k1][k2], sizeof(double) * s->np[q]);
+    if (transfer2_get_k3_list(ppr, ppr2, ppt2, pbs, pbs2, ptr2, k1, k2, s->k3_tr + s->tr_off[q], NULL) == _FAILURE_) {
+      #pragma omp atomic write
+      failed = 1;
+      continue;
+    }
+    /* ppt2->sources[tp][k1][k2][tau*k3_size + k3] (transfer2.h:47-51) -> packed [pair][tp][tau][k3] */
+    for (int tp = 0; tp < tp2; ++tp)
+      memcpy(s->src + s->src_off[q] + (int64_t)tp * ntau * s->np[q], ppt2->sources[tp][k1][k2], sizeof(double) * (size_t)ntau * s->np[q]);
+  }
+  if (failed) { snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); return _FAILURE_; }
   song_los_batch b;
   memset(&b, 0, sizeof b);
   b.n_pairs = s->n_pairs; b.k3_pt_size = s->np; b.k3_tr_size = s->nt; b.phys_start = s->ps; b.phys_size = s->pz;
@@ -560,21 +583,24 @@ static int submit_batch(struct precision *ppr, struct precision2 *ppr2, struct p
 /* waits for the oldest batch in flight and scatters its result into ptr2->transfer[tt][k1][k2][k3]
    (transfer2.c:2107), then applies the per-k1 side effects of transfer2.c:559-567 */
 static int finish_batch(struct precision2 *ppr2, struct perturbs2 *ppt2, struct transfers2 *ptr2, song_los_ctx *ctx,
-                        los_staging *s, char *errmsg)
+                        los_staging *s, int host_threads, char *errmsg)
 {
   const los_k1_batch *kb = s->kb;
   s->kb = NULL;
   if (song_los_wait(ctx, NULL) != SONG_LOS_SUCCESS) {
     snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(ctx)); return _FAILURE_;
   }
-  int p = 0;
   long stored = 0;
-  for (int k1 = kb->k1_first; k1 <= kb->k1_last; ++k1)
-    for (int k2 = 0; k2 <= k1; ++k2, ++p)
-      for (int tt = 0; tt < ptr2->tt2_size; ++tt) {
-        memcpy(ptr2->transfer[tt][k1][k2], s->out + (int64_t)tt * s->n_units + s->tr_off[p], sizeof(double) * s->nt[p]);
-        stored += s->nt[p];
-      }
+  #pragma omp parallel for schedule(dynamic, 8) reduction(+ : stored) num_threads(host_threads) if (host_threads > 1)
+  for (int q = 0; q < s->n_pairs; ++q) {
+    int k1 = kb->k1_first, r = q;
+    while (r > k1) { r -= k1 + 1; ++k1; }
+    const int k2 = r;
+    for (int tt = 0; tt < ptr2->tt2_size; ++tt) {
+      memcpy(ptr2->transfer[tt][k1][k2], s->out + (int64_t)tt * s->n_units + s->tr_off[q], sizeof(double) * s->nt[q]);
+      stored += s->nt[q];
+    }
+  }
   #pragma omp atomic
   ptr2->count_memorised_transfers += stored;                                    /* transfer2.c:2110-2111 */
   if (ppr2->store_transfers_to_disk == _TRUE_)                                  /* :559-567, in k1 order */
@@ -600,6 +626,12 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   }
   ptr2->has_cls = _TRUE_;
   if (ptr2->transfer2_verbose > 0) printf("Computing second-order transfer functions (B200 line-of-sight engine)\n");
+#ifdef _OPENMP
+  const double t_start = omp_get_wtime();
+#define LAP(what) do { if (ptr2->transfer2_verbose > 1) printf("     * %-44s %8.1f ms since the start of transfer2_init\n", what, (omp_get_wtime() - t_start) * 1e3); } while (0)
+#else
+#define LAP(what) do { } while (0)
+#endif
   if ((ppt2->k_size < 4) && (ptr2->stop_at_transfers2 == _FALSE_))
     printf("# WARNING: cannot do cubic interpolation in k1 with less than 4 values. "
            "Increase k_size, or do not trust results for 1st-order transfer functions.\n");
@@ -609,6 +641,7 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   ptr2->rs_rec = pth->rs_rec;
 
   class_call(transfer2_indices_of_transfers(ppr, ppr2, ppt2, pbs, pbs2, ptr, ptr2), ptr2->error_message, ptr2->error_message);
+  LAP("index tables and k3 grid sizes");
 
   if (ppr2->load_transfers_from_disk == _TRUE_) {                                             /* :151-157 */
     if (ptr2->transfer2_verbose > 0) printf(" -> leaving transfer2 module; transfer functions will be read from disk\n");
@@ -631,6 +664,7 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   class_calloc(dev, n_dev, sizeof(los_device), ptr2->error_message);
   if (create_engine(ppr, ppr2, ppt2, pbs2, ptr2, 0, &dev[0].ctx) == _FAILURE_) { free(dev); return _FAILURE_; }   /* no usable GPU: there is no CPU fallback */
 
+  LAP("engine on GPU 0 (context, projection tables)");
   /* k1 batches: consecutive k1 levels up to `batch_units` k3 values.  Large batches make the tensor-core kernel
      efficient (many k3 per table row); several batches per GPU let the copies overlap the kernels; the upper
      bound is what fits in device memory twice (two batches in flight). */
@@ -690,6 +724,15 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   /* Per GPU: a pipeline of up to SONG_LOS_MAX_IN_FLIGHT batches (in k1 order).  While the kernels of batch n run, the host
      packs batch n+1 into the other staging and submits it (its host->device copy overlaps), and the result of
      batch n-1 travels back and is scattered into ptr2->transfer. */
+  /* host threads per GPU for packing the sources and scattering the results (SONG_LOS_HOST_THREADS, default: an even
+     share of the processors) */
+  int host_threads = env_int("SONG_LOS_HOST_THREADS", 0);
+#ifdef _OPENMP
+  if (host_threads <= 0) host_threads = omp_get_num_procs() / (n_dev > 0 ? n_dev : 1);
+  if (n_dev > 1) omp_set_max_active_levels(2);
+#endif
+  if (host_threads < 1) host_threads = 1;
+  if (host_threads > 32) host_threads = 32;
   int abort_flag = _FALSE_;
   ErrorMsg first_error = "";
   #pragma omp parallel for num_threads(n_dev) schedule(static, 1) if (n_dev > 1)
@@ -710,16 +753,21 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
     enum { DEPTH = SONG_LOS_MAX_IN_FLIGHT };
     los_staging stg[DEPTH];
     memset(stg, 0, sizeof stg);
-    for (int i = 0; i < DEPTH && ok; ++i)
-      if (staging_alloc(&stg[i], max_pairs, max_pt, max_units, max_src, ptr2->tt2_size) == _FAILURE_) {
+    int n_mine = 0;
+    for (int ib = 0; ib < n_batches; ++ib) if (batches[ib].device == d) ++n_mine;
+    const int depth = n_mine < DEPTH ? (n_mine > 0 ? n_mine : 1) : DEPTH;    /* page-locking memory is slow: no more sets than batches */
+    for (int i = 0; i < depth && ok; ++i)
+      if (staging_alloc(&stg[i], n_mine > 1, max_pairs, max_pt, max_units, max_src, ptr2->tt2_size) == _FAILURE_) {
         snprintf(local, _ERRORMSGSIZE_, "could not allocate the page-locked staging of a GPU batch (%ld k3 values): %.1000s",
                  (long)max_units, song_los_last_error(NULL));
         ok = _FALSE_;
       }
+    if (d == 0) LAP("page-locked staging allocated (GPU 0)");
     /* device buffers for the largest batch: no allocation (= device-wide synchronisation) inside the pipeline */
-    if (ok && song_los_reserve(dev[d].ctx, mode, max_pairs, max_units, max_pt, max_src) != SONG_LOS_SUCCESS) {
+    if (ok && song_los_reserve(dev[d].ctx, mode, depth, max_pairs, max_units, max_pt, max_src) != SONG_LOS_SUCCESS) {
       snprintf(local, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(dev[d].ctx)); ok = _FALSE_;
     }
+    if (d == 0) LAP("device buffers reserved (GPU 0)");
     int cur = 0, in_flight = 0;
     for (int ib = 0; ok && ib < n_batches; ++ib) {
       if (batches[ib].device != d) continue;
@@ -737,20 +785,22 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
       }
       /* the staging about to be reused must have been drained: at most DEPTH batches are in flight */
       if (ok && stg[cur].kb != NULL) {
-        if (finish_batch(ppr2, ppt2, ptr2, dev[d].ctx, &stg[cur], local) == _FAILURE_) ok = _FALSE_;
+        if (finish_batch(ppr2, ppt2, ptr2, dev[d].ctx, &stg[cur], host_threads, local) == _FAILURE_) ok = _FALSE_;
         --in_flight;
       }
-      if (ok && submit_batch(ppr, ppr2, ppt2, pbs, pbs2, ptr2, dev[d].ctx, mode, kb, &stg[cur], local) == _FAILURE_) ok = _FALSE_;
-      if (ok) { ++in_flight; cur = (cur + 1) % DEPTH; }
+      if (d == 0 && ib == 0) LAP("ptr2->transfer levels of the first batch allocated");
+      if (ok && submit_batch(ppr, ppr2, ppt2, pbs, pbs2, ptr2, dev[d].ctx, mode, kb, &stg[cur], host_threads, local) == _FAILURE_) ok = _FALSE_;
+      if (ok) { ++in_flight; cur = (cur + 1) % depth; }
+      if (d == 0 && ib == 0) LAP("first batch packed and submitted");
       /* the sources of these k1 levels now live in the staging: free them as the reference does (:553) */
       for (int k1 = kb->k1_first; ok && k1 <= kb->k1_last; ++k1)
         if (perturb2_free_k1_level(ppt2, k1) == _FAILURE_) { snprintf(local, _ERRORMSGSIZE_, "%.1500s", ppt2->error_message); ok = _FALSE_; break; }
     }
     /* drain in submission order: stg[cur] holds the older batch */
-    for (int i = 0; i < DEPTH; ++i) {
-      los_staging *s = &stg[(cur + i) % DEPTH];
+    for (int i = 0; i < depth; ++i) {
+      los_staging *s = &stg[(cur + i) % depth];
       if (s->kb == NULL) continue;
-      if (ok) { if (finish_batch(ppr2, ppt2, ptr2, dev[d].ctx, s, local) == _FAILURE_) ok = _FALSE_; }
+      if (ok) { if (finish_batch(ppr2, ppt2, ptr2, dev[d].ctx, s, host_threads, local) == _FAILURE_) ok = _FALSE_; }
       else { song_los_wait(dev[d].ctx, NULL); s->kb = NULL; }
     }
     for (int i = 0; i < DEPTH; ++i) staging_free(&stg[i]);
@@ -759,6 +809,7 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
       { if (abort_flag == _FALSE_) { abort_flag = _TRUE_; snprintf(first_error, _ERRORMSGSIZE_, "%s", local); } }
     }
   }
+  LAP("all batches computed and stored");
   for (int d = 0; d < n_dev; ++d) song_los_destroy(dev[d].ctx);
   free(dev); free(batches);
   class_test(abort_flag == _TRUE_, ptr2->error_message, "%.1900s", first_error);
