@@ -285,7 +285,7 @@ def main():
     cap = eng.max_batch_units(mode, wl.src.size / max(wl.n_units, 1))
     if wl.n_units > cap:
         raise SystemExit(f"bench.py: {args.workload} has {wl.n_units} k3 values, one resident batch holds {cap} on this GPU; "
-                         f"bench.py times configs[1]-sized workloads in one batch -- use tools/run_config.py {args.workload} "
+                         f"bench.py times configs[1]-sized workloads in one batch -- use tests/big/run_config.py {args.workload} "
                          "for the batched end-to-end run of the larger BASELINE workloads")
     peaks = eng.measure_peaks()
     stream = torch.cuda.current_stream()

@@ -2,7 +2,7 @@
 (the way transfer2_gpu.c does), generating the synthetic sources batch by batch, and spot-checks
 parity against the CPU oracle on sampled (k1,k2) pairs.  Prints one JSON line.
 
-usage: python tools/run_config.py NAME [--oracle-pairs N] [--mode fast|exact] [--batch-units N] [--max-pairs N]
+usage: python tests/big/run_config.py NAME [--oracle-pairs N] [--mode fast|exact] [--batch-units N] [--max-pairs N]
 """
 import argparse
 import json
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import oracle_lib as O  # noqa: E402
 from song_b200 import configs, workload  # noqa: E402

@@ -1,5 +1,5 @@
 """Times song_los_compute on BASELINE workloads and spot-checks parity on sampled pairs.
-usage: python tools/time_configs.py [--mode fast|exact|both] [--oracle-pairs N] name [name...]"""
+usage: python tests/big/time_configs.py [--mode fast|exact|both] [--oracle-pairs N] name [name...]"""
 import argparse
 import os
 import sys
@@ -7,7 +7,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import oracle_lib as O  # noqa: E402
 from song_b200 import configs, workload  # noqa: E402

@@ -1,10 +1,10 @@
 """Wall time of transfer2_init (the drop-in module, song_b200/host/transfer2_gpu.c) on a BASELINE workload:
 SONG structs filled by the test harness, sources in ppt2->sources, result in ptr2->transfer.  Includes what the
 C-ABI bench does not: packing the sources into page-locked staging and scattering the result rows.
-usage: python tools/time_dropin.py [NAME] [--reps N]"""
+usage: python tests/big/time_dropin.py [NAME] [--reps N]"""
 import argparse, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import dropin_lib, oracle_lib as O  # noqa: E402
 from song_b200 import configs, workload  # noqa: E402
