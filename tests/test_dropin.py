@@ -96,7 +96,8 @@ def test_transfer2_init_multi_gpu_schedule_and_pipeline(oracle, monkeypatch, mod
 @pytest.mark.gpu
 def test_transfer2_custom_time_sampling(oracle, monkeypatch):
     """ptr2->tau_sampling = custom_tau_sampling through the drop-in (k-dependent time grids, cubic time interpolation)."""
-    wl = _tiny(transfer2_tau_sampling="custom", sources_time_interpolation="cubic", sources_k3_interpolation="cubic")
+    wl = _tiny(transfer2_tau_sampling="custom", sources_time_interpolation="cubic", sources_k3_interpolation="cubic",
+               tau_linstep_song=0.003)
     proj = oracle.build_projection(wl)
     ref, _ = oracle.OracleRun(wl, proj).run()
     got, count, _ = dropin_lib.run_transfer2(wl, Projection(proj.rows, proj.index_xmin, proj.x_size))

@@ -398,3 +398,28 @@ def test_time_grid_custom_sampling(oracle, tiny_workload):
         assert np.diff(g).max() <= 2 * math.pi / k * 0.5 * (1 + 1e-12)
         assert abs(w[:n.value].sum() - 2 * (g[-1] - g[0])) < 1e-9
         assert np.all(left[:n.value] <= wl.tau.size - 2)
+
+
+@pytest.mark.parametrize("interp", ["linear", "cubic"])
+def test_time_interpolation_reproduces_linear_sources(oracle, interp):
+    """transfer2_interpolate_sources_in_time (transfer2.c:2816-2880): a source row that is linear in tau is resampled
+    exactly on the custom grid, by the linear formula and by the cubic spline (second derivatives vanish)."""
+    wl = workload.build_grids(configs.tiny(transfer2_tau_sampling="custom", tau_linstep_song=0.5,
+                                           sources_time_interpolation=interp))
+    proj = oracle.OracleProjection([None] * (wl.layout.J_size * wl.layout.L_size * wl.layout.l_size * wl.layout.m_size),
+                                   np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1))
+    run = oracle.OracleRun(wl, proj)
+    L = oracle.lib()
+    k = 1.0                                                           # short wavelength: steps of 2 pi/k * 0.5 = 3.1 Mpc between the source times
+    nmax = L.oracle_time_grid_size_max(C.byref(run.setup), k)
+    grid = np.zeros(nmax); d = np.zeros(nmax); w = np.zeros(nmax); left = np.zeros(nmax, dtype=np.int32); n = C.c_int(0)
+    assert L.oracle_get_time_grid(C.byref(run.setup), k, _d(grid), _i(left), _d(d), _d(w), C.byref(n)) == 0
+    row = np.ascontiguousarray(3.0 - 0.01 * wl.tau)                  # interp_k row of index_k = 0
+    out = np.zeros(nmax); spline = np.zeros(wl.tau.size)
+    L.oracle_interpolate_sources_in_time.argtypes = [C.POINTER(oracle.Setup), C.c_int, oracle.dp, oracle.dp,
+                                                     C.POINTER(C.c_int), C.c_int, oracle.dp, oracle.dp]
+    assert L.oracle_interpolate_sources_in_time(C.byref(run.setup), 0, _d(row), _d(grid), _i(left), n.value,
+                                                _d(spline), _d(out)) == 0
+    want = 3.0 - 0.01 * grid[:n.value]
+    assert np.max(np.abs(out[:n.value] - want)) < 1e-12
+    assert n.value > wl.tau.size                                        # extra points were really inserted

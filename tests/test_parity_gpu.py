@@ -90,17 +90,23 @@ def test_exact_bitwise_k_dependent_time_grids(oracle, sampling, time_interp):
     """transfer2_tau_sampling = custom / bessel: transfer2_get_time_grid inserts points so that no step exceeds
     2 pi/k tau_linstep_song (transfer2.c:2422) or xx_step/k (:2432); the sources are resampled in time, linearly or
     with a cubic spline (transfer2.c:2816-2880).  Both arithmetic modes route to the exact kernels."""
+    # tau_linstep_song small enough that 2 pi/k * tau_linstep_song (k3 ~ 0.004-0.008 here) falls below the source spacing
+    # (bessel sampling: xx_step/k below the source spacing needs a finer x grid than the default 0.2)
     p = configs.tiny(transfer2_tau_sampling=sampling, sources_time_interpolation=time_interp,
-                     sources_k3_interpolation="cubic", tau_linstep_song=0.6)
+                     sources_k3_interpolation="cubic", tau_linstep_song=0.003, bessel_x_step_song=0.04)
     for mode in (MODE_EXACT, MODE_FAST):
         wl, ref, got = run_both(oracle, p, mode=mode)
         assert np.array_equal(got, ref), f"max abs diff {np.abs(got - ref).max()}"
-    # the grids really are k dependent: more integration points than source times for the largest k3
+    # the grids really are k dependent: extra integration points between the source times for the largest k3
     import ctypes as C
     s = oracle.OracleRun(wl, oracle.build_projection(wl)).setup
     kmax = float(wl.k3_tr.max())
-    nmax = oracle.lib().oracle_time_grid_size_max(C.byref(s), kmax)
-    assert nmax > wl.tau.size
+    L = oracle.lib()
+    nmax = L.oracle_time_grid_size_max(C.byref(s), kmax)
+    grid = np.zeros(nmax); d = np.zeros(nmax); w = np.zeros(nmax); left = np.zeros(nmax, dtype=np.int32); n = C.c_int(0)
+    assert L.oracle_get_time_grid(C.byref(s), kmax, grid.ctypes.data_as(oracle.dp), left.ctypes.data_as(oracle.ip),
+                                  d.ctypes.data_as(oracle.dp), w.ctypes.data_as(oracle.dp), C.byref(n)) == 0
+    assert n.value > wl.tau.size, (n.value, wl.tau.size)
 
 
 # ----------------------------------------------------------------------------------------------
