@@ -401,7 +401,7 @@ __global__ void tc_prep_units_kernel(Batch b, const int *perm, const int *unit_p
 // every (group, tau, slot) column of the chunk -- 4 FMAs each -- and writes them as one contiguous
 // run per group of S[group][sorted unit][tau][slot]: full 256-byte stores, sequential per unit.
 constexpr int TC_SLOTS = 2 * TC_KCS_MAX + 4;
-constexpr int TC_INTERP_THREADS = 256;
+constexpr int TC_INTERP_THREADS = 384;      // measured: 2.58 / 2.37 / 2.31 / 2.53 ms at 128 / 256 / 384 / 512 threads
 struct TcInterp {
   int n_groups;
   int tauc;                               // tau samples per CTA
@@ -413,7 +413,7 @@ struct TcInterp {
   const int *jcount;                      // units per (pair, interval): indexed pt_off[p] + j
 };
 
-__global__ void __launch_bounds__(TC_INTERP_THREADS) tc_interp_units_kernel(Batch b, TcInterp I, int tau_size, int tp2_size,
+__global__ void __launch_bounds__(512) tc_interp_units_kernel(Batch b, TcInterp I, int tau_size, int tp2_size,
                                                               const double2 *CSD, const TcUnitW *uw, const int2 *ujp, double *S)
 {
   extern __shared__ __align__(16) unsigned char interp_smem[];
@@ -427,11 +427,11 @@ __global__ void __launch_bounds__(TC_INTERP_THREADS) tc_interp_units_kernel(Batc
   // per (group, column of the chunk): index of the staged {y, dd} entry (tau_local * tp2 + tp) and the slot,
   // packed as idx | slot << 24; -1 for padding slots.  Replaces a division per element in the inner loop.
   int *s_col = reinterpret_cast<int *>(s_sign + TC_MAX_GROUPS * TC_SLOTS);   // [n_groups][tauc * tpp_max]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = TC_INTERP_THREADS / 32;
-  for (int i = tid; i < I.n_groups * TC_SLOTS; i += TC_INTERP_THREADS) { s_tp[i] = I.slot_tp[i]; s_sign[i] = I.slot_sign[i]; }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x / 32;
+  for (int i = tid; i < I.n_groups * TC_SLOTS; i += blockDim.x) { s_tp[i] = I.slot_tp[i]; s_sign[i] = I.slot_sign[i]; }
   for (int g = 0; g < I.n_groups; ++g) {
     const int tpp = I.grp_tpp[g];
-    for (int c = tid; c < ntau * tpp; c += TC_INTERP_THREADS) {
+    for (int c = tid; c < ntau * tpp; c += blockDim.x) {
       const int tl = c / tpp, slot = c - tl * tpp;
       const int tp = I.slot_tp[g * TC_SLOTS + slot];
       s_col[g * I.col_stride + c] = (tp >= 0) ? ((tl * tp2_size + tp) | (slot << 24)) : -1;
@@ -442,11 +442,11 @@ __global__ void __launch_bounds__(TC_INTERP_THREADS) tc_interp_units_kernel(Batc
   const int64_t rowlen = (int64_t)tau_size * tp2_size;
   const double2 *cs = CSD + b.src_off[p] + (int64_t)tau0 * tp2_size;
   const int *jcount = I.jcount + b.pt_off[p];
-  for (int c = tid; c < chunk; c += TC_INTERP_THREADS) rows[c] = cs[c];      // row 0
+  for (int c = tid; c < chunk; c += blockDim.x) rows[c] = cs[c];      // row 0
   int start = 0;
   for (int j = 0; j + 1 < np; ++j) {
     double2 *r0 = rows + (size_t)(j & 1) * I.tauc * tp2_size, *r1 = rows + (size_t)((j + 1) & 1) * I.tauc * tp2_size;
-    for (int c = tid; c < chunk; c += TC_INTERP_THREADS) r1[c] = cs[(int64_t)(j + 1) * rowlen + c];
+    for (int c = tid; c < chunk; c += blockDim.x) r1[c] = cs[(int64_t)(j + 1) * rowlen + c];
     __syncthreads();
     const int cnt = jcount[j];
     for (int i = start + warp; i < start + cnt; i += nwarps) {
@@ -1302,6 +1302,8 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
   const size_t smem = fixed + (size_t)ns * TP.stage_bytes;
 
   TcInterp &I = fs->interp;
+  int interp_threads = TC_INTERP_THREADS;
+  if (const char *v = getenv("SONG_LOS_TC_INTERP_THREADS")) interp_threads = std::max(64, std::min(512, atoi(v) / 32 * 32));
   // tau samples per CTA: two staged rows of tauc*tp2 {y, dd} entries within ~64 KB
   int tauc = std::max(1, std::min(tau_size, (int)((64 * 1024) / (2 * 16 * (size_t)tp2))));
   if (const char *v = getenv("SONG_LOS_TC_TAUC")) tauc = std::max(1, std::min(tauc, atoi(v)));
@@ -1326,7 +1328,7 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
       dim3 grid((unsigned)b.n_pairs, (unsigned)((tau_size + I.tauc - 1) / I.tauc));
       const size_t ismem = (size_t)2 * I.tauc * tp2 * 16 + (size_t)TC_MAX_GROUPS * TC_SLOTS * 12 + (size_t)I.col_stride * 4;
       FCK(cudaFuncSetAttribute(tc_interp_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
-      tc_interp_units_kernel<<<grid, TC_INTERP_THREADS, ismem, st>>>(b, I, tau_size, tp2, fs->CSD.p, fs->uw.p, fs->ujp.p, fs->S.p);
+      tc_interp_units_kernel<<<grid, interp_threads, ismem, st>>>(b, I, tau_size, tp2, fs->CSD.p, fs->uw.p, fs->ujp.p, fs->S.p);
       FCK(cudaGetLastError());
       ++*n_launches;
       FCK(cudaEventRecord(ev[6 + 2 * n_chunks], st));
