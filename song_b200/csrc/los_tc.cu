@@ -963,6 +963,7 @@ struct FastState {
   TcParams tp{};                 // kernel parameter block (about 3 KB: kept off the stack)
   TcInterp interp{};
   PFN_cuTensorMapEncodeTiled encode = nullptr;
+  cudaStream_t st2 = nullptr; cudaEvent_t ev_join = nullptr;     // second stream: the k3 sort runs beside the splines
 };
 
 FastState *fast_state_create() { return new FastState(); }
@@ -974,6 +975,8 @@ void fast_state_destroy(FastState *f)
   f->col_tt.release(); f->col_l.release(); f->col_lm.release(); f->term_col0.release(); f->nact.release();
   f->perm_in.release(); f->perm.release(); f->unit_pair.release(); f->slot_tp.release();
   f->uw.release(); f->ujp.release(); f->cub_tmp.release(); f->jcount.release(); f->spl_coef.release(); f->spl_ends.release();
+  if (f->st2) cudaStreamDestroy(f->st2);
+  if (f->ev_join) cudaEventDestroy(f->ev_join);
   delete f;
 }
 
@@ -1211,9 +1214,29 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
   const int MT = 16 * fs->wm;
   const int64_t n_tiles = (U + MT - 1) / MT;
 
-  // ---- phase 0: transposed {y, dd} sources ----
+  // ---- phase 0 and 1 side by side: the global k3 order (second stream) does not depend on the splines ----
   FCK(cudaEventRecord(ev[0], st));
+  if (!fs->st2) { FCK(cudaStreamCreateWithFlags(&fs->st2, cudaStreamNonBlocking)); FCK(cudaEventCreateWithFlags(&fs->ev_join, cudaEventDisableTiming)); }
   FCK(fs->CSD.reserve((size_t)h.n_src_total));
+  FCK(fs->perm_in.reserve((size_t)U)); FCK(fs->perm.reserve((size_t)U)); FCK(fs->keys_out.reserve((size_t)U));
+  FCK(fs->unit_pair.reserve((size_t)U));
+  if (U > 0) {
+    cudaStream_t s2 = fs->st2;
+    FCK(cudaStreamWaitEvent(s2, ev[0], 0));
+    tc_unit_pair_kernel<<<(unsigned)b.n_pairs, 128, 0, s2>>>(b, fs->unit_pair.p);
+    FCK(cudaGetLastError());
+    tc_iota_kernel<<<(unsigned)((U + 255) / 256), 256, 0, s2>>>(fs->perm_in.p, U);
+    FCK(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    FCK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, b.k3_tr, fs->keys_out.p, fs->perm_in.p, fs->perm.p,
+                                        (int)U, 0, 64, s2));
+    FCK(fs->cub_tmp.reserve(tmp_bytes));
+    FCK(cub::DeviceRadixSort::SortPairs(fs->cub_tmp.p, tmp_bytes, b.k3_tr, fs->keys_out.p, fs->perm_in.p, fs->perm.p,
+                                        (int)U, 0, 64, s2));
+    FCK(cudaEventRecord(fs->ev_join, s2));
+    *n_launches += 2 + 10;                 // unit_pair, iota + cub (histogram, scan, 8 onesweep passes over 64-bit keys)
+  }
+  // ---- phase 0: transposed {y, dd} sources ----
   {
     int64_t cols = rowlen * b.n_pairs;
     if (cols > 0 && P.cubic_k3 && !getenv("SONG_LOS_TC_OLD_SPLINE")) {
@@ -1230,23 +1253,7 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
     }
   }
   FCK(cudaEventRecord(ev[1], st));
-
-  // ---- phase 1: global k3 order ----
-  FCK(fs->perm_in.reserve((size_t)U)); FCK(fs->perm.reserve((size_t)U)); FCK(fs->keys_out.reserve((size_t)U));
-  FCK(fs->unit_pair.reserve((size_t)U));
-  if (U > 0) {
-    tc_unit_pair_kernel<<<(unsigned)b.n_pairs, 128, 0, st>>>(b, fs->unit_pair.p);
-    FCK(cudaGetLastError());
-    tc_iota_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(fs->perm_in.p, U);
-    FCK(cudaGetLastError());
-    size_t tmp_bytes = 0;
-    FCK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, b.k3_tr, fs->keys_out.p, fs->perm_in.p, fs->perm.p,
-                                        (int)U, 0, 64, st));
-    FCK(fs->cub_tmp.reserve(tmp_bytes));
-    FCK(cub::DeviceRadixSort::SortPairs(fs->cub_tmp.p, tmp_bytes, b.k3_tr, fs->keys_out.p, fs->perm_in.p, fs->perm.p,
-                                        (int)U, 0, 64, st));
-    *n_launches += 2 + 10;                 // unit_pair, iota + cub (histogram, scan, 8 onesweep passes over 64-bit keys)
-  }
+  if (U > 0) FCK(cudaStreamWaitEvent(st, fs->ev_join, 0));      // ms_sort = what is left of the sort after the splines
   FCK(cudaEventRecord(ev[2], st));
 
   // ---- phase 2: per-unit k3 brackets and spline weights ----
