@@ -338,7 +338,7 @@ def main():
     #     still copies all of its inputs to the device and its whole result back; the region is
     #     bracketed by device-wide synchronisation and timed on the host clock (three streams).
     from song_b200.engine import PinnedArray
-    DEPTH = 3                                                   # SONG_LOS_MAX_IN_FLIGHT
+    DEPTH = max(1, min(3, int(os.environ.get("SONG_BENCH_DEPTH", "3"))))     # batches in flight (SONG_LOS_MAX_IN_FLIGHT = 3)
     outs = [PinnedArray((wl.layout.tt2_size, wl.n_units)) for _ in range(DEPTH)]
     out_np = outs[0].array
     eng.transfer_pairs(wl_pin, mode=mode, out=out_np)          # warm
@@ -449,7 +449,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "checksum_abs_sum": checksum,
-                    "api": "song_los_submit/song_los_wait, up to 3 batches in flight (copy-in, kernels, copy-out), pinned host buffers; every step copies "
+                    "api": f"song_los_submit/song_los_wait, up to {DEPTH} batches in flight (copy-in, kernels, copy-out), pinned host buffers; every step copies "
                            "its inputs H2D and its result D2H; host clock between device-wide synchronisations",
                     "h2d_ms_per_step": copy_ms["h2d"] / args.steps, "d2h_ms_per_step": copy_ms["d2h"] / args.steps,
                     "h2d_gbs": h2d / 1e9 / max(copy_ms["h2d"] / args.steps * 1e-3, 1e-12),
