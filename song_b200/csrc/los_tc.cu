@@ -13,22 +13,25 @@
 // which is the 8x8x4 FP64 MMA (the only FP64 tensor instruction of sm_100a; tcgen05 has no f64 kind).
 //
 // Pipeline of one song_los_compute(FAST):
-//   spline_csd    k3 second derivatives of every (pair, tau, source type) column (transfer2.c:2639),
+//   spline        k3 second derivatives of every (pair, tau, source type) column (transfer2.c:2639): the grid-only part
+//                 of the elimination once per pair (spline_coef), then a division-free sweep per column (spline_csd_coef),
 //                 written transposed: CSD[pair][j][tau][tp] = {y, dd}
-//   sort          cub radix sort of (k3, unit)
+//   sort          cub radix sort of (k3, unit), on a second stream beside the splines
 //   prep_units    per unit: bracket j, spline weights (transfer2.c:2683-2691), sorted position; flat
 //                 extrapolation = weights of the first/last physical k3 (transfer2.c:2743-2757)
+//   then, per (column block, K chunk) -- ONE source slab, reused, so that a batch can hold many k3 values:
 //   interp_units  one CTA per (k1,k2) pair walks the pair's units in k3 order, so that the two CSD rows
 //                 of an interval are read once for all the units inside it, and writes the interpolated
-//                 sources in the order the tensor-core kernel consumes them:
-//                 S[group][sorted unit][tau][slot]   (group = K chunk of a column block, slot = term)
-//   los_tc        per CTA one tile of MT sorted units.  One producer warp: a single thread issues, per
+//                 sources of the chunk in the order the tensor-core kernel consumes them:
+//                 S[sorted unit][tau][slot]   (slot = term of the chunk)
+//   los_tc        persistent CTA per SM, tiles of MT sorted units.  Producer warp(s): a single thread issues, per
 //                 tau, ONE cp.async.bulk.tensor (TMA, 3-D box {slots, 1 tau, MT units}) for the sources
-//                 and one cp.async.bulk per needed table row into a shared-memory ring; its lanes
-//                 compute row index and quadrature x lerp weights of every unit.  Eight consumer warps
-//                 wait on the stage's mbarrier, read conflict-free 256-byte fragments and issue DMMAs
-//                 into register accumulators.  Columns whose J is still below the reference's cut at
-//                 this row (x << l) are skipped.
+//                 and one cp.async.bulk per needed table row into a shared-memory ring; the lanes
+//                 compute row index and quadrature x lerp weights of every unit.  8 or 12 consumer warps
+//                 wait on the stage's mbarrier, read 256-byte fragments and issue DMMAs into register
+//                 accumulators.  Columns whose J is still below the reference's cut at this row (x << l) are
+//                 skipped.  Later chunks of a block start from the partial sums the previous launch left in
+//                 the result array; the last one applies 1/(16 (2l+1)).
 #include <cub/cub.cuh>
 #include <cuda.h>
 #include <cudaTypedefs.h>
