@@ -4,8 +4,9 @@
  * This is the "thin C-ABI layer" between SONG's host C code and the CUDA kernels: plain C,
  * plain pointers and sizes, no CUDA or torch types.  The drop-in host module
  * (song_b200/host/transfer2_gpu.c) implements SONG's own module API -- transfer2_init() and
- * friends, reference include/transfer2.h:327-541 -- on top of these entry points; bessel2_gpu.c
- * does the same for the projection-function tables (reference include/bessel2.h:161-260).
+ * friends, reference include/transfer2.h:327-541 -- on top of these entry points;
+ * song_b200/host/bessel2_gpu.c does the same for SONG's bessel2 module (bessel2_init, bessel2_free,
+ * bessel2_convolution, ...; reference include/bessel2.h:161-260).
  *
  * What each entry point replaces in the reference (coccoinomane/song @ 2ea44ecf):
  *
@@ -35,6 +36,13 @@
  *   song_los_host_alloc/_free  page-locked staging memory for ppt2->sources / ptr2->transfer slabs
  *   song_los_max_batch_units   how many k3 values of consecutive k1 levels fit in one batch
  *   song_los_reserve           device buffers for the largest batch, allocated before the k1 loop starts
+ *   song_los_device_count      how many GPUs the (k1,k2) pairs can be spread over (the k1 modes are independent,
+ *                              transfer2.c:549-551)
+ *   song_los_set_time          the members of the run that only transfer2_init knows: pba->conformal_age
+ *                              (transfer2.c:128) and ptr2->tau_sampling (input2.c:1480-1500); lets bessel2_init
+ *                              create the engines and transfer2_init reuse them with their tables in place
+ *   song_los_drop_projection_rows   frees the device copy of pbs2->J_Llm_x once bessel2_init has read it back
+ *   song_los_select_slot       which of the three batch slots the synchronous calls use (several batches resident)
  *
  * Error convention (reference: _SUCCESS_/_FAILURE_ + ErrorMsg): every function
  * returns SONG_LOS_SUCCESS (0) or SONG_LOS_FAILURE (1); the text is available from
@@ -156,7 +164,16 @@ typedef struct song_los_timing {
 
 typedef struct song_los_ctx song_los_ctx;
 
+/* Number of CUDA devices visible to the process (0 and SONG_LOS_FAILURE when there is none). */
+int  song_los_device_count(int *n_devices);
+
 int  song_los_create(const song_los_config *cfg, song_los_ctx **ctx);
+/* Replaces cfg.tau0, cfg.tau_sampling_mode and cfg.tau_linstep_song of an existing context (the time tables are
+   rebuilt; projection tables, buffers and the tensor-core table stay). */
+int  song_los_set_time(song_los_ctx *ctx, double tau0, int tau_sampling_mode, double tau_linstep_song);
+/* 1 when `ctx` was created from a configuration equal to `cfg` in everything but the device and the three members
+   song_los_set_time replaces, 0 otherwise. */
+int  song_los_config_matches(const song_los_ctx *ctx, const song_los_config *cfg);
 int  song_los_destroy(song_los_ctx *ctx);
 const char *song_los_last_error(const song_los_ctx *ctx);   /* ctx may be NULL: last create error */
 
@@ -186,6 +203,13 @@ int  song_los_get_projection(song_los_ctx *ctx, int *index_xmin_J, int *x_size_J
 /* pbs2->ddJ_Llm_x of the device-built tables (cubic Bessel interpolation only; bessel2.c:395-435),
    rows sized and offset like J_rows. */
 int  song_los_get_projection_dd(song_los_ctx *ctx, double *const *ddJ_rows);
+
+/* Frees the undensified device rows behind song_los_get_projection / _dd (the dense tables the kernels read stay). */
+int  song_los_drop_projection_rows(song_los_ctx *ctx);
+
+/* The synchronous calls below work on one of SONG_LOS_MAX_IN_FLIGHT batch slots (default 0): a caller that keeps
+   several batches resident on the device uploads each into its own slot and selects it before compute / download. */
+int  song_los_select_slot(song_los_ctx *ctx, int slot);
 
 int  song_los_upload_pairs(song_los_ctx *ctx, const song_los_batch *batch);
 int  song_los_compute(song_los_ctx *ctx, int mode, song_los_timing *timing);

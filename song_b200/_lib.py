@@ -140,10 +140,12 @@ LOS_SYMBOLS = [
     "song_los_device_result", "song_los_copy_result", "song_los_set_stream", "song_los_measure_peaks",
     "song_los_device_info", "song_los_version",
     "song_los_submit", "song_los_wait", "song_los_host_alloc", "song_los_host_free", "song_los_max_batch_units", "song_los_reserve", "song_los_get_projection_dd",
+    "song_los_device_count", "song_los_set_time", "song_los_config_matches", "song_los_drop_projection_rows",
+    "song_los_select_slot",
 ]
 HOST_SYMBOLS = ["song_host_k3_size", "song_host_k3_list", "song_host_k3_sizes", "song_host_k3_lists",
                 "song_host_bessel2_prepare", "song_host_bessel2_free", "song_host_bessel2_upload",
-                "song_host_lpt_schedule"]
+                "song_host_lpt_schedule", "song_host_schedule_pairs"]
 
 _los = None
 _host = None
@@ -186,6 +188,11 @@ def los():
         lib.song_los_host_free.argtypes = [vp]
         lib.song_los_max_batch_units.argtypes = [vp, C.c_int, C.c_double, c_int64_p]
         lib.song_los_reserve.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64]
+        lib.song_los_device_count.argtypes = [c_int_p]
+        lib.song_los_set_time.argtypes = [vp, C.c_double, C.c_int, C.c_double]
+        lib.song_los_config_matches.argtypes = [vp, C.POINTER(LosConfig)]
+        lib.song_los_drop_projection_rows.argtypes = [vp]
+        lib.song_los_select_slot.argtypes = [vp, C.c_int]
         _los = lib
     return _los
 
@@ -211,6 +218,7 @@ def host():
         lib.song_host_bessel2_upload.argtypes = [C.c_void_p, C.POINTER(Bessel2Host), c_int_p, C.c_double, C.c_double,
                                                  C.c_char_p, C.c_int]
         lib.song_host_lpt_schedule.argtypes = [c_int64_p, C.c_int, C.c_int, c_int_p, c_int64_p]
+        lib.song_host_schedule_pairs.argtypes = [c_int64_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int64_p]
         lib.compat_drc3jj.argtypes = [C.c_double] * 4 + [c_double_p, c_double_p, c_double_p, C.c_int]
         lib.compat_bessel_j.argtypes = [C.c_int, C.c_double]
         lib.compat_bessel_j.restype = C.c_double

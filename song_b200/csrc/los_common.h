@@ -64,6 +64,7 @@ struct ExactParams {
 
 enum { ERR_X_OUT_OF_RANGE = 1, ERR_H_ZERO = 2, ERR_NAN = 4, ERR_TAU_GRID_OVERFLOW = 8 };
 
+constexpr int SPLINE_MAX_NP = 256;          // k3 grids up to this length: spline workspace in thread-local memory
 constexpr int EXACT_UNITS_PER_CTA = 8;     // one warp per k3 value
 constexpr int EXACT_THREADS = 256;
 constexpr int EXACT_MAX_TT_PASSES = 16;    // 16*32 = 512 transfer types per unit pass

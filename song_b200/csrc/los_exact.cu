@@ -13,10 +13,10 @@ namespace songlos {
 // Replaces the serial array_spline_table_columns call of transfer2.c:2639-2648
 // (_SPLINE_EST_DERIV_); one thread per column, columns of a pair share the abscissa k3_pt.
 // ---------------------------------------------------------------------------------------------
-constexpr int SPLINE_MAX_NP = 256;
+
 
 __global__ void __launch_bounds__(128) spline_k3_kernel(Batch b, int tau_size, int tp2_size,
-                                                         double *dd_out, int *err)
+                                                         double *dd_out, double *u_scratch, int *err)
 {
   int64_t cols_per_pair = (int64_t)tp2_size * tau_size;
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -27,8 +27,15 @@ __global__ void __launch_bounds__(128) spline_k3_kernel(Batch b, int tau_size, i
   const double *x = b.k3_pt + b.pt_off[p];
   const double *y = b.src + b.src_off[p] + col * n;
   double *dd = dd_out + b.src_off[p] + col * n;
-  double u[SPLINE_MAX_NP];
-  if (n > SPLINE_MAX_NP || n < 3) { atomicOr(err, ERR_H_ZERO); return; }
+  // right-hand sides of the elimination: thread-local for the usual grid lengths, in global scratch (laid out like dd)
+  // for longer k3 grids, so that any k3_size works as in the reference
+  double u_local[SPLINE_MAX_NP];
+  double *u = u_local;
+  if (n < 3) { atomicOr(err, ERR_H_ZERO); return; }
+  if (n > SPLINE_MAX_NP) {
+    if (u_scratch == nullptr) { atomicOr(err, ERR_H_ZERO); return; }
+    u = u_scratch + b.src_off[p] + col * n;
+  }
 
   double dy_first = ((x[2] - x[0]) * (x[2] - x[0]) * (y[1] - y[0])
                      - (x[1] - x[0]) * (x[1] - x[0]) * (y[2] - y[0]))
@@ -504,14 +511,14 @@ __global__ void __launch_bounds__(EXACT_THREADS) los_exact_resample_kernel(Exact
 }
 
 // launch wrappers (called from song_los_api.cu) ------------------------------------------------
-cudaError_t launch_spline_k3(const Batch &b, int tau_size, int tp2_size, double *dd, int *err,
+cudaError_t launch_spline_k3(const Batch &b, int tau_size, int tp2_size, double *dd, double *u_scratch, int *err,
                              cudaStream_t st)
 {
   int64_t cols = (int64_t)tp2_size * tau_size * b.n_pairs;
   if (cols == 0) return cudaSuccess;
   int threads = 128;
   int64_t blocks = (cols + threads - 1) / threads;
-  spline_k3_kernel<<<(unsigned)blocks, threads, 0, st>>>(b, tau_size, tp2_size, dd, err);
+  spline_k3_kernel<<<(unsigned)blocks, threads, 0, st>>>(b, tau_size, tp2_size, dd, u_scratch, err);
   return cudaGetLastError();
 }
 

@@ -88,6 +88,7 @@ struct TcParams {
   int tau_size;
   const double *tau0_minus_tau, *delta_tau, *xx;
   double inv_xx_step; int xx_size;
+  double xx_step_ref;                     // pbs2->xx_step itself: divisor of transfer2.c:2199 where x * inv_xx_step cannot decide
   double xx_step; int xx_uniform;         // xx[i] == i * xx_step BIT FOR BIT (xx_step = the grid's own delta): no table read for a_J
   int n_cols_total, cols_pad;             // columns of all blocks; padded to 32 (shared-memory copies)
   int n_stages, rmax;                     // ring depth, table rows per stage
@@ -157,6 +158,21 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// index_x of transfer2.c:2199, (int)(x / xx_step), without a division on the common path.  x * (1/xx_step) differs from
+// the correctly rounded quotient by a few ulp (< 1e-11 for x/xx_step < 1e5), which can change the integer part only
+// when the product lies that close to an integer; within 1e-9 of one the division itself decides, so the row index is
+// the reference's for every x (a unit sitting exactly on a grid point included).
+__device__ __noinline__ int tc_index_x_div(double x, double step) { return (int)(x / step); }   // rare: kept out of line
+
+__device__ __forceinline__ int tc_index_x(double x, double inv_step, double step)
+{
+  const double q = x * inv_step;
+  int ix = (int)q;
+  const double f = q - (double)ix;
+  if (f < 1e-9 || f > 1.0 - 1e-9) ix = tc_index_x_div(x, step);
+  return ix;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -230,13 +246,13 @@ __global__ void tc_nact_cummax_kernel(int *nact, int xx_size, int n_blocks)
 }
 
 // ---------------------------------------------------------------------------------------------
-// spline_csd: one thread per (pair, tau, tp) column; writes CSD[pair][j][tau][tp] = {y, dd}
-// (same algorithm as array_spline_table_columns, _SPLINE_EST_DERIV_; transfer2.c:2639)
+// transposed sources CSD[pair][j][tau][tp] = {y, dd}: dd = second derivative in k3 of every (pair, tau, tp) column
+// (array_spline_table_columns with _SPLINE_EST_DERIV_, transfer2.c:2639), one thread per column
 // ---------------------------------------------------------------------------------------------
-constexpr int TC_SPLINE_MAX_NP = 256;
+constexpr int TC_SPLINE_MAX_NP = 256;      // columns up to this length keep their elimination workspace in registers / local memory
 
-__global__ void __launch_bounds__(128) tc_spline_csd_kernel(Batch b, int tau_size, int tp2_size, int cubic,
-                                                            double2 *CSD, int *err)
+// linear k3 interpolation (quick_song_run): the transposed copy alone, dd = 0
+__global__ void __launch_bounds__(128) tc_transpose_csd_kernel(Batch b, int tau_size, int tp2_size, double2 *CSD)
 {
   int64_t rowlen = (int64_t)tp2_size * tau_size;
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,36 +261,9 @@ __global__ void __launch_bounds__(128) tc_spline_csd_kernel(Batch b, int tau_siz
   int64_t col = c - (int64_t)p * rowlen;           // col = tau*tp2 + tp   (tp fastest)
   int tau = (int)(col / tp2_size), tp = (int)(col % tp2_size);
   int n = b.np[p];
-  const double *x = b.k3_pt + b.pt_off[p];
   const double *y = b.src + b.src_off[p] + ((int64_t)tp * tau_size + tau) * n;
   double2 *cs = CSD + b.src_off[p] + col;
-  if (!cubic) {
-    for (int i = 0; i < n; ++i) cs[(int64_t)i * rowlen] = make_double2(y[i], 0.);
-    return;
-  }
-  if (n > TC_SPLINE_MAX_NP || n < 3) { atomicOr(err, ERR_H_ZERO); return; }
-  double u[TC_SPLINE_MAX_NP], dd[TC_SPLINE_MAX_NP];
-  double dy_first = ((x[2] - x[0]) * (x[2] - x[0]) * (y[1] - y[0]) - (x[1] - x[0]) * (x[1] - x[0]) * (y[2] - y[0]))
-                    / ((x[2] - x[0]) * (x[1] - x[0]) * (x[2] - x[1]));
-  dd[0] = -0.5;
-  u[0] = (3. / (x[1] - x[0])) * ((y[1] - y[0]) / (x[1] - x[0]) - dy_first);
-  for (int i = 1; i < n - 1; ++i) {
-    double sig = (x[i] - x[i - 1]) / (x[i + 1] - x[i - 1]);
-    double pp = sig * dd[i - 1] + 2.0;
-    dd[i] = (sig - 1.0) / pp;
-    double ui = (y[i + 1] - y[i]) / (x[i + 1] - x[i]) - (y[i] - y[i - 1]) / (x[i] - x[i - 1]);
-    u[i] = (6.0 * ui / (x[i + 1] - x[i - 1]) - sig * u[i - 1]) / pp;
-  }
-  double dy_last = ((x[n - 3] - x[n - 1]) * (x[n - 3] - x[n - 1]) * (y[n - 2] - y[n - 1])
-                    - (x[n - 2] - x[n - 1]) * (x[n - 2] - x[n - 1]) * (y[n - 3] - y[n - 1]))
-                   / ((x[n - 3] - x[n - 1]) * (x[n - 2] - x[n - 1]) * (x[n - 3] - x[n - 2]));
-  double un = (3. / (x[n - 1] - x[n - 2])) * (dy_last - (y[n - 1] - y[n - 2]) / (x[n - 1] - x[n - 2]));
-  double next = (un - 0.5 * u[n - 2]) / (0.5 * dd[n - 2] + 1.0);
-  cs[(int64_t)(n - 1) * rowlen] = make_double2(y[n - 1], next);
-  for (int i = n - 2; i >= 0; --i) {
-    next = dd[i] * next + u[i];
-    cs[(int64_t)i * rowlen] = make_double2(y[i], next);
-  }
+  for (int i = 0; i < n; ++i) cs[(int64_t)i * rowlen] = make_double2(y[i], 0.);
 }
 
 // The part of the tridiagonal elimination that depends on the k3 grid only is the same for the tp2 x tau_size columns
@@ -290,7 +279,7 @@ __global__ void tc_spline_coef_kernel(Batch b, TcSplineCoef *coef, TcSplineEnds 
   const int n = b.np[p];
   const double *x = b.k3_pt + b.pt_off[p];
   TcSplineCoef *c = coef + b.pt_off[p];
-  if (n > TC_SPLINE_MAX_NP || n < 3) { atomicOr(err, ERR_H_ZERO); return; }
+  if (n < 3) { atomicOr(err, ERR_H_ZERO); return; }
   double ddp = -0.5;
   c[0].ddc = ddp; c[0].sig = 0.; c[0].rpp = 0.; c[0].r6 = 0.;
   for (int i = 0; i + 1 < n; ++i) c[i].rh = 1.0 / (x[i + 1] - x[i]);
@@ -320,34 +309,41 @@ __global__ void __launch_bounds__(128) tc_spline_csd_coef_kernel(Batch b, int ta
   int64_t col = c - (int64_t)p * rowlen;           // col = tau*tp2 + tp   (tp fastest)
   int tau = (int)(col / tp2_size), tp = (int)(col % tp2_size);
   int n = b.np[p];
-  if (n > TC_SPLINE_MAX_NP || n < 3) return;       // flagged by the coefficient kernel
+  if (n < 3) return;                               // flagged by the coefficient kernel
   const double *y = b.src + b.src_off[p] + ((int64_t)tp * tau_size + tau) * n;
   const TcSplineCoef *k = coef + b.pt_off[p];
   const TcSplineEnds e = ends[p];
   double2 *cs = CSD + b.src_off[p] + col;
+  // right-hand sides of the elimination: in local memory for the usual column lengths; longer columns park them in the
+  // dd slot of the output, which the back substitution overwrites in the same order (any k3_size works, as in the reference)
+  const bool big = n > TC_SPLINE_MAX_NP;
   double u[TC_SPLINE_MAX_NP];
+#define TC_U_ST(I, V) do { if (big) cs[(int64_t)(I) * rowlen].y = (V); else u[(I)] = (V); } while (0)
+#define TC_U_LD(I) (big ? cs[(int64_t)(I) * rowlen].y : u[(I)])
   double ylo = y[0], ymid = y[1];
   const double dy_first = e.fa * (ymid - ylo) - e.fb * (y[2] - ylo);
   double up = (3. * k[0].rh) * ((ymid - ylo) * k[0].rh - dy_first);
-  u[0] = up;
+  TC_U_ST(0, up);
   double rh_prev = k[0].rh;
   for (int i = 1; i + 1 < n; ++i) {
     const TcSplineCoef ki = k[i];
     const double yhi = y[i + 1];
     const double ui = (yhi - ymid) * ki.rh - (ymid - ylo) * rh_prev;
     up = (ki.r6 * ui - ki.sig * up) * ki.rpp;
-    u[i] = up;
+    TC_U_ST(i, up);
     ylo = ymid; ymid = yhi; rh_prev = ki.rh;
   }
-  // here ylo = y[n-2], ymid = y[n-1]
+  // here ylo = y[n-2], ymid = y[n-1], up = u[n-2]
   const double dy_last = e.la * (ylo - ymid) - e.lb * (y[n - 3] - ymid);
   const double un = (3. * k[n - 2].rh) * (dy_last - (ymid - ylo) * k[n - 2].rh);
-  double next = (un - 0.5 * u[n - 2]) * e.rbot;
+  double next = (un - 0.5 * up) * e.rbot;
   cs[(int64_t)(n - 1) * rowlen] = make_double2(ymid, next);
   for (int i = n - 2; i >= 0; --i) {
-    next = k[i].ddc * next + u[i];
+    next = k[i].ddc * next + TC_U_LD(i);
     cs[(int64_t)i * rowlen] = make_double2(y[i], next);
   }
+#undef TC_U_ST
+#undef TC_U_LD
 }
 
 // unit -> pair map: one CTA per pair writes its run of the pair-major unit sequence
@@ -482,7 +478,7 @@ __global__ void __launch_bounds__(512) tc_interp_units_kernel(Batch b, TcInterp 
 // ---------------------------------------------------------------------------------------------
 // the DMMA kernel
 // ---------------------------------------------------------------------------------------------
-// shared memory:  [bars: full[8], empty[8]] [unit ids: MT ints] [k3: MT doubles] [tau tables] [stages...]
+// shared memory:  [bars: full[8], empty[8]] [tau tables] [producer row table] [epilogue column tables] [stages...]
 // stage:          header {meta int4 {row_lo, nrows, nact, row_hi}, ixs[MT], cc[MT] double2 {c0, c1}}
 //                 | S[MT][tpp] (TMA box) | B[rmax][b_row]     (each part padded to 128 bytes)
 struct TcStagePtrs {
@@ -675,14 +671,13 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int NS = P.n_stages;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);             // full[8], empty[8]
-  int *unit_id = reinterpret_cast<int *>(smem_raw + 128);               // [2][MT]: tiles alternate buffers
-  double *tau_d = reinterpret_cast<double *>(smem_raw + 128 + MT * 8); // tau0 - tau       [tau_pad]
+  double *tau_d = reinterpret_cast<double *>(smem_raw + 128);           // tau0 - tau       [tau_pad]
   const int tau_pad = (P.tau_size + 15) & ~15;
   double *tau_w = tau_d + tau_pad;                                      // trapezoid weight [tau_pad]
   int4 *prow = reinterpret_cast<int4 *>(tau_w + tau_pad);               // producer: {row_lo, nrows, nact, row_hi} per tau
   double *col_scale_s = reinterpret_cast<double *>(prow + tau_pad);     // epilogue: 1/(16(2l+1)) per column [cols_pad]
   int *col_tt_s = reinterpret_cast<int *>(col_scale_s + P.cols_pad);    //           transfer type per column [cols_pad]
-  unsigned char *stage0 = smem_raw + 128 + MT * 8 + (size_t)tau_pad * 32 + (size_t)P.cols_pad * 12;   // 128-byte aligned
+  unsigned char *stage0 = smem_raw + 128 + (size_t)tau_pad * 32 + (size_t)P.cols_pad * 12;   // 128-byte aligned
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_tiles = (P.n_units + MT - 1) / MT;
@@ -715,8 +710,7 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
     // (transfer2.c:2195-2202, xx[ix+1] recomputed as (ix+1) delta).  Stage sequence per tile: pass, K chunk, tau.
     const int pw = warp - TC_CONSUMERS / 32;
     bool first_round = true;                    // the first NS stages need no empty-slot wait
-    int tbuf = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tbuf ^= 1) {
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t s0 = tile * MT;
       const int64_t nleft = P.n_units - s0;
       const int nvalid = nleft < (int64_t)MT ? (int)nleft : MT;
@@ -726,7 +720,6 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
         const int n = pw * 32 + lane + 32 * NP * i;
         const int64_t sidx = s0 + (n < nvalid ? n : nvalid - 1);      // tail: replicate the last unit, never stored
         kk[i] = __ldg(P.k_sorted + sidx);
-        unit_id[tbuf * MT + n] = (n < nvalid) ? __ldg(P.perm + sidx) : -1;
       }
       double k_first = 0., k_last = 0.;
       if (pw == 0) { k_first = __ldg(P.k_sorted + s0); k_last = __ldg(P.k_sorted + s0 + nvalid - 1); }
@@ -737,7 +730,7 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
         const double d_ = tau_d[T]; \
         _Pragma("unroll") for (int i = 0; i < UPL; ++i) { \
           const double x_ = kk[i] * d_;                                 /* transfer2.c:2195 */ \
-          int ix_ = (int)(x_ * P.inv_xx_step);                          /* transfer2.c:2199 */ \
+          int ix_ = tc_index_x(x_, P.inv_xx_step, P.xx_step_ref);       /* transfer2.c:2199 */ \
           bad_n[i] = (ix_ < 0 || ix_ + 1 >= P.xx_size); \
           if (bad_n[i]) { atomicOr(P.err, ERR_X_OUT_OF_RANGE); ix_ = max(0, min(ix_, P.xx_size - 2)); } \
           x_n[i] = x_; ix_n[i] = ix_; \
@@ -753,7 +746,7 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
           __syncwarp();
           for (int t = lane; t < P.tau_size; t += 32) {
             const double d = tau_d[t];
-            int row_lo = (int)(k_first * d * P.inv_xx_step), row_hi = (int)(k_last * d * P.inv_xx_step);
+            int row_lo = tc_index_x(k_first * d, P.inv_xx_step, P.xx_step_ref), row_hi = tc_index_x(k_last * d, P.inv_xx_step, P.xx_step_ref);
             row_lo = max(0, min(row_lo, P.xx_size - 2)); row_hi = max(row_lo, min(row_hi, P.xx_size - 2));
             const int nact = max(0, min(__ldg(nact_b + row_hi) - ps.sb0, ps.nsb));
             prow[t] = make_int4(row_lo, min(row_hi - row_lo + 1, P.rmax), nact, row_hi);
@@ -813,8 +806,10 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
   const int g0 = warp_m * 2, g1 = g0 + 1;      // the two 8-unit groups of this warp
   const int um = lane >> 2;                    // unit inside a group held by this lane (A and C rows)
   const int ksel = lane & 1, tsel = (lane & 3) >> 1;   // weight {c0,c1} and term of the kc held by this lane
-  int tbuf = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tbuf ^= 1) {
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // original (pair-major) index of this lane's two units, read where it is needed (start of a continued chunk, epilogue):
+    // a tile lasts tens of thousands of cycles, two scattered loads per lane are free, and no shared buffer has to
+    // outlive the ring (a producer running ahead could otherwise overwrite it when a tile has fewer stages than the ring)
     for (int ip = P.pass_begin; ip < P.pass_end; ++ip) {
       const TcPass ps = P.pass[ip];
       const TcBlock B = P.blk[ps.blk];
@@ -823,10 +818,9 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
       for (int j = 0; j < NW; ++j) { acc0[j][0] = acc0[j][1] = 0.; acc1[j][0] = acc1[j][1] = 0.; }
       if (P.acc_in) {
         // later K chunk of the block: continue from the unscaled partial sums the previous launch left in `out`
-        // (the producer has filled unit_id[tbuf] before the first stage of the tile can complete: wait for it)
-        mbar_wait(smem_u32(&bars[s]), ph);
         const int cpair = 2 * (lane & 3);
-        const int u0 = unit_id[tbuf * MT + g0 * 8 + um], u1 = unit_id[tbuf * MT + g1 * 8 + um];
+        const int64_t su0 = tile * MT + g0 * 8 + um, su1 = su0 + 8;
+        const int u0 = (su0 < P.n_units) ? __ldg(P.perm + su0) : -1, u1 = (su1 < P.n_units) ? __ldg(P.perm + su1) : -1;
 #pragma unroll
         for (int j = 0; j < NW; ++j) {
           const int sb = warp_n + j * WN;
@@ -908,7 +902,8 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
       // ---- epilogue: the 1/2 of the trapezoid and the divisions by 4, (2l+1), 2 of
       //      transfer2.c:2092-2098 as one multiplication by 1 / (16 (2l+1)) ----
       const int cpair = 2 * (lane & 3);
-      const int u0 = unit_id[tbuf * MT + g0 * 8 + um], u1 = unit_id[tbuf * MT + g1 * 8 + um];
+      const int64_t su0 = tile * MT + g0 * 8 + um, su1 = su0 + 8;
+      const int u0 = (su0 < P.n_units) ? __ldg(P.perm + su0) : -1, u1 = (su1 < P.n_units) ? __ldg(P.perm + su1) : -1;
 #pragma unroll
       for (int j = 0; j < NW; ++j) {
         const int sb = warp_n + j * WN;
@@ -1242,7 +1237,7 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
   // ---- phase 0: transposed {y, dd} sources ----
   {
     int64_t cols = rowlen * b.n_pairs;
-    if (cols > 0 && P.cubic_k3 && !getenv("SONG_LOS_TC_OLD_SPLINE")) {
+    if (cols > 0 && P.cubic_k3) {
       FCK(fs->spl_coef.reserve((size_t)h.n_pt_total)); FCK(fs->spl_ends.reserve((size_t)b.n_pairs));
       tc_spline_coef_kernel<<<(unsigned)((b.n_pairs + 63) / 64), 64, 0, st>>>(b, fs->spl_coef.p, fs->spl_ends.p, P.err);
       FCK(cudaGetLastError());
@@ -1250,7 +1245,7 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
       FCK(cudaGetLastError());
       *n_launches += 2;
     } else if (cols > 0) {
-      tc_spline_csd_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(b, tau_size, tp2, P.cubic_k3, fs->CSD.p, P.err);
+      tc_transpose_csd_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(b, tau_size, tp2, fs->CSD.p);
       FCK(cudaGetLastError());
       ++*n_launches;
     }
@@ -1287,7 +1282,7 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
   TP.k_sorted = fs->keys_out.p; TP.perm = fs->perm.p; TP.n_units = U;
   TP.tau_size = tau_size;
   TP.tau0_minus_tau = P.tm.tau0_minus_tau; TP.delta_tau = P.tm.delta_tau; TP.xx = P.xx;
-  TP.inv_xx_step = 1.0 / P.xx_step; TP.xx_size = P.xx_size;
+  TP.inv_xx_step = 1.0 / P.xx_step; TP.xx_size = P.xx_size; TP.xx_step_ref = P.xx_step;
   TP.xx_step = h.xx_delta; TP.xx_uniform = h.xx_uniform;
   if (getenv("SONG_LOS_TC_XX_TABLE")) TP.xx_uniform = 0;
   TP.out = b.out; TP.out_stride = U; TP.err = P.err;
@@ -1300,7 +1295,7 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
   int rmax = (MT >= 128) ? 4 : (MT >= 64 ? 3 : 2);
   if (const char *v = getenv("SONG_LOS_TC_RMAX")) rmax = std::max(1, std::min(8, atoi(v)));
   TP.n_cols_total = fs->n_cols_total; TP.cols_pad = (fs->n_cols_total + 31) & ~31;
-  const size_t fixed = 128 + (size_t)MT * 8 + (size_t)((tau_size + 15) & ~15) * 32 + (size_t)TP.cols_pad * 12;
+  const size_t fixed = 128 + (size_t)((tau_size + 15) & ~15) * 32 + (size_t)TP.cols_pad * 12;
   const size_t budget = 224 * 1024;
   auto stage_bytes = [&](int r) { return (size_t)TP.hdr_bytes + TP.a_bytes + (size_t)r * TP.b_row_bytes; };
   while (rmax > 1 && (budget - fixed) / stage_bytes(rmax) < 3) --rmax;

@@ -17,7 +17,7 @@
 
 namespace songlos {
 // los_exact.cu
-cudaError_t launch_spline_k3(const Batch &b, int tau_size, int tp2_size, double *dd, int *err, cudaStream_t st);
+cudaError_t launch_spline_k3(const Batch &b, int tau_size, int tp2_size, double *dd, double *u_scratch, int *err, cudaStream_t st);
 cudaError_t launch_los_exact(const ExactParams &P, int n_tiles, cudaStream_t st);
 cudaError_t launch_los_exact_resample(const ExactParams &P, int n_tiles, int n_ctas, cudaStream_t st);
 int64_t exact_resample_scratch_doubles(int tau_size, int tp2_size, int tau_grid_max);
@@ -50,7 +50,33 @@ static cudaError_t upload(DevBuf<T> &d, const T *h, size_t n, cudaStream_t st)
   return cudaMemcpyAsync(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice, st);
 }
 
-extern "C" int song_los_version(void) { return 100; }
+extern "C" int song_los_version(void) { return 200; }
+
+extern "C" int song_los_device_count(int *n)
+{
+  if (!n) return SONG_LOS_FAILURE;
+  *n = 0;
+  cudaError_t e = cudaGetDeviceCount(n);
+  if (e != cudaSuccess) { *n = 0; return ctx_fail(nullptr, "song_los_device_count: %s; there is no CPU fallback", cudaGetErrorString(e)); }
+  return SONG_LOS_SUCCESS;
+}
+
+// tau grid, tau0 - tau and the trapezoid measure of the sources time sampling (transfer2.c:2567-2580) on the device
+static cudaError_t upload_time_tables(song_los_ctx *ctx)
+{
+  const song_los_config &c = ctx->cfg;
+  std::vector<double> d(c.tau_size), w(c.tau_size);
+  for (int i = 0; i < c.tau_size; ++i) d[i] = c.tau0 - ctx->tau[i];
+  w[0] = ctx->tau[1] - ctx->tau[0];
+  for (int i = 1; i < c.tau_size - 1; ++i) w[i] = ctx->tau[i + 1] - ctx->tau[i - 1];
+  w[c.tau_size - 1] = ctx->tau[c.tau_size - 1] - ctx->tau[c.tau_size - 2];
+  cudaStream_t st = ctx->stream;
+  cudaError_t e = upload(ctx->d_tau, ctx->tau.data(), ctx->tau.size(), st);
+  if (e == cudaSuccess) e = upload(ctx->d_tau0_minus_tau, d.data(), d.size(), st);
+  if (e == cudaSuccess) e = upload(ctx->d_delta_tau, w.data(), w.size(), st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // d and w live on this stack frame
+  return e;
+}
 
 extern "C" const char *song_los_last_error(const song_los_ctx *ctx)
 {
@@ -152,17 +178,8 @@ extern "C" int song_los_create(const song_los_config *cfg, song_los_ctx **out)
     }
   }
 
-  // integration measure for the sources time sampling, transfer2.c:2567-2580
-  std::vector<double> d(cfg->tau_size), w(cfg->tau_size);
-  for (int i = 0; i < cfg->tau_size; ++i) d[i] = cfg->tau0 - ctx->tau[i];
-  w[0] = ctx->tau[1] - ctx->tau[0];
-  for (int i = 1; i < cfg->tau_size - 1; ++i) w[i] = ctx->tau[i + 1] - ctx->tau[i - 1];
-  w[cfg->tau_size - 1] = ctx->tau[cfg->tau_size - 1] - ctx->tau[cfg->tau_size - 2];
-
   cudaStream_t st = ctx->stream;
-  bool ok = upload(ctx->d_tau, ctx->tau.data(), ctx->tau.size(), st) == cudaSuccess
-         && upload(ctx->d_tau0_minus_tau, d.data(), d.size(), st) == cudaSuccess
-         && upload(ctx->d_delta_tau, w.data(), w.size(), st) == cudaSuccess
+  bool ok = upload_time_tables(ctx) == cudaSuccess
          && upload(ctx->d_xx, ctx->xx.data(), ctx->xx.size(), st) == cudaSuccess
          && upload(ctx->d_tt_type, ctx->tt_type.data(), (size_t)ntt, st) == cudaSuccess
          && upload(ctx->d_tt_lm, ctx->tt_lm.data(), (size_t)ntt, st) == cudaSuccess
@@ -199,7 +216,7 @@ extern "C" int song_los_destroy(song_los_ctx *ctx)
   }
   if (ctx->st_h2d) cudaStreamDestroy(ctx->st_h2d);
   if (ctx->st_d2h) cudaStreamDestroy(ctx->st_d2h);
-  ctx->d_dd.release(); ctx->d_err.release(); ctx->d_scratch.release();
+  ctx->d_dd.release(); ctx->d_spline_u.release(); ctx->d_err.release(); ctx->d_scratch.release();
   if (ctx->fast) fast_state_destroy(ctx->fast);
   if (ctx->d_proj_rows) cudaFree(ctx->d_proj_rows);
   if (ctx->d_proj_ddrows) cudaFree(ctx->d_proj_ddrows);
@@ -213,6 +230,51 @@ extern "C" int song_los_set_stream(song_los_ctx *ctx, void *cuda_stream)
 {
   if (!ctx) return SONG_LOS_FAILURE;
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return SONG_LOS_SUCCESS;
+}
+
+extern "C" int song_los_set_time(song_los_ctx *ctx, double tau0, int tau_sampling_mode, double tau_linstep_song)
+{
+  if (!ctx) return SONG_LOS_FAILURE;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->n_in_flight) return ctx_fail(ctx, "song_los_set_time: submitted batches are still in flight");
+  if (tau_sampling_mode != SONG_LOS_TAU_SOURCES && tau_sampling_mode != SONG_LOS_TAU_CUSTOM && tau_sampling_mode != SONG_LOS_TAU_BESSEL)
+    return ctx_fail(ctx, "song_los_set_time: unknown time sampling %d", tau_sampling_mode);
+  ctx->cfg.tau0 = tau0; ctx->cfg.tau_sampling_mode = tau_sampling_mode; ctx->cfg.tau_linstep_song = tau_linstep_song;
+  CK(upload_time_tables(ctx));
+  return SONG_LOS_SUCCESS;
+}
+
+// Does the context describe the run `cfg` would create (everything except the device and the members song_los_set_time
+// replaces)?  transfer2_init asks this before reusing an engine bessel2_init left on the device.
+extern "C" int song_los_config_matches(const song_los_ctx *ctx, const song_los_config *b)
+{
+  if (!ctx || !b) return 0;
+  const song_los_config &a = ctx->cfg;
+  bool same = a.tau_size == b->tau_size && a.sources_k3_interpolation == b->sources_k3_interpolation
+           && a.sources_time_interpolation == b->sources_time_interpolation && a.bessels_interpolation == b->bessels_interpolation
+           && a.k3_extrapolation == b->k3_extrapolation && a.xx_size == b->xx_size && a.xx_step == b->xx_step
+           && a.l_size == b->l_size && a.m_size == b->m_size && a.L_size == b->L_size && a.n_transfers == b->n_transfers
+           && a.has_source_T == b->has_source_T && a.has_source_E == b->has_source_E && a.has_source_B == b->has_source_B
+           && a.tp2_size == b->tp2_size && a.l_max_los_t == b->l_max_los_t && a.l_max_los_p == b->l_max_los_p
+           && a.tt2_size == b->tt2_size && a.J_size == b->J_size && a.index_J_TT == b->index_J_TT
+           && a.index_J_EE == b->index_J_EE && a.index_J_EB == b->index_J_EB;
+  if (same && a.has_source_T) same = a.index_tp2_T == b->index_tp2_T && a.index_tt2_T == b->index_tt2_T;
+  if (same && a.has_source_E) same = a.index_tp2_E == b->index_tp2_E && a.index_tt2_E == b->index_tt2_E;
+  if (same && a.has_source_B) same = a.index_tp2_B == b->index_tp2_B && a.index_tt2_B == b->index_tt2_B;
+  if (!same) return 0;
+  auto eq = [](const auto &v, const auto *p) { for (size_t i = 0; i < v.size(); ++i) if (v[i] != p[i]) return false; return true; };
+  return eq(ctx->tau, b->tau_sampling) && eq(ctx->xx, b->xx) && eq(ctx->l, b->l) && eq(ctx->m, b->m)
+      && eq(ctx->lm_array, b->lm_array) && eq(ctx->lm_src, b->lm_src) && eq(ctx->tt_index_l, b->tt_index_l)
+      && eq(ctx->tt_index_m, b->tt_index_m) ? 1 : 0;
+}
+
+extern "C" int song_los_select_slot(song_los_ctx *ctx, int slot)
+{
+  if (!ctx) return SONG_LOS_FAILURE;
+  if (slot < 0 || slot >= song_los_ctx::N_SLOTS) return ctx_fail(ctx, "song_los_select_slot: slot %d outside [0,%d)", slot, (int)song_los_ctx::N_SLOTS);
+  if (ctx->n_in_flight) return ctx_fail(ctx, "song_los_select_slot: submitted batches are still in flight");
+  ctx->cur = slot;
   return SONG_LOS_SUCCESS;
 }
 
@@ -506,7 +568,7 @@ static int report_device_errors(song_los_ctx *ctx, int h)
 {
   if (h & ERR_X_OUT_OF_RANGE)
     return ctx_fail(ctx, "not enough J's: k*(tau0-tau) exceeds xx_max (transfer2.c:2172); increase l_max or decrease k_max");
-  if (h & ERR_H_ZERO) return ctx_fail(ctx, "stop to avoid division by zero in the k3 interpolation (or k3_size outside [3,256])");
+  if (h & ERR_H_ZERO) return ctx_fail(ctx, "stop to avoid division by zero in the k3 interpolation (two equal k3 values, or fewer than 3 of them)");
   if (h & ERR_TAU_GRID_OVERFLOW) return ctx_fail(ctx, "time integration grid larger than the allocated maximum");
   if (h & ERR_NAN) return ctx_fail(ctx, "found nan in second-order transfer function");
   return SONG_LOS_SUCCESS;
@@ -545,7 +607,9 @@ static int enqueue_compute(song_los_ctx *ctx, song_los_ctx::Slot &S, int mode)
       S.tiles_ready = true; t.n_launches++;
     }
     if (P.cubic_k3) {
-      CK(launch_spline_k3(P.b, c.tau_size, c.tp2_size, ctx->d_dd.p, ctx->d_err.p, st));
+      double *u_scratch = nullptr;                 // only k3 grids longer than SPLINE_MAX_NP need it
+      if (S.max_np > SPLINE_MAX_NP) { CK(ctx->d_spline_u.reserve((size_t)S.hb.n_src_total)); u_scratch = ctx->d_spline_u.p; }
+      CK(launch_spline_k3(P.b, c.tau_size, c.tp2_size, ctx->d_dd.p, u_scratch, ctx->d_err.p, st));
       t.n_launches++;
     }
     CK(cudaEventRecord(S.ev_t[1], st));

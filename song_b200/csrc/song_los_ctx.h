@@ -73,6 +73,7 @@ struct song_los_ctx {
   cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
   std::vector<unsigned char> h_block_nonzero;
   DevBuf<double> d_dd;
+  DevBuf<double> d_spline_u;      // EXACT spline workspace for k3 grids longer than SPLINE_MAX_NP
   DevBuf<int> d_err;
   DevBuf<double> d_scratch;
 

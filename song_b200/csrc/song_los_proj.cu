@@ -308,6 +308,17 @@ extern "C" int song_los_build_projection(song_los_ctx *ctx, int l1_size, const i
 
 static int get_rows(song_los_ctx *ctx, const double *d_rows, double *const *out_rows);
 
+// The undensified rows are kept for song_los_get_projection only; a host module that has read them back (bessel2_init)
+// returns their memory (n_jidx x xx_size doubles, GBs at l_max >= 3000) to the batches.
+extern "C" int song_los_drop_projection_rows(song_los_ctx *ctx)
+{
+  if (!ctx) return SONG_LOS_FAILURE;
+  PCK(cudaSetDevice(ctx->device));
+  if (ctx->d_proj_rows) { PCK(cudaFree(ctx->d_proj_rows)); ctx->d_proj_rows = nullptr; }
+  if (ctx->d_proj_ddrows) { PCK(cudaFree(ctx->d_proj_ddrows)); ctx->d_proj_ddrows = nullptr; }
+  return SONG_LOS_SUCCESS;
+}
+
 extern "C" int song_los_get_projection_dd(song_los_ctx *ctx, double *const *ddJ_rows)
 {
   if (!ctx || !ddJ_rows) return ctx_fail(ctx, "song_los_get_projection_dd: NULL argument");

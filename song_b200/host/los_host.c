@@ -206,3 +206,34 @@ int song_host_lpt_schedule(const int64_t *cost, int n, int n_dev, int *device, i
   free(l); free(order);
   return 0;
 }
+
+/* Static schedule at (k1,k2)-pair granularity.  The pair sequence (reference loop order, k1 major) is cut into
+   n_dev * chunks_per_dev contiguous chunks of about equal cost and the chunks are assigned by LPT: one chunk per
+   device gives every GPU a band of consecutive k1 levels (sources are loaded and freed level by level, transfer2.c:332-344,
+   553); several chunks per device give every GPU the same mix of cheap low-k and expensive high-k pairs, so that the
+   balance does not hinge on the cost model, while the results stay contiguous runs of the transfers_%03d.dat order. */
+int song_host_schedule_pairs(const int64_t *cost, int n_pairs, int n_dev, int chunks_per_dev, int *device_of_pair, int64_t *load)
+{
+  if (!cost || !device_of_pair || n_pairs < 0 || n_dev < 1) return 1;
+  if (chunks_per_dev < 1) chunks_per_dev = 1;
+  int n_chunks = n_dev * chunks_per_dev;
+  if (n_chunks > n_pairs) n_chunks = n_pairs > 0 ? n_pairs : 1;
+  long double total = 0;
+  for (int p = 0; p < n_pairs; ++p) total += (long double)cost[p];
+  int64_t *ccost = (int64_t *)calloc((size_t)n_chunks, sizeof(int64_t));
+  int *cdev = (int *)calloc((size_t)n_chunks, sizeof(int));
+  int *chunk_of = (int *)malloc(sizeof(int) * (size_t)(n_pairs > 0 ? n_pairs : 1));
+  if (!ccost || !cdev || !chunk_of) { free(ccost); free(cdev); free(chunk_of); return 1; }
+  /* cut where the running cost crosses the next multiple of total/n_chunks (prefix rule: no drift) */
+  long double acc = 0;
+  int c = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    /* the pairs left must still fill the chunks left */
+    while (c + 1 < n_chunks && ccost[c] > 0 && (acc >= total * (c + 1) / n_chunks || n_pairs - p <= n_chunks - 1 - c)) ++c;
+    chunk_of[p] = c; ccost[c] += cost[p]; acc += (long double)cost[p];
+  }
+  int rc = song_host_lpt_schedule(ccost, n_chunks, n_dev, cdev, load);
+  if (!rc) for (int p = 0; p < n_pairs; ++p) device_of_pair[p] = cdev[chunk_of[p]];
+  free(ccost); free(cdev); free(chunk_of);
+  return rc;
+}

@@ -55,6 +55,12 @@ int song_host_k3_lists(const song_k3_params *p, int n_pairs, const int *k3_pt_si
    bad arguments. */
 int song_host_lpt_schedule(const int64_t *cost, int n, int n_dev, int *device, int64_t *load);
 
+/* The static multi-GPU schedule of the (k1,k2) pairs (north_star: "partitioned across the GPUs by (k1,k2) pair with a
+   load-balanced static schedule"): the pair sequence in reference order is cut into n_dev * chunks_per_dev contiguous
+   chunks of about equal cost, LPT assigns the chunks.  Writes device_of_pair[p] and, when load != NULL, the per-device
+   cost.  Used by transfer2_init (transfer2_gpu.c) and by the multi-rank driver (song_b200/shard.py). */
+int song_host_schedule_pairs(const int64_t *cost, int n_pairs, int n_dev, int chunks_per_dev, int *device_of_pair, int64_t *load);
+
 #ifdef __cplusplus
 }
 #endif
