@@ -139,6 +139,11 @@ int oracle_bessel2_J_for_Llm(int projection_function, int L, int l, int m, int L
                              double J_Llm_cut,
                              double **row, int *index_xmin, int *x_size, double *x_min);
 
+/* bessel2.c:499-605 (bessel2_convolution): trapezoidal k integral against j_l1(k r) of one l1 */
+int oracle_bessel2_convolution(const double *kk, const double *delta_kk, int k_size, const double *f, const double *g,
+                               const double *j, const double *ddj, double x_min_l1, double xx_step, int cubic, double r,
+                               double *integral);
+
 /* ---------------------------------------------------------------------------------------
  * transfer2.c restatement
  * ------------------------------------------------------------------------------------- */

@@ -257,3 +257,37 @@ fail:
   free(first_3j); free(second_3j);
   return ORACLE_FAIL;
 }
+
+/* bessel2.c:499-605: 1/2 sum_k delta_k k^2 f g j_l1(k r), linear (:575-579) or cubic (:581-588) interpolation in the
+   j_l1 table of one l1 (row j, second derivatives ddj, first abscissa x_min_l1, step xx_step).  g may be NULL (:547-556).
+   Statement order of the reference: zero f or g and x below the table skip the term (:541-563). */
+int oracle_bessel2_convolution(const double *kk, const double *delta_kk, int k_size, const double *f, const double *g,
+                               const double *j, const double *ddj, double x_min_l1, double xx_step, int cubic, double r,
+                               double *integral)
+{
+  *integral = 0;
+  for (int index_k = 0; index_k < k_size; ++index_k) {
+    double f_in_k = f[index_k];
+    if (f_in_k == 0.) continue;
+    double g_in_k = 1.;
+    if (g != NULL) {
+      g_in_k = g[index_k];
+      if (g_in_k == 0.) continue;
+    }
+    double k = kk[index_k];
+    double jv;
+    double x = k * r;
+    if (x < x_min_l1) continue;
+    int index_x = (int)((x - x_min_l1) / xx_step);
+    double a = (x_min_l1 + xx_step * (index_x + 1) - x) / xx_step;
+    if (!cubic)
+      jv = a * j[index_x] + (1. - a) * j[index_x + 1];
+    else
+      jv = a * j[index_x] + (1. - a) * (j[index_x + 1] - a * ((a + 1.) * ddj[index_x] + (2. - a) * ddj[index_x + 1])
+                                                            * xx_step * xx_step / 6.0);
+    double integrand = k * k * jv * f_in_k * g_in_k;
+    *integral += integrand * delta_kk[index_k];
+  }
+  (*integral) *= 0.5;
+  return 0;
+}

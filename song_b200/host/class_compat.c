@@ -157,3 +157,37 @@ int compat_drc3jj(double l2, double l3, double m2, double m3, double *l1min_out,
   free(f); free(g);
   return 0;
 }
+
+/* Tridiagonal system of the interpolating cubic spline (continuity of the first derivative at the inner knots), solved by
+   forward elimination / back substitution; the workspace holds the eliminated right-hand sides. */
+int compat_spline_second_derivatives(const double *x, int n, const double *y, double *ddy, int est_deriv)
+{
+  if (n < 3) return 1;
+  double *rhs = (double *)malloc((size_t)n * sizeof(double));
+  if (!rhs) return 1;
+  if (est_deriv) {
+    const double d1 = x[1] - x[0], d2 = x[2] - x[0];
+    if (d1 == 0. || d2 == 0. || d1 == d2) { free(rhs); return 1; }
+    const double slope0 = (d2 * d2 * (y[1] - y[0]) - d1 * d1 * (y[2] - y[0])) / (d2 * d1 * (d2 - d1));
+    ddy[0] = -0.5;
+    rhs[0] = (3. / d1) * ((y[1] - y[0]) / d1 - slope0);
+  } else { ddy[0] = 0.; rhs[0] = 0.; }
+  for (int i = 1; i < n - 1; ++i) {
+    const double hl = x[i] - x[i - 1], hr = x[i + 1] - x[i], span = x[i + 1] - x[i - 1];
+    if (hl == 0. || hr == 0.) { free(rhs); return 1; }
+    const double w = hl / span, piv = w * ddy[i - 1] + 2.0;
+    ddy[i] = (w - 1.0) / piv;
+    rhs[i] = (6.0 * ((y[i + 1] - y[i]) / hr - (y[i] - y[i - 1]) / hl) / span - w * rhs[i - 1]) / piv;
+  }
+  double qn = 0., un = 0.;
+  if (est_deriv) {
+    const double e1 = x[n - 2] - x[n - 1], e2 = x[n - 3] - x[n - 1];
+    const double slopeN = (e2 * e2 * (y[n - 2] - y[n - 1]) - e1 * e1 * (y[n - 3] - y[n - 1])) / (e2 * e1 * (e2 - e1));
+    qn = 0.5;
+    un = (3. / (x[n - 1] - x[n - 2])) * (slopeN - (y[n - 1] - y[n - 2]) / (x[n - 1] - x[n - 2]));
+  }
+  ddy[n - 1] = (un - qn * rhs[n - 2]) / (qn * ddy[n - 2] + 1.0);
+  for (int i = n - 2; i >= 0; --i) ddy[i] = ddy[i] * ddy[i + 1] + rhs[i];
+  free(rhs);
+  return 0;
+}

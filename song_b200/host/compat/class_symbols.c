@@ -9,6 +9,7 @@
 #include "song_tools.h"
 #include "slatec_3j_C.h"
 #include "bessel.h"
+#include "arrays.h"
 #include "../class_compat.h"
 
 int size_l_indexm(int l_max, int *m_vec, int m_size)
@@ -76,5 +77,16 @@ int bessel_j(struct bessels *pbs, int l, double x, double *j)
 {
   (void)pbs;
   *j = compat_bessel_j(l, x);
+  return _SUCCESS_;
+}
+int array_spline_table_one_column(double *x, int x_size, double *y_array, int y_size, int index_y, double *ddy_array,
+                                  short spline_mode, ErrorMsg errmsg)
+{
+  (void)y_size;
+  if (compat_spline_second_derivatives(x, x_size, y_array + (size_t)index_y * x_size, ddy_array + (size_t)index_y * x_size,
+                                       spline_mode == _SPLINE_EST_DERIV_)) {
+    snprintf(errmsg, _ERRORMSGSIZE_, "array_spline_table_one_column: x_size=%d too small or repeated abscissa", x_size);
+    return _FAILURE_;
+  }
   return _SUCCESS_;
 }

@@ -126,3 +126,131 @@ size_t los_pinned_pooled_bytes(void)
   POOL_UNLOCK();
   return n;
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/*  backing store of ptr2->transfer                                                                  */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct { double *base; size_t doubles; int refs; int pinned; } los_slab;
+typedef struct { int n, cap; int *ids; } los_level;
+
+struct los_transfer_store {
+  const void *owner;
+  int k_size, tt2_size;
+  long n_pairs;
+  double **ptr_block;            /* [tt2_size][n_pairs] */
+  los_slab *slabs; int n_slabs, cap_slabs;
+  los_level *levels;             /* [k_size] */
+  pthread_mutex_t lock;
+};
+
+enum { LOS_MAX_STORES = 8 };
+static los_transfer_store *g_stores[LOS_MAX_STORES];
+
+los_transfer_store *los_store_find(const void *owner)
+{
+  if (!owner) return NULL;
+  for (int i = 0; i < LOS_MAX_STORES; ++i) if (g_stores[i] && g_stores[i]->owner == owner) return g_stores[i];
+  return NULL;
+}
+
+los_transfer_store *los_store_create(const void *owner, int k_size, int tt2_size)
+{
+  if (!owner || k_size < 1 || tt2_size < 1 || los_store_find(owner)) return NULL;
+  int at = -1;
+  for (int i = 0; i < LOS_MAX_STORES; ++i) if (!g_stores[i]) { at = i; break; }
+  if (at < 0) return NULL;
+  los_transfer_store *s = (los_transfer_store *)calloc(1, sizeof *s);
+  if (!s) return NULL;
+  s->owner = owner; s->k_size = k_size; s->tt2_size = tt2_size;
+  s->n_pairs = (long)k_size * (k_size + 1) / 2;
+  s->ptr_block = (double **)calloc((size_t)tt2_size * (size_t)s->n_pairs, sizeof(double *));   /* untouched pages cost nothing */
+  s->levels = (los_level *)calloc((size_t)k_size, sizeof(los_level));
+  if (!s->ptr_block || !s->levels) { free(s->ptr_block); free(s->levels); free(s); return NULL; }
+  pthread_mutex_init(&s->lock, NULL);
+  g_stores[at] = s;
+  return s;
+}
+
+double **los_store_row(los_transfer_store *s, int tt, int k1)
+{
+  return s->ptr_block + (size_t)tt * (size_t)s->n_pairs + (size_t)k1 * (k1 + 1) / 2;
+}
+
+int los_store_new_slab(los_transfer_store *s, size_t doubles, int pinned, double **base)
+{
+  double *p = NULL;
+  int is_pinned = 0;
+  const size_t bytes = (doubles > 0 ? doubles : 1) * sizeof(double);
+  if (pinned) { p = (double *)los_pinned_get(bytes); is_pinned = (p != NULL); }
+  if (!p) p = (double *)malloc(bytes);
+  if (!p) return -1;
+  pthread_mutex_lock(&s->lock);
+  int id = -1;
+  for (int i = 0; i < s->n_slabs; ++i) if (!s->slabs[i].base) { id = i; break; }     /* reuse a vacated entry */
+  if (id < 0) {
+    if (s->n_slabs == s->cap_slabs) {
+      int cap = s->cap_slabs ? 2 * s->cap_slabs : 32;
+      los_slab *ns = (los_slab *)realloc(s->slabs, sizeof(los_slab) * (size_t)cap);
+      if (ns) { s->slabs = ns; s->cap_slabs = cap; }
+    }
+    if (s->n_slabs < s->cap_slabs) id = s->n_slabs++;
+  }
+  if (id >= 0) { s->slabs[id].base = p; s->slabs[id].doubles = doubles; s->slabs[id].refs = 0; s->slabs[id].pinned = is_pinned; }
+  pthread_mutex_unlock(&s->lock);
+  if (id < 0) { if (is_pinned) los_pinned_put(p); else free(p); return -1; }
+  *base = p;
+  return id;
+}
+
+void los_store_link(los_transfer_store *s, int k1, int slab)
+{
+  pthread_mutex_lock(&s->lock);
+  los_level *L = &s->levels[k1];
+  int known = 0;
+  for (int i = 0; i < L->n; ++i) if (L->ids[i] == slab) known = 1;
+  if (!known) {
+    if (L->n == L->cap) {
+      int cap = L->cap ? 2 * L->cap : 4;
+      int *ni = (int *)realloc(L->ids, sizeof(int) * (size_t)cap);
+      if (ni) { L->ids = ni; L->cap = cap; }
+    }
+    if (L->n < L->cap) { L->ids[L->n++] = slab; s->slabs[slab].refs++; }
+  }
+  pthread_mutex_unlock(&s->lock);
+}
+
+static void slab_unref(los_transfer_store *s, int id)
+{
+  los_slab *b = &s->slabs[id];
+  if (--b->refs > 0) return;
+  if (b->pinned) los_pinned_put(b->base); else free(b->base);
+  b->base = NULL; b->doubles = 0; b->refs = 0;
+}
+
+void los_store_release_level(los_transfer_store *s, int k1)
+{
+  pthread_mutex_lock(&s->lock);
+  los_level *L = &s->levels[k1];
+  for (int i = 0; i < L->n; ++i) slab_unref(s, L->ids[i]);
+  L->n = 0;
+  pthread_mutex_unlock(&s->lock);
+}
+
+size_t los_store_live_bytes(const los_transfer_store *s)
+{
+  size_t n = 0;
+  for (int i = 0; i < s->n_slabs; ++i) if (s->slabs[i].base) n += s->slabs[i].doubles * sizeof(double);
+  return n;
+}
+
+void los_store_drop(const void *owner)
+{
+  los_transfer_store *s = los_store_find(owner);
+  if (!s) return;
+  for (int k1 = 0; k1 < s->k_size; ++k1) { los_store_release_level(s, k1); free(s->levels[k1].ids); }
+  for (int i = 0; i < s->n_slabs; ++i)          /* slabs never linked to a level */
+    if (s->slabs[i].base) { if (s->slabs[i].pinned) los_pinned_put(s->slabs[i].base); else free(s->slabs[i].base); }
+  for (int i = 0; i < LOS_MAX_STORES; ++i) if (g_stores[i] == s) g_stores[i] = NULL;
+  pthread_mutex_destroy(&s->lock);
+  free(s->slabs); free(s->levels); free(s->ptr_block); free(s);
+}

@@ -12,22 +12,26 @@
  * re-derive them), memory management of ptr2->transfer (transfer2.c:636-691, 2976-3104) and the disk format
  * (transfer2.c:705-763, 2929-2963: raw doubles, [k1][k2][k3] per transfer type).
  *
- * Batching: the reference handles one (k1,k2) pair at a time; here consecutive k1 levels are packed into one GPU
- * batch (SONG_LOS_BATCH_UNITS k3 values; default: an even share of the run per GPU, at most what
- * song_los_max_batch_units says fits in device memory) because the tensor-core kernel wants many k3 values
- * per table row.  Batches of a GPU run as a three-deep pipeline (song_los_submit / song_los_wait) through page-locked
- * staging, so that the copies of neighbouring batches overlap the kernels.  Side effects keep the reference's per-k1 order: sources of a k1 level are loaded before and freed
- * after use (transfer2.c:332-344, 553), transfers are stored and freed per k1 (transfer2.c:559-567).
- * With several visible GPUs and nothing to write to disk, batches are distributed over one host thread per GPU
- * (static longest-processing-time schedule on the number of k3 values); the results land directly in
- * ptr2->transfer, which is the "gather to the host".
+ * Batching: the reference handles one (k1,k2) pair at a time; here runs of consecutive pairs are packed into GPU
+ * batches, because the tensor-core kernel wants many k3 values per table row.  The pairs are spread over the visible
+ * GPUs by a static load-balanced schedule at pair granularity (song_host_schedule_pairs; transfer2.c:549-551: the k1
+ * modes are independent); every GPU has one host thread that runs its batches as a three-deep pipeline
+ * (song_los_submit / song_los_wait): inputs are packed into page-locked staging, the result of a batch is copied by the
+ * device straight into the slab of ptr2->transfer that holds its pairs (los_module.h) -- that copy is the "gather to
+ * the host".  Side effects keep the reference's per-k1 meaning: sources of a k1 level are loaded before use and freed
+ * once its last pair is packed (transfer2.c:332-344, 553), transfers are stored and freed per k1 in k1 order
+ * (transfer2.c:559-567).  The engines (CUDA contexts, projection tables) are those bessel2_init left on the devices
+ * (bessel2_gpu.c); with the reference's bessel2.c they are built here from pbs2->J_Llm_x.
  *
  * Environment: SONG_LOS_MODE=fast|exact (default fast; cubic Bessel interpolation forces exact),
- * SONG_LOS_DEVICES=<n> (default: all visible), SONG_LOS_BATCH_UNITS=<n>.
+ * SONG_LOS_DEVICES=<n> (default: all visible), SONG_LOS_BATCH_UNITS, SONG_LOS_MIN_BATCHES, SONG_LOS_CHUNKS_PER_DEVICE,
+ * SONG_LOS_HOST_THREADS, SONG_LOS_PINNED_TRANSFERS=0|1, SONG_LOS_PINNED_POOL=0|1.
  */
 #include "transfer2.h"
 #include "song_los.h"
 #include "los_host.h"
+#include "los_glue.h"
+#include "los_module.h"
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -235,59 +239,95 @@ int transfer2_indices_of_transfers(struct precision *ppr, struct precision2 *ppr
 /* ------------------------------------------------------------------------------------------------ */
 /*  memory management and disk format of ptr2->transfer                                              */
 /* ------------------------------------------------------------------------------------------------ */
+/* The reference allocates ptr2->transfer[tt][k1][k2] one array at a time (tt2_size * (k1+1) mallocs per k1 level,
+   transfer2.c:2976-3032).  Here the pointers of all levels live in one block and the values in large page-locked slabs,
+   [tt2_size][k3 values of a run of pairs] each (los_module.h): a GPU batch copies its result straight into its slab.
+   The exported functions keep the reference's meaning and guards. */
+static los_transfer_store *store_of(struct perturbs2 *ppt2, struct transfers2 *ptr2)
+{
+  los_transfer_store *s = los_store_find(ptr2);
+  if (s == NULL) s = los_store_create(ptr2, ppt2->k_size, ptr2->tt2_size);
+  return s;
+}
+
+static int pinned_transfers(void) { return env_int("SONG_LOS_PINNED_TRANSFERS", 1) != 0; }
+
+/* Values of the pairs (k1a,k2a) ... (k1b,k2b), reference loop order, as ONE slab [tt2_size][units of the run]; points
+   ptr2->transfer[tt][k1][k2] at its rows.  *base receives the slab, *n_units the k3 values of the run. */
+static int allocate_pair_run(struct perturbs2 *ppt2, struct transfers2 *ptr2, int k1a, int k2a, int k1b, int k2b,
+                             double **base, int64_t *n_units)
+{
+  los_transfer_store *st = store_of(ppt2, ptr2);
+  class_test(st == NULL, ptr2->error_message, "could not set up the storage of ptr2->transfer");
+  int64_t units = 0;
+  for (int k1 = k1a; k1 <= k1b; ++k1)
+    for (int k2 = (k1 == k1a ? k2a : 0); k2 <= (k1 == k1b ? k2b : k1); ++k2) units += ptr2->k_size_k1k2[k1][k2];
+  double *slab = NULL;
+  int id = los_store_new_slab(st, (size_t)units * ptr2->tt2_size, pinned_transfers(), &slab);
+  class_test(id < 0, ptr2->error_message, "could not allocate %g MB for the transfer functions of k1 levels %d-%d",
+             (double)units * ptr2->tt2_size * 8e-6, k1a, k1b);
+  for (int index_tt = 0; index_tt < ptr2->tt2_size; ++index_tt) {
+    double *row = slab + (size_t)index_tt * (size_t)units;
+    for (int k1 = k1a; k1 <= k1b; ++k1) {
+      double **ptrs = los_store_row(st, index_tt, k1);
+      ptr2->transfer[index_tt][k1] = ptrs;
+      for (int k2 = (k1 == k1a ? k2a : 0); k2 <= (k1 == k1b ? k2b : k1); ++k2) { ptrs[k2] = row; row += ptr2->k_size_k1k2[k1][k2]; }
+    }
+  }
+  for (int k1 = k1a; k1 <= k1b; ++k1) { los_store_link(st, k1, id); ptr2->has_allocated_transfers[k1] = _TRUE_; }
+  const long int count = (long int)units * ptr2->tt2_size;
+  #pragma omp atomic
+  ptr2->count_allocated_transfers += count;
+  if (base) *base = slab;
+  if (n_units) *n_units = units;
+  return _SUCCESS_;
+}
+
 int transfer2_allocate_k1_level(struct perturbs2 *ppt2, struct transfers2 *ptr2, int index_k1)
 {
   class_test(ptr2->has_allocated_transfers[index_k1] == _TRUE_, ptr2->error_message,
              "the index_k1=%d level of ptr2->transfers is already allocated, stop to prevent error", index_k1);
-  long int count = 0;
-  for (int index_tt = 0; index_tt < ptr2->tt2_size; ++index_tt) {
-    class_alloc(ptr2->transfer[index_tt][index_k1], (index_k1 + 1) * sizeof(double *), ptr2->error_message);
-    for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) {
-      class_alloc(ptr2->transfer[index_tt][index_k1][index_k2],
-                  ptr2->k_size_k1k2[index_k1][index_k2] * sizeof(double), ptr2->error_message);
-      count += ptr2->k_size_k1k2[index_k1][index_k2];
-    }
-  }
-  #pragma omp atomic
-  ptr2->count_allocated_transfers += count;
-  ptr2->has_allocated_transfers[index_k1] = _TRUE_;
-  return _SUCCESS_;
+  return allocate_pair_run(ppt2, ptr2, index_k1, 0, index_k1, index_k1, NULL, NULL);
 }
 
 int transfer2_free_k1_level(struct perturbs2 *ppt2, struct transfers2 *ptr2, int index_k1)
 {
   class_test(ptr2->has_allocated_transfers[index_k1] == _FALSE_, ptr2->error_message,
              "the index_k1=%d level of ptr2->transfers is already free, stop to prevent error", index_k1);
-  for (int index_tt = 0; index_tt < ptr2->tt2_size; ++index_tt) {
-    for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) free(ptr2->transfer[index_tt][index_k1][index_k2]);
-    free(ptr2->transfer[index_tt][index_k1]);
-  }
+  los_transfer_store *st = los_store_find(ptr2);
+  if (st != NULL) los_store_release_level(st, index_k1);      /* a slab goes back when its last level is freed */
   ptr2->has_allocated_transfers[index_k1] = _FALSE_;
   return _SUCCESS_;
 }
 
+/* One transfer type for all (k1,k2,k3) -- the layout of a transfers_%03d.dat file (transfer2.c:636-691): one array of
+   values and one of pointers per type; transfer2_free_type_level recovers both from [0][0] and [0]. */
 int transfer2_allocate_type_level(struct perturbs2 *ppt2, struct transfers2 *ptr2, int index_tt)
 {
-  int k1_size = ppt2->k_size;
+  const int k1_size = ppt2->k_size;
+  size_t n_pairs = (size_t)k1_size * (k1_size + 1) / 2, per_type = 0;
+  for (int index_k1 = 0; index_k1 < k1_size; ++index_k1)
+    for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) per_type += ptr2->k_size_k1k2[index_k1][index_k2];
+  double *values, **ptrs;
   class_alloc(ptr2->transfer[index_tt], k1_size * sizeof(double **), ptr2->error_message);
+  class_alloc(ptrs, n_pairs * sizeof(double *), ptr2->error_message);
+  class_alloc(values, (per_type > 0 ? per_type : 1) * sizeof(double), ptr2->error_message);
   for (int index_k1 = 0; index_k1 < k1_size; ++index_k1) {
-    class_alloc(ptr2->transfer[index_tt][index_k1], (index_k1 + 1) * sizeof(double *), ptr2->error_message);
+    ptr2->transfer[index_tt][index_k1] = ptrs + (size_t)index_k1 * (index_k1 + 1) / 2;
     for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) {
-      class_alloc(ptr2->transfer[index_tt][index_k1][index_k2],
-                  ptr2->k_size_k1k2[index_k1][index_k2] * sizeof(double), ptr2->error_message);
-      #pragma omp atomic
-      ptr2->count_allocated_transfers += ptr2->k_size_k1k2[index_k1][index_k2];
+      ptr2->transfer[index_tt][index_k1][index_k2] = values;
+      values += ptr2->k_size_k1k2[index_k1][index_k2];
     }
   }
+  #pragma omp atomic
+  ptr2->count_allocated_transfers += (long int)per_type;
   return _SUCCESS_;
 }
 
 int transfer2_free_type_level(struct perturbs2 *ppt2, struct transfers2 *ptr2, int index_tt)
 {
-  for (int index_k1 = 0; index_k1 < ppt2->k_size; ++index_k1) {
-    for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) free(ptr2->transfer[index_tt][index_k1][index_k2]);
-    free(ptr2->transfer[index_tt][index_k1]);
-  }
+  free(ptr2->transfer[index_tt][0][0]);
+  free(ptr2->transfer[index_tt][0]);
   free(ptr2->transfer[index_tt]);
   return _SUCCESS_;
 }
@@ -308,18 +348,17 @@ int transfer2_load_transfers_from_disk(struct perturbs2 *ppt2, struct transfers2
 {
   class_call(transfer2_allocate_type_level(ppt2, ptr2, index_tt), ptr2->error_message, ptr2->error_message);
   class_open(ptr2->transfers_files[index_tt], ptr2->transfers_paths[index_tt], "rb", ptr2->error_message);
+  /* the file holds [k1][k2][k3] (transfer2.c:725-751), which is the order of the type's array: one read */
+  size_t n_to_read = 0;
   for (int index_k1 = 0; index_k1 < ppt2->k_size; ++index_k1)
-    for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) {
-      int n_to_read = ptr2->k_size_k1k2[index_k1][index_k2];
-      int n_read = (int)fread(ptr2->transfer[index_tt][index_k1][index_k2], sizeof(double), n_to_read,
-                              ptr2->transfers_files[index_tt]);
-      class_test(n_read != n_to_read, ptr2->error_message,
-                 "Could not read in '%s' file, read %d entries but expected %d (index_tt=%d,index_k1=%d,index_k2=%d)",
-                 ptr2->transfers_paths[index_tt], n_read, n_to_read, index_tt, index_k1, index_k2);
-      #pragma omp atomic
-      ptr2->count_memorised_transfers += n_to_read;
-    }
+    for (int index_k2 = 0; index_k2 <= index_k1; ++index_k2) n_to_read += ptr2->k_size_k1k2[index_k1][index_k2];
+  size_t n_read = fread(ptr2->transfer[index_tt][0][0], sizeof(double), n_to_read, ptr2->transfers_files[index_tt]);
   fclose(ptr2->transfers_files[index_tt]);
+  class_test(n_read != n_to_read, ptr2->error_message,
+             "Could not read in '%s' file, read %zu entries but expected %zu (index_tt=%d)",
+             ptr2->transfers_paths[index_tt], n_read, n_to_read, index_tt);
+  #pragma omp atomic
+  ptr2->count_memorised_transfers += (long int)n_to_read;
   return _SUCCESS_;
 }
 
@@ -333,6 +372,7 @@ int transfer2_free(struct precision2 *ppr2, struct perturbs2 *ppt2, struct trans
           class_call(transfer2_free_k1_level(ppt2, ptr2, index_k1), ptr2->error_message, ptr2->error_message);
       for (int index_tt = 0; index_tt < ptr2->tt2_size; ++index_tt) free(ptr2->transfer[index_tt]);
     }
+    los_store_drop(ptr2);
     free(ptr2->transfer);
     free(ptr2->has_allocated_transfers);
     for (int index_k1 = 0; index_k1 < ppt2->k_size; ++index_k1) {
@@ -384,180 +424,91 @@ int transfer2_integrate(struct precision *ppr, struct precision2 *ppr2, struct p
 { ON_DEVICE("transfer2_integrate"); }
 
 /* ------------------------------------------------------------------------------------------------ */
-/*  engine set-up from the SONG structures                                                           */
+/*  GPU batches                                                                                      */
 /* ------------------------------------------------------------------------------------------------ */
+/* One GPU batch = a run of consecutive (k1,k2) pairs in the reference loop order (pair p = k1(k1+1)/2 + k2). */
 typedef struct {
-  song_los_ctx *ctx;
+  int p_first, p_last;             /* pairs of the batch */
+  int64_t n_units, n_pt, n_src;    /* k3 values, coarse k3 points, source doubles */
   int device;
-} los_device;
+  double *slab;                    /* [tt2_size][n_units]: where ptr2->transfer of these pairs lives */
+} los_pair_batch;
 
-static int create_engine(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2, struct bessels2 *pbs2,
-                         struct transfers2 *ptr2, int device, song_los_ctx **out)
-{
-  song_los_config cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.device = device;
-  cfg.tau0 = ptr2->tau0;
-  cfg.tau_size = ppt2->tau_size; cfg.tau_sampling = ppt2->tau_sampling;
-  cfg.tau_sampling_mode = (ptr2->tau_sampling == sources_tau_sampling) ? SONG_LOS_TAU_SOURCES
-                        : (ptr2->tau_sampling == bessel_tau_sampling) ? SONG_LOS_TAU_BESSEL : SONG_LOS_TAU_CUSTOM;
-  cfg.tau_linstep_song = ppr2->tau_linstep_song;
-  cfg.sources_k3_interpolation = (ppr2->sources_k3_interpolation == cubic_interpolation) ? SONG_LOS_INTERP_CUBIC : SONG_LOS_INTERP_LINEAR;
-  cfg.sources_time_interpolation = (ppr2->sources_time_interpolation == cubic_interpolation) ? SONG_LOS_INTERP_CUBIC : SONG_LOS_INTERP_LINEAR;
-  cfg.bessels_interpolation = (ppr->bessels_interpolation == cubic_interpolation) ? SONG_LOS_INTERP_CUBIC : SONG_LOS_INTERP_LINEAR;
-  cfg.k3_extrapolation = (ppr->bispectra_k3_extrapolation == no_k3_extrapolation) ? SONG_LOS_NO_K3_EXTRAPOLATION : SONG_LOS_FLAT_K3_EXTRAPOLATION;
-  cfg.xx_size = pbs2->xx_size; cfg.xx = pbs2->xx; cfg.xx_step = pbs2->xx_step;
-  cfg.l_size = ptr2->l_size; cfg.l = ptr2->l;
-  cfg.m_size = ptr2->m_size; cfg.m = ptr2->m;
-  cfg.L_size = pbs2->L_size;
-  cfg.n_transfers = ptr2->n_transfers;
-
-  /* lm_array as [l_size][m_size] and lm(L,m) of the sources as [L_size][m_size], -1 where not defined */
-  int *lm_array, *lm_src;
-  class_alloc(lm_array, (size_t)ptr2->l_size * ptr2->m_size * sizeof(int), ptr2->error_message);
-  class_alloc(lm_src, (size_t)pbs2->L_size * ptr2->m_size * sizeof(int), ptr2->error_message);
-  for (int index_l = 0; index_l < ptr2->l_size; ++index_l)
-    for (int index_m = 0; index_m < ptr2->m_size; ++index_m)
-      lm_array[index_l * ptr2->m_size + index_m] =
-          (index_m <= ppr2->index_m_max[ptr2->l[index_l]]) ? ptr2->lm_array[index_l][index_m] : -1;
-  for (int L = 0; L < pbs2->L_size; ++L)
-    for (int index_m = 0; index_m < ptr2->m_size; ++index_m)
-      lm_src[L * ptr2->m_size + index_m] = (ptr2->m[index_m] <= L) ? ppt2->lm_array[L][index_m] : -1;   /* lm(L,m), perturbations2_macros.h:53 */
-  cfg.lm_array = lm_array; cfg.lm_src = lm_src;
-
-  cfg.has_source_T = ppt2->has_source_T; cfg.has_source_E = ppt2->has_source_E; cfg.has_source_B = ppt2->has_source_B;
-  cfg.index_tp2_T = ppt2->index_tp2_T; cfg.index_tp2_E = ppt2->index_tp2_E; cfg.index_tp2_B = ppt2->index_tp2_B;
-  cfg.tp2_size = ppt2->tp2_size;
-  cfg.l_max_los_t = ppr2->l_max_los_t; cfg.l_max_los_p = ppr2->l_max_los_p;
-  cfg.index_tt2_T = ptr2->index_tt2_T; cfg.index_tt2_E = ptr2->index_tt2_E; cfg.index_tt2_B = ptr2->index_tt2_B;
-  cfg.tt2_size = ptr2->tt2_size;
-  cfg.tt_index_l = ptr2->corresponding_index_l; cfg.tt_index_m = ptr2->corresponding_index_m;
-  cfg.J_size = pbs2->J_size;
-  cfg.index_J_TT = pbs2->has_J_TT ? pbs2->index_J_TT : -1;
-  cfg.index_J_EE = pbs2->has_J_EE ? pbs2->index_J_EE : -1;
-  cfg.index_J_EB = pbs2->has_J_EB ? pbs2->index_J_EB : -1;
-
-  int rc = song_los_create(&cfg, out);
-  free(lm_array); free(lm_src);
-  class_test(rc != SONG_LOS_SUCCESS, ptr2->error_message, "%.1500s", song_los_last_error(NULL));
-
-  /* projection functions of bessel2_init: ragged [J][L][l][m] rows -> flat list (bessel2.h:64-91) */
-  size_t n_j = (size_t)pbs2->J_size * pbs2->L_size * ptr2->l_size * ptr2->m_size;
-  const double **rows, **ddrows; int *xmin, *xsize;
-  class_calloc(rows, n_j, sizeof(double *), ptr2->error_message);
-  class_calloc(ddrows, n_j, sizeof(double *), ptr2->error_message);
-  class_calloc(xmin, n_j, sizeof(int), ptr2->error_message);
-  class_calloc(xsize, n_j, sizeof(int), ptr2->error_message);
-  int cubic_J = (ppr->bessels_interpolation == cubic_interpolation);
-  for (int J = 0; J < pbs2->J_size; ++J)
-    for (int L = 0; L < pbs2->L_size; ++L)
-      for (int index_l = 0; index_l < ptr2->l_size; ++index_l)
-        for (int index_m = 0; index_m < ptr2->m_size; ++index_m) {
-          if (ptr2->m[index_m] > MIN(pbs2->L[L], ptr2->l[index_l])) continue;       /* not allocated by bessel2_init */
-          size_t q = (((size_t)J * pbs2->L_size + L) * ptr2->l_size + index_l) * ptr2->m_size + index_m;
-          rows[q] = pbs2->J_Llm_x[J][L][index_l][index_m];
-          if (cubic_J) ddrows[q] = pbs2->ddJ_Llm_x[J][L][index_l][index_m];
-          xmin[q] = pbs2->index_xmin_J[J][L][index_l][index_m];
-          xsize[q] = pbs2->x_size_J[J][L][index_l][index_m];
-        }
-  rc = song_los_set_projection(*out, rows, cubic_J ? ddrows : NULL, xmin, xsize);
-  free(rows); free(ddrows); free(xmin); free(xsize);
-  if (rc != SONG_LOS_SUCCESS) {
-    snprintf(ptr2->error_message, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(*out));
-    song_los_destroy(*out); *out = NULL;
-    return _FAILURE_;
-  }
-  return _SUCCESS_;
-}
-
-/* one GPU batch = the k1 levels [k1_first, k1_last] */
-typedef struct { int k1_first, k1_last; long n_units; int device; } los_k1_batch;
-
-/* Page-locked staging of one batch in flight (song_los_host_alloc): the packed inputs the C-ABI reads
-   and the [tt2_size][n_units] result it writes.  SONG_LOS_MAX_IN_FLIGHT of these per GPU, used in turn. */
+/* Page-locked staging of the INPUTS of one batch in flight (the result needs none: it is copied into its slab).
+   SONG_LOS_MAX_IN_FLIGHT of these per GPU, used in turn. */
 typedef struct {
   int *np, *nt, *ps, *pz; int64_t *pt_off, *tr_off, *src_off;
-  double *k3_pt, *k3_tr, *src, *out;
-  int n_pairs; int64_t n_pt, n_units, n_src;
-  const los_k1_batch *kb;          /* NULL when the staging is free */
-  int pinned;                      /* page-locked (song_los_host_alloc) or plain malloc */
+  double *k3_pt, *k3_tr, *src;
+  unsigned char *block; size_t block_bytes;
+  int n_pairs;
+  const los_pair_batch *pb;        /* NULL when the staging is free */
 } los_staging;
 
-static int stg_alloc(los_staging *s, void **ptr, size_t bytes)
-{
-  if (s->pinned) return song_los_host_alloc(ptr, bytes);
-  *ptr = malloc(bytes > 0 ? bytes : 1);
-  return *ptr ? SONG_LOS_SUCCESS : SONG_LOS_FAILURE;
-}
-static void stg_free(los_staging *s, void *ptr) { if (s->pinned) song_los_host_free(ptr); else free(ptr); }
+static void staging_free(los_staging *s) { los_pinned_put(s->block); memset(s, 0, sizeof *s); }
 
-static void staging_free(los_staging *s)
-{
-  stg_free(s, s->np); stg_free(s, s->nt); stg_free(s, s->ps); stg_free(s, s->pz);
-  stg_free(s, s->pt_off); stg_free(s, s->tr_off); stg_free(s, s->src_off);
-  stg_free(s, s->k3_pt); stg_free(s, s->k3_tr); stg_free(s, s->src); stg_free(s, s->out);
-  memset(s, 0, sizeof *s);
-}
-
-/* capacity of the largest batch of a device.  Page-locking costs about half a second per GB: it pays only when
-   copies have something to overlap with, i.e. when the device runs more than one batch. */
-static int staging_alloc(los_staging *s, int pinned, int max_pairs, int64_t max_pt, int64_t max_units, int64_t max_src, int tt2_size)
+/* one page-locked block for the largest batch of a device, carved into the arrays of song_los_batch */
+static int staging_alloc(los_staging *s, int max_pairs, int64_t max_pt, int64_t max_units, int64_t max_src)
 {
   memset(s, 0, sizeof *s);
-  s->pinned = pinned;
-  int rc = 0;
-  rc |= stg_alloc(s, (void **)&s->np, sizeof(int) * (size_t)max_pairs);
-  rc |= stg_alloc(s, (void **)&s->nt, sizeof(int) * (size_t)max_pairs);
-  rc |= stg_alloc(s, (void **)&s->ps, sizeof(int) * (size_t)max_pairs);
-  rc |= stg_alloc(s, (void **)&s->pz, sizeof(int) * (size_t)max_pairs);
-  rc |= stg_alloc(s, (void **)&s->pt_off, sizeof(int64_t) * (size_t)max_pairs);
-  rc |= stg_alloc(s, (void **)&s->tr_off, sizeof(int64_t) * (size_t)max_pairs);
-  rc |= stg_alloc(s, (void **)&s->src_off, sizeof(int64_t) * (size_t)max_pairs);
-  rc |= stg_alloc(s, (void **)&s->k3_pt, sizeof(double) * (size_t)max_pt);
-  rc |= stg_alloc(s, (void **)&s->k3_tr, sizeof(double) * (size_t)max_units);
-  rc |= stg_alloc(s, (void **)&s->src, sizeof(double) * (size_t)max_src);
-  rc |= stg_alloc(s, (void **)&s->out, sizeof(double) * (size_t)max_units * tt2_size);
-  if (rc != SONG_LOS_SUCCESS) { staging_free(s); return _FAILURE_; }
+  const size_t a_int = ((size_t)max_pairs * sizeof(int) + 63) & ~(size_t)63, a_i64 = ((size_t)max_pairs * sizeof(int64_t) + 63) & ~(size_t)63;
+  const size_t a_pt = ((size_t)max_pt * 8 + 63) & ~(size_t)63, a_tr = ((size_t)max_units * 8 + 63) & ~(size_t)63, a_src = (size_t)max_src * 8 + 64;
+  s->block_bytes = 4 * a_int + 3 * a_i64 + a_pt + a_tr + a_src;
+  s->block = (unsigned char *)los_pinned_get(s->block_bytes);
+  if (s->block == NULL) return _FAILURE_;
+  unsigned char *p = s->block;
+  s->np = (int *)p; p += a_int; s->nt = (int *)p; p += a_int; s->ps = (int *)p; p += a_int; s->pz = (int *)p; p += a_int;
+  s->pt_off = (int64_t *)p; p += a_i64; s->tr_off = (int64_t *)p; p += a_i64; s->src_off = (int64_t *)p; p += a_i64;
+  s->k3_pt = (double *)p; p += a_pt; s->k3_tr = (double *)p; p += a_tr; s->src = (double *)p;
   return _SUCCESS_;
 }
 
-static void batch_sizes(struct perturbs2 *ppt2, struct transfers2 *ptr2, const los_k1_batch *kb,
-                        int *n_pairs, int64_t *n_pt, int64_t *n_units, int64_t *n_src)
-{
-  *n_pairs = 0; *n_pt = 0; *n_units = 0; *n_src = 0;
-  for (int k1 = kb->k1_first; k1 <= kb->k1_last; ++k1)
-    for (int k2 = 0; k2 <= k1; ++k2) {
-      ++*n_pairs; *n_pt += ppt2->k3_size[k1][k2]; *n_units += ptr2->k_size_k1k2[k1][k2];
-      *n_src += (int64_t)ppt2->tp2_size * ppt2->tau_size * ppt2->k3_size[k1][k2];
-    }
-}
+/* what a run of the k1 loop shares between the host threads of the GPUs */
+typedef struct {
+  struct precision *ppr; struct precision2 *ppr2; struct perturbs2 *ppt2; struct bessels *pbs; struct bessels2 *pbs2;
+  struct transfers2 *ptr2;
+  int n_pairs; int *pair_k1, *pair_k2;     /* pair -> (index_k1, index_k2) */
+  int *pairs_to_pack;                      /* per k1 level: pairs whose sources have not been packed yet (-> perturb2_free_k1_level) */
+  int mode, host_threads, sources_on_disk, store_to_disk;
+  int next_level_to_load, next_level_to_store;   /* ordered runs (one GPU, batches in k1 order) */
+} los_run;
 
-/* packs the k1 levels of `kb` into the staging and enqueues the batch on the GPU (song_los_submit) */
-static int submit_batch(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2, struct bessels *pbs,
-                        struct bessels2 *pbs2, struct transfers2 *ptr2, song_los_ctx *ctx, int mode, const los_k1_batch *kb,
-                        los_staging *s, int host_threads, char *errmsg)
+/* packs the pairs of `pb` into the staging and enqueues the batch on the GPU (song_los_submit): the kernels' result goes
+   straight to the batch's slab of ptr2->transfer */
+static int submit_batch(los_run *R, song_los_ctx *ctx, los_pair_batch *pb, los_staging *s, char *errmsg)
 {
+  struct perturbs2 *ppt2 = R->ppt2; struct transfers2 *ptr2 = R->ptr2;
   const int tp2 = ppt2->tp2_size, ntau = ppt2->tau_size;
-  batch_sizes(ppt2, ptr2, kb, &s->n_pairs, &s->n_pt, &s->n_units, &s->n_src);
+  const int k1a = R->pair_k1[pb->p_first], k1b = R->pair_k1[pb->p_last];
+
+  /* sources kept on disk arrive one k1 level at a time (transfer2.c:332-344) */
+  if (R->sources_on_disk)
+    for (; R->next_level_to_load <= k1b; ++R->next_level_to_load)
+      if (perturb2_allocate_k1_level(ppt2, R->next_level_to_load) == _FAILURE_ || perturb2_load_sources_from_disk(ppt2, R->next_level_to_load) == _FAILURE_) {
+        snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ppt2->error_message); return _FAILURE_;
+      }
+
+  /* ptr2->transfer of these pairs: one slab, which is also where the device->host copy of the batch lands */
+  int64_t units = 0;
+  if (allocate_pair_run(ppt2, ptr2, k1a, R->pair_k2[pb->p_first], k1b, R->pair_k2[pb->p_last], &pb->slab, &units) == _FAILURE_) {
+    snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); return _FAILURE_;
+  }
+
   /* sizes and offsets first (serial), then every pair is packed independently by the host threads of this GPU */
-  int p = 0;
+  s->n_pairs = pb->p_last - pb->p_first + 1;
   int64_t o_pt = 0, o_tr = 0, o_src = 0;
-  for (int k1 = kb->k1_first; k1 <= kb->k1_last; ++k1)
-    for (int k2 = 0; k2 <= k1; ++k2, ++p) {
-      s->np[p] = ppt2->k3_size[k1][k2]; s->nt[p] = ptr2->k_size_k1k2[k1][k2];
-      s->ps[p] = ptr2->k_physical_start_k1k2[k1][k2]; s->pz[p] = ptr2->k_physical_size_k1k2[k1][k2];
-      s->pt_off[p] = o_pt; s->tr_off[p] = o_tr; s->src_off[p] = o_src;
-      o_pt += s->np[p]; o_tr += s->nt[p]; o_src += (int64_t)tp2 * ntau * s->np[p];
-    }
-  int failed = 0;
-  #pragma omp parallel for schedule(dynamic, 8) num_threads(host_threads) if (host_threads > 1)
   for (int q = 0; q < s->n_pairs; ++q) {
-    /* pair q of the batch -> (k1,k2): k1 levels are consecutive, level k1 holds k1+1 pairs */
-    int k1 = kb->k1_first, r = q;
-    while (r > k1) { r -= k1 + 1; ++k1; }
-    const int k2 = r;
+    const int k1 = R->pair_k1[pb->p_first + q], k2 = R->pair_k2[pb->p_first + q];
+    s->np[q] = ppt2->k3_size[k1][k2]; s->nt[q] = ptr2->k_size_k1k2[k1][k2];
+    s->ps[q] = ptr2->k_physical_start_k1k2[k1][k2]; s->pz[q] = ptr2->k_physical_size_k1k2[k1][k2];
+    s->pt_off[q] = o_pt; s->tr_off[q] = o_tr; s->src_off[q] = o_src;
+    o_pt += s->np[q]; o_tr += s->nt[q]; o_src += (int64_t)tp2 * ntau * s->np[q];
+  }
+  int failed = 0;
+  #pragma omp parallel for schedule(dynamic, 8) num_threads(R->host_threads) if (R->host_threads > 1)
+  for (int q = 0; q < s->n_pairs; ++q) {
+    const int k1 = R->pair_k1[pb->p_first + q], k2 = R->pair_k2[pb->p_first + q];
     memcpy(s->k3_pt + s->pt_off[q], ppt2->k3[k1][k2], sizeof(double) * s->np[q]);
-    if (transfer2_get_k3_list(ppr, ppr2, ppt2, pbs, pbs2, ptr2, k1, k2, s->k3_tr + s->tr_off[q], NULL) == _FAILURE_) {
+    if (transfer2_get_k3_list(R->ppr, R->ppr2, ppt2, R->pbs, R->pbs2, ptr2, k1, k2, s->k3_tr + s->tr_off[q], NULL) == _FAILURE_) {
       #pragma omp atomic write
       failed = 1;
       continue;
@@ -567,47 +518,109 @@ static int submit_batch(struct precision *ppr, struct precision2 *ppr2, struct p
       memcpy(s->src + s->src_off[q] + (int64_t)tp * ntau * s->np[q], ppt2->sources[tp][k1][k2], sizeof(double) * (size_t)ntau * s->np[q]);
   }
   if (failed) { snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); return _FAILURE_; }
+
   song_los_batch b;
   memset(&b, 0, sizeof b);
   b.n_pairs = s->n_pairs; b.k3_pt_size = s->np; b.k3_tr_size = s->nt; b.phys_start = s->ps; b.phys_size = s->pz;
   b.pt_off = s->pt_off; b.tr_off = s->tr_off; b.src_off = s->src_off;
-  b.n_pt_total = s->n_pt; b.n_units = s->n_units; b.n_src_total = s->n_src;
+  b.n_pt_total = o_pt; b.n_units = o_tr; b.n_src_total = o_src;
   b.k3_pt = s->k3_pt; b.k3_tr = s->k3_tr; b.src = s->src;
-  if (song_los_submit(ctx, &b, mode, s->out) != SONG_LOS_SUCCESS) {
+  if (song_los_submit(ctx, &b, R->mode, pb->slab) != SONG_LOS_SUCCESS) {
     snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(ctx)); return _FAILURE_;
   }
-  s->kb = kb;
+  s->pb = pb;
+
+  /* the sources of these pairs now live in the staging: a k1 level whose last pair has been packed is freed as the
+     reference does after its k2 loop (transfer2.c:553) */
+  for (int k1 = k1a; k1 <= k1b; ++k1) {
+    const int lo = (k1 == k1a) ? R->pair_k2[pb->p_first] : 0, hi = (k1 == k1b) ? R->pair_k2[pb->p_last] : k1;
+    int left;
+    #pragma omp atomic capture
+    left = R->pairs_to_pack[k1] -= (hi - lo + 1);
+    if (left == 0) {
+      int rc;
+      #pragma omp critical(los_free_sources)
+      rc = perturb2_free_k1_level(ppt2, k1);
+      if (rc == _FAILURE_) { snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ppt2->error_message); return _FAILURE_; }
+    }
+  }
   return _SUCCESS_;
 }
 
-/* waits for the oldest batch in flight and scatters its result into ptr2->transfer[tt][k1][k2][k3]
-   (transfer2.c:2107), then applies the per-k1 side effects of transfer2.c:559-567 */
-static int finish_batch(struct precision2 *ppr2, struct perturbs2 *ppt2, struct transfers2 *ptr2, song_los_ctx *ctx,
-                        los_staging *s, int host_threads, char *errmsg)
+/* waits for the oldest batch in flight -- its result is then in ptr2->transfer (transfer2.c:2107) -- and applies the
+   per-k1 side effects of transfer2.c:559-567 */
+static int finish_batch(los_run *R, song_los_ctx *ctx, los_staging *s, char *errmsg)
 {
-  const los_k1_batch *kb = s->kb;
-  s->kb = NULL;
+  struct transfers2 *ptr2 = R->ptr2;
+  const los_pair_batch *pb = s->pb;
+  s->pb = NULL;
   if (song_los_wait(ctx, NULL) != SONG_LOS_SUCCESS) {
     snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(ctx)); return _FAILURE_;
   }
-  long stored = 0;
-  #pragma omp parallel for schedule(dynamic, 8) reduction(+ : stored) num_threads(host_threads) if (host_threads > 1)
-  for (int q = 0; q < s->n_pairs; ++q) {
-    int k1 = kb->k1_first, r = q;
-    while (r > k1) { r -= k1 + 1; ++k1; }
-    const int k2 = r;
-    for (int tt = 0; tt < ptr2->tt2_size; ++tt) {
-      memcpy(ptr2->transfer[tt][k1][k2], s->out + (int64_t)tt * s->n_units + s->tr_off[q], sizeof(double) * s->nt[q]);
-      stored += s->nt[q];
-    }
-  }
+  const long int stored = (long int)pb->n_units * ptr2->tt2_size;
   #pragma omp atomic
   ptr2->count_memorised_transfers += stored;                                    /* transfer2.c:2110-2111 */
-  if (ppr2->store_transfers_to_disk == _TRUE_)                                  /* :559-567, in k1 order */
-    for (int k1 = kb->k1_first; k1 <= kb->k1_last; ++k1)
-      if (transfer2_store_transfers_to_disk(ppt2, ptr2, k1) == _FAILURE_ || transfer2_free_k1_level(ppt2, ptr2, k1) == _FAILURE_) {
+  if (R->store_to_disk) {                                                       /* :559-567, in k1 order */
+    /* ordered run: every level up to the one before the level of the last pair is complete, and that one too when the
+       batch ends on its diagonal */
+    int k1_done = R->pair_k1[pb->p_last];
+    if (R->pair_k2[pb->p_last] != k1_done) --k1_done;
+    for (; R->next_level_to_store <= k1_done; ++R->next_level_to_store)
+      if (transfer2_store_transfers_to_disk(R->ppt2, ptr2, R->next_level_to_store) == _FAILURE_ ||
+          transfer2_free_k1_level(R->ppt2, ptr2, R->next_level_to_store) == _FAILURE_) {
         snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); return _FAILURE_;
       }
+  }
+  return _SUCCESS_;
+}
+
+/* The engines of a run: those bessel2_init left on the devices with the projection tables in place (bessel2_gpu.c), or --
+   when pbs2 comes from the reference's bessel2.c -- a private set built from pbs2->J_Llm_x. */
+static int acquire_engines(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2, struct bessels *pbs,
+                           struct bessels2 *pbs2, struct transfers2 *ptr2, int n_dev_wanted, int tau_mode,
+                           los_engine_set *priv, los_engine_set **out, int *is_private)
+{
+  los_config_buf cb;
+  class_call(los_config_from_song(ppr, ppr2, ppt2, pbs, pbs2, ptr2->tau0, tau_mode, 0, &cb, ptr2->error_message),
+             ptr2->error_message, ptr2->error_message);
+  los_engine_set *set = los_engines_find(pbs2);
+  if (set != NULL && set->n_dev > 0 && song_los_config_matches(set->ctx[0], &cb.cfg)) {
+    int ok = _TRUE_;
+    for (int d = 0; d < set->n_dev && ok; ++d)
+      if (song_los_set_time(set->ctx[d], ptr2->tau0, tau_mode, ppr2->tau_linstep_song) != SONG_LOS_SUCCESS) {
+        snprintf(ptr2->error_message, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(set->ctx[d])); ok = _FALSE_;
+      }
+    los_config_release(&cb);
+    if (!ok) return _FAILURE_;
+    *out = set; *is_private = _FALSE_;
+    return _SUCCESS_;
+  }
+  /* no engines for this pbs2 (reference bessel2_init): create them and upload its tables */
+  memset(priv, 0, sizeof *priv);
+  if (n_dev_wanted > LOS_MAX_DEVICES) n_dev_wanted = LOS_MAX_DEVICES;
+  int failed = _FALSE_;
+  ErrorMsg first = "";
+  #pragma omp parallel for num_threads(n_dev_wanted) schedule(static, 1) if (n_dev_wanted > 1)
+  for (int d = 0; d < n_dev_wanted; ++d) {
+    song_los_config cfg = cb.cfg;
+    cfg.device = d;
+    ErrorMsg local = "";
+    int rc = song_los_create(&cfg, &priv->ctx[d]);
+    if (rc != SONG_LOS_SUCCESS) snprintf(local, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(NULL));
+    else if (los_upload_host_projection(ppr, ppr2, pbs, pbs2, priv->ctx[d], local) == _FAILURE_) rc = SONG_LOS_FAILURE;
+    if (rc != SONG_LOS_SUCCESS) {
+      #pragma omp critical(los_engine_error)
+      { if (!failed) { failed = _TRUE_; snprintf(first, _ERRORMSGSIZE_, "GPU %d: %.1500s", d, local); } }
+    }
+  }
+  los_config_release(&cb);
+  priv->n_dev = n_dev_wanted;
+  if (failed) {
+    for (int d = 0; d < n_dev_wanted; ++d) if (priv->ctx[d]) song_los_destroy(priv->ctx[d]);
+    memset(priv, 0, sizeof *priv);
+    class_stop(ptr2->error_message, "%.1900s", first);
+  }
+  *out = priv; *is_private = _TRUE_;
   return _SUCCESS_;
 }
 
@@ -628,7 +641,7 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   if (ptr2->transfer2_verbose > 0) printf("Computing second-order transfer functions (B200 line-of-sight engine)\n");
 #ifdef _OPENMP
   const double t_start = omp_get_wtime();
-#define LAP(what) do { if (ptr2->transfer2_verbose > 1) printf("     * %-44s %8.1f ms since the start of transfer2_init\n", what, (omp_get_wtime() - t_start) * 1e3); } while (0)
+#define LAP(what) do { if (ptr2->transfer2_verbose > 1) printf("     * %-52s %8.1f ms since the start of transfer2_init\n", what, (omp_get_wtime() - t_start) * 1e3); } while (0)
 #else
 #define LAP(what) do { } while (0)
 #endif
@@ -653,79 +666,112 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   const char *mode_env = getenv("SONG_LOS_MODE");
   if ((mode_env && strcmp(mode_env, "exact") == 0) || (ppr->bessels_interpolation == cubic_interpolation))
     mode = SONG_LOS_MODE_EXACT;
+  const int tau_mode = (ptr2->tau_sampling == sources_tau_sampling) ? SONG_LOS_TAU_SOURCES
+                     : (ptr2->tau_sampling == bessel_tau_sampling) ? SONG_LOS_TAU_BESSEL : SONG_LOS_TAU_CUSTOM;
 
-  /* devices: one host thread per GPU when nothing has to be written in k1 order */
+  /* devices: every visible GPU (SONG_LOS_DEVICES caps the number), one host thread each; a run that reads its sources
+     from disk or writes its transfers to disk level by level keeps the k1 order of the files and uses one */
   const int sources_on_disk = (ppr2->load_sources_from_disk == _TRUE_) || (ppr2->store_sources_to_disk == _TRUE_);
   const int ordered = sources_on_disk || (ppr2->store_transfers_to_disk == _TRUE_);
+  int n_visible = 0;
+  class_test(song_los_device_count(&n_visible) != SONG_LOS_SUCCESS || n_visible < 1, ptr2->error_message,
+             "%.1500s", song_los_last_error(NULL));                                            /* no usable GPU: there is no CPU fallback */
   int n_dev = env_int("SONG_LOS_DEVICES", 0);
-  if (n_dev <= 0) n_dev = 64;          /* probe: engines are created on devices 0,1,... until creation fails */
+  if (n_dev <= 0 || n_dev > n_visible) n_dev = n_visible;
+  if (n_dev > LOS_MAX_DEVICES) n_dev = LOS_MAX_DEVICES;
   if (ordered) n_dev = 1;
-  los_device *dev;
-  class_calloc(dev, n_dev, sizeof(los_device), ptr2->error_message);
-  if (create_engine(ppr, ppr2, ppt2, pbs2, ptr2, 0, &dev[0].ctx) == _FAILURE_) { free(dev); return _FAILURE_; }   /* no usable GPU: there is no CPU fallback */
 
-  LAP("engine on GPU 0 (context, projection tables)");
-  /* k1 batches: consecutive k1 levels up to `batch_units` k3 values.  Large batches make the tensor-core kernel
-     efficient (many k3 per table row); several batches per GPU let the copies overlap the kernels; the upper
-     bound is what fits in device memory twice (two batches in flight). */
-  long total_units = 0, total_pt = 0;
-  for (int k1 = 0; k1 < ppt2->k_size; ++k1)
-    for (int k2 = 0; k2 <= k1; ++k2) { total_units += ptr2->k_size_k1k2[k1][k2]; total_pt += ppt2->k3_size[k1][k2]; }
-  int64_t cap_units = 0;
-  if (song_los_max_batch_units(dev[0].ctx, mode, (double)ppt2->tp2_size * ppt2->tau_size * (double)total_pt / (double)(total_units > 0 ? total_units : 1),
-                               &cap_units) != SONG_LOS_SUCCESS) {
-    snprintf(ptr2->error_message, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(dev[0].ctx));
-    song_los_destroy(dev[0].ctx); free(dev); return _FAILURE_;
-  }
-  long batch_units = (long)env_int("SONG_LOS_BATCH_UNITS", 0);
-  if (batch_units <= 0) {
-    /* as large as device memory allows (the kernel's efficiency grows with the number of k3 values per table
-       row), but not larger than an even share of the run per GPU */
-    int n_dev_guess = ordered ? 1 : env_int("SONG_LOS_DEVICES", 1);
-    if (n_dev_guess < 1) n_dev_guess = 1;
-    batch_units = (total_units + n_dev_guess - 1) / n_dev_guess;
-  }
-  if (batch_units > (long)cap_units) batch_units = (long)cap_units;
-  los_k1_batch *batches;
-  class_alloc(batches, ppt2->k_size * sizeof(los_k1_batch), ptr2->error_message);
-  int n_batches = 0;
-  for (int k1 = 0; k1 < ppt2->k_size;) {
-    los_k1_batch kb = {k1, k1, 0, 0};
-    for (; k1 < ppt2->k_size; ++k1) {
-      long level = 0;
-      for (int k2 = 0; k2 <= k1; ++k2) level += ptr2->k_size_k1k2[k1][k2];
-      if (kb.n_units > 0 && kb.n_units + level > batch_units) break;
-      kb.n_units += level; kb.k1_last = k1;
+  los_engine_set private_set, *engines = NULL;
+  int engines_private = _FALSE_;
+  class_call(acquire_engines(ppr, ppr2, ppt2, pbs, pbs2, ptr2, n_dev, tau_mode, &private_set, &engines, &engines_private),
+             ptr2->error_message, ptr2->error_message);
+  if (engines->n_dev < n_dev) n_dev = engines->n_dev;
+  LAP(engines_private ? "engines created from pbs2->J_Llm_x" : "engines of bessel2_init taken over");
+#define RELEASE_ENGINES() do { if (engines_private) for (int d_ = 0; d_ < engines->n_dev; ++d_) song_los_destroy(engines->ctx[d_]); } while (0)
+
+  /* ---- the pairs and their static schedule (transfer2.c:549-551: the k1 modes are independent) ---- */
+  los_run R;
+  memset(&R, 0, sizeof R);
+  R.ppr = ppr; R.ppr2 = ppr2; R.ppt2 = ppt2; R.pbs = pbs; R.pbs2 = pbs2; R.ptr2 = ptr2;
+  R.mode = mode; R.sources_on_disk = sources_on_disk; R.store_to_disk = (ppr2->store_transfers_to_disk == _TRUE_);
+  R.n_pairs = ppt2->k_size * (ppt2->k_size + 1) / 2;
+  int64_t *cost; int *device_of_pair;
+  class_alloc(R.pair_k1, R.n_pairs * sizeof(int), ptr2->error_message);
+  class_alloc(R.pair_k2, R.n_pairs * sizeof(int), ptr2->error_message);
+  class_alloc(R.pairs_to_pack, ppt2->k_size * sizeof(int), ptr2->error_message);
+  class_alloc(cost, R.n_pairs * sizeof(int64_t), ptr2->error_message);
+  class_alloc(device_of_pair, R.n_pairs * sizeof(int), ptr2->error_message);
+  int64_t total_units = 0, total_pt = 0;
+  for (int k1 = 0, p = 0; k1 < ppt2->k_size; ++k1) {
+    R.pairs_to_pack[k1] = k1 + 1;
+    for (int k2 = 0; k2 <= k1; ++k2, ++p) {
+      R.pair_k1[p] = k1; R.pair_k2[p] = k2;
+      cost[p] = ptr2->k_size_k1k2[k1][k2];            /* every k3 value costs tt2_size integrals over the same tau and L ranges */
+      total_units += ptr2->k_size_k1k2[k1][k2]; total_pt += ppt2->k3_size[k1][k2];
     }
-    batches[n_batches++] = kb;
+  }
+  /* several chunks per GPU give every GPU the same mix of low-k (cheap: few active multipoles) and high-k pairs and
+     double as the batches of its copy/compute pipeline */
+  int chunks_per_dev = env_int("SONG_LOS_CHUNKS_PER_DEVICE", 0);
+  if (chunks_per_dev <= 0) chunks_per_dev = (n_dev > 1) ? 3 : 1;
+  if (ordered) chunks_per_dev = 1;
+  if (song_host_schedule_pairs(cost, R.n_pairs, n_dev, chunks_per_dev, device_of_pair, NULL) != 0) {
+    RELEASE_ENGINES();
+    class_stop(ptr2->error_message, "could not schedule %d (k1,k2) pairs on %d GPUs", R.n_pairs, n_dev);
   }
 
-  if (n_dev > n_batches) n_dev = n_batches > 0 ? n_batches : 1;
-  int n_created = 1;
-  for (int d = 1; d < n_dev; ++d) {
-    if (create_engine(ppr, ppr2, ppt2, pbs2, ptr2, d, &dev[d].ctx) == _FAILURE_) break;
-    dev[d].device = d; ++n_created;
+  /* ---- batches: runs of consecutive pairs of one device, at most what fits in device memory, and at least
+     SONG_LOS_MIN_BATCHES per GPU when the run is large enough for the copies to be worth overlapping ---- */
+  int64_t cap_units = 0;
+  const double src_per_unit = (double)ppt2->tp2_size * ppt2->tau_size * (double)total_pt / (double)(total_units > 0 ? total_units : 1);
+  if (song_los_max_batch_units(engines->ctx[0], mode, src_per_unit, &cap_units) != SONG_LOS_SUCCESS) {
+    snprintf(ptr2->error_message, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(engines->ctx[0]));
+    RELEASE_ENGINES();
+    return _FAILURE_;
   }
-  n_dev = n_created;
+  int64_t batch_units = env_int("SONG_LOS_BATCH_UNITS", 0);
+  if (batch_units <= 0) {
+    int min_batches = env_int("SONG_LOS_MIN_BATCHES", 4);
+    if (min_batches < 1) min_batches = 1;
+    batch_units = (total_units / n_dev + min_batches - 1) / min_batches;
+    const int64_t floor_units = env_int("SONG_LOS_MIN_BATCH_UNITS", 150000);   /* below this the kernels are launch-bound */
+    if (batch_units < floor_units) batch_units = floor_units;
+  }
+  if (batch_units > cap_units) batch_units = cap_units;
+  los_pair_batch *batches;
+  class_alloc(batches, R.n_pairs * sizeof(los_pair_batch), ptr2->error_message);
+  int n_batches = 0;
+  for (int p = 0; p < R.n_pairs;) {
+    /* the run of consecutive pairs of one device starting at p, cut into equal parts of at most batch_units */
+    int q = p; int64_t run_units = 0;
+    while (q < R.n_pairs && device_of_pair[q] == device_of_pair[p]) run_units += cost[q++];
+    const int parts = (int)((run_units + batch_units - 1) / batch_units) > 0 ? (int)((run_units + batch_units - 1) / batch_units) : 1;
+    int64_t acc = 0; int part = 0;
+    los_pair_batch pb; memset(&pb, 0, sizeof pb); pb.p_first = p; pb.device = device_of_pair[p];
+    for (int i = p; i < q; ++i) {
+      acc += cost[i];
+      pb.n_units += cost[i]; pb.n_pt += ppt2->k3_size[R.pair_k1[i]][R.pair_k2[i]];
+      pb.p_last = i;
+      if (i + 1 == q || (part + 1 < parts && acc * parts >= run_units * (part + 1))) {
+        pb.n_src = (int64_t)ppt2->tp2_size * ppt2->tau_size * pb.n_pt;
+        batches[n_batches++] = pb;
+        memset(&pb, 0, sizeof pb); pb.p_first = i + 1; pb.device = device_of_pair[p];
+        ++part;
+      }
+    }
+    p = q;
+  }
   if (ptr2->transfer2_verbose > 0)
-    printf(" -> %d k1 batches (up to %ld k3 values each) on %d GPU(s), %s arithmetic\n", n_batches, batch_units, n_dev,
-           mode == SONG_LOS_MODE_FAST ? "tensor-core" : "reference-order");
+    printf(" -> %d (k1,k2) pairs in %d batches (up to %ld k3 values each) on %d GPU(s), %s arithmetic\n", R.n_pairs, n_batches,
+           (long)batch_units, n_dev, mode == SONG_LOS_MODE_FAST ? "tensor-core" : "reference-order");
+  los_transfer_store *st = store_of(ppt2, ptr2);
+  if (st == NULL) { RELEASE_ENGINES(); class_stop(ptr2->error_message, "could not set up the storage of ptr2->transfer"); }
+  LAP("pair schedule and batches");
 
-  /* static longest-processing-time schedule: batches by decreasing size to the least loaded device */
-  {
-    int64_t *cost = malloc(sizeof(int64_t) * (n_batches > 0 ? n_batches : 1));
-    int *where = malloc(sizeof(int) * (n_batches > 0 ? n_batches : 1));
-    for (int i = 0; i < n_batches; ++i) cost[i] = batches[i].n_units;
-    song_host_lpt_schedule(cost, n_batches, n_dev, where, NULL);
-    for (int i = 0; i < n_batches; ++i) batches[i].device = where[i];
-    free(cost); free(where);
-  }
-
-  /* Per GPU: a pipeline of up to SONG_LOS_MAX_IN_FLIGHT batches (in k1 order).  While the kernels of batch n run, the host
-     packs batch n+1 into the other staging and submits it (its host->device copy overlaps), and the result of
-     batch n-1 travels back and is scattered into ptr2->transfer. */
-  /* host threads per GPU for packing the sources and scattering the results (SONG_LOS_HOST_THREADS, default: an even
-     share of the processors) */
+  /* Per GPU: a pipeline of up to SONG_LOS_MAX_IN_FLIGHT batches.  While the kernels of batch n run, the host packs batch
+     n+1 into the next staging and submits it (its host->device copy overlaps), and the result of batch n-1 travels
+     back into ptr2->transfer.  Host threads per GPU for the packing: SONG_LOS_HOST_THREADS (default: an even share of
+     the processors). */
   int host_threads = env_int("SONG_LOS_HOST_THREADS", 0);
 #ifdef _OPENMP
   if (host_threads <= 0) host_threads = omp_get_num_procs() / (n_dev > 0 ? n_dev : 1);
@@ -733,85 +779,70 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
 #endif
   if (host_threads < 1) host_threads = 1;
   if (host_threads > 32) host_threads = 32;
+  R.host_threads = host_threads;
   int abort_flag = _FALSE_;
   ErrorMsg first_error = "";
   #pragma omp parallel for num_threads(n_dev) schedule(static, 1) if (n_dev > 1)
   for (int d = 0; d < n_dev; ++d) {
     ErrorMsg local = "";
     int ok = _TRUE_;
-    /* staging sized for the largest batch of this device */
-    int max_pairs = 1; int64_t max_pt = 1, max_units = 1, max_src = 1;
+    song_los_ctx *ctx = engines->ctx[d];
+    /* staging and device buffers sized for the largest batch of this device */
+    int max_pairs = 1, n_mine = 0; int64_t max_pt = 1, max_units = 1, max_src = 1;
     for (int ib = 0; ib < n_batches; ++ib) {
       if (batches[ib].device != d) continue;
-      int np_; int64_t a, b, c;
-      batch_sizes(ppt2, ptr2, &batches[ib], &np_, &a, &b, &c);
-      if (np_ > max_pairs) max_pairs = np_;
-      if (a > max_pt) max_pt = a;
-      if (b > max_units) max_units = b;
-      if (c > max_src) max_src = c;
+      ++n_mine;
+      if (batches[ib].p_last - batches[ib].p_first + 1 > max_pairs) max_pairs = batches[ib].p_last - batches[ib].p_first + 1;
+      if (batches[ib].n_pt > max_pt) max_pt = batches[ib].n_pt;
+      if (batches[ib].n_units > max_units) max_units = batches[ib].n_units;
+      if (batches[ib].n_src > max_src) max_src = batches[ib].n_src;
     }
     enum { DEPTH = SONG_LOS_MAX_IN_FLIGHT };
     los_staging stg[DEPTH];
     memset(stg, 0, sizeof stg);
-    int n_mine = 0;
-    for (int ib = 0; ib < n_batches; ++ib) if (batches[ib].device == d) ++n_mine;
-    const int depth = n_mine < DEPTH ? (n_mine > 0 ? n_mine : 1) : DEPTH;    /* page-locking memory is slow: no more sets than batches */
+    const int depth = n_mine < DEPTH ? (n_mine > 0 ? n_mine : 1) : DEPTH;
     for (int i = 0; i < depth && ok; ++i)
-      if (staging_alloc(&stg[i], n_mine > 1, max_pairs, max_pt, max_units, max_src, ptr2->tt2_size) == _FAILURE_) {
+      if (staging_alloc(&stg[i], max_pairs, max_pt, max_units, max_src) == _FAILURE_) {
         snprintf(local, _ERRORMSGSIZE_, "could not allocate the page-locked staging of a GPU batch (%ld k3 values): %.1000s",
                  (long)max_units, song_los_last_error(NULL));
         ok = _FALSE_;
       }
-    if (d == 0) LAP("page-locked staging allocated (GPU 0)");
-    /* device buffers for the largest batch: no allocation (= device-wide synchronisation) inside the pipeline */
-    if (ok && song_los_reserve(dev[d].ctx, mode, depth, max_pairs, max_units, max_pt, max_src) != SONG_LOS_SUCCESS) {
-      snprintf(local, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(dev[d].ctx)); ok = _FALSE_;
+    if (d == 0) LAP("page-locked staging (GPU 0)");
+    /* no allocation (= device-wide synchronisation) inside the pipeline */
+    if (ok && song_los_reserve(ctx, mode, depth, max_pairs, max_units, max_pt, max_src) != SONG_LOS_SUCCESS) {
+      snprintf(local, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(ctx)); ok = _FALSE_;
     }
     if (d == 0) LAP("device buffers reserved (GPU 0)");
-    int cur = 0, in_flight = 0;
+    int cur = 0, first = _TRUE_;
     for (int ib = 0; ok && ib < n_batches; ++ib) {
       if (batches[ib].device != d) continue;
       if (abort_flag == _TRUE_) break;
-      const los_k1_batch *kb = &batches[ib];
-      for (int k1 = kb->k1_first; ok && k1 <= kb->k1_last; ++k1) {
-        if (ptr2->transfer2_verbose > 1)
-          printf("     * computing transfer functions today for index_k1=%d of %d, k1=%g\n", k1, ppt2->k_size, ppt2->k[k1]);
-        if (transfer2_allocate_k1_level(ppt2, ptr2, k1) == _FAILURE_) { snprintf(local, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); ok = _FALSE_; break; }
-        if (sources_on_disk) {                                                                 /* :332-344 */
-          if (perturb2_allocate_k1_level(ppt2, k1) == _FAILURE_ || perturb2_load_sources_from_disk(ppt2, k1) == _FAILURE_) {
-            snprintf(local, _ERRORMSGSIZE_, "%.1500s", ppt2->error_message); ok = _FALSE_; break;
-          }
-        }
-      }
-      /* the staging about to be reused must have been drained: at most DEPTH batches are in flight */
-      if (ok && stg[cur].kb != NULL) {
-        if (finish_batch(ppr2, ppt2, ptr2, dev[d].ctx, &stg[cur], host_threads, local) == _FAILURE_) ok = _FALSE_;
-        --in_flight;
-      }
-      if (d == 0 && ib == 0) LAP("ptr2->transfer levels of the first batch allocated");
-      if (ok && submit_batch(ppr, ppr2, ppt2, pbs, pbs2, ptr2, dev[d].ctx, mode, kb, &stg[cur], host_threads, local) == _FAILURE_) ok = _FALSE_;
-      if (ok) { ++in_flight; cur = (cur + 1) % depth; }
-      if (d == 0 && ib == 0) LAP("first batch packed and submitted");
-      /* the sources of these k1 levels now live in the staging: free them as the reference does (:553) */
-      for (int k1 = kb->k1_first; ok && k1 <= kb->k1_last; ++k1)
-        if (perturb2_free_k1_level(ppt2, k1) == _FAILURE_) { snprintf(local, _ERRORMSGSIZE_, "%.1500s", ppt2->error_message); ok = _FALSE_; break; }
+      if (ptr2->transfer2_verbose > 1)
+        printf("     * GPU %d: transfer functions of index_k1=%d..%d (%d pairs, %ld k3 values)\n", d, R.pair_k1[batches[ib].p_first],
+               R.pair_k1[batches[ib].p_last], batches[ib].p_last - batches[ib].p_first + 1, (long)batches[ib].n_units);
+      /* the staging about to be reused must have been drained: at most `depth` batches are in flight */
+      if (stg[cur].pb != NULL && finish_batch(&R, ctx, &stg[cur], local) == _FAILURE_) { ok = _FALSE_; break; }
+      if (submit_batch(&R, ctx, &batches[ib], &stg[cur], local) == _FAILURE_) { ok = _FALSE_; break; }
+      cur = (cur + 1) % depth;
+      if (d == 0 && first) LAP("first batch packed and submitted (GPU 0)");
+      first = _FALSE_;
     }
-    /* drain in submission order: stg[cur] holds the older batch */
+    /* drain in submission order: stg[cur] holds the oldest batch */
     for (int i = 0; i < depth; ++i) {
       los_staging *s = &stg[(cur + i) % depth];
-      if (s->kb == NULL) continue;
-      if (ok) { if (finish_batch(ppr2, ppt2, ptr2, dev[d].ctx, s, host_threads, local) == _FAILURE_) ok = _FALSE_; }
-      else { song_los_wait(dev[d].ctx, NULL); s->kb = NULL; }
+      if (s->pb == NULL) continue;
+      if (ok) { if (finish_batch(&R, ctx, s, local) == _FAILURE_) ok = _FALSE_; }
+      else { song_los_wait(ctx, NULL); s->pb = NULL; }
     }
-    for (int i = 0; i < DEPTH; ++i) staging_free(&stg[i]);
+    for (int i = 0; i < DEPTH; ++i) if (stg[i].block) staging_free(&stg[i]);
     if (!ok) {
-      #pragma omp critical
+      #pragma omp critical(los_first_error)
       { if (abort_flag == _FALSE_) { abort_flag = _TRUE_; snprintf(first_error, _ERRORMSGSIZE_, "%s", local); } }
     }
   }
-  LAP("all batches computed and stored");
-  for (int d = 0; d < n_dev; ++d) song_los_destroy(dev[d].ctx);
-  free(dev); free(batches);
+  LAP("all batches computed and stored in ptr2->transfer");
+  RELEASE_ENGINES();
+  free(batches); free(cost); free(device_of_pair); free(R.pair_k1); free(R.pair_k2); free(R.pairs_to_pack);
   class_test(abort_flag == _TRUE_, ptr2->error_message, "%.1900s", first_error);
 
   if (ppr2->store_transfers_to_disk == _TRUE_)                                                 /* :598-600 */

@@ -16,7 +16,10 @@ DROPIN_SYMBOLS = [  # called from outside the module in the reference (SURVEY.md
     "transfer2_get_k3_sizes", "transfer2_get_k3_size", "transfer2_interpolate_sources_in_k", "transfer2_get_time_grid",
     "transfer2_interpolate_sources_in_time", "transfer2_compute", "transfer2_integrate",
     "transfer2_store_transfers_to_disk", "transfer2_allocate_type_level", "transfer2_allocate_k1_level",
-    "transfer2_free_k1_level"]
+    "transfer2_free_k1_level",
+    # bessel2 module (include/bessel2.h:161-260); bessel2_J_Llm_at_x is declared there but defined nowhere in the reference
+    "bessel2_init", "bessel2_free", "bessel2_convolution", "bessel2_get_l1_list", "bessel2_get_xx_list", "bessel2_j_for_l1",
+    "bessel2_J_for_Llm", "bessel2_J_Llm", "bessel2_l1_at_x", "bessel2_l1_at_x_linear"]
 
 dp, ip, lp = _lib.c_double_p, _lib.c_int_p, C.POINTER(C.c_longlong)
 
@@ -41,6 +44,8 @@ class HarnessInput(C.Structure):
         ("store_to_disk", C.c_int), ("load_from_disk", C.c_int), ("transfers_dir", C.c_char_p),
         ("verbose", C.c_int),
         ("tau_sampling_mode", C.c_int), ("cubic_time", C.c_int), ("tau_linstep_song", C.c_double),
+        ("use_bessel2_init", C.c_int), ("j_l1_cut", C.c_double), ("J_Llm_cut", C.c_double), ("bessel_tol_x_min", C.c_double),
+        ("keep_sources", C.c_int),
     ]
 
 
@@ -54,29 +59,49 @@ def lib():
             raise _lib.SongLosError(f"{PATH} is missing: run __graft_entry__.build() where the SONG headers are available")
         _lib.host()
         _dll = C.CDLL(PATH, mode=C.RTLD_GLOBAL)
+        vp = C.c_void_p
         _dll.harness_transfer2.argtypes = [C.POINTER(HarnessInput), dp, C.c_longlong, lp, ip, C.c_char_p, C.c_int]
+        _dll.harness_create.argtypes = [C.POINTER(HarnessInput), C.c_char_p, C.c_int]
+        _dll.harness_create.restype = vp
+        _dll.harness_fill_sources.argtypes = [vp]
+        _dll.harness_transfer2_init.argtypes = [vp, C.c_char_p, C.c_int]
+        _dll.harness_checksum.argtypes = [vp]
+        _dll.harness_checksum.restype = C.c_double
+        _dll.harness_read.argtypes = [vp, dp, C.c_longlong, lp, ip, C.c_char_p, C.c_int]
+        _dll.harness_transfer2_free.argtypes = [vp, C.c_char_p, C.c_int]
+        _dll.harness_bessel2_tables.argtypes = [vp, ip, ip, C.POINTER(dp), C.POINTER(dp), lp]
+        _dll.harness_bessel2_convolution.argtypes = [vp, dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, dp]
+        _dll.harness_l1_info.argtypes = [vp, ip, dp]
+        _dll.harness_destroy.argtypes = [vp]
     return _dll
 
 
-def run_transfer2(wl, proj, store_dir: str | None = None, verbose: int = 0):
-    """transfer2_init on workload `wl` with projection tables `proj` (rows in bessels2 layout).
-    Returns (transfer [tt2_size][n_units], count_memorised_transfers, labels_ok)."""
+def _input(wl, proj, store_dir=None, verbose=0, use_bessel2_init=False, keep_sources=False):
+    """harness_input for workload `wl`; returns (struct, objects that must stay alive)."""
     lay, p = wl.layout, wl.params
     assert wl.pairs.shape[0] == wl.k.size * (wl.k.size + 1) // 2, "the harness needs every (k1,k2) pair"
     keep = dict(k=np.ascontiguousarray(wl.k), tau=np.ascontiguousarray(wl.tau), l=np.ascontiguousarray(lay.l),
                 m=np.ascontiguousarray(lay.m), xx=np.ascontiguousarray(wl.xx),
-                pt_off=wl.pt_off.astype(np.longlong), src_off=wl.src_off.astype(np.longlong),
-                xmin=np.ascontiguousarray(proj.index_xmin, dtype=np.int32), xsize=np.ascontiguousarray(proj.x_size, dtype=np.int32))
-    rows = (dp * len(proj.rows))()
-    for i, r in enumerate(proj.rows):
-        if r is not None:
-            rows[i] = _lib.dptr(r)
-    ddrows = None
-    if getattr(proj, "ddrows", None) is not None:
-        ddrows = (dp * len(proj.ddrows))()
-        for i, r in enumerate(proj.ddrows):
+                pt_off=wl.pt_off.astype(np.longlong), src_off=wl.src_off.astype(np.longlong), wl=wl, proj=proj)
+    rows = ddrows = None
+    xmin_p = xsize_p = None
+    if proj is not None:
+        keep["xmin"] = np.ascontiguousarray(proj.index_xmin, dtype=np.int32)
+        keep["xsize"] = np.ascontiguousarray(proj.x_size, dtype=np.int32)
+        xmin_p, xsize_p = _lib.iptr(keep["xmin"]), _lib.iptr(keep["xsize"])
+        rows = (dp * len(proj.rows))()
+        for i, r in enumerate(proj.rows):
             if r is not None:
-                ddrows[i] = _lib.dptr(r)
+                rows[i] = _lib.dptr(r)
+        if getattr(proj, "ddrows", None) is not None:
+            ddrows = (dp * len(proj.ddrows))()
+            for i, r in enumerate(proj.ddrows):
+                if r is not None:
+                    ddrows[i] = _lib.dptr(r)
+    else:
+        assert use_bessel2_init, "without projection tables the harness must call bessel2_init"
+    keep["rows"], keep["ddrows"] = rows, ddrows
+    keep["dir"] = store_dir.encode() if store_dir else None
     inp = HarnessInput(
         tau0=wl.cosmo["tau0"], tau_rec=wl.cosmo["tau_rec"], rs_rec=wl.cosmo["rs_rec"],
         k_size=int(wl.k.size), k=_lib.dptr(keep["k"]), tau_size=int(wl.tau.size), tau_sampling=_lib.dptr(keep["tau"]),
@@ -89,19 +114,111 @@ def run_transfer2(wl, proj, store_dir: str | None = None, verbose: int = 0):
         q_linstep_song=float(p["q_linstep_song"]), smallest_allowed_variation=float(p["smallest_allowed_variation"]),
         xx_size=int(wl.xx.size), xx=_lib.dptr(keep["xx"]), xx_step=float(wl.xx_step), xx_max=float(wl.xx_max),
         J_size=lay.J_size, index_J_TT=lay.index_J_TT, index_J_EE=lay.index_J_EE, index_J_EB=lay.index_J_EB,
-        J_rows=rows, ddJ_rows=ddrows, index_xmin_J=_lib.iptr(keep["xmin"]), x_size_J=_lib.iptr(keep["xsize"]),
+        J_rows=rows, ddJ_rows=ddrows, index_xmin_J=xmin_p, x_size_J=xsize_p,
         k3_pt_size=_lib.iptr(wl.k3_pt_size), pt_off=keep["pt_off"].ctypes.data_as(lp), k3_pt=_lib.dptr(wl.k3_pt),
         src_off=keep["src_off"].ctypes.data_as(lp), src=_lib.dptr(wl.src),
         store_to_disk=int(store_dir is not None), load_from_disk=0,
-        transfers_dir=(store_dir.encode() if store_dir else None), verbose=verbose,
+        transfers_dir=keep["dir"], verbose=verbose,
         tau_sampling_mode={"sources": 0, "custom": 1, "smart": 1, "bessel": 2}[p["transfer2_tau_sampling"]],
-        cubic_time=int(p["sources_time_interpolation"] == "cubic"), tau_linstep_song=float(p.get("tau_linstep_song", 0.0)))
-    out = np.zeros((lay.tt2_size, wl.n_units), dtype=np.float64)
-    sizes = (C.c_longlong * 3)()
-    labels_ok = C.c_int(0)
-    err = C.create_string_buffer(4096)
-    rc = lib().harness_transfer2(C.byref(inp), _lib.dptr(out), out.size, sizes, C.byref(labels_ok), err, 4096)
-    if rc:
-        raise _lib.SongLosError(err.value.decode(errors="replace"))
-    assert sizes[0] == lay.tt2_size and sizes[1] == wl.n_units, (list(sizes), lay.tt2_size, wl.n_units)
-    return out, int(sizes[2]), bool(labels_ok.value)
+        cubic_time=int(p["sources_time_interpolation"] == "cubic"), tau_linstep_song=float(p.get("tau_linstep_song", 0.0)),
+        use_bessel2_init=int(use_bessel2_init), j_l1_cut=float(p["bessel_j_cut_song"]), J_Llm_cut=float(p["bessel_J_cut_song"]),
+        bessel_tol_x_min=float(p["bessel_tol_x_min"]), keep_sources=int(keep_sources))
+    return inp, keep
+
+
+class Harness:
+    """The SONG structures of one run, kept alive between calls: main/song.c up to transfer2_init, step by step.
+
+    h = Harness(wl, proj)            # input2, perturbations2, bessel, bessel2 (bessel2_init drop-in when proj is None)
+    h.transfer2_init()               # main/song.c:106 -- the call the benchmark times
+    T = h.read()                     # ptr2->transfer in transfers_%03d.dat order
+    h.transfer2_free(); h.fill_sources(); h.transfer2_init()   # next step
+    """
+
+    def __init__(self, wl, proj=None, store_dir=None, verbose=0, keep_sources=False):
+        self.wl = wl
+        self.inp, self._keep = _input(wl, proj, store_dir, verbose, use_bessel2_init=proj is None, keep_sources=keep_sources)
+        err = C.create_string_buffer(4096)
+        self.h = lib().harness_create(C.byref(self.inp), err, 4096)
+        if not self.h:
+            raise _lib.SongLosError(err.value.decode(errors="replace"))
+
+    def _check(self, rc, err):
+        if rc:
+            raise _lib.SongLosError(err.value.decode(errors="replace"))
+
+    def fill_sources(self):
+        lib().harness_fill_sources(self.h)
+
+    def transfer2_init(self):
+        err = C.create_string_buffer(4096)
+        self._check(lib().harness_transfer2_init(self.h, err, 4096), err)
+
+    def checksum(self) -> float:
+        return float(lib().harness_checksum(self.h))
+
+    def read(self):
+        lay, wl = self.wl.layout, self.wl
+        out = np.zeros((lay.tt2_size, wl.n_units), dtype=np.float64)
+        sizes = (C.c_longlong * 3)()
+        labels_ok = C.c_int(0)
+        err = C.create_string_buffer(4096)
+        self._check(lib().harness_read(self.h, _lib.dptr(out), out.size, sizes, C.byref(labels_ok), err, 4096), err)
+        assert sizes[0] == lay.tt2_size and sizes[1] == wl.n_units, (list(sizes), lay.tt2_size, wl.n_units)
+        return out, int(sizes[2]), bool(labels_ok.value)
+
+    def transfer2_free(self):
+        err = C.create_string_buffer(4096)
+        self._check(lib().harness_transfer2_free(self.h, err, 4096), err)
+
+    def bessel2_tables(self):
+        """(rows, index_xmin_J, x_size_J, ddrows, info) of struct bessels2, flat jidx order (copies)."""
+        lay = self.wl.layout
+        n = lay.J_size * lay.L_size * lay.l_size * lay.m_size
+        sizes = (C.c_longlong * 6)()
+        xmin = np.zeros(n, dtype=np.int32); xsize = np.zeros(n, dtype=np.int32)
+        rows = (dp * n)(); ddrows = (dp * n)()
+        lib().harness_bessel2_tables(self.h, _lib.iptr(xmin), _lib.iptr(xsize), rows, ddrows, sizes)
+        out = [np.ctypeslib.as_array(rows[i], shape=(int(xsize[i]),)).copy() if xsize[i] > 0 and rows[i] else None for i in range(n)]
+        dd = [np.ctypeslib.as_array(ddrows[i], shape=(int(xsize[i]),)).copy() if xsize[i] > 0 and ddrows[i] else None for i in range(n)]
+        info = dict(J_size=sizes[0], L_size=sizes[1], xx_size=sizes[2], l1_size=sizes[3], x_size_max_J=sizes[4], count_allocated_Js=sizes[5])
+        return out, xmin, xsize, dd, info
+
+    def l1_info(self):
+        sizes = (C.c_longlong * 6)()
+        lib().harness_bessel2_tables(self.h, None, None, None, None, sizes)
+        l1 = np.zeros(int(sizes[3]), dtype=np.int32); xmin = np.zeros(int(sizes[3]))
+        lib().harness_l1_info(self.h, _lib.iptr(l1), _lib.dptr(xmin))
+        return l1, xmin
+
+    def bessel2_convolution(self, kk, delta_kk, f, g, index_l1, r) -> float:
+        kk = np.ascontiguousarray(kk, dtype=np.float64); delta_kk = np.ascontiguousarray(delta_kk, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        g = None if g is None else np.ascontiguousarray(g, dtype=np.float64)
+        out = C.c_double(0)
+        rc = lib().harness_bessel2_convolution(self.h, _lib.dptr(kk), _lib.dptr(delta_kk), int(kk.size), _lib.dptr(f),
+                                               None if g is None else _lib.dptr(g), int(index_l1), float(r), C.byref(out))
+        if rc:
+            raise _lib.SongLosError("bessel2_convolution failed")
+        return float(out.value)
+
+    def close(self):
+        if self.h:
+            lib().harness_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def run_transfer2(wl, proj, store_dir: str | None = None, verbose: int = 0):
+    """transfer2_init on workload `wl` with projection tables `proj` (rows in bessels2 layout; None: the bessel2_init
+    drop-in builds them).  Returns (transfer [tt2_size][n_units], count_memorised_transfers, labels_ok)."""
+    with Harness(wl, proj, store_dir=store_dir, verbose=verbose) as h:
+        h.transfer2_init()
+        out = h.read()
+        h.transfer2_free()
+    return out

@@ -96,6 +96,7 @@ def lib():
         L.oracle_multipole2offset_indexl_indexm.argtypes = [C.c_int, C.c_int, ip, C.c_int, ip, C.c_int]
         L.oracle_multipole2offset_l_indexm.argtypes = [C.c_int, C.c_int, ip, C.c_int]
         L.oracle_offset2multipole_indexl_indexm.argtypes = [C.c_int, ip, C.c_int, ip, C.c_int, ip, ip]
+        L.oracle_bessel2_convolution.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, C.c_int, C.c_double, dp]
         L.oracle_free = C.CDLL(None).free
         L.oracle_free.argtypes = [C.c_void_p]
         _lib = L
@@ -287,3 +288,16 @@ class OracleRun:
         if rc:
             raise RuntimeError("oracle_transfer2_run failed: " + L.oracle_last_error().decode())
         return out, int(nterms.value)
+
+
+def bessel2_convolution(kk, delta_kk, f, g, j_row, ddj_row, x_min_l1, xx_step, r, cubic=False) -> float:
+    """bessel2_convolution (bessel2.c:499-605) on one row of the j_l1 table."""
+    kk = np.ascontiguousarray(kk, dtype=np.float64); delta_kk = np.ascontiguousarray(delta_kk, dtype=np.float64)
+    f = np.ascontiguousarray(f, dtype=np.float64); j_row = np.ascontiguousarray(j_row, dtype=np.float64)
+    g = None if g is None else np.ascontiguousarray(g, dtype=np.float64)
+    ddj_row = None if ddj_row is None else np.ascontiguousarray(ddj_row, dtype=np.float64)
+    out = C.c_double(0)
+    lib().oracle_bessel2_convolution(_d(kk), _d(delta_kk), int(kk.size), _d(f), None if g is None else _d(g), _d(j_row),
+                                     None if ddj_row is None else _d(ddj_row), float(x_min_l1), float(xx_step), int(cubic),
+                                     float(r), C.byref(out))
+    return float(out.value)

@@ -117,3 +117,104 @@ def test_transfer2_store_and_load_from_disk(oracle, tmp_path, monkeypatch):
     f = tmp_path / "transfers_000.dat"
     assert f.exists() and f.stat().st_size == 8 * wl.n_units
     assert np.array_equal(np.fromfile(f), ref[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bessel2 drop-in (song_b200/host/bessel2_gpu.c) and the hand-over of its engines to transfer2_init
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(sources_k3_interpolation="cubic"),
+                                dict(modes_song=[0, 1, 2], has_source_B=True),
+                                dict(bessels_interpolation="cubic", sources_k3_interpolation="cubic")],
+                         ids=["scalar", "m012_B", "cubic_bessel"])
+def test_bessel2_init_then_transfer2_init(oracle, kw, monkeypatch):
+    """main/song.c:100-106: bessel2_init fills struct bessels2 (device-built J_Llm_x, host j_l1) and leaves the engines
+    on the GPUs; transfer2_init takes them over.  The oracle, fed the tables read from pbs2, must agree bit for bit in
+    EXACT mode; the tables agree with the oracle's own generators to rounding (different j_l / 3j providers)."""
+    wl = _tiny(**kw)
+    oproj = oracle.build_projection(wl)
+    monkeypatch.setenv("SONG_LOS_MODE", "exact")
+    with dropin_lib.Harness(wl, None) as h:
+        rows, xmin, xsize, dd, info = h.bessel2_tables()
+        assert info["J_size"] == wl.layout.J_size and info["L_size"] == wl.layout.L_size and info["xx_size"] == wl.xx.size
+        assert info["x_size_max_J"] == max(int(x) for x in xsize)
+        n_same = 0
+        for q, ref in enumerate(oproj.rows):
+            if ref is None:
+                assert rows[q] is None
+                continue
+            assert abs(int(xmin[q]) - int(oproj.index_xmin[q])) <= 1 and xsize[q] == wl.xx.size - xmin[q]
+            if xmin[q] == oproj.index_xmin[q]:
+                assert np.allclose(rows[q], ref, rtol=0, atol=1e-11 * max(np.abs(ref).max(), 1e-300))
+                n_same += 1
+        assert n_same > 0
+        cubic = kw.get("bessels_interpolation") == "cubic"
+        proj = oracle.OracleProjection(rows, xmin, xsize, None)
+        if cubic:
+            proj.ddrows = dd
+            assert any(d is not None and np.any(d != 0) for d in dd)
+        ref_T, _ = oracle.OracleRun(wl, proj).run()
+        h.transfer2_init()
+        got, count, labels_ok = h.read()
+        assert np.array_equal(got, ref_T) and count == wl.n_integrals and labels_ok
+        h.transfer2_free()
+        if not cubic:
+            # a second run on the same structures (page-locked blocks come back from the pool), tensor-core arithmetic
+            monkeypatch.setenv("SONG_LOS_MODE", "fast")
+            h.fill_sources()
+            h.transfer2_init()
+            got2, count2, _ = h.read()
+            assert _rel_err(got2, ref_T) < 1e-9 and count2 == wl.n_integrals
+            assert abs(h.checksum() - np.abs(got2).sum()) <= 1e-12 * np.abs(got2).sum()
+            h.transfer2_free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cubic", [False, True], ids=["linear", "cubic"])
+def test_bessel2_convolution_matches_oracle(oracle, cubic):
+    """bessel2_convolution (bispectra2.c:1326) on the j_l1 table of the drop-in against the oracle's restatement of
+    bessel2.c:499-605 on the oracle's own table; zero entries of f and g and x below the table are skipped."""
+    wl = _tiny(bessels_interpolation="cubic" if cubic else "linear")
+    oproj = oracle.build_projection(wl, with_jl1=True, spline=cubic)
+    rng = np.random.default_rng(5)
+    kk = np.sort(rng.uniform(1e-5, 0.9 * wl.xx_max / 14000.0, 200))
+    dk = np.empty_like(kk); dk[1:-1] = kk[2:] - kk[:-2]; dk[0] = kk[1] - kk[0]; dk[-1] = kk[-1] - kk[-2]
+    f = rng.normal(size=kk.size); g = rng.normal(size=kk.size)
+    f[::7] = 0.0; g[3::11] = 0.0
+    with dropin_lib.Harness(wl, None) as h:
+        l1, x_min_l1 = h.l1_info()
+        assert np.array_equal(l1, oproj.jl1["l1"])
+        checked = 0
+        for index_l1 in (0, 1, len(l1) // 2, len(l1) - 1):
+            if x_min_l1[index_l1] != oproj.jl1["x_min_l1"][index_l1]:
+                continue                      # the two j_l providers put the cut one grid point apart: different tables
+            checked += 1
+            ddj = None
+            if cubic:                         # natural spline of the row (bessel2.c:439-463)
+                row = oproj.jl1["j_l1"][index_l1]
+                x = np.ascontiguousarray(wl.xx[oproj.jl1["index_xmin_l1"][index_l1]:][:row.size])
+                ddj = np.zeros_like(row)
+                oracle.lib().oracle_spline_table_columns(oracle._d(x), row.size, oracle._d(row), 1, oracle._d(ddj), 0)
+            for r in (13000.0, 14000.0):
+                for gg in (g, None):
+                    got = h.bessel2_convolution(kk, dk, f, gg, index_l1, r)
+                    ref = oracle.bessel2_convolution(kk, dk, f, gg, oproj.jl1["j_l1"][index_l1], ddj,
+                                                     oproj.jl1["x_min_l1"][index_l1], wl.xx_step, r, cubic=cubic)
+                    assert abs(got - ref) <= 1e-9 * max(abs(ref), 1e-30), (index_l1, r, got, ref)
+        assert checked >= 2
+
+
+@pytest.mark.gpu
+def test_k1_level_memory_semantics(oracle, monkeypatch):
+    """ptr2->transfer lives in per-batch slabs; transfer2_free_k1_level / transfer2_free keep their per-level meaning
+    (has_allocated_transfers guard, count_allocated == count_memorised, transfer2.c:607-610, 2976-3104) when a batch
+    covers parts of several k1 levels."""
+    wl = _tiny(sources_k3_interpolation="cubic")
+    proj = oracle.build_projection(wl)
+    ref, _ = oracle.OracleRun(wl, proj).run()
+    monkeypatch.setenv("SONG_LOS_MODE", "exact")
+    monkeypatch.setenv("SONG_LOS_BATCH_UNITS", "97")          # batches end in the middle of k1 levels
+    for pinned in ("1", "0"):
+        monkeypatch.setenv("SONG_LOS_PINNED_TRANSFERS", pinned)
+        got, count, labels_ok = dropin_lib.run_transfer2(wl, Projection(proj.rows, proj.index_xmin, proj.x_size))
+        assert np.array_equal(got, ref) and count == wl.n_integrals and labels_ok
