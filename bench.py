@@ -4,16 +4,20 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: under torch.distributed.run)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-A "step" is one pass of the hot path (song_los_compute: k3 spline, k3 sort, source interpolation,
-DMMA LOS kernel) over
-one batch of synthetic input.  At N=1 the workload is BASELINE.json configs[1]
-(ini/intrinsic.ini + pre/sn_t_10percent_lmax2000.pre, temperature only: 8.6e7 integrals).  With N
-ranks every rank processes its own (k1,k2) shard of the same size (independent sources, no
-data-path collective): weak scaling, value = all ranks' integrals / max-over-ranks time.
+A "step" is one pass of the hot path (k3 spline, k3 sort, source interpolation, DMMA LOS kernel) over ONE
+workload of synthetic input: BASELINE.json configs[3] (ini/intrinsic.ini + pre/sn_pol_5percent_lmax3000.pre, T+E,
+2.5e9 integrals), the largest configuration that fits one B200.  With N ranks the SAME workload is split by (k1,k2)
+pair with the static schedule of the drop-in (song_host_schedule_pairs): strong scaling, no data-path collective,
+value = integrals of the workload / max-over-ranks time; the per-GPU results are then gathered on rank 0 (NCCL, timed
+separately) and spot-checked against the CPU oracle in the reference pair order.
 
-`value`  : inputs resident in HBM when the timed region starts.
-`e2e`    : the same metric through the C-ABI call with HOST (pinned) buffers: every step copies the
-           sources and grids host->device and the transfer functions device->host.
+`value`  : inputs resident in HBM when the timed region starts (the shard's batches, one per engine slot).
+`e2e`    : the same metric through the reference-facing call -- SONG's transfer2_init() (the drop-in of
+           song_b200/host/transfer2_gpu.c, called on SONG structures exactly as main/song.c:106 does) with the sources
+           in pageable host memory (ppt2->sources) and the result in ptr2->transfer: packing, H2D, kernels, D2H all
+           inside the timed region, on all N GPUs of the box (one host thread per GPU inside the module).
+`configs`: the other single-GPU BASELINE configurations measured the same way with fewer steps (N=1), and
+           configs[4] (sn_pol_5percent_lmax4000) split over the ranks when N=8.
 `--impl reference` : the CPU restatement of the reference's transfer2 loops (oracle/, OpenMP on all
            host threads) on a bounded sample of the same workload.  The reference itself cannot be
            built here (its CLASS fork is an empty submodule), so kind = "port".
@@ -36,7 +40,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
 METRIC = "2nd-order LOS transfer integrals/sec (k1,k2,k3,l,m)"
 UNIT = "integrals/s"
-DEFAULT_WORKLOAD = "sn_t_10percent_lmax2000"
+DEFAULT_WORKLOAD = "sn_pol_5percent_lmax3000"      # BASELINE.json configs[3]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -166,23 +170,19 @@ def count_terms(wl, xmin, xsize) -> int:
     return total
 
 
-def pinned_copy(wl):
-    """The workload with its large host arrays in pinned memory (torch allocator)."""
-    import copy
-    import torch
-    out = copy.copy(wl)
-    keep = []
-    for name in ("src", "k3_pt", "k3_tr"):
-        t = torch.from_numpy(getattr(wl, name)).pin_memory()
-        keep.append(t)
-        setattr(out, name, t.numpy())
-    out._pinned = keep
-    return out
-
-
 # ----------------------------------------------------------------------------------------------
 # the reference arm: CPU restatement of transfer2 (oracle/) on the host cores
 # ----------------------------------------------------------------------------------------------
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def cpu_sample(name: str, target_seconds: float, max_pairs=None):
     """(sub-workload, projection) sized for about `target_seconds` of oracle time per pass."""
     import oracle_lib as O
@@ -225,11 +225,15 @@ def run_reference(args, rank: int, world: int):
               f"{grids.n_pairs} pairs, {sub.n_integrals} of {grids.n_integrals} integrals per step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(workload.describe(grids), workload=args.workload,
-                       note="CPU restatement of reference transfer2 (reference not buildable here: class.git is an empty submodule)"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                       note="CPU restatement of reference transfer2 (reference not buildable here: class.git is an empty submodule); "
+                            "the synthetic inputs (grids, sources) come from the same generator as the GPU arm "
+                            "(song_b200.workload, libsong_host.so for the k3 grids) -- the timed region is the oracle alone, the GPU is idle"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "cpu_model": cpu_model(), "kind": "port", "sample": sample,
+                         "build": "gcc -O3 -std=c99 -fopenmp -ffp-contract=off, reference loop structure (serial pair loop, omp for over k3); "
+                                  "no -DDEBUG variant: the restatement does not carry the reference's debug-only checks"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -239,17 +243,350 @@ def run_reference(args, rank: int, world: int):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+class Dist:
+    """torch.distributed plumbing of one bench process (a no-op at world size 1)."""
+
+    def __init__(self, rank, world, local_rank):
+        import torch
+        self.torch = torch
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            import datetime
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=60))
+            self.dist = dist
+            self.cpu_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(minutes=60))
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def cpu_barrier(self):
+        """Wait on the host only: the GPUs of the waiting ranks stay free (rank 0 drives all of them through transfer2_init)."""
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier(group=self.cpu_group)
+
+    def reduce(self, x: float, op: str = "max") -> float:
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "sum": self.dist.ReduceOp.SUM, "min": self.dist.ReduceOp.MIN}[op])
+        return float(t.item())
+
+    def all_gather_floats(self, x: float):
+        if self.dist is None:
+            return [x]
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def split_bounds(k3_tr_size, cap_units: int, n_slots: int = 3):
+    """Pair indices at which a shard (pairs in reference order) is cut into at most n_slots batches of at most cap_units k3 values."""
+    cum = np.cumsum(np.asarray(k3_tr_size, dtype=np.int64))
+    n_b = max(1, -(-int(cum[-1]) // max(cap_units, 1)))
+    if n_b > n_slots:
+        raise SystemExit(f"bench.py: the shard has {int(cum[-1])} k3 values, the GPU holds {n_slots} batches of {cap_units}")
+    cuts = [0]
+    for i in range(1, n_b):
+        c = int(np.searchsorted(cum, cum[-1] * i / n_b)) + 1
+        if c > cuts[-1]:
+            cuts.append(c)
+    if cuts[-1] < cum.size:
+        cuts.append(int(cum.size))
+    return cuts
+
+
+def split_resident(sub, cap_units: int, n_slots: int = 3):
+    cuts = split_bounds(sub.k3_tr_size, cap_units, n_slots)
+    if len(cuts) == 2:
+        return [sub]
+    return [sub.select(np.arange(cuts[i], cuts[i + 1])) for i in range(len(cuts) - 1)]
+
+
+def spot_check(O, sub, got_of_pair, rows, xmin, xsize, n_check: int, run_scale=None):
+    """Oracle on a few pairs of `sub`; got_of_pair(i) -> [tt2][k3 of pair i].  Max relative error above 1e-6 of the
+    per-(l,m) maximum (BASELINE.json criterion; the maximum is taken over the checked pairs unless run_scale is given)."""
+    idx = np.unique(np.linspace(0, sub.n_pairs - 1, min(n_check, sub.n_pairs)).astype(int))
+    oproj = O.OracleProjection(rows, xmin, xsize, None)
+    ref, _ = O.OracleRun(sub.select(idx), oproj).run()
+    got = np.concatenate([got_of_pair(int(i)) for i in idx], axis=1)
+    scale = run_scale if run_scale is not None else np.abs(ref).max(axis=1, keepdims=True)
+    m = np.abs(ref) > 1e-6 * scale
+    err = float(np.max(np.abs(got - ref)[m] / np.abs(ref)[m])) if m.any() else 0.0
+    return {"pairs_checked": int(idx.size), "max_rel_err_above_1e-6_of_max": err, "tolerance": 1e-9, "ok": bool(err <= 1e-9)}
+
+
+def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_steps: int, with_cpu: bool, sampler=None):
+    """One BASELINE workload on the ranks of this run.  Returns the result dict on rank 0 (None elsewhere)."""
+    import torch
+    import dropin_lib
+    from song_b200 import _lib, configs, shard, workload
+    from song_b200.bessel2 import Bessel2
+    from song_b200.engine import MODE_EXACT, MODE_FAST, LosEngine
+
+    rank, world = D.rank, D.world
+    mode = MODE_FAST if args.mode == "fast" else MODE_EXACT
+    t_setup = time.perf_counter()
+    p = configs.get(name)
+    grids = workload.build_grids(p, max_pairs=args.max_pairs)
+    full_pairs = grids.n_pairs == grids.k.size * (grids.k.size + 1) // 2
+    chunks = args.chunks_per_rank if world > 1 else 1
+    dev_of_pair, load = shard.schedule_pairs(shard.pair_cost(grids), world, chunks)
+    owned = np.nonzero(dev_of_pair == rank)[0]
+    want_e2e = e2e_steps > 0 and full_pairs and os.path.exists(dropin_lib.PATH)
+    if rank == 0 and want_e2e:
+        workload.fill_sources(grids)                 # rank 0 also needs the whole run for transfer2_init
+        sub = grids.select(owned) if world > 1 else grids
+    else:
+        sub = workload.fill_sources(grids.select(owned))
+    eng = LosEngine(sub, device=D.local_rank)
+    b2 = Bessel2(sub).init(eng)                      # bessel2_init: host j_l1 + 3j, device J_Llm assembly
+    cap = int(D.reduce(float(eng.max_batch_units(mode, sub.src.size / max(sub.n_units, 1))), "min"))    # one rule on every rank
+    batches = split_resident(sub, cap)
+    peaks = eng.measure_peaks()
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    for i, b in enumerate(batches):                  # inputs resident in HBM: one slot per batch
+        eng.select_slot(i)
+        eng.upload(b)
+    t_setup = time.perf_counter() - t_setup
+
+    # ---- value: inputs resident in HBM ----
+    def one_step(acc=None):
+        n = 0
+        for i in range(len(batches)):
+            eng.select_slot(i)
+            tm = eng.compute(mode)
+            n += tm["n_launches"]
+            if acc is not None:
+                for k in acc:
+                    acc[k] += tm[k]
+        return n
+    for _ in range(warmup):
+        one_step()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern = {"ms_integrate": 0.0, "ms_spline": 0.0, "ms_sort": 0.0, "ms_interp": 0.0, "ms_total": 0.0}
+    launches = 0
+    D.barrier()
+    if sampler is not None:
+        sampler.start()
+    ev0.record(stream)
+    for _ in range(steps):
+        launches += one_step(kern)
+    ev1.record(stream)
+    D.barrier()
+    my_ms = ev0.elapsed_time(ev1) / steps
+    rank_ms = D.all_gather_floats(my_ms)
+    ms_step = max(rank_ms)
+    for k in kern:
+        kern[k] /= steps
+    n_int_rank = sub.n_integrals
+    n_int_total = grids.n_integrals
+    value = n_int_total / (ms_step * 1e-3)
+    launches_total = int(D.reduce(float(launches), "sum"))
+
+    # ---- parity of what was just computed + the one collective of the path: the gather of the per-GPU results ----
+    import oracle_lib as O
+    rows, xmin, xsize = b2.tables(eng)
+    results = []
+    for i, b in enumerate(batches):
+        eng.select_slot(i)
+        ptr, n = eng.device_result()
+        res = torch.empty(n, dtype=torch.float64, device="cuda")
+        eng.copy_result_to(res.data_ptr(), n)
+        results.append(res)
+    pair_batch = np.concatenate([np.full(b.n_pairs, i) for i, b in enumerate(batches)])
+    pair_local = np.concatenate([np.arange(b.n_pairs) for b in batches])
+
+    def local_pair(i):
+        b = batches[pair_batch[i]]; j = int(pair_local[i])
+        a, n = int(b.tr_off[j]), int(b.k3_tr_size[j])
+        return results[pair_batch[i]].view(sub.layout.tt2_size, b.n_units)[:, a:a + n].cpu().numpy()
+    parity = spot_check(O, sub, local_pair, rows, xmin, xsize, args.check_pairs)
+    gather = None
+    if world > 1:
+        # ragged -> padded (no gatherv): one gather per resident batch slot
+        n_slots = int(D.reduce(float(len(batches)), "max"))
+        sizes = [int(x) for x in D.all_gather_floats(float(sum(r.numel() for r in results)))]
+        n_max = int(D.reduce(float(max(r.numel() for r in results)), "max"))
+        pads = []
+        for i in range(n_slots):
+            t = torch.zeros(n_max, dtype=torch.float64, device="cuda")
+            if i < len(results):
+                t[:results[i].numel()] = results[i]
+            pads.append(t)
+        bufs = [[torch.empty(n_max, dtype=torch.float64, device="cuda") for _ in range(world)] if rank == 0 else None for _ in range(n_slots)]
+        D.dist.gather(pads[0], bufs[0], dst=0)        # untimed: the first collective builds the NCCL communicator
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.barrier()
+        g0.record()
+        for i in range(n_slots):
+            D.dist.gather(pads[i], bufs[i], dst=0)
+        g1.record()
+        D.barrier()
+        gather_ms = D.reduce(g0.elapsed_time(g1), "max")
+        gather = {"ms": gather_ms, "bytes": int(sum(sizes) * 8), "gbs": sum(sizes) * 8 / 1e9 / max(gather_ms * 1e-3, 1e-9),
+                  "api": "torch.distributed.gather over NCCL, one per resident batch slot, padded to the largest batch"}
+        if rank == 0:
+            # the gathered array in the reference pair order: check pairs owned by every rank against the oracle
+            if grids.src is None:
+                workload.fill_sources(grids)
+            tt2 = grids.layout.tt2_size
+            def gathered_pair(ip):
+                r = int(dev_of_pair[ip])
+                own_r = np.nonzero(dev_of_pair == r)[0]
+                sizes_r = grids.k3_tr_size[own_r].astype(np.int64)
+                cuts = split_bounds(sizes_r, cap)               # every rank cut its shard with the same rule
+                j = int(np.searchsorted(own_r, ip))
+                ib = int(np.searchsorted(cuts, j, side="right")) - 1
+                units_b = int(sizes_r[cuts[ib]:cuts[ib + 1]].sum())
+                a = int(sizes_r[cuts[ib]:j].sum()); n = int(sizes_r[j])
+                return bufs[ib][r][:units_b * tt2].view(tt2, units_b)[:, a:a + n].cpu().numpy()
+            gather["parity_of_gathered_array"] = spot_check(O, grids, gathered_pair, rows, xmin, xsize, max(args.check_pairs, world))
+        del bufs, pads
+    del results
+
+    # ---- roofline of the dominant kernel (the DMMA LOS kernel), this rank's shard ----
+    n_terms = count_terms(sub, xmin, xsize)
+    flops = 5.0 * n_terms + 2.0 * n_int_rank * sub.tau.size          # SURVEY.md 8(d): F = 5 N_terms + 2 N_int n_tau
+    t_kernel = kern["ms_integrate"] * 1e-3
+    achieved = flops / t_kernel / 1e12
+    peak = peaks["dmma_tflops"] if mode == MODE_FAST else peaks["dfma_tflops"]
+    alg_bytes = 8.0 * (n_int_rank + sub.src.size + sub.k3_pt.size + sub.k3_tr.size)
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "traffic_bytes.json")
+    if os.path.exists(tfile):
+        try:
+            traffic = json.load(open(tfile)).get(name, {}).get("los_tc_kernel")
+        except Exception:
+            traffic = None
+    fracs = D.all_gather_floats(achieved / peak)
+    roofline = {
+        "bound": "tensor", "kernel": "los_tc_kernel (FP64 tensor core, DMMA m8n8k4, TMA-fed)" if mode == MODE_FAST else "los_exact_kernel",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+        "peak_source": ("DMMA m8n8k4 loop" if mode == MODE_FAST else "DFMA loop") + " measured in this run with song_los_measure_peaks "
+                       "(MEASURED_PEAKS.json has no FP64 entry and the profiling guide no FP64 fallback)",
+        "algorithmic_flops_per_step": flops, "n_terms": n_terms, "kernel_ms_per_step": kern["ms_integrate"],
+        "kernel_share_of_step": kern["ms_integrate"] / max(kern["ms_total"], 1e-9),
+        "step_frac": flops / (my_ms * 1e-3) / 1e12 / peak,
+        "frac_per_rank": fracs,
+        "dfma_peak_tflops": peaks["dfma_tflops"], "dmma_peak_tflops": peaks["dmma_tflops"],
+        "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / (kern["ms_total"] * 1e-3) / 1e9,
+                "peak_gbs": peaks["copy_gbs"], "frac": alg_bytes / (kern["ms_total"] * 1e-3) / 1e9 / peaks["copy_gbs"]},
+        "step_breakdown_ms": kern, "resident_batches": len(batches), "batch_k3_values": [int(b.n_units) for b in batches],
+    }
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    D.cpu_barrier()
+
+    # ---- e2e: SONG's transfer2_init on SONG structures, all N GPUs, host buffers in and out (rank 0 drives it) ----
+    e2e = None
+    if want_e2e and rank == 0:
+        try:                                         # transfer2_init drives every GPU of the box from one process: all host cores
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        except Exception:
+            pass
+        os.environ["SONG_LOS_DEVICES"] = str(world)
+        os.environ["SONG_LOS_MODE"] = args.mode
+        if "LOCAL_RANK" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
+            os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        h = dropin_lib.Harness(grids, None, verbose=0, keep_sources=True)      # bessel2_init (drop-in) leaves the engines on the GPUs
+        if args.dropin_verbose:
+            import ctypes
+            dropin_lib.lib().harness_set_verbose.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        t_b2 = time.perf_counter() - t0
+        first_ms = None
+        for i in range(2):                                                       # warm: CUDA buffers reserved, page-locked pool filled
+            t0 = time.perf_counter(); h.transfer2_init(); dt = time.perf_counter() - t0
+            if first_ms is None:
+                first_ms = dt * 1e3
+            h.transfer2_free(); h.fill_sources()
+        t_all = 0.0; t_read = 0.0; cs = 0.0; each = []
+        for i in range(e2e_steps):
+            if args.dropin_verbose and i + 1 == e2e_steps:
+                sys.stdout.flush()
+                dropin_lib.lib().harness_set_verbose(h.h, args.dropin_verbose)      # laps of the last call on stdout (before the JSON line)
+            t0 = time.perf_counter()
+            h.transfer2_init()
+            t1 = time.perf_counter()
+            cs = h.checksum()                                                    # the step's result, read through ptr2->transfer
+            t2 = time.perf_counter()
+            t_all += t1 - t0; t_read += t2 - t1; each.append((t1 - t0) * 1e3)
+            if i + 1 < e2e_steps:
+                h.transfer2_free(); h.fill_sources()
+        got, count, labels_ok = h.read()
+        tables = h.bessel2_tables()
+        run_scale = np.abs(got).max(axis=1, keepdims=True)
+        e2e_parity = spot_check(O, grids, lambda i: got[:, int(grids.tr_off[i]):int(grids.tr_off[i]) + int(grids.k3_tr_size[i])],
+                                tables[0], tables[1], tables[2], max(args.check_pairs, 2 * world), run_scale=run_scale)
+        del got
+        h.close()
+        e2e_ms = t_all / e2e_steps * 1e3
+        h2d = int(grids.src.nbytes + grids.k3_pt.nbytes + grids.k3_tr.nbytes + (3 * 8 + 5 * 4) * grids.n_pairs)
+        d2h = int(n_int_total * 8)
+        e2e = {"value": n_int_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_ms, "ms_each_step": each, "steps": e2e_steps, "n_gpus": world,
+               "api": "transfer2_init(ppr, ppr2, pba, pth, ppt, ppt2, pbs, pbs2, ptr, ptr2) of the drop-in module on SONG structures "
+                      "(tests/harness/dropin_harness.c plays main/song.c:100-106): sources in pageable ppt2->sources, result in "
+                      "ptr2->transfer; packing, H2D, kernels and D2H of every batch inside the call; host clock around the call",
+               "first_call_ms": first_ms, "first_call_note": "includes page-locking the staging and the ptr2->transfer slabs (kept in a pool afterwards)",
+               "bessel2_init_s": t_b2, "result_read_ms_per_step": t_read / e2e_steps * 1e3, "checksum_abs_sum": cs,
+               "count_memorised_transfers": count, "labels_ok": labels_ok, "parity": e2e_parity}
+    D.cpu_barrier()
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and with_cpu:
+        grids_c, sub_c, proj_c, stride = cpu_sample(name, args.cpu_seconds, max_pairs=args.max_pairs)
+        run = O.OracleRun(sub_c, proj_c)
+        t0 = time.perf_counter(); run.run(); dt = time.perf_counter() - t0
+        cpu = {"value": sub_c.n_integrals / dt, "unit": UNIT, "cores": O.lib().oracle_num_threads(), "cpu_model": cpu_model(), "kind": "port",
+               "sample": f"every {stride}-th (k1,k2) pair, {sub_c.n_pairs} of {grids_c.n_pairs} pairs, "
+                         f"{sub_c.n_integrals} integrals, one pass of {dt:.1f} s; CPU restatement of reference transfer2 "
+                         f"(gcc -O3 -fopenmp, reference loop structure; reference not buildable here)"}
+
+    if rank != 0:
+        return None
+    return {
+        "workload": name, "value": value, "ms_per_step": ms_step, "steps": steps, "warmup": warmup,
+        "per_rank_ms": rank_ms, "imbalance_max_over_mean": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
+        "schedule_load_max_over_mean": float(load.max() / load.mean()),
+        "gpu_launches": launches_total, "describe": workload.describe(grids), "parity": parity, "gather": gather,
+        "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "setup_s": t_setup,
+        "l2_gb_streamed": (3 * sub.src.nbytes + n_int_rank * 8) / 1e9,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
-    ap.add_argument("--max-pairs", type=int, default=None, help="debug: truncate the pair list")
+    ap.add_argument("--max-pairs", type=int, default=None, help="debug: truncate the pair list (disables the transfer2_init leg)")
     ap.add_argument("--cpu-seconds", type=float, default=6.0, help="CPU time per oracle pass of the baselines")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--e2e-steps", type=int, default=5, help="timed transfer2_init calls (at most --steps)")
+    ap.add_argument("--chunks-per-rank", type=int, default=3, help="contiguous pair chunks per GPU in the static schedule")
+    ap.add_argument("--check-pairs", type=int, default=8, help="pairs checked against the CPU oracle per workload")
+    ap.add_argument("--dropin-verbose", type=int, default=0, help="debug: ptr2->transfer2_verbose of the last timed transfer2_init")
+    ap.add_argument("--extra", default="auto", help="comma list of further workloads for the `configs` array; auto: the other "
+                                                  "single-GPU BASELINE configs at N=1, configs[4] at N=8; none: skip")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -261,211 +598,72 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
-    from song_b200 import configs, workload
-    from song_b200.bessel2 import Bessel2
-    from song_b200.engine import MODE_EXACT, MODE_FAST, LosEngine
-
     args.warmup = max(args.warmup, 3)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     numa = bind_to_gpu_numa_node(local_rank)         # before any pinned allocation: page-locked buffers are first-touch local
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    mode = MODE_FAST if args.mode == "fast" else MODE_EXACT
+    D = Dist(rank, world, local_rank)
 
-    # ---- inputs: every rank owns a shard of the same shape with its own sources (weak scaling) ----
-    p = configs.get(args.workload)
-    wl = workload.build_grids(p, max_pairs=args.max_pairs)
-    workload.fill_sources(wl, seed=20261017 + 7919 * rank)
-    eng = LosEngine(wl, device=local_rank)
-    b2 = Bessel2(wl).init(eng)                      # bessel2_init: host j_l1 + 3j, device J_Llm assembly
-    cap = eng.max_batch_units(mode, wl.src.size / max(wl.n_units, 1))
-    if wl.n_units > cap:
-        raise SystemExit(f"bench.py: {args.workload} has {wl.n_units} k3 values, one resident batch holds {cap} on this GPU; "
-                         f"bench.py times configs[1]-sized workloads in one batch -- use tests/big/run_config.py {args.workload} "
-                         "for the batched end-to-end run of the larger BASELINE workloads")
-    peaks = eng.measure_peaks()
-    stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
-    wl_pin = pinned_copy(wl)
-    out_pin = torch.empty((wl.layout.tt2_size, wl.n_units), dtype=torch.float64).pin_memory()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- value: inputs resident in HBM ----
-    eng.upload(wl_pin)
-    for _ in range(args.warmup):
-        eng.compute(mode)
     sampler = ClockSampler(local_rank)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern = {"ms_integrate": 0.0, "ms_spline": 0.0, "ms_sort": 0.0, "ms_interp": 0.0, "ms_total": 0.0}
-    launches = 0
-    barrier()
-    sampler.start()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        tm = eng.compute(mode)
-        for k in kern:
-            kern[k] += tm[k]
-        launches += tm["n_launches"]
-    ev1.record(stream)
-    barrier()
-    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
-    for k in kern:
-        kern[k] /= args.steps
-    n_int_rank = wl.n_integrals
-    n_int_total = n_int_rank * world
-    value = n_int_total / (ms_step * 1e-3)
+    main_res = measure_workload(args.workload, args, D, args.steps, args.warmup, min(args.e2e_steps, args.steps),
+                                with_cpu=(world == 1 and not args.no_cpu_baseline), sampler=sampler)
+    clocks = sampler.stop()          # sampled from the start of the timed `value` region to the end of the e2e region, 50 ms period
 
-    # ---- e2e: host (pinned) buffers through the C-ABI, H2D + D2H inside the timed region ----
-    # (a) the synchronous call, one batch at a time: song_los_transfer_pairs
-    # (b) the pipeline a SONG run uses for its k1 batches: song_los_submit / song_los_wait with three
-    #     batches in flight, so that the copies of neighbouring steps overlap the kernels.  Every step
-    #     still copies all of its inputs to the device and its whole result back; the region is
-    #     bracketed by device-wide synchronisation and timed on the host clock (three streams).
-    from song_b200.engine import PinnedArray
-    DEPTH = max(1, min(3, int(os.environ.get("SONG_BENCH_DEPTH", "3"))))     # batches in flight (SONG_LOS_MAX_IN_FLIGHT = 3)
-    outs = [PinnedArray((wl.layout.tt2_size, wl.n_units)) for _ in range(DEPTH)]
-    out_np = outs[0].array
-    eng.transfer_pairs(wl_pin, mode=mode, out=out_np)          # warm
-    barrier()
-    t_host0 = time.perf_counter()
-    n_sync = min(args.steps, 3)
-    for _ in range(n_sync):
-        eng.transfer_pairs(wl_pin, mode=mode, out=out_np)
-    torch.cuda.synchronize()
-    sync_ms = max_over_ranks((time.perf_counter() - t_host0) * 1e3 / n_sync)
-    checksum = float(np.abs(out_np).sum())
-    for i in range(DEPTH):                                      # warm every slot
-        eng.submit(wl_pin, mode, outs[i].array)
-    for i in range(DEPTH):
-        eng.wait()
-    barrier()
-    t_host0 = time.perf_counter()
-    copy_ms = {"h2d": 0.0, "d2h": 0.0}
-    for i in range(args.steps):
-        eng.submit(wl_pin, mode, outs[i % DEPTH].array)
-        if i >= DEPTH - 1:
-            tm = eng.wait(); copy_ms["h2d"] += tm["ms_h2d"]; copy_ms["d2h"] += tm["ms_d2h"]
-    for i in range(min(DEPTH - 1, args.steps)):
-        tm = eng.wait(); copy_ms["h2d"] += tm["ms_h2d"]; copy_ms["d2h"] += tm["ms_d2h"]
-    torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t_host0) * 1e3 / args.steps)
-    clocks = sampler.stop()          # sampled over both timed regions (value and e2e), 50 ms period
-    if world > 1:
-        dist.barrier()
-    h2d = int(wl.src.nbytes + wl.k3_pt.nbytes + wl.k3_tr.nbytes + (3 * 8 + 5 * 4) * wl.n_pairs)
-    d2h = int(out_np.nbytes)
-    e2e_value = n_int_total / (e2e_ms * 1e-3)
-    checksum_pipe = float(np.abs(outs[(args.steps - 1) % DEPTH].array).sum())
-    if checksum_pipe != checksum:
-        raise SystemExit(f"bench.py: pipelined result differs from the synchronous one ({checksum_pipe} vs {checksum})")
-
-    # ---- multi-GPU: the one collective of the path, the gather of the per-GPU transfer arrays ----
-    gather_ms = None
-    if world > 1:
-        res = torch.empty(wl.layout.tt2_size * wl.n_units, dtype=torch.float64, device="cuda")
-        eng.copy_result_to(res.data_ptr(), res.numel())
-        bufs = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dist.gather(res, bufs, dst=0)                 # untimed: the first collective builds the NCCL communicator
-        barrier()
-        g0.record()
-        dist.gather(res, bufs, dst=0)
-        g1.record()
-        barrier()
-        gather_ms = max_over_ranks(g0.elapsed_time(g1))
-
-    # ---- roofline of the dominant kernel (the DMMA LOS kernel) ----
-    rows, xmin, xsize = None, None, None
-    lay = wl.layout
-    n_j = lay.J_size * lay.L_size * lay.l_size * lay.m_size
-    xmin = np.zeros(n_j, dtype=np.int32); xsize = np.zeros(n_j, dtype=np.int32)
-    from song_b200 import _lib
-    _lib.los().song_los_get_projection(eng.ctx, _lib.iptr(xmin), _lib.iptr(xsize), None)
-    n_terms = count_terms(wl, xmin, xsize)
-    flops = 5.0 * n_terms + 2.0 * n_int_rank * wl.tau.size          # F = 5 N_terms + 2 N_int n_tau
-    t_kernel = kern["ms_integrate"] * 1e-3
-    achieved = flops / t_kernel / 1e12
-    peak = max(peaks["dmma_tflops"], peaks["dfma_tflops"])
-    alg_bytes = 8.0 * (n_int_rank + wl.src.size + wl.k3_pt.size + wl.k3_tr.size)
-    traffic = None
-    tfile = os.path.join(ROOT, "profiles", "traffic_bytes.json")
-    if os.path.exists(tfile):
-        try:
-            traffic = json.load(open(tfile)).get(args.workload, {}).get("los_tc_kernel")
-        except Exception:
-            traffic = None
-    roofline = {
-        "bound": "tensor", "kernel": "los_tc_kernel (FP64 tensor core, DMMA m8n8k4, TMA-fed)" if mode == MODE_FAST else "los_exact_kernel",
-        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-        "peak_source": "measured in this run with song_los_measure_peaks (DMMA m8n8k4 loop; MEASURED_PEAKS.json has no FP64 entry)",
-        "algorithmic_flops_per_launch": flops, "n_terms": n_terms, "kernel_ms": kern["ms_integrate"],
-        "kernel_share_of_step": kern["ms_integrate"] / max(kern["ms_total"], 1e-9),
-        "dfma_peak_tflops": peaks["dfma_tflops"], "dmma_peak_tflops": peaks["dmma_tflops"],
-        "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / (kern["ms_total"] * 1e-3) / 1e9,
-                "peak_gbs": peaks["copy_gbs"], "frac": alg_bytes / (kern["ms_total"] * 1e-3) / 1e9 / peaks["copy_gbs"]},
-        "step_breakdown_ms": kern,
-    }
-
-    # ---- CPU baseline beside it (rank 0, N=1 only) ----
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import oracle_lib as O
-        grids, sub, proj, stride = cpu_sample(args.workload, args.cpu_seconds, max_pairs=args.max_pairs)
-        run = O.OracleRun(sub, proj)
-        t0 = time.perf_counter(); ref, _ = run.run(); dt = time.perf_counter() - t0
-        cpu = {"value": sub.n_integrals / dt, "unit": UNIT, "cores": O.lib().oracle_num_threads(), "kind": "port",
-               "sample": f"every {stride}-th (k1,k2) pair, {sub.n_pairs} of {grids.n_pairs} pairs, "
-                         f"{sub.n_integrals} integrals, one pass of {dt:.1f} s; CPU restatement of reference transfer2 "
-                         f"(gcc -O3 -fopenmp, reference loop structure; reference not buildable here)"}
+    extras = []
+    if args.extra == "auto":
+        names = []
+        if args.workload == DEFAULT_WORKLOAD and args.max_pairs is None:
+            if world == 1:
+                names = ["quick_song_run", "sn_t_10percent_lmax2000", "sn_pol_10percent_lmax2000"]
+            elif world == 8:
+                names = ["sn_pol_5percent_lmax4000"]
+    elif args.extra in ("none", ""):
+        names = []
+    else:
+        names = [n for n in args.extra.split(",") if n]
+    for n in names:
+        big = n.startswith("sn_pol_5percent")
+        r = measure_workload(n, args, D, steps=3 if big else 5, warmup=3, e2e_steps=0 if n == "sn_pol_5percent_lmax4000" else 3,
+                             with_cpu=False)
+        if rank == 0:
+            extras.append({"workload": n, "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "steps": r["steps"],
+                           "n_gpus": world, "integrals": r["describe"]["integrals"], "parity": r["parity"],
+                           "gather": r["gather"], "imbalance_max_over_mean": r["imbalance_max_over_mean"],
+                           "roofline": {k: r["roofline"][k] for k in ("achieved", "peak", "unit", "frac", "step_frac", "kernel_ms_per_step",
+                                                                      "kernel_share_of_step", "resident_batches", "frac_per_rank")},
+                           "e2e": None if r["e2e"] is None else {k: r["e2e"][k] for k in ("value", "ms_per_step", "ms_each_step", "steps", "first_call_ms", "parity",
+                                                                                          "h2d_bytes_per_step", "d2h_bytes_per_step")}})
 
     if rank == 0:
+        r = main_res
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(workload.describe(wl), workload=args.workload, mode=args.mode,
-                           per_gpu_integrals=n_int_rank, parallelism=f"(k1,k2)-pair shards x{world}, no data-path collective",
-                           l2_policy="inputs larger than L2: each step streams ~%.1f GB (sources, transposed sources, "
-                                     "projection table, output) against 126 MB of L2" %
-                                     ((3 * wl.src.nbytes + out_np.nbytes) / 1e9),
+            "config": dict(r["describe"], workload=args.workload, mode=args.mode,
+                           parallelism=f"ONE workload split by (k1,k2) pair over {world} GPU(s): static schedule of song_host_schedule_pairs "
+                                       f"({args.chunks_per_rank if world > 1 else 1} contiguous chunk(s) per GPU, LPT), no data-path collective; results gathered on rank 0",
+                           l2_policy="inputs larger than L2: each step streams ~%.1f GB per GPU (sources, transposed sources, "
+                                     "interpolated slab, projection table, output) against 126 MB of L2" % r["l2_gb_streamed"],
                            tau_sampling="synthetic, geometric 230->330 then linear ->700 Mpc",
                            cpu_affinity=numa),
+            "per_rank_ms": r["per_rank_ms"], "imbalance": r["imbalance_max_over_mean"],
+            "schedule_load_max_over_mean": r["schedule_load_max_over_mean"],
+            "parity": r["parity"],
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "checksum_abs_sum": checksum,
-                    "api": f"song_los_submit/song_los_wait, up to {DEPTH} batches in flight (copy-in, kernels, copy-out), pinned host buffers; every step copies "
-                           "its inputs H2D and its result D2H; host clock between device-wide synchronisations",
-                    "h2d_ms_per_step": copy_ms["h2d"] / args.steps, "d2h_ms_per_step": copy_ms["d2h"] / args.steps,
-                    "h2d_gbs": h2d / 1e9 / max(copy_ms["h2d"] / args.steps * 1e-3, 1e-12),
-                    "d2h_gbs": d2h / 1e9 / max(copy_ms["d2h"] / args.steps * 1e-3, 1e-12),
-                    "sync_call": {"value": n_int_total / (sync_ms * 1e-3), "ms_per_step": sync_ms,
-                                  "api": "song_los_transfer_pairs (upload, kernels, download back to back)"}},
-            "gpu_launches": launches,
-            "roofline": roofline,
-            "cpu_baseline": cpu,
+            "e2e": r["e2e"] if r["e2e"] is not None else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                                          "unavailable": "transfer2_init leg needs libsong_transfer2.so and the full pair list"},
+            "gpu_launches": r["gpu_launches"],
+            "roofline": r["roofline"],
+            "cpu_baseline": r["cpu_baseline"],
+            "configs": extras,
         }
-        if gather_ms is not None:
-            line["nccl_gather_ms"] = gather_ms
+        if r["gather"] is not None:
+            line["nccl_gather"] = r["gather"]
+            line["nccl_gather_ms"] = r["gather"]["ms"]
         print(json.dumps(line), flush=True)
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 if __name__ == "__main__":

@@ -121,6 +121,10 @@ class LosEngine:
                                                      _lib.iptr(proj.index_xmin), _lib.iptr(proj.x_size)))
 
     # -- batches ---------------------------------------------------------------------------
+    def select_slot(self, slot: int):
+        """Which of the three resident batch slots upload / compute / download work on."""
+        self._check(self.lib.song_los_select_slot(self.ctx, int(slot)))
+
     def upload(self, wl: Workload):
         b = make_batch(wl)
         self._check(self.lib.song_los_upload_pairs(self.ctx, C.byref(b)))

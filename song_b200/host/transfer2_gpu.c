@@ -470,7 +470,17 @@ typedef struct {
   int *pairs_to_pack;                      /* per k1 level: pairs whose sources have not been packed yet (-> perturb2_free_k1_level) */
   int mode, host_threads, sources_on_disk, store_to_disk;
   int next_level_to_load, next_level_to_store;   /* ordered runs (one GPU, batches in k1 order) */
+  double t_start;                                /* transfer2_verbose > 2: lap times of every batch */
 } los_run;
+
+static double los_now(void)
+{
+#ifdef _OPENMP
+  return omp_get_wtime();
+#else
+  return 0.;
+#endif
+}
 
 /* packs the pairs of `pb` into the staging and enqueues the batch on the GPU (song_los_submit): the kernels' result goes
    straight to the batch's slab of ptr2->transfer */
@@ -479,6 +489,7 @@ static int submit_batch(los_run *R, song_los_ctx *ctx, los_pair_batch *pb, los_s
   struct perturbs2 *ppt2 = R->ppt2; struct transfers2 *ptr2 = R->ptr2;
   const int tp2 = ppt2->tp2_size, ntau = ppt2->tau_size;
   const int k1a = R->pair_k1[pb->p_first], k1b = R->pair_k1[pb->p_last];
+  const double t0 = los_now();
 
   /* sources kept on disk arrive one k1 level at a time (transfer2.c:332-344) */
   if (R->sources_on_disk)
@@ -493,6 +504,7 @@ static int submit_batch(los_run *R, song_los_ctx *ctx, los_pair_batch *pb, los_s
     snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); return _FAILURE_;
   }
 
+  const double t1 = los_now();
   /* sizes and offsets first (serial), then every pair is packed independently by the host threads of this GPU */
   s->n_pairs = pb->p_last - pb->p_first + 1;
   int64_t o_pt = 0, o_tr = 0, o_src = 0;
@@ -519,6 +531,7 @@ static int submit_batch(los_run *R, song_los_ctx *ctx, los_pair_batch *pb, los_s
   }
   if (failed) { snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); return _FAILURE_; }
 
+  const double t2 = los_now();
   song_los_batch b;
   memset(&b, 0, sizeof b);
   b.n_pairs = s->n_pairs; b.k3_pt_size = s->np; b.k3_tr_size = s->nt; b.phys_start = s->ps; b.phys_size = s->pz;
@@ -529,6 +542,10 @@ static int submit_batch(los_run *R, song_los_ctx *ctx, los_pair_batch *pb, los_s
     snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(ctx)); return _FAILURE_;
   }
   s->pb = pb;
+  if (ptr2->transfer2_verbose > 2)
+    printf("       GPU %d batch of %ld k3 values: allocate %.2f ms, pack %.2f ms (%.1f GB/s), submit %.2f ms; submitted at %.1f ms\n",
+           pb->device, (long)pb->n_units, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (double)o_src * 8e-9 / (t2 - t1 > 0 ? t2 - t1 : 1), (los_now() - t2) * 1e3,
+           (los_now() - R->t_start) * 1e3);
 
   /* the sources of these pairs now live in the staging: a k1 level whose last pair has been packed is freed as the
      reference does after its k2 loop (transfer2.c:553) */
@@ -554,9 +571,14 @@ static int finish_batch(los_run *R, song_los_ctx *ctx, los_staging *s, char *err
   struct transfers2 *ptr2 = R->ptr2;
   const los_pair_batch *pb = s->pb;
   s->pb = NULL;
-  if (song_los_wait(ctx, NULL) != SONG_LOS_SUCCESS) {
+  const double t0 = los_now();
+  song_los_timing tm;
+  if (song_los_wait(ctx, &tm) != SONG_LOS_SUCCESS) {
     snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(ctx)); return _FAILURE_;
   }
+  if (ptr2->transfer2_verbose > 2)
+    printf("       GPU %d batch of %ld k3 values done at %.1f ms (waited %.2f ms): h2d %.2f ms, kernels %.2f ms (LOS %.2f), d2h %.2f ms\n",
+           pb->device, (long)pb->n_units, (los_now() - R->t_start) * 1e3, (los_now() - t0) * 1e3, tm.ms_h2d, tm.ms_total, tm.ms_integrate, tm.ms_d2h);
   const long int stored = (long int)pb->n_units * ptr2->tt2_size;
   #pragma omp atomic
   ptr2->count_memorised_transfers += stored;                                    /* transfer2.c:2110-2111 */
@@ -693,6 +715,10 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   los_run R;
   memset(&R, 0, sizeof R);
   R.ppr = ppr; R.ppr2 = ppr2; R.ppt2 = ppt2; R.pbs = pbs; R.pbs2 = pbs2; R.ptr2 = ptr2;
+  R.t_start = los_now();
+#ifdef _OPENMP
+  R.t_start = t_start;
+#endif
   R.mode = mode; R.sources_on_disk = sources_on_disk; R.store_to_disk = (ppr2->store_transfers_to_disk == _TRUE_);
   R.n_pairs = ppt2->k_size * (ppt2->k_size + 1) / 2;
   int64_t *cost; int *device_of_pair;
@@ -771,10 +797,11 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   /* Per GPU: a pipeline of up to SONG_LOS_MAX_IN_FLIGHT batches.  While the kernels of batch n run, the host packs batch
      n+1 into the next staging and submits it (its host->device copy overlaps), and the result of batch n-1 travels
      back into ptr2->transfer.  Host threads per GPU for the packing: SONG_LOS_HOST_THREADS (default: an even share of
-     the processors). */
+     the processors minus one -- with every processor packing, the driver's own threads are descheduled and the call
+     time becomes erratic: measured 37 ms with 8 of 16, 37-98 ms with 16 of 16 at configs[1]). */
   int host_threads = env_int("SONG_LOS_HOST_THREADS", 0);
 #ifdef _OPENMP
-  if (host_threads <= 0) host_threads = omp_get_num_procs() / (n_dev > 0 ? n_dev : 1);
+  if (host_threads <= 0) host_threads = omp_get_num_procs() / (n_dev > 0 ? n_dev : 1) - 1;   /* one processor per GPU is left to the CUDA driver's threads */
   if (n_dev > 1) omp_set_max_active_levels(2);
 #endif
   if (host_threads < 1) host_threads = 1;

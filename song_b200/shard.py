@@ -29,9 +29,22 @@ def pair_cost(wl) -> np.ndarray:
     return wl.k3_tr_size.astype(np.int64) * lay.tt2_size * int(wl.tau.size) * lay.L_size
 
 
-def shard_pairs(wl, rank: int, world: int) -> np.ndarray:
-    """Indices (ascending, i.e. reference loop order) of the pairs rank `rank` owns."""
-    dev, _ = lpt_schedule(pair_cost(wl), world)
+def schedule_pairs(cost, n_ranks: int, chunks_per_rank: int = 3):
+    """The static multi-GPU schedule of the drop-in (C: song_host_schedule_pairs, the function transfer2_init calls):
+    the pair sequence in reference order is cut into n_ranks * chunks_per_rank contiguous chunks of about equal cost,
+    the chunks are assigned by LPT.  Returns (rank of every pair, per-rank load)."""
+    cost = np.ascontiguousarray(cost, dtype=np.int64)
+    dev = np.zeros(cost.size, dtype=np.int32)
+    load = np.zeros(n_ranks, dtype=np.int64)
+    if _lib.host().song_host_schedule_pairs(_lib.lptr(cost), int(cost.size), int(n_ranks), int(chunks_per_rank),
+                                            _lib.iptr(dev), _lib.lptr(load)):
+        raise _lib.SongLosError("song_host_schedule_pairs: bad arguments")
+    return dev, load
+
+
+def shard_pairs(wl, rank: int, world: int, chunks_per_rank: int = 3) -> np.ndarray:
+    """Indices (ascending, i.e. reference loop order) of the pairs rank `rank` owns: a few contiguous runs."""
+    dev, _ = schedule_pairs(pair_cost(wl), world, chunks_per_rank if world > 1 else 1)
     return np.nonzero(dev == rank)[0]
 
 

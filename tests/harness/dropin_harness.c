@@ -337,6 +337,7 @@ int harness_bessel2_convolution(harness *h, double *kk, double *delta_kk, int k_
   return bessel2_convolution(&h->pr, &h->bs2, kk, delta_kk, k_size, f, g, index_l1, r, integral, msg) == _FAILURE_;
 }
 
+void harness_set_verbose(harness *h, int verbose) { h->tr2.transfer2_verbose = verbose; }
 const struct bessels2 *harness_bessels2(harness *h) { return &h->bs2; }
 int harness_l1_info(harness *h, int *l1, double *x_min_l1) { for (int i = 0; i < h->bs2.l1_size; ++i) { l1[i] = h->bs2.l1[i]; x_min_l1[i] = h->bs2.x_min_l1[i]; } return h->bs2.l1_size; }
 

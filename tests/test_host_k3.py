@@ -33,6 +33,20 @@ def test_grids_bit_identical_to_oracle(oracle, params):
         assert info.k_min == wl.k_min_tr[i] and info.k_max == wl.k_max_tr[i]
 
 
+@pytest.mark.parametrize("name", ["sn_t_10percent_lmax2000", "sn_pol_5percent_lmax3000", "sn_pol_5percent_lmax4000"])
+def test_baseline_grids_bit_identical_to_oracle(oracle, name):
+    """Every (k1,k2) pair of the BASELINE workloads (configs[2] shares the grids of configs[1]): the k3 grids the GPU
+    parity tests feed to the oracle come from los_host.c, so they are compared here with the oracle's own
+    transfer2_get_k3_size / _list restatement."""
+    wl, infos, k3 = both(oracle, configs.get(name))
+    assert np.array_equal(k3, wl.k3_tr)
+    assert np.array_equal(np.array([i.k_size for i in infos]), wl.k3_tr_size)
+    assert np.array_equal(np.array([i.k_physical_start for i in infos]), wl.phys_start)
+    assert np.array_equal(np.array([i.k_physical_size for i in infos]), wl.phys_size)
+    assert np.array_equal(np.array([i.k_min for i in infos]), wl.k_min_tr)
+    assert np.array_equal(np.array([i.k_max for i in infos]), wl.k_max_tr)
+
+
 def test_grid_invariants_quick_song_run():
     wl = workload.build_grids(configs.get("quick_song_run"))
     assert wl.n_pairs == 253 and wl.n_units == 20441          # SURVEY.md 8 table

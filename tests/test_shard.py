@@ -30,11 +30,29 @@ def test_lpt_schedule_properties():
             assert np.unique(dev).size == nd
 
 
+def test_pair_schedule_properties():
+    """song_host_schedule_pairs: contiguous chunks of about equal cost, LPT over the chunks."""
+    rng = np.random.default_rng(11)
+    for n, nd, cpd in ((1, 1, 1), (7, 3, 2), (253, 8, 3), (7260, 8, 3), (7260, 8, 1), (3, 8, 3), (40, 4, 16)):
+        cost = rng.integers(1, 2000, size=n)
+        dev, load = shard.schedule_pairs(cost, nd, cpd)
+        assert dev.min() >= 0 and dev.max() < nd
+        assert np.array_equal(load, np.bincount(dev, weights=cost, minlength=nd).astype(np.int64))
+        runs = 1 + int(np.count_nonzero(np.diff(dev)))          # contiguous runs of one rank
+        assert runs <= min(n, nd * cpd)
+        if n >= nd * cpd * 20:
+            assert load.max() / load.mean() < 1.05
+        dev2, _ = shard.schedule_pairs(cost, nd, cpd)
+        assert np.array_equal(dev, dev2)
+
+
 def test_lpt_balance_on_baseline_workload():
     """configs[1] split over 8 GPUs by pair: the north_star asks for >= 85 % scaling efficiency; the static
     schedule itself must not cost more than a per cent."""
     wl = workload.build_grids(configs.get("sn_t_10percent_lmax2000"))
     dev, load = shard.lpt_schedule(shard.pair_cost(wl), 8)
+    assert load.max() / load.mean() < 1.01
+    dev, load = shard.schedule_pairs(shard.pair_cost(wl), 8, 3)     # the schedule transfer2_init and bench.py use
     assert load.max() / load.mean() < 1.01
     own = [shard.shard_pairs(wl, r, 8) for r in range(8)]
     assert sum(o.size for o in own) == wl.n_pairs and np.array_equal(np.sort(np.concatenate(own)), np.arange(wl.n_pairs))
