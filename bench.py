@@ -414,6 +414,36 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
         a, n = int(b.tr_off[j]), int(b.k3_tr_size[j])
         return results[pair_batch[i]].view(sub.layout.tt2_size, b.n_units)[:, a:a + n].cpu().numpy()
     parity = spot_check(O, sub, local_pair, rows, xmin, xsize, args.check_pairs)
+    # ---- the k3 integral of the intrinsic bispectrum on the transfer functions still in HBM ----
+    k3int = None
+    if args.k3_integral and rank == 0:
+        ht = b2.host_tables()
+        eng.set_bessel_table(ht["j_l1"], ht["x_min_l1"])
+        lay = sub.layout
+        index_l1 = {int(l1): i for i, l1 in enumerate(ht["l1"])}
+        c0 = sub.cosmo["tau0"] - sub.cosmo["tau_rec"]
+        r_size = {"sn_t_10percent_lmax2000": 75, "sn_pol_10percent_lmax2000": 75, "quick_song_run": 50}.get(name, 125)   # r_size of the .pre files
+        r_arr = np.linspace(c0 - 400.0, c0 + 250.0, r_size)
+        bases = ([lay.index_tt2_T] if lay.has_source_T else []) + ([lay.index_tt2_E] if lay.has_source_E else [])
+        tts = np.asarray([bs + int(lay.lm_array[il, 0]) for bs in bases for il in range(lay.l_size)])
+        rws = np.asarray([index_l1[int(l3)] for _ in bases for l3 in lay.l])
+        ms_k3 = 0.0; out_bytes = 0; ok_k3 = True; n_k3 = 0
+        for i, b in enumerate(batches):
+            eng.select_slot(i)
+            I = eng.integrate_k3(tts, rws, r_arr, b.n_pairs)            # [tt][r][pair] of this batch
+            ms_k3 += eng.k3_ms; out_bytes += I.nbytes; n_k3 += I.size
+            if i == 0:                                                    # bitwise against the oracle loop on the same T
+                T_dev = results[0].view(lay.tt2_size, b.n_units)
+                for q in (0, len(tts) // 2, len(tts) - 1):
+                    ref = O.integral_over_k3(b, T_dev[int(tts[q])].cpu().numpy(), ht["j_l1"][int(rws[q])], None, ht["x_min_l1"][int(rws[q])], r_arr)
+                    ok_k3 = ok_k3 and bool(np.array_equal(I[q], ref))
+            del I
+        k3int = {"kernel_ms": ms_k3, "integrals": int(n_k3), "r_size": int(r_size), "requests": int(tts.size),
+                 "k3_terms": int(sub.n_units) * int(tts.size) * int(r_size),
+                 "result_bytes": int(out_bytes), "transfer_bytes_replaced": int(n_int_rank * 8),
+                 "bitwise_equal_to_oracle": ok_k3,
+                 "api": "song_los_integrate_k3 on the resident result of every batch (bispectra2.c:1107-1439, bessel2.c:499-605); "
+                        "rank 0's shard; the result a consumer copies to the host shrinks from transfer_bytes_replaced to result_bytes"}
     gather = None
     if world > 1:
         # ragged -> padded (no gatherv): one gather per resident batch slot
@@ -565,7 +595,7 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
         "per_rank_ms": rank_ms, "imbalance_max_over_mean": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
         "schedule_load_max_over_mean": float(load.max() / load.mean()),
         "gpu_launches": launches_total, "describe": workload.describe(grids), "parity": parity, "gather": gather,
-        "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "setup_s": t_setup,
+        "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "setup_s": t_setup, "k3_integral": k3int,
         "l2_gb_streamed": (3 * sub.src.nbytes + n_int_rank * 8) / 1e9,
     }
 
@@ -584,6 +614,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5, help="timed transfer2_init calls (at most --steps)")
     ap.add_argument("--chunks-per-rank", type=int, default=3, help="contiguous pair chunks per GPU in the static schedule")
     ap.add_argument("--check-pairs", type=int, default=8, help="pairs checked against the CPU oracle per workload")
+    ap.add_argument("--no-k3-integral", dest="k3_integral", action="store_false", help="skip the bispectrum k3-integral leg (SURVEY 8f rank 1)")
     ap.add_argument("--dropin-verbose", type=int, default=0, help="debug: ptr2->transfer2_verbose of the last timed transfer2_init")
     ap.add_argument("--extra", default="auto", help="comma list of further workloads for the `configs` array; auto: the other "
                                                   "single-GPU BASELINE configs at N=1, configs[4] at N=8; none: skip")
@@ -657,6 +688,7 @@ def main():
             "gpu_launches": r["gpu_launches"],
             "roofline": r["roofline"],
             "cpu_baseline": r["cpu_baseline"],
+            "k3_integral": r["k3_integral"],
             "configs": extras,
         }
         if r["gather"] is not None:

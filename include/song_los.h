@@ -43,6 +43,9 @@
  *                              create the engines and transfer2_init reuse them with their tables in place
  *   song_los_drop_projection_rows   frees the device copy of pbs2->J_Llm_x once bessel2_init has read it back
  *   song_los_select_slot       which of the three batch slots the synchronous calls use (several batches resident)
+ *   song_los_set_bessel_table / song_los_integrate_k3   the k3 integral of bispectra2_intrinsic_integrate_over_k3
+ *                              (bispectra2.c:1279-1375 with bessel2_convolution, bessel2.c:499-605) on the transfer
+ *                              functions still in device memory
  *
  * Error convention (reference: _SUCCESS_/_FAILURE_ + ErrorMsg): every function
  * returns SONG_LOS_SUCCESS (0) or SONG_LOS_FAILURE (1); the text is available from
@@ -250,6 +253,28 @@ uint64_t song_los_device_result(song_los_ctx *ctx, int64_t *n_doubles);
 /* Copies the result of the last compute into caller-owned DEVICE memory (device-to-device, on the
    engine's stream, synchronised before returning): the hand-off to an NCCL gather. */
 int  song_los_copy_result(song_los_ctx *ctx, uint64_t device_dst, int64_t n_doubles);
+
+/* ---- the k3 integral of the intrinsic bispectrum on the device ----
+ * bispectra2_intrinsic_integrate_over_k3 (source/bispectra2.c:1107-1439) integrates every T_l3,M3(k1,k2,k3) over k3
+ * against j_L3(k3 r) with bessel2_convolution (source/bessel2.c:499-605).  song_los_integrate_k3 does that on the
+ * transfer functions song_los_compute left in device memory (current slot), for the pairs of that batch:
+ *     out[q][index_r][pair] = 2 * M3_coefficient[q] * 1/2 sum_k3 delta_k3 k3^2 T_tt[q](pair, k3) j_{l1[index_l1[q]]}(k3 r)
+ * (the coefficient is applied only when abs_M3 != 0, bispectra2.c:1369; delta_k3 = trapezoidal measure of the pair's
+ * own k3 grid, :1279-1284).  Bit-identical to the reference's statement order. */
+typedef struct song_los_k3_request {
+  int n_requests;                  /* (l3, M3) combinations */
+  const int *tt;                   /* index_tt2_k3 + ptr2->lm_array[index_l3][index_M3]            [n_requests] */
+  const int *index_l1;             /* pbs2->index_l1[L3], L3 = |l3 - |M3|| + offset_L3 (:1183,1200) [n_requests] */
+  int abs_M3;                      /* pwb->abs_M3 */
+  const double *M3_coefficient;    /* pwb->M3_coefficient[index_M3] per request; may be NULL when abs_M3 == 0 */
+  int r_size; const double *r;     /* pwb->r */
+} song_los_k3_request;
+
+/* pbs2->j_l1 (and ddj_l1 for cubic Bessel interpolation), x_min_l1, x_size_l1 of bessel2_init (bessel2.h:96-106). */
+int  song_los_set_bessel_table(song_los_ctx *ctx, int l1_size, const double *const *j_l1, const double *const *ddj_l1,
+                               const double *x_min_l1, const int *x_size_l1);
+int  song_los_integrate_k3(song_los_ctx *ctx, const song_los_k3_request *request, double *out /* [n_requests][r_size][n_pairs] */);
+float song_los_last_k3_ms(const song_los_ctx *ctx);   /* device time of the last song_los_integrate_k3 kernel */
 
 /* Runs the engine's kernels on an external CUDA stream (a cudaStream_t passed as void*),
    so that a caller's own events see the work.  NULL restores the engine's stream. */

@@ -144,6 +144,11 @@ int oracle_bessel2_convolution(const double *kk, const double *delta_kk, int k_s
                                const double *j, const double *ddj, double x_min_l1, double xx_step, int cubic, double r,
                                double *integral);
 
+/* bispectra2.c:1107-1439 (bispectra2_intrinsic_integrate_over_k3), one (l3, M3): out[index_r * n_pairs + pair] */
+int oracle_integral_over_k3(int n_pairs, const int *k3_size, const long *tr_off, const double *k3_tr, const double *transfer,
+                            const double *j, const double *ddj, double x_min_l1, double xx_step, int cubic,
+                            int r_size, const double *r, int abs_M3, double M3_coefficient, double *out);
+
 /* ---------------------------------------------------------------------------------------
  * transfer2.c restatement
  * ------------------------------------------------------------------------------------- */

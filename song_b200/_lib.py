@@ -96,6 +96,12 @@ class LosTiming(C.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+class K3Request(C.Structure):
+    """struct song_los_k3_request (include/song_los.h)."""
+    _fields_ = [("n_requests", C.c_int), ("tt", c_int_p), ("index_l1", c_int_p), ("abs_M3", C.c_int),
+                ("M3_coefficient", c_double_p), ("r_size", C.c_int), ("r", c_double_p)]
+
+
 class K3Params(C.Structure):
     _fields_ = [
         ("tau0", C.c_double), ("tau_rec", C.c_double), ("rs_rec", C.c_double),
@@ -141,7 +147,7 @@ LOS_SYMBOLS = [
     "song_los_device_info", "song_los_version",
     "song_los_submit", "song_los_wait", "song_los_host_alloc", "song_los_host_free", "song_los_max_batch_units", "song_los_reserve", "song_los_get_projection_dd",
     "song_los_device_count", "song_los_set_time", "song_los_config_matches", "song_los_drop_projection_rows",
-    "song_los_select_slot",
+    "song_los_select_slot", "song_los_set_bessel_table", "song_los_integrate_k3", "song_los_last_k3_ms",
 ]
 HOST_SYMBOLS = ["song_host_k3_size", "song_host_k3_list", "song_host_k3_sizes", "song_host_k3_lists",
                 "song_host_bessel2_prepare", "song_host_bessel2_free", "song_host_bessel2_upload",
@@ -193,6 +199,10 @@ def los():
         lib.song_los_config_matches.argtypes = [vp, C.POINTER(LosConfig)]
         lib.song_los_drop_projection_rows.argtypes = [vp]
         lib.song_los_select_slot.argtypes = [vp, C.c_int]
+        lib.song_los_set_bessel_table.argtypes = [vp, C.c_int, C.POINTER(c_double_p), C.POINTER(c_double_p), c_double_p, c_int_p]
+        lib.song_los_integrate_k3.argtypes = [vp, C.POINTER(K3Request), c_double_p]
+        lib.song_los_last_k3_ms.argtypes = [vp]
+        lib.song_los_last_k3_ms.restype = C.c_float
         _los = lib
     return _los
 

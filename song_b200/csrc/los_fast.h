@@ -22,6 +22,7 @@ struct FastHostLayout {
   int64_t n_pt_total;                   // coarse k3 points of the batch
   int max_np;                           // longest coarse k3 grid of the batch
   int xx_uniform; double xx_delta;      // xx[i] == i*xx_delta bit for bit (bessel2_get_xx_list's lin_space from 0)
+  double rows_spanned;                  // table rows the batch's k3 range covers at a mid-run tau (k3 density = n_units / rows)
 };
 
 struct FastState;

@@ -36,6 +36,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -1053,7 +1054,8 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
   else if (max_sb <= 10) { fs->wm = 12; fs->wn = 1; fs->nw = 10; }
   else if (max_sb <= 16) { fs->wm = 4; fs->wn = 2; fs->nw = 8; }
   else if (max_sb <= 20) { fs->wm = 4; fs->wn = 2; fs->nw = 10; }
-  else if (max_sb <= 21) { fs->wm = 4; fs->wn = 3; fs->nw = 7; }
+  else if (max_sb <= 21) { fs->wm = 12; fs->wn = 1; fs->nw = 7; }    // three column passes of 7: 1367 ms vs 1411 ms with (4,3,7) in one pass
+                                                                      // on the full lmax3000 run, 287 vs 326 ms on its 1/8 shard (round 2)
   else if (max_sb <= 32) { fs->wm = 4; fs->wn = 2; fs->nw = 8; }     // two column passes: 731 ms vs 855 ms with (2,4,8) on the lmax4000 shard
   else { fs->wm = 2; fs->wn = 4; fs->nw = 10; }
   if (const char *v = getenv("SONG_LOS_TC_SHAPE")) {          // A/B measurements: "wm,wn,nw"
@@ -1209,7 +1211,49 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
   const int tau_size = P.tm.tau_size, tp2 = P.ty.tp2_size;
   const int64_t rowlen = (int64_t)tau_size * tp2;
   if (U >= (int64_t)1 << 31) { err = "more than 2^31 k3 units in one batch"; return 1; }
-  const int MT = 16 * fs->wm;
+  // ---- tile shape and row window of this batch ----
+  // The k3-sorted units of a batch sweep `rows_spanned` table rows, rho = U / rows_spanned of them per row.  A tile of MT
+  // units needs MT/rho + 1 rows per stage; rows beyond the `rmax` staged in shared memory are read from L2 by the
+  // consumer warps (slow).  Dense batches (the whole run on one GPU: rho ~ 90) want the widest tile and 4 rows; the
+  // smaller batches of a pipelined or multi-GPU run want more rows per stage, or a narrower tile when the widest one
+  // cannot hold its rows with a ring of 3 stages.  All shapes of a family read the same table layout (one column pass of
+  // at most 8 sub-blocks), so the choice is made per batch.  Measured on configs[1] (los_tc ms, default -> chosen):
+  // 800 k units 4.63 -> 3.91, 400 k 3.44 -> 2.59, 200 k 2.61 -> 2.48; lmax3000 1/4 shard 416 -> 376 (tests/big/ab_knobs.py).
+  int wm = fs->wm, wn = fs->wn, nw = fs->nw, rmax_sel = 0;
+  {
+    const double rho = (h.rows_spanned > 1. && U > 0) ? (double)U / h.rows_spanned : 1e9;
+    const size_t fixed0 = 128 + (size_t)((tau_size + 15) & ~15) * 32 + (size_t)((fs->n_cols_total + 31) & ~31) * 12;
+    auto r128b = [](size_t x) { return (x + 127) / 128 * 128; };
+    auto cap_of = [&](int mt) {        // most rows per stage that still leave a ring of 3 stages
+      int cap = 0;
+      for (int r = 1; r <= 8; ++r) {
+        const size_t stage = r128b(16 + (size_t)mt * 20) + r128b((size_t)mt * fs->tpp_max * 8) + (size_t)r * fs->nsb_pass_max * fs->kcs_max * 256;
+        if ((224 * 1024 - fixed0) / stage >= 3) cap = r;
+      }
+      return cap;
+    };
+    struct Shape { int wm, wn, nw; };
+    std::vector<Shape> family{{fs->wm, fs->wn, fs->nw}};
+    // (blocks covered in several column passes keep their shape: narrower tiles were slower there, 361 vs 287 ms on the
+    //  lmax3000 1/8 shard; only the row window adapts)
+    const bool narrow_ok = (fs->wm == 12 && fs->wn == 1 && fs->nsb_pass_max <= 8 && fs->n_pass == fs->n_blocks && !getenv("SONG_LOS_TC_SHAPE"));
+    if (narrow_ok) { family.push_back({8, 1, 8}); family.push_back({4, 2, 8}); }
+    bool chosen = false;
+    for (const Shape &sh : family) {
+      const int mt = 16 * sh.wm, cap = cap_of(mt);
+      const double need = (double)mt / rho;
+      if (need + 0.5 <= (double)cap) {
+        const int dflt = (mt >= 128) ? 4 : (mt >= 64 ? 3 : 2);
+        wm = sh.wm; wn = sh.wn; nw = sh.nw;
+        rmax_sel = std::max(std::min(dflt, cap), std::min(cap, (int)std::ceil(need + 1.5)));
+        chosen = true;
+        break;
+      }
+    }
+    if (!chosen && narrow_ok) { wm = 8; wn = 1; nw = 8; }     // very sparse batches: every shape reads most rows from L2
+    if (getenv("SONG_LOS_TC_NO_ADAPT")) { wm = fs->wm; wn = fs->wn; nw = fs->nw; rmax_sel = 0; }
+  }
+  const int MT = 16 * wm;
   const int64_t n_tiles = (U + MT - 1) / MT;
 
   // ---- phase 0 and 1 side by side: the global k3 order (second stream) does not depend on the splines ----
@@ -1293,6 +1337,7 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
   TP.a_bytes = (int)r128((size_t)MT * fs->tpp_max * 8);
   TP.b_row_bytes = fs->nsb_pass_max * fs->kcs_max * 256;
   int rmax = (MT >= 128) ? 4 : (MT >= 64 ? 3 : 2);
+  if (rmax_sel > 0) rmax = rmax_sel;
   if (const char *v = getenv("SONG_LOS_TC_RMAX")) rmax = std::max(1, std::min(8, atoi(v)));
   TP.n_cols_total = fs->n_cols_total; TP.cols_pad = (fs->n_cols_total + 31) & ~31;
   const size_t fixed = 128 + (size_t)((tau_size + 15) & ~15) * 32 + (size_t)TP.cols_pad * 12;
@@ -1351,7 +1396,7 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
       TP.pass_begin = pb; TP.pass_end = pe; TP.q_fixed = q;
       TP.acc_in = (q > 0); TP.acc_final = (q == nq - 1);
       cudaError_t e = cudaErrorInvalidValue;
-      const int key = fs->wm * 10000 + fs->wn * 100 + fs->nw;
+      const int key = wm * 10000 + wn * 100 + nw;
       const int64_t n_ctas = std::min<int64_t>(n_tiles, std::max(1, device_sms));     // persistent: one CTA per SM
       const int np1 = getenv("SONG_LOS_TC_NP1") != nullptr;     // A/B: a single producer warp
       switch (key) {

@@ -217,6 +217,9 @@ extern "C" int song_los_destroy(song_los_ctx *ctx)
   if (ctx->st_h2d) cudaStreamDestroy(ctx->st_h2d);
   if (ctx->st_d2h) cudaStreamDestroy(ctx->st_d2h);
   ctx->d_dd.release(); ctx->d_spline_u.release(); ctx->d_err.release(); ctx->d_scratch.release();
+  ctx->d_jl1.release(); ctx->d_ddjl1.release(); ctx->d_jl1_xmin.release(); ctx->d_k3req_coef.release(); ctx->d_k3_r.release();
+  ctx->d_k3_out.release(); ctx->d_jl1_off.release(); ctx->d_jl1_size.release(); ctx->d_k3req_tt.release();
+  ctx->d_k3req_row.release(); ctx->d_k3req_has.release();
   if (ctx->fast) fast_state_destroy(ctx->fast);
   if (ctx->d_proj_rows) cudaFree(ctx->d_proj_rows);
   if (ctx->d_proj_ddrows) cudaFree(ctx->d_proj_ddrows);
@@ -494,9 +497,10 @@ static int enqueue_upload(song_los_ctx *ctx, song_los_ctx::Slot &S, const song_l
   if (b->n_src_total) CK(cudaMemcpyAsync(S.d_src.p, b->src, (size_t)b->n_src_total * 8, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(S.ev_h2d, st));
 
+  // largest k3 of the batch: every pair's grid is ascending (transfer2.c:1727), so its last value is the pair's maximum
   S.k3_max = 0.;
-  if (c.tau_sampling_mode != SONG_LOS_TAU_SOURCES)
-    for (int64_t i = 0; i < b->n_units; ++i) S.k3_max = std::max(S.k3_max, b->k3_tr[i]);
+  for (int p = 0; p < b->n_pairs; ++p)
+    if (b->k3_tr_size[p] > 0) S.k3_max = std::max(S.k3_max, b->k3_tr[b->tr_off[p] + b->k3_tr_size[p] - 1]);
   S.hb = *b;
   S.hb.k3_pt_size = S.hb.k3_tr_size = S.hb.phys_start = S.hb.phys_size = nullptr;
   S.hb.pt_off = S.hb.tr_off = S.hb.src_off = nullptr;
@@ -562,6 +566,9 @@ static void fill_fast_layout(song_los_ctx *ctx, const song_los_ctx::Slot &S, Fas
   h.tau_size = c.tau_size; h.n_pt_total = S.hb.n_pt_total;
   h.xx_uniform = ctx->xx_uniform; h.xx_delta = ctx->xx_delta;
   h.max_np = S.max_np;
+  // table rows the batch's k3 values sweep at a mid-run time: x = k3 (tau0 - tau) / xx_step (transfer2.c:2195-2199)
+  h.rows_spanned = (S.k3_max > 0. && c.xx_step > 0.)
+                 ? S.k3_max * (c.tau0 - ctx->tau[c.tau_size / 2]) / c.xx_step + 1. : (double)c.xx_size;
 }
 
 static int report_device_errors(song_los_ctx *ctx, int h)

@@ -82,6 +82,13 @@ struct song_los_ctx {
   double *d_proj_rows = nullptr, *d_proj_ddrows = nullptr; int proj_rows_n = 0;
   std::vector<int> h_jidx_xmin, h_jidx_xsize;
   cudaEvent_t ev[8]{};
+
+  // k3 integral of the intrinsic bispectrum (los_k3int.cu): j_l1 table and request buffers
+  int jl1_rows = 0;
+  DevBuf<double> d_jl1, d_ddjl1, d_jl1_xmin, d_k3req_coef, d_k3_r, d_k3_out;
+  DevBuf<int64_t> d_jl1_off;
+  DevBuf<int> d_jl1_size, d_k3req_tt, d_k3req_row, d_k3req_has;
+  float k3_ms = 0.f;
 };
 
 

@@ -166,6 +166,30 @@ class LosEngine:
             self._inflight.pop(0)
         return self.timing.as_dict()
 
+    # -- k3 integral of the intrinsic bispectrum on the device-resident transfer functions ----------
+    def set_bessel_table(self, j_l1, x_min_l1, ddj_l1=None):
+        """pbs2->j_l1 rows (list of 1-D arrays), their first abscissa x_min_l1 and, for cubic interpolation, ddj_l1."""
+        rows = [np.ascontiguousarray(r, dtype=np.float64) for r in j_l1]
+        dd = None if ddj_l1 is None else [np.ascontiguousarray(r, dtype=np.float64) for r in ddj_l1]
+        n = len(rows)
+        rp = (_lib.c_double_p * n)(*[_lib.dptr(r) for r in rows])
+        dp_ = None if dd is None else (_lib.c_double_p * n)(*[_lib.dptr(r) for r in dd])
+        xmin = np.ascontiguousarray(x_min_l1, dtype=np.float64)
+        size = np.asarray([r.size for r in rows], dtype=np.int32)
+        self._check(self.lib.song_los_set_bessel_table(self.ctx, n, rp, dp_, _lib.dptr(xmin), _lib.iptr(size)))
+
+    def integrate_k3(self, tt, index_l1, r, n_pairs: int, abs_M3: int = 0, M3_coefficient=None) -> np.ndarray:
+        """bispectra2_intrinsic_integrate_over_k3 on the result of the last compute: [len(tt)][len(r)][n_pairs]."""
+        tt = np.ascontiguousarray(tt, dtype=np.int32); index_l1 = np.ascontiguousarray(index_l1, dtype=np.int32)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        coef = None if M3_coefficient is None else np.ascontiguousarray(M3_coefficient, dtype=np.float64)
+        rq = _lib.K3Request(n_requests=int(tt.size), tt=_lib.iptr(tt), index_l1=_lib.iptr(index_l1), abs_M3=int(abs_M3),
+                            M3_coefficient=None if coef is None else _lib.dptr(coef), r_size=int(r.size), r=_lib.dptr(r))
+        out = np.empty((tt.size, r.size, n_pairs), dtype=np.float64)
+        self._check(self.lib.song_los_integrate_k3(self.ctx, C.byref(rq), _lib.dptr(out)))
+        self.k3_ms = float(self.lib.song_los_last_k3_ms(self.ctx))
+        return out
+
     def max_batch_units(self, mode: int, src_doubles_per_unit: float) -> int:
         n = C.c_int64(0)
         self._check(self.lib.song_los_max_batch_units(self.ctx, mode, float(src_doubles_per_unit), C.byref(n)))

@@ -97,6 +97,8 @@ def lib():
         L.oracle_multipole2offset_l_indexm.argtypes = [C.c_int, C.c_int, ip, C.c_int]
         L.oracle_offset2multipole_indexl_indexm.argtypes = [C.c_int, ip, C.c_int, ip, C.c_int, ip, ip]
         L.oracle_bessel2_convolution.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, C.c_int, C.c_double, dp]
+        L.oracle_integral_over_k3.argtypes = [C.c_int, ip, lp, dp, dp, dp, dp, C.c_double, C.c_double, C.c_int, C.c_int, dp,
+                                              C.c_int, C.c_double, dp]
         L.oracle_free = C.CDLL(None).free
         L.oracle_free.argtypes = [C.c_void_p]
         _lib = L
@@ -301,3 +303,19 @@ def bessel2_convolution(kk, delta_kk, f, g, j_row, ddj_row, x_min_l1, xx_step, r
                                      None if ddj_row is None else _d(ddj_row), float(x_min_l1), float(xx_step), int(cubic),
                                      float(r), C.byref(out))
     return float(out.value)
+
+
+def integral_over_k3(wl, transfer_row, j_row, ddj_row, x_min_l1, r, abs_M3=0, M3_coefficient=1.0, cubic=False) -> np.ndarray:
+    """bispectra2_intrinsic_integrate_over_k3 (bispectra2.c:1107-1439) for one (l3, M3): [r_size][n_pairs]."""
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    out = np.zeros((r.size, wl.n_pairs))
+    tr_off = wl.tr_off.astype(np.int64)
+    t = np.ascontiguousarray(transfer_row, dtype=np.float64)
+    j_row = np.ascontiguousarray(j_row, dtype=np.float64)
+    ddj_row = None if ddj_row is None else np.ascontiguousarray(ddj_row, dtype=np.float64)
+    rc = lib().oracle_integral_over_k3(wl.n_pairs, _i(wl.k3_tr_size), _l(tr_off), _d(wl.k3_tr), _d(t), _d(j_row),
+                                       None if ddj_row is None else _d(ddj_row), float(x_min_l1), float(wl.xx_step), int(cubic),
+                                       int(r.size), _d(r), int(abs_M3), float(M3_coefficient), _d(out))
+    if rc:
+        raise RuntimeError("oracle_integral_over_k3: an integration grid has less than two elements")
+    return out

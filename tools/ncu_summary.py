@@ -23,7 +23,7 @@ st = [(float(v[1]), k.split("issue_stalled_")[1].split("_per")[0]) for k, v in m
 for v, k in sorted(st, reverse=True)[:9]: print(f"  {k:28s} {v:.2f}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-body = rows[2:]
+body = [r for r in rows[2:] if len(r) > 5 and r[2].strip().isdigit() and r[1].strip()]
 tot = sum(int(r[2]) for r in body)
 c = Counter(); ex = Counter()
 for r in body:
