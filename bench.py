@@ -51,8 +51,9 @@ class ClockSampler:
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device_index: int):
+    def __init__(self, device_index: int, period_ms: int = 50):
         self.idx = device_index
+        self.period_ms = period_ms
         self.proc = None
         self.path = None
 
@@ -61,7 +62,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms),
                  "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -341,7 +342,7 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
     p = configs.get(name)
     grids = workload.build_grids(p, max_pairs=args.max_pairs)
     full_pairs = grids.n_pairs == grids.k.size * (grids.k.size + 1) // 2
-    chunks = args.chunks_per_rank if world > 1 else 1
+    chunks = (args.chunks_per_rank or shard.chunks_per_device(grids, world)) if world > 1 else 1
     dev_of_pair, load = shard.schedule_pairs(shard.pair_cost(grids), world, chunks)
     owned = np.nonzero(dev_of_pair == rank)[0]
     want_e2e = e2e_steps > 0 and full_pairs and os.path.exists(dropin_lib.PATH)
@@ -386,6 +387,7 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
         launches += one_step(kern)
     ev1.record(stream)
     D.barrier()
+    clocks = sampler.stop() if sampler is not None else None
     my_ms = ev0.elapsed_time(ev1) / steps
     rank_ms = D.all_gather_floats(my_ms)
     ms_step = max(rank_ms)
@@ -544,6 +546,8 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
             if first_ms is None:
                 first_ms = dt * 1e3
             h.transfer2_free(); h.fill_sources()
+        e2e_sampler = ClockSampler(D.local_rank, period_ms=1000)       # slow polling: see the note at the 50 ms sampler
+        e2e_sampler.start()
         t_all = 0.0; t_read = 0.0; cs = 0.0; each = []
         for i in range(e2e_steps):
             if args.dropin_verbose and i + 1 == e2e_steps:
@@ -557,6 +561,7 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
             t_all += t1 - t0; t_read += t2 - t1; each.append((t1 - t0) * 1e3)
             if i + 1 < e2e_steps:
                 h.transfer2_free(); h.fill_sources()
+        e2e_clocks = e2e_sampler.stop()
         got, count, labels_ok = h.read()
         tables = h.bessel2_tables()
         run_scale = np.abs(got).max(axis=1, keepdims=True)
@@ -574,7 +579,7 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
                       "ptr2->transfer; packing, H2D, kernels and D2H of every batch inside the call; host clock around the call",
                "first_call_ms": first_ms, "first_call_note": "includes page-locking the staging and the ptr2->transfer slabs (kept in a pool afterwards)",
                "bessel2_init_s": t_b2, "result_read_ms_per_step": t_read / e2e_steps * 1e3, "checksum_abs_sum": cs,
-               "count_memorised_transfers": count, "labels_ok": labels_ok, "parity": e2e_parity}
+               "count_memorised_transfers": count, "labels_ok": labels_ok, "parity": e2e_parity, "clocks_gpu0_1s_period": e2e_clocks}
     D.cpu_barrier()
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
@@ -592,10 +597,10 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
         return None
     return {
         "workload": name, "value": value, "ms_per_step": ms_step, "steps": steps, "warmup": warmup,
-        "per_rank_ms": rank_ms, "imbalance_max_over_mean": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
+        "chunks_per_gpu": chunks, "per_rank_ms": rank_ms, "imbalance_max_over_mean": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
         "schedule_load_max_over_mean": float(load.max() / load.mean()),
         "gpu_launches": launches_total, "describe": workload.describe(grids), "parity": parity, "gather": gather,
-        "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "setup_s": t_setup, "k3_integral": k3int,
+        "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "setup_s": t_setup, "k3_integral": k3int, "clocks": clocks,
         "l2_gb_streamed": (3 * sub.src.nbytes + n_int_rank * 8) / 1e9,
     }
 
@@ -612,7 +617,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--e2e-steps", type=int, default=5, help="timed transfer2_init calls (at most --steps)")
-    ap.add_argument("--chunks-per-rank", type=int, default=3, help="contiguous pair chunks per GPU in the static schedule")
+    ap.add_argument("--chunks-per-rank", type=int, default=0, help="contiguous pair chunks per GPU in the static schedule (0: the rule of transfer2_init)")
     ap.add_argument("--check-pairs", type=int, default=8, help="pairs checked against the CPU oracle per workload")
     ap.add_argument("--no-k3-integral", dest="k3_integral", action="store_false", help="skip the bispectrum k3-integral leg (SURVEY 8f rank 1)")
     ap.add_argument("--dropin-verbose", type=int, default=0, help="debug: ptr2->transfer2_verbose of the last timed transfer2_init")
@@ -636,10 +641,11 @@ def main():
     numa = bind_to_gpu_numa_node(local_rank)         # before any pinned allocation: page-locked buffers are first-touch local
     D = Dist(rank, world, local_rank)
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank)               # 50 ms period over the timed `value` region only: nvidia-smi queries take driver
+                                                     # locks and stretched single transfer2_init calls from 34 to 120-480 ms
     main_res = measure_workload(args.workload, args, D, args.steps, args.warmup, min(args.e2e_steps, args.steps),
                                 with_cpu=(world == 1 and not args.no_cpu_baseline), sampler=sampler)
-    clocks = sampler.stop()          # sampled from the start of the timed `value` region to the end of the e2e region, 50 ms period
+    clocks = main_res.get("clocks") if rank == 0 else None
 
     extras = []
     if args.extra == "auto":
@@ -674,7 +680,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": dict(r["describe"], workload=args.workload, mode=args.mode,
                            parallelism=f"ONE workload split by (k1,k2) pair over {world} GPU(s): static schedule of song_host_schedule_pairs "
-                                       f"({args.chunks_per_rank if world > 1 else 1} contiguous chunk(s) per GPU, LPT), no data-path collective; results gathered on rank 0",
+                                       f"({r['chunks_per_gpu']} contiguous chunk(s) per GPU, LPT, cost = k3 values x active multipole share), no data-path collective; results gathered on rank 0",
                            l2_policy="inputs larger than L2: each step streams ~%.1f GB per GPU (sources, transposed sources, "
                                      "interpolated slab, projection table, output) against 126 MB of L2" % r["l2_gb_streamed"],
                            tau_sampling="synthetic, geometric 230->330 then linear ->700 Mpc",

@@ -151,7 +151,7 @@ LOS_SYMBOLS = [
 ]
 HOST_SYMBOLS = ["song_host_k3_size", "song_host_k3_list", "song_host_k3_sizes", "song_host_k3_lists",
                 "song_host_bessel2_prepare", "song_host_bessel2_free", "song_host_bessel2_upload",
-                "song_host_lpt_schedule", "song_host_schedule_pairs"]
+                "song_host_lpt_schedule", "song_host_schedule_pairs", "song_host_pair_costs"]
 
 _los = None
 _host = None
@@ -229,6 +229,7 @@ def host():
                                                  C.c_char_p, C.c_int]
         lib.song_host_lpt_schedule.argtypes = [c_int64_p, C.c_int, C.c_int, c_int_p, c_int64_p]
         lib.song_host_schedule_pairs.argtypes = [c_int64_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int64_p]
+        lib.song_host_pair_costs.argtypes = [C.c_int, c_int_p, c_double_p, c_double_p, C.c_double, C.c_int, c_int64_p]
         lib.compat_drc3jj.argtypes = [C.c_double] * 4 + [c_double_p, c_double_p, c_double_p, C.c_int]
         lib.compat_bessel_j.argtypes = [C.c_int, C.c_double]
         lib.compat_bessel_j.restype = C.c_double

@@ -237,3 +237,26 @@ int song_host_schedule_pairs(const int64_t *cost, int n_pairs, int n_dev, int ch
   free(ccost); free(cdev); free(chunk_of);
   return rc;
 }
+
+/* Cost model of the static schedule.  Every k3 value of a pair costs tt2_size integrals over the same tau and L ranges
+   (SURVEY.md 8e), but the tensor-core kernel skips the multipole columns whose J_Llm(x) is still below the cut at
+   x = k3 (tau0 - tau) << l: about min(1, k3 tau0 / l_max) of the columns are active.  cost = k3 values x (0.65 + 0.35 x
+   active fraction at the middle of the pair's k3 range), in units of 1/1024 k3 value.  The weights are measured: on the
+   lmax3000 run the lowest-k quarter of the pairs costs 0.74 of the rest per k3 value (a stronger correction, 0.35 + active,
+   left one of two GPUs with 1089 ms of kernels against 901 ms). */
+int song_host_pair_costs(int n_pairs, const int *k3_tr_size, const double *k_min, const double *k_max, double tau0, int l_max,
+                         int64_t *cost)
+{
+  if (!k3_tr_size || !cost || n_pairs < 0) return 1;
+  for (int p = 0; p < n_pairs; ++p) {
+    double active = 1.0;
+    if (k_min && k_max && l_max > 0) {
+      active = 0.5 * (k_min[p] + k_max[p]) * tau0 / (double)l_max;
+      if (active > 1.0) active = 1.0;
+      if (active < 0.0) active = 0.0;
+    }
+    cost[p] = (int64_t)((double)k3_tr_size[p] * (0.65 + 0.35 * active) * 1024.0);
+    if (cost[p] < 1) cost[p] = 1;
+  }
+  return 0;
+}

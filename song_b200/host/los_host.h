@@ -61,6 +61,12 @@ int song_host_lpt_schedule(const int64_t *cost, int n, int n_dev, int *device, i
    cost.  Used by transfer2_init (transfer2_gpu.c) and by the multi-rank driver (song_b200/shard.py). */
 int song_host_schedule_pairs(const int64_t *cost, int n_pairs, int n_dev, int chunks_per_dev, int *device_of_pair, int64_t *load);
 
+/* Cost of every (k1,k2) pair for the static schedule: k3 values x (fixed part + fraction of the multipole columns that
+   are active at the pair's k3), in 1/1024 k3 value.  k_min / k_max: ptr2->k_min_k1k2 / k_max_k1k2 flattened in pair order
+   (NULL: every column counted).  l_max: largest multipole of the run. */
+int song_host_pair_costs(int n_pairs, const int *k3_tr_size, const double *k_min, const double *k_max, double tau0, int l_max,
+                         int64_t *cost);
+
 #ifdef __cplusplus
 }
 #endif

@@ -728,26 +728,28 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   class_alloc(cost, R.n_pairs * sizeof(int64_t), ptr2->error_message);
   class_alloc(device_of_pair, R.n_pairs * sizeof(int), ptr2->error_message);
   int64_t total_units = 0, total_pt = 0;
+  int *units_of_pair; double *kmin_of_pair, *kmax_of_pair;
+  class_alloc(units_of_pair, R.n_pairs * sizeof(int), ptr2->error_message);
+  class_alloc(kmin_of_pair, R.n_pairs * sizeof(double), ptr2->error_message);
+  class_alloc(kmax_of_pair, R.n_pairs * sizeof(double), ptr2->error_message);
   for (int k1 = 0, p = 0; k1 < ppt2->k_size; ++k1) {
     R.pairs_to_pack[k1] = k1 + 1;
     for (int k2 = 0; k2 <= k1; ++k2, ++p) {
       R.pair_k1[p] = k1; R.pair_k2[p] = k2;
-      cost[p] = ptr2->k_size_k1k2[k1][k2];            /* every k3 value costs tt2_size integrals over the same tau and L ranges */
+      units_of_pair[p] = ptr2->k_size_k1k2[k1][k2];
+      kmin_of_pair[p] = ptr2->k_min_k1k2[k1][k2]; kmax_of_pair[p] = ptr2->k_max_k1k2[k1][k2];
       total_units += ptr2->k_size_k1k2[k1][k2]; total_pt += ppt2->k3_size[k1][k2];
     }
   }
-  /* several chunks per GPU give every GPU the same mix of low-k (cheap: few active multipoles) and high-k pairs and
-     double as the batches of its copy/compute pipeline */
-  int chunks_per_dev = env_int("SONG_LOS_CHUNKS_PER_DEVICE", 0);
-  if (chunks_per_dev <= 0) chunks_per_dev = (n_dev > 1) ? 3 : 1;
-  if (ordered) chunks_per_dev = 1;
-  if (song_host_schedule_pairs(cost, R.n_pairs, n_dev, chunks_per_dev, device_of_pair, NULL) != 0) {
-    RELEASE_ENGINES();
-    class_stop(ptr2->error_message, "could not schedule %d (k1,k2) pairs on %d GPUs", R.n_pairs, n_dev);
-  }
+  /* cost of a pair: its k3 values, weighted by the share of the multipole columns that are active at its k3 (los_host.c) */
+  song_host_pair_costs(R.n_pairs, units_of_pair, kmin_of_pair, kmax_of_pair, ptr2->tau0, ptr2->l[ptr2->l_size - 1], cost);
+  free(kmin_of_pair); free(kmax_of_pair);
 
-  /* ---- batches: runs of consecutive pairs of one device, at most what fits in device memory, and at least
-     SONG_LOS_MIN_BATCHES per GPU when the run is large enough for the copies to be worth overlapping ---- */
+  /* Batch size.  The tensor-core kernel works on the k3-sorted values of a batch: the more of them share a row of the
+     projection table (pbs2->xx_size rows), the fewer partly filled MMAs it issues -- a batch with 40 k3 values per row
+     runs within ~10 % of the full run's rate, one with 10 per row at half of it.  Small batches, on the other hand, let
+     the copies of one batch overlap the kernels of another.  So: SONG_LOS_MIN_BATCHES (4) batches per GPU when they stay
+     above 40 values per row, fewer and larger ones otherwise; never more than fits in device memory. */
   int64_t cap_units = 0;
   const double src_per_unit = (double)ppt2->tp2_size * ppt2->tau_size * (double)total_pt / (double)(total_units > 0 ? total_units : 1);
   if (song_los_max_batch_units(engines->ctx[0], mode, src_per_unit, &cap_units) != SONG_LOS_SUCCESS) {
@@ -755,15 +757,32 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
     RELEASE_ENGINES();
     return _FAILURE_;
   }
+  const int64_t dense_units = (int64_t)env_int("SONG_LOS_DENSE_K3_PER_ROW", 40) * pbs2->xx_size;
   int64_t batch_units = env_int("SONG_LOS_BATCH_UNITS", 0);
   if (batch_units <= 0) {
     int min_batches = env_int("SONG_LOS_MIN_BATCHES", 4);
     if (min_batches < 1) min_batches = 1;
     batch_units = (total_units / n_dev + min_batches - 1) / min_batches;
-    const int64_t floor_units = env_int("SONG_LOS_MIN_BATCH_UNITS", 150000);   /* below this the kernels are launch-bound */
-    if (batch_units < floor_units) batch_units = floor_units;
+    if (batch_units < dense_units) batch_units = dense_units;
   }
   if (batch_units > cap_units) batch_units = cap_units;
+
+  /* several chunks per GPU give every GPU the same mix of low-k and high-k pairs (the cost model then matters less);
+     not more than keep a chunk dense */
+  int chunks_per_dev = env_int("SONG_LOS_CHUNKS_PER_DEVICE", 0);
+  if (chunks_per_dev <= 0) {
+    chunks_per_dev = (n_dev > 1) ? (int)((total_units / n_dev) / (dense_units > 0 ? dense_units : 1)) : 1;
+    if (chunks_per_dev > 3) chunks_per_dev = 3;
+    if (chunks_per_dev < 1) chunks_per_dev = 1;
+  }
+  if (ordered) chunks_per_dev = 1;
+  if (song_host_schedule_pairs(cost, R.n_pairs, n_dev, chunks_per_dev, device_of_pair, NULL) != 0) {
+    RELEASE_ENGINES();
+    class_stop(ptr2->error_message, "could not schedule %d (k1,k2) pairs on %d GPUs", R.n_pairs, n_dev);
+  }
+  for (int p = 0; p < R.n_pairs; ++p) cost[p] = units_of_pair[p];       /* from here on: k3 values (batch sizes) */
+  free(units_of_pair);
+
   los_pair_batch *batches;
   class_alloc(batches, R.n_pairs * sizeof(los_pair_batch), ptr2->error_message);
   int n_batches = 0;
@@ -771,7 +790,11 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
     /* the run of consecutive pairs of one device starting at p, cut into equal parts of at most batch_units */
     int q = p; int64_t run_units = 0;
     while (q < R.n_pairs && device_of_pair[q] == device_of_pair[p]) run_units += cost[q++];
-    const int parts = (int)((run_units + batch_units - 1) / batch_units) > 0 ? (int)((run_units + batch_units - 1) / batch_units) : 1;
+    /* about batch_units each (rounded to the nearest count: a part never falls far below the dense size), and what fits */
+    int parts = (int)((2 * run_units + batch_units) / (2 * batch_units));
+    const int parts_min = (int)((run_units + cap_units - 1) / cap_units);
+    if (parts < parts_min) parts = parts_min;
+    if (parts < 1) parts = 1;
     int64_t acc = 0; int part = 0;
     los_pair_batch pb; memset(&pb, 0, sizeof pb); pb.p_first = p; pb.device = device_of_pair[p];
     for (int i = p; i < q; ++i) {

@@ -24,9 +24,24 @@ def lpt_schedule(cost, n_ranks: int):
 
 
 def pair_cost(wl) -> np.ndarray:
-    """Cost model of SURVEY.md 8e per (k1,k2) pair: k3 values x tt2_size x tau_size x (L_max+1)."""
-    lay = wl.layout
-    return wl.k3_tr_size.astype(np.int64) * lay.tt2_size * int(wl.tau.size) * lay.L_size
+    """Cost of every (k1,k2) pair as transfer2_init computes it (C: song_host_pair_costs): k3 values x (fixed part +
+    fraction of the multipole columns active at the pair's k3 range); the factors common to all pairs of a run
+    (tt2_size, tau_size, L_max+1) drop out of the schedule."""
+    cost = np.zeros(wl.n_pairs, dtype=np.int64)
+    kmin = np.ascontiguousarray(wl.k_min_tr, dtype=np.float64); kmax = np.ascontiguousarray(wl.k_max_tr, dtype=np.float64)
+    if _lib.host().song_host_pair_costs(wl.n_pairs, _lib.iptr(wl.k3_tr_size), _lib.dptr(kmin), _lib.dptr(kmax),
+                                        float(wl.cosmo["tau0"]), int(wl.layout.l.max()), _lib.lptr(cost)):
+        raise _lib.SongLosError("song_host_pair_costs: bad arguments")
+    return cost
+
+
+def chunks_per_device(wl, n_dev: int) -> int:
+    """Contiguous pair chunks per GPU in the static schedule, the rule of transfer2_init: as many as keep about 40 k3
+    values per table row in every chunk (the tensor-core kernel's efficiency falls with the k3 density), at most 3."""
+    if n_dev <= 1:
+        return 1
+    dense_units = 40 * int(wl.xx.size)
+    return int(max(1, min(3, (wl.n_units // n_dev) // max(dense_units, 1))))
 
 
 def schedule_pairs(cost, n_ranks: int, chunks_per_rank: int = 3):
