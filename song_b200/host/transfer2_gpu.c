@@ -27,6 +27,9 @@
  * SONG_LOS_DEVICES=<n> (default: all visible), SONG_LOS_BATCH_UNITS, SONG_LOS_MIN_BATCHES, SONG_LOS_CHUNKS_PER_DEVICE,
  * SONG_LOS_HOST_THREADS, SONG_LOS_PINNED_TRANSFERS=0|1, SONG_LOS_PINNED_POOL=0|1.
  */
+#ifndef _XOPEN_SOURCE
+#define _XOPEN_SOURCE 700          /* pwrite, fileno (the writer thread of store_transfers_to_disk) */
+#endif
 #include "transfer2.h"
 #include "song_los.h"
 #include "los_host.h"
@@ -36,6 +39,8 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include <pthread.h>
+#include <unistd.h>
 
 /* ------------------------------------------------------------------------------------------------ */
 /*  small helpers                                                                                    */
@@ -469,8 +474,9 @@ typedef struct {
   int n_pairs; int *pair_k1, *pair_k2;     /* pair -> (index_k1, index_k2) */
   int *pairs_to_pack;                      /* per k1 level: pairs whose sources have not been packed yet (-> perturb2_free_k1_level) */
   int mode, host_threads, sources_on_disk, store_to_disk;
-  int next_level_to_load, next_level_to_store;   /* ordered runs (one GPU, batches in k1 order) */
+  int next_level_to_load;                        /* ordered runs (sources read from disk level by level) */
   double t_start;                                /* transfer2_verbose > 2: lap times of every batch */
+  struct los_writer *writer;                     /* store_transfers_to_disk: the thread that writes finished batches */
 } los_run;
 
 static double los_now(void)
@@ -480,6 +486,106 @@ static double los_now(void)
 #else
   return 0.;
 #endif
+}
+
+/* ---- store_transfers_to_disk (transfer2.c:559-567, 2929-2963) without stalling the GPUs ----
+   transfers_%03d.dat holds, per transfer type, the values in [k1][k2][k3] order, i.e. in pair order; the result of a
+   batch is, per type, one contiguous run of that file.  A writer thread therefore puts every finished batch at its offset
+   with one pwrite per type, in whatever order the GPUs finish, while the host threads of the GPUs go on packing and
+   submitting; a k1 level is freed as the reference does (:565) once every pair of it is on disk. */
+typedef struct los_write_job { const los_pair_batch *pb; struct los_write_job *next; } los_write_job;
+typedef struct los_writer {
+  pthread_t thread; pthread_mutex_t lock; pthread_cond_t wake;
+  los_write_job *head, *tail; int closing, failed;
+  los_run *R; int64_t *unit_offset_of_pair;   /* position of every pair in a type's file, in doubles */
+  int *pairs_to_write;                        /* per k1 level */
+  ErrorMsg error;
+} los_writer;
+
+static int writer_store_batch(los_writer *W, const los_pair_batch *pb)
+{
+  los_run *R = W->R; struct transfers2 *ptr2 = R->ptr2;
+  const off_t at = (off_t)W->unit_offset_of_pair[pb->p_first] * (off_t)sizeof(double);
+  const size_t bytes = (size_t)pb->n_units * sizeof(double);
+  for (int index_tt = 0; index_tt < ptr2->tt2_size; ++index_tt) {
+    const char *src = (const char *)(pb->slab + (size_t)index_tt * (size_t)pb->n_units);
+    const int fd = fileno(ptr2->transfers_files[index_tt]);
+    size_t done = 0;
+    while (done < bytes) {
+      ssize_t w = pwrite(fd, src + done, bytes - done, at + (off_t)done);
+      if (w <= 0) { snprintf(W->error, _ERRORMSGSIZE_, "could not write to '%s'", ptr2->transfers_paths[index_tt]); return _FAILURE_; }
+      done += (size_t)w;
+    }
+  }
+  /* levels whose last pair is now on disk */
+  const int k1a = R->pair_k1[pb->p_first], k1b = R->pair_k1[pb->p_last];
+  for (int k1 = k1a; k1 <= k1b; ++k1) {
+    const int lo = (k1 == k1a) ? R->pair_k2[pb->p_first] : 0, hi = (k1 == k1b) ? R->pair_k2[pb->p_last] : k1;
+    W->pairs_to_write[k1] -= hi - lo + 1;                      /* only this thread touches the counters */
+    if (W->pairs_to_write[k1] == 0 && transfer2_free_k1_level(R->ppt2, ptr2, k1) == _FAILURE_) {
+      snprintf(W->error, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); return _FAILURE_;
+    }
+  }
+  return _SUCCESS_;
+}
+
+static void *writer_main(void *arg)
+{
+  los_writer *W = (los_writer *)arg;
+  for (;;) {
+    pthread_mutex_lock(&W->lock);
+    while (W->head == NULL && !W->closing) pthread_cond_wait(&W->wake, &W->lock);
+    los_write_job *job = W->head;
+    if (job != NULL) { W->head = job->next; if (W->head == NULL) W->tail = NULL; }
+    pthread_mutex_unlock(&W->lock);
+    if (job == NULL) return NULL;                               /* closing and drained */
+    if (!W->failed && writer_store_batch(W, job->pb) == _FAILURE_) W->failed = 1;
+    free(job);
+  }
+}
+
+static los_writer *writer_start(los_run *R)
+{
+  los_writer *W = (los_writer *)calloc(1, sizeof *W);
+  if (W == NULL) return NULL;
+  W->R = R;
+  W->unit_offset_of_pair = (int64_t *)malloc(sizeof(int64_t) * (size_t)R->n_pairs);
+  W->pairs_to_write = (int *)malloc(sizeof(int) * (size_t)R->ppt2->k_size);
+  if (!W->unit_offset_of_pair || !W->pairs_to_write) { free(W->unit_offset_of_pair); free(W->pairs_to_write); free(W); return NULL; }
+  int64_t off = 0;
+  for (int p = 0; p < R->n_pairs; ++p) { W->unit_offset_of_pair[p] = off; off += R->ptr2->k_size_k1k2[R->pair_k1[p]][R->pair_k2[p]]; }
+  for (int k1 = 0; k1 < R->ppt2->k_size; ++k1) W->pairs_to_write[k1] = k1 + 1;
+  pthread_mutex_init(&W->lock, NULL); pthread_cond_init(&W->wake, NULL);
+  if (pthread_create(&W->thread, NULL, writer_main, W) != 0) { free(W->unit_offset_of_pair); free(W->pairs_to_write); free(W); return NULL; }
+  return W;
+}
+
+static int writer_push(los_writer *W, const los_pair_batch *pb)
+{
+  los_write_job *job = (los_write_job *)malloc(sizeof *job);
+  if (job == NULL) return _FAILURE_;
+  job->pb = pb; job->next = NULL;
+  pthread_mutex_lock(&W->lock);
+  if (W->tail) W->tail->next = job; else W->head = job;
+  W->tail = job;
+  pthread_cond_signal(&W->wake);
+  pthread_mutex_unlock(&W->lock);
+  return _SUCCESS_;
+}
+
+/* waits for the queue to drain; returns _FAILURE_ (message in errmsg) if a write failed */
+static int writer_finish(los_writer *W, char *errmsg)
+{
+  pthread_mutex_lock(&W->lock);
+  W->closing = 1;
+  pthread_cond_signal(&W->wake);
+  pthread_mutex_unlock(&W->lock);
+  pthread_join(W->thread, NULL);
+  const int failed = W->failed;
+  if (failed) snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", W->error);
+  pthread_mutex_destroy(&W->lock); pthread_cond_destroy(&W->wake);
+  free(W->unit_offset_of_pair); free(W->pairs_to_write); free(W);
+  return failed ? _FAILURE_ : _SUCCESS_;
 }
 
 /* packs the pairs of `pb` into the staging and enqueues the batch on the GPU (song_los_submit): the kernels' result goes
@@ -582,16 +688,8 @@ static int finish_batch(los_run *R, song_los_ctx *ctx, los_staging *s, char *err
   const long int stored = (long int)pb->n_units * ptr2->tt2_size;
   #pragma omp atomic
   ptr2->count_memorised_transfers += stored;                                    /* transfer2.c:2110-2111 */
-  if (R->store_to_disk) {                                                       /* :559-567, in k1 order */
-    /* ordered run: every level up to the one before the level of the last pair is complete, and that one too when the
-       batch ends on its diagonal */
-    int k1_done = R->pair_k1[pb->p_last];
-    if (R->pair_k2[pb->p_last] != k1_done) --k1_done;
-    for (; R->next_level_to_store <= k1_done; ++R->next_level_to_store)
-      if (transfer2_store_transfers_to_disk(R->ppt2, ptr2, R->next_level_to_store) == _FAILURE_ ||
-          transfer2_free_k1_level(R->ppt2, ptr2, R->next_level_to_store) == _FAILURE_) {
-        snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); return _FAILURE_;
-      }
+  if (R->store_to_disk && writer_push(R->writer, pb) == _FAILURE_) {           /* :559-567: written and freed by the writer thread */
+    snprintf(errmsg, _ERRORMSGSIZE_, "out of memory in the disk writer queue"); return _FAILURE_;
   }
   return _SUCCESS_;
 }
@@ -691,10 +789,11 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   const int tau_mode = (ptr2->tau_sampling == sources_tau_sampling) ? SONG_LOS_TAU_SOURCES
                      : (ptr2->tau_sampling == bessel_tau_sampling) ? SONG_LOS_TAU_BESSEL : SONG_LOS_TAU_CUSTOM;
 
-  /* devices: every visible GPU (SONG_LOS_DEVICES caps the number), one host thread each; a run that reads its sources
-     from disk or writes its transfers to disk level by level keeps the k1 order of the files and uses one */
+  /* devices: every visible GPU (SONG_LOS_DEVICES caps the number), one host thread each.  A run that reads its sources
+     from disk level by level (perturb2_load_sources_from_disk, reference code) keeps the k1 order and uses one GPU;
+     transfers written to disk do not constrain the schedule (see the writer thread above) */
   const int sources_on_disk = (ppr2->load_sources_from_disk == _TRUE_) || (ppr2->store_sources_to_disk == _TRUE_);
-  const int ordered = sources_on_disk || (ppr2->store_transfers_to_disk == _TRUE_);
+  const int ordered = sources_on_disk;
   int n_visible = 0;
   class_test(song_los_device_count(&n_visible) != SONG_LOS_SUCCESS || n_visible < 1, ptr2->error_message,
              "%.1500s", song_los_last_error(NULL));                                            /* no usable GPU: there is no CPU fallback */
@@ -832,6 +931,10 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   R.host_threads = host_threads;
   int abort_flag = _FALSE_;
   ErrorMsg first_error = "";
+  if (R.store_to_disk) {
+    R.writer = writer_start(&R);
+    if (R.writer == NULL) { RELEASE_ENGINES(); class_stop(ptr2->error_message, "could not start the disk writer thread"); }
+  }
   #pragma omp parallel for num_threads(n_dev) schedule(static, 1) if (n_dev > 1)
   for (int d = 0; d < n_dev; ++d) {
     ErrorMsg local = "";
@@ -891,6 +994,11 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
     }
   }
   LAP("all batches computed and stored in ptr2->transfer");
+  if (R.writer != NULL) {
+    ErrorMsg werr = "";
+    if (writer_finish(R.writer, werr) == _FAILURE_ && abort_flag == _FALSE_) { abort_flag = _TRUE_; snprintf(first_error, _ERRORMSGSIZE_, "%s", werr); }
+    LAP("transfers_%03d.dat written");
+  }
   RELEASE_ENGINES();
   free(batches); free(cost); free(device_of_pair); free(R.pair_k1); free(R.pair_k2); free(R.pairs_to_pack);
   class_test(abort_flag == _TRUE_, ptr2->error_message, "%.1900s", first_error);

@@ -218,3 +218,23 @@ def test_k1_level_memory_semantics(oracle, monkeypatch):
         monkeypatch.setenv("SONG_LOS_PINNED_TRANSFERS", pinned)
         got, count, labels_ok = dropin_lib.run_transfer2(wl, Projection(proj.rows, proj.index_xmin, proj.x_size))
         assert np.array_equal(got, ref) and count == wl.n_integrals and labels_ok
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["1", "8"])
+def test_transfer2_store_to_disk_many_batches(oracle, tmp_path, monkeypatch, devices):
+    """store_transfers_to_disk with many batches in flight on one or several GPUs: the writer thread puts every finished
+    batch at its offset of the per-type files (the file order is the pair order, transfer2.c:2940-2957), levels are freed
+    once written (:565), and the files read back through transfer2_load_transfers_from_disk equal the oracle."""
+    wl = _tiny(sources_k3_interpolation="cubic")
+    proj = oracle.build_projection(wl)
+    ref, _ = oracle.OracleRun(wl, proj).run()
+    monkeypatch.setenv("SONG_LOS_MODE", "exact")
+    monkeypatch.setenv("SONG_LOS_BATCH_UNITS", "131")
+    monkeypatch.setenv("SONG_LOS_CHUNKS_PER_DEVICE", "3")
+    monkeypatch.setenv("SONG_LOS_DEVICES", devices)
+    got, count, _ = dropin_lib.run_transfer2(wl, Projection(proj.rows, proj.index_xmin, proj.x_size), store_dir=str(tmp_path))
+    assert np.array_equal(got, ref)
+    for tt in (0, wl.layout.tt2_size - 1):
+        f = tmp_path / f"transfers_{tt:03d}.dat"
+        assert f.stat().st_size == 8 * wl.n_units and np.array_equal(np.fromfile(f), ref[tt])
