@@ -46,6 +46,7 @@
  *   song_los_set_bessel_table / song_los_integrate_k3   the k3 integral of bispectra2_intrinsic_integrate_over_k3
  *                              (bispectra2.c:1279-1375 with bessel2_convolution, bessel2.c:499-605) on the transfer
  *                              functions still in device memory
+ *   song_los_cl_sum            the (k1,k2,k3) sum of spectra2_cls (spectra2.c:241-570), likewise
  *
  * Error convention (reference: _SUCCESS_/_FAILURE_ + ErrorMsg): every function
  * returns SONG_LOS_SUCCESS (0) or SONG_LOS_FAILURE (1); the text is available from
@@ -275,6 +276,24 @@ int  song_los_set_bessel_table(song_los_ctx *ctx, int l1_size, const double *con
                                const double *x_min_l1, const int *x_size_l1);
 int  song_los_integrate_k3(song_los_ctx *ctx, const song_los_k3_request *request, double *out /* [n_requests][r_size][n_pairs] */);
 float song_los_last_k3_ms(const song_los_ctx *ctx);   /* device time of the last song_los_integrate_k3 kernel */
+
+/* ---- the (k1,k2,k3) sum of the intrinsic C_l ----
+ * spectra2_cls (source/spectra2.c:241-570) sums total_factor(k1,k2,k3,m) T^X_lm T^Y_lm over the nodes of the transfer
+ * functions, with the trapezoidal steps of :377-381, :409-414, :471-492 (triangular edges included) and the primordial
+ * spectra of :389-398, :421-430.  song_los_cl_sum returns the contribution of the pairs of the batch in the current slot;
+ * the caller adds the batches (and GPUs).  The sum runs over k3 in the reference's order inside a pair and over the pairs
+ * in the reference's order; it is not the reference's single running sum, so agreement is to rounding (1e-13), and for
+ * m != 0 pow() is the device's. */
+typedef struct song_los_cl_request {
+  int n_requests;                  /* (index_ct, index_l, index_M) combinations */
+  const int *tt1, *tt2;            /* index_tt_1, index_tt_2 (spectra2.c:336-353)                 [n_requests] */
+  const int *m;                    /* ptr2->m[index_M] of each request                           [n_requests] */
+  int rescale_cmb_sources;         /* ppt2->rescale_cmb_sources (:505) */
+  int k_size; const double *k;     /* ppt2->k */
+  const double *primordial;        /* primordial_spectrum_at_k (ppm, index_md, linear, k[i]) per k index [k_size] */
+  const int *pair_k1, *pair_k2;    /* index_k1, index_k2 of every pair of the batch */
+} song_los_cl_request;
+int  song_los_cl_sum(song_los_ctx *ctx, const song_los_cl_request *request, double *out /* [n_requests] */);
 
 /* Runs the engine's kernels on an external CUDA stream (a cudaStream_t passed as void*),
    so that a caller's own events see the work.  NULL restores the engine's stream. */

@@ -149,6 +149,11 @@ int oracle_integral_over_k3(int n_pairs, const int *k3_size, const long *tr_off,
                             const double *j, const double *ddj, double x_min_l1, double xx_step, int cubic,
                             int r_size, const double *r, int abs_M3, double M3_coefficient, double *out);
 
+/* spectra2.c:241-570 (spectra2_cls), one (index_ct, index_l, index_M): the (k1,k2,k3) sum over the given pairs */
+double oracle_spectra2_cl(int n_pairs, const int *pair_k1, const int *pair_k2, int k_size, const double *k,
+                          const double *primordial, const int *k3_size, const long *tr_off, const double *k3_tr,
+                          const double *transfer_1, const double *transfer_2, int m, int rescale_cmb_sources);
+
 /* ---------------------------------------------------------------------------------------
  * transfer2.c restatement
  * ------------------------------------------------------------------------------------- */

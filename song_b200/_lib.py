@@ -102,6 +102,12 @@ class K3Request(C.Structure):
                 ("M3_coefficient", c_double_p), ("r_size", C.c_int), ("r", c_double_p)]
 
 
+class ClRequest(C.Structure):
+    """struct song_los_cl_request (include/song_los.h)."""
+    _fields_ = [("n_requests", C.c_int), ("tt1", c_int_p), ("tt2", c_int_p), ("m", c_int_p), ("rescale_cmb_sources", C.c_int),
+                ("k_size", C.c_int), ("k", c_double_p), ("primordial", c_double_p), ("pair_k1", c_int_p), ("pair_k2", c_int_p)]
+
+
 class K3Params(C.Structure):
     _fields_ = [
         ("tau0", C.c_double), ("tau_rec", C.c_double), ("rs_rec", C.c_double),
@@ -147,7 +153,7 @@ LOS_SYMBOLS = [
     "song_los_device_info", "song_los_version",
     "song_los_submit", "song_los_wait", "song_los_host_alloc", "song_los_host_free", "song_los_max_batch_units", "song_los_reserve", "song_los_get_projection_dd",
     "song_los_device_count", "song_los_set_time", "song_los_config_matches", "song_los_drop_projection_rows",
-    "song_los_select_slot", "song_los_set_bessel_table", "song_los_integrate_k3", "song_los_last_k3_ms",
+    "song_los_select_slot", "song_los_set_bessel_table", "song_los_integrate_k3", "song_los_last_k3_ms", "song_los_cl_sum",
 ]
 HOST_SYMBOLS = ["song_host_k3_size", "song_host_k3_list", "song_host_k3_sizes", "song_host_k3_lists",
                 "song_host_bessel2_prepare", "song_host_bessel2_free", "song_host_bessel2_upload",
@@ -201,6 +207,7 @@ def los():
         lib.song_los_select_slot.argtypes = [vp, C.c_int]
         lib.song_los_set_bessel_table.argtypes = [vp, C.c_int, C.POINTER(c_double_p), C.POINTER(c_double_p), c_double_p, c_int_p]
         lib.song_los_integrate_k3.argtypes = [vp, C.POINTER(K3Request), c_double_p]
+        lib.song_los_cl_sum.argtypes = [vp, C.POINTER(ClRequest), c_double_p]
         lib.song_los_last_k3_ms.argtypes = [vp]
         lib.song_los_last_k3_ms.restype = C.c_float
         _los = lib

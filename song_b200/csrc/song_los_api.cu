@@ -220,6 +220,7 @@ extern "C" int song_los_destroy(song_los_ctx *ctx)
   ctx->d_jl1.release(); ctx->d_ddjl1.release(); ctx->d_jl1_xmin.release(); ctx->d_k3req_coef.release(); ctx->d_k3_r.release();
   ctx->d_k3_out.release(); ctx->d_jl1_off.release(); ctx->d_jl1_size.release(); ctx->d_k3req_tt.release();
   ctx->d_k3req_row.release(); ctx->d_k3req_has.release();
+  ctx->d_cl_k.release(); ctx->d_cl_prim.release(); ctx->d_cl_step.release(); ctx->d_cl_k1.release(); ctx->d_cl_k2.release();
   if (ctx->fast) fast_state_destroy(ctx->fast);
   if (ctx->d_proj_rows) cudaFree(ctx->d_proj_rows);
   if (ctx->d_proj_ddrows) cudaFree(ctx->d_proj_ddrows);

@@ -88,6 +88,8 @@ struct song_los_ctx {
   DevBuf<double> d_jl1, d_ddjl1, d_jl1_xmin, d_k3req_coef, d_k3_r, d_k3_out;
   DevBuf<int64_t> d_jl1_off;
   DevBuf<int> d_jl1_size, d_k3req_tt, d_k3req_row, d_k3req_has;
+  DevBuf<double> d_cl_k, d_cl_prim, d_cl_step;   // spectra2_cls sum: k grid, primordial spectrum, k3 steps
+  DevBuf<int> d_cl_k1, d_cl_k2;
   float k3_ms = 0.f;
 };
 

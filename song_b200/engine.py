@@ -190,6 +190,20 @@ class LosEngine:
         self.k3_ms = float(self.lib.song_los_last_k3_ms(self.ctx))
         return out
 
+    def cl_sum(self, wl, tt1, tt2, m, primordial, rescale_cmb_sources: bool = True) -> np.ndarray:
+        """spectra2_cls's (k1,k2,k3) sum over the pairs of `wl` (the batch of the last compute): one number per request."""
+        tt1 = np.ascontiguousarray(tt1, dtype=np.int32); tt2 = np.ascontiguousarray(tt2, dtype=np.int32)
+        m = np.ascontiguousarray(m, dtype=np.int32)
+        k = np.ascontiguousarray(wl.k, dtype=np.float64); prim = np.ascontiguousarray(primordial, dtype=np.float64)
+        k1 = np.ascontiguousarray(wl.pairs[:, 0], dtype=np.int32); k2 = np.ascontiguousarray(wl.pairs[:, 1], dtype=np.int32)
+        rq = _lib.ClRequest(n_requests=int(tt1.size), tt1=_lib.iptr(tt1), tt2=_lib.iptr(tt2), m=_lib.iptr(m),
+                            rescale_cmb_sources=int(rescale_cmb_sources), k_size=int(k.size), k=_lib.dptr(k),
+                            primordial=_lib.dptr(prim), pair_k1=_lib.iptr(k1), pair_k2=_lib.iptr(k2))
+        out = np.empty(tt1.size, dtype=np.float64)
+        self._check(self.lib.song_los_cl_sum(self.ctx, C.byref(rq), _lib.dptr(out)))
+        self.k3_ms = float(self.lib.song_los_last_k3_ms(self.ctx))
+        return out
+
     def max_batch_units(self, mode: int, src_doubles_per_unit: float) -> int:
         n = C.c_int64(0)
         self._check(self.lib.song_los_max_batch_units(self.ctx, mode, float(src_doubles_per_unit), C.byref(n)))

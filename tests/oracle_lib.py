@@ -99,6 +99,8 @@ def lib():
         L.oracle_bessel2_convolution.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, C.c_int, C.c_double, dp]
         L.oracle_integral_over_k3.argtypes = [C.c_int, ip, lp, dp, dp, dp, dp, C.c_double, C.c_double, C.c_int, C.c_int, dp,
                                               C.c_int, C.c_double, dp]
+        L.oracle_spectra2_cl.argtypes = [C.c_int, ip, ip, C.c_int, dp, dp, ip, lp, dp, dp, dp, C.c_int, C.c_int]
+        L.oracle_spectra2_cl.restype = C.c_double
         L.oracle_free = C.CDLL(None).free
         L.oracle_free.argtypes = [C.c_void_p]
         _lib = L
@@ -319,3 +321,13 @@ def integral_over_k3(wl, transfer_row, j_row, ddj_row, x_min_l1, r, abs_M3=0, M3
     if rc:
         raise RuntimeError("oracle_integral_over_k3: an integration grid has less than two elements")
     return out
+
+
+def spectra2_cl(wl, transfer_1, transfer_2, m, primordial, rescale_cmb_sources=True) -> float:
+    """spectra2_cls (spectra2.c:241-570) for one (index_ct, index_l, index_M) over the pairs of `wl`."""
+    k1 = np.ascontiguousarray(wl.pairs[:, 0], dtype=np.int32); k2 = np.ascontiguousarray(wl.pairs[:, 1], dtype=np.int32)
+    tr_off = wl.tr_off.astype(np.int64)
+    t1 = np.ascontiguousarray(transfer_1, dtype=np.float64); t2 = np.ascontiguousarray(transfer_2, dtype=np.float64)
+    prim = np.ascontiguousarray(primordial, dtype=np.float64); k = np.ascontiguousarray(wl.k, dtype=np.float64)
+    return float(lib().oracle_spectra2_cl(wl.n_pairs, _i(k1), _i(k2), int(k.size), _d(k), _d(prim), _i(wl.k3_tr_size), _l(tr_off),
+                                          _d(wl.k3_tr), _d(t1), _d(t2), int(m), int(rescale_cmb_sources)))

@@ -107,3 +107,65 @@ def test_k3_integral_error_convention(oracle):
     with pytest.raises(SongLosError, match="x_max"):
         eng.integrate_k3([0], [0], [1e6], wl.n_pairs)
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# spectra2_cls (source/spectra2.c:241-570) on the device-resident transfer functions
+# ---------------------------------------------------------------------------------------------------------------
+def primordial(k, A_s=2.1e-9, n_s=0.965, k_pivot=0.05):
+    """primordial_spectrum_at_k for the analytic power law of CLASS (the module itself is outside the path)."""
+    return A_s * (k / k_pivot) ** (n_s - 1.0)
+
+
+@pytest.mark.parametrize("kw", [dict(sources_k3_interpolation="cubic"), dict(modes_song=[0, 1, 2], has_source_B=True)],
+                         ids=["scalar", "m012"])
+def test_intrinsic_cl_sum(oracle, kw):
+    """TT, EE, TE (and BB for m != 0) of every l, m against the oracle's restatement of the reference loops: the same
+    products in the same k3 order per pair, pairs added in the reference order; not one running sum, hence 1e-12."""
+    wl = workload.fill_sources(workload.build_grids(configs.tiny(**kw)))
+    oproj = oracle.build_projection(wl)
+    eng = LosEngine(wl, device=0)
+    eng.set_projection(Projection(oproj.rows, oproj.index_xmin, oproj.x_size))
+    T = eng.transfer_pairs(wl, mode=MODE_EXACT)
+    lay = wl.layout
+    prim = primordial(wl.k)
+    tt1, tt2, ms = [], [], []
+    blocks = [(lay.index_tt2_T, lay.index_tt2_T), (lay.index_tt2_E, lay.index_tt2_E), (lay.index_tt2_T, lay.index_tt2_E)]
+    if lay.has_source_B:
+        blocks.append((lay.index_tt2_B, lay.index_tt2_B))
+    for a, b in blocks:
+        for il, l in enumerate(lay.l):
+            for im, m in enumerate(lay.m):
+                if m > l or (a == getattr(lay, "index_tt2_B", -1) and lay.has_source_B and m == 0):
+                    continue
+                tt1.append(a + int(lay.lm_array[il, im])); tt2.append(b + int(lay.lm_array[il, im])); ms.append(int(m))
+    for rescale in (True, False):
+        got = eng.cl_sum(wl, tt1, tt2, ms, prim, rescale_cmb_sources=rescale)
+        ref = np.asarray([oracle.spectra2_cl(wl, T[a], T[b], m, prim, rescale) for a, b, m in zip(tt1, tt2, ms)])
+        assert np.any(ref != 0)
+        scale = np.abs(ref).max()
+        assert np.max(np.abs(got - ref)) <= 1e-12 * scale, float(np.max(np.abs(got - ref)) / scale)
+        m0 = np.asarray(ms) == 0
+        assert np.max(np.abs(got[m0] - ref[m0]) / np.maximum(np.abs(ref[m0]), 1e-300)) < 1e-12
+    eng.close()
+
+
+def test_intrinsic_cl_sum_is_additive_over_batches(oracle):
+    """The caller adds the contributions of batches / GPUs: two halves of the pairs give the whole."""
+    wl = workload.fill_sources(workload.build_grids(configs.tiny(sources_k3_interpolation="cubic")))
+    oproj = oracle.build_projection(wl)
+    eng = LosEngine(wl, device=0)
+    eng.set_projection(Projection(oproj.rows, oproj.index_xmin, oproj.x_size))
+    lay = wl.layout
+    prim = primordial(wl.k)
+    tt = [lay.index_tt2_T + int(lay.lm_array[il, 0]) for il in range(lay.l_size)]
+    ms = [0] * len(tt)
+    eng.transfer_pairs(wl, mode=MODE_FAST)
+    whole = eng.cl_sum(wl, tt, tt, ms, prim)
+    parts = np.zeros_like(whole)
+    for idx in (np.arange(0, wl.n_pairs // 2), np.arange(wl.n_pairs // 2, wl.n_pairs)):
+        sub = wl.select(idx)
+        eng.transfer_pairs(sub, mode=MODE_FAST)
+        parts += eng.cl_sum(sub, tt, tt, ms, prim)
+    assert np.max(np.abs(parts - whole)) <= 1e-12 * np.abs(whole).max()
+    eng.close()
