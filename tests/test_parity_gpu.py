@@ -173,3 +173,14 @@ def test_fast_rejects_cubic_bessel_interpolation(oracle):
     from song_b200._lib import SongLosError
     with pytest.raises(SongLosError, match="linear Bessel interpolation"):
         run_both(oracle, p, mode=MODE_FAST, spline_J=True)
+
+
+def test_long_coarse_k3_grids(oracle):
+    """k3_size above 256 (a high-resolution sources2 sampling): the spline workspaces move from thread-local memory to
+    global scratch; the reference's array_spline_table_columns has no size limit (transfer2.c:2639)."""
+    p = configs.tiny(k3_size_min=300, sources_k3_interpolation="cubic")
+    wl, ref, got = run_both(oracle, p, mode=MODE_EXACT)
+    assert wl.k3_pt_size.max() > 256
+    assert np.array_equal(got, ref)
+    wl, ref, got = run_both(oracle, p, kind="noise", mode=MODE_FAST)
+    assert rel_err_above_floor(got, ref) < REL_TOL
