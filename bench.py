@@ -6,8 +6,11 @@
 
 A "step" is one pass of the hot path (k3 spline, k3 sort, source interpolation, DMMA LOS kernel) over ONE
 workload of synthetic input: BASELINE.json configs[3] (ini/intrinsic.ini + pre/sn_pol_5percent_lmax3000.pre, T+E,
-2.5e9 integrals), the largest configuration that fits one B200.  With N ranks the SAME workload is split by (k1,k2)
-pair with the static schedule of the drop-in (song_host_schedule_pairs): strong scaling, no data-path collective,
+2.5e9 integrals), the largest configuration that fits one B200.  With N ranks the SAME workload is split with the
+static schedule of song_b200/shard.py (C: los_host.c) into (k1,k2)-pair groups x k3 bands: pairs as transfer2_init
+splits them (song_host_schedule_pairs), and -- when pairs alone would leave fewer than 80 k3 values per projection-table
+row on a GPU, which is what the tensor-core kernel's efficiency follows -- bands of the fine k3 axis
+(song_host_band_edges; N=4: 2 x 2, N=8: 2 x 4 at configs[3]).  Strong scaling, no data-path collective,
 value = integrals of the workload / max-over-ranks time; the per-GPU results are then gathered on rank 0 (NCCL, timed
 separately) and spot-checked against the CPU oracle in the reference pair order.
 
@@ -315,12 +318,28 @@ def split_resident(sub, cap_units: int, n_slots: int = 3):
     return [sub.select(np.arange(cuts[i], cuts[i + 1])) for i in range(len(cuts) - 1)]
 
 
+def unit_cost(grids, own, first, last) -> float:
+    """Cost of the fine-grid slices [first, last) of pairs `own` in the model of the static schedule (los_host.c)."""
+    c = 0.0
+    for ip, a, b in zip(own, first, last):
+        k = grids.k3_tr[int(grids.tr_off[ip]) + int(a):int(grids.tr_off[ip]) + int(b)]
+        c += float(np.sum(0.65 + 0.35 * np.minimum(1.0, k * grids.cosmo["tau0"] / grids.layout.l.max())))
+    return c
+
+
 def spot_check(O, sub, got_of_pair, rows, xmin, xsize, n_check: int, run_scale=None):
     """Oracle on a few pairs of `sub`; got_of_pair(i) -> [tt2][k3 of pair i].  Max relative error above 1e-6 of the
-    per-(l,m) maximum (BASELINE.json criterion; the maximum is taken over the checked pairs unless run_scale is given)."""
+    per-(l,m) maximum (BASELINE.json criterion; the maximum is taken over the checked pairs unless run_scale is given).
+    When `sub` holds slices of fine grids (k3 bands) the oracle runs on the whole pairs and its result is cut."""
     idx = np.unique(np.linspace(0, sub.n_pairs - 1, min(n_check, sub.n_pairs)).astype(int))
     oproj = O.OracleProjection(rows, xmin, xsize, None)
-    ref, _ = O.OracleRun(sub.select(idx), oproj).run()
+    if sub.parent is not None:
+        par = sub.parent.select(sub.parent_pair[idx])
+        whole, _ = O.OracleRun(par, oproj).run()
+        ref = np.concatenate([whole[:, int(par.tr_off[q]) + int(sub.slice_start[i]):int(par.tr_off[q]) + int(sub.slice_start[i]) + int(sub.k3_tr_size[i])]
+                              for q, i in enumerate(idx)], axis=1)
+    else:
+        ref, _ = O.OracleRun(sub.select(idx), oproj).run()
     got = np.concatenate([got_of_pair(int(i)) for i in idx], axis=1)
     scale = run_scale if run_scale is not None else np.abs(ref).max(axis=1, keepdims=True)
     m = np.abs(ref) > 1e-6 * scale
@@ -342,18 +361,28 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
     p = configs.get(name)
     grids = workload.build_grids(p, max_pairs=args.max_pairs)
     full_pairs = grids.n_pairs == grids.k.size * (grids.k.size + 1) // 2
-    chunks = (args.chunks_per_rank or shard.chunks_per_device(grids, world)) if world > 1 else 1
-    dev_of_pair, load = shard.schedule_pairs(shard.pair_cost(grids), world, chunks)
-    owned = np.nonzero(dev_of_pair == rank)[0]
+    # static schedule of the run: pair groups x k3 bands (song_b200/shard.py, los_host.h); GPU = group * n_bands + band
+    sched = shard.schedule_bands(grids, world, n_bands=(args.bands or None), chunks_per_group=(args.chunks_per_rank or None))
+    n_groups, n_bands, group_of_pair, band_cut = sched
+    chunks = (args.chunks_per_rank or shard.chunks_per_device(grids, n_groups)) if n_groups > 1 else 1
+    owned, own_first, own_last = shard.shard_units_index(grids, rank, world, sched)
+    load = np.array([unit_cost(grids, *shard.shard_units_index(grids, r, world, sched)) for r in range(world)])
     want_e2e = e2e_steps > 0 and full_pairs and os.path.exists(dropin_lib.PATH)
     if rank == 0 and want_e2e:
         workload.fill_sources(grids)                 # rank 0 also needs the whole run for transfer2_init
-        sub = grids.select(owned) if world > 1 else grids
+        whole = grids.select(owned) if world > 1 else grids
     else:
-        sub = workload.fill_sources(grids.select(owned))
+        whole = workload.fill_sources(grids.select(owned))
+    # the pairs this GPU touches (whole: coarse grids and sources) and, with several bands, the slices of their fine grids
+    sub = whole if n_bands == 1 else whole.select_units(np.arange(whole.n_pairs), own_first, own_last)
     eng = LosEngine(sub, device=D.local_rank)
     b2 = Bessel2(sub).init(eng)                      # bessel2_init: host j_l1 + 3j, device J_Llm assembly
-    cap = int(D.reduce(float(eng.max_batch_units(mode, sub.src.size / max(sub.n_units, 1))), "min"))    # one rule on every rank
+    # resident batches of this GPU: as few as fit (1, 2 or 3 engine slots), the same number and bound on every rank
+    units_max = int(D.reduce(float(sub.n_units), "max"))
+    for n_slots in (1, 2, 3):
+        cap = int(D.reduce(float(eng.max_batch_units(mode, sub.src.size / max(sub.n_units, 1), n_slots)), "min"))
+        if -(-units_max // n_slots) <= int(0.97 * cap) or n_slots == 3:        # 3 % slack: batches are cut at pair boundaries
+            break
     batches = split_resident(sub, cap)
     peaks = eng.measure_peaks()
     stream = torch.cuda.current_stream()
@@ -418,7 +447,10 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
     parity = spot_check(O, sub, local_pair, rows, xmin, xsize, args.check_pairs)
     # ---- the k3 integral of the intrinsic bispectrum on the transfer functions still in HBM ----
     k3int = None
-    if args.k3_integral and rank == 0:
+    if args.k3_integral and rank == 0 and n_bands > 1:
+        k3int = {"skipped": "the k3 integral of a pair needs its whole fine grid (trapezoidal weights of bispectra2.c:1279-1326); with k3 bands "
+                            "a GPU holds slices -- run with --bands 1 for this leg"}
+    elif args.k3_integral and rank == 0:
         ht = b2.host_tables()
         eng.set_bessel_table(ht["j_l1"], ht["x_min_l1"])
         lay = sub.layout
@@ -476,15 +508,20 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
                 workload.fill_sources(grids)
             tt2 = grids.layout.tt2_size
             def gathered_pair(ip):
-                r = int(dev_of_pair[ip])
-                own_r = np.nonzero(dev_of_pair == r)[0]
-                sizes_r = grids.k3_tr_size[own_r].astype(np.int64)
-                cuts = split_bounds(sizes_r, cap)               # every rank cut its shard with the same rule
-                j = int(np.searchsorted(own_r, ip))
-                ib = int(np.searchsorted(cuts, j, side="right")) - 1
-                units_b = int(sizes_r[cuts[ib]:cuts[ib + 1]].sum())
-                a = int(sizes_r[cuts[ib]:j].sum()); n = int(sizes_r[j])
-                return bufs[ib][r][:units_b * tt2].view(tt2, units_b)[:, a:a + n].cpu().numpy()
+                parts = []                                          # the pair's slices, band by band, from the GPUs that own them
+                for band in range(n_bands):
+                    r = int(group_of_pair[ip]) * n_bands + band
+                    own_r, first_r, last_r = shard.shard_units_index(grids, r, world, sched)
+                    j = int(np.searchsorted(own_r, ip))
+                    if j >= own_r.size or own_r[j] != ip:
+                        continue                                    # this band does not touch the pair
+                    sizes_r = (last_r - first_r).astype(np.int64)
+                    cuts = split_bounds(sizes_r, cap)               # every rank cut its shard with the same rule
+                    ib = int(np.searchsorted(cuts, j, side="right")) - 1
+                    units_b = int(sizes_r[cuts[ib]:cuts[ib + 1]].sum())
+                    a = int(sizes_r[cuts[ib]:j].sum()); n = int(sizes_r[j])
+                    parts.append(bufs[ib][r][:units_b * tt2].view(tt2, units_b)[:, a:a + n].cpu().numpy())
+                return np.concatenate(parts, axis=1)
             gather["parity_of_gathered_array"] = spot_check(O, grids, gathered_pair, rows, xmin, xsize, max(args.check_pairs, world))
         del bufs, pads
     del results
@@ -533,7 +570,14 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
         os.environ["SONG_LOS_DEVICES"] = str(world)
         os.environ["SONG_LOS_MODE"] = args.mode
         if "LOCAL_RANK" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
+            # torchrun exports OMP_NUM_THREADS=1 to its workers; a SONG run uses the machine (the drop-in sizes its own
+            # packing teams explicitly, bessel2_init and the harness use the default team)
             os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+            try:
+                import ctypes
+                ctypes.CDLL("libgomp.so.1").omp_set_num_threads(os.cpu_count() or 1)
+            except OSError:
+                pass
         t0 = time.perf_counter()
         h = dropin_lib.Harness(grids, None, verbose=0, keep_sources=True)      # bessel2_init (drop-in) leaves the engines on the GPUs
         if args.dropin_verbose:
@@ -576,7 +620,8 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
                "ms_per_step": e2e_ms, "ms_each_step": each, "steps": e2e_steps, "n_gpus": world,
                "api": "transfer2_init(ppr, ppr2, pba, pth, ppt, ppt2, pbs, pbs2, ptr, ptr2) of the drop-in module on SONG structures "
                       "(tests/harness/dropin_harness.c plays main/song.c:100-106): sources in pageable ppt2->sources, result in "
-                      "ptr2->transfer; packing, H2D, kernels and D2H of every batch inside the call; host clock around the call",
+                      "ptr2->transfer; packing, H2D, kernels and D2H of every batch inside the call; host clock around the call; "
+                      "schedule of the drop-in: (k1,k2) pairs only (every source byte crosses PCIe once), SONG_LOS_DEVICES GPUs from one process",
                "first_call_ms": first_ms, "first_call_note": "includes page-locking the staging and the ptr2->transfer slabs (kept in a pool afterwards)",
                "bessel2_init_s": t_b2, "result_read_ms_per_step": t_read / e2e_steps * 1e3, "checksum_abs_sum": cs,
                "count_memorised_transfers": count, "labels_ok": labels_ok, "parity": e2e_parity, "clocks_gpu0_1s_period": e2e_clocks}
@@ -597,7 +642,8 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
         return None
     return {
         "workload": name, "value": value, "ms_per_step": ms_step, "steps": steps, "warmup": warmup,
-        "chunks_per_gpu": chunks, "per_rank_ms": rank_ms, "imbalance_max_over_mean": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
+        "chunks_per_gpu": chunks, "n_groups": n_groups, "n_bands": n_bands, "per_rank_ms": rank_ms,
+        "source_replication": float(sum(shard.shard_units_index(grids, r, world, sched)[0].size for r in range(world)) / max(grids.n_pairs, 1)), "imbalance_max_over_mean": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
         "schedule_load_max_over_mean": float(load.max() / load.mean()),
         "gpu_launches": launches_total, "describe": workload.describe(grids), "parity": parity, "gather": gather,
         "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "setup_s": t_setup, "k3_integral": k3int, "clocks": clocks,
@@ -618,6 +664,8 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--e2e-steps", type=int, default=5, help="timed transfer2_init calls (at most --steps)")
     ap.add_argument("--chunks-per-rank", type=int, default=0, help="contiguous pair chunks per GPU in the static schedule (0: the rule of transfer2_init)")
+    ap.add_argument("--bands", type=int, default=0, help="k3 bands of the (pair groups x k3 bands) schedule (0: song_host_band_count, the "
+                                                        "fewest that keep 80 k3 values per projection-table row on every GPU)")
     ap.add_argument("--check-pairs", type=int, default=8, help="pairs checked against the CPU oracle per workload")
     ap.add_argument("--no-k3-integral", dest="k3_integral", action="store_false", help="skip the bispectrum k3-integral leg (SURVEY 8f rank 1)")
     ap.add_argument("--dropin-verbose", type=int, default=0, help="debug: ptr2->transfer2_verbose of the last timed transfer2_init")
@@ -679,8 +727,11 @@ def main():
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": dict(r["describe"], workload=args.workload, mode=args.mode,
-                           parallelism=f"ONE workload split by (k1,k2) pair over {world} GPU(s): static schedule of song_host_schedule_pairs "
-                                       f"({r['chunks_per_gpu']} contiguous chunk(s) per GPU, LPT, cost = k3 values x active multipole share), no data-path collective; results gathered on rank 0",
+                           parallelism=f"ONE workload over {world} GPU(s) = {r['n_groups']} (k1,k2)-pair group(s) x {r['n_bands']} k3 band(s): pairs by "
+                                       f"song_host_schedule_pairs ({r['chunks_per_gpu']} contiguous chunk(s) per group, LPT, cost = k3 values x active multipole share), "
+                                       f"bands = cost quantiles of a group's fine k3 values (song_host_band_edges; a band keeps the k3 density per "
+                                       f"projection-table row, the coarse sources of a pair are resident on every band it crosses: x{r['source_replication']:.2f}); "
+                                       f"no data-path collective; results gathered on rank 0",
                            l2_policy="inputs larger than L2: each step streams ~%.1f GB per GPU (sources, transposed sources, "
                                      "interpolated slab, projection table, output) against 126 MB of L2" % r["l2_gb_streamed"],
                            tau_sampling="synthetic, geometric 230->330 then linear ->700 Mpc",

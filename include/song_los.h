@@ -34,7 +34,8 @@
  *                              batch n+1 to the device and of batch n-1 to the host overlap the
  *                              kernels of batch n (the k1 levels are independent, transfer2.c:549-551)
  *   song_los_host_alloc/_free  page-locked staging memory for ppt2->sources / ptr2->transfer slabs
- *   song_los_max_batch_units   how many k3 values of consecutive k1 levels fit in one batch
+ *   song_los_max_batch_units   how many k3 values of consecutive k1 levels fit in one batch (three batches in flight)
+ *   song_los_max_resident_units  the same bound when only n_slots batches are held at once
  *   song_los_reserve           device buffers for the largest batch, allocated before the k1 loop starts
  *   song_los_device_count      how many GPUs the (k1,k2) pairs can be spread over (the k1 modes are independent,
  *                              transfer2.c:549-551)
@@ -132,7 +133,13 @@ typedef struct song_los_config {
  *   sources       src + src_off[p] + tp*tau_size*np + itau*np + j (ppt2->sources[tp][k1][k2])
  *   fine grid     k3_tr + tr_off[p],  k3_tr_size[p] doubles      (transfer2_get_k3_list)
  *   physical range [phys_start[p], phys_start[p]+phys_size[p])   (ptr2->k_physical_*_k1k2)
- * Output unit index of (p, i) is tr_off[p] + i; the transfer array is [tt2_size][n_units]. */
+ * Output unit index of (p, i) is tr_off[p] + i; the transfer array is [tt2_size][n_units].
+ *
+ * A batch may hold only a SLICE [a, b) of a pair's fine grid (the k3 bands of the multi-GPU schedule,
+ * song_host_band_edges): k3_tr then holds the b-a values of the slice, phys_start[p] is given relative to the
+ * slice (ptr2->k_physical_start_k1k2 - a: it may be negative or beyond the slice), and phys_k_first / phys_k_last
+ * carry the k3 of the pair's first / last physical point, which the flat extrapolation of transfer2.c:2743-2757
+ * interpolates the sources at and which may lie outside the slice.  Both are NULL for whole grids. */
 typedef struct song_los_batch {
   int n_pairs;
   const int *k3_pt_size;
@@ -148,6 +155,8 @@ typedef struct song_los_batch {
   const double *k3_pt;
   const double *k3_tr;
   const double *src;
+  const double *phys_k_first;      /* optional [n_pairs]: k3 of the first physical point of the pair's FULL grid */
+  const double *phys_k_last;       /* optional [n_pairs]: k3 of the last one; both or neither */
 } song_los_batch;
 
 /* Device-side timings of the last song_los_compute, in milliseconds (CUDA events on the
@@ -240,6 +249,7 @@ int  song_los_host_free(void *ptr);
  * one compute fit in the free device memory.  src_doubles_per_unit = (source doubles of the run) /
  * (k3 values of the run), i.e. tp2_size * tau_size * <k3_pt> / <k3_tr>.  Needs the projection tables. */
 int  song_los_max_batch_units(song_los_ctx *ctx, int mode, double src_doubles_per_unit, int64_t *units);
+int  song_los_max_resident_units(song_los_ctx *ctx, int mode, double src_doubles_per_unit, int n_slots, int64_t *units);
 
 /* Pre-allocates all device buffers for a pipeline of `n_in_flight` (1..SONG_LOS_MAX_IN_FLIGHT) batches of up to the
  * given sizes (pairs, k3 values, coarse k3 points, source doubles).  Optional, but without it a batch larger than every earlier one makes the

@@ -74,6 +74,8 @@ class LosBatch(C.Structure):
         ("k3_pt", c_double_p),
         ("k3_tr", c_double_p),
         ("src", c_double_p),
+        ("phys_k_first", c_double_p),     # optional: slices of fine grids (k3 bands), see include/song_los.h
+        ("phys_k_last", c_double_p),
     ]
 
 
@@ -151,7 +153,7 @@ LOS_SYMBOLS = [
     "song_los_compute", "song_los_download", "song_los_transfer_pairs",
     "song_los_device_result", "song_los_copy_result", "song_los_set_stream", "song_los_measure_peaks",
     "song_los_device_info", "song_los_version",
-    "song_los_submit", "song_los_wait", "song_los_host_alloc", "song_los_host_free", "song_los_max_batch_units", "song_los_reserve", "song_los_get_projection_dd",
+    "song_los_submit", "song_los_wait", "song_los_host_alloc", "song_los_host_free", "song_los_max_batch_units", "song_los_max_resident_units", "song_los_reserve", "song_los_get_projection_dd",
     "song_los_device_count", "song_los_set_time", "song_los_config_matches", "song_los_drop_projection_rows",
     "song_los_select_slot", "song_los_set_bessel_table", "song_los_integrate_k3", "song_los_last_k3_ms", "song_los_cl_sum",
 ]
@@ -199,6 +201,7 @@ def los():
         lib.song_los_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
         lib.song_los_host_free.argtypes = [vp]
         lib.song_los_max_batch_units.argtypes = [vp, C.c_int, C.c_double, c_int64_p]
+        lib.song_los_max_resident_units.argtypes = [vp, C.c_int, C.c_double, C.c_int, c_int64_p]
         lib.song_los_reserve.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64]
         lib.song_los_device_count.argtypes = [c_int_p]
         lib.song_los_set_time.argtypes = [vp, C.c_double, C.c_int, C.c_double]
@@ -237,6 +240,9 @@ def host():
         lib.song_host_lpt_schedule.argtypes = [c_int64_p, C.c_int, C.c_int, c_int_p, c_int64_p]
         lib.song_host_schedule_pairs.argtypes = [c_int64_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int64_p]
         lib.song_host_pair_costs.argtypes = [C.c_int, c_int_p, c_double_p, c_double_p, C.c_double, C.c_int, c_int64_p]
+        lib.song_host_band_edges.argtypes = [C.c_int, c_int_p, c_int64_p, c_double_p, C.c_void_p, C.c_double, C.c_int, C.c_int, c_double_p]
+        lib.song_host_band_cuts.argtypes = [C.c_int, c_int_p, c_int64_p, c_double_p, C.c_int, c_double_p, c_int_p]
+        lib.song_host_band_count.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int]
         lib.compat_drc3jj.argtypes = [C.c_double] * 4 + [c_double_p, c_double_p, c_double_p, C.c_int]
         lib.compat_bessel_j.argtypes = [C.c_int, C.c_double]
         lib.compat_bessel_j.restype = C.c_double

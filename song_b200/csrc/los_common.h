@@ -44,6 +44,7 @@ struct Batch {
   const int *np, *nt, *phys_start, *phys_size;
   const int64_t *pt_off, *tr_off, *src_off;
   const double *k3_pt, *k3_tr, *src, *dd;
+  const double *phys_k_first, *phys_k_last;   // k3 the wings of the flat extrapolation are interpolated at (transfer2.c:2743-2757)
   int64_t n_units;
   double *out;                  // [tt2_size][n_units]
 };

@@ -115,9 +115,8 @@ __global__ void __launch_bounds__(EXACT_THREADS) los_exact_kernel(ExactParams P)
 
   if (tid < nunits) {
     int it = u0 + tid;
-    int ite = it;
-    if (P.flat_extrap) ite = max(first, min(last, it));                   // transfer2.c:2743-2757
-    double ke = kt[ite];
+    double ke = kt[it];
+    if (P.flat_extrap) ke = (it < first) ? P.b.phys_k_first[p] : (it > last) ? P.b.phys_k_last[p] : ke;   // transfer2.c:2743-2757
     int j = 0;
     while ((j + 1) < np && kp[j + 1] < ke) ++j;                           // transfer2.c:2683 (strict <)
     if (j > np - 2) j = np - 2;
@@ -293,9 +292,8 @@ __global__ void __launch_bounds__(EXACT_THREADS) los_exact_resample_kernel(Exact
 
     if (tid < nunits) {
       int it = u0 + tid;
-      int ite = it;
-      if (P.flat_extrap) ite = max(first, min(last, it));                 // transfer2.c:2743-2757
-      double ke = kt[ite];
+      double ke = kt[it];
+      if (P.flat_extrap) ke = (it < first) ? P.b.phys_k_first[p] : (it > last) ? P.b.phys_k_last[p] : ke;   // transfer2.c:2743-2757
       int j = 0;
       while ((j + 1) < np && kp[j + 1] < ke) ++j;                         // transfer2.c:2683 (strict <)
       if (j > np - 2) j = np - 2;

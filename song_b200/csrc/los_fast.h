@@ -33,8 +33,16 @@ int fast_prepare(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
 int64_t fast_bytes_per_unit(const FastState *fs);
 int fast_reserve(FastState *fs, int64_t n_units, int64_t n_src, int64_t n_pt, std::string &err);
 constexpr int FAST_MAX_EVENTS = 32;     // 5 phase boundaries + 2 per (column block, K chunk) launch
+constexpr int FAST_MAX_BLOCKS = 12;     // (field, m) column blocks
+// Pipelined runs (song_los_submit): the rows [tt_lo, tt_lo + tt_n) of a column block are final once the block's last K
+// chunk has run, so their device->host copy is enqueued on the copy stream right there, under the kernels of the next
+// block, instead of after the whole batch.  fast_enqueue fills the ranges it has taken care of.
+struct FastEarlyOut {
+  cudaStream_t st_d2h; double *host; cudaEvent_t *ev;     // ev: [FAST_MAX_BLOCKS], caller-owned
+  int n_ranges; int tt_lo[FAST_MAX_BLOCKS], tt_n[FAST_MAX_BLOCKS];
+};
 int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, int device_sms, cudaStream_t st,
-                 cudaEvent_t *ev /* [FAST_MAX_EVENTS] */, int *n_launches, int *n_chunks, std::string &err);
+                 cudaEvent_t *ev /* [FAST_MAX_EVENTS] */, int *n_launches, int *n_chunks, FastEarlyOut *early, std::string &err);
 int fast_collect(cudaEvent_t *ev, int n_chunks, song_los_timing *tm, std::string &err);
 
 }  // namespace songlos

@@ -49,7 +49,7 @@ namespace songlos {
 // ---------------------------------------------------------------------------------------------
 // device structures
 // ---------------------------------------------------------------------------------------------
-constexpr int TC_MAX_BLOCKS = 12;
+constexpr int TC_MAX_BLOCKS = FAST_MAX_BLOCKS;
 constexpr int TC_MAX_GROUPS = 12;         // (block, K chunk): one source slab and one tensor map each
 constexpr int TC_MAX_PASSES = 24;
 constexpr int TC_MAX_TERMS = 64;          // K terms of one block (2 per kc)
@@ -379,9 +379,8 @@ __global__ void tc_prep_units_kernel(Batch b, const int *perm, const int *unit_p
   const double *kt = b.k3_tr + b.tr_off[p];
   int np = b.np[p];
   int first = b.phys_start[p], last = first + b.phys_size[p] - 1;
-  int ie = i;
-  if (flat_extrap) ie = max(first, min(last, i));
-  double ke = kt[ie];
+  double ke = kt[i];
+  if (flat_extrap) ke = (i < first) ? b.phys_k_first[p] : (i > last) ? b.phys_k_last[p] : ke;   // k3 of the first / last physical point
   // j = number of interior coarse points kp[i], 1 <= i <= np-2, strictly below ke (strict <, :2683)
   int lo = 1, hi = np - 1;
   while (lo < hi) { int mid = (lo + hi) >> 1; if (kp[mid] < ke) lo = mid + 1; else hi = mid; }
@@ -953,6 +952,7 @@ struct FastState {
   int64_t s_doubles_per_unit = 0;        // sum over groups of tau_size * tpp
   int wm = 8, wn = 1, nw = 8;
   int kcs_max = 1, nsb_pass_max = 1, tpp_max = 4, n_cols_total = 0, tau_size = 0;
+  int blk_tt_lo[TC_MAX_BLOCKS] = {0}, blk_tt_n[TC_MAX_BLOCKS] = {0};   // rows of `out` a block owns when they are one run (else n = 0)
   Buf<double> Jq, keys_out, S, slot_sign, col_scale;
   Buf<double2> CSD;
   Buf<int> col_tt, col_l, col_lm, term_col0, nact, perm_in, perm, unit_pair, slot_tp, jcount;
@@ -1011,6 +1011,12 @@ static int build_layout(FastState *fs, const FastHostLayout &h, const ExactParam
       }
       B.ncols = (int)col_tt.size() - B.col_off;
       if (B.ncols == 0) continue;
+      {
+        bool run = true;
+        for (int c = 1; c < B.ncols; ++c) run = run && (col_tt[B.col_off + c] == col_tt[B.col_off + c - 1] + 1);
+        fs->blk_tt_lo[fs->n_blocks] = col_tt[B.col_off];
+        fs->blk_tt_n[fs->n_blocks] = run ? B.ncols : 0;
+      }
       // segments: (J index, source base, sign)
       struct Seg { int J, tp; double sign; };
       std::vector<Seg> segs;
@@ -1203,8 +1209,9 @@ int fast_reserve(FastState *fs, int64_t U, int64_t n_src, int64_t n_pt, std::str
 // Enqueues the whole FAST pipeline on `st` and returns without waiting; ev[0..4] (caller-owned) are
 // recorded at the phase boundaries and read later by fast_collect.
 int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, int device_sms, cudaStream_t st,
-                 cudaEvent_t *ev, int *n_launches, int *n_chunks_out, std::string &err)
+                 cudaEvent_t *ev, int *n_launches, int *n_chunks_out, FastEarlyOut *early, std::string &err)
 {
+  if (early) early->n_ranges = 0;
   if (fast_prepare(fs, h, P, st, err)) return 1;
   const Batch &b = P.b;
   const int64_t U = b.n_units;
@@ -1419,6 +1426,16 @@ int fast_enqueue(FastState *fs, const FastHostLayout &h, const ExactParams &P, i
       }
       FCK(e);
       ++*n_launches;
+    }
+    // the block's rows are final: send them home under the kernels of the next block
+    if (early && fs->blk_tt_n[ib] > 0 && early->n_ranges < FAST_MAX_BLOCKS && !getenv("SONG_LOS_NO_EARLY_D2H")) {
+      const int k = early->n_ranges;
+      FCK(cudaEventRecord(early->ev[k], st));
+      FCK(cudaStreamWaitEvent(early->st_d2h, early->ev[k], 0));
+      FCK(cudaMemcpyAsync(early->host + (size_t)fs->blk_tt_lo[ib] * (size_t)U, b.out + (size_t)fs->blk_tt_lo[ib] * (size_t)U,
+                          (size_t)fs->blk_tt_n[ib] * (size_t)U * sizeof(double), cudaMemcpyDeviceToHost, early->st_d2h));
+      early->tt_lo[k] = fs->blk_tt_lo[ib]; early->tt_n[k] = fs->blk_tt_n[ib];
+      early->n_ranges = k + 1;
     }
   }
   FCK(cudaEventRecord(ev[4], st));

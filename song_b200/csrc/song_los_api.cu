@@ -212,6 +212,7 @@ extern "C" int song_los_destroy(song_los_ctx *ctx)
     if (S.h_meta) cudaFreeHost(S.h_meta);
     if (S.h_err) cudaFreeHost(S.h_err);
     for (cudaEvent_t e : {S.ev_h2d, S.ev_compute, S.ev_d2h, S.ev_h2d_start, S.ev_d2h_start}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : S.ev_blk) if (e) cudaEventDestroy(e);
     for (auto &e : S.ev_t) if (e) cudaEventDestroy(e);
   }
   if (ctx->st_h2d) cudaStreamDestroy(ctx->st_h2d);
@@ -432,15 +433,18 @@ static int validate_batch(song_los_ctx *ctx, const song_los_batch *b)
   if (b->n_pairs < 0) return ctx_fail(ctx, "song_los_upload_pairs: negative n_pairs");
   // consistency checks (the reference's class_test of transfer2.c:1766-1771 and layout checks)
   int64_t pt = 0, tr = 0, so = 0;
+  if ((b->phys_k_first == nullptr) != (b->phys_k_last == nullptr))
+    return ctx_fail(ctx, "song_los_upload_pairs: phys_k_first and phys_k_last come together");
+  const bool sliced = (b->phys_k_first != nullptr);     // slices of fine grids: the physical range may lie outside them
   const int need = (c.sources_k3_interpolation == SONG_LOS_INTERP_CUBIC) ? 4 : 2;
   for (int p = 0; p < b->n_pairs; ++p) {
     int np = b->k3_pt_size[p], nt = b->k3_tr_size[p];
     if (np < need)
       return ctx_fail(ctx, "pair %d: cannot do interpolation in k3 with just k3_size=%d values. Increase k3_size.", p, np);
     if (nt < 1) return ctx_fail(ctx, "pair %d: empty k3 grid", p);
-    if (b->phys_start[p] < 0 || b->phys_size[p] < 1 || b->phys_start[p] + b->phys_size[p] > nt)
+    if (b->phys_size[p] < 1 || (!sliced && (b->phys_start[p] < 0 || b->phys_start[p] + b->phys_size[p] > nt)))
       return ctx_fail(ctx, "pair %d: physical range [%d,+%d) outside the k3 grid of %d points", p, b->phys_start[p], b->phys_size[p], nt);
-    if (c.k3_extrapolation == SONG_LOS_NO_K3_EXTRAPOLATION && (b->phys_start[p] != 0 || b->phys_size[p] != nt))
+    if (c.k3_extrapolation == SONG_LOS_NO_K3_EXTRAPOLATION && !sliced && (b->phys_start[p] != 0 || b->phys_size[p] != nt))
       return ctx_fail(ctx, "pair %d: when no extrapolation is requested, all k's should be physical", p);
     if (b->pt_off[p] != pt || b->tr_off[p] != tr || b->src_off[p] != so)
       return ctx_fail(ctx, "pair %d: offsets are not the running sums of the sizes (packed layout expected)", p);
@@ -458,8 +462,8 @@ static int enqueue_upload(song_los_ctx *ctx, song_los_ctx::Slot &S, const song_l
   const song_los_config &c = ctx->cfg;
   if (validate_batch(ctx, b) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
   const size_t n = (size_t)b->n_pairs;
-  // packed per-pair arrays: 3 x int64 then 5 x int, one pinned staging buffer, one copy
-  const size_t meta_bytes = n * (3 * sizeof(int64_t) + 5 * sizeof(int));
+  // packed per-pair arrays: 3 x int64, 2 x double, then 5 x int, one pinned staging buffer, one copy
+  const size_t meta_bytes = n * (3 * sizeof(int64_t) + 2 * sizeof(double) + 5 * sizeof(int));
   if (meta_bytes > S.h_meta_cap) {
     if (S.h_meta) cudaFreeHost(S.h_meta);
     S.h_meta = nullptr; S.h_meta_cap = 0;
@@ -468,7 +472,12 @@ static int enqueue_upload(song_los_ctx *ctx, song_los_ctx::Slot &S, const song_l
   }
   CK(S.d_meta.reserve(std::max<size_t>(meta_bytes, 64)));
   int64_t *h64 = reinterpret_cast<int64_t *>(S.h_meta);
-  int *h32 = reinterpret_cast<int *>(S.h_meta + n * 3 * sizeof(int64_t));
+  double *hkf = reinterpret_cast<double *>(S.h_meta + n * 3 * sizeof(int64_t)), *hkl = hkf + n;
+  int *h32 = reinterpret_cast<int *>(S.h_meta + n * 5 * sizeof(int64_t));
+  for (size_t p = 0; p < n; ++p) {       // k3 of the first / last physical point (transfer2.c:2743-2757)
+    hkf[p] = b->phys_k_first ? b->phys_k_first[p] : b->k3_tr[b->tr_off[p] + b->phys_start[p]];
+    hkl[p] = b->phys_k_last ? b->phys_k_last[p] : b->k3_tr[b->tr_off[p] + b->phys_start[p] + b->phys_size[p] - 1];
+  }
   std::memcpy(h64, b->pt_off, n * 8); std::memcpy(h64 + n, b->tr_off, n * 8); std::memcpy(h64 + 2 * n, b->src_off, n * 8);
   std::memcpy(h32, b->k3_pt_size, n * 4); std::memcpy(h32 + n, b->k3_tr_size, n * 4);
   std::memcpy(h32 + 2 * n, b->phys_start, n * 4); std::memcpy(h32 + 3 * n, b->phys_size, n * 4);
@@ -482,7 +491,8 @@ static int enqueue_upload(song_los_ctx *ctx, song_los_ctx::Slot &S, const song_l
   if (n_tiles >= ((int64_t)1 << 31)) return ctx_fail(ctx, "song_los_upload_pairs: too many k3 tiles in one batch");
   S.n_tiles = (int)n_tiles; S.tiles_ready = false;
   int64_t *d64 = reinterpret_cast<int64_t *>(S.d_meta.p);
-  int *d32 = reinterpret_cast<int *>(S.d_meta.p + n * 3 * sizeof(int64_t));
+  int *d32 = reinterpret_cast<int *>(S.d_meta.p + n * 5 * sizeof(int64_t));
+  S.d_phys_k_first = reinterpret_cast<double *>(d64 + 3 * n); S.d_phys_k_last = S.d_phys_k_first + n;
   S.d_pt_off = d64; S.d_tr_off = d64 + n; S.d_src_off = d64 + 2 * n;
   S.d_np = d32; S.d_nt = d32 + n; S.d_phys_start = d32 + 2 * n; S.d_phys_size = d32 + 3 * n; S.d_tile_off = d32 + 4 * n;
 
@@ -506,6 +516,7 @@ static int enqueue_upload(song_los_ctx *ctx, song_los_ctx::Slot &S, const song_l
   S.hb.k3_pt_size = S.hb.k3_tr_size = S.hb.phys_start = S.hb.phys_size = nullptr;
   S.hb.pt_off = S.hb.tr_off = S.hb.src_off = nullptr;
   S.hb.k3_pt = S.hb.k3_tr = S.hb.src = nullptr;
+  S.hb.phys_k_first = S.hb.phys_k_last = nullptr;
   S.have_batch = true;
   S.have_result = false;
   return SONG_LOS_SUCCESS;
@@ -541,6 +552,7 @@ static void fill_params(song_los_ctx *ctx, const song_los_ctx::Slot &S, ExactPar
   P.b.n_pairs = S.hb.n_pairs; P.b.np = S.d_np; P.b.nt = S.d_nt;
   P.b.phys_start = S.d_phys_start; P.b.phys_size = S.d_phys_size;
   P.b.pt_off = S.d_pt_off; P.b.tr_off = S.d_tr_off; P.b.src_off = S.d_src_off;
+  P.b.phys_k_first = S.d_phys_k_first; P.b.phys_k_last = S.d_phys_k_last;
   P.b.k3_pt = S.d_k3_pt.p; P.b.k3_tr = S.d_k3_tr.p; P.b.src = S.d_src.p; P.b.dd = ctx->d_dd.p;
   P.b.n_units = S.hb.n_units; P.b.out = S.d_out.p;
   P.xx = ctx->d_xx.p; P.xx_size = c.xx_size; P.xx_step = c.xx_step;
@@ -583,8 +595,9 @@ static int report_device_errors(song_los_ctx *ctx, int h)
 }
 
 // kernels of one batch on the compute stream, after the slot's upload; records S.ev_compute.  No host wait.
-static int enqueue_compute(song_los_ctx *ctx, song_los_ctx::Slot &S, int mode)
+static int enqueue_compute(song_los_ctx *ctx, song_los_ctx::Slot &S, int mode, double *early_host = nullptr)
 {
+  S.early = songlos::FastEarlyOut{};
   if (!ctx->have_proj) return ctx_fail(ctx, "song_los_compute: projection functions not set (bessel2 first)");
   if (!S.have_batch) return ctx_fail(ctx, "song_los_compute: no pairs uploaded");
   const song_los_config &c = ctx->cfg;
@@ -652,7 +665,13 @@ static int enqueue_compute(song_los_ctx *ctx, song_los_ctx::Slot &S, int mode)
     std::string e;
     FastHostLayout h;
     fill_fast_layout(ctx, S, h);
-    if (fast_enqueue(ctx->fast, h, P, ctx->sm_count, st, S.ev_t, &t.n_launches, &S.n_chunks, e) != 0)
+    songlos::FastEarlyOut *early = nullptr;
+    if (early_host != nullptr) {
+      for (cudaEvent_t &ev : S.ev_blk) if (!ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      S.early.st_d2h = ctx->st_d2h; S.early.host = early_host; S.early.ev = S.ev_blk;
+      early = &S.early;
+    }
+    if (fast_enqueue(ctx->fast, h, P, ctx->sm_count, st, S.ev_t, &t.n_launches, &S.n_chunks, early, e) != 0)
       return ctx_fail(ctx, "%s", e.c_str());
     S.fast_timed = true;
   }
@@ -684,10 +703,23 @@ static int finish_compute(song_los_ctx *ctx, song_los_ctx::Slot &S)
 
 static int enqueue_download(song_los_ctx *ctx, song_los_ctx::Slot &S, double *transfer)
 {
-  size_t n = (size_t)S.hb.n_units * ctx->cfg.tt2_size;
+  const size_t U = (size_t)S.hb.n_units;
+  const int tt2 = ctx->cfg.tt2_size;
   CK(cudaStreamWaitEvent(ctx->st_d2h, S.ev_compute, 0));
-  CK(cudaEventRecord(S.ev_d2h_start, ctx->st_d2h));
-  if (n) CK(cudaMemcpyAsync(transfer, S.d_out.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->st_d2h));
+  const bool early = (S.early.n_ranges > 0 && S.early.host == transfer);
+  CK(cudaEventRecord(S.ev_d2h_start, ctx->st_d2h));          // ms_d2h: the rows that were not sent early
+  // rows the FAST path has not sent already (whole column blocks, enqueued as soon as they were final)
+  std::vector<unsigned char> sent((size_t)tt2, 0);
+  if (early)
+    for (int k = 0; k < S.early.n_ranges; ++k)
+      for (int tt = S.early.tt_lo[k]; tt < S.early.tt_lo[k] + S.early.tt_n[k] && tt < tt2; ++tt) sent[(size_t)tt] = 1;
+  for (int tt = 0; tt < tt2 && U > 0;) {
+    if (sent[(size_t)tt]) { ++tt; continue; }
+    int end = tt;
+    while (end < tt2 && !sent[(size_t)end]) ++end;
+    CK(cudaMemcpyAsync(transfer + (size_t)tt * U, S.d_out.p + (size_t)tt * U, (size_t)(end - tt) * U * sizeof(double), cudaMemcpyDeviceToHost, ctx->st_d2h));
+    tt = end;
+  }
   CK(cudaEventRecord(S.ev_d2h, ctx->st_d2h));
   return SONG_LOS_SUCCESS;
 }
@@ -726,7 +758,7 @@ extern "C" int song_los_submit(song_los_ctx *ctx, const song_los_batch *batch, i
   const int is = (ctx->n_in_flight == 0) ? ctx->cur : (ctx->cur + 1) % song_los_ctx::N_SLOTS;
   song_los_ctx::Slot &S = ctx->slot[is];
   if (enqueue_upload(ctx, S, batch) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
-  if (enqueue_compute(ctx, S, mode) != SONG_LOS_SUCCESS) { cudaDeviceSynchronize(); return SONG_LOS_FAILURE; }
+  if (enqueue_compute(ctx, S, mode, transfer) != SONG_LOS_SUCCESS) { cudaDeviceSynchronize(); return SONG_LOS_FAILURE; }
   if (enqueue_download(ctx, S, transfer) != SONG_LOS_SUCCESS) { cudaDeviceSynchronize(); return SONG_LOS_FAILURE; }
   S.in_flight = true;
   if (ctx->n_in_flight == 0) ctx->oldest = is;
@@ -821,7 +853,15 @@ extern "C" int song_los_reserve(song_los_ctx *ctx, int mode, int n_in_flight, in
 // fine grid of two slots + FAST intermediates; sources are accounted with the caller's ratio.
 extern "C" int song_los_max_batch_units(song_los_ctx *ctx, int mode, double src_doubles_per_unit, int64_t *units)
 {
+  return song_los_max_resident_units(ctx, mode, src_doubles_per_unit, song_los_ctx::N_SLOTS, units);
+}
+
+// The same bound for `n_slots` batches of that size held at once (1..3): a run whose batches stay resident in the slots
+// (bench.py's `value` leg, or a consumer that integrates over k3 on the device) needs fewer than the pipeline's three.
+extern "C" int song_los_max_resident_units(song_los_ctx *ctx, int mode, double src_doubles_per_unit, int n_slots, int64_t *units)
+{
   if (!ctx || !units) return ctx_fail(ctx, "song_los_max_batch_units: NULL argument");
+  if (n_slots < 1 || n_slots > song_los_ctx::N_SLOTS) return ctx_fail(ctx, "song_los_max_resident_units: n_slots must be 1..%d", song_los_ctx::N_SLOTS);
   CK(cudaSetDevice(ctx->device));
   if (!ctx->have_proj) return ctx_fail(ctx, "song_los_max_batch_units: projection functions not set");
   const song_los_config &c = ctx->cfg;
@@ -831,7 +871,7 @@ extern "C" int song_los_max_batch_units(song_los_ctx *ctx, int mode, double src_
   size_t held = 0;
   for (auto &S : ctx->slot) held += (S.d_k3_pt.cap + S.d_k3_tr.cap + S.d_src.cap + S.d_out.cap) * 8 + S.d_tiles.cap * 8;
   held += ctx->d_dd.cap * 8;
-  double per_unit = (double)song_los_ctx::N_SLOTS * (8.0 * c.tt2_size + 8.0 + 8.0 * src_doubles_per_unit);
+  double per_unit = (double)n_slots * (8.0 * c.tt2_size + 8.0 + 8.0 * src_doubles_per_unit);
   if (mode == SONG_LOS_MODE_FAST) {
     std::string e;
     song_los_ctx::Slot dummy;

@@ -55,12 +55,15 @@ struct song_los_ctx {
     DevBuf<unsigned char> d_meta;                               // packed per-pair arrays on the device
     int *d_np = nullptr, *d_nt = nullptr, *d_phys_start = nullptr, *d_phys_size = nullptr, *d_tile_off = nullptr;
     int64_t *d_pt_off = nullptr, *d_tr_off = nullptr, *d_src_off = nullptr;
+    double *d_phys_k_first = nullptr, *d_phys_k_last = nullptr;
     DevBuf<double> d_k3_pt, d_k3_tr, d_src, d_out;
     DevBuf<int2> d_tiles; int n_tiles = 0; bool tiles_ready = false;
     int max_np = 0;               // largest coarse k3 grid of the batch
     double k3_max = 0.;           // largest k3 of the batch (custom/bessel time sampling: grid size bound)
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr, ev_h2d_start = nullptr, ev_d2h_start = nullptr;
     cudaEvent_t ev_t[songlos::FAST_MAX_EVENTS]{};   // phase boundaries of this slot's compute
+    cudaEvent_t ev_blk[songlos::FAST_MAX_BLOCKS]{}; // column blocks whose rows travel home early (song_los_submit)
+    songlos::FastEarlyOut early{};                  // rows already enqueued for the device->host copy
     int n_chunks = 0;             // (column block, K chunk) launches of the last FAST compute
     int *h_err = nullptr;         // pinned copy of the device error flags after this slot's compute
     bool have_batch = false, have_result = false, in_flight = false, fast_timed = false, with_d2h = false;

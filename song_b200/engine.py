@@ -204,9 +204,10 @@ class LosEngine:
         self.k3_ms = float(self.lib.song_los_last_k3_ms(self.ctx))
         return out
 
-    def max_batch_units(self, mode: int, src_doubles_per_unit: float) -> int:
+    def max_batch_units(self, mode: int, src_doubles_per_unit: float, n_slots: int = 3) -> int:
+        """k3 values per batch so that `n_slots` batches (3: the pipeline of song_los_submit) fit in device memory."""
         n = C.c_int64(0)
-        self._check(self.lib.song_los_max_batch_units(self.ctx, mode, float(src_doubles_per_unit), C.byref(n)))
+        self._check(self.lib.song_los_max_resident_units(self.ctx, mode, float(src_doubles_per_unit), int(n_slots), C.byref(n)))
         return int(n.value)
 
     def reserve(self, mode: int, max_pairs: int, max_units: int, max_pt: int, max_src: int, n_in_flight: int = 3):

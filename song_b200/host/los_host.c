@@ -260,3 +260,81 @@ int song_host_pair_costs(int n_pairs, const int *k3_tr_size, const double *k_min
   }
   return 0;
 }
+
+/* ---- k3 bands (los_host.h) ---- */
+static double band_unit_cost(double k3, double tau0, int l_max)
+{
+  double active = (l_max > 0) ? k3 * tau0 / (double)l_max : 1.0;
+  if (active > 1.0) active = 1.0;
+  if (active < 0.0) active = 0.0;
+  return 0.65 + 0.35 * active;
+}
+
+int song_host_band_edges(int n_pairs, const int *k3_tr_size, const int64_t *tr_off, const double *k3_tr, const unsigned char *pair_in_group,
+                         double tau0, int l_max, int n_bands, double *edges)
+{
+  if (!k3_tr_size || !tr_off || !k3_tr || n_pairs < 0 || n_bands < 1 || (n_bands > 1 && !edges)) return 1;
+  if (n_bands == 1) return 0;
+  /* cost histogram over the k3 axis (linear bins: the fine grids are linear in k3), then the quantiles */
+  enum { NBINS = 1 << 16 };
+  double kmin = 0., kmax = 0.; int any = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    if ((pair_in_group && !pair_in_group[p]) || k3_tr_size[p] < 1) continue;
+    const double a = k3_tr[tr_off[p]], b = k3_tr[tr_off[p] + k3_tr_size[p] - 1];
+    if (!any || a < kmin) kmin = a;
+    if (!any || b > kmax) kmax = b;
+    any = 1;
+  }
+  if (!any || !(kmax > kmin)) { for (int r = 0; r + 1 < n_bands; ++r) edges[r] = kmax; return 0; }
+  double *hist = (double *)calloc(NBINS, sizeof(double));
+  if (!hist) return 1;
+  const double scale = (double)NBINS / (kmax - kmin);
+  double total = 0.;
+  for (int p = 0; p < n_pairs; ++p) {
+    if (pair_in_group && !pair_in_group[p]) continue;
+    const double *k = k3_tr + tr_off[p];
+    for (int i = 0; i < k3_tr_size[p]; ++i) {
+      int bin = (int)((k[i] - kmin) * scale);
+      if (bin < 0) bin = 0;
+      if (bin >= NBINS) bin = NBINS - 1;
+      const double c = band_unit_cost(k[i], tau0, l_max);
+      hist[bin] += c; total += c;
+    }
+  }
+  double acc = 0.; int r = 0;
+  for (int bin = 0; bin < NBINS && r + 1 < n_bands; ++bin) {
+    acc += hist[bin];
+    while (r + 1 < n_bands && acc >= total * (double)(r + 1) / (double)n_bands) edges[r++] = kmin + (double)(bin + 1) / scale;
+  }
+  for (; r + 1 < n_bands; ++r) edges[r] = kmax;
+  free(hist);
+  return 0;
+}
+
+int song_host_band_cuts(int n_pairs, const int *k3_tr_size, const int64_t *tr_off, const double *k3_tr,
+                        int n_bands, const double *edges, int *cut)
+{
+  if (!k3_tr_size || !tr_off || !k3_tr || !cut || n_pairs < 0 || n_bands < 1 || (n_bands > 1 && !edges)) return 1;
+  for (int p = 0; p < n_pairs; ++p) {
+    const double *k = k3_tr + tr_off[p];
+    const int n = k3_tr_size[p];
+    int *c = cut + (size_t)p * (size_t)(n_bands + 1);
+    c[0] = 0; c[n_bands] = n;
+    for (int r = 1; r < n_bands; ++r) {
+      int lo = c[r - 1], hi = n;                       /* first index with k >= edges[r-1]; edges ascend */
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] < edges[r - 1]) lo = mid + 1; else hi = mid; }
+      c[r] = lo;
+    }
+  }
+  return 0;
+}
+
+int song_host_band_count(int64_t total_units, int xx_size, int n_dev, int dense_per_row)
+{
+  if (n_dev <= 1 || xx_size < 1 || dense_per_row < 1) return 1;
+  for (int bands = 1; bands <= n_dev; ++bands) {
+    if (n_dev % bands) continue;
+    if ((double)total_units / (double)n_dev * (double)bands / (double)xx_size >= (double)dense_per_row) return bands;
+  }
+  return n_dev;
+}

@@ -67,6 +67,27 @@ int song_host_schedule_pairs(const int64_t *cost, int n_pairs, int n_dev, int ch
 int song_host_pair_costs(int n_pairs, const int *k3_tr_size, const double *k_min, const double *k_max, double tau0, int l_max,
                          int64_t *cost);
 
+/* ---- k3 bands: the second axis of the multi-GPU schedule ----
+   The tensor-core kernel works on the k3-sorted values of a batch and its efficiency follows the number of values that
+   share a row of the projection table.  Splitting a run by pairs alone divides that density by the number of GPUs;
+   splitting the k3 axis into bands keeps it: a band holds, of EVERY pair of its group, the fine-grid values in
+   [edge[r], edge[r+1]) -- fewer table rows for the same number of values.  The price is that the coarse sources of a
+   pair are needed by every band it crosses (the k3 spline is global in the pair).  n_dev GPUs = n_groups pair groups
+   (song_host_schedule_pairs) x n_bands bands.
+
+   song_host_band_edges: the n_bands - 1 interior edges that split the cost of the given fine-grid values evenly;
+   cost of a value = 0.65 + 0.35 min(1, k3 tau0 / l_max) as in song_host_pair_costs.  pair_in_group: NULL = all pairs,
+   else only pairs with pair_in_group[p] != 0 are counted.
+   song_host_band_cuts: cut[p * (n_bands + 1) + r] = first fine-grid index of pair p with k3 >= edge[r]
+   (cut[.. + 0] = 0, cut[.. + n_bands] = k3_tr_size[p]); grids are ascending (transfer2.c:1727). */
+int song_host_band_edges(int n_pairs, const int *k3_tr_size, const int64_t *tr_off, const double *k3_tr, const unsigned char *pair_in_group,
+                         double tau0, int l_max, int n_bands, double *edges);
+int song_host_band_cuts(int n_pairs, const int *k3_tr_size, const int64_t *tr_off, const double *k3_tr,
+                        int n_bands, const double *edges, int *cut);
+/* how many k3 bands for n_dev GPUs: the smallest divisor of n_dev that keeps `dense_per_row` fine-grid values per row of
+   the projection table on every GPU (total_units / n_dev * bands / xx_size), 1 when pairs alone are dense enough */
+int song_host_band_count(int64_t total_units, int xx_size, int n_dev, int dense_per_row);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,54 @@ def schedule_pairs(cost, n_ranks: int, chunks_per_rank: int = 3):
     return dev, load
 
 
+DENSE_K3_PER_ROW = 80      # fine-grid values per projection-table row a GPU should keep (the whole lmax3000 run in 2 batches: 85)
+
+
+def band_count(wl, n_dev: int, dense_per_row: int = DENSE_K3_PER_ROW) -> int:
+    """k3 bands of the (pair groups x k3 bands) schedule for n_dev GPUs (C: song_host_band_count)."""
+    return int(_lib.host().song_host_band_count(int(wl.n_units), int(wl.xx.size), int(n_dev), int(dense_per_row)))
+
+
+def schedule_bands(wl, n_dev: int, n_bands: int | None = None, chunks_per_group: int | None = None):
+    """The static schedule of a run on n_dev GPUs as n_groups pair groups x n_bands k3 bands (los_host.h).  Returns
+    (n_groups, n_bands, group_of_pair, cut) with cut[p, r]..cut[p, r+1] the fine-grid slice of pair p in band r; the
+    band edges are the cost quantiles of each group's own k3 values.  GPU d = group * n_bands + band."""
+    n_bands = band_count(wl, n_dev) if n_bands is None else int(n_bands)
+    assert n_dev % n_bands == 0, "the number of GPUs must be a multiple of the number of k3 bands"
+    n_groups = n_dev // n_bands
+    cost = pair_cost(wl)
+    chunks = chunks_per_group if chunks_per_group else (chunks_per_device(wl, n_groups) if n_groups > 1 else 1)
+    group_of_pair, _ = schedule_pairs(cost, n_groups, chunks)
+    cut = np.zeros((wl.n_pairs, n_bands + 1), dtype=np.int32)
+    tr_off = np.ascontiguousarray(wl.tr_off, dtype=np.int64); nt = np.ascontiguousarray(wl.k3_tr_size, dtype=np.int32)
+    for g in range(n_groups):
+        mask = np.ascontiguousarray(group_of_pair == g, dtype=np.uint8)
+        edges = np.zeros(max(n_bands - 1, 1))
+        cg = np.zeros_like(cut)
+        h = _lib.host()
+        if h.song_host_band_edges(wl.n_pairs, _lib.iptr(nt), _lib.lptr(tr_off), _lib.dptr(wl.k3_tr), mask.ctypes.data_as(_lib.C.c_void_p),
+                                  float(wl.cosmo["tau0"]), int(wl.layout.l.max()), n_bands, _lib.dptr(edges)) or \
+           h.song_host_band_cuts(wl.n_pairs, _lib.iptr(nt), _lib.lptr(tr_off), _lib.dptr(wl.k3_tr), n_bands, _lib.dptr(edges), _lib.iptr(cg)):
+            raise _lib.SongLosError("song_host_band_edges / song_host_band_cuts: bad arguments")
+        cut[mask != 0] = cg[mask != 0]
+    return n_groups, n_bands, group_of_pair, cut
+
+
+def shard_units(wl, rank: int, world: int, n_bands: int | None = None, schedule=None):
+    """The part of `wl` GPU `rank` computes under the (pair groups x k3 bands) schedule: (sub-workload, pair indices in
+    wl, first, last) -- sub is wl.select(pairs) when the run has a single band, else the slices [first, last) of the
+    pairs' fine grids (pairs the band does not touch are left out)."""
+    n_groups, nb, group_of_pair, cut = schedule if schedule is not None else schedule_bands(wl, world, n_bands)
+    g, r = rank // nb, rank % nb
+    own = np.nonzero(group_of_pair == g)[0]
+    first, last = cut[own, r].astype(np.int64), cut[own, r + 1].astype(np.int64)
+    keep = last > first
+    own, first, last = own[keep], first[keep], last[keep]
+    if nb == 1:
+        return wl.select(own), own, first, last
+    return wl.select_units(own, first, last), own, first, last
+
+
 def shard_pairs(wl, rank: int, world: int, chunks_per_rank: int = 3) -> np.ndarray:
     """Indices (ascending, i.e. reference loop order) of the pairs rank `rank` owns: a few contiguous runs."""
     dev, _ = schedule_pairs(pair_cost(wl), world, chunks_per_rank if world > 1 else 1)
@@ -86,6 +134,45 @@ def gather_transfers(local: np.ndarray, wl, owned: np.ndarray, rank: int, world:
         part = bufs[r][:sizes[r]].cpu().numpy().reshape(tt2, -1)
         _scatter_into(full, part, wl, own_r)
     return full
+
+
+def gather_band_transfers(local: np.ndarray, wl, rank: int, world: int, schedule, dist=None, device="cpu"):
+    """gather_transfers for the (pair groups x k3 bands) schedule: `local` is [tt2_size][units of this rank's slices] as
+    shard_units lays them out; rank 0 assembles ptr2->transfer as [tt2_size][n_units] in the reference order."""
+    import torch
+    tt2 = wl.layout.tt2_size
+    parts = [shard_units_index(wl, r, world, schedule) for r in range(world)]       # known to every rank
+    sizes = [int((last - first).sum()) * tt2 for _, first, last in parts]
+    n_max = max(sizes)
+    buf = torch.zeros(n_max, dtype=torch.float64, device=device)
+    buf[:local.size] = torch.from_numpy(np.ascontiguousarray(local).reshape(-1)).to(device)
+    if world > 1:
+        bufs = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, bufs, dst=0)
+    else:
+        bufs = [buf]
+    if rank != 0:
+        return None
+    full = np.full((tt2, wl.n_units), np.nan)
+    for r in range(world):
+        own, first, last = parts[r]
+        part = bufs[r][:sizes[r]].cpu().numpy().reshape(tt2, -1)
+        o = 0
+        for ip, a, b in zip(own, first, last):
+            t = int(wl.tr_off[ip])
+            full[:, t + a:t + b] = part[:, o:o + (b - a)]
+            o += b - a
+    return full
+
+
+def shard_units_index(wl, rank: int, world: int, schedule):
+    """(pair indices, first, last) of shard_units without building the sub-workload."""
+    n_groups, nb, group_of_pair, cut = schedule
+    g, r = rank // nb, rank % nb
+    own = np.nonzero(group_of_pair == g)[0]
+    first, last = cut[own, r].astype(np.int64), cut[own, r + 1].astype(np.int64)
+    keep = last > first
+    return own[keep], first[keep], last[keep]
 
 
 def _scatter_into(full, part, wl, owned):

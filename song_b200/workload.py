@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import dataclasses
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -261,6 +262,14 @@ class Workload:
     k_min_tr: np.ndarray
     k_max_tr: np.ndarray
     src: np.ndarray = None       # packed [pair][tp][tau][k3_pt]
+    # slices of fine grids (k3 bands, song_b200/shard.py): k3 of the first / last physical point of every pair's FULL grid
+    # (phys_start is then relative to the slice and may lie outside it), the parent workload, and for every pair of this
+    # workload its index in the parent and the first unit of the slice inside the parent pair's fine grid
+    phys_k_first: np.ndarray = None
+    phys_k_last: np.ndarray = None
+    parent: "Workload" = None
+    parent_pair: np.ndarray = None
+    slice_start: np.ndarray = None
 
     @property
     def n_pairs(self):
@@ -280,6 +289,9 @@ class Workload:
     def select(self, idx) -> "Workload":
         """The sub-workload made of pairs `idx` (packed arrays rebuilt)."""
         idx = np.asarray(idx, dtype=np.int64)
+        if idx.size == self.n_pairs and np.array_equal(idx, np.arange(self.n_pairs)):      # all pairs: no copy of the big arrays
+            return dataclasses.replace(self, pairs=self.pairs.copy(), k3_tr_size=self.k3_tr_size.copy(), tr_off=self.tr_off.copy(),
+                                       phys_start=self.phys_start.copy(), phys_size=self.phys_size.copy())
         tp2, ntau = self.layout.tp2_size, self.tau.size
         np_ = self.k3_pt_size[idx]
         nt_ = self.k3_tr_size[idx]
@@ -292,12 +304,37 @@ class Workload:
         src = None
         if self.src is not None:
             src = np.concatenate([self.src[self.src_off[i]:self.src_off[i] + int(self.k3_pt_size[i]) * tp2 * ntau] for i in idx]) if idx.size else np.zeros(0)
+        sl = {}
+        if self.parent is not None:                   # pairs of a sliced workload keep their slices
+            sl = dict(phys_k_first=np.ascontiguousarray(self.phys_k_first[idx]), phys_k_last=np.ascontiguousarray(self.phys_k_last[idx]),
+                      parent=self.parent, parent_pair=self.parent_pair[idx], slice_start=self.slice_start[idx])
         return Workload(name=self.name, params=self.params, cosmo=self.cosmo, layout=self.layout, k=self.k,
                         tau=self.tau, xx=self.xx, xx_step=self.xx_step, xx_max=self.xx_max,
                         pairs=self.pairs[idx], k3_pt_size=np.ascontiguousarray(np_), k3_tr_size=np.ascontiguousarray(nt_),
                         phys_start=np.ascontiguousarray(self.phys_start[idx]), phys_size=np.ascontiguousarray(self.phys_size[idx]),
                         pt_off=pt_off, tr_off=tr_off, src_off=src_off, k3_pt=np.ascontiguousarray(k3_pt),
-                        k3_tr=np.ascontiguousarray(k3_tr), k_min_tr=self.k_min_tr[idx], k_max_tr=self.k_max_tr[idx], src=src)
+                        k3_tr=np.ascontiguousarray(k3_tr), k_min_tr=self.k_min_tr[idx], k_max_tr=self.k_max_tr[idx], src=src, **sl)
+
+    def select_units(self, idx, first, last) -> "Workload":
+        """The sub-workload made of the fine-grid slices [first[i], last[i]) of pairs `idx` (a k3 band of the multi-GPU
+        schedule): coarse grids and sources stay whole -- the k3 spline needs the whole column -- the fine grid is cut and
+        the physical range is re-expressed relative to the slice (include/song_los.h, song_los_batch)."""
+        assert self.parent is None, "slices of slices are not needed"
+        idx = np.asarray(idx, dtype=np.int64); first = np.asarray(first, dtype=np.int64); last = np.asarray(last, dtype=np.int64)
+        assert np.all(first >= 0) and np.all(last <= self.k3_tr_size[idx]) and np.all(last > first)
+        sub = self.select(idx)
+        nt = (last - first).astype(np.int32)
+        sub.tr_off = np.concatenate([[0], np.cumsum(nt)[:-1]]).astype(np.int64) if idx.size else np.zeros(0, np.int64)
+        sub.k3_tr = np.ascontiguousarray(np.concatenate([self.k3_tr[self.tr_off[i] + a:self.tr_off[i] + b] for i, a, b in zip(idx, first, last)])
+                                         if idx.size else np.zeros(0))
+        ps, pz = self.phys_start[idx].astype(np.int64), self.phys_size[idx].astype(np.int64)
+        sub.phys_k_first = np.ascontiguousarray(self.k3_tr[self.tr_off[idx] + ps])
+        sub.phys_k_last = np.ascontiguousarray(self.k3_tr[self.tr_off[idx] + ps + pz - 1])
+        sub.phys_start = np.ascontiguousarray((ps - first).astype(np.int32))
+        sub.k3_tr_size = np.ascontiguousarray(nt)
+        sub.k_min_tr = np.array([sub.k3_tr[o] for o in sub.tr_off]); sub.k_max_tr = np.array([sub.k3_tr[o + n - 1] for o, n in zip(sub.tr_off, nt)])
+        sub.parent = self; sub.parent_pair = idx.copy(); sub.slice_start = first.copy()
+        return sub
 
 
 def k3_params_of(p, cosmo, k, xx_max, xx_step) -> _lib.K3Params:
@@ -423,7 +460,9 @@ def make_batch(wl: Workload) -> _lib.LosBatch:
         phys_start=_lib.iptr(wl.phys_start), phys_size=_lib.iptr(wl.phys_size),
         pt_off=_lib.lptr(wl.pt_off), tr_off=_lib.lptr(wl.tr_off), src_off=_lib.lptr(wl.src_off),
         n_pt_total=int(wl.k3_pt.size), n_units=int(wl.k3_tr.size), n_src_total=int(wl.src.size),
-        k3_pt=_lib.dptr(wl.k3_pt), k3_tr=_lib.dptr(wl.k3_tr), src=_lib.dptr(wl.src))
+        k3_pt=_lib.dptr(wl.k3_pt), k3_tr=_lib.dptr(wl.k3_tr), src=_lib.dptr(wl.src),
+        phys_k_first=None if wl.phys_k_first is None else _lib.dptr(wl.phys_k_first),
+        phys_k_last=None if wl.phys_k_last is None else _lib.dptr(wl.phys_k_last))
 
 
 def describe(wl: Workload) -> dict:

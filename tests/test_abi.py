@@ -39,7 +39,7 @@ def test_struct_sizes_match_the_header_layout():
     # natural alignment of the C structs, computed independently of ctypes
     assert C.sizeof(_lib.K3Range) == 8 + 8 + 4 + 4 + 4 + 4
     assert C.sizeof(_lib.LosTiming) == 6 * 4 + 4 + 4 + 8 + 8 + 4 + 4
-    assert C.sizeof(_lib.LosBatch) == 8 + 7 * 8 + 3 * 8 + 3 * 8
+    assert C.sizeof(_lib.LosBatch) == 8 + 7 * 8 + 3 * 8 + 3 * 8 + 2 * 8      # + phys_k_first, phys_k_last (slices of fine grids)
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -184,3 +184,39 @@ def test_long_coarse_k3_grids(oracle):
     assert np.array_equal(got, ref)
     wl, ref, got = run_both(oracle, p, kind="noise", mode=MODE_FAST)
     assert rel_err_above_floor(got, ref) < REL_TOL
+
+
+@pytest.mark.parametrize("n_bands", [2, 3])
+def test_k3_band_slices_match_whole_pairs(oracle, n_bands):
+    """(pair groups x k3 bands) schedule, song_b200/shard.py: every GPU gets slices of the pairs' fine grids.  The slices
+    of all bands, computed in separate batches, must reproduce the oracle on the whole pairs -- including the wings of
+    the flat extrapolation (transfer2.c:2743-2757), whose sources are interpolated at the first / last PHYSICAL k3 of
+    the pair, a point that usually lies in another band (song_los_batch.phys_k_first / phys_k_last)."""
+    from song_b200 import shard
+    wl = workload.build_grids(configs.tiny(sources_k3_interpolation="cubic"))
+    workload.fill_sources(wl, kind="noise")
+    assert np.any(wl.phys_start > 0) and np.any(wl.phys_start + wl.phys_size < wl.k3_tr_size)     # there are wings on both sides
+    oproj = oracle.build_projection(wl)
+    ref, _ = oracle.OracleRun(wl, oproj).run()
+    sched = shard.schedule_bands(wl, 2 * n_bands, n_bands=n_bands)                                # two pair groups as well
+    eng = LosEngine(wl, device=0)
+    eng.set_projection(Projection(oproj.rows, oproj.index_xmin, oproj.x_size, oproj.ddrows))
+    slices_without_their_physical_end = 0
+    for mode in (MODE_EXACT, MODE_FAST):
+        full = np.full_like(ref, np.nan)
+        for rank in range(2 * n_bands):
+            sub, own, first, last = shard.shard_units(wl, rank, 2 * n_bands, schedule=sched)
+            slices_without_their_physical_end += int(np.sum((sub.phys_start < 0) | (sub.phys_start + sub.phys_size > sub.k3_tr_size)))
+            got = eng.transfer_pairs(sub, mode=mode)
+            o = 0
+            for ip, a, b in zip(own, first, last):
+                t = int(wl.tr_off[ip])
+                full[:, t + a:t + b] = got[:, o:o + (b - a)]
+                o += b - a
+        assert not np.isnan(full).any()
+        if mode == MODE_EXACT:
+            assert np.array_equal(full, ref)
+        else:
+            assert rel_err_above_floor(full, ref) < REL_TOL
+    assert slices_without_their_physical_end > 0          # the case the two extra arrays exist for
+    eng.close()

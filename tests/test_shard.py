@@ -58,6 +58,89 @@ def test_lpt_balance_on_baseline_workload():
     assert sum(o.size for o in own) == wl.n_pairs and np.array_equal(np.sort(np.concatenate(own)), np.arange(wl.n_pairs))
 
 
+def test_band_schedule_properties():
+    """(pair groups x k3 bands): every fine-grid value belongs to exactly one GPU, bands are k3 intervals, the slices of a
+    pair tile its grid, the cost is balanced, and the band count follows the density rule of song_host_band_count."""
+    wl = workload.build_grids(configs.get("sn_t_10percent_lmax2000"))
+    assert shard.band_count(wl, 1) == 1
+    assert shard.band_count(wl, 8, dense_per_row=1) == 1            # pairs alone are dense enough
+    assert shard.band_count(wl, 8, dense_per_row=10 ** 9) == 8      # never more bands than GPUs
+    for n_dev, nb in ((2, 2), (4, 2), (8, 4), (8, 8), (6, 3)):
+        sched = shard.schedule_bands(wl, n_dev, n_bands=nb)
+        n_groups, n_bands, group_of_pair, cut = sched
+        assert n_groups * n_bands == n_dev and n_bands == nb
+        assert np.all(cut[:, 0] == 0) and np.all(cut[:, -1] == wl.k3_tr_size) and np.all(np.diff(cut, axis=1) >= 0)
+        seen = np.zeros(wl.n_units, dtype=np.int32)
+        cost = np.zeros(n_dev)
+        for rank in range(n_dev):
+            own, first, last = shard.shard_units_index(wl, rank, n_dev, sched)
+            kmin, kmax = np.inf, -np.inf
+            for ip, a, b in zip(own, first, last):
+                t = int(wl.tr_off[ip])
+                seen[t + a:t + b] += 1
+                k = wl.k3_tr[t + a:t + b]
+                kmin, kmax = min(kmin, k[0]), max(kmax, k[-1])
+                cost[rank] += np.sum(0.65 + 0.35 * np.minimum(1.0, k * wl.cosmo["tau0"] / wl.layout.l.max()))
+            if rank % n_bands:                                       # bands of a group do not overlap in k3
+                assert kmin >= prev_kmax
+            prev_kmax = kmax
+        assert np.all(seen == 1)
+        assert cost.max() / cost.mean() < 1.03
+
+
+def test_select_units_metadata():
+    """Slices of fine grids: whole coarse grids and sources, cut fine grids, physical range relative to the slice and the
+    k3 of the first / last physical point carried along (include/song_los.h, song_los_batch)."""
+    wl = workload.fill_sources(workload.build_grids(configs.tiny(sources_k3_interpolation="cubic")))
+    sched = shard.schedule_bands(wl, 3, n_bands=3)
+    total = 0
+    for rank in range(3):
+        sub, own, first, last = shard.shard_units(wl, rank, 3, schedule=sched)
+        total += sub.n_units
+        assert np.array_equal(sub.k3_pt_size, wl.k3_pt_size[own]) and sub.src.size == sub.src_off[-1] + sub.k3_pt_size[-1] * wl.layout.tp2_size * wl.tau.size
+        for q, (ip, a, b) in enumerate(zip(own, first, last)):
+            t = int(wl.tr_off[ip])
+            assert np.array_equal(sub.k3_tr[sub.tr_off[q]:sub.tr_off[q] + sub.k3_tr_size[q]], wl.k3_tr[t + a:t + b])
+            assert sub.phys_start[q] == wl.phys_start[ip] - a and sub.phys_size[q] == wl.phys_size[ip]
+            assert sub.phys_k_first[q] == wl.k3_tr[t + wl.phys_start[ip]]
+            assert sub.phys_k_last[q] == wl.k3_tr[t + wl.phys_start[ip] + wl.phys_size[ip] - 1]
+    assert total == wl.n_units
+
+
+def _band_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    import oracle_lib as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    wl = workload.build_grids(configs.tiny(sources_k3_interpolation="cubic"))
+    workload.fill_sources(wl)
+    proj = O.build_projection(wl)
+    sched = shard.schedule_bands(wl, world, n_bands=world)
+    own, first, last = shard.shard_units_index(wl, rank, world, sched)
+    whole, _ = O.OracleRun(wl.select(own), proj).run()              # the oracle works on whole pairs: cut its result
+    sub = wl.select(own)
+    local = np.concatenate([whole[:, int(sub.tr_off[q]) + a:int(sub.tr_off[q]) + b] for q, (a, b) in enumerate(zip(first, last))], axis=1)
+    full = shard.gather_band_transfers(local, wl, rank, world, sched, dist=dist)
+    if rank == 0:
+        ref, _ = O.OracleRun(wl, proj).run()
+        np.save(out_path, np.stack([full, ref]))
+    else:
+        assert full is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_band_gather(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "gathered_bands.npy")
+    port = 29800 + (os.getpid() % 200)
+    mp.spawn(_band_worker, args=(2, port, out), nprocs=2, join=True)
+    full, ref = np.load(out)
+    assert np.array_equal(full, ref)          # band slices are disjoint, complete and land in the reference order
+
+
 def _worker(rank, world, port, out_path):
     import torch.distributed as dist
     sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
