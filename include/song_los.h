@@ -33,6 +33,8 @@
  *                              transfer2_init (transfer2.c:315-570) as a pipeline in which the copy of
  *                              batch n+1 to the device and of batch n-1 to the host overlap the
  *                              kernels of batch n (the k1 levels are independent, transfer2.c:549-551)
+ *   song_los_stage_sources     pieces of the next batch's packed sources, copied to the device while the host packs the
+ *                              rest (consecutive from offset 0; song_los_submit copies what is left)
  *   song_los_host_alloc/_free  page-locked staging memory for ppt2->sources / ptr2->transfer slabs
  *   song_los_max_batch_units   how many k3 values of consecutive k1 levels fit in one batch (three batches in flight)
  *   song_los_max_resident_units  the same bound when only n_slots batches are held at once
@@ -172,7 +174,8 @@ typedef struct song_los_timing {
   int64_t n_integrals;             /* stored T values = n_units * tt2_size            */
   int64_t n_terms_upper;           /* n_integrals * tau_size * (L_max+1) upper bound  */
   float ms_h2d;                    /* host->device copy of the batch (copy stream)    */
-  float ms_d2h;                    /* device->host copy of the result (song_los_wait) */
+  float ms_d2h;                    /* device->host copy of the result that follows the last kernel (song_los_wait);
+                                      column blocks finished earlier are already on their way (FAST mode) */
 } song_los_timing;
 
 typedef struct song_los_ctx song_los_ctx;
@@ -249,6 +252,7 @@ int  song_los_host_free(void *ptr);
  * one compute fit in the free device memory.  src_doubles_per_unit = (source doubles of the run) /
  * (k3 values of the run), i.e. tp2_size * tau_size * <k3_pt> / <k3_tr>.  Needs the projection tables. */
 int  song_los_max_batch_units(song_los_ctx *ctx, int mode, double src_doubles_per_unit, int64_t *units);
+int  song_los_stage_sources(song_los_ctx *ctx, const double *src_part, int64_t offset, int64_t n, int64_t n_src_total);
 int  song_los_max_resident_units(song_los_ctx *ctx, int mode, double src_doubles_per_unit, int n_slots, int64_t *units);
 
 /* Pre-allocates all device buffers for a pipeline of `n_in_flight` (1..SONG_LOS_MAX_IN_FLIGHT) batches of up to the

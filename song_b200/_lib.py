@@ -153,13 +153,14 @@ LOS_SYMBOLS = [
     "song_los_compute", "song_los_download", "song_los_transfer_pairs",
     "song_los_device_result", "song_los_copy_result", "song_los_set_stream", "song_los_measure_peaks",
     "song_los_device_info", "song_los_version",
-    "song_los_submit", "song_los_wait", "song_los_host_alloc", "song_los_host_free", "song_los_max_batch_units", "song_los_max_resident_units", "song_los_reserve", "song_los_get_projection_dd",
+    "song_los_submit", "song_los_wait", "song_los_host_alloc", "song_los_host_free", "song_los_max_batch_units", "song_los_max_resident_units", "song_los_stage_sources", "song_los_reserve", "song_los_get_projection_dd",
     "song_los_device_count", "song_los_set_time", "song_los_config_matches", "song_los_drop_projection_rows",
     "song_los_select_slot", "song_los_set_bessel_table", "song_los_integrate_k3", "song_los_last_k3_ms", "song_los_cl_sum",
 ]
 HOST_SYMBOLS = ["song_host_k3_size", "song_host_k3_list", "song_host_k3_sizes", "song_host_k3_lists",
                 "song_host_bessel2_prepare", "song_host_bessel2_free", "song_host_bessel2_upload",
-                "song_host_lpt_schedule", "song_host_schedule_pairs", "song_host_pair_costs"]
+                "song_host_lpt_schedule", "song_host_schedule_pairs", "song_host_pair_costs",
+                "song_host_band_edges", "song_host_band_cuts", "song_host_band_count"]
 
 _los = None
 _host = None
@@ -201,6 +202,7 @@ def los():
         lib.song_los_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
         lib.song_los_host_free.argtypes = [vp]
         lib.song_los_max_batch_units.argtypes = [vp, C.c_int, C.c_double, c_int64_p]
+        lib.song_los_stage_sources.argtypes = [vp, c_double_p, C.c_int64, C.c_int64, C.c_int64]
         lib.song_los_max_resident_units.argtypes = [vp, C.c_int, C.c_double, C.c_int, c_int64_p]
         lib.song_los_reserve.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64]
         lib.song_los_device_count.argtypes = [c_int_p]

@@ -31,6 +31,7 @@ void fast_state_destroy(FastState *);
 void fast_invalidate_table(FastState *);
 int fast_prepare(FastState *fs, const FastHostLayout &h, const ExactParams &P, cudaStream_t st, std::string &err);
 int64_t fast_bytes_per_unit(const FastState *fs);
+int64_t fast_held_bytes(const FastState *fs);
 int fast_reserve(FastState *fs, int64_t n_units, int64_t n_src, int64_t n_pt, std::string &err);
 constexpr int FAST_MAX_EVENTS = 32;     // 5 phase boundaries + 2 per (column block, K chunk) launch
 constexpr int FAST_MAX_BLOCKS = 12;     // (field, m) column blocks

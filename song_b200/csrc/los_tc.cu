@@ -143,17 +143,33 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
       "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
-// 1-D bulk copy global -> shared, completion on an mbarrier
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+// L2 eviction policies for the two operand streams of the kernel.  The source slab is read exactly once per launch
+// (86 GB at configs[3]) while the table rows of a wave of tiles (~20 MB) are re-read by every CTA of the wave and at
+// neighbouring tau: without hints the stream evicts the rows and half of the row fetches go to DRAM (ncu: 300 GB
+// read per launch for 86 GB of slab).
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal()
+{
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+// 1-D bulk copy global -> shared, completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
 // 3-D tensor (TMA descriptor) box copy global -> shared
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar, uint64_t policy)
 {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
@@ -709,6 +725,9 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
     //   x = k3 (tau0-tau),  ix = (int)(x/dx),  a_J = (xx[ix+1] - x)/dx,  c0 = w a_J,  c1 = w - c0
     // (transfer2.c:2195-2202, xx[ix+1] recomputed as (ix+1) delta).  Stage sequence per tile: pass, K chunk, tau.
     const int pw = warp - TC_CONSUMERS / 32;
+    // (dbg 64 / 128: the reversed and the neutral policies, for A/B timing only)
+    const uint64_t pol_stream = (P.dbg & 128) ? l2_policy_evict_normal() : (P.dbg & 64) ? l2_policy_evict_last() : l2_policy_evict_first();   // slab: read once
+    const uint64_t pol_keep = (P.dbg & 128) ? l2_policy_evict_normal() : (P.dbg & 64) ? l2_policy_evict_first() : l2_policy_evict_last();     // table rows: shared by the wave
     bool first_round = true;                    // the first NS stages need no empty-slot wait
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t s0 = tile * MT;
@@ -778,11 +797,11 @@ __global__ void __launch_bounds__((WM * WN + NP) * 32, 1) los_tc_kernel(const __
               const uint32_t bytes_row = (uint32_t)pr.z * bytes_per_sb;
               *reinterpret_cast<int4 *>(st.meta) = pr;
               mbar_arrive_expect_tx(full, ((P.dbg & 8) ? 0u : s_bytes) + ((P.dbg & 16) ? 0u : bytes_row * nrows));
-              if (!(P.dbg & 8)) tma_load_3d(smem_u32(st.S), tmap, 0, t, (int)s0, full);
+              if (!(P.dbg & 8)) tma_load_3d(smem_u32(st.S), tmap, 0, t, (int)s0, full, pol_stream);
               const double *src = P.Jq + (int64_t)pr.x * P.jq_row + q_off;
               if (bytes_row > 0 && !(P.dbg & 16))
                 for (int r = 0; r < nrows; ++r)
-                  bulk_g2s(smem_u32(st.B) + r * P.b_row_bytes, src + (int64_t)r * P.jq_row, bytes_row, full);
+                  bulk_g2s(smem_u32(st.B) + r * P.b_row_bytes, src + (int64_t)r * P.jq_row, bytes_row, full, pol_keep);
             }
 #pragma unroll
             for (int i = 0; i < UPL; ++i) {
@@ -1185,6 +1204,18 @@ int fast_prepare(FastState *fs, const FastHostLayout &h, const ExactParams &P, c
 int64_t fast_bytes_per_unit(const FastState *fs)
 {
   return (int64_t)fs->tau_size * fs->tpp_max * 8 + 8 /*keys*/ + 3 * 4 /*perm_in, perm, unit_pair*/ + (int64_t)sizeof(TcUnitW) + 8 /*ujp*/ + 16 /*cub*/;
+}
+
+// bytes of per-batch intermediates the FAST path already holds: reused by the next batch, so they count as available
+// when the capacity of a batch is computed (song_los_max_batch_units)
+int64_t fast_held_bytes(const FastState *fs)
+{
+  if (!fs) return 0;
+  size_t b = fs->S.cap * sizeof(double) + fs->CSD.cap * sizeof(double2) + fs->keys_out.cap * sizeof(double);
+  b += (fs->perm_in.cap + fs->perm.cap + fs->unit_pair.cap + fs->jcount.cap) * sizeof(int);
+  b += fs->uw.cap * sizeof(TcUnitW) + fs->ujp.cap * sizeof(int2) + fs->cub_tmp.cap;
+  b += fs->spl_coef.cap * sizeof(TcSplineCoef) + fs->spl_ends.cap * sizeof(TcSplineEnds);
+  return (int64_t)b;
 }
 
 // Allocates every intermediate of the FAST path for batches of up to U k3 values / n_src source doubles /

@@ -123,7 +123,7 @@ extern "C" int song_los_create(const song_los_config *cfg, song_los_ctx **out)
     slots_ok = slots_ok && cudaEventCreate(&S.ev_h2d) == cudaSuccess && cudaEventCreate(&S.ev_compute) == cudaSuccess
             && cudaEventCreate(&S.ev_d2h) == cudaSuccess && cudaEventCreate(&S.ev_h2d_start) == cudaSuccess
             && cudaEventCreate(&S.ev_d2h_start) == cudaSuccess
-            && cudaHostAlloc((void **)&S.h_err, sizeof(int), cudaHostAllocDefault) == cudaSuccess;
+            && cudaHostAlloc((void **)&S.h_err, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
     for (auto &e : S.ev_t) slots_ok = slots_ok && cudaEventCreate(&e) == cudaSuccess;
     if (S.h_err) *S.h_err = 0;
   }
@@ -418,6 +418,9 @@ extern "C" int song_los_set_projection(song_los_ctx *ctx, const double *const *J
 // event waits are needed beyond  h2d -> compute -> d2h  inside a slot.
 // ---------------------------------------------------------------------------------------------
 namespace songlos {
+// device error flags -> page-locked host word (device-accessible under unified addressing), and reset
+__global__ void flush_err_kernel(int *d_err, int *h_err) { *h_err = *d_err; *d_err = 0; }
+
 // CTA work list of the exact kernel, (pair, first k3 index), built on the device
 __global__ void fill_tiles_kernel(const int *nt, const int *tile_off, int n_pairs, int2 *tiles)
 {
@@ -501,11 +504,21 @@ static int enqueue_upload(song_los_ctx *ctx, song_los_ctx::Slot &S, const song_l
   CK(S.d_src.reserve((size_t)b->n_src_total));
   CK(S.d_out.reserve((size_t)b->n_units * c.tt2_size));
   cudaStream_t st = ctx->st_h2d;
-  CK(cudaEventRecord(S.ev_h2d_start, st));
+  int64_t staged = 0;                      // leading part of the sources already enqueued by song_los_stage_sources
+  if (S.staged_total > 0) {
+    if (S.staged_total != b->n_src_total)
+      return ctx_fail(ctx, "song_los_submit: %lld source doubles were announced to song_los_stage_sources, the batch has %lld",
+                      (long long)S.staged_total, (long long)b->n_src_total);
+    staged = S.staged_src;
+  } else {
+    CK(cudaEventRecord(S.ev_h2d_start, st));
+  }
+  S.staged_src = S.staged_total = 0;
   if (meta_bytes) CK(cudaMemcpyAsync(S.d_meta.p, S.h_meta, meta_bytes, cudaMemcpyHostToDevice, st));
   if (b->n_pt_total) CK(cudaMemcpyAsync(S.d_k3_pt.p, b->k3_pt, (size_t)b->n_pt_total * 8, cudaMemcpyHostToDevice, st));
   if (b->n_units) CK(cudaMemcpyAsync(S.d_k3_tr.p, b->k3_tr, (size_t)b->n_units * 8, cudaMemcpyHostToDevice, st));
-  if (b->n_src_total) CK(cudaMemcpyAsync(S.d_src.p, b->src, (size_t)b->n_src_total * 8, cudaMemcpyHostToDevice, st));
+  if (b->n_src_total > staged)
+    CK(cudaMemcpyAsync(S.d_src.p + staged, b->src + staged, (size_t)(b->n_src_total - staged) * 8, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(S.ev_h2d, st));
 
   // largest k3 of the batch: every pair's grid is ascending (transfer2.c:1727), so its last value is the pair's maximum
@@ -675,9 +688,11 @@ static int enqueue_compute(song_los_ctx *ctx, song_los_ctx::Slot &S, int mode, d
       return ctx_fail(ctx, "%s", e.c_str());
     S.fast_timed = true;
   }
-  // error flags of this batch: copied to the slot's pinned word, then cleared for the next batch
-  CK(cudaMemcpyAsync(S.h_err, ctx->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), st));
+  // error flags of this batch: written to the slot's page-locked word by a one-thread kernel, then cleared for the next
+  // batch.  (Not a cudaMemcpyAsync: a device->host copy on the compute stream queues on the same copy engine as the
+  // result rows already travelling home and stalled the next batch's kernels behind several GB of them: 87 ms per batch.)
+  flush_err_kernel<<<1, 1, 0, st>>>(ctx->d_err.p, S.h_err);
+  CK(cudaGetLastError());
   CK(cudaEventRecord(S.ev_compute, st));
   return SONG_LOS_SUCCESS;
 }
@@ -747,6 +762,40 @@ extern "C" int song_los_download(song_los_ctx *ctx, double *transfer)
   return SONG_LOS_SUCCESS;
 }
 
+// The slot the next song_los_submit fills: the one after the newest batch in flight.
+static int next_submit_slot(const song_los_ctx *ctx)
+{
+  if (ctx->stage_slot >= 0) return ctx->stage_slot;
+  return (ctx->n_in_flight == 0) ? ctx->cur : (ctx->cur + 1) % song_los_ctx::N_SLOTS;
+}
+
+// Sources of the NEXT batch, part by part: the host packs ppt2->sources into its page-locked staging in pieces and hands
+// every finished piece over at once, so that the host->device copy runs under the packing of the following pieces instead
+// of after all of them.  The pieces must be consecutive from offset 0 of the batch's packed `src`; what has not been
+// staged when song_los_submit is called is copied there.
+extern "C" int song_los_stage_sources(song_los_ctx *ctx, const double *src_part, int64_t offset, int64_t n, int64_t n_src_total)
+{
+  if (!ctx || !src_part || offset < 0 || n < 0 || offset + n > n_src_total) return ctx_fail(ctx, "song_los_stage_sources: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->n_in_flight >= song_los_ctx::N_SLOTS)
+    return ctx_fail(ctx, "song_los_stage_sources: %d batches already in flight; call song_los_wait first", ctx->n_in_flight);
+  const int is = next_submit_slot(ctx);
+  song_los_ctx::Slot &S = ctx->slot[is];
+  if (S.staged_total == 0) {
+    if (offset != 0) return ctx_fail(ctx, "song_los_stage_sources: the first part must start at offset 0");
+    CK(S.d_src.reserve((size_t)n_src_total));
+    CK(cudaEventRecord(S.ev_h2d_start, ctx->st_h2d));
+    S.staged_total = n_src_total; S.staged_src = 0;
+    ctx->stage_slot = is;
+  }
+  if (n_src_total != S.staged_total || offset != S.staged_src)
+    return ctx_fail(ctx, "song_los_stage_sources: parts must be consecutive (expected offset %lld of %lld, got %lld of %lld)",
+                    (long long)S.staged_src, (long long)S.staged_total, (long long)offset, (long long)n_src_total);
+  if (n) CK(cudaMemcpyAsync(S.d_src.p + offset, src_part, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->st_h2d));
+  S.staged_src += n;
+  return SONG_LOS_SUCCESS;
+}
+
 // Asynchronous path: enqueue upload, kernels and download of one batch and return.  Up to three batches
 // may be in flight; they complete in submission order through song_los_wait.
 extern "C" int song_los_submit(song_los_ctx *ctx, const song_los_batch *batch, int mode, double *transfer)
@@ -755,7 +804,8 @@ extern "C" int song_los_submit(song_los_ctx *ctx, const song_los_batch *batch, i
   CK(cudaSetDevice(ctx->device));
   if (ctx->n_in_flight >= song_los_ctx::N_SLOTS)
     return ctx_fail(ctx, "song_los_submit: %d batches already in flight; call song_los_wait first", ctx->n_in_flight);
-  const int is = (ctx->n_in_flight == 0) ? ctx->cur : (ctx->cur + 1) % song_los_ctx::N_SLOTS;
+  const int is = next_submit_slot(ctx);
+  ctx->stage_slot = -1;
   song_los_ctx::Slot &S = ctx->slot[is];
   if (enqueue_upload(ctx, S, batch) != SONG_LOS_SUCCESS) return SONG_LOS_FAILURE;
   if (enqueue_compute(ctx, S, mode, transfer) != SONG_LOS_SUCCESS) { cudaDeviceSynchronize(); return SONG_LOS_FAILURE; }
@@ -778,7 +828,7 @@ extern "C" int song_los_wait(song_los_ctx *ctx, song_los_timing *tm)
   ctx->oldest = (ctx->oldest + 1) % song_los_ctx::N_SLOTS;
   if (finish_compute(ctx, S) != SONG_LOS_SUCCESS) { cudaDeviceSynchronize(); return SONG_LOS_FAILURE; }
   CK(cudaEventSynchronize(S.ev_d2h));
-  CK(cudaEventElapsedTime(&S.t.ms_d2h, S.ev_d2h_start, S.ev_d2h));
+  CK(cudaEventElapsedTime(&S.t.ms_d2h, S.ev_compute, S.ev_d2h));     // what is left of the copy after the last kernel
   if (tm) *tm = S.t;
   return SONG_LOS_SUCCESS;
 }
@@ -880,6 +930,8 @@ extern "C" int song_los_max_resident_units(song_los_ctx *ctx, int mode, double s
     if (fast_prepare(ctx->fast, h, P, ctx->stream, e) != 0) return ctx_fail(ctx, "%s", e.c_str());
     size_t fr2 = 0; CK(cudaMemGetInfo(&fr2, &tot)); fr = fr2;
     per_unit += (double)fast_bytes_per_unit(ctx->fast) + 16.0 * src_doubles_per_unit;   // S, sort arrays, {y,dd} sources
+    held += (size_t)fast_held_bytes(ctx->fast);          // the previous batch's intermediates are reused (a second call of
+                                                         // transfer2_init must find the capacity of the first)
   } else {
     per_unit += 8.0 * src_doubles_per_unit + 8.0 / EXACT_UNITS_PER_CTA;                 // dd, tiles
   }

@@ -67,12 +67,14 @@ struct song_los_ctx {
     int n_chunks = 0;             // (column block, K chunk) launches of the last FAST compute
     int *h_err = nullptr;         // pinned copy of the device error flags after this slot's compute
     bool have_batch = false, have_result = false, in_flight = false, fast_timed = false, with_d2h = false;
+    int64_t staged_src = 0, staged_total = 0;   // song_los_stage_sources: leading source doubles already on their way to d_src
     song_los_timing t{};
   };
   static constexpr int N_SLOTS = 3;
   Slot slot[N_SLOTS];
   int cur = 0;                    // slot of the synchronous upload/compute/download calls and of the last submit
   int n_in_flight = 0, oldest = 0;
+  int stage_slot = -1;            // slot song_los_stage_sources is filling for the next song_los_submit
   cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
   std::vector<unsigned char> h_block_nonzero;
   DevBuf<double> d_dd;

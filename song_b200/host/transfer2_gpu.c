@@ -621,19 +621,31 @@ static int submit_batch(los_run *R, song_los_ctx *ctx, los_pair_batch *pb, los_s
     s->pt_off[q] = o_pt; s->tr_off[q] = o_tr; s->src_off[q] = o_src;
     o_pt += s->np[q]; o_tr += s->nt[q]; o_src += (int64_t)tp2 * ntau * s->np[q];
   }
+  /* Packed in pieces of ~256 MB of sources: a finished piece starts its host->device copy at once
+     (song_los_stage_sources), under the packing of the next ones; the last piece travels with song_los_submit. */
   int failed = 0;
-  #pragma omp parallel for schedule(dynamic, 8) num_threads(R->host_threads) if (R->host_threads > 1)
-  for (int q = 0; q < s->n_pairs; ++q) {
-    const int k1 = R->pair_k1[pb->p_first + q], k2 = R->pair_k2[pb->p_first + q];
-    memcpy(s->k3_pt + s->pt_off[q], ppt2->k3[k1][k2], sizeof(double) * s->np[q]);
-    if (transfer2_get_k3_list(R->ppr, R->ppr2, ppt2, R->pbs, R->pbs2, ptr2, k1, k2, s->k3_tr + s->tr_off[q], NULL) == _FAILURE_) {
-      #pragma omp atomic write
-      failed = 1;
-      continue;
+  const int64_t piece_doubles = (int64_t)env_int("SONG_LOS_STAGE_MB", 256) * 131072;
+  for (int q0 = 0; q0 < s->n_pairs && !failed;) {
+    int q1 = q0 + 1;
+    while (q1 < s->n_pairs && (piece_doubles <= 0 || s->src_off[q1] - s->src_off[q0] < piece_doubles)) ++q1;
+    #pragma omp parallel for schedule(dynamic, 8) num_threads(R->host_threads) if (R->host_threads > 1)
+    for (int q = q0; q < q1; ++q) {
+      const int k1 = R->pair_k1[pb->p_first + q], k2 = R->pair_k2[pb->p_first + q];
+      memcpy(s->k3_pt + s->pt_off[q], ppt2->k3[k1][k2], sizeof(double) * s->np[q]);
+      if (transfer2_get_k3_list(R->ppr, R->ppr2, ppt2, R->pbs, R->pbs2, ptr2, k1, k2, s->k3_tr + s->tr_off[q], NULL) == _FAILURE_) {
+        #pragma omp atomic write
+        failed = 1;
+        continue;
+      }
+      /* ppt2->sources[tp][k1][k2][tau*k3_size + k3] (transfer2.h:47-51) -> packed [pair][tp][tau][k3] */
+      for (int tp = 0; tp < tp2; ++tp)
+        memcpy(s->src + s->src_off[q] + (int64_t)tp * ntau * s->np[q], ppt2->sources[tp][k1][k2], sizeof(double) * (size_t)ntau * s->np[q]);
     }
-    /* ppt2->sources[tp][k1][k2][tau*k3_size + k3] (transfer2.h:47-51) -> packed [pair][tp][tau][k3] */
-    for (int tp = 0; tp < tp2; ++tp)
-      memcpy(s->src + s->src_off[q] + (int64_t)tp * ntau * s->np[q], ppt2->sources[tp][k1][k2], sizeof(double) * (size_t)ntau * s->np[q]);
+    if (!failed && q1 < s->n_pairs && piece_doubles > 0 &&
+        song_los_stage_sources(ctx, s->src + s->src_off[q0], s->src_off[q0], s->src_off[q1] - s->src_off[q0], o_src) != SONG_LOS_SUCCESS) {
+      snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", song_los_last_error(ctx)); return _FAILURE_;
+    }
+    q0 = q1;
   }
   if (failed) { snprintf(errmsg, _ERRORMSGSIZE_, "%.1500s", ptr2->error_message); return _FAILURE_; }
 
@@ -843,6 +855,7 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   /* cost of a pair: its k3 values, weighted by the share of the multipole columns that are active at its k3 (los_host.c) */
   song_host_pair_costs(R.n_pairs, units_of_pair, kmin_of_pair, kmax_of_pair, ptr2->tau0, ptr2->l[ptr2->l_size - 1], cost);
   free(kmin_of_pair); free(kmax_of_pair);
+  LAP("pair costs");
 
   /* Batch size.  The tensor-core kernel works on the k3-sorted values of a batch: the more of them share a row of the
      projection table (pbs2->xx_size rows), the fewer partly filled MMAs it issues -- a batch with 40 k3 values per row
@@ -856,6 +869,7 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
     RELEASE_ENGINES();
     return _FAILURE_;
   }
+  LAP("device capacity (song_los_max_batch_units)");
   const int64_t dense_units = (int64_t)env_int("SONG_LOS_DENSE_K3_PER_ROW", 40) * pbs2->xx_size;
   int64_t batch_units = env_int("SONG_LOS_BATCH_UNITS", 0);
   if (batch_units <= 0) {
@@ -900,21 +914,30 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
     if (parts < 1) parts = 1;
     /* Sizes of the parts.  Nothing of a GPU's first batch overlaps anything: its packing and host->device copy are pure
        latency (0.23 s of a 2.2 s call at configs[3] with four equal batches), and so is the device->host copy of the last
-       one.  The first run of a device therefore starts with a small batch and grows: weights 1 : 2 : 3 : 3 : ... -- the
-       copies of batch n+1 still fit under the kernels of batch n (the kernels take ~2.4x the copies of the same pairs).
+       one.  The first run of a device therefore starts with a small batch and grows: weights 1 : 2 : 3.5 : 3.5 : ... -- the
+       packing of batch n+1 (with its host->device copy beside it, song_los_stage_sources: 0.115 us per k3 value on the
+       bench host) about fits under the kernels of batch n (0.15 us per k3 value for the cheap low-k pairs of a first batch,
+       0.23-0.25 later), and the large batches keep the k3 density.
        SONG_LOS_RAMP=0: equal parts. */
     double bound[LOS_MAX_PARTS + 1];
     if (parts > LOS_MAX_PARTS) parts = LOS_MAX_PARTS;
     const int ramp = ramp_enabled && !device_started[device_of_pair[p]] && parts >= 2;
     device_started[device_of_pair[p]] = 1;
     {
-      double wsum = 0., w[LOS_MAX_PARTS];
-      for (int i = 0; i < parts; ++i) { w[i] = ramp ? (i == 0 ? 1. : i == 1 ? 2. : 3.) : 1.; wsum += w[i]; }
-      int fits = 1;
-      for (int i = 0; i < parts; ++i) if (w[i] / wsum * (double)run_units > (double)cap_units) fits = 0;
-      if (!fits) { for (int i = 0; i < parts; ++i) w[i] = 1.; wsum = parts; }
+      double w[LOS_MAX_PARTS];
+      for (int i = 0; i < parts; ++i) { w[i] = ramp ? (i == 0 ? 1. : i == 1 ? 2. : 3.5) : 1.; }
+      /* sizes min(cap, lambda w[i]) that add up to the run: a part that would exceed the device's capacity is clipped
+         and the others grow (parts >= parts_min: the capacity suffices) */
+      double lo = 0., hi = (double)run_units + 1.;
+      for (int it = 0; it < 60; ++it) {
+        const double lambda = 0.5 * (lo + hi);
+        double sum = 0.;
+        for (int i = 0; i < parts; ++i) sum += (lambda * w[i] < 0.98 * (double)cap_units) ? lambda * w[i] : 0.98 * (double)cap_units;
+        if (sum < (double)run_units) lo = lambda; else hi = lambda;
+      }
       bound[0] = 0.;
-      for (int i = 0; i < parts; ++i) bound[i + 1] = bound[i] + w[i] / wsum * (double)run_units;
+      for (int i = 0; i < parts; ++i) bound[i + 1] = bound[i] + ((hi * w[i] < 0.98 * (double)cap_units) ? hi * w[i] : 0.98 * (double)cap_units);
+      bound[parts] = (double)run_units;
     }
     int64_t acc = 0; int part = 0;
     los_pair_batch pb; memset(&pb, 0, sizeof pb); pb.p_first = p; pb.device = device_of_pair[p];
@@ -934,6 +957,8 @@ int transfer2_init(struct precision *ppr, struct precision2 *ppr2, struct backgr
   if (ptr2->transfer2_verbose > 0)
     printf(" -> %d (k1,k2) pairs in %d batches (up to %ld k3 values each) on %d GPU(s), %s arithmetic\n", R.n_pairs, n_batches,
            (long)batch_units, n_dev, mode == SONG_LOS_MODE_FAST ? "tensor-core" : "reference-order");
+  LAP("batches cut");
+  LAP("batches cut");
   los_transfer_store *st = store_of(ppt2, ptr2);
   if (st == NULL) { RELEASE_ENGINES(); class_stop(ptr2->error_message, "could not set up the storage of ptr2->transfer"); }
   LAP("pair schedule and batches");
