@@ -323,7 +323,7 @@ def unit_cost(grids, own, first, last) -> float:
     c = 0.0
     for ip, a, b in zip(own, first, last):
         k = grids.k3_tr[int(grids.tr_off[ip]) + int(a):int(grids.tr_off[ip]) + int(b)]
-        c += float(np.sum(0.65 + 0.35 * np.minimum(1.0, k * grids.cosmo["tau0"] / grids.layout.l.max())))
+        c += float(np.sum(0.5 + 0.5 * np.minimum(1.0, k * grids.cosmo["tau0"] / grids.layout.l.max())))
     return c
 
 
@@ -384,6 +384,9 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
         if -(-units_max // n_slots) <= int(0.88 * cap) or n_slots == 3:        # slack: batches are cut at pair boundaries, and the
                                                                                 # parity / gather buffers of this script need room too
             break
+    if int(D.reduce(float(-(-sub.n_units // max(cap, 1))), "max")) > 3:      # decided together: no rank may leave the others in a collective
+        eng.close()
+        raise RuntimeError(f"{name}: a GPU's shard does not fit three resident batches of {cap} k3 values on {world} GPU(s)")
     batches = split_resident(sub, cap)
     peaks = eng.measure_peaks()
     stream = torch.cuda.current_stream()
@@ -538,23 +541,30 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
     achieved = flops / t_kernel / 1e12
     peak = peaks["dmma_tflops"] if mode == MODE_FAST else peaks["dfma_tflops"]
     alg_bytes = 8.0 * (n_int_rank + sub.src.size + sub.k3_pt.size + sub.k3_tr.size)
-    traffic = None
+    traffic = None; tinfo = {}
     tfile = os.path.join(ROOT, "profiles", "traffic_bytes.json")
     if os.path.exists(tfile):
         try:
-            traffic = json.load(open(tfile)).get(name, {}).get("los_tc_kernel")
+            tinfo = json.load(open(tfile)).get(name, {})
+            traffic = tinfo.get("los_tc_kernel")
         except Exception:
             traffic = None
     fracs = D.all_gather_floats(achieved / peak)
+    per_rank = {k: D.all_gather_floats(float(v)) for k, v in (("ms_integrate", kern["ms_integrate"]), ("ms_interp", kern["ms_interp"]),
+                                                              ("ms_spline", kern["ms_spline"]), ("k3_values", float(sub.n_units)),
+                                                              ("pairs_touched", float(sub.n_pairs)))}
     roofline = {
         "bound": "tensor", "kernel": "los_tc_kernel (FP64 tensor core, DMMA m8n8k4, TMA-fed)" if mode == MODE_FAST else "los_exact_kernel",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+        "traffic_note": (None if traffic is None else
+                         "DRAM bytes of ONE captured launch (ncu --set full, profiles/traffic_bytes.json): %s ms, one of %s launches per step; "
+                         "algorithmic flops of a launch = algorithmic_flops_per_step / launches" % (tinfo.get("launch_ms", "the step's only"), tinfo.get("launches_per_step", 1))),
         "peak_source": ("DMMA m8n8k4 loop" if mode == MODE_FAST else "DFMA loop") + " measured in this run with song_los_measure_peaks "
                        "(MEASURED_PEAKS.json has no FP64 entry and the profiling guide no FP64 fallback)",
         "algorithmic_flops_per_step": flops, "n_terms": n_terms, "kernel_ms_per_step": kern["ms_integrate"],
         "kernel_share_of_step": kern["ms_integrate"] / max(kern["ms_total"], 1e-9),
         "step_frac": flops / (my_ms * 1e-3) / 1e12 / peak,
-        "frac_per_rank": fracs,
+        "frac_per_rank": fracs, "per_rank": per_rank,
         "dfma_peak_tflops": peaks["dfma_tflops"], "dmma_peak_tflops": peaks["dmma_tflops"],
         "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / (kern["ms_total"] * 1e-3) / 1e9,
                 "peak_gbs": peaks["copy_gbs"], "frac": alg_bytes / (kern["ms_total"] * 1e-3) / 1e9 / peaks["copy_gbs"]},
@@ -690,9 +700,17 @@ def main():
         raise SystemExit("bench.py: no CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     numa = bind_to_gpu_numa_node(local_rank)         # before any pinned allocation: page-locked buffers are first-touch local
+    if world > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+        # torchrun exports OMP_NUM_THREADS=1 to its workers: give every rank its share of the host for the host-side
+        # work of the set-up (bessel2's j_l1 / 3j tables, the oracle of the parity spot checks)
+        try:
+            import ctypes
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(max(1, (os.cpu_count() or 1) // world))
+        except OSError:
+            pass
     D = Dist(rank, world, local_rank)
 
-    sampler = ClockSampler(local_rank)               # 50 ms period over the timed `value` region only: nvidia-smi queries take driver
+    sampler = ClockSampler(local_rank, period_ms=100) # over the timed `value` region only: nvidia-smi queries take driver
                                                      # locks and stretched single transfer2_init calls from 34 to 120-480 ms
     main_res = measure_workload(args.workload, args, D, args.steps, args.warmup, min(args.e2e_steps, args.steps),
                                 with_cpu=(world == 1 and not args.no_cpu_baseline), sampler=sampler)
@@ -712,8 +730,13 @@ def main():
         names = [n for n in args.extra.split(",") if n]
     for n in names:
         big = n.startswith("sn_pol_5percent")
-        r = measure_workload(n, args, D, steps=3 if big else 5, warmup=3, e2e_steps=0 if n == "sn_pol_5percent_lmax4000" else 3,
-                             with_cpu=False)
+        try:
+            r = measure_workload(n, args, D, steps=3 if big else 5, warmup=3, e2e_steps=0 if n == "sn_pol_5percent_lmax4000" else 3,
+                                 with_cpu=False)
+        except RuntimeError as exc:                  # raised on every rank alike (see measure_workload): the main line still goes out
+            if rank == 0:
+                extras.append({"workload": n, "error": str(exc)[:300]})
+            continue
         if rank == 0:
             extras.append({"workload": n, "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "steps": r["steps"],
                            "n_gpus": world, "integrals": r["describe"]["integrals"], "parity": r["parity"],

@@ -76,7 +76,7 @@ int song_host_pair_costs(int n_pairs, const int *k3_tr_size, const double *k_min
    (song_host_schedule_pairs) x n_bands bands.
 
    song_host_band_edges: the n_bands - 1 interior edges that split the cost of the given fine-grid values evenly;
-   cost of a value = 0.65 + 0.35 min(1, k3 tau0 / l_max) as in song_host_pair_costs.  pair_in_group: NULL = all pairs,
+   cost of a value = 0.5 + 0.5 min(1, k3 tau0 / l_max) (measured, los_host.c).  pair_in_group: NULL = all pairs,
    else only pairs with pair_in_group[p] != 0 are counted.
    song_host_band_cuts: cut[p * (n_bands + 1) + r] = first fine-grid index of pair p with k3 >= edge[r]
    (cut[.. + 0] = 0, cut[.. + n_bands] = k3_tr_size[p]); grids are ascending (transfer2.c:1727). */

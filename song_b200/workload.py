@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import dataclasses
 from dataclasses import dataclass, field
 
@@ -429,7 +430,12 @@ def fill_sources(wl: Workload, kind: str = "smooth", seed: int = 20261017) -> Wo
                 if mv <= L:
                     tp_info.append((base + lay.lm_src[L, im], field_name, L, int(mv)))
     tp_info.sort()
-    for ip in range(wl.n_pairs):
+    # per source type: index of the k3 power (min(L,2)) and whether the type is identically zero (E, B with L < 2)
+    tp_index = np.array([t[0] for t in tp_info], dtype=np.int64)
+    tp_pow = np.array([min(t[2], 2) for t in tp_info], dtype=np.int64)
+    tp_live = np.array([not (t[1] != "T" and t[2] < 2) for t in tp_info])
+    tp_norm = np.array([1.0 / (t[2] + 1) ** 2 for t in tp_info])
+    def fill_pair(ip):
         i1, i2 = int(wl.pairs[ip, 0]), int(wl.pairs[ip, 1])
         rng = np.random.Generator(np.random.PCG64(seed + 1000 * i1 + i2))
         n = int(wl.k3_pt_size[ip])
@@ -437,17 +443,32 @@ def fill_sources(wl: Workload, kind: str = "smooth", seed: int = 20261017) -> Wo
         blk = src[wl.src_off[ip]:wl.src_off[ip] + tp2 * ntau * n].reshape(tp2, ntau, n)
         if kind == "noise":
             blk[...] = rng.standard_normal(blk.shape)
-            continue
+            return
         amp = rng.uniform(0.5, 1.5, size=tp2)
         phi = rng.uniform(0.0, 2 * math.pi, size=tp2)
         env = np.exp(-(k3 / 0.15) ** 2)
-        for tp, fname, L, mv in tp_info:
-            if fname != "T" and L < 2:
-                blk[tp] = 0.0
-                continue
-            a = amp[tp] / (L + 1) ** 2
-            blk[tp] = a * g[:, None] * np.cos(k3[None, :] * rs[:, None] + phi[tp]) \
-                * ((k3 / k_rec) ** min(L, 2))[None, :] * env[None, :]
+        # cos(k3 r_s + phi_tp) = cos(k3 r_s) cos(phi_tp) - sin(k3 r_s) sin(phi_tp): the two tau x k3 tables are evaluated once
+        # per pair and every source type is a combination of them (the generator, not the GPU, dominated the set-up of the
+        # big workloads); one broadcast expression per pair
+        arg = k3[None, :] * rs[:, None]
+        cg, sg = np.cos(arg) * g[:, None], np.sin(arg) * g[:, None]
+        kpow = np.stack([env, (k3 / k_rec) * env, (k3 / k_rec) ** 2 * env])               # [3][n]
+        a = np.where(tp_live, amp[tp_index] * tp_norm, 0.0)
+        ca, sa = a * np.cos(phi[tp_index]), a * np.sin(phi[tp_index])
+        blk[...] = 0.0
+        blk[tp_index] = (ca[:, None, None] * cg[None, :, :] - sa[:, None, None] * sg[None, :, :]) * kpow[tp_pow][:, None, :]
+
+    # pairs are independent (own generator each): a few threads, numpy releases the GIL inside the array expressions
+    n_threads = max(1, min(16, int(os.environ.get("SONG_FILL_THREADS", "0")) or
+                           len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    if n_threads == 1 or wl.n_pairs < 64:
+        for ip in range(wl.n_pairs):
+            fill_pair(ip)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        chunks = [range(a, min(a + 32, wl.n_pairs)) for a in range(0, wl.n_pairs, 32)]
+        with ThreadPoolExecutor(n_threads) as pool:
+            list(pool.map(lambda r: [fill_pair(ip) for ip in r], chunks))
     wl.src = src
     return wl
 

@@ -1,0 +1,179 @@
+"""bench.py end to end on the CPU with the engine replaced by the oracle: checks the script's own logic -- schedule,
+resident batches, timing bookkeeping, parity spot checks, the k3-integral leg, the `configs` array, the CPU baseline and
+the shape of the ONE JSON line the driver parses -- where no GPU is available.  The numbers it prints mean nothing (the
+"kernels" are the CPU oracle); the GPU runs of the same script are the measurements.
+
+The fakes live here, in tests/: nothing under song_b200/ or in bench.py's product path knows about them.
+"""
+import ctypes
+import io
+import json
+import os
+import sys
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+from song_b200.bessel2 import Bessel2 as RealBessel2  # noqa: E402  (before the fixture swaps the module attribute)
+
+
+class FakeEngine:
+    """LosEngine's interface as bench.py uses it; results come from the oracle."""
+
+    def __init__(self, wl, device=0):
+        import oracle_lib as O
+        self.O = O
+        self.wl0 = wl
+        self.slots = {}
+        self.cur = 0
+        self.results = {}
+        self.k3_ms = 0.0
+        self.proj = O.build_projection(wl)
+
+    def max_batch_units(self, mode, src_per_unit, n_slots=3):
+        return 10 ** 9
+
+    def measure_peaks(self, copy=True):
+        return {"dfma_tflops": 30.0, "dmma_tflops": 37.0, "copy_gbs": 6500.0}
+
+    def set_stream(self, s):
+        pass
+
+    def select_slot(self, i):
+        self.cur = i
+
+    def upload(self, b):
+        self.slots[self.cur] = b
+
+    def compute(self, mode):
+        b = self.slots[self.cur]
+        if self.cur not in self.results:
+            self.results[self.cur], _ = self.O.OracleRun(b, self.proj).run()
+        return {"ms_total": 1.0, "ms_spline": 0.1, "ms_sort": 0.0, "ms_interp": 0.2, "ms_integrate": 0.7, "n_launches": 12}
+
+    def device_result(self):
+        return 0, int(self.results[self.cur].size)
+
+    def copy_result_to(self, ptr, n):
+        src = np.ascontiguousarray(self.results[self.cur])
+        assert n == src.size
+        ctypes.memmove(ptr, src.ctypes.data, src.nbytes)
+
+    def set_bessel_table(self, j_l1, x_min_l1, ddj_l1=None):
+        self.jl, self.jl_xmin = j_l1, x_min_l1
+
+    def integrate_k3(self, tt, index_l1, r, n_pairs, abs_M3=0, M3_coefficient=None):
+        b = self.slots[self.cur]
+        T = self.results[self.cur]
+        out = np.stack([self.O.integral_over_k3(b, T[int(t)], self.jl[int(row)], None, self.jl_xmin[int(row)], np.asarray(r))
+                        for t, row in zip(tt, index_l1)])
+        self.k3_ms = 0.5
+        return out
+
+    def close(self):
+        pass
+
+
+class FakeBessel2:
+    def __init__(self, wl):
+        self.real = RealBessel2(wl)
+
+    def init(self, eng):
+        self.eng = eng
+        self.real.prepare()                          # the host half runs without a GPU
+        return self
+
+    def tables(self, eng):
+        p = eng.proj
+        return p.rows, p.index_xmin, p.x_size
+
+    def host_tables(self):
+        return self.real.host_tables()
+
+
+class FakeEvent:
+    def __init__(self, enable_timing=True):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def elapsed_time(self, other):
+        return 5.0
+
+
+class FakeStream:
+    cuda_stream = 0
+
+
+@pytest.fixture
+def fake_gpu(monkeypatch):
+    import torch
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    import song_b200.bessel2 as b2mod
+    import song_b200.engine as engmod
+    monkeypatch.setattr(engmod, "LosEngine", FakeEngine)
+    monkeypatch.setattr(b2mod, "Bessel2", FakeBessel2)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: FakeStream())
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    real_empty, real_zeros = torch.empty, torch.zeros
+    monkeypatch.setattr(torch, "empty", lambda *a, device=None, **k: real_empty(*a, **k))
+    monkeypatch.setattr(torch, "zeros", lambda *a, device=None, **k: real_zeros(*a, **k))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    return torch
+
+
+def run_bench(monkeypatch, argv):
+    import importlib
+    import bench
+    importlib.reload(bench)
+    monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        bench.main()
+    lines = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
+    assert len(lines) == 1, "bench.py prints ONE JSON line"
+    return json.loads(lines[0])
+
+
+def test_bench_line_single_gpu(fake_gpu, monkeypatch):
+    line = run_bench(monkeypatch, ["--workload", "quick_song_run", "--max-pairs", "40", "--steps", "2", "--warmup", "3",
+                                   "--cpu-seconds", "0.3", "--extra", "quick_song_run"])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "k3_integral", "configs", "parity"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3 and line["higher_is_better"] is True
+    assert line["scaling"] == "strong" and line["dtype"] == "f64" and line["vs_baseline"] is None
+    assert line["config"]["workload"] == "quick_song_run" and "model" not in line["config"]
+    assert line["parity"]["ok"] and line["parity"]["pairs_checked"] >= 2          # the fake engine IS the oracle
+    r = line["roofline"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel_ms_per_step", "step_frac", "frac_per_rank", "per_rank"):
+        assert key in r, key
+    assert r["bound"] == "tensor" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert line["gpu_launches"] == 2 * 12
+    c = line["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    assert line["k3_integral"]["bitwise_equal_to_oracle"] is True
+    assert line["e2e"]["value"] is None and "unavailable" in line["e2e"]           # --max-pairs: no transfer2_init leg
+    assert len(line["configs"]) == 1 and line["configs"][0]["workload"] == "quick_song_run" and line["configs"][0]["parity"]["ok"]
+
+
+def test_bench_refuses_to_run_without_a_gpu(monkeypatch):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    import bench
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "quick_song_run", "--max-pairs", "8"])
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    with pytest.raises(SystemExit, match="no CUDA device"):
+        bench.main()

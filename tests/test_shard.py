@@ -80,7 +80,7 @@ def test_band_schedule_properties():
                 seen[t + a:t + b] += 1
                 k = wl.k3_tr[t + a:t + b]
                 kmin, kmax = min(kmin, k[0]), max(kmax, k[-1])
-                cost[rank] += np.sum(0.65 + 0.35 * np.minimum(1.0, k * wl.cosmo["tau0"] / wl.layout.l.max()))
+                cost[rank] += np.sum(0.5 + 0.5 * np.minimum(1.0, k * wl.cosmo["tau0"] / wl.layout.l.max()))
             if rank % n_bands:                                       # bands of a group do not overlap in k3
                 assert kmin >= prev_kmax
             prev_kmax = kmax
