@@ -318,6 +318,16 @@ def split_resident(sub, cap_units: int, n_slots: int = 3):
     return [sub.select(np.arange(cuts[i], cuts[i + 1])) for i in range(len(cuts) - 1)]
 
 
+def set_omp_threads(n: int):
+    """Team size of the OpenMP runtime the oracle and the host libraries share in this process (torchrun starts its
+    workers with OMP_NUM_THREADS=1; the runtime was loaded with that value)."""
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
 def unit_cost(grids, own, first, last) -> float:
     """Cost of the fine-grid slices [first, last) of pairs `own` in the model of the static schedule (los_host.c)."""
     c = 0.0
@@ -327,17 +337,43 @@ def unit_cost(grids, own, first, last) -> float:
     return c
 
 
+def oracle_view_of_slices(sub, idx):
+    """A workload the oracle can run as it is for pairs `idx` of a sliced workload (k3 bands), and per pair the columns of
+    its result that belong to the slice.  The oracle, like the reference, takes the fine k3 grid of a pair as given and
+    evaluates every physical point on its own; only the wings of the flat extrapolation (transfer2.c:2743-2757) look at
+    another point, the first / last PHYSICAL one.  The view is therefore the slice itself, plus that one point when the
+    slice holds wing values but not the physical end they copy (it then sorts before / after the whole slice)."""
+    par = sub.parent
+    whole = par.select(sub.parent_pair[idx])          # coarse grids + sources of the whole pairs; fine grids replaced below
+    grids, starts, sizes, keep = [], [], [], []
+    for q, i in enumerate(idx):
+        ip = int(sub.parent_pair[i]); a = int(sub.slice_start[i]); n = int(sub.k3_tr_size[i]); b = a + n
+        K = par.k3_tr[int(par.tr_off[ip]):int(par.tr_off[ip]) + int(par.k3_tr_size[ip])]
+        f = int(par.phys_start[ip]); l = f + int(par.phys_size[ip]) - 1
+        if f >= b:                                    # the whole slice is left wing: copies the first physical point
+            grids.append(np.concatenate([K[a:b], K[f:f + 1]])); starts.append(n); sizes.append(1); keep.append((0, n))
+        elif l < a:                                   # the whole slice is right wing: copies the last physical point
+            grids.append(np.concatenate([K[l:l + 1], K[a:b]])); starts.append(0); sizes.append(1); keep.append((1, n + 1))
+        else:                                         # the slice holds the physical ends its wings copy
+            grids.append(K[a:b]); starts.append(max(f, a) - a); sizes.append(min(l, b - 1) - max(f, a) + 1); keep.append((0, n))
+    nt = np.array([g.size for g in grids], dtype=np.int32)
+    whole.k3_tr_size = nt
+    whole.tr_off = np.concatenate([[0], np.cumsum(nt)[:-1]]).astype(np.int64)
+    whole.k3_tr = np.ascontiguousarray(np.concatenate(grids))
+    whole.phys_start = np.array(starts, dtype=np.int32); whole.phys_size = np.array(sizes, dtype=np.int32)
+    return whole, keep
+
+
 def spot_check(O, sub, got_of_pair, rows, xmin, xsize, n_check: int, run_scale=None):
     """Oracle on a few pairs of `sub`; got_of_pair(i) -> [tt2][k3 of pair i].  Max relative error above 1e-6 of the
     per-(l,m) maximum (BASELINE.json criterion; the maximum is taken over the checked pairs unless run_scale is given).
-    When `sub` holds slices of fine grids (k3 bands) the oracle runs on the whole pairs and its result is cut."""
+    When `sub` holds slices of fine grids (k3 bands) the oracle runs on a view of the slices (oracle_view_of_slices)."""
     idx = np.unique(np.linspace(0, sub.n_pairs - 1, min(n_check, sub.n_pairs)).astype(int))
     oproj = O.OracleProjection(rows, xmin, xsize, None)
     if sub.parent is not None:
-        par = sub.parent.select(sub.parent_pair[idx])
-        whole, _ = O.OracleRun(par, oproj).run()
-        ref = np.concatenate([whole[:, int(par.tr_off[q]) + int(sub.slice_start[i]):int(par.tr_off[q]) + int(sub.slice_start[i]) + int(sub.k3_tr_size[i])]
-                              for q, i in enumerate(idx)], axis=1)
+        view, keep = oracle_view_of_slices(sub, idx)
+        res, _ = O.OracleRun(view, oproj).run()
+        ref = np.concatenate([res[:, int(view.tr_off[q]) + lo:int(view.tr_off[q]) + hi] for q, (lo, hi) in enumerate(keep)], axis=1)
     else:
         ref, _ = O.OracleRun(sub.select(idx), oproj).run()
     got = np.concatenate([got_of_pair(int(i)) for i in idx], axis=1)
@@ -512,8 +548,6 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
                   "api": "torch.distributed.gather over NCCL, one per resident batch slot, padded to the largest batch"}
         if rank == 0:
             # the gathered array in the reference pair order: check pairs owned by every rank against the oracle
-            if grids.src is None:
-                workload.fill_sources(grids)
             tt2 = grids.layout.tt2_size
             def gathered_pair(ip):
                 parts = []                                          # the pair's slices, band by band, from the GPUs that own them
@@ -530,7 +564,16 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
                     a = int(sizes_r[cuts[ib]:j].sum()); n = int(sizes_r[j])
                     parts.append(bufs[ib][r][:units_b * tt2].view(tt2, units_b)[:, a:a + n].cpu().numpy())
                 return np.concatenate(parts, axis=1)
-            gather["parity_of_gathered_array"] = spot_check(O, grids, gathered_pair, rows, xmin, xsize, max(args.check_pairs, world))
+            # the other ranks are idle here: the oracle gets the whole host; sources are generated for the checked pairs only
+            # (the generator is deterministic per pair)
+            n_chk = max(args.check_pairs, world)
+            idx_chk = np.unique(np.linspace(0, grids.n_pairs - 1, min(n_chk, grids.n_pairs)).astype(int))
+            chk = grids.select(idx_chk)
+            if chk.src is None:
+                workload.fill_sources(chk)
+            set_omp_threads(os.cpu_count() or 1)
+            gather["parity_of_gathered_array"] = spot_check(O, chk, lambda j: gathered_pair(int(idx_chk[j])), rows, xmin, xsize, idx_chk.size)
+            set_omp_threads(max(1, (os.cpu_count() or 1) // world))
         del bufs, pads
     del results
 
@@ -586,11 +629,7 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
             # torchrun exports OMP_NUM_THREADS=1 to its workers; a SONG run uses the machine (the drop-in sizes its own
             # packing teams explicitly, bessel2_init and the harness use the default team)
             os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-            try:
-                import ctypes
-                ctypes.CDLL("libgomp.so.1").omp_set_num_threads(os.cpu_count() or 1)
-            except OSError:
-                pass
+            set_omp_threads(os.cpu_count() or 1)
         t0 = time.perf_counter()
         h = dropin_lib.Harness(grids, None, verbose=0, keep_sources=True)      # bessel2_init (drop-in) leaves the engines on the GPUs
         if args.dropin_verbose:
@@ -619,6 +658,8 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
             if i + 1 < e2e_steps:
                 h.transfer2_free(); h.fill_sources()
         e2e_clocks = e2e_sampler.stop()
+        if world > 1:
+            set_omp_threads(max(1, (os.cpu_count() or 1) // world))
         got, count, labels_ok = h.read()
         tables = h.bessel2_tables()
         run_scale = np.abs(got).max(axis=1, keepdims=True)
@@ -703,11 +744,7 @@ def main():
     if world > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
         # torchrun exports OMP_NUM_THREADS=1 to its workers: give every rank its share of the host for the host-side
         # work of the set-up (bessel2's j_l1 / 3j tables, the oracle of the parity spot checks)
-        try:
-            import ctypes
-            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(max(1, (os.cpu_count() or 1) // world))
-        except OSError:
-            pass
+        set_omp_threads(max(1, (os.cpu_count() or 1) // world))
     D = Dist(rank, world, local_rank)
 
     sampler = ClockSampler(local_rank, period_ms=100) # over the timed `value` region only: nvidia-smi queries take driver

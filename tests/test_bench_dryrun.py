@@ -31,7 +31,7 @@ class FakeEngine:
         self.cur = 0
         self.results = {}
         self.k3_ms = 0.0
-        self.proj = O.build_projection(wl)
+        self.proj = O.build_projection(wl if wl.parent is None else wl.parent)
 
     def max_batch_units(self, mode, src_per_unit, n_slots=3):
         return 10 ** 9
@@ -51,7 +51,14 @@ class FakeEngine:
     def compute(self, mode):
         b = self.slots[self.cur]
         if self.cur not in self.results:
-            self.results[self.cur], _ = self.O.OracleRun(b, self.proj).run()
+            if b.parent is not None:                 # slices of fine grids (k3 bands): the oracle on the whole pairs, cut
+                par = b.parent.select(b.parent_pair)
+                whole, _ = self.O.OracleRun(par, self.proj).run()
+                self.results[self.cur] = np.ascontiguousarray(np.concatenate(
+                    [whole[:, int(par.tr_off[q]) + int(a):int(par.tr_off[q]) + int(a) + int(n)]
+                     for q, (a, n) in enumerate(zip(b.slice_start, b.k3_tr_size))], axis=1))
+            else:
+                self.results[self.cur], _ = self.O.OracleRun(b, self.proj).run()
         return {"ms_total": 1.0, "ms_spline": 0.1, "ms_sort": 0.0, "ms_interp": 0.2, "ms_integrate": 0.7, "n_launches": 12}
 
     def device_result(self):
@@ -177,3 +184,60 @@ def test_bench_refuses_to_run_without_a_gpu(monkeypatch):
         monkeypatch.delenv(k, raising=False)
     with pytest.raises(SystemExit, match="no CUDA device"):
         bench.main()
+
+
+# ---- two ranks (gloo): pair groups x k3 bands, gather and the parity of the gathered array ----
+def _two_rank_worker(rank, world, port, bands, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import song_b200.bessel2 as b2mod
+    import song_b200.engine as engmod
+    engmod.LosEngine = FakeEngine
+    b2mod.Bessel2 = FakeBessel2
+    torch.cuda.is_available = lambda: True
+    torch.cuda.set_device = lambda d: None
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.empty_cache = lambda: None
+    torch.cuda.current_stream = lambda *a, **k: FakeStream()
+    torch.cuda.Event = FakeEvent
+    real_empty, real_zeros, real_tensor = torch.empty, torch.zeros, torch.tensor
+    torch.empty = lambda *a, device=None, **k: real_empty(*a, **k)
+    torch.zeros = lambda *a, device=None, **k: real_zeros(*a, **k)
+    torch.tensor = lambda *a, device=None, **k: real_tensor(*a, **k)
+    import bench
+
+    def gloo_init(self, rank, world, local_rank):               # Dist.__init__ with gloo in place of NCCL
+        self.torch = torch
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        self.dist = dist
+        self.cpu_group = dist.new_group(backend="gloo")
+    bench.Dist.__init__ = gloo_init
+    sys.argv = ["bench.py", "--gpus", str(world), "--workload", "quick_song_run", "--max-pairs", "60", "--steps", "2", "--warmup", "3",
+                "--bands", str(bands), "--extra", "none", "--no-cpu-baseline"]
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        bench.main()
+    if rank == 0:
+        open(os.path.join(out_dir, "line.json"), "w").write([l for l in buf.getvalue().splitlines() if l.startswith("{")][0])
+    else:
+        assert not [l for l in buf.getvalue().splitlines() if l.startswith("{")]     # rank 0 alone prints the line
+
+
+@pytest.mark.parametrize("bands", [1, 2])
+def test_bench_line_two_ranks_gloo(tmp_path, bands):
+    import torch.multiprocessing as mp
+    port = 29900 + (os.getpid() % 90) + bands
+    mp.spawn(_two_rank_worker, args=(2, port, bands, str(tmp_path)), nprocs=2, join=True)
+    line = json.loads(open(tmp_path / "line.json").read())
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and len(line["per_rank_ms"]) == 2
+    assert f"x {bands} k3 band(s)" in line["config"]["parallelism"]
+    assert line["parity"]["ok"]
+    g = line["nccl_gather"]
+    assert g["parity_of_gathered_array"]["ok"] and g["parity_of_gathered_array"]["pairs_checked"] >= 2
+    assert g["parity_of_gathered_array"]["max_rel_err_above_1e-6_of_max"] == 0.0     # the fake engine IS the oracle
+    assert len(line["roofline"]["per_rank"]["k3_values"]) == 2
+    if bands > 1:
+        assert "skipped" in line["k3_integral"]

@@ -171,3 +171,27 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     full, ref = np.load(out)
     assert np.array_equal(full, ref)          # shards are disjoint, complete and land in the reference order
+
+
+def test_oracle_view_of_slices_equals_whole_pairs_cut():
+    """bench.py checks band shards against the oracle on a VIEW of the slices (slice + the physical end its wings copy):
+    the view must give what the oracle gives on the whole pairs, cut -- bit for bit."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    import bench
+    import oracle_lib as O
+    wl = workload.fill_sources(workload.build_grids(configs.tiny(sources_k3_interpolation="cubic")), kind="noise")
+    proj = O.build_projection(wl)
+    ref, _ = O.OracleRun(wl, proj).run()
+    sched = shard.schedule_bands(wl, 4, n_bands=4)
+    cases = {"left": 0, "right": 0, "inside": 0}
+    for rank in range(4):
+        sub, own, first, last = shard.shard_units(wl, rank, 4, schedule=sched)
+        idx = np.arange(sub.n_pairs)
+        view, keep = bench.oracle_view_of_slices(sub, idx)
+        res, _ = O.OracleRun(view, proj).run()
+        for q, (lo, hi) in enumerate(keep):
+            ip, a, b = int(own[q]), int(first[q]), int(last[q])
+            got = res[:, int(view.tr_off[q]) + lo:int(view.tr_off[q]) + hi]
+            assert np.array_equal(got, ref[:, int(wl.tr_off[ip]) + a:int(wl.tr_off[ip]) + b])
+            cases["left" if view.k3_tr_size[q] > b - a and lo == 0 else "right" if lo == 1 else "inside"] += 1
+    assert cases["left"] > 0 and cases["right"] > 0 and cases["inside"] > 0, cases
