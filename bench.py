@@ -658,8 +658,6 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
             if i + 1 < e2e_steps:
                 h.transfer2_free(); h.fill_sources()
         e2e_clocks = e2e_sampler.stop()
-        if world > 1:
-            set_omp_threads(max(1, (os.cpu_count() or 1) // world))
         got, count, labels_ok = h.read()
         tables = h.bessel2_tables()
         run_scale = np.abs(got).max(axis=1, keepdims=True)
@@ -667,6 +665,8 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
                                 tables[0], tables[1], tables[2], max(args.check_pairs, 2 * world), run_scale=run_scale)
         del got
         h.close()
+        if world > 1:                                 # back to this rank's share of the host (the other ranks were idle so far)
+            set_omp_threads(max(1, (os.cpu_count() or 1) // world))
         e2e_ms = t_all / e2e_steps * 1e3
         h2d = int(grids.src.nbytes + grids.k3_pt.nbytes + grids.k3_tr.nbytes + (3 * 8 + 5 * 4) * grids.n_pairs)
         d2h = int(n_int_total * 8)

@@ -168,7 +168,8 @@ int compat_spline_second_derivatives(const double *x, int n, const double *y, do
   if (est_deriv) {
     const double d1 = x[1] - x[0], d2 = x[2] - x[0];
     if (d1 == 0. || d2 == 0. || d1 == d2) { free(rhs); return 1; }
-    const double slope0 = (d2 * d2 * (y[1] - y[0]) - d1 * d1 * (y[2] - y[0])) / (d2 * d1 * (d2 - d1));
+    /* denominator as upstream CLASS writes it (tools/arrays.c): (x2-x0)(x1-x0)(x2-x1), not (d2-d1) -- one ulp apart */
+    const double slope0 = (d2 * d2 * (y[1] - y[0]) - d1 * d1 * (y[2] - y[0])) / (d2 * d1 * (x[2] - x[1]));
     ddy[0] = -0.5;
     rhs[0] = (3. / d1) * ((y[1] - y[0]) / d1 - slope0);
   } else { ddy[0] = 0.; rhs[0] = 0.; }
@@ -182,7 +183,7 @@ int compat_spline_second_derivatives(const double *x, int n, const double *y, do
   double qn = 0., un = 0.;
   if (est_deriv) {
     const double e1 = x[n - 2] - x[n - 1], e2 = x[n - 3] - x[n - 1];
-    const double slopeN = (e2 * e2 * (y[n - 2] - y[n - 1]) - e1 * e1 * (y[n - 3] - y[n - 1])) / (e2 * e1 * (e2 - e1));
+    const double slopeN = (e2 * e2 * (y[n - 2] - y[n - 1]) - e1 * e1 * (y[n - 3] - y[n - 1])) / (e2 * e1 * (x[n - 3] - x[n - 2]));
     qn = 0.5;
     un = (3. / (x[n - 1] - x[n - 2])) * (slopeN - (y[n - 1] - y[n - 2]) / (x[n - 1] - x[n - 2]));
   }

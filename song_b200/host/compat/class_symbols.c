@@ -83,6 +83,10 @@ int array_spline_table_one_column(double *x, int x_size, double *y_array, int y_
                                   short spline_mode, ErrorMsg errmsg)
 {
   (void)y_size;
+  if (x_size < 3) {          /* upstream has no such test (it would read x[2]); tables this short are never interpolated in */
+    for (int i = 0; i < x_size; ++i) ddy_array[(size_t)index_y * x_size + i] = 0.;
+    return _SUCCESS_;
+  }
   if (compat_spline_second_derivatives(x, x_size, y_array + (size_t)index_y * x_size, ddy_array + (size_t)index_y * x_size,
                                        spline_mode == _SPLINE_EST_DERIV_)) {
     snprintf(errmsg, _ERRORMSGSIZE_, "array_spline_table_one_column: x_size=%d too small or repeated abscissa", x_size);

@@ -10,6 +10,8 @@ import numpy as np
 from song_b200 import _lib
 
 PATH = os.path.join(os.path.dirname(_lib.LOS_PATH), "libsong_transfer2.so")
+# the REFERENCE's own transfer2.c + bessel2.c behind the same harness (oracle/Makefile, target `ref`; test infrastructure)
+REF_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libsong_ref.so")
 DROPIN_SYMBOLS = [  # called from outside the module in the reference + the rest of transfer2.h:327-541
     "transfer2_init", "transfer2_free", "transfer2_get_k3_list", "transfer2_load_transfers_from_disk",
     "transfer2_free_type_level", "transfer2_indices_of_transfers", "transfer2_get_l_list", "transfer2_get_lm_lists",
@@ -49,16 +51,21 @@ class HarnessInput(C.Structure):
     ]
 
 
-_dll = None
+_dlls = {}
 
 
-def lib():
-    global _dll
+def lib(path: str | None = None):
+    """The harness library: the drop-in (default) or, with path=REF_PATH, the reference's own modules.  The reference
+    library is loaded RTLD_LOCAL (and linked -Bsymbolic): both export transfer2_init & co."""
+    path = path or PATH
+    _dll = _dlls.get(path)
     if _dll is None:
-        if not os.path.exists(PATH):
-            raise _lib.SongLosError(f"{PATH} is missing: run __graft_entry__.build() where the SONG headers are available")
-        _lib.host()
-        _dll = C.CDLL(PATH, mode=C.RTLD_GLOBAL)
+        if not os.path.exists(path):
+            raise _lib.SongLosError(f"{path} is missing: run __graft_entry__.build() where the SONG headers are available")
+        if path == PATH:
+            _lib.host()
+        _dll = C.CDLL(path, mode=C.RTLD_GLOBAL if path == PATH else C.RTLD_LOCAL)
+        _dlls[path] = _dll
         vp = C.c_void_p
         _dll.harness_transfer2.argtypes = [C.POINTER(HarnessInput), dp, C.c_longlong, lp, ip, C.c_char_p, C.c_int]
         _dll.harness_create.argtypes = [C.POINTER(HarnessInput), C.c_char_p, C.c_int]
@@ -135,27 +142,31 @@ class Harness:
     h.transfer2_free(); h.fill_sources(); h.transfer2_init()   # next step
     """
 
-    def __init__(self, wl, proj=None, store_dir=None, verbose=0, keep_sources=False):
+    def __init__(self, wl, proj=None, store_dir=None, verbose=0, keep_sources=False, lib_path=None):
         self.wl = wl
+        self.lib_path = lib_path
         self.inp, self._keep = _input(wl, proj, store_dir, verbose, use_bessel2_init=proj is None, keep_sources=keep_sources)
         err = C.create_string_buffer(4096)
-        self.h = lib().harness_create(C.byref(self.inp), err, 4096)
+        self.h = self._lib().harness_create(C.byref(self.inp), err, 4096)
         if not self.h:
             raise _lib.SongLosError(err.value.decode(errors="replace"))
+
+    def _lib(self):
+        return lib(self.lib_path)
 
     def _check(self, rc, err):
         if rc:
             raise _lib.SongLosError(err.value.decode(errors="replace"))
 
     def fill_sources(self):
-        lib().harness_fill_sources(self.h)
+        self._lib().harness_fill_sources(self.h)
 
     def transfer2_init(self):
         err = C.create_string_buffer(4096)
-        self._check(lib().harness_transfer2_init(self.h, err, 4096), err)
+        self._check(self._lib().harness_transfer2_init(self.h, err, 4096), err)
 
     def checksum(self) -> float:
-        return float(lib().harness_checksum(self.h))
+        return float(self._lib().harness_checksum(self.h))
 
     def read(self):
         lay, wl = self.wl.layout, self.wl
@@ -163,13 +174,13 @@ class Harness:
         sizes = (C.c_longlong * 3)()
         labels_ok = C.c_int(0)
         err = C.create_string_buffer(4096)
-        self._check(lib().harness_read(self.h, _lib.dptr(out), out.size, sizes, C.byref(labels_ok), err, 4096), err)
+        self._check(self._lib().harness_read(self.h, _lib.dptr(out), out.size, sizes, C.byref(labels_ok), err, 4096), err)
         assert sizes[0] == lay.tt2_size and sizes[1] == wl.n_units, (list(sizes), lay.tt2_size, wl.n_units)
         return out, int(sizes[2]), bool(labels_ok.value)
 
     def transfer2_free(self):
         err = C.create_string_buffer(4096)
-        self._check(lib().harness_transfer2_free(self.h, err, 4096), err)
+        self._check(self._lib().harness_transfer2_free(self.h, err, 4096), err)
 
     def bessel2_tables(self):
         """(rows, index_xmin_J, x_size_J, ddrows, info) of struct bessels2, flat jidx order (copies)."""
@@ -178,7 +189,7 @@ class Harness:
         sizes = (C.c_longlong * 6)()
         xmin = np.zeros(n, dtype=np.int32); xsize = np.zeros(n, dtype=np.int32)
         rows = (dp * n)(); ddrows = (dp * n)()
-        lib().harness_bessel2_tables(self.h, _lib.iptr(xmin), _lib.iptr(xsize), rows, ddrows, sizes)
+        self._lib().harness_bessel2_tables(self.h, _lib.iptr(xmin), _lib.iptr(xsize), rows, ddrows, sizes)
         out = [np.ctypeslib.as_array(rows[i], shape=(int(xsize[i]),)).copy() if xsize[i] > 0 and rows[i] else None for i in range(n)]
         dd = [np.ctypeslib.as_array(ddrows[i], shape=(int(xsize[i]),)).copy() if xsize[i] > 0 and ddrows[i] else None for i in range(n)]
         info = dict(J_size=sizes[0], L_size=sizes[1], xx_size=sizes[2], l1_size=sizes[3], x_size_max_J=sizes[4], count_allocated_Js=sizes[5])
@@ -186,9 +197,9 @@ class Harness:
 
     def l1_info(self):
         sizes = (C.c_longlong * 6)()
-        lib().harness_bessel2_tables(self.h, None, None, None, None, sizes)
+        self._lib().harness_bessel2_tables(self.h, None, None, None, None, sizes)
         l1 = np.zeros(int(sizes[3]), dtype=np.int32); xmin = np.zeros(int(sizes[3]))
-        lib().harness_l1_info(self.h, _lib.iptr(l1), _lib.dptr(xmin))
+        self._lib().harness_l1_info(self.h, _lib.iptr(l1), _lib.dptr(xmin))
         return l1, xmin
 
     def bessel2_convolution(self, kk, delta_kk, f, g, index_l1, r) -> float:
@@ -196,7 +207,7 @@ class Harness:
         f = np.ascontiguousarray(f, dtype=np.float64)
         g = None if g is None else np.ascontiguousarray(g, dtype=np.float64)
         out = C.c_double(0)
-        rc = lib().harness_bessel2_convolution(self.h, _lib.dptr(kk), _lib.dptr(delta_kk), int(kk.size), _lib.dptr(f),
+        rc = self._lib().harness_bessel2_convolution(self.h, _lib.dptr(kk), _lib.dptr(delta_kk), int(kk.size), _lib.dptr(f),
                                                None if g is None else _lib.dptr(g), int(index_l1), float(r), C.byref(out))
         if rc:
             raise _lib.SongLosError("bessel2_convolution failed")
@@ -204,7 +215,7 @@ class Harness:
 
     def close(self):
         if self.h:
-            lib().harness_destroy(self.h)
+            self._lib().harness_destroy(self.h)
             self.h = None
 
     def __enter__(self):

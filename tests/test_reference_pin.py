@@ -1,0 +1,172 @@
+"""The oracle pinned against the REFERENCE ITSELF, run here.
+
+oracle/Makefile (target `ref`) compiles the reference's own source/transfer2.c and source/bessel2.c, where they lie under
+/root/reference, into oracle/_ref/libsong_ref.so together with the harness that plays main/song.c:100-106.  The CLASS
+fork the reference depends on is absent (an empty submodule), so its declarations and the handful of helpers the two
+files call are stand-ins (oracle/ref_build/ref_prelude.h); everything between transfer2_init and transfer2_integrate,
+and between bessel2_init and bessel2_J_Llm, is the reference's own code, unmodified.
+
+What is compared, bit for bit (np.array_equal):
+  * ptr2->transfer after the reference's transfer2_init  ==  the oracle's transfer functions, for the same sources and the
+    same projection tables, over the options of the path (k3 interpolation, extrapolation, fields, m, time sampling and
+    time interpolation, Bessel interpolation, long k3 grids) and on BASELINE configs[0] at full size;
+  * struct bessels2 after the reference's bessel2_init  ==  the oracle's tables, when both start from the same j_l(x) and
+    3j numbers (libsong_ref_op.so: the two providers of the absent fork answered by the oracle's);
+  * bessel2_convolution.
+The GPU path is bit-identical to the oracle in EXACT mode (tests -m gpu), hence to the reference's code.
+
+The library does not exist on the GPU box unless it travelled with the snapshot; tests skip when it is missing.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import dropin_lib
+from song_b200 import configs, workload
+
+REF = dropin_lib.REF_PATH
+REF_OP = REF.replace("libsong_ref.so", "libsong_ref_op.so")
+needs_ref = pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/libsong_ref.so not built (needs /root/reference)")
+needs_ref_op = pytest.mark.skipif(not os.path.exists(REF_OP), reason="oracle/_ref/libsong_ref_op.so not built")
+
+
+def reference_transfer2(wl, proj, lib_path=REF):
+    with dropin_lib.Harness(wl, proj, lib_path=lib_path) as h:
+        h.transfer2_init()
+        got, count, labels_ok = h.read()
+        h.transfer2_free()
+    return got, count, labels_ok
+
+
+VARIANTS = [
+    dict(sources_k3_interpolation="linear"),
+    dict(sources_k3_interpolation="cubic"),
+    dict(output=["tBisp"], sources_k3_interpolation="cubic"),
+    dict(bispectra_k3_extrapolation="no_extrapolation", sources_k3_interpolation="cubic"),
+    dict(modes_song=[0, 1, 2], sources_k3_interpolation="cubic", has_source_B=True),
+    dict(bessels_interpolation="cubic", sources_k3_interpolation="cubic"),
+    dict(k3_size_min=300, sources_k3_interpolation="cubic"),
+    dict(l_max_los_t=14, l_max_los_p=14, sources_k3_interpolation="cubic"),
+    dict(extra_k3_oscillations_left=0.5, extra_k3_oscillations_right=12, sources_k3_interpolation="cubic"),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["smooth", "noise"])
+@pytest.mark.parametrize("kw", VARIANTS, ids=lambda kw: ",".join(f"{k}={v}" for k, v in kw.items())[:60])
+def test_reference_transfer2_init_equals_oracle(oracle, kw, kind):
+    wl = workload.fill_sources(workload.build_grids(configs.tiny(**kw)), kind=kind)
+    proj = oracle.build_projection(wl, spline=kw.get("bessels_interpolation") == "cubic")
+    ref, _ = oracle.OracleRun(wl, proj).run()
+    got, count, labels_ok = reference_transfer2(wl, proj)
+    assert got.shape == ref.shape                      # the k3 grids of transfer2_get_k3_sizes have the oracle's / los_host.c's sizes
+    assert count == wl.n_integrals and labels_ok       # count_memorised_transfers (transfer2.c:607-610), labels
+    assert np.array_equal(got, ref), f"max abs diff {np.abs(got - ref).max()}"
+    assert np.abs(ref).max() > 0
+
+
+@needs_ref
+@pytest.mark.parametrize("time_interp", ["linear", "cubic"])
+@pytest.mark.parametrize("sampling", ["custom", "bessel"])
+def test_reference_k_dependent_time_grids_equal_oracle(oracle, sampling, time_interp):
+    """transfer2_get_time_grid (transfer2.c:2366-2585) and transfer2_interpolate_sources_in_time (:2783-2908)."""
+    p = configs.tiny(transfer2_tau_sampling=sampling, sources_time_interpolation=time_interp,
+                     sources_k3_interpolation="cubic", tau_linstep_song=0.003, bessel_x_step_song=0.04)
+    wl = workload.fill_sources(workload.build_grids(p), kind="noise")
+    proj = oracle.build_projection(wl)
+    ref, _ = oracle.OracleRun(wl, proj).run()
+    got, count, _ = reference_transfer2(wl, proj)
+    assert count == wl.n_integrals
+    assert np.array_equal(got, ref), f"max abs diff {np.abs(got - ref).max()}"
+
+
+@needs_ref
+def test_reference_equals_oracle_on_baseline_config0(oracle):
+    """BASELINE.json configs[0] (quick_song_run) at full size through the reference's transfer2_init."""
+    wl = workload.fill_sources(workload.build_grids(configs.get("quick_song_run")))
+    proj = oracle.build_projection(wl)
+    ref, _ = oracle.OracleRun(wl, proj).run()
+    got, count, labels_ok = reference_transfer2(wl, proj)
+    assert count == wl.n_integrals == 654112 and labels_ok
+    assert np.array_equal(got, ref)
+
+
+@needs_ref_op
+@pytest.mark.parametrize("kw", [dict(sources_k3_interpolation="cubic"), dict(output=["tBisp"]),
+                                dict(modes_song=[0, 1, 2], sources_k3_interpolation="cubic", has_source_B=True),
+                                dict(bessels_interpolation="cubic", sources_k3_interpolation="cubic")],
+                         ids=["T+E", "T", "m012+B", "cubicJ"])
+def test_reference_bessel2_init_equals_oracle(oracle, kw):
+    """struct bessels2 as the reference's bessel2_init leaves it (bessel2.c:75-468) against the oracle's restatement of
+    bessel2_get_l1_list, bessel2_j_for_l1, bessel2_J_for_Llm and bessel2_J_Llm, from the same j_l(x) and 3j numbers; then
+    transfer2_init on those tables."""
+    wl = workload.fill_sources(workload.build_grids(configs.tiny(**kw)), kind="noise")
+    spline = kw.get("bessels_interpolation") == "cubic"
+    proj = oracle.build_projection(wl, with_jl1=True, spline=spline)
+    dropin_lib.lib(REF_OP).ref_set_bessel_table_lmax(ctypes.c_int(int(proj.jl1["l1"].max())))
+    with dropin_lib.Harness(wl, None, lib_path=REF_OP) as h:      # proj None: the harness calls bessel2_init
+        rows, xmin, xsize, dd, info = h.bessel2_tables()
+        l1, x_min_l1 = h.l1_info()
+        h.transfer2_init()
+        got, count, _ = h.read()
+        h.transfer2_free()
+    assert np.array_equal(l1, proj.jl1["l1"]) and np.array_equal(x_min_l1, proj.jl1["x_min_l1"])      # l1 list and lower cuts
+    assert np.array_equal(xsize, proj.x_size)
+    live = proj.x_size > 0
+    assert np.array_equal(xmin[live], proj.index_xmin[live])
+    n = 0
+    for a, b in zip(rows, proj.rows):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert np.array_equal(a, b)
+            n += 1
+    assert n == int(live.sum()) and n > 0
+    if spline:                                          # pbs2->ddJ_Llm_x, bessel2.c:395-435
+        # (tables shorter than 3 points: upstream reads past the end there; neither side uses them)
+        assert all(np.array_equal(a, b) for a, b, r in zip(dd, proj.ddrows, proj.rows) if a is not None and r.size >= 3)
+    ref, _ = oracle.OracleRun(wl, proj).run()
+    assert count == wl.n_integrals and np.array_equal(got, ref)
+
+
+@needs_ref_op
+def test_reference_bessel2_convolution_equals_oracle(oracle):
+    """bessel2_convolution (bessel2.c:499-605) of the reference on its own j_l1 table against the oracle's restatement on
+    the oracle's table -- the same numbers, see test_reference_bessel2_init_equals_oracle."""
+    wl = workload.fill_sources(workload.build_grids(configs.tiny(sources_k3_interpolation="cubic")))
+    proj = oracle.build_projection(wl, with_jl1=True)
+    dropin_lib.lib(REF_OP).ref_set_bessel_table_lmax(ctypes.c_int(int(proj.jl1["l1"].max())))
+    rng = np.random.default_rng(5)
+    kk = np.sort(rng.uniform(1e-4, 0.05, 60)); dk = np.gradient(kk); f = rng.standard_normal(60); g = rng.standard_normal(60)
+    f[7] = 0.0; g[11] = 0.0
+    with dropin_lib.Harness(wl, None, lib_path=REF_OP) as h:
+        l1, x_min_l1 = h.l1_info()
+        vals = [(i, r, h.bessel2_convolution(kk, dk, f, g if i % 2 else None, i, r)) for i in (0, 3, len(l1) - 1) for r in (200.0, 1000.0)]   # k r stays inside the table (xx_max = 63)
+    assert any(v != 0.0 for _, _, v in vals)
+    assert np.array_equal(proj.jl1["l1"], l1) and np.array_equal(proj.jl1["x_min_l1"], x_min_l1)
+    L = oracle.lib()
+    for i, r, v in vals:
+        out = ctypes.c_double(0)
+        gp = g.ctypes.data_as(oracle.dp) if i % 2 else None
+        row = np.ascontiguousarray(proj.jl1["j_l1"][i])
+        assert L.oracle_bessel2_convolution(kk.ctypes.data_as(oracle.dp), dk.ctypes.data_as(oracle.dp), 60, f.ctypes.data_as(oracle.dp), gp,
+                                            row.ctypes.data_as(oracle.dp), None, float(x_min_l1[i]), float(wl.xx_step), 0, float(r),
+                                            ctypes.byref(out)) == 0
+        assert out.value == v, (i, r, out.value, v)
+
+
+@needs_ref
+def test_reference_and_dropin_libraries_coexist():
+    """Both libraries export transfer2_init & co.; the reference one is linked -Bsymbolic and loaded RTLD_LOCAL, so that
+    neither binds to the other's symbols when a test process holds both."""
+    if not os.path.exists(dropin_lib.PATH):
+        pytest.skip("libsong_transfer2.so not built")
+    a, b = dropin_lib.lib(), dropin_lib.lib(REF)
+    assert ctypes.cast(a.transfer2_init, ctypes.c_void_p).value != ctypes.cast(b.transfer2_init, ctypes.c_void_p).value
+    wl = workload.fill_sources(workload.build_grids(configs.tiny()))
+    import oracle_lib as O
+    proj = O.build_projection(wl)
+    ref, _ = O.OracleRun(wl, proj).run()
+    got, _, _ = reference_transfer2(wl, proj)          # with the drop-in loaded: still the reference's own code path
+    assert np.array_equal(got, ref)
