@@ -207,6 +207,59 @@ def cpu_sample(name: str, target_seconds: float, max_pairs=None):
     return grids, sub, proj, stride
 
 
+def reference_triangle(name: str, n_k: int, max_pairs=None):
+    """The workload restricted to `n_k` of its k values: the reference's transfer2_init loops over the whole (k1,k2)
+    triangle of ppt2->k, so a bounded sample of a run is the whole triangle of a thinned k list (every pair of it is a pair
+    of the full run, with the same coarse and fine k3 grids).  The k values kept are the midpoints of n_k equal strata of
+    the k list, so that the kept pairs form a regular lattice over the full triangle and cheap low-k and expensive high-k
+    pairs appear in the run's own proportions (keeping both ends of the list instead over-weights the most expensive
+    row: 1.15e5 instead of ~4e5 integrals/s at configs[3])."""
+    from song_b200 import configs, workload
+    p = configs.get(name)
+    k_full = workload.build_grids(p, max_pairs=1).k
+    n_k = max(2, min(n_k, k_full.size))
+    idx = np.unique(np.floor((np.arange(n_k) + 0.5) * k_full.size / n_k).astype(int))
+    return workload.build_grids(dict(p, k=k_full[idx]), max_pairs=max_pairs), int(k_full.size)
+
+
+def time_reference_library(name: str, target_seconds: float, steps: int, warmup: int):
+    """oracle/_ref/libsong_ref.so -- the reference's own source/transfer2.c, compiled where it lies (oracle/Makefile) --
+    timed on a bounded sample of workload `name`: transfer2_init on SONG structures, all host threads (the reference
+    parallelises the k3 loop of every pair with OpenMP, transfer2.c:450).  Returns None when the library is not there."""
+    import dropin_lib
+    import oracle_lib as O
+    from song_b200 import workload
+    if not os.path.exists(dropin_lib.REF_PATH):
+        return None
+    probe, k_size = reference_triangle(name, 3)
+    workload.fill_sources(probe)
+    proj = O.build_projection(probe)                   # the tables depend on the multipole lists and the x grid only
+    with dropin_lib.Harness(probe, proj, lib_path=dropin_lib.REF_PATH, keep_sources=True) as h:
+        t = time.perf_counter(); h.transfer2_init(); dt = time.perf_counter() - t
+        got, count, _ = h.read()
+        h.transfer2_free()
+    ref, _ = O.OracleRun(probe, proj).run()
+    same = bool(np.array_equal(got, ref))              # the arm being timed computes what the oracle computes, bit for bit
+    # a triangle of n_k of the k_size values holds about (n_k / k_size)^2 of the run's integrals
+    from song_b200 import configs
+    full_integrals = workload.build_grids(configs.get(name)).n_integrals
+    rate = probe.n_integrals / max(dt, 1e-9)
+    n_k = int(max(4, min(k_size, round(k_size * (target_seconds * rate / full_integrals) ** 0.5))))
+    sub, _ = reference_triangle(name, n_k)
+    workload.fill_sources(sub)
+    each = []
+    with dropin_lib.Harness(sub, proj, lib_path=dropin_lib.REF_PATH, keep_sources=True) as h:
+        for i in range(warmup + steps):
+            t = time.perf_counter(); h.transfer2_init(); dt = time.perf_counter() - t
+            if i >= warmup:
+                each.append(dt)
+            h.transfer2_free(); h.fill_sources()
+    dt = sum(each) / max(len(each), 1)
+    return {"value": sub.n_integrals / dt, "seconds_per_step": dt, "integrals": sub.n_integrals, "pairs": sub.n_pairs,
+            "k_values": int(sub.k.size), "k_size_full": k_size, "probe_bitwise_equal_to_oracle": same,
+            "cores": O.lib().oracle_num_threads()}
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
@@ -214,7 +267,32 @@ def run_reference(args, rank: int, world: int):
     if "LOCAL_RANK" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import oracle_lib as O
-    from song_b200 import workload
+    from song_b200 import configs, workload
+    set_omp_threads(os.cpu_count() or 1)
+    lib_run = time_reference_library(args.workload, args.cpu_seconds, max(args.steps, 1), args.warmup)
+    if lib_run is not None:
+        grids = workload.build_grids(configs.get(args.workload))
+        value = lib_run["value"]
+        sample = (f"transfer2_init of the reference on the whole (k1,k2) triangle of {lib_run['k_values']} of the {lib_run['k_size_full']} k values of "
+                  f"{args.workload} (midpoints of equal strata of the k list): {lib_run['pairs']} pairs, {lib_run['integrals']} of {grids.n_integrals} integrals per step")
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": lib_run["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload.describe(grids), workload=args.workload,
+                           note="the reference's own source/transfer2.c (coccoinomane/song @ 2ea44ecf), compiled where it lies into oracle/_ref/"
+                                "libsong_ref.so with stand-ins for the declarations and helpers of its absent CLASS fork (oracle/ref_build/), "
+                                "run through its module API transfer2_init on SONG structures; synthetic inputs from the same generator as "
+                                "the GPU arm; projection tables from the oracle's bessel2 restatement; the GPU is idle"),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": lib_run["cores"], "cpu_model": cpu_model(), "kind": "reference", "sample": sample,
+                             "probe_bitwise_equal_to_oracle": lib_run["probe_bitwise_equal_to_oracle"],
+                             "build": "gcc -O2 -std=gnu99 -fopenmp -ffp-contract=off on /root/reference/source/transfer2.c (oracle/Makefile, target ref); "
+                                      "no -DDEBUG (the reference Makefile's default adds debug-only checks)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return
     grids, sub, proj, stride = cpu_sample(args.workload, args.cpu_seconds)
     run = O.OracleRun(sub, proj)
     for _ in range(args.warmup):
@@ -683,7 +761,16 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None
-    if rank == 0 and with_cpu:
+    lib_run = None
+    if rank == 0 and with_cpu and args.max_pairs is None:
+        lib_run = time_reference_library(name, args.cpu_seconds, 1, 0)       # the reference's own transfer2.c when oracle/_ref is there
+    if lib_run is not None:
+        cpu = {"value": lib_run["value"], "unit": UNIT, "cores": lib_run["cores"], "cpu_model": cpu_model(), "kind": "reference",
+               "sample": f"transfer2_init of the reference's own source/transfer2.c (oracle/_ref/libsong_ref.so) on the whole (k1,k2) triangle of "
+                         f"{lib_run['k_values']} of the {lib_run['k_size_full']} k values (midpoints of equal strata): {lib_run['pairs']} pairs, {lib_run['integrals']} "
+                         f"integrals, one call of {lib_run['seconds_per_step']:.1f} s",
+               "probe_bitwise_equal_to_oracle": lib_run["probe_bitwise_equal_to_oracle"]}
+    elif rank == 0 and with_cpu:
         grids_c, sub_c, proj_c, stride = cpu_sample(name, args.cpu_seconds, max_pairs=args.max_pairs)
         run = O.OracleRun(sub_c, proj_c)
         t0 = time.perf_counter(); run.run(); dt = time.perf_counter() - t0

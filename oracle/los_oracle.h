@@ -5,14 +5,20 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may build,
  * load or call it, and only as the checker / the CPU baseline.
  *
- * PARITY UNPINNED: the reference (coccoinomane/song @ 2ea44ecf) ships no golden vectors or
- * known-answer tests for this path (test/print_transfers2.c only prints), and it cannot be
- * compiled here because its CLASS fork (class.git @ 2643d443) is an empty submodule.  This
- * oracle is a restatement of the reference loops, function by function, with the reference
- * file:line quoted at each function.  The helpers that live in the missing CLASS fork
- * (array_spline_table_columns, drc3jj, lin_space, *_indexl_indexm, bessel_j) are restated
- * from the published upstream CLASS / SLATEC algorithms and are flagged "UPSTREAM-RECALLED".
- * The oracle is additionally pinned by analytic known-answer tests (tests/test_oracle_kat.py).
+ * PARITY STATUS.  The reference (coccoinomane/song @ 2ea44ecf) ships no golden vectors or known-answer tests for
+ * this path (test/print_transfers2.c only prints), and as a whole it cannot be compiled here because its CLASS fork
+ * (class.git @ 2643d443) is an empty submodule.  Its two source files of THIS path, source/transfer2.c and
+ * source/bessel2.c, do compile where they lie against stand-ins for the fork's declarations and the handful of fork
+ * helpers they call (oracle/Makefile target `ref`, oracle/ref_build/): oracle/_ref/libsong_ref.so runs the reference's
+ * own transfer2_init, bessel2_init and bessel2_convolution on the test harness's structures, and
+ * tests/test_reference_pin.py finds this oracle's restatement of transfer2.c and bessel2.c BIT-IDENTICAL to them over
+ * the options of the path and on BASELINE configs[0] at full size.  That pins oracle_transfer2.c, oracle_bessel2.c and
+ * the helpers they use.  Still unpinned by reference execution: the helpers that live in the missing fork themselves
+ * (array_spline_table_columns, drc3jj, lin_space, *_indexl_indexm, bessel_j: restated from the published upstream
+ * CLASS / SLATEC algorithms, flagged "UPSTREAM-RECALLED"; bessel_j is a Miller recurrence, not CLASS's approximation --
+ * parity is defined on the same j_l(x) inputs), and the loops of oracle_bispectra2.c / oracle_spectra2.c around the
+ * pinned bessel2_convolution (bispectra2.c and spectra2.c need far more of the fork).  Those are pinned by analytic
+ * known-answer tests only (tests/test_oracle_kat.py).
  *
  * Floating-point contract: compile with -ffp-contract=off so every statement is evaluated
  * in the C left-to-right order written in the reference (no FMA contraction).

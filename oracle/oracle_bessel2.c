@@ -1,6 +1,6 @@
 /*
  * oracle_bessel2.c -- restatement of the projection-function tables of SONG's bessel2.c.
- * TEST INFRASTRUCTURE ONLY (see los_oracle.h).  PARITY UNPINNED.
+ * TEST INFRASTRUCTURE ONLY (see los_oracle.h).  PINNED: bit-identical to the reference's own source/bessel2.c run here on the same j_l(x) / 3j numbers (tests/test_reference_pin.py).
  */
 #include <math.h>
 #include <stdio.h>

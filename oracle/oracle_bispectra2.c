@@ -1,7 +1,7 @@
 /*
  * oracle_bispectra2.c -- restatement of the k3 integral of SONG's intrinsic bispectrum,
  * bispectra2_intrinsic_integrate_over_k3 (source/bispectra2.c:1107-1439).
- * TEST INFRASTRUCTURE ONLY (see los_oracle.h).  PARITY UNPINNED.
+ * TEST INFRASTRUCTURE ONLY (see los_oracle.h).  PARITY UNPINNED by reference execution (bispectra2.c needs far more of the absent fork); its inner bessel2_convolution is pinned.
  */
 #include <math.h>
 #include <stdio.h>

@@ -1,6 +1,6 @@
 /*
  * oracle_tools.c -- restatements of the CLASS-fork helpers the hot path calls.
- * TEST INFRASTRUCTURE ONLY (see los_oracle.h).  PARITY UNPINNED.
+ * TEST INFRASTRUCTURE ONLY (see los_oracle.h).  Helpers of the absent CLASS fork, UPSTREAM-RECALLED: pinned by known-answer tests only (tests/test_oracle_kat.py).
  *
  * Every function here is UPSTREAM-RECALLED: the sources (class.git/tools/arrays.c,
  * song_tools.c, slatec_3j_C.c, source/bessel.c) are absent from /root/reference, so the

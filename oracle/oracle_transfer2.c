@@ -1,6 +1,6 @@
 /*
  * oracle_transfer2.c -- restatement of the compute phase of SONG's source/transfer2.c.
- * TEST INFRASTRUCTURE ONLY (see los_oracle.h).  PARITY UNPINNED.
+ * TEST INFRASTRUCTURE ONLY (see los_oracle.h).  PINNED: bit-identical to the reference's own source/transfer2.c run here (tests/test_reference_pin.py).
  *
  * Statement order inside each expression follows the reference (C left-to-right); build with
  * -ffp-contract=off.  Struct-pointer plumbing is replaced by the flat oracle_setup record.

@@ -241,3 +241,19 @@ def test_bench_line_two_ranks_gloo(tmp_path, bands):
     assert len(line["roofline"]["per_rank"]["k3_values"]) == 2
     if bands > 1:
         assert "skipped" in line["k3_integral"]
+
+
+def test_reference_arm_times_the_reference_library(monkeypatch):
+    """bench.py --impl reference: the CPU arm is the reference's own transfer2.c (oracle/_ref) when that library is there,
+    the oracle port otherwise; either way one JSON line with impl = reference and no GPU work."""
+    import dropin_lib
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    line = run_bench(monkeypatch, ["--impl", "reference", "--workload", "quick_song_run", "--steps", "1", "--warmup", "0", "--cpu-seconds", "0.5"])
+    assert line["impl"] == "reference" and line["gpu_launches"] == 0 and line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    c = line["cpu_baseline"]
+    assert c["value"] == line["value"] and c["cores"] >= 1 and "sample" in c
+    if os.path.exists(dropin_lib.REF_PATH):
+        assert c["kind"] == "reference" and c["probe_bitwise_equal_to_oracle"] is True
+    else:
+        assert c["kind"] == "port"

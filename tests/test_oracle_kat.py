@@ -1,8 +1,10 @@
 """Known-answer tests that pin the CPU oracle.
 
-The reference ships no golden vectors for this path ("parity unpinned"), so the oracle is pinned
-by answers that depend on neither implementation: closed forms, exact rational arithmetic,
-scipy special functions and an independent vectorised numpy restatement of the LOS sum.
+The reference ships no golden vectors for this path.  Its own transfer2.c and bessel2.c, compiled where they lie, pin
+the oracle's restatement of those two files bit for bit (tests/test_reference_pin.py); the helpers of its absent CLASS
+fork (splines, 3j, j_l, index maps) cannot be pinned that way, so they -- and the LOS sum once more -- are pinned here by
+answers that depend on neither implementation: closed forms, exact rational arithmetic, scipy special functions and an
+independent vectorised numpy restatement of the LOS sum.
 """
 import ctypes as C
 import math
