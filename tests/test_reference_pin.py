@@ -170,3 +170,32 @@ def test_reference_and_dropin_libraries_coexist():
     ref, _ = O.OracleRun(wl, proj).run()
     got, _, _ = reference_transfer2(wl, proj)          # with the drop-in loaded: still the reference's own code path
     assert np.array_equal(got, ref)
+
+
+# ---- the GPU against the reference's own code, directly (driver-run: -m gpu) ----
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("kw,kind", [(dict(sources_k3_interpolation="cubic"), "noise"),
+                                     (dict(modes_song=[0, 1, 2], sources_k3_interpolation="cubic", has_source_B=True), "smooth")],
+                         ids=["T+E", "m012+B"])
+def test_gpu_equals_reference_transfer2_init(oracle, kw, kind, monkeypatch):
+    """The engine through the C-ABI (EXACT: bit for bit; FAST: <= 1e-9) and the drop-in's transfer2_init (EXACT) against
+    ptr2->transfer as the reference's own transfer2_init leaves it, same sources, same projection tables."""
+    from song_b200.engine import MODE_EXACT, MODE_FAST, LosEngine, Projection
+    wl = workload.fill_sources(workload.build_grids(configs.tiny(**kw)), kind=kind)
+    proj = oracle.build_projection(wl)
+    ref, count, _ = reference_transfer2(wl, proj)
+    assert count == wl.n_integrals
+    eng = LosEngine(wl, device=0)
+    eng.set_projection(Projection(proj.rows, proj.index_xmin, proj.x_size, proj.ddrows))
+    got = eng.transfer_pairs(wl, mode=MODE_EXACT)
+    assert np.array_equal(got, ref), f"max abs diff {np.abs(got - ref).max()}"
+    fast = eng.transfer_pairs(wl, mode=MODE_FAST)
+    eng.close()
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    sel = np.abs(ref) > 1e-6 * scale
+    assert float(np.max(np.abs(fast - ref)[sel] / np.abs(ref)[sel])) < 1e-9
+    if os.path.exists(dropin_lib.PATH):
+        monkeypatch.setenv("SONG_LOS_MODE", "exact")
+        got2, count2, labels_ok = dropin_lib.run_transfer2(wl, Projection(proj.rows, proj.index_xmin, proj.x_size))
+        assert count2 == count and labels_ok and np.array_equal(got2, ref)
