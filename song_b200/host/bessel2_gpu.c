@@ -189,6 +189,16 @@ int bessel2_convolution(struct precision *ppr, struct bessels2 *pbs2, double *kk
 /* ------------------------------------------------------------------------------------------------ */
 /*  bessel2_init (reference: bessel2.c:75-468)                                                       */
 /* ------------------------------------------------------------------------------------------------ */
+#ifndef SONG_B200_COMPAT_HEADERS
+/* CLASS's bessel_j behind the provider signature of bessel2_host.h */
+static double los_class_bessel_j(int l, double x, void *user)
+{
+  double j = 0.;
+  bessel_j((struct bessels *)user, l, x, &j);
+  return j;
+}
+#endif
+
 int bessel2_init(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2, struct bessels *pbs, struct bessels2 *pbs2)
 {
   if ((pbs->l_max == 0) || ((ppt2->has_cmb_spectra == _FALSE_) && (ppt2->has_cmb_bispectra == _FALSE_))
@@ -230,6 +240,11 @@ int bessel2_init(struct precision *ppr, struct precision2 *ppr2, struct perturbs
     printf(" -> will compute size_J=%d projection functions\n", pbs2->J_size);
 
   /* ---- host half: l1 list, j_l1(x), 3j symbols ---- */
+#ifndef SONG_B200_COMPAT_HEADERS
+  /* a SONG tree: CLASS's own bessel_j, called point by point as bessel2_j_for_l1 does (bessel2.c:1706,1724,1804), so that
+     pbs2->j_l1 -- and everything assembled from it -- holds the reference's numbers (bessel2_host.h) */
+  song_host_bessel2_set_provider(los_class_bessel_j, pbs);
+#endif
   song_bessel2_host *hb = NULL;
   class_test(song_host_bessel2_prepare(pbs->l, pbs->l_size, pbs2->m, pbs2->m_size, pbs2->L_max, pbs2->xx, pbs2->xx_size, pbs2->xx_max,
                                        pbs2->J_size, J_types, pbs2->j_l1_cut, ppr->bessel_tol_x_min, ppr->smallest_allowed_variation,

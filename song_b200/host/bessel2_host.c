@@ -9,6 +9,12 @@
 #include "bessel2_host.h"
 #include "class_compat.h"
 
+/* j_l(x) provider (bessel2_host.h) */
+static song_host_bessel_fn g_bessel_fn = NULL;
+static void *g_bessel_user = NULL;
+void song_host_bessel2_set_provider(song_host_bessel_fn fn, void *user) { g_bessel_fn = fn; g_bessel_user = user; }
+static double jl_point(int l, double x) { return g_bessel_fn ? g_bessel_fn(l, x, g_bessel_user) : compat_bessel_j(l, x); }
+
 static int b2_fail(char *errmsg, int errlen, const char *text)
 {
   if (errmsg && errlen > 0) snprintf(errmsg, (size_t)errlen, "%s", text);
@@ -68,11 +74,11 @@ int song_host_bessel2_prepare(const int *l, int l_size, const int *m, int m_size
     t->index_xmin_l1[i] = 0;
     if (l1 != 0) {
       double lo = 0, hi = (double)l1 + 0.5;
-      if (compat_bessel_j(l1, hi) < j_l1_cut) { bad = 1; continue; }  /* :1713 */
+      if (jl_point(l1, hi) < j_l1_cut) { bad = 1; continue; }  /* :1713 */
       while ((hi - lo) / lo > tol_x_min) {
         if ((hi - lo) < smallest_var) { hi = lo; break; }
         double mid = 0.5 * (hi + lo);
-        if (compat_bessel_j(l1, mid) >= j_l1_cut) hi = mid; else lo = mid;
+        if (jl_point(l1, mid) >= j_l1_cut) hi = mid; else lo = mid;
       }
       x_min = lo;
       if (x_min < xx_max) {
@@ -93,7 +99,17 @@ int song_host_bessel2_prepare(const int *l, int l_size, const int *m, int m_size
   if (bad) { free(all_negligible); song_host_bessel2_free(t); return b2_fail(errmsg, errlen, "in bisection, wrong initial guess for x_min_up."); }
   for (int i = 0; i < n1; ++i) t->count_allocated_Js += t->x_size_l1[i];
 
-  /* ---- fill j_l1(xx) (bessel2.c:1802-1810), one recurrence per x serving every l1 ---- */
+  /* ---- fill j_l1(xx) (bessel2.c:1802-1810) ---- */
+  const char *pp = getenv("SONG_LOS_JL1_PER_POINT");
+  if (g_bessel_fn != NULL || (pp != NULL && pp[0] == '1')) {
+    /* the reference's call pattern: the provider once per (l1, x) */
+    #pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < n1; ++i) {
+      if (all_negligible[i]) continue;
+      for (int r = 0; r < t->x_size_l1[i]; ++r) t->j_l1[i][r] = jl_point(t->l1[i], xx[t->index_xmin_l1[i] + r]);
+    }
+  } else {
+  /* default provider: one recurrence per x serves every l1 */
   int lmax = t->l1[n1 - 1];
   #pragma omp parallel
   {
@@ -108,6 +124,7 @@ int song_host_bessel2_prepare(const int *l, int l_size, const int *m, int m_size
       }
     }
     free(col);
+  }
   }
   free(all_negligible);
 

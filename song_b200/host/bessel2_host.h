@@ -29,6 +29,14 @@ int song_host_bessel2_prepare(const int *l, int l_size, const int *m, int m_size
                               double j_l1_cut, double bessel_tol_x_min, double smallest_allowed_variation,
                               song_bessel2_host **out, char *errmsg, int errlen);
 void song_host_bessel2_free(song_bessel2_host *t);
+/* The j_l(x) provider of song_host_bessel2_prepare.  NULL (default): the recurrence of class_compat.c, where ONE downward
+   recurrence per x serves every l1 of the table.  In a SONG tree bessel2_gpu.c registers CLASS's own bessel_j, which is
+   then called point by point exactly as the reference's bessel2_j_for_l1 does (bessel2.c:1706,1724,1804), so that
+   pbs2->j_l1 holds the reference's numbers bit for bit (a recurrence started above the largest l1 and one started above
+   l1 itself agree only to the last 1-3 bits).  SONG_LOS_JL1_PER_POINT=1 selects the point-by-point pattern with the
+   default provider (tests/test_reference_pin.py compares it with the reference's own table). */
+typedef double (*song_host_bessel_fn)(int l, double x, void *user);
+void song_host_bessel2_set_provider(song_host_bessel_fn fn, void *user);
 /* hands the tables to the engine: J_Llm(x) is assembled on the device */
 int song_host_bessel2_upload(song_los_ctx *ctx, const song_bessel2_host *t, const int *J_types,
                              double J_Llm_cut, double xx_max, char *errmsg, int errlen);

@@ -79,6 +79,7 @@ def lib(path: str | None = None):
         _dll.harness_bessel2_tables.argtypes = [vp, ip, ip, C.POINTER(dp), C.POINTER(dp), lp]
         _dll.harness_bessel2_convolution.argtypes = [vp, dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, dp]
         _dll.harness_l1_info.argtypes = [vp, ip, dp]
+        _dll.harness_j_l1_row.argtypes = [vp, C.c_int, dp, C.c_int, ip]
         _dll.harness_destroy.argtypes = [vp]
     return _dll
 
@@ -201,6 +202,17 @@ class Harness:
         l1 = np.zeros(int(sizes[3]), dtype=np.int32); xmin = np.zeros(int(sizes[3]))
         self._lib().harness_l1_info(self.h, _lib.iptr(l1), _lib.dptr(xmin))
         return l1, xmin
+
+    def j_l1_rows(self, xx_size: int):
+        """pbs2->j_l1 as bessel2_init left it: (rows, index_xmin_l1)."""
+        sizes = (C.c_longlong * 6)()
+        self._lib().harness_bessel2_tables(self.h, None, None, None, None, sizes)
+        rows, xmin = [], []
+        buf = np.zeros(int(xx_size)); ix = C.c_int(0)
+        for i in range(int(sizes[3])):
+            n = self._lib().harness_j_l1_row(self.h, i, _lib.dptr(buf), int(xx_size), C.byref(ix))
+            rows.append(buf[:n].copy()); xmin.append(int(ix.value))
+        return rows, np.asarray(xmin, dtype=np.int32)
 
     def bessel2_convolution(self, kk, delta_kk, f, g, index_l1, r) -> float:
         kk = np.ascontiguousarray(kk, dtype=np.float64); delta_kk = np.ascontiguousarray(delta_kk, dtype=np.float64)

@@ -339,6 +339,15 @@ int harness_bessel2_convolution(harness *h, double *kk, double *delta_kk, int k_
 
 void harness_set_verbose(harness *h, int verbose) { h->tr2.transfer2_verbose = verbose; }
 const struct bessels2 *harness_bessels2(harness *h) { return &h->bs2; }
+/* pbs2->j_l1[index_l1][0 .. x_size_l1) and its first grid index: the table bessel2_j_for_l1 leaves (bessel2.c:1802-1810) */
+int harness_j_l1_row(harness *h, int index_l1, double *out, int n_max, int *index_xmin_l1)
+{
+  if (index_l1 < 0 || index_l1 >= h->bs2.l1_size || h->bs2.j_l1 == NULL) return -1;
+  const int n = h->bs2.x_size_l1[index_l1];
+  if (index_xmin_l1) *index_xmin_l1 = h->bs2.index_xmin_l1[index_l1];
+  for (int i = 0; i < n && i < n_max; ++i) out[i] = h->bs2.j_l1[index_l1][i];
+  return n;
+}
 int harness_l1_info(harness *h, int *l1, double *x_min_l1) { for (int i = 0; i < h->bs2.l1_size; ++i) { l1[i] = h->bs2.l1[i]; x_min_l1[i] = h->bs2.x_min_l1[i]; } return h->bs2.l1_size; }
 
 void harness_destroy(harness *h)

@@ -199,3 +199,25 @@ def test_gpu_equals_reference_transfer2_init(oracle, kw, kind, monkeypatch):
         monkeypatch.setenv("SONG_LOS_MODE", "exact")
         got2, count2, labels_ok = dropin_lib.run_transfer2(wl, Projection(proj.rows, proj.index_xmin, proj.x_size))
         assert count2 == count and labels_ok and np.array_equal(got2, ref)
+
+
+@needs_ref
+def test_product_host_half_equals_reference_j_l1_table(oracle, monkeypatch):
+    """The host half of the bessel2 drop-in (bessel2_host.c) against pbs2->j_l1 as the reference's bessel2_init leaves it
+    (bessel2_j_for_l1, bessel2.c:1669-1815), same j_l provider on both sides: l1 list, lower cuts, first grid indices and,
+    with the reference's point-by-point call pattern (the one a SONG tree gets, where CLASS's bessel_j is the provider),
+    every value of the table, bit for bit.  The default pattern of the stand-in provider (one recurrence per x for all
+    l1) gives the same numbers to the last 1-3 bits."""
+    from song_b200.bessel2 import Bessel2
+    wl = workload.fill_sources(workload.build_grids(configs.tiny(modes_song=[0, 1, 2], has_source_B=True)))
+    with dropin_lib.Harness(wl, None, lib_path=REF) as h:          # the reference's bessel2_init, compat providers
+        l1, x_min_l1 = h.l1_info()
+        rows, xmin = h.j_l1_rows(wl.xx.size)
+    monkeypatch.setenv("SONG_LOS_JL1_PER_POINT", "1")
+    ht = Bessel2(wl).prepare().host_tables()
+    assert np.array_equal(ht["l1"], l1) and np.array_equal(ht["x_min_l1"], x_min_l1) and np.array_equal(ht["index_xmin_l1"], xmin)
+    assert all(np.array_equal(a, b) for a, b in zip(ht["j_l1"], rows)) and len(rows) == len(ht["j_l1"]) > 10
+    monkeypatch.setenv("SONG_LOS_JL1_PER_POINT", "0")
+    ht0 = Bessel2(wl).prepare().host_tables()
+    worst = max(float(np.max(np.abs(a - b))) for a, b in zip(ht0["j_l1"], rows))
+    assert np.array_equal(ht0["index_xmin_l1"], xmin) and worst < 1e-15
