@@ -226,19 +226,21 @@ def _two_rank_worker(rank, world, port, bands, out_dir):
         assert not [l for l in buf.getvalue().splitlines() if l.startswith("{")]     # rank 0 alone prints the line
 
 
-@pytest.mark.parametrize("bands", [1, 2])
-def test_bench_line_two_ranks_gloo(tmp_path, bands):
+@pytest.mark.parametrize("world,bands", [(2, 1), (2, 2), (4, 2)], ids=["2 groups", "2 bands", "2 groups x 2 bands"])
+def test_bench_line_several_ranks_gloo(tmp_path, world, bands):
     import torch.multiprocessing as mp
-    port = 29900 + (os.getpid() % 90) + bands
-    mp.spawn(_two_rank_worker, args=(2, port, bands, str(tmp_path)), nprocs=2, join=True)
+    port = 29900 + (os.getpid() % 80) + 3 * world + bands
+    mp.spawn(_two_rank_worker, args=(world, port, bands, str(tmp_path)), nprocs=world, join=True)
     line = json.loads(open(tmp_path / "line.json").read())
-    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and len(line["per_rank_ms"]) == 2
+    assert line["n_gpus"] == world and line["scaling"] == "strong" and len(line["per_rank_ms"]) == world
+    assert f"{world // bands} (k1,k2)-pair group(s) x {bands} k3 band(s)" in line["config"]["parallelism"]
     assert f"x {bands} k3 band(s)" in line["config"]["parallelism"]
     assert line["parity"]["ok"]
     g = line["nccl_gather"]
     assert g["parity_of_gathered_array"]["ok"] and g["parity_of_gathered_array"]["pairs_checked"] >= 2
     assert g["parity_of_gathered_array"]["max_rel_err_above_1e-6_of_max"] == 0.0     # the fake engine IS the oracle
-    assert len(line["roofline"]["per_rank"]["k3_values"]) == 2
+    assert len(line["roofline"]["per_rank"]["k3_values"]) == world
+    assert sum(line["roofline"]["per_rank"]["k3_values"]) == line["config"]["k3_units"]      # every k3 value on exactly one GPU
     if bands > 1:
         assert "skipped" in line["k3_integral"]
 

@@ -221,3 +221,23 @@ def test_product_host_half_equals_reference_j_l1_table(oracle, monkeypatch):
     ht0 = Bessel2(wl).prepare().host_tables()
     worst = max(float(np.max(np.abs(a - b))) for a, b in zip(ht0["j_l1"], rows))
     assert np.array_equal(ht0["index_xmin_l1"], xmin) and worst < 1e-15
+
+
+@needs_ref
+def test_reference_disk_format_is_what_the_dropin_writes(oracle, tmp_path):
+    """store_transfers_to_disk through the REFERENCE (transfer2.c:559-567, 2929-2963): one transfers_%03d.dat per type, the
+    values in [k1][k2][k3] order -- the layout the drop-in's writer thread reproduces with one pwrite per batch and type
+    (tests/test_dropin.py checks its files against the same expectation on the GPU) -- and read back through the
+    reference's transfer2_load_transfers_from_disk / transfer2_free_type_level (the path bispectra2.c:1213,1298 takes)."""
+    wl = workload.fill_sources(workload.build_grids(configs.tiny()))
+    proj = oracle.build_projection(wl)
+    ref, _ = oracle.OracleRun(wl, proj).run()
+    with dropin_lib.Harness(wl, proj, store_dir=str(tmp_path), lib_path=REF) as h:
+        h.transfer2_init()
+        got, count, _ = h.read()                       # with store_to_disk the harness reads every type back from its file
+        h.transfer2_free()
+    assert np.array_equal(got, ref)
+    for tt in (0, wl.layout.tt2_size // 2, wl.layout.tt2_size - 1):
+        f = tmp_path / f"transfers_{tt:03d}.dat"
+        assert f.exists() and f.stat().st_size == 8 * wl.n_units
+        assert np.array_equal(np.fromfile(f), ref[tt])
