@@ -10,3 +10,6 @@ cuobjdump -sass "$SO" | awk '
 echo
 echo "# totals over the library"
 cuobjdump -sass "$SO" | grep -oE "\b(DMMA\.[0-9x]+|UTMALDG\.[0-9A-Z.]+|UBLKCP\.[A-Z.]+|SYNCS\.[A-Z_.0-9]+|UTCMMA[.A-Z0-9]*|LDTM[.A-Z0-9]*)" | sort | uniq -c | sort -nr
+echo
+echo "# TMA / bulk copies that carry an L2 cache-policy descriptor (createpolicy evict_first / evict_last, los_tc.cu)"
+cuobjdump -sass "$SO" | grep -E "UTMALDG|UBLKCP" | awk '{ t++; if ($0 ~ /desc\[/) d++ } END { printf "%d of %d\n", d, t }'
