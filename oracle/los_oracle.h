@@ -12,13 +12,14 @@
  * helpers they call (oracle/Makefile target `ref`, oracle/ref_build/): oracle/_ref/libsong_ref.so runs the reference's
  * own transfer2_init, bessel2_init and bessel2_convolution on the test harness's structures, and
  * tests/test_reference_pin.py finds this oracle's restatement of transfer2.c and bessel2.c BIT-IDENTICAL to them over
- * the options of the path and on BASELINE configs[0] at full size.  That pins oracle_transfer2.c, oracle_bessel2.c and
- * the helpers they use.  Still unpinned by reference execution: the helpers that live in the missing fork themselves
+ * the options of the path and on BASELINE configs[0] at full size.  A third build adds the reference's own
+ * source/bispectra2.c and source/spectra2.c (more stand-ins: oracle/ref_build/fork_stubs/): their
+ * bispectra2_intrinsic_integrate_over_k3 and spectra2_cls are bit-identical to oracle_bispectra2.c / oracle_spectra2.c.
+ * Still unpinned by reference execution: the helpers that live in the missing fork themselves
  * (array_spline_table_columns, drc3jj, lin_space, *_indexl_indexm, bessel_j: restated from the published upstream
  * CLASS / SLATEC algorithms, flagged "UPSTREAM-RECALLED"; bessel_j is a Miller recurrence, not CLASS's approximation --
- * parity is defined on the same j_l(x) inputs), and the loops of oracle_bispectra2.c / oracle_spectra2.c around the
- * pinned bessel2_convolution (bispectra2.c and spectra2.c need far more of the fork).  Those are pinned by analytic
- * known-answer tests only (tests/test_oracle_kat.py).
+ * parity is defined on the same j_l(x) inputs).  Those are pinned by analytic known-answer tests only
+ * (tests/test_oracle_kat.py).
  *
  * Floating-point contract: compile with -ffp-contract=off so every statement is evaluated
  * in the C left-to-right order written in the reference (no FMA contraction).

@@ -1,7 +1,8 @@
 /*
  * oracle_bispectra2.c -- restatement of the k3 integral of SONG's intrinsic bispectrum,
  * bispectra2_intrinsic_integrate_over_k3 (source/bispectra2.c:1107-1439).
- * TEST INFRASTRUCTURE ONLY (see los_oracle.h).  PARITY UNPINNED by reference execution (bispectra2.c needs far more of the absent fork); its inner bessel2_convolution is pinned.
+ * TEST INFRASTRUCTURE ONLY (see los_oracle.h).  PINNED: bit-identical to the reference's own bispectra2_intrinsic_integrate_over_k3 run here (oracle/_ref/libsong_ref_bisp.so,
+ * tests/test_reference_pin.py).
  */
 #include <math.h>
 #include <stdio.h>

@@ -1,6 +1,7 @@
 /*
  * oracle_spectra2.c -- restatement of the (k1,k2,k3) sum of SONG's intrinsic C_l, spectra2_cls
- * (source/spectra2.c:241-570).  TEST INFRASTRUCTURE ONLY (see los_oracle.h).  PARITY UNPINNED by reference execution (spectra2.c needs far more of the absent fork).
+ * (source/spectra2.c:241-570).  TEST INFRASTRUCTURE ONLY (see los_oracle.h).  PINNED: bit-identical to
+ * the reference's own spectra2_cls run here (oracle/_ref/libsong_ref_bisp.so, tests/test_reference_pin.py).
  */
 #include <math.h>
 #include <stdio.h>

@@ -103,6 +103,9 @@ struct precision {
   double k_max_tau0_over_l_max;           /* transfer2.c:2175 (debug message only) */
   double bessel_tol_x_min;                /* bessel2.c:1717 */
   short load_bispectra_from_disk;         /* bessel2.c:90 */
+#ifdef SONG_COMPAT_PRECISION_EXTRA
+  SONG_COMPAT_PRECISION_EXTRA             /* test builds of further reference files (oracle/ref_build/) add the members those read */
+#endif
   ErrorMsg error_message;
 };
 #endif

@@ -81,6 +81,9 @@ def lib(path: str | None = None):
         _dll.harness_l1_info.argtypes = [vp, ip, dp]
         _dll.harness_j_l1_row.argtypes = [vp, C.c_int, dp, C.c_int, ip]
         _dll.harness_destroy.argtypes = [vp]
+        if hasattr(_dll, "ref_integrate_over_k3"):       # oracle/_ref/libsong_ref_bisp.so only (the reference's bispectra2.c)
+            _dll.ref_integrate_over_k3.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, dp, C.c_int, dp, C.c_char_p, C.c_int]
+            _dll.ref_spectra2_cls.argtypes = [vp, dp, C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_char_p, C.c_int]
     return _dll
 
 
@@ -213,6 +216,25 @@ class Harness:
             n = self._lib().harness_j_l1_row(self.h, i, _lib.dptr(buf), int(xx_size), C.byref(ix))
             rows.append(buf[:n].copy()); xmin.append(int(ix.value))
         return rows, np.asarray(xmin, dtype=np.int32)
+
+    def integrate_over_k3(self, index_tt2_k3, index_M3, offset_L3, abs_M3, M3_coefficient, r) -> np.ndarray:
+        """The reference's bispectra2_intrinsic_integrate_over_k3 (libsong_ref_bisp.so): [l_size][r_size][n_pairs]."""
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        out = np.zeros((self.wl.layout.l_size, r.size, self.wl.n_pairs))
+        err = C.create_string_buffer(4096)
+        self._check(self._lib().ref_integrate_over_k3(self.h, int(index_tt2_k3), int(index_M3), int(offset_L3), int(abs_M3),
+                                                      float(M3_coefficient), _lib.dptr(r), int(r.size), _lib.dptr(out), err, 4096), err)
+        return out
+
+    def spectra2_cls(self, primordial, has_tt2=True, has_ee2=True, has_te2=True, rescale_cmb_sources=True) -> np.ndarray:
+        """The reference's spectra2_cls (libsong_ref_bisp.so): [requested C_l types in the order tt2, ee2, te2][l_size]."""
+        prim = np.ascontiguousarray(primordial, dtype=np.float64)
+        n_ct = int(has_tt2) + int(has_ee2) + int(has_te2)
+        out = np.zeros((n_ct, self.wl.layout.l_size))
+        err = C.create_string_buffer(4096)
+        self._check(self._lib().ref_spectra2_cls(self.h, _lib.dptr(prim), int(has_tt2), int(has_ee2), int(has_te2),
+                                                 int(rescale_cmb_sources), _lib.dptr(out), err, 4096), err)
+        return out
 
     def bessel2_convolution(self, kk, delta_kk, f, g, index_l1, r) -> float:
         kk = np.ascontiguousarray(kk, dtype=np.float64); delta_kk = np.ascontiguousarray(delta_kk, dtype=np.float64)

@@ -12,7 +12,9 @@ What is compared, bit for bit (np.array_equal):
     time interpolation, Bessel interpolation, long k3 grids) and on BASELINE configs[0] at full size;
   * struct bessels2 after the reference's bessel2_init  ==  the oracle's tables, when both start from the same j_l(x) and
     3j numbers (libsong_ref_op.so: the two providers of the absent fork answered by the oracle's);
-  * bessel2_convolution.
+  * bessel2_convolution; the product's host half of bessel2 against the reference's pbs2->j_l1; the disk format;
+  * bispectra2_intrinsic_integrate_over_k3 and spectra2_cls of the reference's own bispectra2.c / spectra2.c
+    (libsong_ref_bisp.so, further stand-ins under oracle/ref_build/fork_stubs/)  ==  oracle_bispectra2.c / oracle_spectra2.c.
 The GPU path is bit-identical to the oracle in EXACT mode (tests -m gpu), hence to the reference's code.
 
 The library does not exist on the GPU box unless it travelled with the snapshot; tests skip when it is missing.
@@ -241,3 +243,68 @@ def test_reference_disk_format_is_what_the_dropin_writes(oracle, tmp_path):
         f = tmp_path / f"transfers_{tt:03d}.dat"
         assert f.exists() and f.stat().st_size == 8 * wl.n_units
         assert np.array_equal(np.fromfile(f), ref[tt])
+
+
+REF_BISP = REF.replace("libsong_ref.so", "libsong_ref_bisp.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BISP), reason="oracle/_ref/libsong_ref_bisp.so not built")
+@pytest.mark.parametrize("abs_M3,offset_L3", [(0, 0), (1, 0), (1, 2)])
+def test_reference_integrate_over_k3_equals_oracle(oracle, abs_M3, offset_L3):
+    """bispectra2_intrinsic_integrate_over_k3 (bispectra2.c:1107-1439) of the reference -- its own bispectra2.c, compiled
+    where it lies -- on ptr2->transfer and pbs2->j_l1 as the reference's transfer2_init and bessel2_init left them, against
+    the oracle's restatement (oracle_bispectra2.c; the loop song_los_integrate_k3 reproduces on the GPU) on the same
+    numbers: the trapezoidal k3 measure of :1279-1284, bessel2_convolution, the M3 coefficient and the factor 2."""
+    kw = dict(sources_k3_interpolation="cubic") if abs_M3 == 0 else dict(modes_song=[0, 1, 2], sources_k3_interpolation="cubic", has_source_B=True)
+    wl = workload.fill_sources(workload.build_grids(configs.tiny(**kw)))
+    lay = wl.layout
+    index_M3 = int(np.nonzero(lay.m == abs_M3)[0][0])
+    r = np.linspace(0.55, 0.9, 7) * wl.xx_max / float(wl.k3_tr.max())        # k3 r stays inside the j_l1 table
+    coef = 0.7
+    with dropin_lib.Harness(wl, None, lib_path=REF_BISP) as h:
+        h.transfer2_init()
+        T, count, _ = h.read()
+        l1, x_min_l1 = h.l1_info()
+        rows, _ = h.j_l1_rows(wl.xx.size)
+        got = h.integrate_over_k3(lay.index_tt2_T, index_M3, offset_L3, abs_M3, coef, r)
+        h.transfer2_free()
+    assert count == wl.n_integrals
+    checked = 0
+    for il in range(lay.l_size):
+        l3 = int(lay.l[il])
+        L3 = abs(l3 - abs_M3) + offset_L3
+        if abs_M3 > l3 or L3 > l3 + abs_M3:
+            assert not got[il].any()                   # skipped configurations stay zero (:1181-1190)
+            continue
+        index_L3 = int(np.nonzero(l1 == L3)[0][0])
+        tt = lay.index_tt2_T + int(lay.lm_array[il, index_M3])
+        ref = oracle.integral_over_k3(wl, T[tt], rows[index_L3], None, float(x_min_l1[index_L3]), r, abs_M3=abs_M3, M3_coefficient=coef)
+        assert np.array_equal(got[il], ref), (il, float(np.abs(got[il] - ref).max()))
+        assert np.abs(ref).max() > 0
+        checked += 1
+    assert checked >= 2
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BISP), reason="oracle/_ref/libsong_ref_bisp.so not built")
+@pytest.mark.parametrize("rescale", [True, False])
+def test_reference_spectra2_cls_equals_oracle(oracle, rescale):
+    """spectra2_cls (spectra2.c:241-570) of the reference -- its own spectra2.c, compiled where it lies -- on ptr2->transfer
+    as the reference's transfer2_init left it, against the oracle's restatement (oracle_spectra2.c; the sum song_los_cl_sum
+    reproduces on the GPU): tt2, ee2 and te2 for every l, m = 0, with the k1/k2/k3 trapezoidal steps, the triangular
+    clipping of the k3 step and the primordial spectra of :371-515."""
+    wl = workload.fill_sources(workload.build_grids(configs.tiny(sources_k3_interpolation="cubic")))
+    lay = wl.layout
+    prim = 2.1e-9 * (wl.k / 0.05) ** (0.96 - 1.0)
+    proj = oracle.build_projection(wl)
+    with dropin_lib.Harness(wl, proj, lib_path=REF_BISP) as h:
+        h.transfer2_init()
+        T, count, _ = h.read()
+        got = h.spectra2_cls(prim, rescale_cmb_sources=rescale)
+        h.transfer2_free()
+    assert count == wl.n_integrals and got.shape == (3, lay.l_size)
+    for il in range(lay.l_size):
+        tT = lay.index_tt2_T + int(lay.lm_array[il, 0]); tE = lay.index_tt2_E + int(lay.lm_array[il, 0])
+        for ct, (a, b) in enumerate(((tT, tT), (tE, tE), (tT, tE))):
+            ref = oracle.spectra2_cl(wl, T[a], T[b], 0, prim, rescale_cmb_sources=rescale)
+            assert got[ct, il] == ref, (ct, il, got[ct, il], ref)
+    assert np.abs(got).max() > 0
