@@ -104,7 +104,7 @@ struct precision {
   double bessel_tol_x_min;                /* bessel2.c:1717 */
   short load_bispectra_from_disk;         /* bessel2.c:90 */
 #ifdef SONG_COMPAT_PRECISION_EXTRA
-  SONG_COMPAT_PRECISION_EXTRA             /* test builds of further reference files (oracle/ref_build/) add the members those read */
+  SONG_COMPAT_PRECISION_EXTRA             /* test builds that compile further files of the reference add the members those read */
 #endif
   ErrorMsg error_message;
 };
