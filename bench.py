@@ -286,8 +286,8 @@ def run_reference(args, rank: int, world: int):
                                 "the GPU arm; projection tables from the oracle's bessel2 restatement; the GPU is idle"),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": lib_run["cores"], "cpu_model": cpu_model(), "kind": "reference", "sample": sample,
                              "probe_bitwise_equal_to_oracle": lib_run["probe_bitwise_equal_to_oracle"],
-                             "build": "gcc -O2 -std=gnu99 -fopenmp -ffp-contract=off on /root/reference/source/transfer2.c (oracle/Makefile, target ref); "
-                                      "no -DDEBUG (the reference Makefile's default adds debug-only checks)"},
+                             "build": "gcc -O3 -g -DDEBUG -std=c99 -w (the reference Makefile's own defaults) -fopenmp (its optional parallel flags) "
+                                      "-ffp-contract=off on /root/reference/source/transfer2.c, oracle/Makefile target ref"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
