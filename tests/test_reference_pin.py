@@ -308,3 +308,23 @@ def test_reference_spectra2_cls_equals_oracle(oracle, rescale):
             ref = oracle.spectra2_cl(wl, T[a], T[b], 0, prim, rescale_cmb_sources=rescale)
             assert got[ct, il] == ref, (ct, il, got[ct, il], ref)
     assert np.abs(got).max() > 0
+
+
+@needs_ref
+@pytest.mark.parametrize("name,n_k", [("sn_t_10percent_lmax2000", 6), ("sn_pol_10percent_lmax2000", 6),
+                                      ("sn_pol_5percent_lmax3000", 3), ("sn_pol_5percent_lmax4000", 3)])
+def test_reference_equals_oracle_on_baseline_triangles(oracle, name, n_k):
+    """BASELINE.json configs[1]-[4] at their own parameters (l lists up to 4000, x grids of 17-53 thousand points, L up to
+    17, 60-240 time samples): the reference's transfer2_init on the whole (k1,k2) triangle of n_k of the run's k values
+    (the sample bench.py's CPU arm times) against the oracle, bit for bit."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    wl, k_size = bench.reference_triangle(name, n_k)
+    assert wl.n_pairs == n_k * (n_k + 1) // 2 and wl.k.size == n_k < k_size
+    workload.fill_sources(wl)
+    proj = oracle.build_projection(wl)
+    ref, _ = oracle.OracleRun(wl, proj).run()
+    got, count, labels_ok = reference_transfer2(wl, proj)
+    assert count == wl.n_integrals and labels_ok
+    assert np.array_equal(got, ref), f"max abs diff {np.abs(got - ref).max()}"
