@@ -80,6 +80,7 @@ def lib(path: str | None = None):
         _dll.harness_bessel2_convolution.argtypes = [vp, dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, dp]
         _dll.harness_l1_info.argtypes = [vp, ip, dp]
         _dll.harness_j_l1_row.argtypes = [vp, C.c_int, dp, C.c_int, ip]
+        _dll.harness_k3_list.argtypes = [vp, C.c_int, C.c_int, dp, C.c_int]
         _dll.harness_destroy.argtypes = [vp]
         if hasattr(_dll, "ref_integrate_over_k3"):       # oracle/_ref/libsong_ref_bisp.so only (the reference's bispectra2.c)
             _dll.ref_integrate_over_k3.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, dp, C.c_int, dp, C.c_char_p, C.c_int]
@@ -205,6 +206,16 @@ class Harness:
         l1 = np.zeros(int(sizes[3]), dtype=np.int32); xmin = np.zeros(int(sizes[3]))
         self._lib().harness_l1_info(self.h, _lib.iptr(l1), _lib.dptr(xmin))
         return l1, xmin
+
+    def k3_lists(self) -> np.ndarray:
+        """transfer2_get_k3_list of the module for every pair, packed in the reference loop order (after transfer2_init)."""
+        out = np.zeros(self.wl.n_units)
+        for ip in range(self.wl.n_pairs):
+            a, n = int(self.wl.tr_off[ip]), int(self.wl.k3_tr_size[ip])
+            got = self._lib().harness_k3_list(self.h, int(self.wl.pairs[ip, 0]), int(self.wl.pairs[ip, 1]), _lib.dptr(out[a:a + n]), n)
+            if got != n:
+                raise _lib.SongLosError(f"pair {ip}: transfer2_get_k3_list gives {got} values, the workload has {n}")
+        return out
 
     def j_l1_rows(self, xx_size: int):
         """pbs2->j_l1 as bessel2_init left it: (rows, index_xmin_l1)."""

@@ -348,6 +348,17 @@ int harness_j_l1_row(harness *h, int index_l1, double *out, int n_max, int *inde
   for (int i = 0; i < n && i < n_max; ++i) out[i] = h->bs2.j_l1[index_l1][i];
   return n;
 }
+/* transfer2_get_k3_list of the module under test for pair (index_k1, index_k2) (what bispectra2.c:1255 and spectra2.c:451
+   call): returns ptr2->k_size_k1k2 and fills out[0 .. size); needs transfer2_init (or transfer2_indices_of_transfers) first */
+int harness_k3_list(harness *h, int index_k1, int index_k2, double *out, int n_max)
+{
+  if (!h->transfer2_done) return -1;
+  const int n = h->tr2.k_size_k1k2[index_k1][index_k2];
+  if (n > n_max) return -n;
+  int dump = 0;
+  if (transfer2_get_k3_list(&h->pr, &h->pr2, &h->pt2, &h->bs, &h->bs2, &h->tr2, index_k1, index_k2, out, &dump) == _FAILURE_) return -1;
+  return n;
+}
 int harness_l1_info(harness *h, int *l1, double *x_min_l1) { for (int i = 0; i < h->bs2.l1_size; ++i) { l1[i] = h->bs2.l1[i]; x_min_l1[i] = h->bs2.x_min_l1[i]; } return h->bs2.l1_size; }
 
 void harness_destroy(harness *h)

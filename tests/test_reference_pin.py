@@ -328,3 +328,22 @@ def test_reference_equals_oracle_on_baseline_triangles(oracle, name, n_k):
     got, count, labels_ok = reference_transfer2(wl, proj)
     assert count == wl.n_integrals and labels_ok
     assert np.array_equal(got, ref), f"max abs diff {np.abs(got - ref).max()}"
+
+
+@needs_ref
+@pytest.mark.parametrize("kw", [dict(), dict(bispectra_k3_extrapolation="no_extrapolation"),
+                                dict(extra_k3_oscillations_left=0.5, extra_k3_oscillations_right=12), dict(q_linstep_song=0.13)],
+                         ids=["default", "no extrapolation", "asymmetric wings", "finer q step"])
+def test_reference_k3_grids_equal_the_products(oracle, kw):
+    """transfer2_get_k3_list of the reference (transfer2.c:1566-1737), pair by pair, against the fine k3 grids the product's
+    host code builds (song_b200/host/los_host.c, what the GPU integrates on) and against the oracle's: bit for bit, and the
+    physical ranges of transfer2_get_k3_size (:1329-1550) through the wing handling of the transfer functions."""
+    wl = workload.fill_sources(workload.build_grids(configs.tiny(**kw)))
+    proj = oracle.build_projection(wl)
+    with dropin_lib.Harness(wl, proj, lib_path=REF) as h:
+        h.transfer2_init()
+        grids = h.k3_lists()
+        h.transfer2_free()
+    assert np.array_equal(grids, wl.k3_tr)
+    _, ogrids = oracle.OracleRun(wl, proj).k3_grids()
+    assert np.array_equal(grids, ogrids)
