@@ -81,6 +81,8 @@ def lib(path: str | None = None):
         _dll.harness_l1_info.argtypes = [vp, ip, dp]
         _dll.harness_j_l1_row.argtypes = [vp, C.c_int, dp, C.c_int, ip]
         _dll.harness_k3_list.argtypes = [vp, C.c_int, C.c_int, dp, C.c_int]
+        _dll.harness_indices_digest.argtypes = [vp, C.c_char_p, C.c_longlong]
+        _dll.harness_indices_digest.restype = C.c_longlong
         _dll.harness_destroy.argtypes = [vp]
         if hasattr(_dll, "ref_integrate_over_k3"):       # oracle/_ref/libsong_ref_bisp.so only (the reference's bispectra2.c)
             _dll.ref_integrate_over_k3.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, dp, C.c_int, dp, C.c_char_p, C.c_int]
@@ -88,7 +90,7 @@ def lib(path: str | None = None):
     return _dll
 
 
-def _input(wl, proj, store_dir=None, verbose=0, use_bessel2_init=False, keep_sources=False):
+def _input(wl, proj, store_dir=None, verbose=0, use_bessel2_init=False, keep_sources=False, load_dir=None):
     """harness_input for workload `wl`; returns (struct, objects that must stay alive)."""
     lay, p = wl.layout, wl.params
     assert wl.pairs.shape[0] == wl.k.size * (wl.k.size + 1) // 2, "the harness needs every (k1,k2) pair"
@@ -113,7 +115,8 @@ def _input(wl, proj, store_dir=None, verbose=0, use_bessel2_init=False, keep_sou
     else:
         assert use_bessel2_init, "without projection tables the harness must call bessel2_init"
     keep["rows"], keep["ddrows"] = rows, ddrows
-    keep["dir"] = store_dir.encode() if store_dir else None
+    assert not (store_dir and load_dir)
+    keep["dir"] = store_dir.encode() if store_dir else (load_dir.encode() if load_dir else None)
     inp = HarnessInput(
         tau0=wl.cosmo["tau0"], tau_rec=wl.cosmo["tau_rec"], rs_rec=wl.cosmo["rs_rec"],
         k_size=int(wl.k.size), k=_lib.dptr(keep["k"]), tau_size=int(wl.tau.size), tau_sampling=_lib.dptr(keep["tau"]),
@@ -129,7 +132,7 @@ def _input(wl, proj, store_dir=None, verbose=0, use_bessel2_init=False, keep_sou
         J_rows=rows, ddJ_rows=ddrows, index_xmin_J=xmin_p, x_size_J=xsize_p,
         k3_pt_size=_lib.iptr(wl.k3_pt_size), pt_off=keep["pt_off"].ctypes.data_as(lp), k3_pt=_lib.dptr(wl.k3_pt),
         src_off=keep["src_off"].ctypes.data_as(lp), src=_lib.dptr(wl.src),
-        store_to_disk=int(store_dir is not None), load_from_disk=0,
+        store_to_disk=int(store_dir is not None), load_from_disk=int(load_dir is not None),
         transfers_dir=keep["dir"], verbose=verbose,
         tau_sampling_mode={"sources": 0, "custom": 1, "smart": 1, "bessel": 2}[p["transfer2_tau_sampling"]],
         cubic_time=int(p["sources_time_interpolation"] == "cubic"), tau_linstep_song=float(p.get("tau_linstep_song", 0.0)),
@@ -147,10 +150,11 @@ class Harness:
     h.transfer2_free(); h.fill_sources(); h.transfer2_init()   # next step
     """
 
-    def __init__(self, wl, proj=None, store_dir=None, verbose=0, keep_sources=False, lib_path=None):
+    def __init__(self, wl, proj=None, store_dir=None, verbose=0, keep_sources=False, lib_path=None, load_dir=None):
         self.wl = wl
         self.lib_path = lib_path
-        self.inp, self._keep = _input(wl, proj, store_dir, verbose, use_bessel2_init=proj is None, keep_sources=keep_sources)
+        self.inp, self._keep = _input(wl, proj, store_dir, verbose, use_bessel2_init=proj is None, keep_sources=keep_sources,
+                                      load_dir=load_dir)
         err = C.create_string_buffer(4096)
         self.h = self._lib().harness_create(C.byref(self.inp), err, 4096)
         if not self.h:
@@ -206,6 +210,14 @@ class Harness:
         l1 = np.zeros(int(sizes[3]), dtype=np.int32); xmin = np.zeros(int(sizes[3]))
         self._lib().harness_l1_info(self.h, _lib.iptr(l1), _lib.dptr(xmin))
         return l1, xmin
+
+    def indices_digest(self) -> str:
+        """Index tables, labels, grid sizes and physical ranges of struct transfers2 as text (harness_indices_digest)."""
+        cap = 64 * 1024 * 1024
+        buf = C.create_string_buffer(cap)
+        n = self._lib().harness_indices_digest(self.h, buf, cap)
+        assert 0 < n < cap
+        return buf.value.decode()
 
     def k3_lists(self) -> np.ndarray:
         """transfer2_get_k3_list of the module for every pair, packed in the reference loop order (after transfer2_init)."""

@@ -348,6 +348,35 @@ int harness_j_l1_row(harness *h, int index_l1, double *out, int n_max, int *inde
   for (int i = 0; i < n && i < n_max; ++i) out[i] = h->bs2.j_l1[index_l1][i];
   return n;
 }
+/* Every member of struct transfers2 that transfer2_indices_of_transfers (transfer2.c:866-1285) and transfer2_get_k3_sizes
+   (:1752-1834) leave behind, as text: called on the structures right after transfer2_init (with load_transfers_from_disk
+   the module returns after exactly those two steps, :151-157, and needs no GPU).  Two modules that agree on this digest
+   agree on the index tables, the labels, the grid sizes and the physical ranges. */
+long long harness_indices_digest(harness *h, char *out, long long cap)
+{
+  struct transfers2 *t = &h->tr2; const harness_input *in = &h->in;
+  long long n = 0;
+#define DIG(...) do { if (n < cap) n += snprintf(out + n, (size_t)(cap - n), __VA_ARGS__); } while (0)
+  DIG("tt2_size=%d n_transfers=%d T=%d E=%d B=%d nzE=%d nzB=%d l_size=%d m_size=%d k3_size_max=%d has_cls=%d\n", t->tt2_size, t->n_transfers,
+      in->has_T ? t->index_tt2_T : -1, in->has_E ? t->index_tt2_E : -1, in->has_B ? t->index_tt2_B : -1,
+      in->has_E ? t->n_nonzero_transfers_E : -1, in->has_B ? t->n_nonzero_transfers_B : -1, t->l_size, t->m_size, t->k3_size_max, (int)t->has_cls);
+  DIG("tau0=%.17g tau_rec=%.17g rs_rec=%.17g\n", t->tau0, t->tau_rec, t->rs_rec);
+  for (int i = 0; i < t->l_size; ++i) DIG("l%d ", t->l[i]);
+  for (int i = 0; i < t->m_size; ++i) DIG("m%d ", t->m[i]);
+  DIG("\n");
+  for (int il = 0; il < t->l_size; ++il) for (int im = 0; im < t->m_size; ++im) if (t->m[im] <= t->l[il]) DIG("%d ", t->lm_array[il][im]);
+  DIG("\n");
+  for (int tt = 0; tt < t->tt2_size; ++tt)
+    DIG("%s:%d:%d:%d:%d ", t->tt2_labels[tt], t->corresponding_index_l[tt], t->corresponding_index_m[tt], t->index_tt2_monopole[tt], t->index_pt2_monopole[tt]);
+  DIG("\n");
+  for (int k1 = 0; k1 < in->k_size; ++k1) for (int k2 = 0; k2 <= k1; ++k2)
+    DIG("%d,%d,%d,%.17g,%.17g ", t->k_size_k1k2[k1][k2], t->k_physical_start_k1k2[k1][k2], t->k_physical_size_k1k2[k1][k2],
+        t->k_min_k1k2[k1][k2], t->k_max_k1k2[k1][k2]);
+  DIG("\n");
+#undef DIG
+  return n;
+}
+
 /* transfer2_get_k3_list of the module under test for pair (index_k1, index_k2) (what bispectra2.c:1255 and spectra2.c:451
    call): returns ptr2->k_size_k1k2 and fills out[0 .. size); needs transfer2_init (or transfer2_indices_of_transfers) first */
 int harness_k3_list(harness *h, int index_k1, int index_k2, double *out, int n_max)

@@ -347,3 +347,31 @@ def test_reference_k3_grids_equal_the_products(oracle, kw):
     assert np.array_equal(grids, wl.k3_tr)
     _, ogrids = oracle.OracleRun(wl, proj).k3_grids()
     assert np.array_equal(grids, ogrids)
+
+
+@needs_ref
+@pytest.mark.parametrize("kw", [dict(), dict(output=["tBisp"]), dict(modes_song=[0, 1, 2], has_source_B=True),
+                                dict(bispectra_k3_extrapolation="no_extrapolation")], ids=["T+E", "T", "m012+B", "no extrapolation"])
+def test_dropin_host_module_against_reference_without_a_gpu(oracle, kw, tmp_path):
+    """The host side of the drop-in (song_b200/host/transfer2_gpu.c) against the reference's transfer2.c where no GPU is
+    involved: with load_transfers_from_disk the module runs transfer2_indices_of_transfers and transfer2_get_k3_sizes and
+    returns (transfer2.c:151-157).  (1) Both modules leave the same index tables, labels, counters, grid sizes and physical
+    ranges in struct transfers2; (2) the drop-in's transfer2_load_transfers_from_disk / transfer2_free_type_level read the
+    transfers_%03d.dat files THE REFERENCE wrote and return its values bit for bit (the path bispectra2.c:1213 takes)."""
+    if not os.path.exists(dropin_lib.PATH):
+        pytest.skip("libsong_transfer2.so not built")
+    wl = workload.fill_sources(workload.build_grids(configs.tiny(**kw)))
+    proj = oracle.build_projection(wl)
+    with dropin_lib.Harness(wl, proj, store_dir=str(tmp_path), lib_path=REF) as h:       # the reference computes and stores
+        h.transfer2_init()
+        ref_vals, count, _ = h.read()
+        ref_digest = h.indices_digest()
+        h.transfer2_free()
+    assert count == wl.n_integrals
+    with dropin_lib.Harness(wl, proj, load_dir=str(tmp_path)) as h:                       # the drop-in: indices + load, no GPU
+        h.transfer2_init()
+        digest = h.indices_digest()
+        got, _, labels_ok = h.read()
+        h.transfer2_free()
+    assert digest == ref_digest
+    assert labels_ok and np.array_equal(got, ref_vals)
