@@ -197,6 +197,11 @@ static double los_class_bessel_j(int l, double x, void *user)
   bessel_j((struct bessels *)user, l, x, &j);
   return j;
 }
+/* the fork's drc3jj (tools/slatec_3j_C.c) behind the 3j provider signature */
+static int los_class_drc3jj(double l2, double l3, double m2, double m3, double *l1min, double *l1max, double *thrcof, int ndim, void *user)
+{
+  return drc3jj(l2, l3, m2, m3, l1min, l1max, thrcof, ndim, ((struct bessels2 *)user)->error_message) == _FAILURE_;
+}
 #endif
 
 int bessel2_init(struct precision *ppr, struct precision2 *ppr2, struct perturbs2 *ppt2, struct bessels *pbs, struct bessels2 *pbs2)
@@ -244,6 +249,7 @@ int bessel2_init(struct precision *ppr, struct precision2 *ppr2, struct perturbs
   /* a SONG tree: CLASS's own bessel_j, called point by point as bessel2_j_for_l1 does (bessel2.c:1706,1724,1804), so that
      pbs2->j_l1 -- and everything assembled from it -- holds the reference's numbers (bessel2_host.h) */
   song_host_bessel2_set_provider(los_class_bessel_j, pbs);
+  song_host_bessel2_set_3j_provider(los_class_drc3jj, pbs2);
 #endif
   song_bessel2_host *hb = NULL;
   class_test(song_host_bessel2_prepare(pbs->l, pbs->l_size, pbs2->m, pbs2->m_size, pbs2->L_max, pbs2->xx, pbs2->xx_size, pbs2->xx_max,

@@ -14,6 +14,13 @@ static song_host_bessel_fn g_bessel_fn = NULL;
 static void *g_bessel_user = NULL;
 void song_host_bessel2_set_provider(song_host_bessel_fn fn, void *user) { g_bessel_fn = fn; g_bessel_user = user; }
 static double jl_point(int l, double x) { return g_bessel_fn ? g_bessel_fn(l, x, g_bessel_user) : compat_bessel_j(l, x); }
+static song_host_3j_fn g_3j_fn = NULL;
+static void *g_3j_user = NULL;
+void song_host_bessel2_set_3j_provider(song_host_3j_fn fn, void *user) { g_3j_fn = fn; g_3j_user = user; }
+static int threej(double l2, double l3, double m2, double m3, double *lo, double *hi, double *f, int ndim)
+{
+  return g_3j_fn ? g_3j_fn(l2, l3, m2, m3, lo, hi, f, ndim, g_3j_user) : compat_drc3jj(l2, l3, m2, m3, lo, hi, f, ndim);
+}
 
 static int b2_fail(char *errmsg, int errlen, const char *text)
 {
@@ -151,11 +158,11 @@ int song_host_bessel2_prepare(const int *l, int l_size, const int *m, int m_size
           if (S > lv || S > L || (pf == SONG_LOS_J_EB && mv == 0)) continue;   /* :1090-1100 -> l1_count 0 */
           double lo, hi;
           double *f1 = t->first_3j + q * t->ndim, *f2 = t->second_3j + q * t->ndim;
-          if (compat_drc3jj(L, lv, S, -S, &lo, &hi, f1, t->ndim)) { bad = 1; continue; }      /* :1131 */
+          if (threej(L, lv, S, -S, &lo, &hi, f1, t->ndim)) { bad = 1; continue; }      /* :1131 */
           int l1min = (int)(lo + 1e-6), l1max = (int)(hi + 1e-6);
           int cnt = l1max - l1min + 1;
           if ((S != 0) || (mv != 0)) {
-            if (compat_drc3jj(L, lv, -mv, mv, &lo, &hi, f2, t->ndim)) { bad = 1; continue; }  /* :1154 */
+            if (threej(L, lv, -mv, mv, &lo, &hi, f2, t->ndim)) { bad = 1; continue; }  /* :1154 */
           } else {
             memcpy(f2, f1, (size_t)cnt * sizeof(double));                                    /* :1165 */
           }

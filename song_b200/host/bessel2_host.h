@@ -37,6 +37,10 @@ void song_host_bessel2_free(song_bessel2_host *t);
    default provider (tests/test_reference_pin.py compares it with the reference's own table). */
 typedef double (*song_host_bessel_fn)(int l, double x, void *user);
 void song_host_bessel2_set_provider(song_host_bessel_fn fn, void *user);
+/* Likewise the Wigner 3j provider (bessel2.c:1131,1154): NULL = the recursion of class_compat.c; a SONG tree registers
+   the fork's drc3jj (tools/slatec_3j_C.c).  Returns 0 on success; thrcof has ndim entries. */
+typedef int (*song_host_3j_fn)(double l2, double l3, double m2, double m3, double *l1min, double *l1max, double *thrcof, int ndim, void *user);
+void song_host_bessel2_set_3j_provider(song_host_3j_fn fn, void *user);
 /* hands the tables to the engine: J_Llm(x) is assembled on the device */
 int song_host_bessel2_upload(song_los_ctx *ctx, const song_bessel2_host *t, const int *J_types,
                              double J_Llm_cut, double xx_max, char *errmsg, int errlen);
