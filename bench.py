@@ -406,15 +406,6 @@ def set_omp_threads(n: int):
         pass
 
 
-def unit_cost(grids, own, first, last) -> float:
-    """Cost of the fine-grid slices [first, last) of pairs `own` in the model of the static schedule (los_host.c)."""
-    c = 0.0
-    for ip, a, b in zip(own, first, last):
-        k = grids.k3_tr[int(grids.tr_off[ip]) + int(a):int(grids.tr_off[ip]) + int(b)]
-        c += float(np.sum(0.5 + 0.5 * np.minimum(1.0, k * grids.cosmo["tau0"] / grids.layout.l.max())))
-    return c
-
-
 def oracle_view_of_slices(sub, idx):
     """A workload the oracle can run as it is for pairs `idx` of a sliced workload (k3 bands), and per pair the columns of
     its result that belong to the slice.  The oracle, like the reference, takes the fine k3 grid of a pair as given and
@@ -480,7 +471,7 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
     n_groups, n_bands, group_of_pair, band_cut = sched
     chunks = (args.chunks_per_rank or shard.chunks_per_device(grids, n_groups)) if n_groups > 1 else 1
     owned, own_first, own_last = shard.shard_units_index(grids, rank, world, sched)
-    load = np.array([unit_cost(grids, *shard.shard_units_index(grids, r, world, sched)) for r in range(world)])
+    load = np.array([shard.predicted_ms(grids, *shard.shard_units_index(grids, r, world, sched)) for r in range(world)])   # model of los_host.c
     want_e2e = e2e_steps > 0 and full_pairs and os.path.exists(dropin_lib.PATH)
     if rank == 0 and want_e2e:
         workload.fill_sources(grids)                 # rank 0 also needs the whole run for transfer2_init

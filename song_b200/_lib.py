@@ -160,7 +160,7 @@ LOS_SYMBOLS = [
 HOST_SYMBOLS = ["song_host_k3_size", "song_host_k3_list", "song_host_k3_sizes", "song_host_k3_lists",
                 "song_host_bessel2_prepare", "song_host_bessel2_free", "song_host_bessel2_upload",
                 "song_host_lpt_schedule", "song_host_schedule_pairs", "song_host_pair_costs",
-                "song_host_band_edges", "song_host_band_cuts", "song_host_band_count"]
+                "song_host_band_edges", "song_host_band_cuts", "song_host_band_count", "song_host_pair_costs_model"]
 
 _los = None
 _host = None
@@ -242,7 +242,10 @@ def host():
         lib.song_host_lpt_schedule.argtypes = [c_int64_p, C.c_int, C.c_int, c_int_p, c_int64_p]
         lib.song_host_schedule_pairs.argtypes = [c_int64_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int64_p]
         lib.song_host_pair_costs.argtypes = [C.c_int, c_int_p, c_double_p, c_double_p, C.c_double, C.c_int, c_int64_p]
-        lib.song_host_band_edges.argtypes = [C.c_int, c_int_p, c_int64_p, c_double_p, C.c_void_p, C.c_double, C.c_int, C.c_int, c_double_p]
+        lib.song_host_band_edges.argtypes = [C.c_int, c_int_p, c_int64_p, c_double_p, c_int_p, C.c_void_p, C.c_double, C.c_int, C.c_double,
+                                             C.c_int, c_double_p]
+        lib.song_host_pair_costs_model.argtypes = [C.c_int, c_int_p, c_int64_p, c_double_p, c_int_p, C.c_double, C.c_int, C.c_double, C.c_int,
+                                                   c_int64_p]
         lib.song_host_band_cuts.argtypes = [C.c_int, c_int_p, c_int64_p, c_double_p, C.c_int, c_double_p, c_int_p]
         lib.song_host_band_count.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int]
         lib.compat_drc3jj.argtypes = [C.c_double] * 4 + [c_double_p, c_double_p, c_double_p, C.c_int]

@@ -262,22 +262,84 @@ int song_host_pair_costs(int n_pairs, const int *k3_tr_size, const double *k_min
 }
 
 /* ---- k3 bands (los_host.h) ---- */
-static double band_unit_cost(double k3, double tau0, int l_max)
+/* Cost model of the FAST path, microseconds, fitted to the per-GPU kernel times of configs[3] on 8 GPUs (2 pair groups x
+   4 bands) and cross-checked against the one-, two- and eight-GPU runs by pairs (all within 3 %):
+     a k3 value costs   c_interp + (c0 + c1 a) (1 + rho0 / rho)
+       a   = min(1, k3 tau0 / l_max), the share of multipole columns not skipped at x << l,
+       rho = k3 values of the GPU per row of the projection table around this k3 (the DMMA kernel's tile holds the rows of
+             192 consecutive values: the fewer values share a row, the more rows a tile fetches and the more of its 8-value
+             groups straddle two rows),
+     a coarse k3 point of a pair the GPU touches costs c_point (its spline, and its row staged by the interpolation kernel). */
+static const double MODEL_C_INTERP = 0.0167, MODEL_C0 = 0.070, MODEL_C1 = 0.098, MODEL_RHO0 = 31.0, MODEL_C_POINT = 0.245;
+enum { MODEL_DENSITY_ROWS = 50 };          /* the density is estimated over windows of this many table rows */
+
+static double model_active(double k3, double tau0, int l_max)
 {
-  double active = (l_max > 0) ? k3 * tau0 / (double)l_max : 1.0;
-  if (active > 1.0) active = 1.0;
-  if (active < 0.0) active = 0.0;
-  /* measured on configs[3] cut into two bands: the low band's values cost 0.71 of the high band's, where the weights of
-     the pair model (0.65 + 0.35 active) had predicted 0.80 -- a whole band of low k3 skips more columns than the middle
-     of a pair's range suggests */
-  return 0.5 + 0.5 * active;
+  double a = (l_max > 0) ? k3 * tau0 / (double)l_max : 1.0;
+  return a > 1.0 ? 1.0 : (a < 0.0 ? 0.0 : a);
 }
 
-int song_host_band_edges(int n_pairs, const int *k3_tr_size, const int64_t *tr_off, const double *k3_tr, const unsigned char *pair_in_group,
-                         double tau0, int l_max, int n_bands, double *edges)
+/* density table of the selected pairs: values per table row in windows of MODEL_DENSITY_ROWS rows; row of a value =
+   k3 * rows_per_k.  Returns the table (caller frees) and its length. */
+static double *model_density(int n_pairs, const int *k3_tr_size, const int64_t *tr_off, const double *k3_tr,
+                             const unsigned char *pair_in_group, double rows_per_k, int64_t *n_win_out)
 {
-  if (!k3_tr_size || !tr_off || !k3_tr || n_pairs < 0 || n_bands < 1 || (n_bands > 1 && !edges)) return 1;
+  double kmax = 0.;
+  for (int p = 0; p < n_pairs; ++p)
+    if ((!pair_in_group || pair_in_group[p]) && k3_tr_size[p] > 0 && k3_tr[tr_off[p] + k3_tr_size[p] - 1] > kmax)
+      kmax = k3_tr[tr_off[p] + k3_tr_size[p] - 1];
+  const int64_t n_win = (int64_t)(kmax * rows_per_k / MODEL_DENSITY_ROWS) + 2;
+  double *rho = (double *)calloc((size_t)n_win, sizeof(double));
+  if (!rho) return NULL;
+  for (int p = 0; p < n_pairs; ++p) {
+    if (pair_in_group && !pair_in_group[p]) continue;
+    const double *k = k3_tr + tr_off[p];
+    for (int i = 0; i < k3_tr_size[p]; ++i) {
+      int64_t w = (int64_t)(k[i] * rows_per_k / MODEL_DENSITY_ROWS);
+      if (w < 0) w = 0;
+      if (w >= n_win) w = n_win - 1;
+      rho[w] += 1.0 / MODEL_DENSITY_ROWS;
+    }
+  }
+  *n_win_out = n_win;
+  return rho;
+}
+
+static double model_unit_cost(double k3, double tau0, int l_max, const double *rho, int64_t n_win, double rows_per_k, double share)
+{
+  int64_t w = (int64_t)(k3 * rows_per_k / MODEL_DENSITY_ROWS);
+  if (w < 0) w = 0;
+  if (w >= n_win) w = n_win - 1;
+  const double r = rho[w] * share;
+  return MODEL_C_INTERP + (MODEL_C0 + MODEL_C1 * model_active(k3, tau0, l_max)) * (1.0 + (r > 0. ? MODEL_RHO0 / r : 0.));
+}
+
+int song_host_pair_costs_model(int n_pairs, const int *k3_tr_size, const int64_t *tr_off, const double *k3_tr, const int *k3_pt_size,
+                               double tau0, int l_max, double rows_per_k, int n_groups, int64_t *cost)
+{
+  if (!k3_tr_size || !tr_off || !k3_tr || !k3_pt_size || !cost || n_pairs < 0 || n_groups < 1 || !(rows_per_k > 0.)) return 1;
+  int64_t n_win = 0;
+  double *rho = model_density(n_pairs, k3_tr_size, tr_off, k3_tr, NULL, rows_per_k, &n_win);
+  if (!rho) return 1;
+  /* a group of an n_groups-way split by interleaved chunks holds about 1/n_groups of the run's values at every k3 */
+  const double share = 1.0 / (double)n_groups;
+  for (int p = 0; p < n_pairs; ++p) {
+    const double *k = k3_tr + tr_off[p];
+    double c = MODEL_C_POINT * (double)k3_pt_size[p];
+    for (int i = 0; i < k3_tr_size[p]; ++i) c += model_unit_cost(k[i], tau0, l_max, rho, n_win, rows_per_k, share);
+    cost[p] = (int64_t)(c * 1024.0);
+    if (cost[p] < 1) cost[p] = 1;
+  }
+  free(rho);
+  return 0;
+}
+
+int song_host_band_edges(int n_pairs, const int *k3_tr_size, const int64_t *tr_off, const double *k3_tr, const int *k3_pt_size,
+                         const unsigned char *pair_in_group, double tau0, int l_max, double rows_per_k, int n_bands, double *edges)
+{
+  if (!k3_tr_size || !tr_off || !k3_tr || !k3_pt_size || n_pairs < 0 || n_bands < 1 || (n_bands > 1 && !edges) || !(rows_per_k > 0.)) return 1;
   if (n_bands == 1) return 0;
+  if (n_bands > 64) return 1;
   /* cost histogram over the k3 axis (linear bins: the fine grids are linear in k3), then the quantiles */
   enum { NBINS = 1 << 16 };
   double kmin = 0., kmax = 0.; int any = 0;
@@ -289,8 +351,10 @@ int song_host_band_edges(int n_pairs, const int *k3_tr_size, const int64_t *tr_o
     any = 1;
   }
   if (!any || !(kmax > kmin)) { for (int r = 0; r + 1 < n_bands; ++r) edges[r] = kmax; return 0; }
+  int64_t n_win = 0;
+  double *rho = model_density(n_pairs, k3_tr_size, tr_off, k3_tr, pair_in_group, rows_per_k, &n_win);
   double *hist = (double *)calloc(NBINS, sizeof(double));
-  if (!hist) return 1;
+  if (!hist || !rho) { free(hist); free(rho); return 1; }
   const double scale = (double)NBINS / (kmax - kmin);
   double total = 0.;
   for (int p = 0; p < n_pairs; ++p) {
@@ -300,16 +364,41 @@ int song_host_band_edges(int n_pairs, const int *k3_tr_size, const int64_t *tr_o
       int bin = (int)((k[i] - kmin) * scale);
       if (bin < 0) bin = 0;
       if (bin >= NBINS) bin = NBINS - 1;
-      const double c = band_unit_cost(k[i], tau0, l_max);
+      const double c = model_unit_cost(k[i], tau0, l_max, rho, n_win, rows_per_k, 1.0);
       hist[bin] += c; total += c;
     }
   }
-  double acc = 0.; int r = 0;
-  for (int bin = 0; bin < NBINS && r + 1 < n_bands; ++bin) {
-    acc += hist[bin];
-    while (r + 1 < n_bands && acc >= total * (double)(r + 1) / (double)n_bands) edges[r++] = kmin + (double)(bin + 1) / scale;
+  free(rho);
+  /* Every band should cost the same INCLUDING the coarse points of the pairs it touches, which depend on the edges: three
+     rounds of  edges from the targets -> points per band -> targets. */
+  double point_cost[64];
+  for (int r = 0; r < n_bands; ++r) point_cost[r] = 0.;
+  for (int round = 0; round < 3; ++round) {
+    double psum = 0.;
+    for (int r = 0; r < n_bands; ++r) psum += point_cost[r];
+    const double per_band = (total + psum) / (double)n_bands;
+    double target = 0., acc = 0.; int r = 0;
+    target = per_band - point_cost[0];
+    for (int bin = 0; bin < NBINS && r + 1 < n_bands; ++bin) {
+      acc += hist[bin];
+      while (r + 1 < n_bands && acc >= target) { edges[r++] = kmin + (double)(bin + 1) / scale; if (r < n_bands) target += per_band - point_cost[r]; }
+    }
+    for (; r + 1 < n_bands; ++r) edges[r] = kmax;
+    for (int b = 0; b < n_bands; ++b) point_cost[b] = 0.;
+    for (int p = 0; p < n_pairs; ++p) {
+      if ((pair_in_group && !pair_in_group[p]) || k3_tr_size[p] < 1) continue;
+      const double *k = k3_tr + tr_off[p];
+      const int n = k3_tr_size[p];
+      int lo_prev = 0;
+      for (int b = 0; b < n_bands; ++b) {
+        int lo = lo_prev, hi = n;
+        if (b + 1 < n_bands) { while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] < edges[b]) lo = mid + 1; else hi = mid; } }
+        else lo = n;
+        if (lo > lo_prev) point_cost[b] += MODEL_C_POINT * (double)k3_pt_size[p];       /* the band holds values of this pair */
+        lo_prev = lo;
+      }
+    }
   }
-  for (; r + 1 < n_bands; ++r) edges[r] = kmax;
   free(hist);
   return 0;
 }

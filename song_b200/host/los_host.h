@@ -75,13 +75,19 @@ int song_host_pair_costs(int n_pairs, const int *k3_tr_size, const double *k_min
    pair are needed by every band it crosses (the k3 spline is global in the pair).  n_dev GPUs = n_groups pair groups
    (song_host_schedule_pairs) x n_bands bands.
 
-   song_host_band_edges: the n_bands - 1 interior edges that split the cost of the given fine-grid values evenly;
-   cost of a value = 0.5 + 0.5 min(1, k3 tau0 / l_max) (measured, los_host.c).  pair_in_group: NULL = all pairs,
-   else only pairs with pair_in_group[p] != 0 are counted.
+   song_host_band_edges: the n_bands - 1 interior edges that split the predicted time of the selected pairs evenly over the
+   bands, under the measured cost model of los_host.c (a k3 value costs more where few values share a table row and where
+   many multipole columns are active; a coarse point costs its spline and its staging on every band its pair crosses).
+   rows_per_k = (tau0 - a mid-run tau) / xx_step converts k3 into rows of the projection table.  pair_in_group: NULL = all
+   pairs, else only pairs with pair_in_group[p] != 0 are counted.
+   song_host_pair_costs_model: the same model per pair, for the split of the pairs into n_groups groups
+   (song_host_schedule_pairs); units of 1/1024 microsecond.
    song_host_band_cuts: cut[p * (n_bands + 1) + r] = first fine-grid index of pair p with k3 >= edge[r]
    (cut[.. + 0] = 0, cut[.. + n_bands] = k3_tr_size[p]); grids are ascending (transfer2.c:1727). */
-int song_host_band_edges(int n_pairs, const int *k3_tr_size, const int64_t *tr_off, const double *k3_tr, const unsigned char *pair_in_group,
-                         double tau0, int l_max, int n_bands, double *edges);
+int song_host_band_edges(int n_pairs, const int *k3_tr_size, const int64_t *tr_off, const double *k3_tr, const int *k3_pt_size,
+                         const unsigned char *pair_in_group, double tau0, int l_max, double rows_per_k, int n_bands, double *edges);
+int song_host_pair_costs_model(int n_pairs, const int *k3_tr_size, const int64_t *tr_off, const double *k3_tr, const int *k3_pt_size,
+                               double tau0, int l_max, double rows_per_k, int n_groups, int64_t *cost);
 int song_host_band_cuts(int n_pairs, const int *k3_tr_size, const int64_t *tr_off, const double *k3_tr,
                         int n_bands, const double *edges, int *cut);
 /* how many k3 bands for n_dev GPUs: the smallest divisor of n_dev that keeps `dense_per_row` fine-grid values per row of

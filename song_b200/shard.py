@@ -65,25 +65,63 @@ def band_count(wl, n_dev: int, dense_per_row: int = DENSE_K3_PER_ROW) -> int:
     return int(_lib.host().song_host_band_count(int(wl.n_units), int(wl.xx.size), int(n_dev), int(dense_per_row)))
 
 
+def rows_per_k(wl) -> float:
+    """Rows of the projection table per unit of k3 at a mid-run time: x = k3 (tau0 - tau), row = x / xx_step."""
+    return float((wl.cosmo["tau0"] - float(np.median(wl.tau))) / wl.xx_step)
+
+
+# the cost model of los_host.c (microseconds): C_INTERP + (C0 + C1 a)(1 + RHO0 / rho) per k3 value, C_POINT per coarse point
+MODEL = dict(c_interp=0.0167, c0=0.070, c1=0.098, rho0=31.0, c_point=0.245, density_rows=50)
+
+
+def predicted_ms(wl, own, first, last) -> float:
+    """Time the model of los_host.c predicts for a GPU that computes the fine-grid slices [first, last) of pairs `own`
+    (numpy restatement of model_unit_cost / song_host_band_edges, used for reporting and by the tests)."""
+    own = np.asarray(own, dtype=np.int64)
+    if own.size == 0:
+        return 0.0
+    ks = np.concatenate([wl.k3_tr[int(wl.tr_off[ip]) + int(a):int(wl.tr_off[ip]) + int(b)] for ip, a, b in zip(own, first, last)])
+    win = (ks * rows_per_k(wl) / MODEL["density_rows"]).astype(np.int64)
+    rho = (np.bincount(win) / MODEL["density_rows"])[win]
+    act = np.minimum(1.0, ks * wl.cosmo["tau0"] / float(wl.layout.l.max()))
+    us = np.sum(MODEL["c_interp"] + (MODEL["c0"] + MODEL["c1"] * act) * (1.0 + MODEL["rho0"] / rho)) \
+        + MODEL["c_point"] * float(wl.k3_pt_size[own].sum())
+    return float(us) * 1e-3
+
+
+def pair_cost_model(wl, n_groups: int) -> np.ndarray:
+    """Predicted cost of every pair under the measured model of los_host.c (C: song_host_pair_costs_model), 1/1024 us."""
+    cost = np.zeros(wl.n_pairs, dtype=np.int64)
+    tr_off = np.ascontiguousarray(wl.tr_off, dtype=np.int64); nt = np.ascontiguousarray(wl.k3_tr_size, dtype=np.int32)
+    npt = np.ascontiguousarray(wl.k3_pt_size, dtype=np.int32)
+    if _lib.host().song_host_pair_costs_model(wl.n_pairs, _lib.iptr(nt), _lib.lptr(tr_off), _lib.dptr(wl.k3_tr), _lib.iptr(npt),
+                                              float(wl.cosmo["tau0"]), int(wl.layout.l.max()), rows_per_k(wl), int(n_groups), _lib.lptr(cost)):
+        raise _lib.SongLosError("song_host_pair_costs_model: bad arguments")
+    return cost
+
+
 def schedule_bands(wl, n_dev: int, n_bands: int | None = None, chunks_per_group: int | None = None):
     """The static schedule of a run on n_dev GPUs as n_groups pair groups x n_bands k3 bands (los_host.h).  Returns
-    (n_groups, n_bands, group_of_pair, cut) with cut[p, r]..cut[p, r+1] the fine-grid slice of pair p in band r; the
-    band edges are the cost quantiles of each group's own k3 values.  GPU d = group * n_bands + band."""
+    (n_groups, n_bands, group_of_pair, cut) with cut[p, r]..cut[p, r+1] the fine-grid slice of pair p in band r.  Pairs
+    and band edges are balanced under the measured cost model of los_host.c (k3 density, active multipole share, coarse
+    points touched); the edges are those of each group's own k3 values.  GPU d = group * n_bands + band."""
     n_bands = band_count(wl, n_dev) if n_bands is None else int(n_bands)
     assert n_dev % n_bands == 0, "the number of GPUs must be a multiple of the number of k3 bands"
     n_groups = n_dev // n_bands
-    cost = pair_cost(wl)
+    cost = pair_cost_model(wl, n_groups)
     chunks = chunks_per_group if chunks_per_group else (chunks_per_device(wl, n_groups) if n_groups > 1 else 1)
     group_of_pair, _ = schedule_pairs(cost, n_groups, chunks)
     cut = np.zeros((wl.n_pairs, n_bands + 1), dtype=np.int32)
     tr_off = np.ascontiguousarray(wl.tr_off, dtype=np.int64); nt = np.ascontiguousarray(wl.k3_tr_size, dtype=np.int32)
+    npt = np.ascontiguousarray(wl.k3_pt_size, dtype=np.int32)
     for g in range(n_groups):
         mask = np.ascontiguousarray(group_of_pair == g, dtype=np.uint8)
         edges = np.zeros(max(n_bands - 1, 1))
         cg = np.zeros_like(cut)
         h = _lib.host()
-        if h.song_host_band_edges(wl.n_pairs, _lib.iptr(nt), _lib.lptr(tr_off), _lib.dptr(wl.k3_tr), mask.ctypes.data_as(_lib.C.c_void_p),
-                                  float(wl.cosmo["tau0"]), int(wl.layout.l.max()), n_bands, _lib.dptr(edges)) or \
+        if h.song_host_band_edges(wl.n_pairs, _lib.iptr(nt), _lib.lptr(tr_off), _lib.dptr(wl.k3_tr), _lib.iptr(npt),
+                                  mask.ctypes.data_as(_lib.C.c_void_p), float(wl.cosmo["tau0"]), int(wl.layout.l.max()), rows_per_k(wl),
+                                  n_bands, _lib.dptr(edges)) or \
            h.song_host_band_cuts(wl.n_pairs, _lib.iptr(nt), _lib.lptr(tr_off), _lib.dptr(wl.k3_tr), n_bands, _lib.dptr(edges), _lib.iptr(cg)):
             raise _lib.SongLosError("song_host_band_edges / song_host_band_cuts: bad arguments")
         cut[mask != 0] = cg[mask != 0]
