@@ -312,7 +312,7 @@ def test_reference_spectra2_cls_equals_oracle(oracle, rescale):
 
 @needs_ref
 @pytest.mark.parametrize("name,n_k", [("sn_t_10percent_lmax2000", 6), ("sn_pol_10percent_lmax2000", 6),
-                                      ("sn_pol_5percent_lmax3000", 3), ("sn_pol_5percent_lmax4000", 3)])
+                                      ("sn_pol_5percent_lmax3000", 3), ("sn_pol_5percent_lmax4000", 2)])
 def test_reference_equals_oracle_on_baseline_triangles(oracle, name, n_k):
     """BASELINE.json configs[1]-[4] at their own parameters (l lists up to 4000, x grids of 17-53 thousand points, L up to
     17, 60-240 time samples): the reference's transfer2_init on the whole (k1,k2) triangle of n_k of the run's k values
