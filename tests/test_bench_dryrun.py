@@ -259,3 +259,18 @@ def test_reference_arm_times_the_reference_library(monkeypatch):
         assert c["kind"] == "reference" and c["probe_bitwise_equal_to_oracle"] is True
     else:
         assert c["kind"] == "port"
+
+
+def test_bench_cpu_baseline_leg_uses_the_reference_library(fake_gpu, monkeypatch):
+    """The cpu_baseline object of the main line: the reference's own transfer2.c (kind "reference") when oracle/_ref is
+    there.  The transfer2_init leg needs a GPU: the drop-in library is hidden for this run."""
+    import dropin_lib
+    if not os.path.exists(dropin_lib.REF_PATH):
+        pytest.skip("oracle/_ref/libsong_ref.so not built")
+    monkeypatch.setattr(dropin_lib, "PATH", os.path.join(ROOT, "song_b200", "no_such_library.so"))
+    line = run_bench(monkeypatch, ["--workload", "quick_song_run", "--steps", "1", "--warmup", "3", "--cpu-seconds", "0.5",
+                                   "--extra", "none", "--no-k3-integral", "--check-pairs", "2"])
+    c = line["cpu_baseline"]
+    assert c["kind"] == "reference" and c["probe_bitwise_equal_to_oracle"] is True and c["value"] > 0 and c["cores"] >= 1
+    assert "transfer2_init of the reference" in c["sample"]
+    assert line["e2e"]["value"] is None
