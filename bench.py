@@ -560,33 +560,36 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
         k3int = {"skipped": "the k3 integral of a pair needs its whole fine grid (trapezoidal weights of bispectra2.c:1279-1326); with k3 bands "
                             "a GPU holds slices -- run with --bands 1 for this leg"}
     elif args.k3_integral and rank == 0:
-        ht = b2.host_tables()
-        eng.set_bessel_table(ht["j_l1"], ht["x_min_l1"])
-        lay = sub.layout
-        index_l1 = {int(l1): i for i, l1 in enumerate(ht["l1"])}
-        c0 = sub.cosmo["tau0"] - sub.cosmo["tau_rec"]
-        r_size = {"sn_t_10percent_lmax2000": 75, "sn_pol_10percent_lmax2000": 75, "quick_song_run": 50}.get(name, 125)   # r_size of the .pre files
-        r_arr = np.linspace(c0 - 400.0, c0 + 250.0, r_size)
-        bases = ([lay.index_tt2_T] if lay.has_source_T else []) + ([lay.index_tt2_E] if lay.has_source_E else [])
-        tts = np.asarray([bs + int(lay.lm_array[il, 0]) for bs in bases for il in range(lay.l_size)])
-        rws = np.asarray([index_l1[int(l3)] for _ in bases for l3 in lay.l])
-        ms_k3 = 0.0; out_bytes = 0; ok_k3 = True; n_k3 = 0
-        for i, b in enumerate(batches):
-            eng.select_slot(i)
-            I = eng.integrate_k3(tts, rws, r_arr, b.n_pairs)            # [tt][r][pair] of this batch
-            ms_k3 += eng.k3_ms; out_bytes += I.nbytes; n_k3 += I.size
-            if i == 0:                                                    # bitwise against the oracle loop on the same T
-                T_dev = results[0].view(lay.tt2_size, b.n_units)
-                for q in (0, len(tts) // 2, len(tts) - 1):
-                    ref = O.integral_over_k3(b, T_dev[int(tts[q])].cpu().numpy(), ht["j_l1"][int(rws[q])], None, ht["x_min_l1"][int(rws[q])], r_arr)
-                    ok_k3 = ok_k3 and bool(np.array_equal(I[q], ref))
-            del I
-        k3int = {"kernel_ms": ms_k3, "integrals": int(n_k3), "r_size": int(r_size), "requests": int(tts.size),
-                 "k3_terms": int(sub.n_units) * int(tts.size) * int(r_size),
-                 "result_bytes": int(out_bytes), "transfer_bytes_replaced": int(n_int_rank * 8),
-                 "bitwise_equal_to_oracle": ok_k3,
-                 "api": "song_los_integrate_k3 on the resident result of every batch (bispectra2.c:1107-1439, bessel2.c:499-605); "
-                        "rank 0's shard; the result a consumer copies to the host shrinks from transfer_bytes_replaced to result_bytes"}
+        try:                                         # rank 0 alone is in here: an exception must not leave the other ranks in a collective
+            ht = b2.host_tables()
+            eng.set_bessel_table(ht["j_l1"], ht["x_min_l1"])
+            lay = sub.layout
+            index_l1 = {int(l1): i for i, l1 in enumerate(ht["l1"])}
+            c0 = sub.cosmo["tau0"] - sub.cosmo["tau_rec"]
+            r_size = {"sn_t_10percent_lmax2000": 75, "sn_pol_10percent_lmax2000": 75, "quick_song_run": 50}.get(name, 125)   # r_size of the .pre files
+            r_arr = np.linspace(c0 - 400.0, c0 + 250.0, r_size)
+            bases = ([lay.index_tt2_T] if lay.has_source_T else []) + ([lay.index_tt2_E] if lay.has_source_E else [])
+            tts = np.asarray([bs + int(lay.lm_array[il, 0]) for bs in bases for il in range(lay.l_size)])
+            rws = np.asarray([index_l1[int(l3)] for _ in bases for l3 in lay.l])
+            ms_k3 = 0.0; out_bytes = 0; ok_k3 = True; n_k3 = 0
+            for i, b in enumerate(batches):
+                eng.select_slot(i)
+                I = eng.integrate_k3(tts, rws, r_arr, b.n_pairs)            # [tt][r][pair] of this batch
+                ms_k3 += eng.k3_ms; out_bytes += I.nbytes; n_k3 += I.size
+                if i == 0:                                                    # bitwise against the oracle loop on the same T
+                    T_dev = results[0].view(lay.tt2_size, b.n_units)
+                    for q in (0, len(tts) // 2, len(tts) - 1):
+                        ref = O.integral_over_k3(b, T_dev[int(tts[q])].cpu().numpy(), ht["j_l1"][int(rws[q])], None, ht["x_min_l1"][int(rws[q])], r_arr)
+                        ok_k3 = ok_k3 and bool(np.array_equal(I[q], ref))
+                del I
+            k3int = {"kernel_ms": ms_k3, "integrals": int(n_k3), "r_size": int(r_size), "requests": int(tts.size),
+                     "k3_terms": int(sub.n_units) * int(tts.size) * int(r_size),
+                     "result_bytes": int(out_bytes), "transfer_bytes_replaced": int(n_int_rank * 8),
+                     "bitwise_equal_to_oracle": ok_k3,
+                     "api": "song_los_integrate_k3 on the resident result of every batch (bispectra2.c:1107-1439, bessel2.c:499-605); "
+                            "rank 0's shard; the result a consumer copies to the host shrinks from transfer_bytes_replaced to result_bytes"}
+        except Exception as exc:
+            k3int = {"error": str(exc)[:400]}
     # everything below works on the copies in `results`: release the engine's device memory before the gather buffers
     rank_batches = [int(b.n_units) for b in batches]
     eng.close()
@@ -687,7 +690,7 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
 
     # ---- e2e: SONG's transfer2_init on SONG structures, all N GPUs, host buffers in and out (rank 0 drives it) ----
     e2e = None
-    if want_e2e and rank == 0:
+    def run_e2e():
         try:                                         # transfer2_init drives every GPU of the box from one process: all host cores
             os.sched_setaffinity(0, range(os.cpu_count() or 1))
         except Exception:
@@ -748,13 +751,25 @@ def measure_workload(name: str, args, D: Dist, steps: int, warmup: int, e2e_step
                "first_call_ms": first_ms, "first_call_note": "includes page-locking the staging and the ptr2->transfer slabs (kept in a pool afterwards)",
                "bessel2_init_s": t_b2, "result_read_ms_per_step": t_read / e2e_steps * 1e3, "checksum_abs_sum": cs,
                "count_memorised_transfers": count, "labels_ok": labels_ok, "parity": e2e_parity, "clocks_gpu0_1s_period": e2e_clocks}
+        return e2e
+
+    if want_e2e and rank == 0:
+        try:                                         # rank 0 alone is in here: an exception must not leave the other ranks in a barrier
+            e2e = run_e2e()
+        except Exception as exc:
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "unavailable": "transfer2_init leg failed: " + str(exc)[:400]}
+            set_omp_threads(max(1, (os.cpu_count() or 1) // world))
     D.cpu_barrier()
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None
     lib_run = None
     if rank == 0 and with_cpu and args.max_pairs is None:
-        lib_run = time_reference_library(name, args.cpu_seconds, 1, 0)       # the reference's own transfer2.c when oracle/_ref is there
+        try:
+            lib_run = time_reference_library(name, args.cpu_seconds, 1, 0)   # the reference's own transfer2.c when oracle/_ref is there
+        except Exception as exc:                     # falls back to the oracle port below
+            sys.stderr.write(f"bench.py: the reference library could not be timed ({str(exc)[:200]}); using the oracle port\n")
     if lib_run is not None:
         cpu = {"value": lib_run["value"], "unit": UNIT, "cores": lib_run["cores"], "cpu_model": cpu_model(), "kind": "reference",
                "sample": f"transfer2_init of the reference's own source/transfer2.c (oracle/_ref/libsong_ref.so) on the whole (k1,k2) triangle of "
@@ -858,8 +873,8 @@ def main():
                            "gather": r["gather"], "imbalance_max_over_mean": r["imbalance_max_over_mean"],
                            "roofline": {k: r["roofline"][k] for k in ("achieved", "peak", "unit", "frac", "step_frac", "kernel_ms_per_step",
                                                                       "kernel_share_of_step", "resident_batches", "frac_per_rank")},
-                           "e2e": None if r["e2e"] is None else {k: r["e2e"][k] for k in ("value", "ms_per_step", "ms_each_step", "steps", "first_call_ms", "parity",
-                                                                                          "h2d_bytes_per_step", "d2h_bytes_per_step")}})
+                           "e2e": None if r["e2e"] is None else {k: r["e2e"].get(k) for k in ("value", "ms_per_step", "ms_each_step", "steps", "first_call_ms", "parity",
+                                                                                              "h2d_bytes_per_step", "d2h_bytes_per_step", "unavailable")}})
 
     if rank == 0:
         r = main_res
