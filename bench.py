@@ -20,10 +20,13 @@ separately) and spot-checked against the CPU oracle in the reference pair order.
            in pageable host memory (ppt2->sources) and the result in ptr2->transfer: packing, H2D, kernels, D2H all
            inside the timed region, on all N GPUs of the box (one host thread per GPU inside the module).
 `configs`: the other single-GPU BASELINE configurations measured the same way with fewer steps (N=1), and
-           configs[4] (sn_pol_5percent_lmax4000) split over the ranks when N=8.
-`--impl reference` : the CPU restatement of the reference's transfer2 loops (oracle/, OpenMP on all
-           host threads) on a bounded sample of the same workload.  The reference itself cannot be
-           built here (its CLASS fork is an empty submodule), so kind = "port".
+           configs[4] (sn_pol_5percent_lmax4000) split over the ranks when N=8.  These legs run after the main workload is
+           measured and under a deadline (--extra-deadline): a leg that would start late is skipped, one that is still
+           running at the deadline is abandoned, and the main line goes out either way with a note in `configs`.
+`--impl reference` : the reference's own source/transfer2.c, compiled where it lies into oracle/_ref/libsong_ref.so
+           (oracle/Makefile target `ref`; stand-ins only for its absent CLASS fork), run through its module API
+           transfer2_init on SONG structures with all host threads, on a bounded sample of the same workload
+           (kind = "reference"); where that library is absent, the CPU restatement of the same loops (oracle/, kind = "port").
 """
 from __future__ import annotations
 
@@ -38,6 +41,7 @@ import time
 
 import numpy as np
 
+T_PROCESS_START = time.time()                      # the deadline of the `configs` legs counts from here (see --extra-deadline)
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
@@ -822,6 +826,10 @@ def main():
     ap.add_argument("--dropin-verbose", type=int, default=0, help="debug: ptr2->transfer2_verbose of the last timed transfer2_init")
     ap.add_argument("--extra", default="auto", help="comma list of further workloads for the `configs` array; auto: the other "
                                                   "single-GPU BASELINE configs at N=1, configs[4] at N=8; none: skip")
+    ap.add_argument("--extra-deadline", type=float, default=600.0,
+                    help="seconds after the start of the process by which the `configs` legs must be over: no further workload is started "
+                         "in the last quarter of it, and one still running at the deadline is abandoned -- the main line, measured before, "
+                         "goes out with a note in `configs` (0: no deadline)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -862,25 +870,19 @@ def main():
         names = []
     else:
         names = [n for n in args.extra.split(",") if n]
-    for n in names:
-        big = n.startswith("sn_pol_5percent")
-        try:
-            r = measure_workload(n, args, D, steps=3 if big else 5, warmup=3, e2e_steps=0 if n == "sn_pol_5percent_lmax4000" else 3,
-                                 with_cpu=False)
-        except RuntimeError as exc:                  # raised on every rank alike (see measure_workload): the main line still goes out
-            if rank == 0:
-                extras.append({"workload": n, "error": str(exc)[:300]})
-            continue
-        if rank == 0:
-            extras.append({"workload": n, "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "steps": r["steps"],
-                           "n_gpus": world, "integrals": r["describe"]["integrals"], "parity": r["parity"],
-                           "gather": r["gather"], "imbalance_max_over_mean": r["imbalance_max_over_mean"],
-                           "roofline": {k: r["roofline"][k] for k in ("achieved", "peak", "unit", "frac", "step_frac", "kernel_ms_per_step",
-                                                                      "kernel_share_of_step", "resident_batches", "frac_per_rank")},
-                           "e2e": None if r["e2e"] is None else {k: r["e2e"].get(k) for k in ("value", "ms_per_step", "ms_each_step", "steps", "first_call_ms", "parity",
-                                                                                              "h2d_bytes_per_step", "d2h_bytes_per_step", "unavailable")}})
+    # The main workload is measured; the `configs` legs that follow must not be able to lose it.  A leg is not started in the
+    # last quarter of --extra-deadline, and a watchdog on every rank abandons one that is still running at the deadline
+    # (rank 0 prints the line first): a slow host or a stuck leg costs that leg, not the run.
+    emitted = threading.Lock()
+    state = {"current": None}
+    has_deadline = args.extra_deadline > 0
 
-    if rank == 0:
+    def emit_line():
+        """The one JSON line of the run, once (rank 0): the main workload and whatever `configs` legs are complete."""
+        if not emitted.acquire(blocking=False):
+            return
+        if rank != 0:
+            return
         r = main_res
         line = {
             "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -888,7 +890,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": dict(r["describe"], workload=args.workload, mode=args.mode,
                            parallelism=f"ONE workload over {world} GPU(s) = {r['n_groups']} (k1,k2)-pair group(s) x {r['n_bands']} k3 band(s): pairs by "
-                                       f"song_host_schedule_pairs ({r['chunks_per_gpu']} contiguous chunk(s) per group, LPT, cost = k3 values x active multipole share), "
+                                       f"song_host_schedule_pairs ({r['chunks_per_gpu']} contiguous chunk(s) per group, LPT under the cost model of los_host.c: "
+                                       f"k3 density per projection-table row, active multipole share, coarse points touched), "
                                        f"bands = cost quantiles of a group's fine k3 values (song_host_band_edges; a band keeps the k3 density per "
                                        f"projection-table row, the coarse sources of a pair are resident on every band it crosses: x{r['source_replication']:.2f}); "
                                        f"no data-path collective; results gathered on rank 0",
@@ -906,12 +909,56 @@ def main():
             "roofline": r["roofline"],
             "cpu_baseline": r["cpu_baseline"],
             "k3_integral": r["k3_integral"],
-            "configs": extras,
+            "configs": list(extras),
         }
         if r["gather"] is not None:
             line["nccl_gather"] = r["gather"]
             line["nccl_gather_ms"] = r["gather"]["ms"]
         print(json.dumps(line), flush=True)
+
+    def watchdog():
+        while has_deadline and state["current"] is not None:
+            if time.time() >= T_PROCESS_START + args.extra_deadline + (0.0 if rank == 0 else 3.0):   # rank 0 prints before the others leave
+                extras.append({"workload": state["current"],
+                               "error": f"leg abandoned: still running {args.extra_deadline:.0f} s after the start of the process (--extra-deadline)"})
+                emit_line()
+                sys.stdout.flush()
+                os._exit(0)                          # every rank leaves at its own copy of the deadline; nothing of the main line is pending
+            time.sleep(0.5)
+
+    for n in names:
+        start_leg = 1.0
+        if has_deadline:
+            start_leg = 0.0 if time.time() > T_PROCESS_START + 0.75 * args.extra_deadline else 1.0
+            start_leg = D.reduce(start_leg, "min")   # decided together: no rank may enter a leg the others skip
+        if start_leg < 0.5:
+            if rank == 0:
+                extras.append({"workload": n, "skipped": f"not started: more than {0.75 * args.extra_deadline:.0f} s of the {args.extra_deadline:.0f} s "
+                                                         "of --extra-deadline were used when its turn came"})
+            continue
+        big = n.startswith("sn_pol_5percent")
+        state["current"] = n
+        dog = threading.Thread(target=watchdog, daemon=True)
+        dog.start()
+        try:
+            r = measure_workload(n, args, D, steps=3 if big else 5, warmup=3, e2e_steps=0 if n == "sn_pol_5percent_lmax4000" else 3,
+                                 with_cpu=False)
+        except RuntimeError as exc:                  # raised on every rank alike (see measure_workload): the main line still goes out
+            state["current"] = None
+            if rank == 0:
+                extras.append({"workload": n, "error": str(exc)[:300]})
+            continue
+        state["current"] = None
+        if rank == 0:
+            extras.append({"workload": n, "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "steps": r["steps"],
+                           "n_gpus": world, "integrals": r["describe"]["integrals"], "parity": r["parity"],
+                           "gather": r["gather"], "imbalance_max_over_mean": r["imbalance_max_over_mean"],
+                           "roofline": {k: r["roofline"][k] for k in ("achieved", "peak", "unit", "frac", "step_frac", "kernel_ms_per_step",
+                                                                      "kernel_share_of_step", "resident_batches", "frac_per_rank")},
+                           "e2e": None if r["e2e"] is None else {k: r["e2e"].get(k) for k in ("value", "ms_per_step", "ms_each_step", "steps", "first_call_ms", "parity",
+                                                                                              "h2d_bytes_per_step", "d2h_bytes_per_step", "unavailable")}})
+
+    emit_line()
     D.close()
 
 

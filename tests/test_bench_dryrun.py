@@ -274,3 +274,42 @@ def test_bench_cpu_baseline_leg_uses_the_reference_library(fake_gpu, monkeypatch
     assert c["kind"] == "reference" and c["probe_bitwise_equal_to_oracle"] is True and c["value"] > 0 and c["cores"] >= 1
     assert "transfer2_init of the reference" in c["sample"]
     assert line["e2e"]["value"] is None
+
+
+def test_bench_skips_a_configs_leg_that_would_start_late(fake_gpu, monkeypatch):
+    """--extra-deadline: the `configs` legs cannot cost the main line.  With (almost) no time left the leg is not started."""
+    line = run_bench(monkeypatch, ["--workload", "quick_song_run", "--max-pairs", "20", "--steps", "1", "--warmup", "3", "--no-cpu-baseline",
+                                   "--no-k3-integral", "--check-pairs", "2", "--extra", "quick_song_run", "--extra-deadline", "0.001"])
+    assert line["value"] > 0 and line["parity"]["ok"]
+    assert line["configs"] == [{"workload": "quick_song_run", "skipped": line["configs"][0]["skipped"]}]
+    assert "not started" in line["configs"][0]["skipped"]
+
+
+def test_bench_abandons_a_configs_leg_at_the_deadline(fake_gpu, monkeypatch):
+    """A `configs` leg still running at the deadline: the watchdog prints the main line (measured before) with a note and
+    leaves.  os._exit is replaced by a flag here, and the stuck leg is a sleep."""
+    import importlib
+    import time
+    import bench
+    importlib.reload(bench)
+    real = bench.measure_workload
+    calls, exits = [], []
+
+    def measure(name, args, D, steps, warmup, e2e_steps, with_cpu, sampler=None):
+        calls.append(name)
+        if len(calls) == 1:
+            return real(name, args, D, steps, warmup, e2e_steps, with_cpu, sampler=sampler)
+        bench.T_PROCESS_START = time.time() - 10000.0          # the deadline is long past while this leg "runs"
+        t0 = time.time()
+        while not exits and time.time() - t0 < 20:
+            time.sleep(0.1)
+        raise RuntimeError("the process would be gone by now")
+    monkeypatch.setattr(bench, "measure_workload", measure)
+    monkeypatch.setattr(bench.os, "_exit", lambda code: exits.append(code))
+    monkeypatch.setattr(importlib, "reload", lambda m: m)         # run_bench reloads bench: keep the patched module
+    line = run_bench(monkeypatch, ["--workload", "quick_song_run", "--max-pairs", "20", "--steps", "1", "--warmup", "3", "--no-cpu-baseline",
+                                   "--no-k3-integral", "--check-pairs", "2", "--extra", "sn_t_10percent_lmax2000", "--extra-deadline", "5000"])
+    assert exits == [0] and calls == ["quick_song_run", "sn_t_10percent_lmax2000"]
+    assert line["value"] > 0 and line["parity"]["ok"]
+    assert len(line["configs"]) == 1 and line["configs"][0]["workload"] == "sn_t_10percent_lmax2000"
+    assert "abandoned" in line["configs"][0]["error"]
