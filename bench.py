@@ -226,7 +226,30 @@ def reference_triangle(name: str, n_k: int, max_pairs=None):
     return workload.build_grids(dict(p, k=k_full[idx]), max_pairs=max_pairs), int(k_full.size)
 
 
+class c_stdout_to_stderr:
+    """The reference prints to the C stdout (e.g. its warning about fewer than 4 k values, transfer2.c:120-123); the one JSON
+    line of this script must stay alone there: file descriptor 1 points to stderr while the library runs."""
+
+    def __enter__(self):
+        import ctypes
+        self.libc = ctypes.CDLL(None)
+        sys.stdout.flush(); self.libc.fflush(None)
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        self.libc.fflush(None)
+        os.dup2(self.saved, 1); os.close(self.saved)
+        return False
+
+
 def time_reference_library(name: str, target_seconds: float, steps: int, warmup: int):
+    with c_stdout_to_stderr():
+        return _time_reference_library(name, target_seconds, steps, warmup)
+
+
+def _time_reference_library(name: str, target_seconds: float, steps: int, warmup: int):
     """oracle/_ref/libsong_ref.so -- the reference's own source/transfer2.c, compiled where it lies (oracle/Makefile) --
     timed on a bounded sample of workload `name`: transfer2_init on SONG structures, all host threads (the reference
     parallelises the k3 loop of every pair with OpenMP, transfer2.c:450).  Returns None when the library is not there."""
@@ -248,7 +271,7 @@ def time_reference_library(name: str, target_seconds: float, steps: int, warmup:
     from song_b200 import configs
     full_integrals = workload.build_grids(configs.get(name)).n_integrals
     rate = probe.n_integrals / max(dt, 1e-9)
-    n_k = int(max(4, min(k_size, round(k_size * (target_seconds * rate / full_integrals) ** 0.5))))
+    n_k = int(max(2, min(k_size, round(k_size * (target_seconds * rate / full_integrals) ** 0.5))))   # 2 values = 3 pairs at least
     sub, _ = reference_triangle(name, n_k)
     workload.fill_sources(sub)
     each = []
@@ -274,7 +297,9 @@ def run_reference(args, rank: int, world: int):
     from song_b200 import configs, workload
     set_omp_threads(os.cpu_count() or 1)
     try:
-        lib_run = time_reference_library(args.workload, args.cpu_seconds, max(args.steps, 1), args.warmup)
+        # a step is a bounded sample: about --cpu-seconds of host time, less when K + W calls would not end within a few minutes
+        per_step = max(1.0, min(args.cpu_seconds, 240.0 / max(args.steps + args.warmup, 1)))
+        lib_run = time_reference_library(args.workload, per_step, max(args.steps, 1), args.warmup)
     except Exception as exc:                         # the oracle port below is always there
         sys.stderr.write(f"bench.py: the reference library could not be timed ({str(exc)[:200]}); using the oracle port\n")
         lib_run = None
