@@ -13,6 +13,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """GPU tests against the reference's own output (golden fixtures, oracle/_ref) run after the GPU-vs-oracle parity tests
+    they build on: under `-x` a failure there must not hide the results of the parity suite."""
+    late = {"test_golden.py", "test_reference_pin.py"}
+    items.sort(key=lambda it: 1 if (it.get_closest_marker("gpu") is not None and os.path.basename(str(it.fspath)) in late) else 0)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     import oracle_lib
