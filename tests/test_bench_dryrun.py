@@ -187,7 +187,7 @@ def test_bench_refuses_to_run_without_a_gpu(monkeypatch):
 
 
 # ---- two ranks (gloo): pair groups x k3 bands, gather and the parity of the gathered array ----
-def _two_rank_worker(rank, world, port, bands, out_dir):
+def _two_rank_worker(rank, world, port, bands, out_dir, extra="none"):
     import torch
     import torch.distributed as dist
     sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
@@ -216,7 +216,7 @@ def _two_rank_worker(rank, world, port, bands, out_dir):
         self.cpu_group = dist.new_group(backend="gloo")
     bench.Dist.__init__ = gloo_init
     sys.argv = ["bench.py", "--gpus", str(world), "--workload", "quick_song_run", "--max-pairs", "60", "--steps", "2", "--warmup", "3",
-                "--bands", str(bands), "--extra", "none", "--no-cpu-baseline"]
+                "--bands", str(bands), "--extra", extra, "--no-cpu-baseline"]
     buf = io.StringIO()
     with redirect_stdout(buf):
         bench.main()
@@ -243,6 +243,18 @@ def test_bench_line_several_ranks_gloo(tmp_path, world, bands):
     assert sum(line["roofline"]["per_rank"]["k3_values"]) == line["config"]["k3_units"]      # every k3 value on exactly one GPU
     if bands > 1:
         assert "skipped" in line["k3_integral"]
+
+
+def test_bench_configs_leg_on_several_ranks_gloo(tmp_path):
+    """The `configs` legs of a multi-rank run: every rank takes the start / skip decision of a leg together (a collective)
+    and runs it under its own watchdog; rank 0 alone prints the line, with the leg in `configs`."""
+    import torch.multiprocessing as mp
+    port = 29990 + (os.getpid() % 7)
+    mp.spawn(_two_rank_worker, args=(2, port, 1, str(tmp_path), "quick_song_run"), nprocs=2, join=True)
+    line = json.loads(open(tmp_path / "line.json").read())
+    assert line["n_gpus"] == 2 and line["parity"]["ok"]
+    assert len(line["configs"]) == 1 and line["configs"][0]["workload"] == "quick_song_run"
+    assert line["configs"][0]["n_gpus"] == 2 and line["configs"][0]["parity"]["ok"] and line["configs"][0]["gather"] is not None
 
 
 def test_reference_arm_times_the_reference_library(monkeypatch):
