@@ -941,16 +941,24 @@ def main():
             line["nccl_gather_ms"] = r["gather"]["ms"]
         print(json.dumps(line), flush=True)
 
+    legs_done = threading.Event()
+
     def watchdog():
-        while has_deadline and state["current"] is not None:
+        """One per process, from the first `configs` leg to the end of the run: whatever a rank is stuck in at the deadline --
+        a leg, or a collective the others never entered because a leg failed on one rank only -- it leaves with status 0,
+        rank 0 after printing the line."""
+        while not legs_done.wait(0.5):
             if time.time() >= T_PROCESS_START + args.extra_deadline + (0.0 if rank == 0 else 3.0):   # rank 0 prints before the others leave
-                extras.append({"workload": state["current"],
-                               "error": f"leg abandoned: still running {args.extra_deadline:.0f} s after the start of the process (--extra-deadline)"})
+                if state["current"] is not None:
+                    extras.append({"workload": state["current"],
+                                   "error": f"leg abandoned: still running {args.extra_deadline:.0f} s after the start of the process (--extra-deadline)"})
                 emit_line()
                 sys.stdout.flush()
                 os._exit(0)                          # every rank leaves at its own copy of the deadline; nothing of the main line is pending
-            time.sleep(0.5)
+                return
 
+    if names and has_deadline:
+        threading.Thread(target=watchdog, daemon=True).start()
     for n in names:
         start_leg = 1.0
         if has_deadline:
@@ -963,8 +971,6 @@ def main():
             continue
         big = n.startswith("sn_pol_5percent")
         state["current"] = n
-        dog = threading.Thread(target=watchdog, daemon=True)
-        dog.start()
         try:
             r = measure_workload(n, args, D, steps=3 if big else 5, warmup=3, e2e_steps=0 if n == "sn_pol_5percent_lmax4000" else 3,
                                  with_cpu=False)
@@ -983,8 +989,15 @@ def main():
                            "e2e": None if r["e2e"] is None else {k: r["e2e"].get(k) for k in ("value", "ms_per_step", "ms_each_step", "steps", "first_call_ms", "parity",
                                                                                               "h2d_bytes_per_step", "d2h_bytes_per_step", "unavailable")}})
 
+    state["current"] = None
     emit_line()
-    D.close()
+    sys.stdout.flush()
+    closer = threading.Thread(target=D.close, daemon=True)     # the line is out: a process group that does not shut down cleanly
+    closer.start()                                             # (a rank that left a leg early) must not keep the run alive
+    closer.join(60.0)
+    legs_done.set()
+    if closer.is_alive():
+        os._exit(0)
 
 
 if __name__ == "__main__":
