@@ -851,7 +851,7 @@ def main():
     ap.add_argument("--dropin-verbose", type=int, default=0, help="debug: ptr2->transfer2_verbose of the last timed transfer2_init")
     ap.add_argument("--extra", default="auto", help="comma list of further workloads for the `configs` array; auto: the other "
                                                   "single-GPU BASELINE configs at N=1, configs[4] at N=8; none: skip")
-    ap.add_argument("--extra-deadline", type=float, default=600.0,
+    ap.add_argument("--extra-deadline", type=float, default=660.0,
                     help="seconds after the start of the process by which the `configs` legs must be over: no further workload is started "
                          "in the last quarter of it, and one still running at the deadline is abandoned -- the main line, measured before, "
                          "goes out with a note in `configs` (0: no deadline)")
