@@ -91,6 +91,26 @@ def test_band_schedule_properties():
         assert cost.max() / cost.mean() < 1.06, (n_dev, nb, cost)    # and so do the groups, up to their density difference
 
 
+@pytest.mark.parametrize("name,n_dev,expect", [("sn_pol_5percent_lmax3000", 2, (2, 1)), ("sn_pol_5percent_lmax3000", 4, (2, 2)),
+                                               ("sn_pol_5percent_lmax3000", 8, (2, 4)), ("sn_pol_5percent_lmax4000", 8, (2, 4))])
+def test_default_schedules_of_the_scaling_runs(name, n_dev, expect):
+    """The schedules `bench.py --gpus N` runs by default (configs[3] at N = 2, 4, 8; configs[4] at N = 8), at full size:
+    groups x bands as DESIGN.md states, every fine-grid value on exactly one GPU, no idle GPU, predicted times balanced."""
+    wl = workload.build_grids(configs.get(name))
+    sched = shard.schedule_bands(wl, n_dev)
+    assert (sched[0], sched[1]) == expect
+    seen = np.zeros(wl.n_units, dtype=np.int8)
+    ms = []
+    for rank in range(n_dev):
+        own, first, last = shard.shard_units_index(wl, rank, n_dev, sched)
+        assert own.size > 0 and int(np.sum(np.asarray(last) - np.asarray(first))) > 0
+        for ip, a, b in zip(own, first, last):
+            seen[int(wl.tr_off[ip]) + int(a):int(wl.tr_off[ip]) + int(b)] += 1
+        ms.append(shard.predicted_ms(wl, own, first, last))
+    assert np.all(seen == 1)
+    assert max(ms) / (sum(ms) / len(ms)) < 1.04, ms
+
+
 def test_select_units_metadata():
     """Slices of fine grids: whole coarse grids and sources, cut fine grids, physical range relative to the slice and the
     k3 of the first / last physical point carried along (include/song_los.h, song_los_batch)."""
