@@ -992,8 +992,11 @@ def main():
     state["current"] = None
     emit_line()
     sys.stdout.flush()
-    closer = threading.Thread(target=D.close, daemon=True)     # the line is out: a process group that does not shut down cleanly
-    closer.start()                                             # (a rank that left a leg early) must not keep the run alive
+    def close_group():
+        torch.cuda.set_device(local_rank)                      # the current device is per thread
+        D.close()
+    closer = threading.Thread(target=close_group, daemon=True)  # the line is out: a process group that does not shut down cleanly
+    closer.start()                                              # (a rank that left a leg early) must not keep the run alive
     closer.join(60.0)
     legs_done.set()
     if closer.is_alive():
