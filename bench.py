@@ -992,15 +992,8 @@ def main():
     state["current"] = None
     emit_line()
     sys.stdout.flush()
-    def close_group():
-        torch.cuda.set_device(local_rank)                      # the current device is per thread
-        D.close()
-    closer = threading.Thread(target=close_group, daemon=True)  # the line is out: a process group that does not shut down cleanly
-    closer.start()                                              # (a rank that left a leg early) must not keep the run alive
-    closer.join(60.0)
-    legs_done.set()
-    if closer.is_alive():
-        os._exit(0)
+    D.close()                                      # the watchdog, if any, still bounds this: a process group that cannot shut down
+    legs_done.set()                                # cleanly (a rank that left a leg early) ends at the deadline, the line being out
 
 
 if __name__ == "__main__":
